@@ -1,0 +1,135 @@
+/*
+ * b200sa.h -- C ABI of the B200-native suffix-array / BWT / FM-index engine.
+ *
+ * This is the drop-in boundary for the hot path of mailund/stralg: the functions a binding of
+ * stralg's suffix_array.h / bwt.h would call (reference file:line cited per entry point; paths
+ * are relative to the stralg checkout).  Plain pointers and sizes only, no CUDA or torch types.
+ * The reference-named shims (sa_is_construction, compute_lcp, init_bwt_table,
+ * init_bwt_exact_match_iter, ...) live in include/stralg_compat/ and are implemented on top of
+ * this header by libstralg_b200.so.
+ *
+ * Conventions (stralg README.md:106-134, stralg/error.h:7-21): an `enum b200sa_error *err`
+ * out-parameter is the LAST argument, 0 means success, it is written on every call and may be
+ * NULL.  Functions returning int return the same code.  b200sa_last_error() gives a
+ * thread-local message.  There is no CPU fallback: without a CUDA device every call fails with
+ * B200SA_ERR_CUDA.
+ *
+ * Texts are "remapped codes" (stralg/remap.c:73-114): n bytes in 1..sigma-1; the sentinel 0 is
+ * implicit (text[n] is never read).  All tables have len = n + 1 entries/rows because the
+ * sentinel suffix is a real suffix (stralg/suffix_array_internal.c:7-19); n <= 2^32 - 2.
+ */
+#ifndef B200SA_H
+#define B200SA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200sa_index b200sa_index;
+
+enum b200sa_error {
+    B200SA_OK = 0,
+    B200SA_ERR_CUDA = 1,          /* CUDA runtime failure or no device */
+    B200SA_ERR_BAD_ARGUMENT = 2,
+    B200SA_ERR_BAD_SYMBOL = 3,    /* text holds a code 0 or >= sigma (remap.c:80-84 returns NULL) */
+    B200SA_ERR_TOO_LARGE = 4,     /* n > 2^32 - 2, or a dense table that cannot be indexed in u32 */
+    B200SA_ERR_NOT_BUILT = 5,     /* table was not requested at build time */
+    B200SA_ERR_OUT_OF_MEMORY = 6,
+    B200SA_ERR_INTERNAL = 7
+};
+
+/* build flags */
+#define B200SA_BUILD_ISA 0x1u        /* keep the inverse suffix array   (suffix_array.c:55-62)  */
+#define B200SA_BUILD_LCP 0x2u        /* LCP array                       (suffix_array.c:64-85)  */
+#define B200SA_BUILD_BWT 0x4u        /* keep the BWT rows               (bwt.c:13-20)           */
+#define B200SA_BUILD_OCC 0x8u        /* C table + sampled O table       (bwt.c:35-65)           */
+#define B200SA_TEXT_ON_DEVICE 0x100u /* `codes` is a device pointer (borrowed during the call)  */
+#define B200SA_PROFILE 0x200u        /* record per-stage device times (b200sa_profile)          */
+#define B200SA_DROP_SA 0x400u        /* release the suffix array after the tables are built     */
+
+struct b200sa_stats {
+    uint32_t length;       /* n + 1 */
+    uint32_t sigma;
+    uint32_t primary;      /* row r with SA[r] == 0 (BWT row holding the sentinel) */
+    uint32_t rounds;       /* prefix-doubling rounds after the initial sort */
+    uint32_t k0;           /* symbols packed into the initial sort key */
+    uint32_t radix_bits;
+    uint32_t passes0;      /* radix passes of the initial sort */
+    uint32_t occ_layout;   /* 1 = 32-byte DNA blocks, 2 = byte blocks */
+    uint64_t sorted_total; /* elements sorted, summed over rounds */
+    uint64_t passes_elems; /* elements moved, summed over all radix passes */
+    uint64_t occ_bytes;
+};
+
+/* ---- construction ------------------------------------------------------------------------
+ * Replaces sa_is_construction / sa_is_mem_construction / skew_sa_construction /
+ * qsort_sa_construction (suffix_array.h:22-41), compute_inverse / compute_lcp
+ * (suffix_array.h:96-101) and init_bwt_table (bwt.h:73-76) in one call.
+ * `stream` is a cudaStream_t (NULL = default stream).  */
+b200sa_index *b200sa_build(const uint8_t *codes, uint64_t n, uint32_t sigma, uint32_t flags,
+                           int device, void *stream, enum b200sa_error *err);
+void b200sa_free(b200sa_index *idx);
+const char *b200sa_last_error(void);
+
+int b200sa_stats(const b200sa_index *idx, struct b200sa_stats *out);
+/* per-stage device times of the last build (needs B200SA_PROFILE): fills up to `cap` entries,
+ * returns the number of stages.  bytes[] = algorithmic bytes of the stage (SURVEY 8d model). */
+int b200sa_profile(const b200sa_index *idx, const char **names, float *ms, double *bytes, int cap);
+
+/* ---- device-resident views (valid until b200sa_free) --------------------------------------- */
+const uint32_t *b200sa_device_sa(const b200sa_index *idx);   /* struct suffix_array.array   */
+const uint32_t *b200sa_device_isa(const b200sa_index *idx);  /* .inverse                    */
+const uint32_t *b200sa_device_lcp(const b200sa_index *idx);  /* .lcp                        */
+const uint8_t *b200sa_device_bwt(const b200sa_index *idx);
+const uint8_t *b200sa_device_occ(const b200sa_index *idx);
+
+/* ---- copies into caller-owned HOST memory (len entries each) ------------------------------- */
+int b200sa_copy_sa(const b200sa_index *idx, uint32_t *host);
+int b200sa_copy_isa(const b200sa_index *idx, uint32_t *host);
+int b200sa_copy_lcp(const b200sa_index *idx, uint32_t *host);
+int b200sa_copy_bwt(const b200sa_index *idx, uint8_t *host);
+int b200sa_copy_c_table(const b200sa_index *idx, uint32_t *host /* sigma entries */);
+/* Dense O table in the reference layout o[i * sigma + a], i in [0, len] (bwt.c:47-65).
+ * Fails with B200SA_ERR_TOO_LARGE where the reference's own u32 size computation overflows. */
+int b200sa_copy_o_dense(const b200sa_index *idx, uint32_t *host /* (len + 1) * sigma */);
+/* O(a[q], i[q]) for q < count (the O(a,i) macro of bwt.h:48-50); host buffers. */
+int b200sa_occ(const b200sa_index *idx, const uint8_t *a, const uint32_t *i, uint64_t count,
+               uint32_t *out);
+
+/* ---- batched exact search (init_bwt_exact_match_iter, bwt.c:164-199) -----------------------
+ * Patterns are remapped codes, concatenated; pattern p is patterns[offsets[p] .. offsets[p+1]).
+ * With offsets == NULL every pattern has fixed_len symbols.  Results: half-open SA intervals
+ * [L[p], R[p]); L >= R means no match.  Host-buffer and device-buffer variants. */
+int b200sa_search_batch(const b200sa_index *idx, const uint8_t *patterns, const uint64_t *offsets,
+                        uint32_t fixed_len, uint64_t npat, uint32_t *L, uint32_t *R);
+int b200sa_search_device(const b200sa_index *idx, const uint8_t *d_patterns,
+                         const uint64_t *d_offsets, uint32_t fixed_len, uint64_t npat,
+                         uint32_t *d_L, uint32_t *d_R, void *stream);
+
+/* ---- locate (next_bwt_exact_match_iter, bwt.c:201-217) -------------------------------------
+ * pos_off[npat + 1] receives a CSR; positions of pattern p are pos[pos_off[p] .. pos_off[p+1]),
+ * in suffix-array order like the reference iterator.  Call with pos == NULL to size the output
+ * (*total is always written); pos_capacity is in entries.  Host buffers. */
+int b200sa_locate_batch(const b200sa_index *idx, const uint32_t *L, const uint32_t *R,
+                        uint64_t npat, uint64_t *pos_off, uint32_t *pos, uint64_t pos_capacity,
+                        uint64_t *total);
+int b200sa_locate_device(const b200sa_index *idx, const uint32_t *d_L, const uint32_t *d_R,
+                         uint64_t npat, uint64_t *d_pos_off, uint32_t *d_pos,
+                         uint64_t pos_capacity, uint64_t *total, void *stream);
+
+/* ---- synthetic inputs on the device (bench / tests; mirrors performance/suffix_array_search.c:13-32)
+ * d_text must hold n + 1 bytes; symbols are 1 + hash(seed + i) % nsym, d_text[n] = 0. */
+int b200sa_synth_codes(uint8_t *d_text, uint64_t n, uint32_t nsym, uint64_t seed, int device,
+                       void *stream);
+int b200sa_synth_reads(const uint8_t *d_text, uint64_t n, uint32_t nsym, uint8_t *d_reads,
+                       uint64_t nreads, uint32_t m, uint32_t miss_per_1024, uint64_t seed,
+                       int device, void *stream);
+
+int b200sa_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SA_H */

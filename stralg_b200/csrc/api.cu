@@ -1,0 +1,366 @@
+// api.cu -- the C ABI declared in include/b200sa.h.
+#include "../../include/b200sa.h"
+#include "engine.h"
+
+#include <mutex>
+#include <new>
+#include <string.h>
+
+using namespace b200sa;
+
+struct b200sa_index {
+    DeviceIndex ix;
+    uint32_t flags = 0;
+    float prof_ms[StageTimer::MAX];
+    const char *prof_name[StageTimer::MAX];
+    double prof_bytes[StageTimer::MAX];
+    int prof_n = 0;
+};
+
+static thread_local std::string g_last_error;
+
+static int fail(enum b200sa_error code, const std::string &msg, enum b200sa_error *err) {
+    g_last_error = msg;
+    if (err) *err = code;
+    return (int)code;
+}
+static int ok(enum b200sa_error *err) {
+    if (err) *err = B200SA_OK;
+    return 0;
+}
+
+static enum b200sa_error code_of(cudaError_t e) {
+    return e == cudaErrorMemoryAllocation ? B200SA_ERR_OUT_OF_MEMORY : B200SA_ERR_CUDA;
+}
+
+#define API_GUARD_BEGIN try {
+#define API_GUARD_END(errptr)                                                    \
+    }                                                                            \
+    catch (const CudaFailure &e) {                                               \
+        cudaGetLastError();                                                      \
+        return fail(code_of(e.code), e.what(), errptr);                          \
+    }                                                                            \
+    catch (const std::bad_alloc &) {                                             \
+        return fail(B200SA_ERR_OUT_OF_MEMORY, "host allocation failed", errptr); \
+    }                                                                            \
+    catch (const std::exception &e) {                                            \
+        return fail(B200SA_ERR_INTERNAL, e.what(), errptr);                      \
+    }
+
+static void use_device(int device) {
+    CUDA_CHECK(cudaSetDevice(device));
+    static std::mutex mu;
+    static bool pool_set[64] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    if (device >= 0 && device < 64 && !pool_set[device]) {
+        cudaMemPool_t pool;
+        CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t never = UINT64_MAX;
+        CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never));
+        pool_set[device] = true;
+    }
+}
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char *b200sa_last_error(void) { return g_last_error.c_str(); }
+
+int b200sa_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+__attribute__((visibility("hidden"))) static int build_into(b200sa_index *h, const uint8_t *codes, uint64_t n, uint32_t sigma, uint32_t flags, int device,
+                      void *stream, enum b200sa_error *err) {
+    API_GUARD_BEGIN
+    use_device(device);
+    DeviceIndex &ix = h->ix;
+    ix.stream = (cudaStream_t)stream;
+    ix.device = device;
+    ix.n = (u32)n;
+    ix.len = (u32)n + 1;
+    ix.sigma = sigma;
+    ix.pk = packing_for_sigma(sigma);
+    h->flags = flags;
+    cudaStream_t st = ix.stream;
+    if (flags & B200SA_PROFILE) ix.timer.enable(st);
+
+    if (flags & B200SA_TEXT_ON_DEVICE) {
+        ix.text_ptr = codes;
+    } else {
+        ix.text.alloc((size_t)n + 1, st);
+        if (n) CUDA_CHECK(cudaMemcpyAsync(ix.text.ptr, codes, n, cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemsetAsync(ix.text.ptr + n, 0, 1, st));
+        ix.text_ptr = ix.text.ptr;
+    }
+    DevBuf<int> d_err(1, st);
+    CUDA_CHECK(cudaMemsetAsync(d_err.ptr, 0, 4, st));
+    pack_text(ix, d_err.ptr);
+    int herr = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&herr, d_err.ptr, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (herr) return fail(B200SA_ERR_BAD_SYMBOL, "text holds a code outside 1..sigma-1", err);
+    ix.text.release();  // everything downstream reads the packed text
+    ix.text_ptr = nullptr;
+
+    const bool want_lcp = flags & B200SA_BUILD_LCP;
+    const bool want_isa = (flags & B200SA_BUILD_ISA) || want_lcp;
+    build_suffix_array(ix, want_isa);
+    if (want_lcp) build_lcp(ix);
+    if (!(flags & B200SA_BUILD_ISA)) ix.isa.release();
+    if (flags & (B200SA_BUILD_OCC | B200SA_BUILD_BWT)) build_bwt_tables(ix, flags & B200SA_BUILD_BWT);
+    ix.packed.release();
+    if (flags & B200SA_DROP_SA) ix.sa.release();
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (flags & B200SA_PROFILE) {
+        h->prof_n = ix.timer.n;
+        for (int i = 0; i < ix.timer.n; ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ix.timer.ev[i][0], ix.timer.ev[i][1]);
+            h->prof_ms[i] = ms;
+            h->prof_name[i] = ix.timer.name[i];
+            h->prof_bytes[i] = ix.timer.bytes[i];
+        }
+        ix.timer.clear();
+    }
+    return ok(err);
+    API_GUARD_END(err)
+}
+
+b200sa_index *b200sa_build(const uint8_t *codes, uint64_t n, uint32_t sigma, uint32_t flags, int device,
+                           void *stream, enum b200sa_error *err) {
+    if ((!codes && n) || sigma < 1 || sigma > 256) {
+        fail(B200SA_ERR_BAD_ARGUMENT, "bad text pointer or sigma outside 1..256", err);
+        return nullptr;
+    }
+    if (n > 0xFFFFFFFEull) {
+        fail(B200SA_ERR_TOO_LARGE, "n exceeds 2^32 - 2 (uint32 suffix arrays, suffix_array.h:10-20)", err);
+        return nullptr;
+    }
+    b200sa_index *h = new (std::nothrow) b200sa_index();
+    if (!h) {
+        fail(B200SA_ERR_OUT_OF_MEMORY, "host allocation failed", err);
+        return nullptr;
+    }
+    if (build_into(h, codes, n, sigma, flags, device, stream, err) != 0) {
+        b200sa_free(h);
+        return nullptr;
+    }
+    return h;
+}
+
+void b200sa_free(b200sa_index *idx) {
+    if (!idx) return;
+    cudaSetDevice(idx->ix.device);
+    delete idx;
+}
+
+int b200sa_stats(const b200sa_index *idx, struct b200sa_stats *out) {
+    if (!idx || !out) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    const DeviceIndex &ix = idx->ix;
+    out->length = ix.len;
+    out->sigma = ix.sigma;
+    out->primary = ix.primary;
+    out->rounds = ix.stats.rounds;
+    out->k0 = ix.stats.k0;
+    out->radix_bits = ix.stats.radix_bits;
+    out->passes0 = ix.stats.passes0;
+    out->occ_layout = (uint32_t)ix.occ_layout;
+    out->sorted_total = ix.stats.sorted_total;
+    out->passes_elems = ix.stats.passes_elems;
+    out->occ_bytes = ix.occ.bytes();
+    return 0;
+}
+
+int b200sa_profile(const b200sa_index *idx, const char **names, float *ms, double *bytes, int cap) {
+    if (!idx) return 0;
+    int n = idx->prof_n < cap ? idx->prof_n : cap;
+    for (int i = 0; i < n; ++i) {
+        if (names) names[i] = idx->prof_name[i];
+        if (ms) ms[i] = idx->prof_ms[i];
+        if (bytes) bytes[i] = idx->prof_bytes[i];
+    }
+    return idx->prof_n;
+}
+
+const uint32_t *b200sa_device_sa(const b200sa_index *idx) { return idx ? idx->ix.sa.ptr : nullptr; }
+const uint32_t *b200sa_device_isa(const b200sa_index *idx) { return idx ? idx->ix.isa.ptr : nullptr; }
+const uint32_t *b200sa_device_lcp(const b200sa_index *idx) { return idx ? idx->ix.lcp.ptr : nullptr; }
+const uint8_t *b200sa_device_bwt(const b200sa_index *idx) { return idx ? idx->ix.bwt.ptr : nullptr; }
+const uint8_t *b200sa_device_occ(const b200sa_index *idx) { return idx ? idx->ix.occ.ptr : nullptr; }
+
+static int copy_out(const b200sa_index *idx, const void *dptr, void *host, size_t bytes, const char *what) {
+    if (!idx || !host) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    if (!dptr) return fail(B200SA_ERR_NOT_BUILT, std::string(what) + " was not requested at build time", nullptr);
+    API_GUARD_BEGIN
+    CUDA_CHECK(cudaSetDevice(idx->ix.device));
+    CUDA_CHECK(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, idx->ix.stream));
+    CUDA_CHECK(cudaStreamSynchronize(idx->ix.stream));
+    return 0;
+    API_GUARD_END(nullptr)
+}
+
+int b200sa_copy_sa(const b200sa_index *idx, uint32_t *host) {
+    return copy_out(idx, idx ? idx->ix.sa.ptr : nullptr, host, idx ? (size_t)idx->ix.len * 4 : 0, "SA");
+}
+int b200sa_copy_isa(const b200sa_index *idx, uint32_t *host) {
+    return copy_out(idx, idx ? idx->ix.isa.ptr : nullptr, host, idx ? (size_t)idx->ix.len * 4 : 0, "ISA");
+}
+int b200sa_copy_lcp(const b200sa_index *idx, uint32_t *host) {
+    return copy_out(idx, idx ? idx->ix.lcp.ptr : nullptr, host, idx ? (size_t)idx->ix.len * 4 : 0, "LCP");
+}
+int b200sa_copy_bwt(const b200sa_index *idx, uint8_t *host) {
+    return copy_out(idx, idx ? idx->ix.bwt.ptr : nullptr, host, idx ? (size_t)idx->ix.len : 0, "BWT");
+}
+int b200sa_copy_c_table(const b200sa_index *idx, uint32_t *host) {
+    if (!idx || !host) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    memcpy(host, idx->ix.c_host, (size_t)idx->ix.sigma * 4);
+    return 0;
+}
+
+int b200sa_copy_o_dense(const b200sa_index *idx, uint32_t *host) {
+    if (!idx || !host) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    const DeviceIndex &ix = idx->ix;
+    if (ix.occ_layout == OCC_NONE) return fail(B200SA_ERR_NOT_BUILT, "O table was not requested at build time", nullptr);
+    uint64_t entries = ((uint64_t)ix.len + 1) * ix.sigma;
+    if (entries * 4 > 0xFFFFFFFFull)
+        return fail(B200SA_ERR_TOO_LARGE, "dense O table exceeds the reference's u32 byte size (bwt.c:50)", nullptr);
+    API_GUARD_BEGIN
+    CUDA_CHECK(cudaSetDevice(ix.device));
+    DevBuf<u32> d(entries, ix.stream);
+    occ_dense(ix, d.ptr);
+    CUDA_CHECK(cudaMemcpyAsync(host, d.ptr, entries * 4, cudaMemcpyDeviceToHost, ix.stream));
+    CUDA_CHECK(cudaStreamSynchronize(ix.stream));
+    return 0;
+    API_GUARD_END(nullptr)
+}
+
+int b200sa_occ(const b200sa_index *idx, const uint8_t *a, const uint32_t *i, uint64_t count, uint32_t *out) {
+    if (!idx || (count && (!a || !i || !out))) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    const DeviceIndex &ix = idx->ix;
+    if (ix.occ_layout == OCC_NONE) return fail(B200SA_ERR_NOT_BUILT, "O table was not requested at build time", nullptr);
+    for (uint64_t q = 0; q < count; ++q)
+        if (a[q] >= ix.sigma || i[q] > ix.len) return fail(B200SA_ERR_BAD_ARGUMENT, "O(a,i) query out of range", nullptr);
+    if (!count) return 0;
+    API_GUARD_BEGIN
+    CUDA_CHECK(cudaSetDevice(ix.device));
+    cudaStream_t st = ix.stream;
+    DevBuf<u8> da(count, st);
+    DevBuf<u32> di(count, st), dout(count, st);
+    CUDA_CHECK(cudaMemcpyAsync(da.ptr, a, count, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(di.ptr, i, count * 4, cudaMemcpyHostToDevice, st));
+    occ_probe(ix, da.ptr, di.ptr, count, dout.ptr);
+    CUDA_CHECK(cudaMemcpyAsync(out, dout.ptr, count * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    return 0;
+    API_GUARD_END(nullptr)
+}
+
+int b200sa_search_device(const b200sa_index *idx, const uint8_t *d_patterns, const uint64_t *d_offsets,
+                         uint32_t fixed_len, uint64_t npat, uint32_t *d_L, uint32_t *d_R, void *stream) {
+    if (!idx || (npat && (!d_patterns || !d_L || !d_R))) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    if (idx->ix.occ_layout == OCC_NONE) return fail(B200SA_ERR_NOT_BUILT, "O table was not requested at build time", nullptr);
+    API_GUARD_BEGIN
+    CUDA_CHECK(cudaSetDevice(idx->ix.device));
+    fm_search(idx->ix, d_patterns, d_offsets, fixed_len, npat, d_L, d_R, (cudaStream_t)stream);
+    return 0;
+    API_GUARD_END(nullptr)
+}
+
+int b200sa_search_batch(const b200sa_index *idx, const uint8_t *patterns, const uint64_t *offsets,
+                        uint32_t fixed_len, uint64_t npat, uint32_t *L, uint32_t *R) {
+    if (!idx || (npat && (!patterns || !L || !R))) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    if (idx->ix.occ_layout == OCC_NONE) return fail(B200SA_ERR_NOT_BUILT, "O table was not requested at build time", nullptr);
+    if (!npat) return 0;
+    API_GUARD_BEGIN
+    const DeviceIndex &ix = idx->ix;
+    CUDA_CHECK(cudaSetDevice(ix.device));
+    cudaStream_t st = ix.stream;
+    uint64_t total = offsets ? offsets[npat] : (uint64_t)fixed_len * npat;
+    DevBuf<u8> dp(total ? total : 1, st);
+    DevBuf<u64> doff;
+    DevBuf<u32> dL(npat, st), dR(npat, st);
+    if (total) CUDA_CHECK(cudaMemcpyAsync(dp.ptr, patterns, total, cudaMemcpyHostToDevice, st));
+    if (offsets) {
+        doff.alloc(npat + 1, st);
+        CUDA_CHECK(cudaMemcpyAsync(doff.ptr, offsets, (npat + 1) * 8, cudaMemcpyHostToDevice, st));
+    }
+    fm_search(ix, dp.ptr, offsets ? doff.ptr : nullptr, fixed_len, npat, dL.ptr, dR.ptr, st);
+    CUDA_CHECK(cudaMemcpyAsync(L, dL.ptr, npat * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(R, dR.ptr, npat * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    return 0;
+    API_GUARD_END(nullptr)
+}
+
+int b200sa_locate_device(const b200sa_index *idx, const uint32_t *d_L, const uint32_t *d_R, uint64_t npat,
+                         uint64_t *d_pos_off, uint32_t *d_pos, uint64_t pos_capacity, uint64_t *total, void *stream) {
+    if (!idx || !d_pos_off || (npat && (!d_L || !d_R))) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    if (!idx->ix.sa.ptr) return fail(B200SA_ERR_NOT_BUILT, "suffix array was dropped (B200SA_DROP_SA)", nullptr);
+    API_GUARD_BEGIN
+    CUDA_CHECK(cudaSetDevice(idx->ix.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    u64 t = fm_locate_count(idx->ix, d_L, d_R, npat, d_pos_off, st);
+    if (total) *total = t;
+    if (d_pos) {
+        if (t > pos_capacity) return fail(B200SA_ERR_BAD_ARGUMENT, "position buffer too small", nullptr);
+        fm_locate_fill(idx->ix, d_L, d_R, npat, d_pos_off, t, d_pos, st);
+    }
+    return 0;
+    API_GUARD_END(nullptr)
+}
+
+int b200sa_locate_batch(const b200sa_index *idx, const uint32_t *L, const uint32_t *R, uint64_t npat,
+                        uint64_t *pos_off, uint32_t *pos, uint64_t pos_capacity, uint64_t *total) {
+    if (!idx || !pos_off || (npat && (!L || !R))) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    if (!idx->ix.sa.ptr) return fail(B200SA_ERR_NOT_BUILT, "suffix array was dropped (B200SA_DROP_SA)", nullptr);
+    API_GUARD_BEGIN
+    const DeviceIndex &ix = idx->ix;
+    CUDA_CHECK(cudaSetDevice(ix.device));
+    cudaStream_t st = ix.stream;
+    DevBuf<u32> dL(npat ? npat : 1, st), dR(npat ? npat : 1, st);
+    DevBuf<u64> doff(npat + 1, st);
+    if (npat) {
+        CUDA_CHECK(cudaMemcpyAsync(dL.ptr, L, npat * 4, cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(dR.ptr, R, npat * 4, cudaMemcpyHostToDevice, st));
+    }
+    u64 t = fm_locate_count(ix, dL.ptr, dR.ptr, npat, doff.ptr, st);
+    if (total) *total = t;
+    CUDA_CHECK(cudaMemcpyAsync(pos_off, doff.ptr, (npat + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (pos && t) {
+        if (t > pos_capacity) return fail(B200SA_ERR_BAD_ARGUMENT, "position buffer too small", nullptr);
+        DevBuf<u32> dpos(t, st);
+        fm_locate_fill(ix, dL.ptr, dR.ptr, npat, doff.ptr, t, dpos.ptr, st);
+        CUDA_CHECK(cudaMemcpyAsync(pos, dpos.ptr, t * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    return 0;
+    API_GUARD_END(nullptr)
+}
+
+int b200sa_synth_codes(uint8_t *d_text, uint64_t n, uint32_t nsym, uint64_t seed, int device, void *stream) {
+    if (!d_text || nsym < 1 || nsym > 255) return fail(B200SA_ERR_BAD_ARGUMENT, "bad argument", nullptr);
+    API_GUARD_BEGIN
+    CUDA_CHECK(cudaSetDevice(device));
+    synth_codes(d_text, n, nsym, seed, (cudaStream_t)stream);
+    return 0;
+    API_GUARD_END(nullptr)
+}
+
+int b200sa_synth_reads(const uint8_t *d_text, uint64_t n, uint32_t nsym, uint8_t *d_reads, uint64_t nreads,
+                       uint32_t m, uint32_t miss_per_1024, uint64_t seed, int device, void *stream) {
+    if (!d_text || !d_reads || nsym < 1 || nsym > 255) return fail(B200SA_ERR_BAD_ARGUMENT, "bad argument", nullptr);
+    API_GUARD_BEGIN
+    CUDA_CHECK(cudaSetDevice(device));
+    synth_reads(d_text, n, nsym, d_reads, nreads, m, miss_per_1024, seed, (cudaStream_t)stream);
+    return 0;
+    API_GUARD_END(nullptr)
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

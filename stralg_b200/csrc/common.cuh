@@ -1,0 +1,141 @@
+// common.cuh -- shared helpers for the b200sa kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdexcept>
+#include <string>
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+namespace b200sa {
+
+struct CudaFailure : public std::runtime_error {
+    cudaError_t code;
+    CudaFailure(cudaError_t c, const char *what, const char *file, int line)
+        : std::runtime_error(std::string(what) + ": " + cudaGetErrorString(c) + " at " + file + ":" +
+                             std::to_string(line)),
+          code(c) {}
+};
+
+#define CUDA_CHECK(expr)                                                          \
+    do {                                                                          \
+        cudaError_t _e = (expr);                                                  \
+        if (_e != cudaSuccess) throw ::b200sa::CudaFailure(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define KERNEL_CHECK() CUDA_CHECK(cudaGetLastError())
+
+// Stream-ordered device buffer.  The default mempool keeps freed blocks (release threshold is
+// raised to "never" in api.cu), so steady-state builds do not pay cudaMalloc.
+template <typename T>
+struct DevBuf {
+    T *ptr = nullptr;
+    size_t count = 0;
+    cudaStream_t stream = 0;
+    DevBuf() {}
+    DevBuf(size_t n, cudaStream_t s) { alloc(n, s); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : ptr(o.ptr), count(o.count), stream(o.stream) { o.ptr = nullptr; o.count = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) {
+            release();
+            ptr = o.ptr; count = o.count; stream = o.stream;
+            o.ptr = nullptr; o.count = 0;
+        }
+        return *this;
+    }
+    void alloc(size_t n, cudaStream_t s) {
+        release();
+        stream = s;
+        count = n;
+        if (n) CUDA_CHECK(cudaMallocAsync((void **)&ptr, n * sizeof(T), s));
+    }
+    void release() {
+        if (ptr) cudaFreeAsync(ptr, stream);
+        ptr = nullptr;
+        count = 0;
+    }
+    T *detach() {
+        T *p = ptr;
+        ptr = nullptr;
+        count = 0;
+        return p;
+    }
+    ~DevBuf() { release(); }
+    size_t bytes() const { return count * sizeof(T); }
+};
+
+static inline unsigned div_up_u(u64 a, u64 b) { return (unsigned)((a + b - 1) / b); }
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// streaming (read-once) loads/stores: keep them out of L1
+__device__ __forceinline__ u64 ld_stream_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ u32 ld_stream_u32(const u32 *p) {
+    u32 v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ld_stream_u128(const void *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(u64 *p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Per-stage device timing (optional; enabled with B200SA_PROFILE).
+struct StageTimer {
+    static const int MAX = 64;
+    cudaEvent_t ev[MAX][2];
+    const char *name[MAX];
+    double bytes[MAX];
+    int n = 0;
+    bool on = false;
+    cudaStream_t stream = 0;
+    void enable(cudaStream_t s) { on = true; stream = s; }
+    int begin(const char *nm, double algorithmic_bytes) {
+        if (!on || n >= MAX) return -1;
+        cudaEventCreate(&ev[n][0]);
+        cudaEventCreate(&ev[n][1]);
+        name[n] = nm;
+        bytes[n] = algorithmic_bytes;
+        cudaEventRecord(ev[n][0], stream);
+        return n++;
+    }
+    void end(int id) {
+        if (id >= 0) cudaEventRecord(ev[id][1], stream);
+    }
+    void clear() {
+        for (int i = 0; i < n; ++i) {
+            cudaEventDestroy(ev[i][0]);
+            cudaEventDestroy(ev[i][1]);
+        }
+        n = 0;
+    }
+};
+
+}  // namespace b200sa

@@ -1,0 +1,76 @@
+// engine.h -- internal C++ interface between the C ABI (api.cu) and the kernel files.
+#pragma once
+#include "common.cuh"
+
+namespace b200sa {
+
+// Text packing parameters derived from the alphabet size (sentinel included in sigma).
+struct Packing {
+    int bits;   // bits per packed symbol (1, 2, 4 or 8); packed symbol = code - 1
+    int cpw;    // symbols per 64-bit word
+};
+static inline Packing packing_for_sigma(u32 sigma) {
+    u32 nsym = sigma > 1 ? sigma - 1 : 1;  // codes 1..sigma-1
+    Packing p;
+    p.bits = nsym <= 2 ? 1 : nsym <= 4 ? 2 : nsym <= 16 ? 4 : 8;
+    p.cpw = 64 / p.bits;
+    return p;
+}
+
+struct BuildStats {
+    u32 rounds;          // doubling rounds after the initial K-character sort
+    u32 k0;              // characters packed into the round-0 key
+    u32 radix_bits;
+    u32 passes0;         // radix passes in round 0
+    u64 sorted_total;    // sum over rounds of elements sorted
+    u64 passes_elems;    // sum over all radix passes of elements moved
+};
+
+// Occurrence-table layouts
+enum OccLayout { OCC_NONE = 0, OCC_DNA32 = 1, OCC_BYTE = 2 };
+
+struct DeviceIndex {
+    cudaStream_t stream = 0;
+    int device = 0;
+    u32 n = 0, len = 0, sigma = 0;
+    Packing pk{};
+    // owned device arrays (may be null when not requested / released)
+    DevBuf<u8> text;        // len bytes of codes (text[n] = 0), only when we own a copy
+    const u8 *text_ptr = nullptr;
+    DevBuf<u64> packed;     // packed text, padded with >= 2 zero words
+    DevBuf<u32> sa, isa, lcp;
+    DevBuf<u8> bwt;
+    DevBuf<u32> c_table;    // sigma entries (device)
+    u32 c_host[256];
+    u64 sym_counts_host[256];
+    u32 primary = 0;        // row r with sa[r] == 0
+    OccLayout occ_layout = OCC_NONE;
+    DevBuf<u8> occ;         // occurrence blocks
+    u64 occ_blocks = 0;
+    u32 occ_block_bytes = 0;
+    BuildStats stats{};
+    StageTimer timer;
+};
+
+// sa_build.cu
+void pack_text(DeviceIndex &ix, int *d_err);
+void build_suffix_array(DeviceIndex &ix, bool keep_isa);
+// lcp.cu
+void build_lcp(DeviceIndex &ix);
+// bwt_occ.cu
+void build_bwt_tables(DeviceIndex &ix, bool keep_bwt);
+void occ_probe(const DeviceIndex &ix, const u8 *d_a, const u32 *d_i, u64 count, u32 *d_out);
+void occ_dense(const DeviceIndex &ix, u32 *d_out);  // (len+1)*sigma entries, reference layout
+// fm_search.cu
+void fm_search(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fixed_len, u64 npat, u32 *d_L,
+               u32 *d_R, cudaStream_t st);
+u64 fm_locate_count(const DeviceIndex &ix, const u32 *d_L, const u32 *d_R, u64 npat, u64 *d_pos_off,
+                    cudaStream_t st);
+void fm_locate_fill(const DeviceIndex &ix, const u32 *d_L, const u32 *d_R, u64 npat, const u64 *d_pos_off,
+                    u64 total, u32 *d_pos, cudaStream_t st);
+// synth.cu
+void synth_codes(u8 *d_text, u64 n, u32 nsym, u64 seed, cudaStream_t st);
+void synth_reads(const u8 *d_text, u64 n, u32 nsym, u8 *d_reads, u64 nreads, u32 m, u32 miss_per_1024,
+                 u64 seed, cudaStream_t st);
+
+}  // namespace b200sa

@@ -1,0 +1,184 @@
+// fm_search.cu -- batched FM-index backward exact search and locate (sm_100a).
+//
+// One lane per pattern runs the recurrence of stralg/bwt.c:164-199:
+//     L = 0, R = len;  a pattern longer than len gives (L, R) = (1, 0);
+//     for i = m-1 .. 0 while L < R:  L = C(a) + O(a, L),  R = C(a) + O(a, R)
+// and locate expands [L, R) into SA[L..R) in suffix-array order (bwt.c:201-217).
+// O(a, i) is one 32-byte block fetch + popcount (occ.cuh).  The two fetches of a step are
+// independent, so every lane keeps two sector loads in flight; occupancy hides the rest.
+// A pattern symbol outside 1..sigma-1 (the reference asserts, bwt.c:189-190) yields the empty
+// interval (1, 0).  An empty pattern yields (0, len) (the reference underflows, bwt.c:185).
+#include "engine.h"
+#include "occ.cuh"
+
+namespace b200sa {
+
+struct CTable5 {
+    u32 c[8];
+};
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) fm_search_kernel(OccView ov, CTable5 c5, const u32 *__restrict__ c_dev,
+                                                        u32 len, const u8 *__restrict__ pat,
+                                                        const u64 *__restrict__ off, u32 fixed_len, u64 npat,
+                                                        u32 *__restrict__ outL, u32 *__restrict__ outR) {
+    __shared__ u32 c_sh[256];
+    if (LAYOUT != 1) {
+        for (u32 i = threadIdx.x; i < 256; i += blockDim.x) c_sh[i] = i < ov.sigma ? c_dev[i] : 0;
+        __syncthreads();
+    }
+    u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npat) return;
+    u64 begin = off ? off[q] : q * (u64)fixed_len;
+    u64 m = off ? off[q + 1] - begin : (u64)fixed_len;
+    const u8 *p = pat + begin;
+    u32 L = 0, R = len;
+    if (m > (u64)len) {
+        L = 1;
+        R = 0;
+    }
+    for (int64_t i = (int64_t)m - 1; i >= 0 && L < R; --i) {
+        u32 a = p[i];
+        if (a == 0 || a >= ov.sigma) {
+            L = 1;
+            R = 0;
+            break;
+        }
+        u32 oL, oR, ca;
+        if (LAYOUT == 1) {
+            oL = occ_dna(ov, a, L);
+            oR = occ_dna(ov, a, R);
+            ca = c5.c[a];
+        } else {
+            oL = occ_byte(ov, a, L);
+            oR = occ_byte(ov, a, R);
+            ca = c_sh[a];
+        }
+        L = ca + oL;
+        R = ca + oR;
+    }
+    outL[q] = L;
+    outR[q] = R;
+}
+
+void fm_search(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fixed_len, u64 npat, u32 *d_L,
+               u32 *d_R, cudaStream_t st) {
+    if (!npat) return;
+    OccView ov = occ_view(ix);
+    CTable5 c5;
+    for (int i = 0; i < 8; ++i) c5.c[i] = ix.c_host[i];
+    unsigned blocks = div_up_u(npat, 256);
+    if (ix.occ_layout == OCC_DNA32)
+        fm_search_kernel<1><<<blocks, 256, 0, st>>>(ov, c5, ix.c_table.ptr, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R);
+    else
+        fm_search_kernel<2><<<blocks, 256, 0, st>>>(ov, c5, ix.c_table.ptr, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R);
+    KERNEL_CHECK();
+}
+
+// ---- locate -----------------------------------------------------------------------------------
+static constexpr int LC_NT = 1024;
+
+__global__ void __launch_bounds__(LC_NT) locate_count_kernel(const u32 *__restrict__ L, const u32 *__restrict__ R,
+                                                             u64 npat, u64 *__restrict__ pos_off,
+                                                             u64 *__restrict__ tile_tot) {
+    __shared__ u64 wsum[32];
+    u64 q = (u64)blockIdx.x * LC_NT + threadIdx.x;
+    u64 v = 0;
+    if (q < npat) {
+        u32 l = L[q], r = R[q];
+        v = r > l ? (u64)(r - l) : 0;
+    }
+    u64 incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u64 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane_id() >= (unsigned)o) incl += t;
+    }
+    if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    u64 wb = 0;
+    for (unsigned w = 0; w < (threadIdx.x >> 5); ++w) wb += wsum[w];
+    if (q < npat) pos_off[q] = wb + incl - v;
+    if (threadIdx.x == LC_NT - 1) tile_tot[blockIdx.x] = wb + incl;
+}
+
+__global__ void __launch_bounds__(1024) scan_u64_kernel(u64 *__restrict__ vals, u64 count, u64 *__restrict__ total) {
+    __shared__ u64 wsum[32];
+    __shared__ u64 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (u64 base = 0; base < count; base += 1024) {
+        u64 i = base + threadIdx.x;
+        u64 v = i < count ? vals[i] : 0;
+        u64 incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u64 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane_id() >= (unsigned)o) incl += t;
+        }
+        if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        u64 wb = 0;
+        for (unsigned w = 0; w < (threadIdx.x >> 5); ++w) wb += wsum[w];
+        u64 excl = carry + wb + incl - v;
+        if (i < count) vals[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(LC_NT) locate_add_kernel(u64 *__restrict__ pos_off, u64 npat,
+                                                           const u64 *__restrict__ tile_prefix,
+                                                           const u64 *__restrict__ total) {
+    u64 q = (u64)blockIdx.x * LC_NT + threadIdx.x;
+    if (q < npat) pos_off[q] += tile_prefix[blockIdx.x];
+    if (q == npat - 1) pos_off[npat] = *total;
+}
+
+u64 fm_locate_count(const DeviceIndex &ix, const u32 *d_L, const u32 *d_R, u64 npat, u64 *d_pos_off,
+                    cudaStream_t st) {
+    if (!npat) {
+        CUDA_CHECK(cudaMemsetAsync(d_pos_off, 0, 8, st));
+        return 0;
+    }
+    unsigned tiles = div_up_u(npat, LC_NT);
+    DevBuf<u64> tile_tot(tiles, st), total(1, st);
+    locate_count_kernel<<<tiles, LC_NT, 0, st>>>(d_L, d_R, npat, d_pos_off, tile_tot.ptr);
+    KERNEL_CHECK();
+    scan_u64_kernel<<<1, 1024, 0, st>>>(tile_tot.ptr, tiles, total.ptr);
+    KERNEL_CHECK();
+    locate_add_kernel<<<tiles, LC_NT, 0, st>>>(d_pos_off, npat, tile_tot.ptr, total.ptr);
+    KERNEL_CHECK();
+    u64 h = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&h, total.ptr, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    return h;
+}
+
+// one thread per output position; the owning pattern is found by binary search in pos_off
+__global__ void __launch_bounds__(256) locate_fill_kernel(const u32 *__restrict__ sa, const u32 *__restrict__ L,
+                                                          const u64 *__restrict__ pos_off, u64 npat, u64 total,
+                                                          u32 *__restrict__ pos) {
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    // largest q with pos_off[q] <= t
+    u64 lo = 0, hi = npat;  // pos_off[npat] = total > t
+    while (hi - lo > 1) {
+        u64 mid = lo + (hi - lo) / 2;
+        if (pos_off[mid] <= t) lo = mid;
+        else hi = mid;
+    }
+    pos[t] = sa[(u64)L[lo] + (t - pos_off[lo])];
+}
+
+void fm_locate_fill(const DeviceIndex &ix, const u32 *d_L, const u32 *d_R, u64 npat, const u64 *d_pos_off,
+                    u64 total, u32 *d_pos, cudaStream_t st) {
+    (void)d_R;
+    if (!total) return;
+    locate_fill_kernel<<<div_up_u(total, 256), 256, 0, st>>>(ix.sa.ptr, d_L, d_pos_off, npat, total, d_pos);
+    KERNEL_CHECK();
+}
+
+}  // namespace b200sa

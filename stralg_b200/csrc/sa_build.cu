@@ -1,0 +1,724 @@
+// sa_build.cu -- suffix-array construction by GPU prefix doubling (sm_100a).
+//
+// Produces the array the reference's four constructors agree on (stralg/suffix_array.c:32-48,
+// sa_is.c:466-509, sa_is_mem.c:471-494, skew.c:388-395): all len = n+1 suffixes of text+sentinel
+// in strcmp order, SA[0] = n.  None of the reference's algorithms is ported.  The pipeline:
+//
+//   pack_text        codes 1..sigma-1 -> (code-1) packed big-endian at 1/2/4/8 bits per symbol,
+//                    symbol counts for the C table fused (stralg/remap.c:73-88, bwt.c:35-45)
+//   cmer_hist        histogram of all digit-wide symbol groups; every round-0 radix pass's digit
+//                    histogram is that histogram up to <= K boundary corrections (round0_bases)
+//   make_keys0       key(s) = first K symbols of suffix s; the <= K suffixes that reach the
+//                    sentinel inside the window are fed first, shortest first, so that the STABLE
+//                    sort leaves them ahead of their padded-equal long neighbours
+//   onesweep passes  radix_sort.cuh
+//   rank_kernel      bucket heads by key comparison, rank[s] = SA index of the bucket head,
+//                    head bitmap for singleton retirement
+//   compact          suffixes in non-singleton buckets form the next active set
+//   rounds           key = (rank[s], rank[s+h]) for active suffixes only, sort, re-rank, h *= 2
+//
+// After the last round rank[] is the inverse suffix array (stralg/suffix_array.c:55-62).
+#include "engine.h"
+#include "radix_sort.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+namespace b200sa {
+
+// ---------------------------------------------------------------------------------------------
+// Packed-text access
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 window_at(const u64 *__restrict__ packed, u64 sym_index, int bits) {
+    // 64 bits of the packed stream starting at symbol sym_index (big-endian inside each word)
+    u64 bitpos = sym_index * (u64)bits;
+    u64 wi = bitpos >> 6;
+    unsigned o = (unsigned)(bitpos & 63);
+    u64 hi = packed[wi];
+    if (o == 0) return hi;
+    u64 lo = packed[wi + 1];
+    return (hi << o) | (lo >> (64 - o));
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack_text: one thread per packed word.  err[0] is set if a code is 0 or >= sigma.
+// sym_counts[c] (u64) accumulates the number of text positions holding code c (c >= 1).
+// ---------------------------------------------------------------------------------------------
+template <int BITS>
+__global__ void __launch_bounds__(256) pack_kernel(const u8 *__restrict__ text, u32 n, u32 sigma, u64 nwords,
+                                                   u64 *__restrict__ packed,
+                                                   unsigned long long *__restrict__ sym_counts,
+                                                   int *__restrict__ err) {
+    constexpr int CPW = 64 / BITS;
+    __shared__ u32 sh_counts[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh_counts[i] = 0;
+    __syncthreads();
+    u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    if (w < nwords) {
+        u64 t0 = w * CPW;
+        u64 word = 0;
+        if (t0 < n) {
+            const bool aligned = ((((uintptr_t)text) & 15) == 0);
+#pragma unroll
+            for (int c0 = 0; c0 < CPW; c0 += 16) {
+                __align__(16) u8 b[16];
+                u64 t = t0 + c0;
+                constexpr int CH = CPW < 16 ? CPW : 16;
+                if (CH == 16 && aligned && t + 16 <= n) {
+                    uint4 v = ld_stream_u128(text + t);
+                    *(uint4 *)b = v;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < CH; ++q) b[q] = (t + q < n) ? text[t + q] : (u8)1;
+                }
+#pragma unroll
+                for (int q = 0; q < CH; ++q) {
+                    u32 code = b[q];
+                    u32 sym = 0;
+                    if (t + q < n) {
+                        if (code == 0 || code >= sigma) bad = true;
+                        sym = (code - 1) & ((1u << BITS) - 1);
+                        if (BITS > 2) atomicAdd(&sh_counts[code & 255], 1u);
+                    }
+                    word |= (u64)sym << (64 - BITS - (c0 + q) * BITS);
+                }
+            }
+            if (BITS <= 2) {
+                // symbol counts straight from the packed word (padding symbols are 0)
+                u32 nv = (u32)((u64)n - t0 < (u64)CPW ? (u64)n - t0 : (u64)CPW);
+                if (BITS == 1) {
+                    u32 c1 = __popcll(word);
+                    atomicAdd(&sh_counts[2], c1);
+                    atomicAdd(&sh_counts[1], nv - c1);
+                } else {
+#pragma unroll
+                    for (u32 x = 0; x < 4; ++x) {
+                        u64 y = word ^ (x * 0x5555555555555555ull);
+                        u64 mm = ~(y | (y >> 1)) & 0x5555555555555555ull;
+                        u32 cx = __popcll(mm);
+                        if (x == 0) cx -= (CPW - nv);
+                        if (cx) atomicAdd(&sh_counts[x + 1], cx);
+                    }
+                }
+            }
+        }
+        packed[w] = word;
+    }
+    if (bad) *err = 1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (sh_counts[i]) atomicAdd(&sym_counts[i], (unsigned long long)sh_counts[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cmer_hist: H[x] = #{t in [0, n] : first RB bits of the packed stream at symbol t == x}
+// ---------------------------------------------------------------------------------------------
+template <int RB, int BITS>
+__global__ void __launch_bounds__(256) cmer_hist_kernel(const u64 *__restrict__ packed, u32 n, u64 nwords_data,
+                                                        u32 *__restrict__ hist) {
+    constexpr int BINS = 1 << RB;
+    constexpr int CPW = 64 / BITS;
+    __shared__ u32 sh[BINS];
+    for (int i = threadIdx.x; i < BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < nwords_data; w += stride) {
+        u64 hi = packed[w], lo = packed[w + 1];
+        u64 t0 = w * CPW;
+#pragma unroll
+        for (int q = 0; q < CPW; ++q) {
+            if (t0 + q <= n) {
+                const int o = q * BITS;
+                u64 win = o ? ((hi << o) | (lo >> (64 - o))) : hi;
+                atomicAdd(&sh[(u32)(win >> (64 - RB))], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < BINS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// Block p turns H into the exclusive digit offsets of round-0 pass p (p = 0 is the least
+// significant digit, i.e. the LAST c symbols of the K-symbol key).
+template <int RB>
+__global__ void __launch_bounds__(256) round0_bases_kernel(const u32 *__restrict__ H, const u64 *__restrict__ packed,
+                                                           u32 n, int K, int bits, u32 *__restrict__ digit_base) {
+    constexpr int BINS = 1 << RB;
+    constexpr int NT = 256;
+    constexpr int DPT = (BINS + NT - 1) / NT;
+    __shared__ u32 h[BINS];
+    __shared__ u32 warp_tot[NT / 32];
+    const int p = blockIdx.x;
+    const int c = RB / bits;
+    for (int i = threadIdx.x; i < BINS; i += NT) h[i] = H[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // digit p of suffix s is the c-mer at symbol s + off; suffixes s in [0, n]
+        u64 off = (u64)K - (u64)c * (p + 1);
+        u64 cut = off < (u64)n + 1 ? off : (u64)n + 1;
+        for (u64 t = 0; t < cut; ++t) h[(u32)(window_at(packed, t, bits) >> (64 - RB))]--;
+        h[0] += (u32)cut;
+    }
+    __syncthreads();
+    u32 v[DPT];
+    u32 sum = 0;
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+        int d = threadIdx.x * DPT + q;
+        v[q] = d < BINS ? h[d] : 0;
+        sum += v[q];
+    }
+    u32 incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane_id() >= (unsigned)o) incl += t;
+    }
+    if (lane_id() == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    u32 base = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) base += warp_tot[w];
+    u32 run = base + incl - sum;
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+        int d = threadIdx.x * DPT + q;
+        if (d < BINS) digit_base[(size_t)p * BINS + d] = run;
+        run += v[q];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// make_keys0: element j -> suffix s (short suffixes first, shortest first), key = first K symbols.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) make_keys0_kernel(const u64 *__restrict__ packed, u32 n, u32 len, int K,
+                                                         int bits, u64 *__restrict__ keys, u32 *__restrict__ vals) {
+    const u32 nshort = (u32)K < len ? (u32)K : len;
+    const int keybits = K * bits;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < len; j += stride) {
+        u32 s = j < nshort ? n - (u32)j : (u32)j - nshort;
+        u64 win = window_at(packed, s, bits);
+        keys[j] = win >> (64 - keybits);
+        vals[j] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// make_keys_round: key = (rank[s] << lo_bits) | rank[s + h] for the active suffixes.
+// Active suffixes share their first h symbols with another suffix, hence s + h <= n.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) make_keys_round_kernel(const u32 *__restrict__ act, u32 m,
+                                                              const u32 *__restrict__ rank, u64 h, u32 len,
+                                                              int lo_bits, u64 *__restrict__ keys) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
+        u32 s = act[j];
+        u64 t = (u64)s + h;
+        u64 lo = t < len ? (u64)rank[t] : 0ull;
+        keys[j] = ((u64)rank[s] << lo_bits) | lo;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rank_kernel: on a sorted (key, suffix) list of m elements.
+//   group(key) = key >> gs   (gs >= 64: one group starting at SA index 0 -- round 0)
+//   jb = first index of the element's group, jh = first index with the element's full key
+//   SA position of element j      = hi + (j - jb)      (hi = group value = SA index of the bucket)
+//   new rank of its suffix        = hi + (jh - jb)
+// Round 0 (K > 0): suffixes whose K-window reaches the sentinel are forced into singleton
+// buckets (they were fed first, so they already stand ahead of their padded-equal neighbours).
+// headbits: bit (j & 7) of byte j >> 3 is set when j starts a new bucket.
+// ---------------------------------------------------------------------------------------------
+static constexpr int RK_NT = 256;
+static constexpr int RK_IPT = 8;
+static constexpr int RK_TILE = RK_NT * RK_IPT;
+
+__device__ __forceinline__ u64 group_of(u64 key, int gs) { return gs >= 64 ? 0ull : key >> gs; }
+
+// first index f <= start with cmp(keys[f..start]) all equal to x under shift gs
+__device__ u32 gallop_first_equal(const u64 *__restrict__ keys, u32 start, u64 x, int gs) {
+    // precondition: (keys[start] >> gs) == x
+    u64 lo = start;
+    u64 step = 1;
+    while (lo >= step && (keys[lo - step] >> gs) == x) {
+        lo -= step;
+        step <<= 1;
+    }
+    int64_t bad = lo >= step ? (int64_t)(lo - step) : -1;
+    int64_t good = (int64_t)lo;
+    while (good - bad > 1) {
+        int64_t mid = bad + (good - bad) / 2;
+        if ((keys[mid] >> gs) == x) good = mid;
+        else bad = mid;
+    }
+    return (u32)good;
+}
+
+__global__ void __launch_bounds__(RK_NT) rank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ vals, u32 m,
+                                                     int gs, int K0, u32 n, u32 *__restrict__ rank,
+                                                     u32 *__restrict__ sa_out, u8 *__restrict__ headbits) {
+    __shared__ u32 warp_s[RK_NT / 32], warp_b[RK_NT / 32];
+    __shared__ u32 carry_s, carry_b;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u64 tile_base = (u64)blockIdx.x * RK_TILE;
+    const u64 j0 = tile_base + (u64)tid * RK_IPT;
+
+    u64 k[RK_IPT];
+    u32 s[RK_IPT];
+    u64 kprev = 0;
+    u32 sprev = 0;
+    if (j0 + RK_IPT <= m) {
+        const uint4 *kp = (const uint4 *)(keys + j0);
+#pragma unroll
+        for (int q = 0; q < RK_IPT / 2; ++q) {
+            uint4 v = kp[q];
+            k[2 * q] = ((u64)v.y << 32) | v.x;
+            k[2 * q + 1] = ((u64)v.w << 32) | v.z;
+        }
+        const uint4 *vp = (const uint4 *)(vals + j0);
+#pragma unroll
+        for (int q = 0; q < RK_IPT / 4; ++q) {
+            uint4 v = vp[q];
+            s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < RK_IPT; ++q) {
+            k[q] = j0 + q < m ? keys[j0 + q] : 0;
+            s[q] = j0 + q < m ? vals[j0 + q] : 0;
+        }
+    }
+    if (j0 > 0 && j0 < m) {
+        kprev = keys[j0 - 1];
+        sprev = vals[j0 - 1];
+    }
+
+    // ---- flags and thread-local running heads (tile-local index + 1; 0 = none yet) ----
+    u32 hs_idx[RK_IPT], hb_idx[RK_IPT];
+    u32 run_s = 0, run_b = 0;
+    u32 bits = 0;
+    {
+        u64 pk = kprev;
+        u32 ps = sprev;
+#pragma unroll
+        for (int q = 0; q < RK_IPT; ++q) {
+            u64 j = j0 + q;
+            bool valid = j < m;
+            bool hs = (j == 0) || (k[q] != pk);
+            bool hb = (j == 0) || (group_of(k[q], gs) != group_of(pk, gs));
+            if (K0 > 0 && j > 0) {
+                bool sh_cur = (u64)s[q] + (u64)K0 > (u64)n;
+                bool sh_prev = (u64)ps + (u64)K0 > (u64)n;
+                hs = hs || sh_cur || sh_prev;
+            }
+            if (valid && hs) {
+                run_s = (u32)(j - tile_base) + 1;
+                bits |= 1u << q;
+            }
+            if (valid && hb) run_b = (u32)(j - tile_base) + 1;
+            hs_idx[q] = run_s;
+            hb_idx[q] = run_b;
+            pk = k[q];
+            ps = s[q];
+        }
+    }
+    if (j0 < m) headbits[j0 >> 3] = (u8)bits;
+
+    // ---- carry-in for the tile (only when its first element does not start a bucket) ----
+    if (tid == 0) {
+        u32 cs = 0, cb = 0;  // global index of the head for the tile's first element
+        if (tile_base > 0 && tile_base < m) {
+            bool first_is_hs = bits & 1u;
+            bool first_is_hb = hb_idx[0] != 0;
+            if (!first_is_hs) {
+                u32 f = gallop_first_equal(keys, (u32)tile_base, k[0], 0);
+                if (K0 > 0) {
+                    // short suffixes stand first inside an equal-key run and are singletons
+                    while ((u64)vals[f] + (u64)K0 > (u64)n) ++f;
+                }
+                cs = f;
+            }
+            if (!first_is_hb && gs < 64) cb = gallop_first_equal(keys, (u32)tile_base, k[0] >> gs, gs);
+        }
+        carry_s = cs;
+        carry_b = cb;
+    }
+
+    // ---- block-wide "last head so far" (max-scan; indices grow with position) ----
+    u32 ex_s = run_s, ex_b = run_b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 ts = __shfl_up_sync(0xffffffffu, ex_s, o);
+        u32 tb = __shfl_up_sync(0xffffffffu, ex_b, o);
+        if (lane >= (unsigned)o) {
+            ex_s = max(ex_s, ts);
+            ex_b = max(ex_b, tb);
+        }
+    }
+    if (lane == 31) {
+        warp_s[warp] = ex_s;
+        warp_b[warp] = ex_b;
+    }
+    // exclusive within the warp
+    u32 pre_s = __shfl_up_sync(0xffffffffu, ex_s, 1);
+    u32 pre_b = __shfl_up_sync(0xffffffffu, ex_b, 1);
+    if (lane == 0) pre_s = pre_b = 0;
+    __syncthreads();
+    for (unsigned w = 0; w < warp; ++w) {
+        pre_s = max(pre_s, warp_s[w]);
+        pre_b = max(pre_b, warp_b[w]);
+    }
+    const u32 cs = carry_s, cb = carry_b;
+
+#pragma unroll
+    for (int q = 0; q < RK_IPT; ++q) {
+        u64 j = j0 + q;
+        if (j >= m) break;
+        u32 ls = hs_idx[q] ? hs_idx[q] : pre_s;
+        u32 lb = hb_idx[q] ? hb_idx[q] : pre_b;
+        u64 jh = ls ? tile_base + ls - 1 : (u64)cs;
+        u64 jb = gs >= 64 ? 0ull : (lb ? tile_base + lb - 1 : (u64)cb);
+        u64 hi = group_of(k[q], gs);
+        rank[s[q]] = (u32)(hi + (jh - jb));
+        if (sa_out) sa_out[(u32)(hi + (j - jb))] = s[q];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Active-set compaction from the head bitmap: element j stays active unless it is a singleton
+// (head[j] && (j + 1 == m || head[j + 1])).
+// ---------------------------------------------------------------------------------------------
+static constexpr int CP_NT = 256;
+static constexpr int CP_TILE = CP_NT * 64;
+
+__device__ __forceinline__ u64 active_mask(const u8 *__restrict__ headbits, u64 word, u32 m) {
+    // headbits is padded to a multiple of 8 bytes plus one extra word
+    const u64 *hb = (const u64 *)headbits;
+    u64 base = word * 64;
+    if (base >= m) return 0;
+    u64 H = hb[word];
+    u64 next = hb[word + 1];
+    u64 valid = (m - base >= 64) ? ~0ull : ((1ull << (m - base)) - 1ull);
+    H &= valid;
+    // head of j+1: shift right by one, pull in bit 0 of the next word
+    u64 Hn = (H >> 1) | (next << 63);
+    // position m (one past the end) counts as a head
+    u64 last = m - 1 - base;
+    if (m - base <= 64) {
+        Hn &= ~(1ull << last);
+        Hn |= (1ull << last);
+    }
+    u64 singleton = H & Hn;
+    return (~singleton) & valid;
+}
+
+__global__ void __launch_bounds__(CP_NT) count_active_kernel(const u8 *__restrict__ headbits, u32 m,
+                                                             u32 *__restrict__ tile_counts) {
+    __shared__ u32 wsum[CP_NT / 32];
+    u64 word = (u64)blockIdx.x * CP_NT + threadIdx.x;
+    u32 c = __popcll(active_mask(headbits, word, m));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane_id() == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 t = 0;
+        for (int w = 0; w < CP_NT / 32; ++w) t += wsum[w];
+        tile_counts[blockIdx.x] = t;
+    }
+}
+
+// single-block exclusive scan of u32 counts; total (u64) written to *total
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(u32 *__restrict__ counts, u32 ntiles,
+                                                          unsigned long long *__restrict__ total) {
+    __shared__ u64 wsum[32];
+    __shared__ u64 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (u32 base = 0; base < ntiles; base += 1024) {
+        u32 i = base + threadIdx.x;
+        u64 v = i < ntiles ? counts[i] : 0;
+        u64 incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u64 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane_id() >= (unsigned)o) incl += t;
+        }
+        if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        u64 wb = 0;
+        for (unsigned w = 0; w < (threadIdx.x >> 5); ++w) wb += wsum[w];
+        u64 excl = carry + wb + incl - v;
+        if (i < ntiles) counts[i] = (u32)excl;  // active counts fit u32 (<= m < 2^32)
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(CP_NT) scatter_active_kernel(const u8 *__restrict__ headbits,
+                                                               const u32 *__restrict__ vals, u32 m,
+                                                               const u32 *__restrict__ tile_offsets,
+                                                               u32 *__restrict__ out) {
+    __shared__ u32 wsum[CP_NT / 32];
+    u64 word = (u64)blockIdx.x * CP_NT + threadIdx.x;
+    u64 mask = active_mask(headbits, word, m);
+    u32 c = __popcll(mask);
+    u32 incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane_id() >= (unsigned)o) incl += t;
+    }
+    if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    u32 wb = 0;
+    for (unsigned w = 0; w < (threadIdx.x >> 5); ++w) wb += wsum[w];
+    u32 o = tile_offsets[blockIdx.x] + wb + incl - c;
+    u64 base = word * 64;
+    while (mask) {
+        int b = __ffsll((long long)mask) - 1;
+        mask &= mask - 1;
+        out[o++] = vals[base + b];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host orchestration
+// ---------------------------------------------------------------------------------------------
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+void pack_text(DeviceIndex &ix, int *d_err) {
+    cudaStream_t st = ix.stream;
+    const int b = ix.pk.bits, cpw = ix.pk.cpw;
+    u64 nwords_data = ((u64)ix.len + cpw - 1) / cpw;  // words holding positions 0..n
+    u64 nwords = nwords_data + 4;                      // zero padding for window reads
+    ix.packed.alloc(nwords, st);
+    DevBuf<unsigned long long> counts(256, st);
+    CUDA_CHECK(cudaMemsetAsync(counts.ptr, 0, 256 * 8, st));
+    int tid = ix.timer.begin("pack_text", (double)ix.len * (1.0 + b / 8.0));
+    unsigned blocks = div_up_u(nwords, 256);
+    switch (b) {
+        case 1: pack_kernel<1><<<blocks, 256, 0, st>>>(ix.text_ptr, ix.n, ix.sigma, nwords, ix.packed.ptr, counts.ptr, d_err); break;
+        case 2: pack_kernel<2><<<blocks, 256, 0, st>>>(ix.text_ptr, ix.n, ix.sigma, nwords, ix.packed.ptr, counts.ptr, d_err); break;
+        case 4: pack_kernel<4><<<blocks, 256, 0, st>>>(ix.text_ptr, ix.n, ix.sigma, nwords, ix.packed.ptr, counts.ptr, d_err); break;
+        default: pack_kernel<8><<<blocks, 256, 0, st>>>(ix.text_ptr, ix.n, ix.sigma, nwords, ix.packed.ptr, counts.ptr, d_err); break;
+    }
+    KERNEL_CHECK();
+    ix.timer.end(tid);
+    unsigned long long hc[256];
+    CUDA_CHECK(cudaMemcpyAsync(hc, counts.ptr, sizeof hc, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    // C table (stralg/bwt.c:35-45): the sentinel is the single occurrence of code 0
+    for (int i = 0; i < 256; ++i) ix.sym_counts_host[i] = hc[i];
+    ix.sym_counts_host[0] = 1;
+    u64 run = 0;
+    for (u32 a = 0; a < 256; ++a) {
+        ix.c_host[a] = (u32)run;
+        if (a < ix.sigma) run += ix.sym_counts_host[a];
+    }
+    ix.c_table.alloc(ix.sigma > 0 ? ix.sigma : 1, st);
+    CUDA_CHECK(cudaMemcpyAsync(ix.c_table.ptr, ix.c_host, (size_t)ix.sigma * 4, cudaMemcpyHostToDevice, st));
+}
+
+template <int RB>
+static void launch_cmer_hist(const DeviceIndex &ix, u64 nwords_data, u32 *hist, cudaStream_t st) {
+    unsigned blocks = div_up_u(nwords_data, 256 * 4);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks == 0) blocks = 1;
+    switch (ix.pk.bits) {
+        case 1: cmer_hist_kernel<RB, 1><<<blocks, 256, 0, st>>>(ix.packed.ptr, ix.n, nwords_data, hist); break;
+        case 2: cmer_hist_kernel<RB, 2><<<blocks, 256, 0, st>>>(ix.packed.ptr, ix.n, nwords_data, hist); break;
+        case 4: cmer_hist_kernel<RB, 4><<<blocks, 256, 0, st>>>(ix.packed.ptr, ix.n, nwords_data, hist); break;
+        default: cmer_hist_kernel<RB, 8><<<blocks, 256, 0, st>>>(ix.packed.ptr, ix.n, nwords_data, hist); break;
+    }
+    KERNEL_CHECK();
+}
+
+struct ActiveSet {
+    u32 m;
+};
+
+// headbits -> compacted list of still-active suffixes (in current SA order)
+static u32 compact_active(DeviceIndex &ix, const u8 *headbits, const u32 *vals, u32 m, DevBuf<u32> &tile_counts,
+                          unsigned long long *d_total, DevBuf<u32> &out, cudaStream_t st) {
+    u32 ntiles = div_up_u(m, CP_TILE);
+    if (tile_counts.count < ntiles) tile_counts.alloc(ntiles, st);
+    count_active_kernel<<<ntiles, CP_NT, 0, st>>>(headbits, m, tile_counts.ptr);
+    KERNEL_CHECK();
+    scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_counts.ptr, ntiles, d_total);
+    KERNEL_CHECK();
+    unsigned long long total = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (total == 0) return 0;
+    if (out.count < total) out.alloc(total, st);
+    scatter_active_kernel<<<ntiles, CP_NT, 0, st>>>(headbits, vals, m, tile_counts.ptr, out.ptr);
+    KERNEL_CHECK();
+    return (u32)total;
+}
+
+template <int RB>
+static void build_sa_impl(DeviceIndex &ix, bool keep_isa) {
+    typedef rs::Sorter<RB> S;
+    constexpr int BINS = 1 << RB;
+    cudaStream_t st = ix.stream;
+    const u32 n = ix.n, len = ix.len;
+    const int b = ix.pk.bits, cpw = ix.pk.cpw;
+    const int c = RB / b;  // symbols per digit
+
+    // ---- round-0 key width ----
+    int log2len = 0;
+    while ((1ull << log2len) < (u64)len) ++log2len;
+    double eff = std::log2((double)(ix.sigma > 2 ? ix.sigma - 1 : 1));
+    if (eff < 0.5) eff = 0.5;
+    int margin = env_int("B200SA_KEY_MARGIN", 8);
+    int P0 = (int)std::ceil((log2len + margin) / (c * eff));
+    int maxP = 64 / RB;
+    P0 = std::max(1, std::min(P0, maxP));
+    P0 = env_int("B200SA_PASSES0", P0);
+    P0 = std::max(1, std::min(P0, maxP));
+    const int K = c * P0;
+    ix.stats.k0 = K;
+    ix.stats.radix_bits = RB;
+    ix.stats.passes0 = P0;
+    ix.stats.rounds = 0;
+    ix.stats.sorted_total = len;
+    ix.stats.passes_elems = (u64)len * P0;
+
+    // ---- buffers ----
+    DevBuf<u64> keysA(len, st), keysB(len, st);
+    DevBuf<u32> valsA(len, st), valsB(len, st);
+    DevBuf<u32> rank(len, st);
+    DevBuf<u64> lookback(S::lookback_words(len), st);
+    DevBuf<u32> hist((size_t)8 * BINS, st), uniform(8, st), ticket(1, st);
+    size_t hb_bytes = (((size_t)len + 63) / 64 + 2) * 8;
+    DevBuf<u8> headbits(hb_bytes, st);
+    DevBuf<u32> tile_counts(div_up_u(len, CP_TILE), st);
+    DevBuf<unsigned long long> d_total(1, st);
+
+    // ---- round 0 ----
+    u64 nwords_data = ((u64)len + cpw - 1) / cpw;
+    int t;
+    t = ix.timer.begin("cmer_hist", (double)len * b / 8.0);
+    CUDA_CHECK(cudaMemsetAsync(hist.ptr, 0, (size_t)BINS * 4, st));
+    launch_cmer_hist<RB>(ix, nwords_data, hist.ptr, st);
+    DevBuf<u32> bases0((size_t)P0 * BINS, st);
+    round0_bases_kernel<RB><<<P0, 256, 0, st>>>(hist.ptr, ix.packed.ptr, n, K, b, bases0.ptr);
+    KERNEL_CHECK();
+    ix.timer.end(t);
+
+    t = ix.timer.begin("make_keys0", (double)len * 12.0);
+    {
+        unsigned blocks = div_up_u(len, 256 * 4);
+        make_keys0_kernel<<<blocks, 256, 0, st>>>(ix.packed.ptr, n, len, K, b, keysA.ptr, valsA.ptr);
+        KERNEL_CHECK();
+    }
+    ix.timer.end(t);
+
+    u64 *kin = keysA.ptr, *kout = keysB.ptr;
+    u32 *vin = valsA.ptr, *vout = valsB.ptr;
+    for (int p = 0; p < P0; ++p) {
+        t = ix.timer.begin("radix_pass0", (double)len * 24.0);
+        S::pass(kin, vin, kout, vout, len, p * RB, RB, bases0.ptr + (size_t)p * BINS, lookback.ptr, ticket.ptr, st);
+        ix.timer.end(t);
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+    }
+    // sorted data now in (kin, vin)
+    t = ix.timer.begin("rank0", (double)len * 16.0);
+    CUDA_CHECK(cudaMemsetAsync(headbits.ptr, 0, hb_bytes, st));
+    rank_kernel<<<div_up_u(len, RK_TILE), RK_NT, 0, st>>>(kin, vin, len, 64, K, n, rank.ptr, nullptr, headbits.ptr);
+    KERNEL_CHECK();
+    ix.timer.end(t);
+
+    // the sorted value buffer becomes the suffix array
+    DevBuf<u32> sa_buf, spare_vals;
+    if (vin == valsA.ptr) {
+        sa_buf = std::move(valsA);
+        spare_vals = std::move(valsB);
+    } else {
+        sa_buf = std::move(valsB);
+        spare_vals = std::move(valsA);
+    }
+    u32 *sa = sa_buf.ptr;
+
+    DevBuf<u32> act;  // active suffixes
+    t = ix.timer.begin("compact0", (double)len * 0.125);
+    u32 m = compact_active(ix, headbits.ptr, sa, len, tile_counts, d_total.ptr, spare_vals, st);
+    ix.timer.end(t);
+    act = std::move(spare_vals);
+    DevBuf<u32> act2;
+
+    // ---- doubling rounds over the active set ----
+    const int lo_bits = std::max(1, log2len);
+    const int key_bits = std::min(64, 2 * lo_bits);
+    u64 h = (u64)K;
+    u32 huniform[8];
+    while (m > 0) {
+        ix.stats.rounds++;
+        ix.stats.sorted_total += m;
+        if (act2.count < m) act2.alloc(m, st);
+        t = ix.timer.begin("round_keys", (double)m * 20.0);
+        make_keys_round_kernel<<<std::max(1u, std::min(div_up_u(m, 256 * 4), 148u * 16u)), 256, 0, st>>>(
+            act.ptr, m, rank.ptr, h, len, lo_bits, keysA.ptr);
+        KERNEL_CHECK();
+        ix.timer.end(t);
+        int npass = (key_bits + RB - 1) / RB;
+        t = ix.timer.begin("round_hist", (double)m * 8.0);
+        S::histogram(keysA.ptr, m, 0, key_bits, npass, hist.ptr, st);
+        S::scan(hist.ptr, m, npass, uniform.ptr, st);
+        CUDA_CHECK(cudaMemcpyAsync(huniform, uniform.ptr, (size_t)npass * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        ix.timer.end(t);
+        kin = keysA.ptr; kout = keysB.ptr;
+        vin = act.ptr; vout = act2.ptr;
+        for (int p = 0; p < npass; ++p) {
+            if (huniform[p]) continue;
+            int bits_here = std::min(RB, key_bits - p * RB);
+            t = ix.timer.begin("radix_pass", (double)m * 24.0);
+            S::pass(kin, vin, kout, vout, m, p * RB, bits_here, hist.ptr + (size_t)p * BINS, lookback.ptr, ticket.ptr, st);
+            ix.timer.end(t);
+            ix.stats.passes_elems += m;
+            std::swap(kin, kout);
+            std::swap(vin, vout);
+        }
+        t = ix.timer.begin("round_rank", (double)m * 24.0);
+        size_t hbm = (((size_t)m + 63) / 64 + 2) * 8;
+        CUDA_CHECK(cudaMemsetAsync(headbits.ptr, 0, hbm, st));
+        rank_kernel<<<div_up_u(m, RK_TILE), RK_NT, 0, st>>>(kin, vin, m, lo_bits, 0, n, rank.ptr, sa, headbits.ptr);
+        KERNEL_CHECK();
+        ix.timer.end(t);
+        // next active set goes to whichever value buffer does not hold the sorted list
+        DevBuf<u32> &sorted_buf = (vin == act.ptr) ? act : act2;
+        DevBuf<u32> &other_buf = (vin == act.ptr) ? act2 : act;
+        t = ix.timer.begin("compact", (double)m * 4.0);
+        u32 m2 = compact_active(ix, headbits.ptr, sorted_buf.ptr, m, tile_counts, d_total.ptr, other_buf, st);
+        ix.timer.end(t);
+        if (&other_buf != &act) std::swap(act, act2);
+        m = m2;
+        h *= 2;
+        if (h > (u64)len * 2 + 2 && m > 0)
+            throw std::runtime_error("prefix doubling failed to converge (internal error)");
+    }
+
+    ix.sa = std::move(sa_buf);
+    if (keep_isa) ix.isa = std::move(rank);
+}
+
+void build_suffix_array(DeviceIndex &ix, bool keep_isa) {
+    int rb = env_int("B200SA_RADIX_BITS", 8);
+    // the digit must hold a whole number of packed symbols
+    if (rb == 10 && (10 % ix.pk.bits) == 0) build_sa_impl<10>(ix, keep_isa);
+    else build_sa_impl<8>(ix, keep_isa);
+}
+
+}  // namespace b200sa

@@ -1,0 +1,201 @@
+"""GPU parity tests: the CUDA path (through the C ABI of include/b200sa.h) against the oracle.
+
+Integer work: every comparison is bit-exact (np.array_equal).  Expected values come from the
+committed golden fixtures, from the unmodified reference in oracle/_ref when its prebuilt library
+travelled with the snapshot, and otherwise from the restatement oracle.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def expected_sa(oracle, ref, codes, sigma):
+    if ref is not None and len(codes) > 2:
+        return ref.sa(codes, sigma, "sa_is")
+    return oracle.sa(codes)
+
+
+def texts():
+    """(name, symbols without sentinel, sigma)"""
+    rng = np.random.default_rng(777)
+    out = []
+    for n in (1, 2, 3, 31, 63, 64, 65, 255, 2047, 2048, 2049, 6143, 6144, 6145, 16383, 16384, 16385, 100003):
+        out.append((f"dna_{n}", rng.integers(1, 5, n), 5))
+    out.append(("bin_50000", rng.integers(1, 3, 50000), 3))
+    out.append(("unary_sigma5_30000", np.full(30000, 3), 5))
+    out.append(("unary_sigma2_70001", np.ones(70001, dtype=np.int64), 2))
+    out.append(("sym16_40000", rng.integers(1, 17, 40000), 17))
+    out.append(("sym20_40000", rng.integers(1, 21, 40000), 21))
+    out.append(("byte_60000", rng.integers(1, 256, 60000), 256))
+    out.append(("acgt_period4_65537", np.tile([1, 2, 3, 4], 16385)[:65537], 5))
+    out.append(("period1000_200000", np.tile(rng.integers(1, 5, 1000), 200), 5))
+    a, b = [1], [1, 2]
+    while len(b) < 100000:
+        a, b = b, b + a
+    out.append(("fibonacci_100000", np.array(b[:100000]), 3))
+    out.append(("dna_tail_poly_a", np.concatenate([rng.integers(1, 5, 5000), np.ones(300, dtype=np.int64)]), 5))
+    out.append(("dna_1M", rng.integers(1, 5, 1 << 20), 5))
+    out.append(("repeat_rich_1M", np.tile(rng.integers(1, 5, 40000), 27)[: (1 << 20) - 3], 5))
+    return out
+
+
+TEXTS = texts()
+
+
+@pytest.mark.parametrize("radix_bits", [8, 10])
+@pytest.mark.parametrize("case", TEXTS, ids=[t[0] for t in TEXTS])
+def test_suffix_array_tables_match_oracle(engine, oracle, ref, case, radix_bits, monkeypatch):
+    monkeypatch.setenv("B200SA_RADIX_BITS", str(radix_bits))
+    name, sym, sigma = case
+    codes = np.concatenate([np.asarray(sym, dtype=np.uint8), np.zeros(1, np.uint8)])
+    idx = engine.SuffixArrayIndex.build(codes[:-1], sigma, isa=True, bwt=True, occ=True)
+    sa_exp = expected_sa(oracle, ref, codes, sigma)
+    sa = idx.sa()
+    assert np.array_equal(sa, sa_exp), f"{name}: first mismatch at {np.nonzero(sa != sa_exp)[0][:5]}"
+    assert np.array_equal(idx.isa(), oracle.inverse(sa_exp))
+    bwt_exp = oracle.bwt(codes, sa_exp)
+    assert np.array_equal(idx.bwt(), bwt_exp)
+    assert np.array_equal(idx.c_table(), oracle.c_table(codes, sigma))
+    assert idx.primary == int(np.nonzero(sa_exp == 0)[0][0])
+    # O(a, i): every checkpoint row plus random probes; the full dense table for small inputs
+    ck = oracle.o_checkpoints(bwt_exp, sigma, 64)
+    rows = np.arange(0, len(sa) + 1, 64, dtype=np.uint32)
+    rng = np.random.default_rng(1)
+    for a in sorted(set([0, 1, sigma - 1, int(rng.integers(0, sigma))])):
+        got = idx.occ(np.full(len(rows), a, dtype=np.uint8), rows)
+        assert np.array_equal(got, ck[:, a]), (name, a)
+    qa = rng.integers(0, sigma, 5000).astype(np.uint8)
+    qi = rng.integers(0, len(sa) + 1, 5000).astype(np.uint32)
+    qi[:4] = [0, len(sa), len(sa) - 1, min(1, len(sa))]
+    assert np.array_equal(idx.occ(qa, qi), oracle.o_probe(bwt_exp, ck, sigma, 64, qa, qi))
+    if len(sa) <= 20000 and sigma <= 21:
+        assert np.array_equal(idx.o_dense(), oracle.o_table(bwt_exp, sigma))
+    idx.close()
+
+
+def test_golden_fixtures(engine, golden):
+    """Outputs of the reference itself on its own test strings (tests/golden/make_golden.py)."""
+    for name in golden_cases(golden):
+        codes = golden[f"{name}/codes"]
+        sigma = int(golden[f"{name}/sigma"][0])
+        idx = engine.SuffixArrayIndex.build(codes[:-1], sigma, isa=True, bwt=True, occ=True)
+        assert np.array_equal(idx.sa(), golden[f"{name}/sa"]), name
+        assert np.array_equal(idx.isa(), golden[f"{name}/isa"]), name
+        if f"{name}/c" in golden.files:
+            assert np.array_equal(idx.c_table(), golden[f"{name}/c"]), name
+        if f"{name}/o" in golden.files:
+            assert np.array_equal(idx.o_dense(), golden[f"{name}/o"]), name
+        pats = sorted({k.split("/")[1] for k in golden.files if k.startswith(name + "/pat")})
+        for p in pats:
+            pc = golden[f"{name}/{p}/codes"]
+            L, R = idx.search_one(pc)
+            assert [L, R] == golden[f"{name}/{p}/LR"].tolist(), (name, p)
+            assert np.array_equal(idx.exact_matches(pc), golden[f"{name}/{p}/pos"]), (name, p)
+        idx.close()
+
+
+def make_patterns(rng, codes, nsym, npat, mmin, mmax):
+    n = len(codes) - 1
+    lens = rng.integers(mmin, mmax + 1, npat)
+    off = np.zeros(npat + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    pat = np.empty(int(off[-1]), dtype=np.uint8)
+    for k in range(npat):
+        m = int(lens[k])
+        if k % 2 and n > m:
+            s = int(rng.integers(0, n - m))
+            pat[int(off[k]):int(off[k + 1])] = codes[s:s + m]
+        else:
+            pat[int(off[k]):int(off[k + 1])] = rng.integers(1, nsym + 1, m)
+    return pat, off
+
+
+@pytest.mark.parametrize("n,nsym,mmax", [(1 << 20, 4, 24), (200000, 4, 40), (50000, 2, 30), (80000, 20, 6),
+                                         (60000, 255, 4), (3000, 1, 50)])
+def test_batched_search_and_locate(engine, oracle, n, nsym, mmax):
+    """(L, R) per pattern and the position sets against the restatement of bwt.c:164-217;
+    config 1 of BASELINE.json is the first row (1 Mi random ACGT, 10 k patterns)."""
+    rng = np.random.default_rng(n + nsym)
+    codes = oracle.random_codes(n, nsym, seed=n)
+    sigma = nsym + 1
+    idx = engine.SuffixArrayIndex.build(codes[:-1], sigma)
+    sa = idx.sa()
+    bwt = oracle.bwt(codes, sa)
+    ck = oracle.o_checkpoints(bwt, sigma, 64)
+    c = oracle.c_table(codes, sigma)
+    pat, off = make_patterns(rng, codes, nsym, 10000, 1, mmax)
+    L, R = idx.search(pat, off)
+    Le, Re = oracle.search_ck(c, bwt, ck, 64, pat, off, threads=4)
+    assert np.array_equal(L, Le) and np.array_equal(R, Re)
+    poff, pos = idx.locate(L, R)
+    poff_e, pos_e = oracle.locate(oracle.sa(codes) if n <= 3000 else sa, Le, Re)
+    assert np.array_equal(poff, poff_e) and np.array_equal(pos, pos_e)
+    # fixed-length batch entry point
+    m = min(20, n)
+    fixed = np.concatenate([codes[s:s + m] for s in rng.integers(0, n - m + 1, 500)])
+    Lf, Rf = idx.search(fixed, fixed_len=m)
+    Lfe, Rfe = oracle.search_ck(c, bwt, ck, 64, fixed, np.arange(0, 501 * m, m, dtype=np.uint64))
+    assert np.array_equal(Lf, Lfe) and np.array_equal(Rf, Rfe) and (Rf > Lf).all()
+    idx.close()
+
+
+def test_search_edge_cases(engine, oracle):
+    codes, sigma, table = oracle.remap(b"mississippi")
+    idx = engine.SuffixArrayIndex.build(codes[:-1], sigma)
+    # pattern longer than the text: (1, 0) like bwt.c:179-181
+    long_pat = np.tile(codes[:-1], 2)
+    assert idx.search_one(long_pat) == (1, 0)
+    # a symbol outside 1..sigma-1: empty interval
+    assert idx.search_one(np.array([1, 7], dtype=np.uint8)) == (1, 0)
+    # whole text matches once at position 0
+    L, R = idx.search_one(codes[:-1])
+    assert R - L == 1 and idx.exact_matches(codes[:-1]).tolist() == [0]
+    idx.close()
+
+
+def test_bad_symbol_is_reported(engine):
+    with pytest.raises(engine.B200saError) as e:
+        engine.SuffixArrayIndex.build(np.array([1, 2, 0, 3], dtype=np.uint8), 5)
+    assert e.value.code == 3
+    with pytest.raises(engine.B200saError) as e:
+        engine.SuffixArrayIndex.build(np.array([1, 2, 5, 3], dtype=np.uint8), 5)
+    assert e.value.code == 3
+
+
+def test_device_resident_text_and_synth(engine, oracle):
+    """Device-pointer entry points: text generated on the GPU, built without a host copy."""
+    import ctypes as C
+    import torch
+    n = 300000
+    text = torch.empty(n + 1, dtype=torch.uint8, device="cuda")
+    lib = engine.load()
+    assert lib.b200sa_synth_codes(C.c_void_p(text.data_ptr()), n, 4, 99, 0, None) == 0
+    torch.cuda.synchronize()
+    host = np.empty(n + 1, dtype=np.uint8)
+    oracle.lib.oracle_synth_codes(host.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint64(n), C.c_uint32(4),
+                                  C.c_uint64(99))
+    assert np.array_equal(text.cpu().numpy(), host)
+    idx = engine.SuffixArrayIndex.build(text[:n], 5)
+    assert np.array_equal(idx.sa(), oracle.sa(host))
+    reads = torch.empty(1000 * 30, dtype=torch.uint8, device="cuda")
+    assert lib.b200sa_synth_reads(C.c_void_p(text.data_ptr()), n, 4, C.c_void_p(reads.data_ptr()), 1000, 30, 100, 7,
+                                  0, None) == 0
+    hreads = np.empty(1000 * 30, dtype=np.uint8)
+    oracle.lib.oracle_synth_reads(host.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint64(n), C.c_uint32(4),
+                                  hreads.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint64(1000), C.c_uint32(30),
+                                  C.c_uint32(100), C.c_uint64(7))
+    torch.cuda.synchronize()
+    assert np.array_equal(reads.cpu().numpy(), hreads)
+    dL = torch.empty(1000, dtype=torch.int32, device="cuda")
+    dR = torch.empty(1000, dtype=torch.int32, device="cuda")
+    idx.search_device(reads, None, 30, 1000, dL, dR, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    L, R = idx.search(hreads, fixed_len=30)
+    assert np.array_equal(dL.cpu().numpy().view(np.uint32), L) and np.array_equal(dR.cpu().numpy().view(np.uint32), R)
+    assert ((R > L).sum()) >= 850  # ~90 % of the reads are sampled from the text
+    idx.close()
