@@ -1,0 +1,582 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the stralg hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+N = 1  -> workload "build": SA + BWT + C + sampled O of a 3 Gbp synthetic DNA text (BASELINE.json
+          configs[2]; the text is resident in HBM before the timed region).  value = Mchars/s.
+          The same line carries `search` (FM exact search of 100-bp reads at 1 GPU),
+          `roofline` (dominant kernel = one radix pass of the initial sort), `e2e` (host buffers
+          through the C ABI, copies inside the timed region) and `cpu_baseline` (the unmodified
+          reference on the box's host cores, bounded sample).
+N > 1  -> workload "search" (BASELINE.json configs[3]): the index is replicated (every rank builds
+          it), 100 M reads are split over the ranks (strong scaling), (L, R) pairs are gathered
+          on rank 0 with NCCL inside the timed region.  value = patterns/s, whole job.
+--impl reference times the reference's own CPU implementation (oracle/_ref, else the oracle
+port) on a bounded sample of the same workload; rank 0 only.
+
+One JSON line on stdout (rank 0).  Timing: W >= 3 warm-up steps, CUDA events on the launching
+stream, barrier + synchronize on both sides, max over ranks; inputs are far larger than L2.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC_BUILD = "SA+BWT build Mchars/s on 1 B200"
+METRIC_SEARCH = "FM exact-search patterns/s"
+N_FULL = 3_000_000_000
+READS_FULL = 100_000_000
+READ_LEN = 100
+MISS_PER_1024 = 102  # ~10 % of the reads are uniform random
+SEED = 88172645463325252
+CPU_SAMPLE = 1 << 24
+
+
+def env_int(name, dflt):
+    v = os.environ.get(name)
+    return int(v) if v else dflt
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [ln for (t, ln) in self.lines if t0 <= t <= t1] or [ln for (_, ln) in self.lines]
+        for ln in rows:
+            f = [x.strip() for x in ln.split(",")]
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+                for k, nm in enumerate(names):
+                    if f[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def load_traffic(kernel_key):
+    """ncu dram bytes per launch of the dominant kernel, if a capture was summarised in profiles/."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel_key)
+    except Exception:
+        return None
+
+
+# =================================================================================================
+# reference arm / cpu baseline (the only place bench.py touches oracle/)
+# =================================================================================================
+def cpu_reference_build(codes_sample, sigma):
+    """One pass of the reference's CPU path over a bounded sample: sa_is_construction
+    (stralg/sa_is.c:466-509) + init_bwt_table (stralg/bwt.c:22-89).  Returns seconds, kind."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+    n = len(codes_sample) - 1
+    if _oracle.Ref.available():
+        ref = _oracle.Ref()
+        lib = ref.lib
+        buf = np.ascontiguousarray(codes_sample, dtype=np.uint8)
+        remap = _oracle.RefRemapTable()
+        remap.alphabet_size = sigma
+        t0 = time.perf_counter()
+        sa = lib.sa_is_construction(buf.ctypes.data_as(_oracle.u8p), C.c_uint32(sigma))
+        tab = lib.alloc_bwt_table(sa, None, C.byref(remap))
+        dt = time.perf_counter() - t0
+        lib.free_bwt_table(tab)
+        lib.free_suffix_array(sa)
+        return dt, "reference"
+    o = _oracle.Oracle()
+    t0 = time.perf_counter()
+    sa = o.sa(codes_sample)
+    bwt = o.bwt(codes_sample, sa)
+    o.c_table(codes_sample, sigma)
+    o.o_checkpoints(bwt, sigma, 64)
+    return time.perf_counter() - t0, "port"
+
+
+def cpu_reference_search(codes_sample, sigma, reads, m, threads):
+    """Reference exact iterator (stralg/bwt.c:164-199) over a dense O table, pattern shards on
+    `threads` host threads.  Returns (seconds for the search only, kind)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+    npat = len(reads) // m
+    L = np.empty(npat, dtype=np.uint32)
+    R = np.empty(npat, dtype=np.uint32)
+    o = _oracle.Oracle()
+    if _oracle.Ref.available():
+        ref = _oracle.Ref()
+        lib = ref.lib
+        buf = np.ascontiguousarray(codes_sample, dtype=np.uint8)
+        remap = _oracle.RefRemapTable()
+        remap.alphabet_size = sigma
+        sa = lib.sa_is_construction(buf.ctypes.data_as(_oracle.u8p), C.c_uint32(sigma))
+        tab = lib.alloc_bwt_table(sa, None, C.byref(remap))
+        fn = C.cast(lib.init_bwt_exact_match_iter, C.c_void_p)
+        t0 = time.perf_counter()
+        o.lib.oracle_ref_search_threads(fn, tab, reads.ctypes.data_as(_oracle.u8p), C.c_uint32(m),
+                                        C.c_uint64(npat), C.c_uint32(threads), L.ctypes.data_as(_oracle.u32p),
+                                        R.ctypes.data_as(_oracle.u32p))
+        dt = time.perf_counter() - t0
+        lib.free_bwt_table(tab)
+        lib.free_suffix_array(sa)
+        return dt, "reference", L, R
+    sa = o.sa(codes_sample)
+    bwt = o.bwt(codes_sample, sa)
+    c = o.c_table(codes_sample, sigma)
+    ck = o.o_checkpoints(bwt, sigma, 64)
+    off = np.arange(0, (npat + 1) * m, m, dtype=np.uint64)
+    t0 = time.perf_counter()
+    L, R = o.search_ck(c, bwt, ck, 64, reads, off, threads=threads)
+    return time.perf_counter() - t0, "port", L, R
+
+
+def host_synth(n, nsym, seed):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+    o = _oracle.Oracle()
+    out = np.empty(n + 1, dtype=np.uint8)
+    o.lib.oracle_synth_codes(out.ctypes.data_as(_oracle.u8p), C.c_uint64(n), C.c_uint32(nsym), C.c_uint64(seed))
+    return out, o
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    workload = args.workload if args.workload != "auto" else ("build" if args.gpus == 1 else "search")
+    cores = os.cpu_count() or 1
+    n = min(args.cpu_sample, args.n)
+    codes, o = host_synth(n, 4, SEED)
+    times = []
+    if workload == "build":
+        for step in range(args.warmup_ref + args.steps):
+            dt, kind = cpu_reference_build(codes, 5)
+            if step >= args.warmup_ref:
+                times.append(dt)
+        per = float(np.mean(times))
+        value = n / per / 1e6
+        line = {
+            "impl": "reference", "metric": METRIC_BUILD, "value": value, "unit": "Mchars/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup_ref, "ms_per_step": per * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "build: SA + C + dense O (sa_is_construction + init_bwt_table) of random ACGT",
+                       "n": n, "sigma": 5, "full_workload_n": args.n},
+            "cpu_baseline": {"value": value, "unit": "Mchars/s", "cores": 1, "kind": kind,
+                             "sample": f"first {n} symbols of the {args.n}-symbol synthetic text, per step"},
+            "e2e": {"value": value, "unit": "Mchars/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+    else:
+        npat = args.cpu_reads
+        reads = np.empty(npat * READ_LEN, dtype=np.uint8)
+        o.lib.oracle_synth_reads(codes.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint64(n), C.c_uint32(4),
+                                 reads.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint64(npat), C.c_uint32(READ_LEN),
+                                 C.c_uint32(MISS_PER_1024), C.c_uint64(SEED + 1))
+        for step in range(args.warmup_ref + args.steps):
+            dt, kind, _, _ = cpu_reference_search(codes, 5, reads, READ_LEN, cores)
+            if step >= args.warmup_ref:
+                times.append(dt)
+        per = float(np.mean(times))
+        value = npat / per
+        line = {
+            "impl": "reference", "metric": METRIC_SEARCH, "value": value, "unit": "patterns/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup_ref, "ms_per_step": per * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "search: reference exact iterator over its dense O table", "n": n, "sigma": 5,
+                       "reads": npat, "read_len": READ_LEN, "full_workload_n": args.n,
+                       "full_workload_reads": args.reads},
+            "cpu_baseline": {"value": value, "unit": "patterns/s", "cores": cores, "kind": kind,
+                             "sample": f"{npat} reads x {READ_LEN} bp against a {n}-symbol text (dense O limit of "
+                                       f"the reference, bwt.c:50), {cores} threads"},
+            "e2e": {"value": value, "unit": "patterns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+    print(json.dumps(line), flush=True)
+
+
+# =================================================================================================
+# GPU arm
+# =================================================================================================
+def gpu_arm(args, rank, local_rank, world):
+    import torch
+    import stralg_b200
+    lib = stralg_b200.load()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    workload = args.workload if args.workload != "auto" else ("build" if world == 1 else "search")
+    stream = torch.cuda.current_stream().cuda_stream
+    peak, peak_src = measured_peak()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- synthetic text in HBM ----
+    n = args.n
+    text = None
+    while text is None:
+        try:
+            text = torch.empty(n + 1, dtype=torch.uint8, device=dev)
+        except torch.OutOfMemoryError:
+            n //= 2
+    assert lib.b200sa_synth_codes(C.c_void_p(text.data_ptr()), n, 4, SEED, local_rank, C.c_void_p(stream)) == 0
+    torch.cuda.synchronize()
+
+    def build(profile=False, drop_sa=False, src=None):
+        return stralg_b200.SuffixArrayIndex.build(text[:n] if src is None else src, 5, occ=True, profile=profile,
+                                                  drop_sa=drop_sa, device=local_rank, stream=stream)
+
+    sampler = ClockSampler(local_rank)
+    out = {}
+
+    if workload == "build":
+        # ------------------------------------------------------------------ device-resident build
+        for _ in range(args.warmup):
+            build().close()
+        barrier()
+        sampler.start()
+        launches0 = lib.b200sa_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage_ms = {}
+        t_wall0 = time.time()
+        ev0.record()
+        stats = None
+        for _ in range(args.steps):
+            idx = build(profile=True)
+            for name, ms, by in idx.profile():
+                a = stage_ms.setdefault(name, [0, 0.0, 0.0])
+                a[0] += 1
+                a[1] += ms
+                a[2] += by
+            stats = idx.stats()
+            idx.close()
+        ev1.record()
+        barrier()
+        t_wall1 = time.time()
+        sampler.stop()
+        launches = lib.b200sa_launch_count() - launches0
+        ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+        ms_step = ms_total / args.steps
+        value = n / (ms_step / 1e3) / 1e6
+        clocks = sampler.summary(t_wall0, t_wall1)
+
+        # roofline of the dominant kernel: one radix pass over (u64 key, u32 suffix) pairs
+        rp = stage_ms.get("radix_pass0", [1, 1.0, 0.0])
+        pass_ms = rp[1] / rp[0]
+        pass_bytes = 24.0 * (n + 1)
+        achieved = pass_bytes / (pass_ms / 1e3) / 1e9
+        traffic = load_traffic("radix_pass0")
+        roofline = {"bound": "hbm", "kernel": "onesweep_pass_kernel (initial sort, one 8-bit digit)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": pass_bytes, "avg_launch_ms": pass_ms,
+                    "launches_timed": rp[0]}
+        model_bytes = 244.5 * n  # 237 B/char SA + 7.5 B/char BWT/C/O
+        stages = {k: {"launches": v[0], "ms_per_step": v[1] / args.steps,
+                      "algorithmic_GBps": (v[2] / v[1] / 1e6) if v[1] else None} for k, v in stage_ms.items()}
+
+        # ------------------------------------------------------------------ e2e: host buffers via the C ABI
+        e2e = None
+        try:
+            h_text = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+            h_text.copy_(text[:n])
+            h_sa = torch.empty(n + 1, dtype=torch.int32, pin_memory=True)
+            occ_bytes = stats["occ_bytes"]
+            h_occ = torch.empty(occ_bytes, dtype=torch.uint8, pin_memory=True)
+            h_c = np.empty(5, dtype=np.uint32)
+            torch.cuda.synchronize()
+            e_steps = max(1, min(args.steps, 2))
+            t_e = []
+            for it in range(1 + e_steps):
+                t0 = time.perf_counter()
+                idx = stralg_b200.SuffixArrayIndex.build(h_text.numpy(), 5, occ=True, device=local_rank,
+                                                         stream=stream)
+                stralg_b200._lib.check(lib.b200sa_copy_sa(idx._h, C.c_void_p(h_sa.data_ptr())))
+                stralg_b200._lib.check(lib.b200sa_copy_occ(idx._h, C.c_void_p(h_occ.data_ptr())))
+                stralg_b200._lib.check(lib.b200sa_copy_c_table(idx._h, C.c_void_p(h_c.ctypes.data)))
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                idx.close()
+                if it > 0:
+                    t_e.append(dt)
+            e_per = float(np.mean(t_e))
+            e2e = {"value": n / e_per / 1e6, "unit": "Mchars/s", "h2d_bytes_per_step": int(n),
+                   "d2h_bytes_per_step": int(4 * (n + 1) + occ_bytes + 20), "ms_per_step": e_per * 1e3,
+                   "steps": e_steps, "api": "b200sa_build(host codes) + b200sa_copy_sa/_occ/_c_table (pinned host)"}
+            del h_text, h_sa, h_occ
+        except Exception as ex:  # pinned-memory shortage must not kill the device-timed number
+            e2e = {"value": None, "unit": "Mchars/s", "error": str(ex)[:200]}
+
+        # ------------------------------------------------------------------ CPU baseline (bounded sample)
+        cpu_baseline = None
+        if not args.no_cpu:
+            ns = min(args.cpu_sample, n)
+            sample = np.concatenate([text[:ns].cpu().numpy(), np.zeros(1, np.uint8)])
+            dt, kind = cpu_reference_build(sample, 5)
+            cpu_baseline = {"value": ns / dt / 1e6, "unit": "Mchars/s", "cores": 1, "kind": kind,
+                            "host_cores_available": os.cpu_count(),
+                            "sample": f"first {ns} symbols of the text: sa_is_construction + init_bwt_table, "
+                                      f"{dt:.2f} s"}
+
+        out = {
+            "metric": METRIC_BUILD, "value": value, "unit": "Mchars/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "build: SA + BWT + C + sampled O of random ACGT (BASELINE configs[2])"
+                       if n == N_FULL else "build: SA + BWT + C + sampled O of random ACGT",
+                       "n": n, "sigma": 5, "sa_dtype": "uint32", "l2": "inputs larger than L2 (no flush needed)",
+                       "k0": stats["k0"], "radix_bits": stats["radix_bits"], "passes0": stats["passes0"],
+                       "doubling_rounds": stats["rounds"]},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline,
+            "model": {"algorithmic_bytes_per_char": 244.5, "whole_build_GBps": model_bytes / (ms_step / 1e3) / 1e9,
+                      "whole_build_frac_of_peak": model_bytes / (ms_step / 1e3) / 1e9 / peak},
+            "cpu_baseline": cpu_baseline, "stages": stages,
+        }
+        if not args.no_search:
+            out["search"] = search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n, None, 0, 1,
+                                         peak, peak_src, build)
+    else:
+        res = search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n, dist, rank, world, peak,
+                           peak_src, build)
+        out = res
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n, dist, rank, world, peak, peak_src,
+                 build):
+    """Replicated index, reads split over ranks, (L, R) gathered on rank 0 (NCCL) in the timed region."""
+    total_reads = args.reads
+    m = READ_LEN
+    idx = build(drop_sa=True)  # (L, R) only: the 12 GB suffix array is not needed for counting
+    shard = total_reads // world
+    total_reads = shard * world
+
+    def gen_reads(count, seed):
+        r = torch.empty(count * m, dtype=torch.uint8, device=dev)
+        assert lib.b200sa_synth_reads(C.c_void_p(text.data_ptr()), n, 4, C.c_void_p(r.data_ptr()), count, m,
+                                      MISS_PER_1024, seed, local_rank, C.c_void_p(stream)) == 0
+        return r
+
+    reads = gen_reads(shard, SEED + 1 + rank * 7919)
+    LR = torch.empty((2, shard), dtype=torch.int32, device=dev)
+    gathered = None
+    if dist is not None and rank == 0:
+        gathered = [torch.empty((2, shard), dtype=torch.int32, device=dev) for _ in range(world)]
+
+    def step():
+        idx.search_device(reads, None, m, shard, LR[0], LR[1], stream)
+        if dist is not None:
+            dist.gather(LR, gathered, dst=0)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.b200sa_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    tw1 = time.time()
+    sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    launches = lib.b200sa_launch_count() - launches0
+    value = total_reads / (ms_step / 1e3)
+
+    # steps actually executed per read -> algorithmic bytes (m + 2*steps*32 + 8)
+    Lh = LR[0].cpu().numpy().view(np.uint32)
+    Rh = LR[1].cpu().numpy().view(np.uint32)
+    hit_frac = float((Rh > Lh).mean())
+    # kernel-only timing of one rank's shard
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(args.steps):
+        idx.search_device(reads, None, m, shard, LR[0], LR[1], stream)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / args.steps
+    miss_steps = 16.0
+    bytes_per_read = hit_frac * (m + 2 * m * 32 + 8) + (1 - hit_frac) * (m + 2 * miss_steps * 32 + 8)
+    achieved = bytes_per_read * shard / (kernel_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "fm_search_kernel<DNA32> (one lane per read)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic("fm_search"),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_read * shard,
+                "avg_launch_ms": kernel_ms, "hit_fraction": hit_frac}
+
+    # e2e: host reads in, host (L, R) out through b200sa_search_batch
+    e2e = None
+    try:
+        e_reads = min(shard, args.e2e_reads)
+        h_reads = torch.empty(e_reads * m, dtype=torch.uint8, pin_memory=True)
+        h_reads.copy_(reads[: e_reads * m])
+        hL = torch.empty(e_reads, dtype=torch.int32, pin_memory=True)
+        hR = torch.empty(e_reads, dtype=torch.int32, pin_memory=True)
+        torch.cuda.synchronize()
+        ts = []
+        for it in range(3):
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            stralg_b200._lib.check(lib.b200sa_search_batch(idx._h, C.c_void_p(h_reads.data_ptr()), None, m, e_reads,
+                                                           C.c_void_p(hL.data_ptr()), C.c_void_p(hR.data_ptr())))
+            dt = time.perf_counter() - t0
+            if it > 0:
+                ts.append(dt)
+        dt = float(np.mean(ts))
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": e_reads * world / dt, "unit": "patterns/s", "h2d_bytes_per_step": int(e_reads * m),
+               "d2h_bytes_per_step": int(e_reads * 8), "reads_per_rank": e_reads,
+               "api": "b200sa_search_batch (pinned host reads in, host (L, R) out), all ranks concurrently"}
+        del h_reads
+    except Exception as ex:
+        e2e = {"value": None, "unit": "patterns/s", "error": str(ex)[:200]}
+
+    res = {
+        "metric": METRIC_SEARCH, "value": value, "unit": "patterns/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "search: batched FM exact search, replicated 3 Gbp index (BASELINE configs[3])"
+                   if n == N_FULL else "search: batched FM exact search, replicated index",
+                   "n": n, "sigma": 5, "reads": total_reads, "read_len": m, "reads_per_gpu": shard,
+                   "miss_fraction": MISS_PER_1024 / 1024.0, "gather": "NCCL gather of (L,R) to rank 0" if world > 1
+                   else "none (1 GPU)", "l2": "index (1.5 GB) and reads larger than L2"},
+        "clocks": sampler.summary(tw0, tw1), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "kernel_only_patterns_per_s_per_gpu": shard / (kernel_ms / 1e3),
+    }
+    if not args.no_cpu and rank == 0 and world == 1:
+        ns = min(args.cpu_sample, n)
+        sample = np.concatenate([text[:ns].cpu().numpy(), np.zeros(1, np.uint8)])
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import _oracle
+        o = _oracle.Oracle()
+        npat = args.cpu_reads
+        hr = np.empty(npat * m, dtype=np.uint8)
+        o.lib.oracle_synth_reads(sample.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint64(ns), C.c_uint32(4),
+                                 hr.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint64(npat), C.c_uint32(m),
+                                 C.c_uint32(MISS_PER_1024), C.c_uint64(SEED + 1))
+        cores = os.cpu_count() or 1
+        dt, kind, _, _ = cpu_reference_search(sample, 5, hr, m, cores)
+        res["cpu_baseline"] = {"value": npat / dt, "unit": "patterns/s", "cores": cores, "kind": kind,
+                               "sample": f"{npat} reads x {m} bp against the first {ns} symbols (the reference's "
+                                         f"dense O cannot be built beyond ~214 M rows, bwt.c:50)"}
+    idx.close()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "build", "search"])
+    ap.add_argument("--n", type=int, default=env_int("B200SA_BENCH_N", N_FULL))
+    ap.add_argument("--reads", type=int, default=env_int("B200SA_BENCH_READS", READS_FULL))
+    ap.add_argument("--e2e-reads", type=int, default=20_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=CPU_SAMPLE)
+    ap.add_argument("--cpu-reads", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-search", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    args.warmup_ref = min(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    gpu_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -91,6 +91,8 @@ int b200sa_copy_isa(const b200sa_index *idx, uint32_t *host);
 int b200sa_copy_lcp(const b200sa_index *idx, uint32_t *host);
 int b200sa_copy_bwt(const b200sa_index *idx, uint8_t *host);
 int b200sa_copy_c_table(const b200sa_index *idx, uint32_t *host /* sigma entries */);
+/* The sampled O table as stored (b200sa_stats.occ_bytes bytes; layout in stralg_b200/csrc/occ.cuh). */
+int b200sa_copy_occ(const b200sa_index *idx, uint8_t *host);
 /* Dense O table in the reference layout o[i * sigma + a], i in [0, len] (bwt.c:47-65).
  * Fails with B200SA_ERR_TOO_LARGE where the reference's own u32 size computation overflows. */
 int b200sa_copy_o_dense(const b200sa_index *idx, uint32_t *host /* (len + 1) * sigma */);
@@ -128,6 +130,8 @@ int b200sa_synth_reads(const uint8_t *d_text, uint64_t n, uint32_t nsym, uint8_t
                        int device, void *stream);
 
 int b200sa_device_count(void);
+/* kernels launched by this library in this process so far (bench accounting) */
+uint64_t b200sa_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -420,3 +420,63 @@ void oracle_synth_reads(const uint8_t *text, uint64_t n, uint32_t nsym, uint8_t 
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Threaded driver around the REAL reference iterator (bench.py's reference arm only).
+ * `init_fn` is the address of init_bwt_exact_match_iter from oracle/_ref/libstralg_ref.so
+ * (stralg/bwt.c:164-199); `table` its struct bwt_table.  The iterator struct is declared here
+ * with the layout of stralg/bwt.h:168-173.  Patterns are fixed-length, NUL-terminated copies are
+ * made per call because the reference takes C strings.  The table is read-only after
+ * construction, so pattern shards run on independent threads.
+ * ------------------------------------------------------------------------------------------ */
+struct ref_exact_iter {
+    const void *sa;
+    uint32_t L;
+    int64_t i;
+    uint32_t R;
+};
+typedef void (*ref_init_fn)(struct ref_exact_iter *, void *, const uint8_t *);
+
+struct ref_job {
+    ref_init_fn init;
+    void *table;
+    const uint8_t *pat;
+    uint32_t m;
+    uint64_t begin, end;
+    uint32_t *outL, *outR;
+};
+
+static void *ref_worker(void *arg)
+{
+    struct ref_job *j = arg;
+    uint8_t *buf = malloc((size_t)j->m + 1);
+    for (uint64_t p = j->begin; p < j->end; ++p) {
+        memcpy(buf, j->pat + p * j->m, j->m);
+        buf[j->m] = 0;
+        struct ref_exact_iter it;
+        j->init(&it, j->table, buf);
+        j->outL[p] = it.L;
+        j->outR[p] = it.R;
+    }
+    free(buf);
+    return 0;
+}
+
+void oracle_ref_search_threads(void *init_fn, void *table, const uint8_t *pat, uint32_t m,
+                               uint64_t npat, uint32_t threads, uint32_t *outL, uint32_t *outR)
+{
+    if (threads < 1)
+        threads = 1;
+    if (threads > 256)
+        threads = 256;
+    pthread_t tid[256];
+    struct ref_job jobs[256];
+    for (uint32_t t = 0; t < threads; ++t) {
+        struct ref_job j = {(ref_init_fn)init_fn, table, pat, m, npat * t / threads,
+                            npat * (t + 1) / threads, outL, outR};
+        jobs[t] = j;
+        pthread_create(&tid[t], 0, ref_worker, &jobs[t]);
+    }
+    for (uint32_t t = 0; t < threads; ++t)
+        pthread_join(tid[t], 0);
+}

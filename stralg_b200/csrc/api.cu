@@ -17,6 +17,8 @@ struct b200sa_index {
     int prof_n = 0;
 };
 
+namespace b200sa { unsigned long long g_kernel_launches = 0; }
+
 static thread_local std::string g_last_error;
 
 static int fail(enum b200sa_error code, const std::string &msg, enum b200sa_error *err) {
@@ -217,6 +219,10 @@ int b200sa_copy_lcp(const b200sa_index *idx, uint32_t *host) {
 int b200sa_copy_bwt(const b200sa_index *idx, uint8_t *host) {
     return copy_out(idx, idx ? idx->ix.bwt.ptr : nullptr, host, idx ? (size_t)idx->ix.len : 0, "BWT");
 }
+int b200sa_copy_occ(const b200sa_index *idx, uint8_t *host) {
+    return copy_out(idx, idx ? idx->ix.occ.ptr : nullptr, host, idx ? idx->ix.occ.bytes() : 0, "O table");
+}
+uint64_t b200sa_launch_count(void) { return b200sa::g_kernel_launches; }
 int b200sa_copy_c_table(const b200sa_index *idx, uint32_t *host) {
     if (!idx || !host) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
     memcpy(host, idx->ix.c_host, (size_t)idx->ix.sigma * 4);

@@ -27,7 +27,13 @@ struct CudaFailure : public std::runtime_error {
         if (_e != cudaSuccess) throw ::b200sa::CudaFailure(_e, #expr, __FILE__, __LINE__); \
     } while (0)
 
-#define KERNEL_CHECK() CUDA_CHECK(cudaGetLastError())
+// every kernel launch of the library is counted (b200sa_launch_count, bench.py "gpu_launches")
+extern unsigned long long g_kernel_launches;
+#define KERNEL_CHECK()                      \
+    do {                                    \
+        ++::b200sa::g_kernel_launches;      \
+        CUDA_CHECK(cudaGetLastError());     \
+    } while (0)
 
 // Stream-ordered device buffer.  The default mempool keeps freed blocks (release threshold is
 // raised to "never" in api.cu), so steady-state builds do not pay cudaMalloc.

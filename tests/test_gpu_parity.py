@@ -53,11 +53,14 @@ def test_suffix_array_tables_match_oracle(engine, oracle, ref, case, radix_bits,
     monkeypatch.setenv("B200SA_RADIX_BITS", str(radix_bits))
     name, sym, sigma = case
     codes = np.concatenate([np.asarray(sym, dtype=np.uint8), np.zeros(1, np.uint8)])
-    idx = engine.SuffixArrayIndex.build(codes[:-1], sigma, isa=True, bwt=True, occ=True)
+    idx = engine.SuffixArrayIndex.build(codes[:-1], sigma, isa=True, lcp=True, bwt=True, occ=True)
     sa_exp = expected_sa(oracle, ref, codes, sigma)
     sa = idx.sa()
     assert np.array_equal(sa, sa_exp), f"{name}: first mismatch at {np.nonzero(sa != sa_exp)[0][:5]}"
     assert np.array_equal(idx.isa(), oracle.inverse(sa_exp))
+    lcp_exp = oracle.lcp(codes, sa_exp)
+    lcp = idx.lcp()
+    assert np.array_equal(lcp, lcp_exp), f"{name}: LCP mismatch at {np.nonzero(lcp != lcp_exp)[0][:5]}"
     bwt_exp = oracle.bwt(codes, sa_exp)
     assert np.array_equal(idx.bwt(), bwt_exp)
     assert np.array_equal(idx.c_table(), oracle.c_table(codes, sigma))
@@ -83,9 +86,10 @@ def test_golden_fixtures(engine, golden):
     for name in golden_cases(golden):
         codes = golden[f"{name}/codes"]
         sigma = int(golden[f"{name}/sigma"][0])
-        idx = engine.SuffixArrayIndex.build(codes[:-1], sigma, isa=True, bwt=True, occ=True)
+        idx = engine.SuffixArrayIndex.build(codes[:-1], sigma, isa=True, lcp=True, bwt=True, occ=True)
         assert np.array_equal(idx.sa(), golden[f"{name}/sa"]), name
         assert np.array_equal(idx.isa(), golden[f"{name}/isa"]), name
+        assert np.array_equal(idx.lcp(), golden[f"{name}/lcp"]), name
         if f"{name}/c" in golden.files:
             assert np.array_equal(idx.c_table(), golden[f"{name}/c"]), name
         if f"{name}/o" in golden.files:
