@@ -130,6 +130,10 @@ int b200sa_synth_reads(const uint8_t *d_text, uint64_t n, uint32_t nsym, uint8_t
                        int device, void *stream);
 
 int b200sa_device_count(void);
+/* The build workspace (a few large device allocations) persists per device between builds so that
+ * steady-state builds never call cudaMalloc; release it explicitly when memory is needed. */
+uint64_t b200sa_workspace_bytes(int device);
+int b200sa_release_workspace(int device);
 /* kernels launched by this library in this process so far (bench accounting) */
 uint64_t b200sa_launch_count(void);
 

@@ -49,6 +49,9 @@ static enum b200sa_error code_of(cudaError_t e) {
         return fail(B200SA_ERR_INTERNAL, e.what(), errptr);                      \
     }
 
+static Arena g_arena[64];
+static std::mutex g_arena_mu[64];
+
 static void use_device(int device) {
     CUDA_CHECK(cudaSetDevice(device));
     static std::mutex mu;
@@ -100,23 +103,35 @@ __attribute__((visibility("hidden"))) static int build_into(b200sa_index *h, con
         CUDA_CHECK(cudaMemsetAsync(ix.text.ptr + n, 0, 1, st));
         ix.text_ptr = ix.text.ptr;
     }
+    // one build at a time per device: the workspace arena is shared and persistent
+    std::lock_guard<std::mutex> arena_lock(g_arena_mu[device & 63]);
+    Arena &arena = g_arena[device & 63];
+    arena.reset();
+    arena.reserve_first(build_workspace_estimate(ix.len, ix.pk.bits));
+    ix.arena = &arena;
+
     DevBuf<int> d_err(1, st);
     CUDA_CHECK(cudaMemsetAsync(d_err.ptr, 0, 4, st));
     pack_text(ix, d_err.ptr);
     int herr = 0;
     CUDA_CHECK(cudaMemcpyAsync(&herr, d_err.ptr, 4, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    if (herr) return fail(B200SA_ERR_BAD_SYMBOL, "text holds a code outside 1..sigma-1", err);
+    if (herr) {
+        ix.arena = nullptr;
+        return fail(B200SA_ERR_BAD_SYMBOL, "text holds a code outside 1..sigma-1", err);
+    }
     ix.text.release();  // everything downstream reads the packed text
     ix.text_ptr = nullptr;
 
-    const bool want_lcp = flags & B200SA_BUILD_LCP;
-    const bool want_isa = (flags & B200SA_BUILD_ISA) || want_lcp;
-    build_suffix_array(ix, want_isa);
-    if (want_lcp) build_lcp(ix);
-    if (!(flags & B200SA_BUILD_ISA)) ix.isa.release();
-    if (flags & (B200SA_BUILD_OCC | B200SA_BUILD_BWT)) build_bwt_tables(ix, flags & B200SA_BUILD_BWT);
-    ix.packed.release();
+    const bool want_tables = flags & (B200SA_BUILD_OCC | B200SA_BUILD_BWT);
+    Arena::Mark after_pack = arena.mark();
+    build_suffix_array(ix, want_tables);
+    arena.release_to(after_pack);  // the sort workspace is dead; LCP reuses it (same stream)
+    if (flags & B200SA_BUILD_ISA) build_inverse(ix);
+    if (flags & B200SA_BUILD_LCP) build_lcp(ix);
+    if (flags & B200SA_BUILD_OCC) build_bwt_tables(ix, flags & B200SA_BUILD_BWT);
+    ix.packed = nullptr;
+    ix.arena = nullptr;
     if (flags & B200SA_DROP_SA) ix.sa.release();
     CUDA_CHECK(cudaStreamSynchronize(st));
     if (flags & B200SA_PROFILE) {
@@ -223,6 +238,15 @@ int b200sa_copy_occ(const b200sa_index *idx, uint8_t *host) {
     return copy_out(idx, idx ? idx->ix.occ.ptr : nullptr, host, idx ? idx->ix.occ.bytes() : 0, "O table");
 }
 uint64_t b200sa_launch_count(void) { return b200sa::g_kernel_launches; }
+uint64_t b200sa_workspace_bytes(int device) { return g_arena[device & 63].reserved(); }
+int b200sa_release_workspace(int device) {
+    API_GUARD_BEGIN
+    CUDA_CHECK(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lock(g_arena_mu[device & 63]);
+    g_arena[device & 63].release_all();
+    return 0;
+    API_GUARD_END(nullptr)
+}
 int b200sa_copy_c_table(const b200sa_index *idx, uint32_t *host) {
     if (!idx || !host) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
     memcpy(host, idx->ix.c_host, (size_t)idx->ix.sigma * 4);

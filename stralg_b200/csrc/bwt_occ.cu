@@ -12,42 +12,6 @@
 
 namespace b200sa {
 
-__device__ __forceinline__ u32 packed_code(const u64 *__restrict__ packed, u32 t, int bits) {
-    // code (1..sigma-1) of text position t
-    u64 bitpos = (u64)t * bits;
-    u64 w = packed[bitpos >> 6];
-    unsigned sh = 64 - bits - (unsigned)(bitpos & 63);
-    return (u32)((w >> sh) & ((1u << bits) - 1u)) + 1u;
-}
-
-// 4 rows per thread; primary[0] receives the row with sa[r] == 0
-__global__ void __launch_bounds__(256) bwt_gather_kernel(const u32 *__restrict__ sa, const u64 *__restrict__ packed,
-                                                         u32 len, int bits, u8 *__restrict__ bwt,
-                                                         u32 *__restrict__ primary) {
-    u64 r0 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (r0 >= len) return;
-    u32 s[4];
-    if (r0 + 4 <= len) {
-        uint4 v = ld_stream_u128(sa + r0);
-        s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
-    } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) s[q] = r0 + q < len ? sa[r0 + q] : 1u;
-    }
-    u32 out = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        u32 code = 0;
-        if (r0 + q < len) {
-            if (s[q] == 0) *primary = (u32)(r0 + q);
-            else code = packed_code(packed, s[q] - 1, bits);
-        }
-        out |= code << (8 * q);
-    }
-    // bwt buffer is padded to a multiple of 64 bytes
-    *(u32 *)(bwt + r0) = out;
-}
-
 // ---- OCC_DNA32 --------------------------------------------------------------------------------
 static constexpr int OD_NT = 256;  // blocks per tile
 
@@ -239,18 +203,11 @@ void occ_dense(const DeviceIndex &ix, u32 *d_out) {
 
 // ---- host orchestration -----------------------------------------------------------------------
 void build_bwt_tables(DeviceIndex &ix, bool keep_bwt) {
+    // ix.bwt (rows padded to a multiple of 64 with zeros) and ix.primary come from the SA build
     cudaStream_t st = ix.stream;
     const u32 len = ix.len;
-    size_t bwt_bytes = (((size_t)len + 63) / 64 + 1) * 64;
-    DevBuf<u8> bwt(bwt_bytes, st);
-    DevBuf<u32> d_primary(1, st);
-    CUDA_CHECK(cudaMemsetAsync(bwt.ptr + (bwt_bytes - 128), 0, 128, st));
-    int t = ix.timer.begin("bwt_gather", (double)len * 6.0);
-    bwt_gather_kernel<<<div_up_u(((u64)len + 3) / 4, 256), 256, 0, st>>>(ix.sa.ptr, ix.packed.ptr, len, ix.pk.bits,
-                                                                          bwt.ptr, d_primary.ptr);
-    KERNEL_CHECK();
-    ix.timer.end(t);
-    CUDA_CHECK(cudaMemcpyAsync(&ix.primary, d_primary.ptr, 4, cudaMemcpyDeviceToHost, st));
+    DevBuf<u8> &bwt = ix.bwt;
+    int t;
 
     const u64 nblocks = (u64)len / 64 + 1;  // O(a, len) may address one block past the last row
     ix.occ_blocks = nblocks;
@@ -284,8 +241,7 @@ void build_bwt_tables(DeviceIndex &ix, bool keep_bwt) {
         KERNEL_CHECK();
     }
     ix.timer.end(t);
-    CUDA_CHECK(cudaStreamSynchronize(st));  // primary is now valid on the host
-    if (keep_bwt) ix.bwt = std::move(bwt);
+    if (!keep_bwt) ix.bwt.release();
 }
 
 }  // namespace b200sa

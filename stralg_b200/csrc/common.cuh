@@ -76,6 +76,72 @@ struct DevBuf {
     size_t bytes() const { return count * sizeof(T); }
 };
 
+// Build workspace: a few large device allocations that persist across builds (per device) and
+// are carved with a bump pointer, so a steady-state build issues no cudaMalloc at all and the
+// driver never has to re-map physical pages between differently sized requests.
+struct Arena {
+    struct Chunk {
+        u8 *base;
+        size_t cap, top;
+    };
+    static const int MAX_CHUNKS = 16;
+    Chunk chunks[MAX_CHUNKS];
+    int nchunks = 0;
+    void reset() {
+        for (int i = 0; i < nchunks; ++i) chunks[i].top = 0;
+    }
+    // make sure the FIRST chunk can hold `bytes` (called before anything is carved)
+    void reserve_first(size_t bytes) {
+        bytes = (bytes + ((size_t)64 << 20)) & ~(((size_t)1 << 20) - 1);
+        if (nchunks > 0 && chunks[0].cap >= bytes) return;
+        release_all();
+        u8 *p = nullptr;
+        CUDA_CHECK(cudaMalloc((void **)&p, bytes));
+        chunks[0] = Chunk{p, bytes, 0};
+        nchunks = 1;
+    }
+    void *alloc(size_t bytes) {
+        bytes = (bytes + 511) & ~(size_t)511;
+        for (int i = 0; i < nchunks; ++i)
+            if (chunks[i].top + bytes <= chunks[i].cap) {
+                void *p = chunks[i].base + chunks[i].top;
+                chunks[i].top += bytes;
+                return p;
+            }
+        if (nchunks == MAX_CHUNKS) throw std::runtime_error("workspace arena exhausted");
+        size_t cap = (bytes + ((size_t)256 << 20)) & ~(((size_t)1 << 20) - 1);
+        u8 *p = nullptr;
+        CUDA_CHECK(cudaMalloc((void **)&p, cap));
+        chunks[nchunks] = Chunk{p, cap, bytes};
+        return chunks[nchunks++].base;
+    }
+    template <typename T>
+    T *get(size_t count) { return (T *)alloc(count * sizeof(T)); }
+    struct Mark {
+        size_t tops[MAX_CHUNKS];
+        int n;
+    };
+    Mark mark() const {
+        Mark m;
+        m.n = nchunks;
+        for (int i = 0; i < nchunks; ++i) m.tops[i] = chunks[i].top;
+        return m;
+    }
+    void release_to(const Mark &m) {
+        for (int i = 0; i < nchunks; ++i) chunks[i].top = i < m.n ? m.tops[i] : 0;
+    }
+    void release_all() {
+        if (nchunks) cudaDeviceSynchronize();
+        for (int i = 0; i < nchunks; ++i) cudaFree(chunks[i].base);
+        nchunks = 0;
+    }
+    size_t reserved() const {
+        size_t t = 0;
+        for (int i = 0; i < nchunks; ++i) t += chunks[i].cap;
+        return t;
+    }
+};
+
 static inline unsigned div_up_u(u64 a, u64 b) { return (unsigned)((a + b - 1) / b); }
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }

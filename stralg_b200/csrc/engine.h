@@ -37,7 +37,8 @@ struct DeviceIndex {
     // owned device arrays (may be null when not requested / released)
     DevBuf<u8> text;        // len bytes of codes (text[n] = 0), only when we own a copy
     const u8 *text_ptr = nullptr;
-    DevBuf<u64> packed;     // packed text, padded with >= 2 zero words
+    u64 *packed = nullptr;  // packed text (workspace arena), padded with zero words
+    Arena *arena = nullptr; // per-device build workspace (valid during the build only)
     DevBuf<u32> sa, isa, lcp;
     DevBuf<u8> bwt;
     DevBuf<u32> c_table;    // sigma entries (device)
@@ -54,7 +55,9 @@ struct DeviceIndex {
 
 // sa_build.cu
 void pack_text(DeviceIndex &ix, int *d_err);
-void build_suffix_array(DeviceIndex &ix, bool keep_isa);
+size_t build_workspace_estimate(u32 len, int bits);
+void build_suffix_array(DeviceIndex &ix, bool want_bwt);  // fills ix.sa (+ ix.bwt, ix.primary)
+void build_inverse(DeviceIndex &ix);
 // lcp.cu
 void build_lcp(DeviceIndex &ix);
 // bwt_occ.cu

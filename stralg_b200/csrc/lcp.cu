@@ -49,7 +49,8 @@ static constexpr int T1_WORDS = 4;  // words compared by the per-position thread
 __global__ void __launch_bounds__(256) plcp_irreducible_kernel(const u64 *__restrict__ packed, int bits, u32 n,
                                                                const u32 *__restrict__ phi, u32 *__restrict__ v,
                                                                LongPair *__restrict__ queue,
-                                                               unsigned long long *__restrict__ queue_count) {
+                                                               unsigned long long *__restrict__ queue_count,
+                                                               u64 queue_cap) {
     u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx > n) return;
     const u32 i = (u32)idx;
@@ -81,10 +82,21 @@ __global__ void __launch_bounds__(256) plcp_irreducible_kernel(const u64 *__rest
     }
     if (!done) {
         unsigned long long slot = atomicAdd(queue_count, 1ull);
-        queue[slot].i = i;
-        queue[slot].matched = l;
-        v[i] = i;  // placeholder (defined); plcp_long_kernel writes the final value
-        return;
+        if (slot < queue_cap) {
+            queue[slot].i = i;
+            queue[slot].matched = l;
+            v[i] = i;  // placeholder (defined); plcp_long_kernel writes the final value
+            return;
+        }
+        // queue full (cannot happen within the 2 n log n bound, kept for safety): finish here
+        while (l < maxl) {
+            u64 x = lcp_window(packed, (u64)i + l, bits) ^ lcp_window(packed, (u64)j + l, bits);
+            if (x) {
+                l += (u32)(__clzll((long long)x) / bits);
+                break;
+            }
+            l += cpw;
+        }
     }
     v[i] = (l < maxl ? l : maxl) + i;
 }
@@ -92,11 +104,12 @@ __global__ void __launch_bounds__(256) plcp_irreducible_kernel(const u64 *__rest
 __global__ void __launch_bounds__(256) plcp_long_kernel(const u64 *__restrict__ packed, int bits, u32 n,
                                                         const u32 *__restrict__ phi, u32 *__restrict__ v,
                                                         const LongPair *__restrict__ queue,
-                                                        const unsigned long long *__restrict__ queue_count) {
+                                                        const unsigned long long *__restrict__ queue_count,
+                                                        u64 queue_cap) {
     __shared__ u32 wmin[8];
     __shared__ u32 result;
     const int cpw = 64 / bits;
-    const u64 count = *queue_count;
+    const u64 count = *queue_count < queue_cap ? *queue_count : queue_cap;
     for (u64 q = blockIdx.x; q < count; q += gridDim.x) {
         const u32 i = queue[q].i;
         const u32 j = phi[i];
@@ -235,40 +248,41 @@ void build_lcp(DeviceIndex &ix) {
     cudaStream_t st = ix.stream;
     const u32 len = ix.len, n = ix.n;
     const int bits = ix.pk.bits;
-    DevBuf<u32> phi(len, st), v(len, st);
+    Arena &ar = *ix.arena;
+    u32 *phi = ar.get<u32>(len), *v = ar.get<u32>(len);
     int t = ix.timer.begin("lcp_phi", (double)len * 8.0);
-    phi_kernel<<<div_up_u(len, 256), 256, 0, st>>>(ix.sa.ptr, len, phi.ptr);
+    phi_kernel<<<div_up_u(len, 256), 256, 0, st>>>(ix.sa.ptr, len, phi);
     KERNEL_CHECK();
     ix.timer.end(t);
 
     // every queued pair consumed T1_WORDS full words first, and irreducible LCPs sum to at most
     // 2 n log2 n symbols, which bounds the queue; len entries is a safe (and simple) capacity
-    DevBuf<LongPair> queue(len, st);
-    DevBuf<unsigned long long> qcount(1, st);
-    CUDA_CHECK(cudaMemsetAsync(qcount.ptr, 0, 8, st));
+    const u64 qcap = (u64)len / 2 + 1024;
+    LongPair *queue = ar.get<LongPair>(qcap);
+    unsigned long long *qcount = ar.get<unsigned long long>(1);
+    CUDA_CHECK(cudaMemsetAsync(qcount, 0, 8, st));
     t = ix.timer.begin("lcp_irreducible", (double)len * 8.0);
-    plcp_irreducible_kernel<<<div_up_u((u64)n + 1, 256), 256, 0, st>>>(ix.packed.ptr, bits, n, phi.ptr, v.ptr,
-                                                                       queue.ptr, qcount.ptr);
+    plcp_irreducible_kernel<<<div_up_u((u64)n + 1, 256), 256, 0, st>>>(ix.packed, bits, n, phi, v,
+                                                                       queue, qcount, qcap);
     KERNEL_CHECK();
-    plcp_long_kernel<<<148 * 4, 256, 0, st>>>(ix.packed.ptr, bits, n, phi.ptr, v.ptr, queue.ptr, qcount.ptr);
+    plcp_long_kernel<<<148 * 4, 256, 0, st>>>(ix.packed, bits, n, phi, v, queue, qcount, qcap);
     KERNEL_CHECK();
     ix.timer.end(t);
 
     t = ix.timer.begin("lcp_fill", (double)len * 8.0);
     u32 ntiles = div_up_u(len, FL_TILE);
-    DevBuf<u32> tile_last(ntiles, st);
-    plcp_tile_last_kernel<<<ntiles, FL_NT, 0, st>>>(v.ptr, len, tile_last.ptr);
+    u32 *tile_last = ar.get<u32>(ntiles);
+    plcp_tile_last_kernel<<<ntiles, FL_NT, 0, st>>>(v, len, tile_last);
     KERNEL_CHECK();
-    plcp_scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_last.ptr, ntiles);
+    plcp_scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_last, ntiles);
     KERNEL_CHECK();
-    plcp_fill_kernel<<<ntiles, FL_NT, 0, st>>>(v.ptr, len, tile_last.ptr);
+    plcp_fill_kernel<<<ntiles, FL_NT, 0, st>>>(v, len, tile_last);
     KERNEL_CHECK();
     ix.timer.end(t);
 
-    phi.release();
     ix.lcp.alloc(len, st);
     t = ix.timer.begin("lcp_gather", (double)len * 12.0);
-    lcp_gather_kernel<<<div_up_u(len, 256), 256, 0, st>>>(ix.sa.ptr, v.ptr, len, ix.lcp.ptr);
+    lcp_gather_kernel<<<div_up_u(len, 256), 256, 0, st>>>(ix.sa.ptr, v, len, ix.lcp.ptr);
     KERNEL_CHECK();
     ix.timer.end(t);
 }

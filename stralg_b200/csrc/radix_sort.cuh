@@ -9,6 +9,7 @@
 // scatters of stralg/sa_is.c:203-263; none of that code is reused.
 #pragma once
 #include "common.cuh"
+#include <cstdlib>
 
 namespace b200sa {
 namespace rs {
@@ -99,7 +100,8 @@ struct PassCfg {
     static constexpr int TILE = NT * IPT;
     static constexpr int WARPS = NT / 32;
     static constexpr int DPT = (BINS + NT - 1) / NT;  // digits owned per thread
-    static constexpr size_t SMEM = (size_t)TILE * 8 + (size_t)TILE * 4 + (size_t)WARPS * BINS * 2 +
+    static constexpr int RBATCH = IPT % 6 == 0 ? 6 : 4;  // items ranked per match/atomic/shuffle batch
+    static constexpr size_t SMEM = (size_t)TILE * 8 + (size_t)TILE * 4 + (size_t)WARPS * BINS * 4 +
                                    (size_t)BINS * 4 * 2 + 64 * 4;
 };
 
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(NT) onesweep_pass_kernel(const u64 *__restrict
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *keys_s = (u64 *)smem_raw;
     u32 *vals_s = (u32 *)(keys_s + TILE);
-    u16 *warp_hist = (u16 *)(vals_s + TILE);       // [WARPS][BINS]
+    u32 *warp_hist = (u32 *)(vals_s + TILE);       // [WARPS][BINS]
     u32 *tile_start = (u32 *)(warp_hist + WARPS * BINS);  // [BINS]
     u32 *adj = tile_start + BINS;                  // [BINS]
     u32 *misc = adj + BINS;                        // [64]: warp totals, tile id
@@ -123,8 +125,8 @@ __global__ void __launch_bounds__(NT) onesweep_pass_kernel(const u64 *__restrict
     if (tid == 0) misc[63] = atomicAdd(ticket, 1u);
     // zero this warp's histogram row
     {
-        u32 *row32 = (u32 *)(warp_hist + warp * BINS);
-        for (int i = lane; i < BINS / 2; i += 32) row32[i] = 0;
+        u32 *row32 = warp_hist + warp * BINS;
+        for (int i = lane; i < BINS; i += 32) row32[i] = 0;
     }
     __syncthreads();
     const u32 tile = misc[63];
@@ -140,22 +142,34 @@ __global__ void __launch_bounds__(NT) onesweep_pass_kernel(const u64 *__restrict
         k[j] = idx < n ? ld_stream_u64(kin + idx) : ~0ull;
     }
     // ---- per-warp stable ranking ----
-    u16 *myhist = warp_hist + warp * BINS;
+    // Batches of RBATCH items keep several match / shared-atomic / shuffle chains in flight.
+    // The shared atomics of one warp retire in program order (and __syncwarp orders them between
+    // lanes), so an earlier item always receives the smaller offset: the ranking is stable.
+    u32 *myhist = warp_hist + warp * BINS;
     u32 pos[IPT];
     const unsigned lt = lanemask_lt();
+    constexpr int RBATCH = Cfg::RBATCH;
 #pragma unroll
-    for (int j = 0; j < IPT; ++j) {
-        u32 d = (u32)(k[j] >> shift) & digit_mask;
-        unsigned peers = __match_any_sync(0xffffffffu, d);
-        int leader = __ffs(peers) - 1;
-        u32 before = 0;
-        if ((int)lane == leader) {
-            before = myhist[d];
-            myhist[d] = (u16)(before + __popc(peers));
+    for (int j0 = 0; j0 < IPT; j0 += RBATCH) {
+        unsigned peers[RBATCH];
+        u32 dg[RBATCH], before[RBATCH];
+#pragma unroll
+        for (int b = 0; b < RBATCH; ++b) {
+            dg[b] = (u32)(k[j0 + b] >> shift) & digit_mask;
+            peers[b] = __match_any_sync(0xffffffffu, dg[b]);
         }
-        before = __shfl_sync(0xffffffffu, before, leader);
-        pos[j] = before + __popc(peers & lt);
-        __syncwarp();
+#pragma unroll
+        for (int b = 0; b < RBATCH; ++b) {
+            before[b] = 0;
+            if ((peers[b] & lt) == 0) before[b] = atomicAdd(&myhist[dg[b]], (u32)__popc(peers[b]));
+            __syncwarp();
+        }
+#pragma unroll
+        for (int b = 0; b < RBATCH; ++b) {
+            int leader = __ffs(peers[b]) - 1;
+            before[b] = __shfl_sync(0xffffffffu, before[b], leader);
+            pos[j0 + b] = before[b] + __popc(peers[b] & lt);
+        }
     }
     __syncthreads();
 
@@ -170,7 +184,7 @@ __global__ void __launch_bounds__(NT) onesweep_pass_kernel(const u64 *__restrict
 #pragma unroll
             for (int w = 0; w < WARPS; ++w) {
                 u32 c = warp_hist[w * BINS + d];
-                warp_hist[w * BINS + d] = (u16)run;
+                warp_hist[w * BINS + d] = run;
                 run += c;
             }
             // publish this tile's count right away so later tiles can make progress
@@ -224,13 +238,24 @@ __global__ void __launch_bounds__(NT) onesweep_pass_kernel(const u64 *__restrict
         if (d < BINS) {
             u32 excl = 0;
             if (tile > 0) {
+                // LB_UNROLL predecessors are fetched per step so their L2 latencies overlap
+                constexpr int LB_UNROLL = 8;
                 int t = (int)tile - 1;
-                while (true) {
-                    u64 s = ld_relaxed_u64(lookback + (size_t)t * BINS + d);
-                    if ((s >> 62) == 0) continue;
-                    excl += (u32)(s & LB_VALUE_MASK);
-                    if (s & LB_PREFIX) break;
-                    --t;
+                bool done = false;
+                while (!done) {
+                    u64 sv[LB_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < LB_UNROLL; ++u)
+                        sv[u] = t - u >= 0 ? ld_relaxed_u64(lookback + (size_t)(t - u) * BINS + d) : LB_PREFIX;
+#pragma unroll
+                    for (int u = 0; u < LB_UNROLL; ++u) {
+                        if (done) break;
+                        u64 sx = sv[u];
+                        while ((sx >> 62) == 0) sx = ld_relaxed_u64(lookback + (size_t)(t - u) * BINS + d);
+                        excl += (u32)(sx & LB_VALUE_MASK);
+                        if (sx & LB_PREFIX) done = true;
+                    }
+                    t -= LB_UNROLL;
                 }
                 st_relaxed_u64(lookback + (size_t)tile * BINS + d, LB_PREFIX | (u64)(excl + cnt[q]));
             }
@@ -265,18 +290,49 @@ struct SortPlan {
 
 template <int RB>
 struct Sorter {
-    static constexpr int NT = RB <= 8 ? 512 : 256;
-    static constexpr int IPT = RB <= 8 ? 12 : 16;
-    typedef PassCfg<RB, NT, IPT> Cfg;
     static constexpr int BINS = 1 << RB;
 
-    static size_t lookback_words(u32 n) { return (size_t)div_up_u(n, Cfg::TILE) * BINS; }
+    // pass-kernel shape: selectable with B200SA_PASS_CFG for tuning runs
+    static int cfg_id() {
+        static int id = -1;
+        if (id < 0) {
+            const char *e = getenv("B200SA_PASS_CFG");
+            id = e && *e ? atoi(e) : 0;
+            if (id < 0 || id > 3) id = 0;
+        }
+        return id;
+    }
+    static int tile_size() {
+        switch (cfg_id()) {
+            case 1: return 512 * 12;
+            case 2: return 256 * 16;
+            case 3: return 384 * 12;
+            default: return 256 * 12;
+        }
+    }
+    static size_t lookback_words(u32 n) { return (size_t)div_up_u(n, 256 * 12) * BINS; }
+
+    template <int NT, int IPT>
+    static void launch_pass(const u64 *kin, const u32 *vin, u64 *kout, u32 *vout, u32 n, int shift, u32 mask,
+                            const u32 *digit_base, u64 *lookback, u32 *ticket, cudaStream_t st) {
+        typedef PassCfg<RB, NT, IPT> Cfg;
+        static bool configured = false;
+        if (!configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(onesweep_pass_kernel<RB, NT, IPT>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+            configured = true;
+        }
+        unsigned tiles = div_up_u(n, Cfg::TILE);
+        CUDA_CHECK(cudaMemsetAsync(lookback, 0, (size_t)tiles * BINS * 8, st));
+        CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, st));
+        onesweep_pass_kernel<RB, NT, IPT><<<tiles, NT, Cfg::SMEM, st>>>(kin, vin, kout, vout, n, shift, mask,
+                                                                         digit_base, lookback, ticket);
+        KERNEL_CHECK();
+    }
 
     static void configure() {
         static bool done = false;
         if (done) return;
-        CUDA_CHECK(cudaFuncSetAttribute(onesweep_pass_kernel<RB, NT, IPT>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(hist_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         8 * BINS * 4));
         done = true;
@@ -302,14 +358,13 @@ struct Sorter {
     // One pass; digit_base = the scanned histogram row of this pass.
     static void pass(const u64 *kin, const u32 *vin, u64 *kout, u32 *vout, u32 n, int shift, int bits,
                      const u32 *digit_base, u64 *lookback, u32 *ticket, cudaStream_t st) {
-        configure();
-        unsigned tiles = div_up_u(n, Cfg::TILE);
-        CUDA_CHECK(cudaMemsetAsync(lookback, 0, (size_t)tiles * BINS * 8, st));
-        CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, st));
         u32 mask = bits >= RB ? (u32)(BINS - 1) : ((1u << bits) - 1u);
-        onesweep_pass_kernel<RB, NT, IPT><<<tiles, NT, Cfg::SMEM, st>>>(kin, vin, kout, vout, n, shift, mask,
-                                                                         digit_base, lookback, ticket);
-        KERNEL_CHECK();
+        switch (cfg_id()) {
+            case 1: launch_pass<512, 12>(kin, vin, kout, vout, n, shift, mask, digit_base, lookback, ticket, st); break;
+            case 2: launch_pass<256, 16>(kin, vin, kout, vout, n, shift, mask, digit_base, lookback, ticket, st); break;
+            case 3: launch_pass<384, 12>(kin, vin, kout, vout, n, shift, mask, digit_base, lookback, ticket, st); break;
+            default: launch_pass<256, 12>(kin, vin, kout, vout, n, shift, mask, digit_base, lookback, ticket, st); break;
+        }
     }
 };
 

@@ -192,34 +192,83 @@ __global__ void __launch_bounds__(256) round0_bases_kernel(const u32 *__restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// make_keys0: element j -> suffix s (short suffixes first, shortest first), key = first K symbols.
+// Round-0 key layout (u64):
+//   bits [0, K*b)            the first K packed symbols of suffix s (zero padded past the text end)
+//   bits [PREV_SHIFT, 64)    code of the PRECEDING symbol (text[s-1], 0 for s == 0), b+1 bits;
+//                            above every sorted digit, so it rides along for free and rank0
+//                            emits the BWT (stralg/bwt.c:13-20) without a gather
 // ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int prev_shift_for(int bits) { return 64 - (bits + 1); }
+
+// make_keys0: element j -> suffix s (short suffixes first, shortest first).
 __global__ void __launch_bounds__(256) make_keys0_kernel(const u64 *__restrict__ packed, u32 n, u32 len, int K,
                                                          int bits, u64 *__restrict__ keys, u32 *__restrict__ vals) {
     const u32 nshort = (u32)K < len ? (u32)K : len;
     const int keybits = K * bits;
+    const int pshift = prev_shift_for(bits);
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < len; j += stride) {
         u32 s = j < nshort ? n - (u32)j : (u32)j - nshort;
-        u64 win = window_at(packed, s, bits);
-        keys[j] = win >> (64 - keybits);
+        u64 key;
+        if (s == 0) {
+            key = window_at(packed, 0, bits) >> (64 - keybits);
+        } else {
+            // one window holds the preceding symbol and the K key symbols ((K+1)*b <= 64)
+            u64 win = window_at(packed, (u64)s - 1, bits);
+            u64 prev_code = (win >> (64 - bits)) + 1;
+            key = ((win << bits) >> (64 - keybits)) | (prev_code << pshift);
+        }
+        keys[j] = key;
         vals[j] = s;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
+// Lazy ranks.  After round 0 only suffixes in non-singleton buckets ("active") get rank[] written
+// and their bit set in `valid`.  The rank of any other suffix t is its position in the round-0
+// order, recovered on demand by a binary search of its K-symbol key in the sorted key array.
+// Short suffixes (window reaches the sentinel) stand first inside an equal-key run, shortest
+// first, and are singletons; a long singleton stands right after them.
+// ---------------------------------------------------------------------------------------------
+struct LazyRank {
+    const u32 *rank;
+    const u32 *valid;      // null: rank[] is complete (dense mode)
+    const u64 *keys0;      // round-0 sorted keys
+    const u32 *sa0;        // suffix array (round-0 order is final at singleton positions)
+    const u64 *packed;
+    u64 keymask;
+    u32 n, len;
+    int K, bits;
+};
+
+__device__ __forceinline__ u32 lazy_rank_of(const LazyRank &lr, u32 t) {
+    if (lr.valid == nullptr || ((lr.valid[t >> 5] >> (t & 31)) & 1u)) return lr.rank[t];
+    const u64 key = window_at(lr.packed, t, lr.bits) >> (64 - lr.K * lr.bits);
+    u32 lo = 0, hi = lr.len;  // first index with keys0 >= key
+    while (lo < hi) {
+        u32 mid = lo + (hi - lo) / 2;
+        if ((lr.keys0[mid] & lr.keymask) < key) lo = mid + 1;
+        else hi = mid;
+    }
+    const bool t_short = (u64)t + (u64)lr.K > (u64)lr.n;
+    if (t_short) {
+        while (lr.sa0[lo] != t) ++lo;
+    } else {
+        while ((u64)lr.sa0[lo] + (u64)lr.K > (u64)lr.n) ++lo;
+    }
+    return lo;
+}
+
 // make_keys_round: key = (rank[s] << lo_bits) | rank[s + h] for the active suffixes.
 // Active suffixes share their first h symbols with another suffix, hence s + h <= n.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) make_keys_round_kernel(const u32 *__restrict__ act, u32 m,
-                                                              const u32 *__restrict__ rank, u64 h, u32 len,
+__global__ void __launch_bounds__(256) make_keys_round_kernel(const u32 *__restrict__ act, u32 m, LazyRank lr, u64 h,
                                                               int lo_bits, u64 *__restrict__ keys) {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
         u32 s = act[j];
         u64 t = (u64)s + h;
-        u64 lo = t < len ? (u64)rank[t] : 0ull;
-        keys[j] = ((u64)rank[s] << lo_bits) | lo;
+        u64 lo = t < lr.len ? (u64)lazy_rank_of(lr, (u32)t) : 0ull;
+        keys[j] = ((u64)lr.rank[s] << lo_bits) | lo;
     }
 }
 
@@ -229,8 +278,10 @@ __global__ void __launch_bounds__(256) make_keys_round_kernel(const u32 *__restr
 //   jb = first index of the element's group, jh = first index with the element's full key
 //   SA position of element j      = hi + (j - jb)      (hi = group value = SA index of the bucket)
 //   new rank of its suffix        = hi + (jh - jb)
-// Round 0 (K > 0): suffixes whose K-window reaches the sentinel are forced into singleton
-// buckets (they were fed first, so they already stand ahead of their padded-equal neighbours).
+// Round 0 (K0 > 0): suffixes whose K-window reaches the sentinel are forced into singleton
+// buckets (they were fed first, so they already stand ahead of their padded-equal neighbours);
+// ranks are written for active suffixes only (all suffixes when scatter_all), BWT rows come from
+// the key's top bits.  Later rounds write SA, rank and BWT rows of every active suffix.
 // headbits: bit (j & 7) of byte j >> 3 is set when j starts a new bucket.
 // ---------------------------------------------------------------------------------------------
 static constexpr int RK_NT = 256;
@@ -239,12 +290,11 @@ static constexpr int RK_TILE = RK_NT * RK_IPT;
 
 __device__ __forceinline__ u64 group_of(u64 key, int gs) { return gs >= 64 ? 0ull : key >> gs; }
 
-// first index f <= start with cmp(keys[f..start]) all equal to x under shift gs
-__device__ u32 gallop_first_equal(const u64 *__restrict__ keys, u32 start, u64 x, int gs) {
-    // precondition: (keys[start] >> gs) == x
+// first index f <= start such that ((keys[f..start] & mask) >> gs) all equal x
+__device__ u32 gallop_first_equal(const u64 *__restrict__ keys, u32 start, u64 x, int gs, u64 mask) {
     u64 lo = start;
     u64 step = 1;
-    while (lo >= step && (keys[lo - step] >> gs) == x) {
+    while (lo >= step && ((keys[lo - step] & mask) >> gs) == x) {
         lo -= step;
         step <<= 1;
     }
@@ -252,25 +302,48 @@ __device__ u32 gallop_first_equal(const u64 *__restrict__ keys, u32 start, u64 x
     int64_t good = (int64_t)lo;
     while (good - bad > 1) {
         int64_t mid = bad + (good - bad) / 2;
-        if ((keys[mid] >> gs) == x) good = mid;
+        if (((keys[mid] & mask) >> gs) == x) good = mid;
         else bad = mid;
     }
     return (u32)good;
 }
 
-__global__ void __launch_bounds__(RK_NT) rank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ vals, u32 m,
-                                                     int gs, int K0, u32 n, u32 *__restrict__ rank,
-                                                     u32 *__restrict__ sa_out, u8 *__restrict__ headbits) {
+struct RankArgs {
+    const u64 *keys;
+    const u32 *vals;
+    u32 m;
+    int gs;          // group shift (>= 64 in round 0)
+    u64 keymask;     // bits that take part in comparisons
+    int K0;          // round 0: symbols in the key; 0 in later rounds
+    u32 n;
+    u32 *rank;
+    u32 *valid;      // round 0, lazy mode: bitmap of suffixes whose rank[] is maintained
+    int scatter_all; // round 0, dense mode: write every rank, touch nothing else
+    u32 *sa_out;     // later rounds
+    u8 *headbits;
+    u8 *bwt;         // optional
+    int prev_shift;  // round 0: where the preceding code sits in the key
+    const u64 *packed;
+    int bits;
+    u32 *primary;
+};
+
+__global__ void __launch_bounds__(RK_NT) rank_kernel(RankArgs a) {
     __shared__ u32 warp_s[RK_NT / 32], warp_b[RK_NT / 32];
     __shared__ u32 carry_s, carry_b;
+    const u64 *__restrict__ keys = a.keys;
+    const u32 *__restrict__ vals = a.vals;
+    const u32 m = a.m, n = a.n;
+    const int gs = a.gs, K0 = a.K0;
+    const u64 mask = a.keymask;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const u64 tile_base = (u64)blockIdx.x * RK_TILE;
     const u64 j0 = tile_base + (u64)tid * RK_IPT;
 
     u64 k[RK_IPT];
     u32 s[RK_IPT];
-    u64 kprev = 0;
-    u32 sprev = 0;
+    u64 kprev = 0, knext = 0;
+    u32 sprev = 0, snext = 0;
     if (j0 + RK_IPT <= m) {
         const uint4 *kp = (const uint4 *)(keys + j0);
 #pragma unroll
@@ -296,6 +369,11 @@ __global__ void __launch_bounds__(RK_NT) rank_kernel(const u64 *__restrict__ key
         kprev = keys[j0 - 1];
         sprev = vals[j0 - 1];
     }
+    const bool has_next = j0 + RK_IPT < m;
+    if (has_next) {
+        knext = keys[j0 + RK_IPT];
+        snext = vals[j0 + RK_IPT];
+    }
 
     // ---- flags and thread-local running heads (tile-local index + 1; 0 = none yet) ----
     u32 hs_idx[RK_IPT], hb_idx[RK_IPT];
@@ -308,8 +386,8 @@ __global__ void __launch_bounds__(RK_NT) rank_kernel(const u64 *__restrict__ key
         for (int q = 0; q < RK_IPT; ++q) {
             u64 j = j0 + q;
             bool valid = j < m;
-            bool hs = (j == 0) || (k[q] != pk);
-            bool hb = (j == 0) || (group_of(k[q], gs) != group_of(pk, gs));
+            bool hs = (j == 0) || ((k[q] & mask) != (pk & mask));
+            bool hb = (j == 0) || (group_of(k[q] & mask, gs) != group_of(pk & mask, gs));
             if (K0 > 0 && j > 0) {
                 bool sh_cur = (u64)s[q] + (u64)K0 > (u64)n;
                 bool sh_prev = (u64)ps + (u64)K0 > (u64)n;
@@ -326,7 +404,14 @@ __global__ void __launch_bounds__(RK_NT) rank_kernel(const u64 *__restrict__ key
             ps = s[q];
         }
     }
-    if (j0 < m) headbits[j0 >> 3] = (u8)bits;
+    // is the element after this thread's last one a bucket head? (end of list counts as one)
+    bool next_head = true;
+    if (has_next) {
+        next_head = (knext & mask) != (k[RK_IPT - 1] & mask);
+        if (K0 > 0)
+            next_head = next_head || ((u64)snext + (u64)K0 > (u64)n) || ((u64)s[RK_IPT - 1] + (u64)K0 > (u64)n);
+    }
+    if (!a.scatter_all && j0 < m) a.headbits[j0 >> 3] = (u8)bits;
 
     // ---- carry-in for the tile (only when its first element does not start a bucket) ----
     if (tid == 0) {
@@ -335,14 +420,14 @@ __global__ void __launch_bounds__(RK_NT) rank_kernel(const u64 *__restrict__ key
             bool first_is_hs = bits & 1u;
             bool first_is_hb = hb_idx[0] != 0;
             if (!first_is_hs) {
-                u32 f = gallop_first_equal(keys, (u32)tile_base, k[0], 0);
+                u32 f = gallop_first_equal(keys, (u32)tile_base, k[0] & mask, 0, mask);
                 if (K0 > 0) {
                     // short suffixes stand first inside an equal-key run and are singletons
                     while ((u64)vals[f] + (u64)K0 > (u64)n) ++f;
                 }
                 cs = f;
             }
-            if (!first_is_hb && gs < 64) cb = gallop_first_equal(keys, (u32)tile_base, k[0] >> gs, gs);
+            if (!first_is_hb && gs < 64) cb = gallop_first_equal(keys, (u32)tile_base, (k[0] & mask) >> gs, gs, mask);
         }
         carry_s = cs;
         carry_b = cb;
@@ -363,7 +448,6 @@ __global__ void __launch_bounds__(RK_NT) rank_kernel(const u64 *__restrict__ key
         warp_s[warp] = ex_s;
         warp_b[warp] = ex_b;
     }
-    // exclusive within the warp
     u32 pre_s = __shfl_up_sync(0xffffffffu, ex_s, 1);
     u32 pre_b = __shfl_up_sync(0xffffffffu, ex_b, 1);
     if (lane == 0) pre_s = pre_b = 0;
@@ -374,6 +458,7 @@ __global__ void __launch_bounds__(RK_NT) rank_kernel(const u64 *__restrict__ key
     }
     const u32 cs = carry_s, cb = carry_b;
 
+    u64 bwt8 = 0;
 #pragma unroll
     for (int q = 0; q < RK_IPT; ++q) {
         u64 j = j0 + q;
@@ -382,9 +467,40 @@ __global__ void __launch_bounds__(RK_NT) rank_kernel(const u64 *__restrict__ key
         u32 lb = hb_idx[q] ? hb_idx[q] : pre_b;
         u64 jh = ls ? tile_base + ls - 1 : (u64)cs;
         u64 jb = gs >= 64 ? 0ull : (lb ? tile_base + lb - 1 : (u64)cb);
-        u64 hi = group_of(k[q], gs);
-        rank[s[q]] = (u32)(hi + (jh - jb));
-        if (sa_out) sa_out[(u32)(hi + (j - jb))] = s[q];
+        u64 hi = group_of(k[q] & mask, gs);
+        u32 newrank = (u32)(hi + (jh - jb));
+        if (K0 > 0) {
+            // round 0
+            bool head_here = (bits >> q) & 1u;
+            bool head_after = q + 1 < RK_IPT ? (j + 1 >= m || ((bits >> (q + 1)) & 1u)) : next_head;
+            bool active = !(head_here && head_after);
+            if (a.scatter_all) {
+                a.rank[s[q]] = newrank;
+            } else {
+                if (active) {
+                    a.rank[s[q]] = newrank;
+                    atomicOr(&a.valid[s[q] >> 5], 1u << (s[q] & 31));
+                }
+                bwt8 |= ((k[q] >> a.prev_shift) & 0xffull) << (8 * q);
+                if (s[q] == 0) *a.primary = (u32)j;
+            }
+        } else {
+            u32 pos = (u32)(hi + (j - jb));
+            a.rank[s[q]] = newrank;
+            a.sa_out[pos] = s[q];
+            if (s[q] == 0) {
+                *a.primary = pos;
+                if (a.bwt) a.bwt[pos] = 0;
+            } else if (a.bwt) {
+                u64 bitpos = (u64)(s[q] - 1) * a.bits;
+                u64 w = a.packed[bitpos >> 6];
+                a.bwt[pos] = (u8)(((w >> (64 - a.bits - (unsigned)(bitpos & 63))) & ((1u << a.bits) - 1u)) + 1u);
+            }
+        }
+    }
+    if (K0 > 0 && !a.scatter_all && a.bwt && j0 < m) {
+        // the BWT buffer is padded to a multiple of 64 rows, so the 8-byte store is always in range
+        *(u64 *)(a.bwt + j0) = bwt8;
     }
 }
 
@@ -496,26 +612,33 @@ static int env_int(const char *name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
+size_t build_workspace_estimate(u32 len, int bits) {
+    // packed text + round-0 keys (2 x 8) + one value buffer + ranks + look-back + bitmaps, with slack
+    size_t l = len;
+    return l * bits / 8 + 16 * l + 4 * l + 4 * l + l / 2 + ((size_t)div_up_u(len, 256 * 12) * 1024 * 8) +
+           ((size_t)128 << 20);
+}
+
 void pack_text(DeviceIndex &ix, int *d_err) {
     cudaStream_t st = ix.stream;
     const int b = ix.pk.bits, cpw = ix.pk.cpw;
     u64 nwords_data = ((u64)ix.len + cpw - 1) / cpw;  // words holding positions 0..n
     u64 nwords = nwords_data + 4;                      // zero padding for window reads
-    ix.packed.alloc(nwords, st);
-    DevBuf<unsigned long long> counts(256, st);
-    CUDA_CHECK(cudaMemsetAsync(counts.ptr, 0, 256 * 8, st));
+    ix.packed = ix.arena->get<u64>(nwords);
+    unsigned long long *counts = ix.arena->get<unsigned long long>(256);
+    CUDA_CHECK(cudaMemsetAsync(counts, 0, 256 * 8, st));
     int tid = ix.timer.begin("pack_text", (double)ix.len * (1.0 + b / 8.0));
     unsigned blocks = div_up_u(nwords, 256);
     switch (b) {
-        case 1: pack_kernel<1><<<blocks, 256, 0, st>>>(ix.text_ptr, ix.n, ix.sigma, nwords, ix.packed.ptr, counts.ptr, d_err); break;
-        case 2: pack_kernel<2><<<blocks, 256, 0, st>>>(ix.text_ptr, ix.n, ix.sigma, nwords, ix.packed.ptr, counts.ptr, d_err); break;
-        case 4: pack_kernel<4><<<blocks, 256, 0, st>>>(ix.text_ptr, ix.n, ix.sigma, nwords, ix.packed.ptr, counts.ptr, d_err); break;
-        default: pack_kernel<8><<<blocks, 256, 0, st>>>(ix.text_ptr, ix.n, ix.sigma, nwords, ix.packed.ptr, counts.ptr, d_err); break;
+        case 1: pack_kernel<1><<<blocks, 256, 0, st>>>(ix.text_ptr, ix.n, ix.sigma, nwords, ix.packed, counts, d_err); break;
+        case 2: pack_kernel<2><<<blocks, 256, 0, st>>>(ix.text_ptr, ix.n, ix.sigma, nwords, ix.packed, counts, d_err); break;
+        case 4: pack_kernel<4><<<blocks, 256, 0, st>>>(ix.text_ptr, ix.n, ix.sigma, nwords, ix.packed, counts, d_err); break;
+        default: pack_kernel<8><<<blocks, 256, 0, st>>>(ix.text_ptr, ix.n, ix.sigma, nwords, ix.packed, counts, d_err); break;
     }
     KERNEL_CHECK();
     ix.timer.end(tid);
     unsigned long long hc[256];
-    CUDA_CHECK(cudaMemcpyAsync(hc, counts.ptr, sizeof hc, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(hc, counts, sizeof hc, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     // C table (stralg/bwt.c:35-45): the sentinel is the single occurrence of code 0
     for (int i = 0; i < 256; ++i) ix.sym_counts_host[i] = hc[i];
@@ -535,42 +658,38 @@ static void launch_cmer_hist(const DeviceIndex &ix, u64 nwords_data, u32 *hist, 
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks == 0) blocks = 1;
     switch (ix.pk.bits) {
-        case 1: cmer_hist_kernel<RB, 1><<<blocks, 256, 0, st>>>(ix.packed.ptr, ix.n, nwords_data, hist); break;
-        case 2: cmer_hist_kernel<RB, 2><<<blocks, 256, 0, st>>>(ix.packed.ptr, ix.n, nwords_data, hist); break;
-        case 4: cmer_hist_kernel<RB, 4><<<blocks, 256, 0, st>>>(ix.packed.ptr, ix.n, nwords_data, hist); break;
-        default: cmer_hist_kernel<RB, 8><<<blocks, 256, 0, st>>>(ix.packed.ptr, ix.n, nwords_data, hist); break;
+        case 1: cmer_hist_kernel<RB, 1><<<blocks, 256, 0, st>>>(ix.packed, ix.n, nwords_data, hist); break;
+        case 2: cmer_hist_kernel<RB, 2><<<blocks, 256, 0, st>>>(ix.packed, ix.n, nwords_data, hist); break;
+        case 4: cmer_hist_kernel<RB, 4><<<blocks, 256, 0, st>>>(ix.packed, ix.n, nwords_data, hist); break;
+        default: cmer_hist_kernel<RB, 8><<<blocks, 256, 0, st>>>(ix.packed, ix.n, nwords_data, hist); break;
     }
     KERNEL_CHECK();
 }
 
-struct ActiveSet {
-    u32 m;
-};
-
-// headbits -> compacted list of still-active suffixes (in current SA order)
-static u32 compact_active(DeviceIndex &ix, const u8 *headbits, const u32 *vals, u32 m, DevBuf<u32> &tile_counts,
-                          unsigned long long *d_total, DevBuf<u32> &out, cudaStream_t st) {
+// headbits -> compacted list of still-active suffixes (in current SA order); returns the count
+static u32 count_active(const u8 *headbits, u32 m, u32 *tile_counts, unsigned long long *d_total, cudaStream_t st) {
     u32 ntiles = div_up_u(m, CP_TILE);
-    if (tile_counts.count < ntiles) tile_counts.alloc(ntiles, st);
-    count_active_kernel<<<ntiles, CP_NT, 0, st>>>(headbits, m, tile_counts.ptr);
+    count_active_kernel<<<ntiles, CP_NT, 0, st>>>(headbits, m, tile_counts);
     KERNEL_CHECK();
-    scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_counts.ptr, ntiles, d_total);
+    scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_counts, ntiles, d_total);
     KERNEL_CHECK();
     unsigned long long total = 0;
     CUDA_CHECK(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    if (total == 0) return 0;
-    if (out.count < total) out.alloc(total, st);
-    scatter_active_kernel<<<ntiles, CP_NT, 0, st>>>(headbits, vals, m, tile_counts.ptr, out.ptr);
-    KERNEL_CHECK();
     return (u32)total;
+}
+static void scatter_active(const u8 *headbits, const u32 *vals, u32 m, const u32 *tile_offsets, u32 *out,
+                           cudaStream_t st) {
+    scatter_active_kernel<<<div_up_u(m, CP_TILE), CP_NT, 0, st>>>(headbits, vals, m, tile_offsets, out);
+    KERNEL_CHECK();
 }
 
 template <int RB>
-static void build_sa_impl(DeviceIndex &ix, bool keep_isa) {
+static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
     typedef rs::Sorter<RB> S;
     constexpr int BINS = 1 << RB;
     cudaStream_t st = ix.stream;
+    Arena &ar = *ix.arena;
     const u32 n = ix.n, len = ix.len;
     const int b = ix.pk.bits, cpw = ix.pk.cpw;
     const int c = RB / b;  // symbols per digit
@@ -582,11 +701,13 @@ static void build_sa_impl(DeviceIndex &ix, bool keep_isa) {
     if (eff < 0.5) eff = 0.5;
     int margin = env_int("B200SA_KEY_MARGIN", 8);
     int P0 = (int)std::ceil((log2len + margin) / (c * eff));
-    int maxP = 64 / RB;
+    const int pshift = prev_shift_for(b);
+    int maxP = pshift / RB;  // the preceding-symbol field sits above the sorted digits
     P0 = std::max(1, std::min(P0, maxP));
     P0 = env_int("B200SA_PASSES0", P0);
     P0 = std::max(1, std::min(P0, maxP));
     const int K = c * P0;
+    const u64 keymask0 = (K * b >= 64) ? ~0ull : ((1ull << (K * b)) - 1ull);
     ix.stats.k0 = K;
     ix.stats.radix_bits = RB;
     ix.stats.passes0 = P0;
@@ -594,131 +715,176 @@ static void build_sa_impl(DeviceIndex &ix, bool keep_isa) {
     ix.stats.sorted_total = len;
     ix.stats.passes_elems = (u64)len * P0;
 
-    // ---- buffers ----
-    DevBuf<u64> keysA(len, st), keysB(len, st);
-    DevBuf<u32> valsA(len, st), valsB(len, st);
-    DevBuf<u32> rank(len, st);
-    DevBuf<u64> lookback(S::lookback_words(len), st);
-    DevBuf<u32> hist((size_t)8 * BINS, st), uniform(8, st), ticket(1, st);
+    // ---- outputs (stream-ordered allocations that outlive the build) ----
+    ix.sa.alloc(len, st);
+    size_t bwt_bytes = (((size_t)len + 63) / 64 + 1) * 64;
+    if (want_bwt) {
+        ix.bwt.alloc(bwt_bytes, st);
+        CUDA_CHECK(cudaMemsetAsync(ix.bwt.ptr + (bwt_bytes - 128), 0, 128, st));
+    }
+    DevBuf<u32> d_primary(1, st);
+
+    // ---- workspace ----
+    u64 *keysA = ar.get<u64>(len), *keysB = ar.get<u64>(len);
+    u32 *valsV = ar.get<u32>(len);
+    u32 *rank = ar.get<u32>(len);
+    size_t valid_words = ((size_t)len + 31) / 32 + 2;
+    u32 *valid = ar.get<u32>(valid_words);
+    u64 *lookback = ar.get<u64>(S::lookback_words(len));
+    u32 *hist = ar.get<u32>((size_t)8 * BINS), *uniform = ar.get<u32>(8), *ticket = ar.get<u32>(1);
+    u32 *bases0 = ar.get<u32>((size_t)P0 * BINS);
     size_t hb_bytes = (((size_t)len + 63) / 64 + 2) * 8;
-    DevBuf<u8> headbits(hb_bytes, st);
-    DevBuf<u32> tile_counts(div_up_u(len, CP_TILE), st);
-    DevBuf<unsigned long long> d_total(1, st);
+    u8 *headbits = ar.get<u8>(hb_bytes);
+    u32 *tile_counts = ar.get<u32>(div_up_u(len, CP_TILE) + 1);
+    unsigned long long *d_total = ar.get<unsigned long long>(1);
 
     // ---- round 0 ----
     u64 nwords_data = ((u64)len + cpw - 1) / cpw;
     int t;
     t = ix.timer.begin("cmer_hist", (double)len * b / 8.0);
-    CUDA_CHECK(cudaMemsetAsync(hist.ptr, 0, (size_t)BINS * 4, st));
-    launch_cmer_hist<RB>(ix, nwords_data, hist.ptr, st);
-    DevBuf<u32> bases0((size_t)P0 * BINS, st);
-    round0_bases_kernel<RB><<<P0, 256, 0, st>>>(hist.ptr, ix.packed.ptr, n, K, b, bases0.ptr);
+    CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)BINS * 4, st));
+    launch_cmer_hist<RB>(ix, nwords_data, hist, st);
+    round0_bases_kernel<RB><<<P0, 256, 0, st>>>(hist, ix.packed, n, K, b, bases0);
     KERNEL_CHECK();
     ix.timer.end(t);
 
+    // the value ping-pong is arranged so that the last pass writes straight into the SA output
+    u64 *kin = keysA, *kout = keysB;
+    u32 *vin = (P0 % 2) ? valsV : ix.sa.ptr;
+    u32 *vout = (P0 % 2) ? ix.sa.ptr : valsV;
     t = ix.timer.begin("make_keys0", (double)len * 12.0);
-    {
-        unsigned blocks = div_up_u(len, 256 * 4);
-        make_keys0_kernel<<<blocks, 256, 0, st>>>(ix.packed.ptr, n, len, K, b, keysA.ptr, valsA.ptr);
-        KERNEL_CHECK();
-    }
+    make_keys0_kernel<<<div_up_u(len, 256 * 4), 256, 0, st>>>(ix.packed, n, len, K, b, kin, vin);
+    KERNEL_CHECK();
     ix.timer.end(t);
-
-    u64 *kin = keysA.ptr, *kout = keysB.ptr;
-    u32 *vin = valsA.ptr, *vout = valsB.ptr;
     for (int p = 0; p < P0; ++p) {
         t = ix.timer.begin("radix_pass0", (double)len * 24.0);
-        S::pass(kin, vin, kout, vout, len, p * RB, RB, bases0.ptr + (size_t)p * BINS, lookback.ptr, ticket.ptr, st);
+        S::pass(kin, vin, kout, vout, len, p * RB, RB, bases0 + (size_t)p * BINS, lookback, ticket, st);
         ix.timer.end(t);
         std::swap(kin, kout);
         std::swap(vin, vout);
     }
-    // sorted data now in (kin, vin)
+    u32 *sa = ix.sa.ptr;  // == vin
+    const u64 *keys0 = kin;
+
     t = ix.timer.begin("rank0", (double)len * 16.0);
-    CUDA_CHECK(cudaMemsetAsync(headbits.ptr, 0, hb_bytes, st));
-    rank_kernel<<<div_up_u(len, RK_TILE), RK_NT, 0, st>>>(kin, vin, len, 64, K, n, rank.ptr, nullptr, headbits.ptr);
+    CUDA_CHECK(cudaMemsetAsync(headbits, 0, hb_bytes, st));
+    CUDA_CHECK(cudaMemsetAsync(valid, 0, valid_words * 4, st));
+    RankArgs ra{};
+    ra.keys = keys0; ra.vals = sa; ra.m = len; ra.gs = 64; ra.keymask = keymask0; ra.K0 = K; ra.n = n;
+    ra.rank = rank; ra.valid = valid; ra.scatter_all = 0; ra.sa_out = nullptr; ra.headbits = headbits;
+    ra.bwt = want_bwt ? ix.bwt.ptr : nullptr; ra.prev_shift = pshift; ra.packed = ix.packed; ra.bits = b;
+    ra.primary = d_primary.ptr;
+    rank_kernel<<<div_up_u(len, RK_TILE), RK_NT, 0, st>>>(ra);
     KERNEL_CHECK();
     ix.timer.end(t);
 
-    // the sorted value buffer becomes the suffix array
-    DevBuf<u32> sa_buf, spare_vals;
-    if (vin == valsA.ptr) {
-        sa_buf = std::move(valsA);
-        spare_vals = std::move(valsB);
-    } else {
-        sa_buf = std::move(valsB);
-        spare_vals = std::move(valsA);
-    }
-    u32 *sa = sa_buf.ptr;
-
-    DevBuf<u32> act;  // active suffixes
     t = ix.timer.begin("compact0", (double)len * 0.125);
-    u32 m = compact_active(ix, headbits.ptr, sa, len, tile_counts, d_total.ptr, spare_vals, st);
+    u32 m = count_active(headbits, len, tile_counts, d_total, st);
+    u32 *act = valsV, *act2 = nullptr;  // valsV is free once the sort is done
+    if (m) scatter_active(headbits, sa, len, tile_counts, act, st);
     ix.timer.end(t);
-    act = std::move(spare_vals);
-    DevBuf<u32> act2;
 
     // ---- doubling rounds over the active set ----
-    const int lo_bits = std::max(1, log2len);
-    const int key_bits = std::min(64, 2 * lo_bits);
-    u64 h = (u64)K;
-    u32 huniform[8];
-    while (m > 0) {
-        ix.stats.rounds++;
-        ix.stats.sorted_total += m;
-        if (act2.count < m) act2.alloc(m, st);
-        t = ix.timer.begin("round_keys", (double)m * 20.0);
-        make_keys_round_kernel<<<std::max(1u, std::min(div_up_u(m, 256 * 4), 148u * 16u)), 256, 0, st>>>(
-            act.ptr, m, rank.ptr, h, len, lo_bits, keysA.ptr);
-        KERNEL_CHECK();
-        ix.timer.end(t);
-        int npass = (key_bits + RB - 1) / RB;
-        t = ix.timer.begin("round_hist", (double)m * 8.0);
-        S::histogram(keysA.ptr, m, 0, key_bits, npass, hist.ptr, st);
-        S::scan(hist.ptr, m, npass, uniform.ptr, st);
-        CUDA_CHECK(cudaMemcpyAsync(huniform, uniform.ptr, (size_t)npass * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
-        ix.timer.end(t);
-        kin = keysA.ptr; kout = keysB.ptr;
-        vin = act.ptr; vout = act2.ptr;
-        for (int p = 0; p < npass; ++p) {
-            if (huniform[p]) continue;
-            int bits_here = std::min(RB, key_bits - p * RB);
-            t = ix.timer.begin("radix_pass", (double)m * 24.0);
-            S::pass(kin, vin, kout, vout, m, p * RB, bits_here, hist.ptr + (size_t)p * BINS, lookback.ptr, ticket.ptr, st);
+    if (m) {
+        const bool dense = (u64)m * 8 > (u64)len;
+        LazyRank lr{};
+        lr.rank = rank; lr.valid = valid; lr.keys0 = keys0; lr.sa0 = sa; lr.packed = ix.packed;
+        lr.keymask = keymask0; lr.n = n; lr.len = len; lr.K = K; lr.bits = b;
+        u64 *rkA, *rkB;
+        if (dense) {
+            // most suffixes are still active: materialise every rank, then the round-0 keys are dead
+            t = ix.timer.begin("rank0_fill", (double)len * 16.0);
+            RankArgs rf = ra;
+            rf.scatter_all = 1;
+            rank_kernel<<<div_up_u(len, RK_TILE), RK_NT, 0, st>>>(rf);
+            KERNEL_CHECK();
             ix.timer.end(t);
-            ix.stats.passes_elems += m;
-            std::swap(kin, kout);
-            std::swap(vin, vout);
+            lr.valid = nullptr;
+            rkA = keysA;
+            rkB = keysB;
+        } else {
+            rkA = ar.get<u64>(m);
+            rkB = ar.get<u64>(m);
         }
-        t = ix.timer.begin("round_rank", (double)m * 24.0);
-        size_t hbm = (((size_t)m + 63) / 64 + 2) * 8;
-        CUDA_CHECK(cudaMemsetAsync(headbits.ptr, 0, hbm, st));
-        rank_kernel<<<div_up_u(m, RK_TILE), RK_NT, 0, st>>>(kin, vin, m, lo_bits, 0, n, rank.ptr, sa, headbits.ptr);
-        KERNEL_CHECK();
-        ix.timer.end(t);
-        // next active set goes to whichever value buffer does not hold the sorted list
-        DevBuf<u32> &sorted_buf = (vin == act.ptr) ? act : act2;
-        DevBuf<u32> &other_buf = (vin == act.ptr) ? act2 : act;
-        t = ix.timer.begin("compact", (double)m * 4.0);
-        u32 m2 = compact_active(ix, headbits.ptr, sorted_buf.ptr, m, tile_counts, d_total.ptr, other_buf, st);
-        ix.timer.end(t);
-        if (&other_buf != &act) std::swap(act, act2);
-        m = m2;
-        h *= 2;
-        if (h > (u64)len * 2 + 2 && m > 0)
-            throw std::runtime_error("prefix doubling failed to converge (internal error)");
+        act2 = ar.get<u32>(m);
+        const int lo_bits = std::max(1, log2len);
+        const int key_bits = std::min(64, 2 * lo_bits);
+        u64 h = (u64)K;
+        u32 huniform[8];
+        while (m > 0) {
+            ix.stats.rounds++;
+            ix.stats.sorted_total += m;
+            t = ix.timer.begin("round_keys", (double)m * 20.0);
+            make_keys_round_kernel<<<std::max(1u, std::min(div_up_u(m, 256 * 4), 148u * 16u)), 256, 0, st>>>(
+                act, m, lr, h, lo_bits, rkA);
+            KERNEL_CHECK();
+            ix.timer.end(t);
+            int npass = (key_bits + RB - 1) / RB;
+            t = ix.timer.begin("round_hist", (double)m * 8.0);
+            S::histogram(rkA, m, 0, key_bits, npass, hist, st);
+            S::scan(hist, m, npass, uniform, st);
+            CUDA_CHECK(cudaMemcpyAsync(huniform, uniform, (size_t)npass * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            ix.timer.end(t);
+            u64 *rin = rkA, *rout = rkB;
+            u32 *ain = act, *aout = act2;
+            for (int p = 0; p < npass; ++p) {
+                if (huniform[p]) continue;
+                int bits_here = std::min(RB, key_bits - p * RB);
+                t = ix.timer.begin("radix_pass", (double)m * 24.0);
+                S::pass(rin, ain, rout, aout, m, p * RB, bits_here, hist + (size_t)p * BINS, lookback, ticket, st);
+                ix.timer.end(t);
+                ix.stats.passes_elems += m;
+                std::swap(rin, rout);
+                std::swap(ain, aout);
+            }
+            t = ix.timer.begin("round_rank", (double)m * 24.0);
+            size_t hbm = (((size_t)m + 63) / 64 + 2) * 8;
+            CUDA_CHECK(cudaMemsetAsync(headbits, 0, hbm, st));
+            RankArgs rr{};
+            rr.keys = rin; rr.vals = ain; rr.m = m; rr.gs = lo_bits; rr.keymask = ~0ull; rr.K0 = 0; rr.n = n;
+            rr.rank = rank; rr.valid = nullptr; rr.scatter_all = 0; rr.sa_out = sa; rr.headbits = headbits;
+            rr.bwt = want_bwt ? ix.bwt.ptr : nullptr; rr.prev_shift = 0; rr.packed = ix.packed; rr.bits = b;
+            rr.primary = d_primary.ptr;
+            rank_kernel<<<div_up_u(m, RK_TILE), RK_NT, 0, st>>>(rr);
+            KERNEL_CHECK();
+            ix.timer.end(t);
+            // next active set goes to whichever value buffer does not hold the sorted list
+            t = ix.timer.begin("compact", (double)m * 4.0);
+            u32 m2 = count_active(headbits, m, tile_counts, d_total, st);
+            if (m2) scatter_active(headbits, ain, m, tile_counts, aout, st);
+            ix.timer.end(t);
+            act = aout;
+            act2 = ain;
+            m = m2;
+            h *= 2;
+            if (h > (u64)len * 2 + 2 && m > 0)
+                throw std::runtime_error("prefix doubling failed to converge (internal error)");
+        }
     }
-
-    ix.sa = std::move(sa_buf);
-    if (keep_isa) ix.isa = std::move(rank);
+    CUDA_CHECK(cudaMemcpyAsync(&ix.primary, d_primary.ptr, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
-void build_suffix_array(DeviceIndex &ix, bool keep_isa) {
+void build_suffix_array(DeviceIndex &ix, bool want_bwt) {
     int rb = env_int("B200SA_RADIX_BITS", 8);
     // the digit must hold a whole number of packed symbols
-    if (rb == 10 && (10 % ix.pk.bits) == 0) build_sa_impl<10>(ix, keep_isa);
-    else build_sa_impl<8>(ix, keep_isa);
+    if (rb == 10 && (10 % ix.pk.bits) == 0) build_sa_impl<10>(ix, want_bwt);
+    else build_sa_impl<8>(ix, want_bwt);
+}
+
+// inverse suffix array on request (stralg/suffix_array.c:55-62): isa[sa[r]] = r
+__global__ void __launch_bounds__(256) inverse_kernel(const u32 *__restrict__ sa, u32 len, u32 *__restrict__ isa) {
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < len) isa[sa[r]] = (u32)r;
+}
+
+void build_inverse(DeviceIndex &ix) {
+    ix.isa.alloc(ix.len, ix.stream);
+    int t = ix.timer.begin("inverse", (double)ix.len * 8.0);
+    inverse_kernel<<<div_up_u(ix.len, 256), 256, 0, ix.stream>>>(ix.sa.ptr, ix.len, ix.isa.ptr);
+    KERNEL_CHECK();
+    ix.timer.end(t);
 }
 
 }  // namespace b200sa
