@@ -1,0 +1,138 @@
+/*
+ * stralg_compat.h -- drop-in declarations for the hot-path surface of mailund/stralg, served by
+ * the B200 engine (libstralg_b200.so, built from stralg_b200/csrc/compat.cpp on top of b200sa.h).
+ *
+ * Every name, argument list and struct layout below is the reference's (file:line cited, paths
+ * relative to the stralg checkout), so a caller compiled against stralg's own suffix_array.h /
+ * bwt.h / remap.h links against this library unchanged.  Only the hot path is covered: alphabet
+ * remap, the four suffix-array constructors (all served by ONE GPU constructor), inverse + LCP,
+ * the SA binary searches (host code over the copied array), BWT C/O tables, and the exact-match
+ * iterator.  The approximate iterator, suffix trees etc. are out of scope.
+ *
+ * Ownership follows the reference: arrays hanging off these structs are malloc()'d host memory,
+ * free_suffix_array() frees array/inverse/lcp with free(), the string is borrowed unless the
+ * *_complete_* variants are used (suffix_array.c:11-23, bwt.c:91-132).
+ * Failure convention: these signatures have no error channel (the reference never checks
+ * malloc either); on a CUDA failure the shim prints b200sa_last_error() to stderr and aborts.
+ */
+#ifndef STRALG_COMPAT_H
+#define STRALG_COMPAT_H
+
+#include <stdbool.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- remap.h:9-19 ------------------------------------------------------------------------ */
+struct remap_table {
+    uint32_t alphabet_size;
+    signed char table[256];
+    signed char rev_table[128];
+};
+struct remap_table *alloc_remap_table(const uint8_t *string);                 /* remap.h:21-23 */
+void init_remap_table(struct remap_table *table, const uint8_t *string);      /* remap.h:24-27 */
+void dealloc_remap_table(struct remap_table *table);                          /* remap.h:28-30 */
+void free_remap_table(struct remap_table *table);                             /* remap.h:31-33 */
+uint8_t *remap(uint8_t *output, const uint8_t *input, struct remap_table *table);      /* :43-47 */
+uint8_t *rev_remap(uint8_t *output, const uint8_t *input, struct remap_table *table);  /* :48-52 */
+uint8_t *remap_between(uint8_t *output, const uint8_t *from, const uint8_t *to,
+                       struct remap_table *table);                                     /* :54-59 */
+uint8_t *rev_remap_between(uint8_t *output, const uint8_t *from, const uint8_t *to,
+                           struct remap_table *table);                                 /* :60-65 */
+uint8_t *remap_between0(uint8_t *output, const uint8_t *from, const uint8_t *to,
+                        struct remap_table *table);                                    /* :66-71 */
+uint8_t *rev_remap_between0(uint8_t *output, const uint8_t *from, const uint8_t *to,
+                            struct remap_table *table);                                /* :72-77 */
+uint32_t remap_string(uint8_t *output, uint8_t *input);                                /* :83-86 */
+bool identical_remap_tables(const struct remap_table *a, const struct remap_table *b); /* :116-119 */
+
+/* ---- suffix_array.h:10-20 ----------------------------------------------------------------- */
+struct suffix_array {
+    uint8_t *string;   /* borrowed, NUL terminated */
+    uint32_t length;   /* strlen(string) + 1: the sentinel suffix is a real suffix */
+    uint32_t *array;
+    uint32_t *inverse; /* NULL until compute_inverse() */
+    uint32_t *lcp;     /* NULL until compute_lcp() */
+};
+/* suffix_array.h:22-41 -- four names, one GPU prefix-doubling constructor */
+struct suffix_array *qsort_sa_construction(uint8_t *string);
+struct suffix_array *skew_sa_construction(uint8_t *string);
+struct suffix_array *sa_is_construction(uint8_t *remapped_string, uint32_t alphabet_size);
+struct suffix_array *sa_is_mem_construction(uint8_t *remapped_string, uint32_t alphabet_size);
+void free_suffix_array(struct suffix_array *sa);                     /* suffix_array.h:45-47 */
+void free_complete_suffix_array(struct suffix_array *sa);            /* suffix_array.h:49-51 */
+void compute_inverse(struct suffix_array *sa);                       /* suffix_array.h:96-98 */
+void compute_lcp(struct suffix_array *sa);                           /* suffix_array.h:99-101 */
+bool identical_suffix_arrays(const struct suffix_array *sa1, const struct suffix_array *sa2);
+
+/* suffix_array.h:54-94 -- binary searches over the (host copy of the) suffix array */
+uint32_t lower_bound_search(struct suffix_array *sa, const uint8_t *key);
+uint32_t upper_bound_search(struct suffix_array *sa, const uint8_t *key);
+uint32_t lower_bound_k(struct suffix_array *sa, uint32_t k, uint8_t a, uint32_t L, uint32_t R);
+uint32_t upper_bound_k(struct suffix_array *sa, uint32_t k, uint8_t a, uint32_t L, uint32_t R);
+struct sa_match_iter {
+    struct suffix_array *sa;
+    uint32_t L;
+    uint32_t R;
+    uint32_t i;
+};
+struct sa_match {
+    uint32_t position;
+};
+void init_sa_match_iter(struct sa_match_iter *iter, const uint8_t *pattern, struct suffix_array *sa);
+bool next_sa_match(struct sa_match_iter *iter, struct sa_match *match);
+void dealloc_sa_match_iter(struct sa_match_iter *iter);
+
+/* ---- bwt.h:36-50 ---------------------------------------------------------------------------- */
+struct bwt_table {
+    struct remap_table *remap_table;
+    struct suffix_array *sa;
+    uint32_t *c_table;
+    uint32_t *o_table;     /* dense (length+1) x sigma, row-major by position; NULL when the   */
+    uint32_t **o_indices;  /* reference's own u32 size computation would overflow (bwt.c:50)   */
+    uint32_t *ro_table;
+    uint32_t **ro_indices;
+};
+#ifndef STRALG_COMPAT_NO_MACROS
+#define C(a) (bwt_table->c_table[(a)])
+#define O(a, i) (bwt_table->o_indices[i][a])
+#define RO(a, i) (bwt_table->ro_indices[i][a])
+#endif
+void init_bwt_table(struct bwt_table *bwt_table, struct suffix_array *sa, struct suffix_array *rsa,
+                    struct remap_table *remap_table);                               /* bwt.h:73-76 */
+struct bwt_table *alloc_bwt_table(struct suffix_array *sa, struct suffix_array *rsa,
+                                  struct remap_table *remap_table);                 /* bwt.h:97-99 */
+void dealloc_bwt_table(struct bwt_table *bwt_table);                                /* bwt.h:109 */
+void free_bwt_table(struct bwt_table *bwt_table);                                   /* bwt.h:119 */
+void completely_dealloc_bwt_table(struct bwt_table *bwt_table);                     /* bwt.h:129 */
+void completely_free_bwt_table(struct bwt_table *bwt_table);                        /* bwt.h:138 */
+struct bwt_table *build_complete_table(const uint8_t *string, bool include_reverse); /* bwt.h:156-160 */
+bool equivalent_bwt_tables(struct bwt_table *table1, struct bwt_table *table2);
+
+/* bwt.h:168-234 -- exact-match iterator (stack allocated by callers, so the layout is ABI) */
+struct bwt_exact_match_iter {
+    const struct suffix_array *sa;
+    uint32_t L;
+    int64_t i;
+    uint32_t R;
+};
+struct bwt_exact_match {
+    uint32_t pos;
+};
+void init_bwt_exact_match_iter(struct bwt_exact_match_iter *iter, struct bwt_table *bwt_table,
+                               const uint8_t *remapped_pattern);
+bool next_bwt_exact_match_iter(struct bwt_exact_match_iter *iter, struct bwt_exact_match *match);
+void dealloc_bwt_exact_match_iter(struct bwt_exact_match_iter *iter);
+
+/* ---- extension: the batched entry point a read mapper should call instead of one iterator per
+ * read (tools/readmappers/bwt_readmapper/bwt_readmapper.c:128-161 maps one read at a time). */
+void bwt_exact_match_batch(struct bwt_table *bwt_table, const uint8_t *remapped_patterns,
+                           const uint64_t *offsets, uint64_t npatterns, uint32_t *L, uint32_t *R);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STRALG_COMPAT_H */

@@ -42,6 +42,7 @@ class Stats(C.Structure):
 SIGNATURES = {
     "b200sa_build": (C.c_void_p, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p,
                                   C.POINTER(C.c_int)]),
+    "b200sa_extend": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "b200sa_free": (None, [C.c_void_p]),
     "b200sa_last_error": (C.c_char_p, []),
     "b200sa_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),

@@ -171,6 +171,50 @@ b200sa_index *b200sa_build(const uint8_t *codes, uint64_t n, uint32_t sigma, uin
     return h;
 }
 
+int b200sa_extend(b200sa_index *idx, const uint8_t *codes, uint32_t flags) {
+    if (!idx || (!codes && idx->ix.n)) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    DeviceIndex &ix = idx->ix;
+    if (!ix.sa.ptr) return fail(B200SA_ERR_NOT_BUILT, "suffix array was dropped (B200SA_DROP_SA)", nullptr);
+    const bool need_isa = (flags & B200SA_BUILD_ISA) && !ix.isa.ptr;
+    const bool need_lcp = (flags & B200SA_BUILD_LCP) && !ix.lcp.ptr;
+    const bool need_occ = (flags & B200SA_BUILD_OCC) && ix.occ_layout == OCC_NONE;
+    const bool need_bwt = ((flags & B200SA_BUILD_BWT) && !ix.bwt.ptr) || need_occ;
+    if (!need_isa && !need_lcp && !need_bwt) return 0;
+    API_GUARD_BEGIN
+    use_device(ix.device);
+    cudaStream_t st = ix.stream;
+    std::lock_guard<std::mutex> arena_lock(g_arena_mu[ix.device & 63]);
+    Arena &arena = g_arena[ix.device & 63];
+    arena.reset();
+    arena.reserve_first((size_t)ix.len * ix.pk.bits / 8 + (need_lcp ? (size_t)ix.len * 13 : 0) + ((size_t)64 << 20));
+    ix.arena = &arena;
+    if (flags & B200SA_TEXT_ON_DEVICE) {
+        ix.text_ptr = codes;
+    } else {
+        ix.text.alloc((size_t)ix.n + 1, st);
+        if (ix.n) CUDA_CHECK(cudaMemcpyAsync(ix.text.ptr, codes, ix.n, cudaMemcpyHostToDevice, st));
+        ix.text_ptr = ix.text.ptr;
+    }
+    DevBuf<int> d_err(1, st);
+    CUDA_CHECK(cudaMemsetAsync(d_err.ptr, 0, 4, st));
+    pack_text(ix, d_err.ptr);
+    ix.text.release();
+    ix.text_ptr = nullptr;
+    if (need_isa) build_inverse(ix);
+    if (need_lcp) build_lcp(ix);
+    if (need_bwt) {
+        const bool had_bwt = ix.bwt.ptr != nullptr;
+        if (!had_bwt) gather_bwt(ix);
+        if (need_occ) build_bwt_tables(ix, had_bwt || (flags & B200SA_BUILD_BWT));
+    }
+    ix.packed = nullptr;
+    ix.arena = nullptr;
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    idx->flags |= flags & (B200SA_BUILD_ISA | B200SA_BUILD_LCP | B200SA_BUILD_BWT | B200SA_BUILD_OCC);
+    return 0;
+    API_GUARD_END(nullptr)
+}
+
 void b200sa_free(b200sa_index *idx) {
     if (!idx) return;
     cudaSetDevice(idx->ix.device);

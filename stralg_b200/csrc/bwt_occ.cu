@@ -12,6 +12,46 @@
 
 namespace b200sa {
 
+// ---- BWT rows by gather (only for tables added to an existing SA; builds carry them in the keys) ----
+__global__ void __launch_bounds__(256) bwt_gather_kernel(const u32 *__restrict__ sa, const u64 *__restrict__ packed,
+                                                         u32 len, int bits, u8 *__restrict__ bwt,
+                                                         u32 *__restrict__ primary) {
+    u64 r0 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (r0 >= len) return;
+    u32 out = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        u32 code = 0;
+        if (r0 + q < len) {
+            u32 s = sa[r0 + q];
+            if (s == 0) {
+                *primary = (u32)(r0 + q);
+            } else {
+                u64 bitpos = (u64)(s - 1) * bits;
+                u64 w = packed[bitpos >> 6];
+                code = (u32)((w >> (64 - bits - (unsigned)(bitpos & 63))) & ((1u << bits) - 1u)) + 1u;
+            }
+        }
+        out |= code << (8 * q);
+    }
+    *(u32 *)(bwt + r0) = out;  // the buffer is padded to a multiple of 64 rows
+}
+
+void gather_bwt(DeviceIndex &ix) {
+    cudaStream_t st = ix.stream;
+    size_t bwt_bytes = (((size_t)ix.len + 63) / 64 + 1) * 64;
+    ix.bwt.alloc(bwt_bytes, st);
+    CUDA_CHECK(cudaMemsetAsync(ix.bwt.ptr + (bwt_bytes - 128), 0, 128, st));
+    DevBuf<u32> d_primary(1, st);
+    int t = ix.timer.begin("bwt_gather", (double)ix.len * 6.0);
+    bwt_gather_kernel<<<div_up_u(((u64)ix.len + 3) / 4, 256), 256, 0, st>>>(ix.sa.ptr, ix.packed, ix.len, ix.pk.bits,
+                                                                             ix.bwt.ptr, d_primary.ptr);
+    KERNEL_CHECK();
+    ix.timer.end(t);
+    CUDA_CHECK(cudaMemcpyAsync(&ix.primary, d_primary.ptr, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
 // ---- OCC_DNA32 --------------------------------------------------------------------------------
 static constexpr int OD_NT = 256;  // blocks per tile
 

@@ -1,0 +1,428 @@
+// compat.cpp -- libstralg_b200.so: the reference-named hot-path functions of mailund/stralg
+// (include/stralg_compat.h) implemented on top of the B200 engine's C ABI (include/b200sa.h).
+//
+// Every array these functions hand out is malloc()'d host memory with the reference's layout and
+// ownership; every computation that the reference does in sa_is.c / skew.c / suffix_array.c:55-85 /
+// bwt.c:22-89 / bwt.c:164-199 runs on the GPU.  A side registry maps each `struct suffix_array *`
+// to its device-resident index so that later calls (compute_lcp, init_bwt_table, the exact
+// iterator) reuse the suffix array already in HBM.  Host-only pieces: the alphabet remap
+// (remap.c), the SA binary searches (suffix_array.c:90-233, kept on the host by design, SURVEY
+// 8a row a16) and the comparison helpers.
+#include "../../include/b200sa.h"
+#define STRALG_COMPAT_NO_MACROS
+#include "../../include/stralg_compat.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
+
+namespace {
+
+std::mutex g_mu;
+std::unordered_map<const void *, b200sa_index *> g_index;  // struct suffix_array* -> device index
+
+[[noreturn]] void die(const char *where) {
+    fprintf(stderr, "stralg_b200: %s failed: %s\n", where, b200sa_last_error());
+    abort();
+}
+
+b200sa_index *lookup(const struct suffix_array *sa) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto it = g_index.find(sa);
+    return it == g_index.end() ? nullptr : it->second;
+}
+
+void remember(const struct suffix_array *sa, b200sa_index *idx) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_index[sa] = idx;
+}
+
+void forget(const struct suffix_array *sa) {
+    b200sa_index *idx = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        auto it = g_index.find(sa);
+        if (it != g_index.end()) {
+            idx = it->second;
+            g_index.erase(it);
+        }
+    }
+    b200sa_free(idx);
+}
+
+int device_id() {
+    const char *e = getenv("STRALG_B200_DEVICE");
+    return e && *e ? atoi(e) : 0;
+}
+
+// One GPU constructor behind the four reference names.
+struct suffix_array *construct(uint8_t *string, uint32_t sigma, const char *who) {
+    struct suffix_array *sa = (struct suffix_array *)malloc(sizeof *sa);
+    size_t n = strlen((const char *)string);
+    sa->string = string;
+    sa->length = (uint32_t)n + 1;  // suffix_array_internal.c:12
+    sa->array = (uint32_t *)malloc((size_t)sa->length * sizeof(uint32_t));
+    sa->inverse = nullptr;
+    sa->lcp = nullptr;
+    enum b200sa_error err;
+    b200sa_index *idx = b200sa_build(string, n, sigma, 0, device_id(), nullptr, &err);
+    if (!idx) die(who);
+    if (b200sa_copy_sa(idx, sa->array)) die(who);
+    remember(sa, idx);
+    return sa;
+}
+
+// The device index of `sa`; rebuilt from sa->string if the array did not come from us
+// (e.g. read_suffix_array) -- the result is the same array by uniqueness.
+b200sa_index *index_of(struct suffix_array *sa, uint32_t sigma, bool exact_sigma = false) {
+    b200sa_index *idx = lookup(sa);
+    if (idx && exact_sigma) {
+        // e.g. qsort_sa_construction(remapped) built with sigma 256, tables want the remapped sigma
+        struct b200sa_stats st;
+        b200sa_stats(idx, &st);
+        if (st.sigma != sigma) {
+            forget(sa);
+            idx = nullptr;
+        }
+    }
+    if (idx) return idx;
+    enum b200sa_error err;
+    idx = b200sa_build(sa->string, sa->length - 1, sigma, 0, device_id(), nullptr, &err);
+    if (!idx) die("b200sa_build");
+    remember(sa, idx);
+    return idx;
+}
+
+uint32_t sigma_guess(const struct suffix_array *sa) {
+    // largest code + 1; only used when an index has to be rebuilt without a remap table
+    uint32_t mx = 0;
+    for (uint32_t i = 0; i + 1 < sa->length; ++i)
+        if (sa->string[i] > mx) mx = sa->string[i];
+    return mx + 1;
+}
+
+// dense O rows in the reference layout (bwt.c:47-65); returns false where its u32 size overflows
+bool dense_o(b200sa_index *idx, uint32_t sigma, uint32_t length, uint32_t **table, uint32_t ***rows) {
+    uint64_t entries = ((uint64_t)length + 1) * sigma;
+    if (entries * 4 > 0xFFFFFFFFull) {
+        *table = nullptr;
+        *rows = nullptr;
+        return false;
+    }
+    *table = (uint32_t *)malloc(entries * sizeof(uint32_t));
+    *rows = (uint32_t **)malloc(((size_t)length + 1) * sizeof(uint32_t *));
+    if (b200sa_copy_o_dense(idx, *table)) die("b200sa_copy_o_dense");
+    for (uint64_t i = 0; i <= length; ++i) (*rows)[i] = *table + i * sigma;
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------------
+// remap.c (host side, tiny): letters present get codes 1..sigma-1 in byte order, 0 = sentinel
+// ------------------------------------------------------------------------------------------------
+void init_remap_table(struct remap_table *t, const uint8_t *string) {
+    bool present[256] = {false};
+    for (const uint8_t *p = string; *p; ++p) present[*p] = true;
+    memset(t->table, -1, sizeof t->table);
+    memset(t->rev_table, -1, sizeof t->rev_table);
+    t->table[0] = 0;
+    t->rev_table[0] = 0;
+    uint32_t next = 1;
+    for (int c = 1; c < 256; ++c) {
+        if (!present[c]) continue;
+        t->table[c] = (signed char)next;
+        if (next < 128) t->rev_table[next] = (signed char)c;
+        ++next;
+    }
+    t->alphabet_size = next;
+}
+
+struct remap_table *alloc_remap_table(const uint8_t *string) {
+    struct remap_table *t = (struct remap_table *)malloc(sizeof *t);
+    init_remap_table(t, string);
+    return t;
+}
+
+void dealloc_remap_table(struct remap_table *) {}
+void free_remap_table(struct remap_table *t) { free(t); }
+
+static uint8_t *map_range(uint8_t *out, const uint8_t *from, const uint8_t *to, const signed char *tab) {
+    for (const uint8_t *p = from; p != to; ++p, ++out) {
+        signed char code = tab[*p];
+        *out = (uint8_t)code;
+        if (code < 0) return nullptr;  // letter without a code (remap.c:80-84)
+    }
+    return out;
+}
+
+uint8_t *remap_between(uint8_t *output, const uint8_t *from, const uint8_t *to, struct remap_table *t) {
+    return map_range(output, from, to, t->table);
+}
+uint8_t *rev_remap_between(uint8_t *output, const uint8_t *from, const uint8_t *to, struct remap_table *t) {
+    // codes >= 128 cannot index the 128-entry reverse table
+    for (const uint8_t *p = from; p != to; ++p)
+        if (*p >= 128) return nullptr;
+    return map_range(output, from, to, t->rev_table);
+}
+uint8_t *remap_between0(uint8_t *output, const uint8_t *from, const uint8_t *to, struct remap_table *t) {
+    uint8_t *end = remap_between(output, from, to, t);
+    if (!end) return nullptr;
+    *end = 0;
+    return end + 1;
+}
+uint8_t *rev_remap_between0(uint8_t *output, const uint8_t *from, const uint8_t *to, struct remap_table *t) {
+    uint8_t *end = rev_remap_between(output, from, to, t);
+    if (!end) return nullptr;
+    *end = 0;
+    return end + 1;
+}
+uint8_t *remap(uint8_t *output, const uint8_t *input, struct remap_table *t) {
+    // the terminating NUL is mapped too (0 -> 0), so the output is sentinel-terminated (remap.c:102-114)
+    return remap_between(output, input, input + strlen((const char *)input) + 1, t);
+}
+uint8_t *rev_remap(uint8_t *output, const uint8_t *input, struct remap_table *t) {
+    return rev_remap_between(output, input, input + strlen((const char *)input) + 1, t);
+}
+uint32_t remap_string(uint8_t *output, uint8_t *input) {
+    struct remap_table t;
+    init_remap_table(&t, input);
+    remap(output, input, &t);
+    return t.alphabet_size;
+}
+bool identical_remap_tables(const struct remap_table *a, const struct remap_table *b) {
+    if (a->alphabet_size != b->alphabet_size) return false;
+    return memcmp(a->table, b->table, a->alphabet_size) == 0;  // same prefix the reference compares
+}
+
+// ------------------------------------------------------------------------------------------------
+// suffix arrays
+// ------------------------------------------------------------------------------------------------
+struct suffix_array *qsort_sa_construction(uint8_t *string) { return construct(string, 256, "qsort_sa_construction"); }
+struct suffix_array *skew_sa_construction(uint8_t *string) { return construct(string, 256, "skew_sa_construction"); }
+struct suffix_array *sa_is_construction(uint8_t *s, uint32_t sigma) { return construct(s, sigma, "sa_is_construction"); }
+struct suffix_array *sa_is_mem_construction(uint8_t *s, uint32_t sigma) {
+    return construct(s, sigma, "sa_is_mem_construction");
+}
+
+void free_suffix_array(struct suffix_array *sa) {
+    forget(sa);
+    free(sa->array);
+    free(sa->inverse);
+    free(sa->lcp);
+    free(sa);
+}
+void free_complete_suffix_array(struct suffix_array *sa) {
+    free(sa->string);
+    free_suffix_array(sa);
+}
+
+void compute_inverse(struct suffix_array *sa) {
+    if (sa->inverse) return;  // idempotent like suffix_array.c:57
+    b200sa_index *idx = index_of(sa, sigma_guess(sa));
+    if (b200sa_extend(idx, sa->string, B200SA_BUILD_ISA)) die("compute_inverse");
+    sa->inverse = (uint32_t *)malloc((size_t)sa->length * sizeof(uint32_t));
+    if (b200sa_copy_isa(idx, sa->inverse)) die("compute_inverse");
+}
+
+void compute_lcp(struct suffix_array *sa) {
+    if (sa->lcp) return;  // suffix_array.c:66
+    compute_inverse(sa);  // the reference fills both (suffix_array.c:70)
+    b200sa_index *idx = index_of(sa, sigma_guess(sa));
+    if (b200sa_extend(idx, sa->string, B200SA_BUILD_LCP)) die("compute_lcp");
+    sa->lcp = (uint32_t *)malloc((size_t)sa->length * sizeof(uint32_t));
+    if (b200sa_copy_lcp(idx, sa->lcp)) die("compute_lcp");
+}
+
+bool identical_suffix_arrays(const struct suffix_array *a, const struct suffix_array *b) {
+    if (a->length != b->length) return false;
+    if (strcmp((const char *)a->string, (const char *)b->string) != 0) return false;
+    if (memcmp(a->array, b->array, (size_t)a->length * sizeof(uint32_t)) != 0) return false;
+    return strlen((const char *)a->string) + 1 == a->length;
+}
+
+// ---- binary searches over the host copy (suffix_array.c:90-233); return values are pinned by
+// ---- tests/stralg/suffix_array_test.c:33-126 and reproduced in tests/test_compat.py
+uint32_t lower_bound_search(struct suffix_array *sa, const uint8_t *key) {
+    const size_t klen = strlen((const char *)key);
+    uint32_t lo = 0, hi = sa->length;
+    while (lo < hi) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (strncmp((const char *)key, (const char *)sa->string + sa->array[mid], klen) > 0) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo <= hi ? lo : hi;
+}
+
+uint32_t upper_bound_search(struct suffix_array *sa, const uint8_t *key) {
+    const size_t klen = strlen((const char *)key);
+    uint32_t lo = 0, hi = sa->length;
+    while (lo < hi) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (strncmp((const char *)key, (const char *)sa->string + sa->array[mid], klen) < 0) hi = mid - 1;
+        else lo = mid + 1;
+    }
+    uint32_t r = hi > lo ? hi : lo;
+    if (r == sa->length) return r;
+    return strncmp((const char *)key, (const char *)sa->string + sa->array[r], klen) >= 0 ? r + 1 : r;
+}
+
+uint32_t lower_bound_k(struct suffix_array *sa, uint32_t k, uint8_t a, uint32_t L, uint32_t R) {
+    while (L < R) {
+        uint32_t mid = L + (R - L) / 2;
+        uint32_t at = sa->array[mid] + k;
+        // a suffix that ends before offset k is smaller than any letter
+        if (at >= sa->length || sa->string[at] < a) L = mid + 1;
+        else R = mid;
+    }
+    return L <= R ? L : R;
+}
+
+uint32_t upper_bound_k(struct suffix_array *sa, uint32_t k, uint8_t a, uint32_t L, uint32_t R) {
+    const uint32_t end = R;
+    while (L < R) {
+        uint32_t mid = L + (R - L) / 2;
+        uint32_t at = sa->array[mid] + k;
+        if (at >= sa->length) L = mid + 1;
+        else if (a < sa->string[at]) R = mid - 1;
+        else L = mid + 1;
+    }
+    uint32_t r = R > L ? R : L;
+    if (r == end) return r;
+    return a >= sa->string[sa->array[r] + k] ? r + 1 : r;
+}
+
+void init_sa_match_iter(struct sa_match_iter *iter, const uint8_t *pattern, struct suffix_array *sa) {
+    iter->sa = sa;
+    const uint32_t m = (uint32_t)strlen((const char *)pattern);
+    uint32_t L = 0, R = sa->length;
+    for (uint32_t i = 0; i < m && L < R; ++i) {
+        L = lower_bound_k(sa, i, pattern[i], L, R);
+        R = upper_bound_k(sa, i, pattern[i], L, R);
+    }
+    // closed interval [L, R-1] as in suffix_array.c:216-218 (an empty one has R - 1 < L)
+    iter->L = L;
+    iter->R = R - 1;
+    iter->i = L;
+}
+bool next_sa_match(struct sa_match_iter *iter, struct sa_match *match) {
+    if (iter->i > iter->R) return false;
+    match->position = iter->sa->array[iter->i++];
+    return true;
+}
+void dealloc_sa_match_iter(struct sa_match_iter *) {}
+
+// ------------------------------------------------------------------------------------------------
+// BWT tables
+// ------------------------------------------------------------------------------------------------
+void init_bwt_table(struct bwt_table *tbl, struct suffix_array *sa, struct suffix_array *rsa,
+                    struct remap_table *remap_table) {
+    const uint32_t sigma = remap_table->alphabet_size;
+    tbl->remap_table = remap_table;
+    tbl->sa = sa;
+    b200sa_index *idx = index_of(sa, sigma, true);
+    if (b200sa_extend(idx, sa->string, B200SA_BUILD_OCC)) die("init_bwt_table");
+    tbl->c_table = (uint32_t *)calloc(sigma, sizeof(uint32_t));
+    if (b200sa_copy_c_table(idx, tbl->c_table)) die("init_bwt_table");
+    dense_o(idx, sigma, sa->length, &tbl->o_table, &tbl->o_indices);
+    tbl->ro_table = nullptr;
+    tbl->ro_indices = nullptr;
+    if (rsa) {  // O table of the reversed text (bwt.c:67-84); only the approximate search reads it
+        b200sa_index *ridx = index_of(rsa, sigma, true);
+        if (b200sa_extend(ridx, rsa->string, B200SA_BUILD_OCC)) die("init_bwt_table(rsa)");
+        dense_o(ridx, sigma, rsa->length, &tbl->ro_table, &tbl->ro_indices);
+    }
+}
+
+struct bwt_table *alloc_bwt_table(struct suffix_array *sa, struct suffix_array *rsa, struct remap_table *rt) {
+    struct bwt_table *tbl = (struct bwt_table *)malloc(sizeof *tbl);
+    init_bwt_table(tbl, sa, rsa, rt);
+    return tbl;
+}
+
+void dealloc_bwt_table(struct bwt_table *tbl) {
+    free(tbl->c_table);
+    free(tbl->o_table);
+    free(tbl->o_indices);
+    free(tbl->ro_table);
+    free(tbl->ro_indices);
+}
+void free_bwt_table(struct bwt_table *tbl) {
+    dealloc_bwt_table(tbl);
+    free(tbl);
+}
+void completely_dealloc_bwt_table(struct bwt_table *tbl) {
+    free_complete_suffix_array(tbl->sa);
+    free_remap_table(tbl->remap_table);
+    dealloc_bwt_table(tbl);
+}
+void completely_free_bwt_table(struct bwt_table *tbl) {
+    completely_dealloc_bwt_table(tbl);
+    free(tbl);
+}
+
+struct bwt_table *build_complete_table(const uint8_t *string, bool include_reverse) {
+    const size_t n = strlen((const char *)string);
+    struct remap_table *rt = alloc_remap_table(string);
+    uint8_t *codes = (uint8_t *)malloc(n + 1);
+    remap(codes, string, rt);
+    struct suffix_array *sa = sa_is_construction(codes, rt->alphabet_size);
+    struct suffix_array *rsa = nullptr;
+    if (include_reverse) {
+        uint8_t *rev = (uint8_t *)malloc(n + 1);
+        for (size_t i = 0; i < n; ++i) rev[i] = codes[n - 1 - i];
+        rev[n] = 0;
+        rsa = sa_is_construction(rev, rt->alphabet_size);
+    }
+    struct bwt_table *tbl = alloc_bwt_table(sa, rsa, rt);
+    if (rsa) free_complete_suffix_array(rsa);  // bwt.c:156-158
+    return tbl;
+}
+
+bool equivalent_bwt_tables(struct bwt_table *t1, struct bwt_table *t2) {
+    if (!identical_remap_tables(t1->remap_table, t2->remap_table)) return false;
+    if (!identical_suffix_arrays(t1->sa, t2->sa)) return false;
+    const uint32_t sigma = t1->remap_table->alphabet_size;
+    if (memcmp(t1->c_table, t2->c_table, (size_t)sigma * 4) != 0) return false;
+    const size_t o_entries = (size_t)sigma * t1->sa->length;  // the reference compares this many (bwt.c:579)
+    if (!t1->o_table != !t2->o_table) return false;
+    if (t1->o_table && memcmp(t1->o_table, t2->o_table, o_entries * 4) != 0) return false;
+    if (!t1->ro_table != !t2->ro_table) return false;
+    if (t1->ro_table && memcmp(t1->ro_table, t2->ro_table, o_entries * 4) != 0) return false;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact search (bwt.c:164-217): the backward search runs on the GPU, positions come from sa->array
+// ------------------------------------------------------------------------------------------------
+void bwt_exact_match_batch(struct bwt_table *tbl, const uint8_t *patterns, const uint64_t *offsets,
+                           uint64_t npatterns, uint32_t *L, uint32_t *R) {
+    b200sa_index *idx = index_of(tbl->sa, tbl->remap_table->alphabet_size, true);
+    if (b200sa_extend(idx, tbl->sa->string, B200SA_BUILD_OCC)) die("bwt_exact_match_batch");
+    if (b200sa_search_batch(idx, patterns, offsets, 0, npatterns, L, R)) die("bwt_exact_match_batch");
+}
+
+void init_bwt_exact_match_iter(struct bwt_exact_match_iter *iter, struct bwt_table *tbl,
+                               const uint8_t *remapped_pattern) {
+    iter->sa = tbl->sa;
+    const uint64_t off[2] = {0, (uint64_t)strlen((const char *)remapped_pattern)};
+    uint32_t L = 0, R = 0;
+    bwt_exact_match_batch(tbl, remapped_pattern, off, 1, &L, &R);
+    iter->L = L;
+    iter->R = R;
+    iter->i = L;
+}
+
+bool next_bwt_exact_match_iter(struct bwt_exact_match_iter *iter, struct bwt_exact_match *match) {
+    if (iter->i < 0 || iter->i >= (int64_t)iter->R) return false;
+    match->pos = iter->sa->array[iter->i++];
+    return true;
+}
+void dealloc_bwt_exact_match_iter(struct bwt_exact_match_iter *) {}
+
+}  // extern "C"

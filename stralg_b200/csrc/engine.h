@@ -61,6 +61,7 @@ void build_inverse(DeviceIndex &ix);
 // lcp.cu
 void build_lcp(DeviceIndex &ix);
 // bwt_occ.cu
+void gather_bwt(DeviceIndex &ix);  // ix.bwt + ix.primary from an existing SA
 void build_bwt_tables(DeviceIndex &ix, bool keep_bwt);
 void occ_probe(const DeviceIndex &ix, const u8 *d_a, const u32 *d_i, u64 count, u32 *d_out);
 void occ_dense(const DeviceIndex &ix, u32 *d_out);  // (len+1)*sigma entries, reference layout

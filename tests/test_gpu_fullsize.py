@@ -1,0 +1,167 @@
+"""Full-size parity through size-independent properties (BASELINE.json configs[1..3]).
+
+At 256 Mi .. 3 G symbols the CPU oracle no longer finishes in seconds, so the suffix array and
+the tables are checked with properties that pin them uniquely:
+
+* SA is a permutation of 0..n and, for every r >= 1, suffix SA[r-1] < suffix SA[r]
+  (first symbols compared, ties resolved through the inverse permutation of the NEXT
+  positions) -- the classic linear-time suffix-array checker; together these two facts imply
+  SA is THE suffix array the reference's constructors produce.
+* BWT rows equal text[SA[r] - 1]; every sampled-O block header equals the running symbol counts
+  of the BWT at its 64-row boundary and every payload equals the packed rows; C equals the
+  exclusive symbol histogram (stralg/bwt.c:13-20, 35-65).
+* For a sample of reads, [L, R) holds exactly the suffixes that start with the read: all of
+  SA[L..R) match, and the neighbours SA[L-1], SA[R] do not (bwt.c:164-217).
+
+The checks run on the GPU with torch (chunked), independently of the product kernels.
+Sizes: B200SA_FULLSIZE_N (default 3e9 when >= 150 GB of device memory is free, else 2^28).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CHUNK = 1 << 27
+
+
+def pick_n(torch):
+    env = os.environ.get("B200SA_FULLSIZE_N")
+    if env:
+        return int(float(env))
+    free, _ = torch.cuda.mem_get_info()
+    return 3_000_000_000 if free > 150e9 else (1 << 28)
+
+
+def test_fullsize_properties(engine):
+    import torch
+    lib = engine.load()
+    n = pick_n(torch)
+    dev = torch.device("cuda", 0)
+    text = torch.empty(n + 1, dtype=torch.uint8, device=dev)
+    assert lib.b200sa_synth_codes(C.c_void_p(text.data_ptr()), n, 4, 424242, 0, None) == 0
+    torch.cuda.synchronize()
+    idx = engine.SuffixArrayIndex.build(text[:n], 5, isa=False, bwt=True, occ=True)
+    lib.b200sa_release_workspace(0)  # give the memory back before torch needs it
+    length = n + 1
+    st = idx.stats()
+    assert st["length"] == length
+    print(f"[fullsize] n = {n}, stats = {st}")
+
+    def view(ptr, count, dtype):
+        # zero-copy torch view of a device array owned by the index
+        itemsize = torch.empty(0, dtype=dtype).element_size()
+        iface = {"shape": (count,), "typestr": {1: "|u1", 4: "<i4"}[itemsize], "data": (ptr, False), "version": 2}
+
+        class Holder:
+            __cuda_array_interface__ = iface
+        return torch.as_tensor(Holder(), device=dev)
+
+    sa = view(idx.device_ptr("sa"), length, torch.int32)
+    bwt = view(idx.device_ptr("bwt"), length, torch.uint8)
+
+    # ---- permutation + inverse ----
+    isa = torch.empty(length, dtype=torch.int32, device=dev)
+    for lo in range(0, length, CHUNK):
+        hi = min(length, lo + CHUNK)
+        s = sa[lo:hi].long() & 0xFFFFFFFF
+        assert int(s.max()) <= n
+        isa[s] = torch.arange(lo, hi, device=dev, dtype=torch.int64).to(torch.int32)
+    for lo in range(0, length, CHUNK):
+        hi = min(length, lo + CHUNK)
+        s = sa[lo:hi].long() & 0xFFFFFFFF
+        back = isa[s].long() & 0xFFFFFFFF
+        assert bool((back == torch.arange(lo, hi, device=dev)).all()), "SA is not a permutation"
+    assert int(sa[0].long() & 0xFFFFFFFF) == n  # the sentinel suffix sorts first
+
+    # ---- sortedness of adjacent suffixes ----
+    for lo in range(1, length, CHUNK):
+        hi = min(length, lo + CHUNK)
+        a = sa[lo - 1:hi - 1].long() & 0xFFFFFFFF
+        b = sa[lo:hi].long() & 0xFFFFFFFF
+        ta, tb = text[a], text[b]
+        ra = isa[torch.clamp(a + 1, max=n)].long() & 0xFFFFFFFF
+        rb = isa[torch.clamp(b + 1, max=n)].long() & 0xFFFFFFFF
+        ok = (ta < tb) | ((ta == tb) & (ra < rb))
+        assert bool(ok.all()), f"suffixes out of order near row {lo + int((~ok).nonzero()[0])}"
+        del a, b, ta, tb, ra, rb, ok
+    del isa
+
+    # ---- BWT rows, primary ----
+    primary = idx.primary
+    assert int(sa[primary].long() & 0xFFFFFFFF) == 0
+    for lo in range(0, length, CHUNK):
+        hi = min(length, lo + CHUNK)
+        s = sa[lo:hi].long() & 0xFFFFFFFF
+        exp = torch.where(s > 0, text[torch.clamp(s - 1, min=0)], torch.zeros_like(text[:1]))
+        assert bool((bwt[lo:hi] == exp).all()), "BWT row mismatch"
+
+    # ---- C table ----
+    counts = torch.stack([torch.bincount(text[i:min(n, i + CHUNK)].int(), minlength=5)
+                          for i in range(0, n, CHUNK)]).sum(0)
+    counts = counts.cpu().numpy().astype(np.int64)
+    counts[0] = 1
+    c_exp = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.uint32)
+    assert np.array_equal(idx.c_table(), c_exp)
+
+    # ---- sampled O: headers and payloads of every block ----
+    assert st["occ_layout"] == 1
+    nblocks = length // 64 + 1
+    occ = view(idx.device_ptr("occ"), nblocks * 8, torch.int32).view(nblocks, 8)
+    run = torch.zeros(4, dtype=torch.int64, device=dev)
+    rows_per_chunk = CHUNK  # multiple of 64
+    for lo in range(0, nblocks * 64, rows_per_chunk):
+        hi = min(nblocks * 64, lo + rows_per_chunk)
+        rows = torch.zeros(hi - lo, dtype=torch.uint8, device=dev)
+        valid_hi = min(hi, length)
+        if valid_hi > lo:
+            rows[: valid_hi - lo] = bwt[lo:valid_hi]
+        blk = rows.view(-1, 64)
+        b0, b1 = lo // 64, hi // 64
+        for a in range(1, 5):
+            per_block = (blk == a).sum(1)
+            excl = torch.cumsum(per_block, 0) - per_block + run[a - 1]
+            got = occ[b0:b1, a - 1].long() & 0xFFFFFFFF
+            assert bool((got == excl).all()), f"O header mismatch for symbol {a}"
+            run[a - 1] += per_block.sum()
+        sym = torch.where(blk > 0, blk - 1, torch.zeros_like(blk)).long()
+        shifts = (2 * torch.arange(32, device=dev, dtype=torch.int64))
+        for half in range(2):
+            word = (sym[:, 32 * half:32 * half + 32] << shifts).sum(1)
+            lo32 = occ[b0:b1, 4 + 2 * half].long() & 0xFFFFFFFF
+            hi32 = occ[b0:b1, 5 + 2 * half].long() & 0xFFFFFFFF
+            got = lo32 | (hi32 << 32)
+            assert bool((got == word).all()), "O payload mismatch"
+        del rows, blk, sym
+
+    # ---- search intervals on a sample of reads ----
+    m, nreads = 100, 200000
+    reads = torch.empty(nreads * m, dtype=torch.uint8, device=dev)
+    assert lib.b200sa_synth_reads(C.c_void_p(text.data_ptr()), n, 4, C.c_void_p(reads.data_ptr()), nreads, m, 102, 9,
+                                  0, None) == 0
+    dL = torch.empty(nreads, dtype=torch.int32, device=dev)
+    dR = torch.empty(nreads, dtype=torch.int32, device=dev)
+    idx.search_device(reads, None, m, nreads, dL, dR, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    L = dL.long() & 0xFFFFFFFF
+    R = dR.long() & 0xFFFFFFFF
+    hit = R > L
+    assert 0.85 < float(hit.float().mean()) < 0.95
+    rd = reads.view(nreads, m)
+    ar = torch.arange(m, device=dev)
+
+    def matches(rows, which):
+        pos = sa[rows].long() & 0xFFFFFFFF
+        idxs = torch.clamp(pos[:, None] + ar[None, :], max=n)
+        return (text[idxs] == rd[which]).all(1)
+
+    hq = hit.nonzero()[:, 0]
+    assert bool(matches(L[hq], hq).all()) and bool(matches(R[hq] - 1, hq).all())
+    inner = hq[(L[hq] > 0)]
+    assert not bool(matches(L[inner] - 1, inner).any())
+    inner = hq[(R[hq] < length)]
+    assert not bool(matches(R[inner], inner).any())
+    # misses: a random 100-mer does not occur (checked through the count of exact hits being 0)
+    idx.close()
