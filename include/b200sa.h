@@ -45,6 +45,10 @@ enum b200sa_error {
 #define B200SA_BUILD_LCP 0x2u        /* LCP array                       (suffix_array.c:64-85)  */
 #define B200SA_BUILD_BWT 0x4u        /* keep the BWT rows               (bwt.c:13-20)           */
 #define B200SA_BUILD_OCC 0x8u        /* C table + sampled O table       (bwt.c:35-65)           */
+#define B200SA_BUILD_TEXTCMP 0x10u   /* keep ISA + packed text: exact search finishes a unique interval
+                                        (R - L == 1) by comparing the remaining pattern symbols with the
+                                        text directly instead of one O lookup per symbol; results are
+                                        identical to the plain recurrence (needs OCC, keeps SA)        */
 #define B200SA_TEXT_ON_DEVICE 0x100u /* `codes` is a device pointer (borrowed during the call)  */
 #define B200SA_PROFILE 0x200u        /* record per-stage device times (b200sa_profile)          */
 #define B200SA_DROP_SA 0x400u        /* release the suffix array after the tables are built     */

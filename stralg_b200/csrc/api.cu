@@ -62,6 +62,14 @@ static void use_device(int device) {
         CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
         uint64_t never = UINT64_MAX;
         CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never));
+        if (const char *g = getenv("B200SA_L2_FETCH")) {
+            size_t before = 0;
+            cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+            cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+            size_t after = 0;
+            cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+            fprintf(stderr, "b200sa: L2 fetch granularity %zu -> %zu (%s)\n", before, after, cudaGetErrorString(e));
+        }
         pool_set[device] = true;
     }
 }
@@ -127,12 +135,17 @@ __attribute__((visibility("hidden"))) static int build_into(b200sa_index *h, con
     Arena::Mark after_pack = arena.mark();
     build_suffix_array(ix, want_tables);
     arena.release_to(after_pack);  // the sort workspace is dead; LCP reuses it (same stream)
-    if (flags & B200SA_BUILD_ISA) build_inverse(ix);
+    if (flags & (B200SA_BUILD_ISA | B200SA_BUILD_TEXTCMP)) build_inverse(ix);
     if (flags & B200SA_BUILD_LCP) build_lcp(ix);
     if (flags & B200SA_BUILD_OCC) build_bwt_tables(ix, flags & B200SA_BUILD_BWT);
+    if (flags & B200SA_BUILD_TEXTCMP) {
+        size_t words = ((size_t)ix.len + ix.pk.cpw - 1) / ix.pk.cpw + 4;
+        ix.text_packed.alloc(words, st);
+        CUDA_CHECK(cudaMemcpyAsync(ix.text_packed.ptr, ix.packed, words * 8, cudaMemcpyDeviceToDevice, st));
+    }
     ix.packed = nullptr;
     ix.arena = nullptr;
-    if (flags & B200SA_DROP_SA) ix.sa.release();
+    if ((flags & B200SA_DROP_SA) && !(flags & B200SA_BUILD_TEXTCMP)) ix.sa.release();
     CUDA_CHECK(cudaStreamSynchronize(st));
     if (flags & B200SA_PROFILE) {
         h->prof_n = ix.timer.n;
@@ -356,7 +369,7 @@ int b200sa_search_batch(const b200sa_index *idx, const uint8_t *patterns, const 
     CUDA_CHECK(cudaSetDevice(ix.device));
     cudaStream_t st = ix.stream;
     uint64_t total = offsets ? offsets[npat] : (uint64_t)fixed_len * npat;
-    DevBuf<u8> dp(total ? total : 1, st);
+    DevBuf<u8> dp(total + 16, st);  // padded: the DNA kernel reads whole aligned 8-byte words
     DevBuf<u64> doff;
     DevBuf<u32> dL(npat, st), dR(npat, st);
     if (total) CUDA_CHECK(cudaMemcpyAsync(dp.ptr, patterns, total, cudaMemcpyHostToDevice, st));

@@ -40,6 +40,7 @@ struct DeviceIndex {
     u64 *packed = nullptr;  // packed text (workspace arena), padded with zero words
     Arena *arena = nullptr; // per-device build workspace (valid during the build only)
     DevBuf<u32> sa, isa, lcp;
+    DevBuf<u64> text_packed;  // kept copy of the packed text (B200SA_BUILD_TEXTCMP: search shortcut)
     DevBuf<u8> bwt;
     DevBuf<u32> c_table;    // sigma entries (device)
     u32 c_host[256];

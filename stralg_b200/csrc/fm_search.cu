@@ -11,6 +11,8 @@
 #include "engine.h"
 #include "occ.cuh"
 
+#include <cstdlib>
+
 namespace b200sa {
 
 struct CTable5 {
@@ -61,6 +63,142 @@ __global__ void __launch_bounds__(256) fm_search_kernel(OccView ov, CTable5 c5, 
     outR[q] = R;
 }
 
+// ---------------------------------------------------------------------------------------------
+// DNA32 fast path.  Per backward step a lane issues ONE 256-bit load per distinct block (the L and
+// R rows share a block once the interval is narrower than 64 rows, i.e. after ~log4(len) steps on
+// random DNA), and pattern symbols come from an aligned 8-byte word fetched once per 8 steps.
+// Requires the pattern buffer to be 8-byte aligned and readable up to the next 8-byte boundary
+// (true for cudaMalloc / torch allocations; the host entry point pads its staging buffer).
+// ---------------------------------------------------------------------------------------------
+struct BlockRegs {
+    u32 c0, c1, c2, c3;
+    u64 w0, w1;
+};
+
+template <int LM>
+__device__ __forceinline__ BlockRegs load_dna_block(const u8 *blocks, u32 b) {
+    u64 a, bb, c, d;
+    const u8 *p = blocks + (size_t)b * 32;
+    if (LM == 0) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(a), "=l"(bb), "=l"(c), "=l"(d) : "l"(p));
+    } else if (LM == 1) {
+        uint4 x = __ldg((const uint4 *)p), y = __ldg((const uint4 *)p + 1);
+        a = ((u64)x.y << 32) | x.x; bb = ((u64)x.w << 32) | x.z;
+        c = ((u64)y.y << 32) | y.x; d = ((u64)y.w << 32) | y.z;
+    } else if (LM == 2) {
+        asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(a), "=l"(bb), "=l"(c), "=l"(d) : "l"(p));
+    } else {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(a), "=l"(bb), "=l"(c), "=l"(d) : "l"(p));
+    }
+    BlockRegs r;
+    r.c0 = (u32)a; r.c1 = (u32)(a >> 32); r.c2 = (u32)bb; r.c3 = (u32)(bb >> 32);
+    r.w0 = c; r.w1 = d;
+    return r;
+}
+
+__device__ __forceinline__ u32 rank_in_block(const BlockRegs &blk, u32 a, u32 i, u32 primary) {
+    u32 base = a == 1 ? blk.c0 : a == 2 ? blk.c1 : a == 3 ? blk.c2 : blk.c3;
+    u32 c = base + dna_match_count(blk.w0, blk.w1, a - 1, i & 63u);
+    if (a == 1) {
+        u32 start = i & ~63u;
+        if (primary >= start && primary < i) c -= 1;  // the sentinel row is stored as value 0
+    }
+    return c;
+}
+
+// Pointers for the unique-interval shortcut (B200SA_BUILD_TEXTCMP); all null when it is off.
+struct TextCmp {
+    const u32 *sa;
+    const u32 *isa;
+    const u64 *packed;  // 2-bit symbols, big-endian inside each word (sa_build.cu pack_kernel<2>)
+};
+
+template <int LM, bool SC>
+__global__ void __launch_bounds__(256) fm_search_dna_kernel(OccView ov, CTable5 c5, TextCmp tc, u32 len,
+                                                            const u8 *__restrict__ pat,
+                                                            const u64 *__restrict__ off, u32 fixed_len, u64 npat,
+                                                            u32 *__restrict__ outL, u32 *__restrict__ outR) {
+    u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npat) return;
+    u64 begin = off ? off[q] : q * (u64)fixed_len;
+    u64 m = off ? off[q + 1] - begin : (u64)fixed_len;
+    u32 L = 0, R = len;
+    if (m > (u64)len) {
+        L = 1;
+        R = 0;
+    }
+    u64 word = 0;
+    u64 word_addr = ~0ull;
+    for (int64_t i = (int64_t)m - 1; i >= 0 && L < R; --i) {
+        if (SC && R - L == 1) {
+            // One candidate suffix s = SA[L] is left.  The recurrence would now consume the remaining
+            // symbols pattern[i], pattern[i-1], ... one O lookup each, moving to ISA[s-1], ISA[s-2], ...
+            // as long as they equal text[s-1], text[s-2], ...; compare them against the text instead.
+            const u32 s = tc.sa[L];
+            const u64 rem = (u64)i + 1;
+            u64 k = 0;
+            u64 tw = 0, tw_idx = ~0ull;
+            u32 a = 0;
+            while (k < rem) {
+                u64 addr = begin + (u64)i - k;
+                if ((addr & ~7ull) != word_addr) {
+                    word_addr = addr & ~7ull;
+                    word = *(const u64 *)(pat + word_addr);
+                }
+                a = (u32)(word >> (8 * (addr & 7))) & 0xffu;
+                if (k >= (u64)s) break;  // suffix 0 is preceded by the sentinel only
+                u64 t = (u64)s - 1 - k;
+                if ((t >> 5) != tw_idx) {
+                    tw_idx = t >> 5;
+                    tw = tc.packed[tw_idx];
+                }
+                u32 sym = (u32)(tw >> (62 - 2 * (t & 31))) & 3u;
+                if (a - 1u != sym) break;
+                ++k;
+            }
+            if (k == rem) {
+                L = tc.isa[s - (u32)rem];
+                R = L + 1;
+            } else if (a - 1u > 3u || a >= ov.sigma) {
+                L = 1;
+                R = 0;
+            } else {
+                // the step that fails: BWT[Lk] != a, so both ranks coincide and the interval is empty
+                const u32 Lk = k ? tc.isa[s - (u32)k] : L;
+                BlockRegs kb = load_dna_block<LM>(ov.blocks, Lk >> 6);
+                BlockRegs kb2 = kb;
+                if (((Lk + 1) >> 6) != (Lk >> 6)) kb2 = load_dna_block<LM>(ov.blocks, (Lk + 1) >> 6);
+                L = c5.c[a] + rank_in_block(kb, a, Lk, ov.primary);
+                R = c5.c[a] + rank_in_block(kb2, a, Lk + 1, ov.primary);
+            }
+            break;
+        }
+        u64 addr = begin + (u64)i;
+        if ((addr & ~7ull) != word_addr) {
+            word_addr = addr & ~7ull;
+            word = *(const u64 *)(pat + word_addr);
+        }
+        u32 a = (u32)(word >> (8 * (addr & 7))) & 0xffu;
+        if (a - 1u > 3u || a >= ov.sigma) {
+            L = 1;
+            R = 0;
+            break;
+        }
+        const u32 bL = L >> 6, bR = R >> 6;
+        BlockRegs kL = load_dna_block<LM>(ov.blocks, bL);
+        BlockRegs kR = kL;
+        if (bR != bL) kR = load_dna_block<LM>(ov.blocks, bR);
+        const u32 ca = c5.c[a];
+        L = ca + rank_in_block(kL, a, L, ov.primary);
+        R = ca + rank_in_block(kR, a, R, ov.primary);
+    }
+    outL[q] = L;
+    outR[q] = R;
+}
+
 void fm_search(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fixed_len, u64 npat, u32 *d_L,
                u32 *d_R, cudaStream_t st) {
     if (!npat) return;
@@ -68,7 +206,27 @@ void fm_search(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fix
     CTable5 c5;
     for (int i = 0; i < 8; ++i) c5.c[i] = ix.c_host[i];
     unsigned blocks = div_up_u(npat, 256);
-    if (ix.occ_layout == OCC_DNA32)
+    static const bool force_generic = getenv("B200SA_SEARCH_GENERIC") != nullptr;
+    if (ix.occ_layout == OCC_DNA32 && (((uintptr_t)d_pat) & 7) == 0 && !force_generic)
+    {
+        static const int lm = getenv("B200SA_SEARCH_LM") ? atoi(getenv("B200SA_SEARCH_LM")) : 3;
+        static const bool no_sc = getenv("B200SA_SEARCH_NO_TEXTCMP") != nullptr;
+        TextCmp tc{ix.sa.ptr, ix.isa.ptr, ix.text_packed.ptr};
+        const bool sc = tc.sa && tc.isa && tc.packed && ix.pk.bits == 2 && !no_sc;
+#define LAUNCH_DNA(LM_, SC_) fm_search_dna_kernel<LM_, SC_><<<blocks, 256, 0, st>>>(ov, c5, tc, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R)
+        if (sc) {
+            if (lm == 0) LAUNCH_DNA(0, true); else LAUNCH_DNA(3, true);
+        } else {
+            switch (lm) {
+                case 0: LAUNCH_DNA(0, false); break;
+                case 1: LAUNCH_DNA(1, false); break;
+                case 2: LAUNCH_DNA(2, false); break;
+                default: LAUNCH_DNA(3, false); break;
+            }
+        }
+#undef LAUNCH_DNA
+    }
+    else if (ix.occ_layout == OCC_DNA32)
         fm_search_kernel<1><<<blocks, 256, 0, st>>>(ov, c5, ix.c_table.ptr, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R);
     else
         fm_search_kernel<2><<<blocks, 256, 0, st>>>(ov, c5, ix.c_table.ptr, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R);

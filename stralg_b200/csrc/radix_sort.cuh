@@ -106,7 +106,7 @@ struct PassCfg {
 };
 
 template <int RB, int NT, int IPT>
-__global__ void __launch_bounds__(NT) onesweep_pass_kernel(const u64 *__restrict__ kin, const u32 *__restrict__ vin,
+__global__ void __launch_bounds__(NT, (NT <= 256 ? 4 : (NT <= 384 ? 2 : 2))) onesweep_pass_kernel(const u64 *__restrict__ kin, const u32 *__restrict__ vin,
                                                            u64 *__restrict__ kout, u32 *__restrict__ vout, u32 n,
                                                            int shift, u32 digit_mask,
                                                            const u32 *__restrict__ digit_base,
@@ -171,6 +171,13 @@ __global__ void __launch_bounds__(NT) onesweep_pass_kernel(const u64 *__restrict
             pos[j0 + b] = before[b] + __popc(peers[b] & lt);
         }
     }
+    // values: issued now, consumed after the digit scan (their latency hides behind it)
+    u32 v[IPT];
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+        u64 idx = wbase + (u64)j * 32;
+        v[j] = idx < n ? ld_stream_u32(vin + idx) : 0u;
+    }
     __syncthreads();
 
     // ---- per digit: exclusive scan over warps, tile totals ----
@@ -220,17 +227,10 @@ __global__ void __launch_bounds__(NT) onesweep_pass_kernel(const u64 *__restrict
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
         u32 d = (u32)(k[j] >> shift) & digit_mask;
-        pos[j] += tile_start[d] + warp_hist[warp * BINS + d];
-        keys_s[pos[j]] = k[j];
+        u32 p = pos[j] + tile_start[d] + warp_hist[warp * BINS + d];
+        keys_s[p] = k[j];
+        vals_s[p] = v[j];
     }
-    // values are loaded now (keys' registers are dead); latency overlaps the look-back
-    u32 v[IPT];
-#pragma unroll
-    for (int j = 0; j < IPT; ++j) {
-        u64 idx = wbase + (u64)j * 32;
-        v[j] = idx < n ? ld_stream_u32(vin + idx) : 0u;
-    }
-
     // ---- decoupled look-back: exclusive count of each digit over all earlier tiles ----
 #pragma unroll
     for (int q = 0; q < DPT; ++q) {
@@ -264,18 +264,13 @@ __global__ void __launch_bounds__(NT) onesweep_pass_kernel(const u64 *__restrict
     }
     __syncthreads();
 
-    // ---- write keys: consecutive threads write consecutive slots of a digit run ----
+    // ---- write out: consecutive threads write consecutive slots of a digit run ----
     for (u32 i = tid; i < nvalid; i += NT) {
         u64 key = keys_s[i];
         u32 d = (u32)(key >> shift) & digit_mask;
-        kout[(u32)(i + adj[d])] = key;
-    }
-#pragma unroll
-    for (int j = 0; j < IPT; ++j) vals_s[pos[j]] = v[j];
-    __syncthreads();
-    for (u32 i = tid; i < nvalid; i += NT) {
-        u32 d = (u32)(keys_s[i] >> shift) & digit_mask;
-        vout[(u32)(i + adj[d])] = vals_s[i];
+        u32 g = i + adj[d];
+        kout[g] = key;
+        vout[g] = vals_s[i];
     }
 }
 

@@ -119,20 +119,27 @@ def make_patterns(rng, codes, nsym, npat, mmin, mmax):
     return pat, off
 
 
+@pytest.mark.parametrize("textcmp", [False, True], ids=["plain", "textcmp"])
 @pytest.mark.parametrize("n,nsym,mmax", [(1 << 20, 4, 24), (200000, 4, 40), (50000, 2, 30), (80000, 20, 6),
-                                         (60000, 255, 4), (3000, 1, 50)])
-def test_batched_search_and_locate(engine, oracle, n, nsym, mmax):
+                                         (60000, 255, 4), (3000, 1, 50), (40000, 3, 200), (5000, 4, 300)])
+def test_batched_search_and_locate(engine, oracle, n, nsym, mmax, textcmp):
     """(L, R) per pattern and the position sets against the restatement of bwt.c:164-217;
     config 1 of BASELINE.json is the first row (1 Mi random ACGT, 10 k patterns)."""
     rng = np.random.default_rng(n + nsym)
     codes = oracle.random_codes(n, nsym, seed=n)
     sigma = nsym + 1
-    idx = engine.SuffixArrayIndex.build(codes[:-1], sigma)
+    idx = engine.SuffixArrayIndex.build(codes[:-1], sigma, textcmp=textcmp)
     sa = idx.sa()
     bwt = oracle.bwt(codes, sa)
     ck = oracle.o_checkpoints(bwt, sigma, 64)
     c = oracle.c_table(codes, sigma)
     pat, off = make_patterns(rng, codes, nsym, 10000, 1, mmax)
+    # near-misses: copies of text windows with one symbol changed (exercise the failing step)
+    for k in range(0, 10000, 7):
+        lo, hi = int(off[k]), int(off[k + 1])
+        if hi - lo >= 2 and k % 2:
+            j = lo + int(rng.integers(0, hi - lo))
+            pat[j] = 1 + (pat[j] % nsym)
     L, R = idx.search(pat, off)
     Le, Re = oracle.search_ck(c, bwt, ck, 64, pat, off, threads=4)
     assert np.array_equal(L, Le) and np.array_equal(R, Re)
@@ -150,7 +157,12 @@ def test_batched_search_and_locate(engine, oracle, n, nsym, mmax):
 
 def test_search_edge_cases(engine, oracle):
     codes, sigma, table = oracle.remap(b"mississippi")
-    idx = engine.SuffixArrayIndex.build(codes[:-1], sigma)
+    for textcmp in (False, True):
+        _search_edge_cases(engine, codes, sigma, textcmp)
+
+
+def _search_edge_cases(engine, codes, sigma, textcmp):
+    idx = engine.SuffixArrayIndex.build(codes[:-1], sigma, textcmp=textcmp)
     # pattern longer than the text: (1, 0) like bwt.c:179-181
     long_pat = np.tile(codes[:-1], 2)
     assert idx.search_one(long_pat) == (1, 0)
