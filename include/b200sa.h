@@ -59,12 +59,14 @@ struct b200sa_stats {
     uint32_t primary;      /* row r with SA[r] == 0 (BWT row holding the sentinel) */
     uint32_t rounds;       /* prefix-doubling rounds after the initial sort */
     uint32_t k0;           /* symbols packed into the initial sort key */
-    uint32_t radix_bits;
-    uint32_t passes0;      /* radix passes of the initial sort */
+    uint32_t radix_bits;   /* digit bits: LSD passes, or the first partition level of the bucket sort */
+    uint32_t passes0;      /* radix passes (LSD) or partition levels (bucket sort) of the initial sort */
     uint32_t occ_layout;   /* 1 = 32-byte DNA blocks, 2 = byte blocks */
     uint64_t sorted_total; /* elements sorted, summed over rounds */
     uint64_t passes_elems; /* elements moved, summed over all radix passes */
     uint64_t occ_bytes;
+    uint32_t round0_mode;  /* initial sort: 0 = LSD radix passes, 1 = MSD bucket sort of 8-byte elements */
+    uint32_t bucket_bits;  /* bucket sort: leading key bits that select a bucket */
 };
 
 /* ---- construction ------------------------------------------------------------------------

@@ -36,6 +36,7 @@ class Stats(C.Structure):
         ("length", C.c_uint32), ("sigma", C.c_uint32), ("primary", C.c_uint32), ("rounds", C.c_uint32),
         ("k0", C.c_uint32), ("radix_bits", C.c_uint32), ("passes0", C.c_uint32), ("occ_layout", C.c_uint32),
         ("sorted_total", C.c_uint64), ("passes_elems", C.c_uint64), ("occ_bytes", C.c_uint64),
+        ("round0_mode", C.c_uint32), ("bucket_bits", C.c_uint32),
     ]
 
 

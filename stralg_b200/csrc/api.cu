@@ -248,6 +248,8 @@ int b200sa_stats(const b200sa_index *idx, struct b200sa_stats *out) {
     out->sorted_total = ix.stats.sorted_total;
     out->passes_elems = ix.stats.passes_elems;
     out->occ_bytes = ix.occ.bytes();
+    out->round0_mode = ix.stats.round0_mode;
+    out->bucket_bits = ix.stats.bucket_bits;
     return 0;
 }
 

@@ -40,8 +40,10 @@ __global__ void __launch_bounds__(256) bwt_gather_kernel(const u32 *__restrict__
 void gather_bwt(DeviceIndex &ix) {
     cudaStream_t st = ix.stream;
     size_t bwt_bytes = (((size_t)ix.len + 63) / 64 + 1) * 64;
-    ix.bwt.alloc(bwt_bytes, st);
-    CUDA_CHECK(cudaMemsetAsync(ix.bwt.ptr + (bwt_bytes - 128), 0, 128, st));
+    if (!ix.bwt.ptr) {
+        ix.bwt.alloc(bwt_bytes, st);
+        CUDA_CHECK(cudaMemsetAsync(ix.bwt.ptr + (bwt_bytes - 128), 0, 128, st));
+    }
     DevBuf<u32> d_primary(1, st);
     int t = ix.timer.begin("bwt_gather", (double)ix.len * 6.0);
     bwt_gather_kernel<<<div_up_u(((u64)ix.len + 3) / 4, 256), 256, 0, st>>>(ix.sa.ptr, ix.packed, ix.len, ix.pk.bits,

@@ -24,6 +24,8 @@ struct BuildStats {
     u32 passes0;         // radix passes in round 0
     u64 sorted_total;    // sum over rounds of elements sorted
     u64 passes_elems;    // sum over all radix passes of elements moved
+    u32 round0_mode;     // 0: LSD radix passes, 1: MSD bucket sort (round0_msd.cu)
+    u32 bucket_bits;     // MSD: leading key bits that select a bucket
 };
 
 // Occurrence-table layouts

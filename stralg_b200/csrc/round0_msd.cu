@@ -1,0 +1,890 @@
+// round0_msd.cu -- the initial K-symbol sort of suffix-array construction as an MSD bucket sort
+// (sm_100a).  Replaces, for round 0 only, the LSD passes of radix_sort.cuh: every suffix is one
+// 8-byte element
+//
+//      [ rest of the key : KB - D1 bits | preceding symbol : pb bits | suffix start : 32 bits ]
+//
+// that is partitioned by the leading digits of its K-symbol key (1..3 levels, <= 1024 bins each,
+// a digit that has been consumed is implied by the bucket and dropped), until buckets fit one
+// SM's shared memory, where they are ordered by the remaining key bits.  MSD partitioning needs
+// no stability, so ranking inside a tile is ONE shared-memory atomicAdd per element (2.7 SM
+// cycles per warp on B200 against 62 for match.any, tools/ubench.cu) and tiles reserve their
+// output ranges with global atomics instead of a look-back chain.  The last kernel emits, per
+// bucket, what round 0 of prefix doubling needs (stralg/sa_is.c:295-336 "naming" is the
+// reference's counterpart): SA order, BWT rows (stralg/bwt.c:13-20), and for suffixes whose
+// K-symbol key is shared: the rank of their group, the valid bit and a slot in the active list.
+//
+// Suffixes whose K-window reaches the sentinel ("short", at most K of them) are padded with the
+// smallest symbol; among equal padded keys they precede every long suffix, shortest first, which
+// is strcmp order on NUL-terminated strings (stralg/suffix_array.c:26-30).
+#include "round0_msd.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+namespace b200sa {
+
+static constexpr int MSD_MAXBINS = 1024;
+// partition kernels
+static constexpr int P_NT = 512;
+static constexpr int P_IPT = 8;
+static constexpr int P_TILE = P_NT * P_IPT;  // 4096 elements
+// local sort
+static constexpr int L3_NT = 512;
+static constexpr int L3_IPT = 12;
+static constexpr int L3_CAP = L3_NT * L3_IPT;      // 6144 elements in shared memory
+static constexpr int L3_TSZ = 2048;                // a tile owns the buckets that START in its span
+static constexpr int L3_MAXB = L3_CAP - L3_TSZ;    // 4096: largest bucket the fast path accepts
+static constexpr int L3_CROWD = 64;                // more elements than this in one bin -> robust kernel
+static constexpr int L3_MASKW = L3_CAP / 32;       // 192 words of segment-start bits
+static constexpr int RB_N = 8192;                  // robust kernel: bitonic network size
+
+static int env_int2(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Planning
+// ---------------------------------------------------------------------------------------------
+bool msd_make_plan(u32 len, u32 sigma, int bits, MsdPlan &pl) {
+    const char *mode = getenv("B200SA_ROUND0");
+    if (mode && !strcmp(mode, "lsd")) return false;
+    const int b = bits;
+    int dmax = (b == 4 || b == 8) ? 8 : 10;
+    dmax = env_int2("B200SA_MSD_DMAX", dmax);
+    dmax = std::max(b, std::min(10, dmax / b * b));
+    const int target = std::max(1, env_int2("B200SA_MSD_AVG", 3400));
+    int BB = b;
+    while (((u64)len >> BB) > (u64)target && BB + b <= 3 * dmax) BB += b;
+    int forced = env_int2("B200SA_MSD_BB", 0);
+    if (forced > 0) BB = std::max(b, std::min(3 * dmax, forced / b * b));
+    const int nl = (BB + dmax - 1) / dmax;
+    const int syms = BB / b;
+    for (int i = 0; i < 3; ++i) pl.D[i] = 0;
+    for (int i = 0; i < nl; ++i) pl.D[i] = b * (syms / nl + (i < syms % nl ? 1 : 0));
+    pl.nlevels = nl;
+    pl.BB = BB;
+
+    int log2len = 0;
+    while ((1ull << log2len) < (u64)len) ++log2len;
+    double eff = std::log2((double)(sigma > 2 ? sigma - 1 : 1));
+    if (eff < 0.5) eff = 0.5;
+    const int margin = env_int2("B200SA_KEY_MARGIN", 8);
+    const int k_wanted = std::max(1, (int)std::ceil((log2len + margin) / eff));
+    const int k_min = (BB + b - 1) / b;
+    auto kcap = [&](int pb) {
+        int by_elem = (32 - pb + pl.D[0]) / b;      // 32 + pb + (KB - D1) <= 64
+        int by_window = 64 / b - (pb ? 1 : 0);      // one 64-bit window holds prev + K symbols
+        return std::min(by_elem, by_window);
+    };
+    int kc = std::min(k_wanted, kcap(b)), kn = std::min(k_wanted, kcap(0));
+    int K, pb;
+    if (kc >= k_wanted || kn <= kc) {
+        K = kc;
+        pb = b;
+    } else {
+        K = kn;
+        pb = 0;
+    }
+    int kf = env_int2("B200SA_MSD_K", 0);
+    if (kf > 0) K = std::min(kf, kcap(pb));
+    if (K < k_min) {
+        K = k_min;
+        if (K > kcap(pb)) return false;
+    }
+    pl.K = K;
+    pl.KB = K * b;
+    pl.pb = pb;
+    pl.R = pl.KB - BB;
+    return pl.R >= 0 && pl.R <= 32;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Level-1 histogram straight from the packed text: hist[x] = #{t in [0, n] : first D key bits of
+// suffix t == x}
+// ---------------------------------------------------------------------------------------------
+template <int BITS>
+__global__ void __launch_bounds__(256) msd_hist_text_kernel(const u64 *__restrict__ packed, u32 n, u64 nwords_data,
+                                                            int D, u32 *__restrict__ hist) {
+    constexpr int CPW = 64 / BITS;
+    __shared__ u32 sh[MSD_MAXBINS];
+    const int bins = 1 << D;
+    for (int i = threadIdx.x; i < bins; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < nwords_data; w += stride) {
+        u64 hi = packed[w], lo = packed[w + 1];
+        u64 t0 = w * CPW;
+#pragma unroll
+        for (int q = 0; q < CPW; ++q) {
+            if (t0 + q <= n) {
+                const int o = q * BITS;
+                u64 win = o ? ((hi << o) | (lo >> (64 - o))) : hi;
+                atomicAdd(&sh[(u32)(win >> (64 - D))], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < bins; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// One CTA per parent bucket: child_start[p*B + d] = parent_start[p] + exclusive scan of the
+// parent's digit counts; the counts are replaced by the same values (they become the write
+// cursors of the partition kernel).  blockDim.x >= B, a multiple of 32.
+__global__ void __launch_bounds__(1024) msd_scan_children_kernel(u32 *__restrict__ hist,
+                                                                 const u32 *__restrict__ parent_start, int D,
+                                                                 u32 nparents, u32 len, u32 *__restrict__ child_start,
+                                                                 u32 *__restrict__ maxbucket) {
+    __shared__ u32 wsum[32];
+    __shared__ u32 wmax[32];
+    const u32 B = 1u << D;
+    const u32 p = blockIdx.x, d = threadIdx.x;
+    const unsigned lane = d & 31u, warp = d >> 5, nwarps = blockDim.x >> 5;
+    const size_t at = (size_t)p * B + d;
+    u32 c = d < B ? hist[at] : 0u;
+    u32 incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += t;
+    }
+    u32 mx = c;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 31) wsum[warp] = incl;
+    if (lane == 0) wmax[warp] = mx;
+    __syncthreads();
+    u32 base = parent_start ? parent_start[p] : 0u;
+    for (unsigned w = 0; w < warp; ++w) base += wsum[w];
+    if (d < B) {
+        u32 st = base + incl - c;
+        child_start[at] = st;
+        hist[at] = st;
+    }
+    if (d == 0) {
+        if (maxbucket) {
+            u32 m = 0;
+            for (unsigned w = 0; w < nwarps; ++w) m = max(m, wmax[w]);
+            atomicMax(maxbucket, m);
+        }
+        if (p == nparents - 1) child_start[(size_t)nparents * B] = len;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tiles of a partition level >= 2: a tile never straddles two parent buckets.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) msd_tile_offsets_kernel(const u32 *__restrict__ pstart, u32 nparents,
+                                                                u32 *__restrict__ tile_off, u32 *__restrict__ d_ntiles) {
+    __shared__ u32 wsum[32];
+    __shared__ u32 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (u32 base = 0; base < nparents; base += 1024) {
+        u32 p = base + threadIdx.x;
+        u32 nt = 0;
+        if (p < nparents) nt = (pstart[p + 1] - pstart[p] + (P_TILE - 1)) / P_TILE;
+        u32 incl = nt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        u32 wb = 0;
+        for (unsigned w = 0; w < warp; ++w) wb += wsum[w];
+        u32 excl = carry + wb + incl - nt;
+        if (p < nparents) tile_off[p] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + nt;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        tile_off[nparents] = carry;
+        *d_ntiles = carry;
+    }
+}
+
+// one warp per parent: desc = {first element, count, parent, 0}
+__global__ void __launch_bounds__(256) msd_tile_desc_kernel(const u32 *__restrict__ pstart, u32 nparents,
+                                                            const u32 *__restrict__ tile_off, uint4 *__restrict__ desc) {
+    u32 p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= nparents) return;
+    const u32 s0 = pstart[p], c = pstart[p + 1] - s0;
+    const u32 nt = (c + (P_TILE - 1)) / P_TILE, t0 = tile_off[p];
+    for (u32 k = threadIdx.x & 31u; k < nt; k += 32) {
+        u32 off = k * P_TILE;
+        desc[t0 + k] = make_uint4(s0 + off, min((u32)P_TILE, c - off), p, 0u);
+    }
+}
+
+// digit histogram of one level >= 2 (per parent), from the elements the previous level wrote
+__global__ void __launch_bounds__(P_NT) msd_hist_elems_kernel(const u64 *__restrict__ in, const uint4 *__restrict__ desc,
+                                                              const u32 *__restrict__ d_ntiles, int D, int dshift,
+                                                              u32 *__restrict__ hist) {
+    if (blockIdx.x >= *d_ntiles) return;
+    __shared__ u32 sh[MSD_MAXBINS];
+    const u32 B = 1u << D;
+    for (u32 i = threadIdx.x; i < B; i += P_NT) sh[i] = 0;
+    __syncthreads();
+    const uint4 ds = desc[blockIdx.x];
+    const u64 *src = in + ds.x;
+    for (u32 i = threadIdx.x; i < ds.y; i += P_NT) {
+        u64 e = ld_stream_u64(src + i);
+        atomicAdd(&sh[(u32)(e >> dshift) & (B - 1)], 1u);
+    }
+    __syncthreads();
+    u32 *h = hist + (size_t)ds.z * B;
+    for (u32 i = threadIdx.x; i < B; i += P_NT)
+        if (sh[i]) atomicAdd(&h[i], sh[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Partition kernel: one tile of <= P_TILE elements is split by one digit.
+//   FROM_TEXT: the tile is P_TILE consecutive suffix starts, elements are formed from the packed
+//              text and the digit (the key's leading D bits) is not stored in the element.
+//   else     : elements come from the previous level; the digit sits at element bit `dshift`.
+// ---------------------------------------------------------------------------------------------
+struct PartArgs {
+    const u64 *in;
+    u64 *out;
+    const u64 *packed;
+    u32 n, len;
+    int bits, KB, pb;
+    int D;
+    int dshift;       // FROM_TEXT: digit = key >> dshift, rest = key & restmask; else digit = (e >> dshift) & (B-1)
+    u64 restmask;
+    int rest_shift;   // 32 + pb
+    u32 *cursor;      // [nparents << D] next free slot of every child bucket
+    const uint4 *desc;
+    const u32 *d_ntiles;
+};
+
+static constexpr size_t P_SMEM = (size_t)P_TILE * 8 + (size_t)MSD_MAXBINS * 4 * 2 + (size_t)P_TILE * 2 + 32 * 4;
+
+template <bool FROM_TEXT>
+__global__ void __launch_bounds__(P_NT, 2) msd_partition_kernel(PartArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *buf = (u64 *)smem_raw;                   // [P_TILE]
+    u32 *hist = (u32 *)(buf + P_TILE);            // [MAXBINS] counts, then tile-local offsets
+    u32 *gofs = hist + MSD_MAXBINS;               // [MAXBINS] global slot of the digit's run minus its tile offset
+    u16 *dig = (u16 *)(gofs + MSD_MAXBINS);       // [P_TILE] digit of the element in slot i (FROM_TEXT)
+    u32 *wsum = (u32 *)(dig + P_TILE);            // [32]
+
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u32 B = 1u << a.D;
+    u64 begin;
+    u32 count, parent;
+    if (FROM_TEXT) {
+        begin = (u64)blockIdx.x * P_TILE;
+        count = (u32)min((u64)P_TILE, (u64)a.len - begin);
+        parent = 0;
+    } else {
+        if (blockIdx.x >= *a.d_ntiles) return;
+        const uint4 ds = a.desc[blockIdx.x];
+        begin = ds.x;
+        count = ds.y;
+        parent = ds.z;
+    }
+    for (u32 i = tid; i < B; i += P_NT) hist[i] = 0;
+    __syncthreads();
+
+    // ---- elements, digits, slot inside the tile's digit group (arbitrary order: MSD) ----
+    u64 e[P_IPT];
+    u32 ds[P_IPT];
+#pragma unroll
+    for (int j = 0; j < P_IPT; ++j) {
+        const u32 i = (u32)j * P_NT + tid;
+        ds[j] = 0;
+        e[j] = 0;
+        if (i < count) {
+            u32 d;
+            if (FROM_TEXT) {
+                const u32 p = (u32)(begin + i);
+                u64 key, prev = 0;
+                if (a.pb && p > 0) {
+                    u64 win = window_at(a.packed, (u64)p - 1, a.bits);
+                    prev = win >> (64 - a.bits);
+                    key = (win << a.bits) >> (64 - a.KB);
+                } else {
+                    key = window_at(a.packed, (u64)p, a.bits) >> (64 - a.KB);
+                }
+                d = (u32)(key >> a.dshift);
+                e[j] = ((key & a.restmask) << a.rest_shift) | (prev << 32) | (u64)p;
+            } else {
+                e[j] = ld_stream_u64(a.in + begin + i);
+                d = (u32)(e[j] >> a.dshift) & (B - 1);
+            }
+            u32 slot = atomicAdd(&hist[d], 1u);
+            ds[j] = d | (slot << 10);
+        }
+    }
+    __syncthreads();
+
+    // ---- exclusive scan of the digit counts; reserve the runs in the child buckets ----
+    {
+        constexpr int DPT = MSD_MAXBINS / P_NT;  // 2
+        const u32 d0 = tid * DPT;
+        u32 c[DPT];
+        u32 sum = 0;
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) {
+            c[q] = d0 + q < B ? hist[d0 + q] : 0u;
+            sum += c[q];
+        }
+        u32 g[DPT];
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) {
+            g[q] = 0;
+            if (c[q]) g[q] = atomicAdd(&a.cursor[(size_t)parent * B + d0 + q], c[q]);
+        }
+        u32 incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        u32 run = incl - sum;
+        for (u32 w = 0; w < warp; ++w) run += wsum[w];
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) {
+            if (d0 + q < B) {
+                hist[d0 + q] = run;
+                gofs[d0 + q] = g[q] - run;
+            }
+            run += c[q];
+        }
+    }
+    __syncthreads();
+
+    // ---- group the tile by digit in shared memory ----
+#pragma unroll
+    for (int j = 0; j < P_IPT; ++j) {
+        const u32 i = (u32)j * P_NT + tid;
+        if (i < count) {
+            const u32 d = ds[j] & 1023u;
+            const u32 pos = hist[d] + (ds[j] >> 10);
+            buf[pos] = e[j];
+            if (FROM_TEXT) dig[pos] = (u16)d;
+        }
+    }
+    __syncthreads();
+
+    // ---- consecutive threads write consecutive slots of a digit run ----
+    for (u32 i = tid; i < count; i += P_NT) {
+        const u64 v = buf[i];
+        const u32 d = FROM_TEXT ? (u32)dig[i] : ((u32)(v >> a.dshift) & (B - 1));
+        a.out[gofs[d] + i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Local-sort tiles: tile t owns the buckets whose first element lies in [t*TSZ, (t+1)*TSZ).
+// tile_first[t] = smallest bucket b with bstart[b] >= t*TSZ  (b in [0, nb]; bstart[nb] = len)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) msd_tile_first_kernel(const u32 *__restrict__ bstart, u64 nb, u32 ntiles,
+                                                             u32 *__restrict__ tile_first) {
+    u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nb) return;
+    const u32 s = bstart[b];
+    u32 lo = b == 0 ? 0u : bstart[b - 1] / L3_TSZ + 1u;
+    u32 hi = b == nb ? ntiles : s / L3_TSZ;
+    if (hi > ntiles) hi = ntiles;
+    for (u32 t = lo; t <= hi; ++t) tile_first[t] = (u32)b;
+}
+
+struct L3Args {
+    const u64 *in;
+    const u32 *bstart;
+    const u32 *tile_first;
+    u32 n;
+    int K, pb, R;
+    u32 *sa;
+    u8 *bwt;           // may be null
+    u32 *rank, *valid;
+    u32 *act, *act_count;
+    u32 *primary;
+    u32 *flagged, *nflagged;   // tiles the fast kernel declined (a crowded bin)
+};
+
+__device__ __forceinline__ u32 seg_index(const u32 *segmask, const u32 *segpre, u32 i) {
+    // number of segment starts at positions <= i, minus one
+    return segpre[i >> 5] + (u32)__popc(segmask[i >> 5] & (0xffffffffu >> (31u - (i & 31u)))) - 1u;
+}
+
+// segment-start bitmap, per-word prefix counts and (offset, count) of every non-empty bucket
+__device__ __forceinline__ void l3_segments(const u32 *__restrict__ bstart, u32 b0, u32 b1, u32 E0, u32 M, u32 *segmask,
+                                            u32 *segpre, uint2 *segtab, int NT) {
+    const u32 tid = threadIdx.x;
+    for (u32 i = tid; i < (u32)L3_MASKW + 1; i += NT) segmask[i] = 0;
+    __syncthreads();
+    for (u32 b = b0 + tid; b < b1; b += NT) {
+        u32 s0 = bstart[b], s1 = bstart[b + 1];
+        if (s1 > s0) atomicOr(&segmask[(s0 - E0) >> 5], 1u << ((s0 - E0) & 31u));
+    }
+    __syncthreads();
+    if (tid < 32) {
+        constexpr int WPL = L3_MASKW / 32;  // 6 words per lane
+        u32 loc[WPL];
+        u32 sum = 0;
+#pragma unroll
+        for (int q = 0; q < WPL; ++q) {
+            loc[q] = (u32)__popc(segmask[tid * WPL + q]);
+            sum += loc[q];
+        }
+        u32 incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (tid >= (unsigned)o) incl += t;
+        }
+        u32 run = incl - sum;
+#pragma unroll
+        for (int q = 0; q < WPL; ++q) {
+            segpre[tid * WPL + q] = run;
+            run += loc[q];
+        }
+    }
+    __syncthreads();
+    for (u32 b = b0 + tid; b < b1; b += NT) {
+        u32 s0 = bstart[b], s1 = bstart[b + 1];
+        if (s1 > s0) {
+            u32 i0 = s0 - E0;
+            segtab[seg_index(segmask, segpre, i0)] = make_uint2(i0, s1 - s0);
+        }
+    }
+    (void)M;
+}
+
+__device__ __forceinline__ bool is_short_suffix(u32 s, int K, u32 n) { return (u64)s + (u64)K > (u64)n; }
+
+// emits one sorted position: SA, BWT row, and for members of a group of equal long keys the
+// group rank, the valid bit and a slot in the active list (warp-aggregated append)
+__device__ __forceinline__ void l3_emit(const L3Args &a, u32 g, u64 e, bool active, u32 group_head) {
+    const u32 s = (u32)e;
+    a.sa[g] = s;
+    if (a.bwt) a.bwt[g] = s ? (u8)(((u32)(e >> 32) & ((1u << a.pb) - 1u)) + 1u) : (u8)0;
+    if (s == 0) *a.primary = g;
+    const unsigned am = __ballot_sync(__activemask(), active);
+    if (active) {
+        a.rank[s] = group_head;
+        atomicOr(&a.valid[s >> 5], 1u << (s & 31u));
+        const unsigned lane = threadIdx.x & 31u;
+        const int leader = __ffs(am) - 1;
+        u32 base = 0;
+        if ((int)lane == leader) base = atomicAdd(a.act_count, (u32)__popc(am));
+        base = __shfl_sync(am, base, leader);
+        a.act[base + (u32)__popc(am & ((1u << lane) - 1u))] = s;
+    }
+}
+
+static constexpr size_t L3_SMEM = (size_t)L3_CAP * 8 + (size_t)(L3_CAP + 4) * 4 + (size_t)(L3_MASKW + 1) * 4 * 2 + 64 * 4;
+
+__global__ void __launch_bounds__(L3_NT, 2) msd_local_sort_kernel(L3Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *X = (u64 *)smem_raw;                         // [L3_CAP] elements grouped by bin
+    u32 *cnt = (u32 *)(X + L3_CAP);                   // [L3_CAP + 4] bin counts -> bin starts
+    u32 *segmask = cnt + (L3_CAP + 4);                // [MASKW + 1]
+    u32 *segpre = segmask + (L3_MASKW + 1);           // [MASKW + 1]
+    u32 *misc = segpre + (L3_MASKW + 1);              // [64]
+    uint2 *segtab = (uint2 *)X;                       // aliases X until the elements are scattered
+    u16 *perm = (u16 *)cnt;                           // aliases cnt once the bin starts are consumed
+
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u32 t = blockIdx.x;
+    const u32 b0 = a.tile_first[t], b1 = a.tile_first[t + 1];
+    if (b0 == b1) return;
+    const u32 E0 = a.bstart[b0], E1 = a.bstart[b1];
+    const u32 M = E1 - E0;
+    if (M == 0) return;
+
+    if (tid == 0) misc[32] = 0;  // crowded flag
+    for (u32 i = tid; i < (u32)L3_CAP + 4; i += L3_NT) cnt[i] = 0;
+    l3_segments(a.bstart, b0, b1, E0, M, segmask, segpre, segtab, L3_NT);
+    __syncthreads();
+
+    const int eshift = 32 + a.pb;
+    const u64 remmask = a.R >= 64 ? ~0ull : ((1ull << a.R) - 1ull);
+    const u64 *src = a.in + E0;
+
+    // ---- pass 1: bin = expected sorted position of the element inside its bucket ----
+    u32 meta[L3_IPT];
+#pragma unroll
+    for (int j = 0; j < L3_IPT; ++j) {
+        const u32 i = (u32)j * L3_NT + tid;
+        meta[j] = 0;
+        if (i < M) {
+            const u64 e = src[i];
+            const uint2 sg = segtab[seg_index(segmask, segpre, i)];
+            const u64 rem = (e >> eshift) & remmask;
+            const u32 bin = sg.x + (u32)((rem * (u64)sg.y) >> a.R);
+            const u32 slot = atomicAdd(&cnt[bin], 1u);
+            if (slot >= (u32)L3_CROWD) misc[32] = 1;
+            meta[j] = bin | (slot << 13);
+        }
+    }
+    __syncthreads();
+    if (misc[32]) {
+        if (tid == 0) a.flagged[atomicAdd(a.nflagged, 1u)] = t;
+        return;
+    }
+
+    // ---- exclusive scan of the bin counts (blocked: thread owns L3_IPT consecutive bins) ----
+    {
+        uint4 *c4 = (uint4 *)(cnt + tid * L3_IPT);
+        u32 v[L3_IPT];
+#pragma unroll
+        for (int q = 0; q < L3_IPT / 4; ++q) {
+            uint4 x = c4[q];
+            v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+        }
+        u32 sum = 0;
+#pragma unroll
+        for (int q = 0; q < L3_IPT; ++q) sum += v[q];
+        u32 incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 x = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += x;
+        }
+        if (lane == 31) misc[warp] = incl;
+        __syncthreads();
+        u32 run = incl - sum;
+        for (u32 w = 0; w < warp; ++w) run += misc[w];
+#pragma unroll
+        for (int q = 0; q < L3_IPT; ++q) {
+            u32 c = v[q];
+            v[q] = run;
+            run += c;
+        }
+#pragma unroll
+        for (int q = 0; q < L3_IPT / 4; ++q) c4[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        if (tid == L3_NT - 1) cnt[L3_CAP] = run;
+    }
+    __syncthreads();
+
+    // ---- pass 2: elements (re-read: L2 hits) go to their bin ----
+#pragma unroll
+    for (int j = 0; j < L3_IPT; ++j) {
+        const u32 i = (u32)j * L3_NT + tid;
+        if (i < M) {
+            const u64 e = src[i];
+            const u32 bin = meta[j] & 8191u, slot = meta[j] >> 13;
+            const u32 p0 = cnt[bin], p1 = cnt[bin + 1];
+            X[p0 + slot] = e;
+            meta[j] = p0 | (slot << 13) | ((p1 - p0) << 19);
+        }
+    }
+    __syncthreads();
+
+    // ---- order inside every bin: final slot = bin start + number of smaller elements ----
+#pragma unroll
+    for (int j = 0; j < L3_IPT; ++j) {
+        const u32 i = (u32)j * L3_NT + tid;
+        if (i < M) {
+            const u32 p0 = meta[j] & 8191u, slot = (meta[j] >> 13) & 63u, c = meta[j] >> 19;
+            if (c == 1) {
+                perm[p0] = (u16)p0;
+            } else {
+                const u64 e = X[p0 + slot];
+                const u64 ke = (e >> eshift) & remmask;
+                const u32 se = (u32)e;
+                const bool e_short = is_short_suffix(se, a.K, a.n);
+                u32 less = 0, active = 0;
+                for (u32 q = 0; q < c; ++q) {
+                    if (q == slot) continue;
+                    const u64 o = X[p0 + q];
+                    const u64 ko = (o >> eshift) & remmask;
+                    if (ko < ke) {
+                        ++less;
+                    } else if (ko == ke) {
+                        const u32 so = (u32)o;
+                        if (is_short_suffix(so, a.K, a.n)) {
+                            if (!e_short || so > se) ++less;   // short ones first, shortest first
+                        } else if (!e_short) {
+                            active = 1;                        // two long suffixes share the key
+                            if (q < slot) ++less;
+                        }
+                    }
+                }
+                perm[p0 + less] = (u16)((p0 + slot) | (active << 15));
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- output in sorted order (coalesced) ----
+    for (u32 i = tid; i < ((M + 31u) & ~31u); i += L3_NT) {
+        if (i < M) {
+            const u32 v = perm[i];
+            const u64 e = X[v & 8191u];
+            const bool active = v >> 15;
+            u32 h = i;
+            if (active) {
+                const u64 ke = (e >> eshift) & remmask;
+                while (h > 0 && !((segmask[h >> 5] >> (h & 31u)) & 1u)) {
+                    const u32 v2 = perm[h - 1];
+                    if (!(v2 >> 15)) break;
+                    if (((X[v2 & 8191u] >> eshift) & remmask) != ke) break;
+                    --h;
+                }
+            }
+            l3_emit(a, E0 + i, e, active, E0 + h);
+        }
+    }
+}
+
+// Robust variant for the tiles the fast kernel declined: bitonic sort of (composite key, element)
+// pairs.  composite = [segment : 13 | remaining key : 32 | long : 1 | n - s for short suffixes : 8]
+static constexpr size_t RB_SMEM = (size_t)RB_N * 8 * 2 + (size_t)(L3_MASKW + 1) * 4 * 2 + 64;
+
+__global__ void __launch_bounds__(L3_NT, 1) msd_local_sort_robust_kernel(L3Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *SK = (u64 *)smem_raw;            // [RB_N]
+    u64 *XV = SK + RB_N;                  // [RB_N]
+    u32 *segmask = (u32 *)(XV + RB_N);
+    u32 *segpre = segmask + (L3_MASKW + 1);
+    uint2 *segtab = (uint2 *)XV;          // only while the composites are formed
+
+    if (blockIdx.x >= *a.nflagged) return;
+    const u32 tid = threadIdx.x;
+    const u32 t = a.flagged[blockIdx.x];
+    const u32 b0 = a.tile_first[t], b1 = a.tile_first[t + 1];
+    const u32 E0 = a.bstart[b0], E1 = a.bstart[b1];
+    const u32 M = E1 - E0;
+    l3_segments(a.bstart, b0, b1, E0, M, segmask, segpre, segtab, L3_NT);
+    __syncthreads();
+    const int eshift = 32 + a.pb;
+    const u64 remmask = a.R >= 64 ? ~0ull : ((1ull << a.R) - 1ull);
+    u32 N = 32;
+    while (N < M) N <<= 1;
+    for (u32 i = tid; i < N; i += L3_NT) {
+        u64 sk = ~0ull;
+        if (i < M) {
+            const u64 e = a.in[E0 + i];
+            const u32 s = (u32)e;
+            const u64 seg = seg_index(segmask, segpre, i);
+            const u64 rem = (e >> eshift) & remmask;
+            const bool sh = is_short_suffix(s, a.K, a.n);
+            sk = (seg << 41) | (rem << 9) | (sh ? (u64)(a.n - s) : 256ull);
+        }
+        SK[i] = sk;
+    }
+    __syncthreads();
+    for (u32 i = tid; i < N; i += L3_NT) XV[i] = i < M ? a.in[E0 + i] : 0ull;
+    __syncthreads();
+    for (u32 k = 2; k <= N; k <<= 1) {
+        for (u32 j = k >> 1; j > 0; j >>= 1) {
+            for (u32 i = tid; i < N; i += L3_NT) {
+                const u32 x = i ^ j;
+                if (x > i) {
+                    const bool asc = (i & k) == 0;
+                    const u64 ka = SK[i], kb = SK[x];
+                    if ((ka > kb) == asc && ka != kb) {
+                        SK[i] = kb;
+                        SK[x] = ka;
+                        const u64 va = XV[i];
+                        XV[i] = XV[x];
+                        XV[x] = va;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (u32 i = tid; i < ((M + 31u) & ~31u); i += L3_NT) {
+        if (i < M) {
+            const u64 sk = SK[i];
+            const bool is_long = ((sk >> 8) & 1ull) != 0;
+            bool active = false;
+            u32 h = i;
+            if (is_long) {
+                active = (i > 0 && SK[i - 1] == sk) || (i + 1 < M && SK[i + 1] == sk);
+                while (h > 0 && SK[h - 1] == sk) --h;
+            }
+            l3_emit(a, E0 + i, XV[i], active, E0 + h);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fill_singleton_ranks_kernel(const u32 *__restrict__ sa, u32 len,
+                                                                   const u32 *__restrict__ valid, u32 *__restrict__ rank) {
+    u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= len) return;
+    u32 s = sa[g];
+    if (!((valid[s >> 5] >> (s & 31u)) & 1u)) rank[s] = (u32)g;
+}
+
+void fill_singleton_ranks(const DeviceIndex &ix, const u32 *valid, u32 *rank) {
+    fill_singleton_ranks_kernel<<<div_up_u(ix.len, 256), 256, 0, ix.stream>>>(ix.sa.ptr, ix.len, valid, rank);
+    KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host orchestration
+// ---------------------------------------------------------------------------------------------
+template <int BITS>
+static void launch_hist_text(const DeviceIndex &ix, u64 nwords_data, int D, u32 *hist, cudaStream_t st) {
+    unsigned blocks = div_up_u(nwords_data, 256 * 4);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks == 0) blocks = 1;
+    msd_hist_text_kernel<BITS><<<blocks, 256, 0, st>>>(ix.packed, ix.n, nwords_data, D, hist);
+    KERNEL_CHECK();
+}
+
+bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
+    cudaStream_t st = ix.stream;
+    Arena &ar = *ix.arena;
+    const MsdPlan &pl = r.plan;
+    const u32 n = ix.n, len = ix.len;
+    const int b = ix.pk.bits;
+
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_local_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L3_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_local_sort_robust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
+        configured = true;
+    }
+
+    // ---- tables ----
+    u64 nb[3] = {0, 0, 0};  // buckets after level l
+    {
+        u64 acc = 1;
+        for (int l = 0; l < pl.nlevels; ++l) {
+            acc <<= pl.D[l];
+            nb[l] = acc;
+        }
+    }
+    u32 *start[3], *cursor[3];
+    for (int l = 0; l < pl.nlevels; ++l) {
+        start[l] = ar.get<u32>(nb[l] + 1);
+        cursor[l] = ar.get<u32>(nb[l]);
+        CUDA_CHECK(cudaMemsetAsync(cursor[l], 0, nb[l] * 4, st));
+    }
+    u32 *d_misc = ar.get<u32>(8);  // 0: max final bucket, 1: tiles of the current level, 3: actives, 4: declined tiles
+    CUDA_CHECK(cudaMemsetAsync(d_misc, 0, 8 * 4, st));
+    const u32 ntl3 = div_up_u(len, L3_TSZ);
+    u32 *tile_first = ar.get<u32>((size_t)ntl3 + 2);
+    u32 *flagged = ar.get<u32>((size_t)ntl3 + 1);
+    size_t max_parents = pl.nlevels > 1 ? nb[pl.nlevels - 2] : 1;
+    size_t desc_cap = (size_t)div_up_u(len, P_TILE) + max_parents + 1;
+    uint4 *desc = pl.nlevels > 1 ? ar.get<uint4>(desc_cap) : nullptr;
+    u32 *tile_off = pl.nlevels > 1 ? ar.get<u32>(max_parents + 2) : nullptr;
+
+    const size_t valid_words = ((size_t)len + 31) / 32 + 2;
+    CUDA_CHECK(cudaMemsetAsync(r.valid, 0, valid_words * 4, st));
+
+    // ---- level 1: from the text ----
+    const u64 nwords_data = ((u64)len + ix.pk.cpw - 1) / ix.pk.cpw;
+    int t = ix.timer.begin("msd_hist1", (double)len * b / 8.0);
+    switch (b) {
+        case 1: launch_hist_text<1>(ix, nwords_data, pl.D[0], cursor[0], st); break;
+        case 2: launch_hist_text<2>(ix, nwords_data, pl.D[0], cursor[0], st); break;
+        case 4: launch_hist_text<4>(ix, nwords_data, pl.D[0], cursor[0], st); break;
+        default: launch_hist_text<8>(ix, nwords_data, pl.D[0], cursor[0], st); break;
+    }
+    {
+        unsigned bd = std::max(32u, (unsigned)nb[0]);
+        msd_scan_children_kernel<<<1, bd, 0, st>>>(cursor[0], nullptr, pl.D[0], 1, len, start[0],
+                                                   pl.nlevels == 1 ? d_misc : nullptr);
+        KERNEL_CHECK();
+    }
+    ix.timer.end(t);
+
+    PartArgs pa{};
+    pa.packed = ix.packed; pa.n = n; pa.len = len; pa.bits = b; pa.KB = pl.KB; pa.pb = pl.pb;
+    pa.rest_shift = 32 + pl.pb;
+    pa.in = nullptr; pa.out = r.bufA;
+    pa.D = pl.D[0];
+    pa.dshift = pl.KB - pl.D[0];
+    pa.restmask = pa.dshift >= 64 ? ~0ull : ((1ull << pa.dshift) - 1ull);
+    pa.cursor = cursor[0];
+    pa.desc = nullptr; pa.d_ntiles = nullptr;
+    t = ix.timer.begin("msd_part1", (double)len * (8.0 + b / 8.0));
+    msd_partition_kernel<true><<<div_up_u(len, P_TILE), P_NT, P_SMEM, st>>>(pa);
+    KERNEL_CHECK();
+    ix.timer.end(t);
+
+    u64 *cur = r.bufA, *other = r.bufB;
+    int consumed = pl.D[0];
+    for (int l = 1; l < pl.nlevels; ++l) {
+        const u32 nparents = (u32)nb[l - 1];
+        const int dshift = 32 + pl.pb + (pl.KB - consumed - pl.D[l]);
+        t = ix.timer.begin("msd_hist", (double)len * 8.0);
+        msd_tile_offsets_kernel<<<1, 1024, 0, st>>>(start[l - 1], nparents, tile_off, d_misc + 1);
+        KERNEL_CHECK();
+        msd_tile_desc_kernel<<<div_up_u(nparents, 8), 256, 0, st>>>(start[l - 1], nparents, tile_off, desc);
+        KERNEL_CHECK();
+        const unsigned grid = (unsigned)desc_cap;
+        msd_hist_elems_kernel<<<grid, P_NT, 0, st>>>(cur, desc, d_misc + 1, pl.D[l], dshift, cursor[l]);
+        KERNEL_CHECK();
+        {
+            unsigned bd = std::max(32u, 1u << pl.D[l]);
+            msd_scan_children_kernel<<<nparents, bd, 0, st>>>(cursor[l], start[l - 1], pl.D[l], nparents, len, start[l],
+                                                              l == pl.nlevels - 1 ? d_misc : nullptr);
+            KERNEL_CHECK();
+        }
+        ix.timer.end(t);
+        pa.in = cur; pa.out = other;
+        pa.D = pl.D[l];
+        pa.dshift = dshift;
+        pa.cursor = cursor[l];
+        pa.desc = desc; pa.d_ntiles = d_misc + 1;
+        t = ix.timer.begin("msd_part", (double)len * 16.0);
+        msd_partition_kernel<false><<<grid, P_NT, P_SMEM, st>>>(pa);
+        KERNEL_CHECK();
+        ix.timer.end(t);
+        std::swap(cur, other);
+        consumed += pl.D[l];
+    }
+
+    // ---- do the buckets fit one SM? ----
+    u32 maxbucket = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&maxbucket, d_misc, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (maxbucket > (u32)L3_MAXB) return false;
+
+    // ---- in-SM sort of every bucket, outputs of round 0 ----
+    const int last = pl.nlevels - 1;
+    t = ix.timer.begin("msd_local_sort", (double)len * (8.0 + 4.0 + (want_bwt && pl.pb ? 1.0 : 0.0)));
+    msd_tile_first_kernel<<<div_up_u(nb[last] + 1, 256), 256, 0, st>>>(start[last], nb[last], ntl3, tile_first);
+    KERNEL_CHECK();
+    L3Args la{};
+    la.in = cur; la.bstart = start[last]; la.tile_first = tile_first; la.n = n;
+    la.K = pl.K; la.pb = pl.pb; la.R = pl.R;
+    la.sa = ix.sa.ptr;
+    la.bwt = (want_bwt && pl.pb) ? ix.bwt.ptr : nullptr;
+    la.rank = r.rank; la.valid = r.valid; la.act = r.act; la.act_count = d_misc + 3;
+    la.primary = r.d_primary;
+    la.flagged = flagged; la.nflagged = d_misc + 4;
+    msd_local_sort_kernel<<<ntl3, L3_NT, L3_SMEM, st>>>(la);
+    KERNEL_CHECK();
+    u32 hmisc[8];
+    CUDA_CHECK(cudaMemcpyAsync(hmisc, d_misc, sizeof hmisc, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (hmisc[4]) {
+        msd_local_sort_robust_kernel<<<hmisc[4], L3_NT, RB_SMEM, st>>>(la);
+        KERNEL_CHECK();
+        CUDA_CHECK(cudaMemcpyAsync(hmisc, d_misc, sizeof hmisc, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    ix.timer.end(t);
+
+    r.bucket_start = start[last];
+    r.m = hmisc[3];
+    r.bwt_written = la.bwt != nullptr;
+    return true;
+}
+
+}  // namespace b200sa

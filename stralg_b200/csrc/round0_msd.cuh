@@ -1,0 +1,52 @@
+// round0_msd.cuh -- interface of the bucketed initial sort (round0_msd.cu) used by sa_build.cu.
+#pragma once
+#include "engine.h"
+
+namespace b200sa {
+
+// 64 bits of the packed text starting at symbol sym_index (big-endian inside each word)
+__device__ __forceinline__ u64 window_at(const u64 *__restrict__ packed, u64 sym_index, int bits) {
+    u64 bitpos = sym_index * (u64)bits;
+    u64 wi = bitpos >> 6;
+    unsigned o = (unsigned)(bitpos & 63);
+    u64 hi = packed[wi];
+    if (o == 0) return hi;
+    u64 lo = packed[wi + 1];
+    return (hi << o) | (lo >> (64 - o));
+}
+
+struct MsdPlan {
+    int nlevels;       // 1..3 partition levels
+    int D[3];          // digit bits per level (multiples of the symbol width)
+    int BB;            // total bucket bits = D[0] + D[1] + D[2]
+    int K;             // symbols in the round-0 key
+    int KB;            // K * bits
+    int pb;            // bits of the preceding symbol carried in an element (0: BWT is gathered afterwards)
+    int R;             // key bits left for the in-SM sort = KB - BB
+};
+
+struct Round0Msd {
+    // workspace handed in by the caller
+    u64 *bufA, *bufB;  // len elements each
+    u32 *act;          // len entries: receives the active suffixes
+    u32 *rank;         // len entries
+    u32 *valid;        // (len + 31) / 32 + 2 words, zeroed by round0_msd
+    u32 *d_primary;    // 1 word
+    // results
+    MsdPlan plan;
+    const u32 *bucket_start;  // 2^BB + 1 entries (workspace arena)
+    u32 m;                    // number of active suffixes written to act
+    bool bwt_written;         // BWT rows were emitted by the sort (else gather them from the final SA)
+};
+
+// Plans the levels for this text; false when the bucketed sort does not apply (e.g. disabled).
+bool msd_make_plan(u32 len, u32 sigma, int bits, MsdPlan &plan);
+
+// Sorts all suffixes by their first K symbols.  Returns false (nothing usable written) when a
+// bucket exceeds what one SM sorts in shared memory; the caller then runs the LSD path.
+bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r);
+
+// rank[sa[g]] = g for every suffix whose valid bit is clear (dense doubling rounds)
+void fill_singleton_ranks(const DeviceIndex &ix, const u32 *valid, u32 *rank);
+
+}  // namespace b200sa

@@ -20,6 +20,7 @@
 // After the last round rank[] is the inverse suffix array (stralg/suffix_array.c:55-62).
 #include "engine.h"
 #include "radix_sort.cuh"
+#include "round0_msd.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -27,20 +28,6 @@
 #include <vector>
 
 namespace b200sa {
-
-// ---------------------------------------------------------------------------------------------
-// Packed-text access
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ u64 window_at(const u64 *__restrict__ packed, u64 sym_index, int bits) {
-    // 64 bits of the packed stream starting at symbol sym_index (big-endian inside each word)
-    u64 bitpos = sym_index * (u64)bits;
-    u64 wi = bitpos >> 6;
-    unsigned o = (unsigned)(bitpos & 63);
-    u64 hi = packed[wi];
-    if (o == 0) return hi;
-    u64 lo = packed[wi + 1];
-    return (hi << o) | (lo >> (64 - o));
-}
 
 // ---------------------------------------------------------------------------------------------
 // pack_text: one thread per packed word.  err[0] is set if a code is 0 or >= sigma.
@@ -233,7 +220,9 @@ __global__ void __launch_bounds__(256) make_keys0_kernel(const u64 *__restrict__
 struct LazyRank {
     const u32 *rank;
     const u32 *valid;      // null: rank[] is complete (dense mode)
-    const u64 *keys0;      // round-0 sorted keys
+    const u64 *keys0;      // round-0 sorted keys (LSD round 0); null after the bucketed round 0
+    const u32 *bstart;     // bucketed round 0: start of every bucket (2^BB + 1 entries)
+    int BB;                // bucketed round 0: leading key bits that select the bucket
     const u32 *sa0;        // suffix array (round-0 order is final at singleton positions)
     const u64 *packed;
     u64 keymask;
@@ -243,12 +232,28 @@ struct LazyRank {
 
 __device__ __forceinline__ u32 lazy_rank_of(const LazyRank &lr, u32 t) {
     if (lr.valid == nullptr || ((lr.valid[t >> 5] >> (t & 31)) & 1u)) return lr.rank[t];
-    const u64 key = window_at(lr.packed, t, lr.bits) >> (64 - lr.K * lr.bits);
-    u32 lo = 0, hi = lr.len;  // first index with keys0 >= key
-    while (lo < hi) {
-        u32 mid = lo + (hi - lo) / 2;
-        if ((lr.keys0[mid] & lr.keymask) < key) lo = mid + 1;
-        else hi = mid;
+    const int kb = lr.K * lr.bits;
+    const u64 key = window_at(lr.packed, t, lr.bits) >> (64 - kb);
+    u32 lo, hi;  // first index with key(index) >= key
+    if (lr.keys0) {
+        lo = 0;
+        hi = lr.len;
+        while (lo < hi) {
+            u32 mid = lo + (hi - lo) / 2;
+            if ((lr.keys0[mid] & lr.keymask) < key) lo = mid + 1;
+            else hi = mid;
+        }
+    } else {
+        // the bucket is known from the leading bits; inside it the keys come from the text
+        const u64 bid = key >> (kb - lr.BB);
+        lo = lr.bstart[bid];
+        hi = lr.bstart[bid + 1];
+        while (lo < hi) {
+            u32 mid = lo + (hi - lo) / 2;
+            u64 km = window_at(lr.packed, lr.sa0[mid], lr.bits) >> (64 - kb);
+            if (km < key) lo = mid + 1;
+            else hi = mid;
+        }
     }
     const bool t_short = (u64)t + (u64)lr.K > (u64)lr.n;
     if (t_short) {
@@ -694,26 +699,10 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
     const int b = ix.pk.bits, cpw = ix.pk.cpw;
     const int c = RB / b;  // symbols per digit
 
-    // ---- round-0 key width ----
     int log2len = 0;
     while ((1ull << log2len) < (u64)len) ++log2len;
-    double eff = std::log2((double)(ix.sigma > 2 ? ix.sigma - 1 : 1));
-    if (eff < 0.5) eff = 0.5;
-    int margin = env_int("B200SA_KEY_MARGIN", 8);
-    int P0 = (int)std::ceil((log2len + margin) / (c * eff));
-    const int pshift = prev_shift_for(b);
-    int maxP = pshift / RB;  // the preceding-symbol field sits above the sorted digits
-    P0 = std::max(1, std::min(P0, maxP));
-    P0 = env_int("B200SA_PASSES0", P0);
-    P0 = std::max(1, std::min(P0, maxP));
-    const int K = c * P0;
-    const u64 keymask0 = (K * b >= 64) ? ~0ull : ((1ull << (K * b)) - 1ull);
-    ix.stats.k0 = K;
-    ix.stats.radix_bits = RB;
-    ix.stats.passes0 = P0;
-    ix.stats.rounds = 0;
+    ix.stats = BuildStats{};
     ix.stats.sorted_total = len;
-    ix.stats.passes_elems = (u64)len * P0;
 
     // ---- outputs (stream-ordered allocations that outlive the build) ----
     ix.sa.alloc(len, st);
@@ -732,72 +721,127 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
     u32 *valid = ar.get<u32>(valid_words);
     u64 *lookback = ar.get<u64>(S::lookback_words(len));
     u32 *hist = ar.get<u32>((size_t)8 * BINS), *uniform = ar.get<u32>(8), *ticket = ar.get<u32>(1);
-    u32 *bases0 = ar.get<u32>((size_t)P0 * BINS);
     size_t hb_bytes = (((size_t)len + 63) / 64 + 2) * 8;
     u8 *headbits = ar.get<u8>(hb_bytes);
     u32 *tile_counts = ar.get<u32>(div_up_u(len, CP_TILE) + 1);
     unsigned long long *d_total = ar.get<unsigned long long>(1);
 
-    // ---- round 0 ----
-    u64 nwords_data = ((u64)len + cpw - 1) / cpw;
+    u32 *sa = ix.sa.ptr;
+    u32 m = 0;           // suffixes whose round-0 key is shared with another suffix
+    u32 *act = valsV;    // ... listed here
+    int K = 0;
+    bool bwt_in_sort = true;  // BWT rows ride along with the sort (else: gathered from the final SA)
+    LazyRank lr{};
+    lr.rank = rank; lr.valid = valid; lr.sa0 = sa; lr.packed = ix.packed; lr.n = n; lr.len = len; lr.bits = b;
     int t;
-    t = ix.timer.begin("cmer_hist", (double)len * b / 8.0);
-    CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)BINS * 4, st));
-    launch_cmer_hist<RB>(ix, nwords_data, hist, st);
-    round0_bases_kernel<RB><<<P0, 256, 0, st>>>(hist, ix.packed, n, K, b, bases0);
-    KERNEL_CHECK();
-    ix.timer.end(t);
 
-    // the value ping-pong is arranged so that the last pass writes straight into the SA output
-    u64 *kin = keysA, *kout = keysB;
-    u32 *vin = (P0 % 2) ? valsV : ix.sa.ptr;
-    u32 *vout = (P0 % 2) ? ix.sa.ptr : valsV;
-    t = ix.timer.begin("make_keys0", (double)len * 12.0);
-    make_keys0_kernel<<<div_up_u(len, 256 * 4), 256, 0, st>>>(ix.packed, n, len, K, b, kin, vin);
-    KERNEL_CHECK();
-    ix.timer.end(t);
-    for (int p = 0; p < P0; ++p) {
-        t = ix.timer.begin("radix_pass0", (double)len * 24.0);
-        S::pass(kin, vin, kout, vout, len, p * RB, RB, bases0 + (size_t)p * BINS, lookback, ticket, st);
-        ix.timer.end(t);
-        std::swap(kin, kout);
-        std::swap(vin, vout);
+    // ---- round 0, preferred: MSD bucket sort of 8-byte elements (round0_msd.cu) ----
+    bool done0 = false;
+    {
+        Round0Msd r0{};
+        if (msd_make_plan(len, ix.sigma, b, r0.plan)) {
+            Arena::Mark mk = ar.mark();
+            r0.bufA = keysA; r0.bufB = keysB; r0.act = valsV; r0.rank = rank; r0.valid = valid;
+            r0.d_primary = d_primary.ptr;
+            done0 = round0_msd(ix, want_bwt, r0);
+            if (done0) {
+                m = r0.m;
+                K = r0.plan.K;
+                bwt_in_sort = r0.bwt_written;
+                lr.keys0 = nullptr; lr.bstart = r0.bucket_start; lr.BB = r0.plan.BB; lr.K = K;
+                lr.keymask = (K * b >= 64) ? ~0ull : ((1ull << (K * b)) - 1ull);
+                ix.stats.k0 = K;
+                ix.stats.radix_bits = r0.plan.D[0];
+                ix.stats.passes0 = r0.plan.nlevels;
+                ix.stats.round0_mode = 1;
+                ix.stats.bucket_bits = r0.plan.BB;
+                ix.stats.passes_elems = (u64)len * r0.plan.nlevels;
+            } else {
+                ar.release_to(mk);
+            }
+        }
     }
-    u32 *sa = ix.sa.ptr;  // == vin
-    const u64 *keys0 = kin;
 
-    t = ix.timer.begin("rank0", (double)len * 16.0);
-    CUDA_CHECK(cudaMemsetAsync(headbits, 0, hb_bytes, st));
-    CUDA_CHECK(cudaMemsetAsync(valid, 0, valid_words * 4, st));
+    // ---- round 0, general: LSD radix passes over (u64 key, u32 suffix) pairs ----
     RankArgs ra{};
-    ra.keys = keys0; ra.vals = sa; ra.m = len; ra.gs = 64; ra.keymask = keymask0; ra.K0 = K; ra.n = n;
-    ra.rank = rank; ra.valid = valid; ra.scatter_all = 0; ra.sa_out = nullptr; ra.headbits = headbits;
-    ra.bwt = want_bwt ? ix.bwt.ptr : nullptr; ra.prev_shift = pshift; ra.packed = ix.packed; ra.bits = b;
-    ra.primary = d_primary.ptr;
-    rank_kernel<<<div_up_u(len, RK_TILE), RK_NT, 0, st>>>(ra);
-    KERNEL_CHECK();
-    ix.timer.end(t);
+    if (!done0) {
+        double eff = std::log2((double)(ix.sigma > 2 ? ix.sigma - 1 : 1));
+        if (eff < 0.5) eff = 0.5;
+        int margin = env_int("B200SA_KEY_MARGIN", 8);
+        int P0 = (int)std::ceil((log2len + margin) / (c * eff));
+        const int pshift = prev_shift_for(b);
+        int maxP = pshift / RB;  // the preceding-symbol field sits above the sorted digits
+        P0 = std::max(1, std::min(P0, maxP));
+        P0 = env_int("B200SA_PASSES0", P0);
+        P0 = std::max(1, std::min(P0, maxP));
+        K = c * P0;
+        const u64 keymask0 = (K * b >= 64) ? ~0ull : ((1ull << (K * b)) - 1ull);
+        ix.stats.k0 = K;
+        ix.stats.radix_bits = RB;
+        ix.stats.passes0 = P0;
+        ix.stats.passes_elems = (u64)len * P0;
+        u32 *bases0 = ar.get<u32>((size_t)P0 * BINS);
 
-    t = ix.timer.begin("compact0", (double)len * 0.125);
-    u32 m = count_active(headbits, len, tile_counts, d_total, st);
-    u32 *act = valsV, *act2 = nullptr;  // valsV is free once the sort is done
-    if (m) scatter_active(headbits, sa, len, tile_counts, act, st);
-    ix.timer.end(t);
+        u64 nwords_data = ((u64)len + cpw - 1) / cpw;
+        t = ix.timer.begin("cmer_hist", (double)len * b / 8.0);
+        CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)BINS * 4, st));
+        launch_cmer_hist<RB>(ix, nwords_data, hist, st);
+        round0_bases_kernel<RB><<<P0, 256, 0, st>>>(hist, ix.packed, n, K, b, bases0);
+        KERNEL_CHECK();
+        ix.timer.end(t);
+
+        // the value ping-pong is arranged so that the last pass writes straight into the SA output
+        u64 *kin = keysA, *kout = keysB;
+        u32 *vin = (P0 % 2) ? valsV : ix.sa.ptr;
+        u32 *vout = (P0 % 2) ? ix.sa.ptr : valsV;
+        t = ix.timer.begin("make_keys0", (double)len * 12.0);
+        make_keys0_kernel<<<div_up_u(len, 256 * 4), 256, 0, st>>>(ix.packed, n, len, K, b, kin, vin);
+        KERNEL_CHECK();
+        ix.timer.end(t);
+        for (int p = 0; p < P0; ++p) {
+            t = ix.timer.begin("radix_pass0", (double)len * 24.0);
+            S::pass(kin, vin, kout, vout, len, p * RB, RB, bases0 + (size_t)p * BINS, lookback, ticket, st);
+            ix.timer.end(t);
+            std::swap(kin, kout);
+            std::swap(vin, vout);
+        }
+        const u64 *keys0 = kin;  // vin == ix.sa.ptr
+
+        t = ix.timer.begin("rank0", (double)len * 16.0);
+        CUDA_CHECK(cudaMemsetAsync(headbits, 0, hb_bytes, st));
+        CUDA_CHECK(cudaMemsetAsync(valid, 0, valid_words * 4, st));
+        ra.keys = keys0; ra.vals = sa; ra.m = len; ra.gs = 64; ra.keymask = keymask0; ra.K0 = K; ra.n = n;
+        ra.rank = rank; ra.valid = valid; ra.scatter_all = 0; ra.sa_out = nullptr; ra.headbits = headbits;
+        ra.bwt = want_bwt ? ix.bwt.ptr : nullptr; ra.prev_shift = pshift; ra.packed = ix.packed; ra.bits = b;
+        ra.primary = d_primary.ptr;
+        rank_kernel<<<div_up_u(len, RK_TILE), RK_NT, 0, st>>>(ra);
+        KERNEL_CHECK();
+        ix.timer.end(t);
+
+        t = ix.timer.begin("compact0", (double)len * 0.125);
+        m = count_active(headbits, len, tile_counts, d_total, st);
+        if (m) scatter_active(headbits, sa, len, tile_counts, act, st);  // valsV is free once the sort is done
+        ix.timer.end(t);
+        lr.keys0 = keys0; lr.keymask = keymask0; lr.K = K;
+    }
 
     // ---- doubling rounds over the active set ----
+    u8 *bwt_rows = (want_bwt && bwt_in_sort) ? ix.bwt.ptr : nullptr;
     if (m) {
         const bool dense = (u64)m * 8 > (u64)len;
-        LazyRank lr{};
-        lr.rank = rank; lr.valid = valid; lr.keys0 = keys0; lr.sa0 = sa; lr.packed = ix.packed;
-        lr.keymask = keymask0; lr.n = n; lr.len = len; lr.K = K; lr.bits = b;
+        u32 *act2 = nullptr;
         u64 *rkA, *rkB;
         if (dense) {
-            // most suffixes are still active: materialise every rank, then the round-0 keys are dead
+            // most suffixes are still active: materialise every rank, then the round-0 buffers are dead
             t = ix.timer.begin("rank0_fill", (double)len * 16.0);
-            RankArgs rf = ra;
-            rf.scatter_all = 1;
-            rank_kernel<<<div_up_u(len, RK_TILE), RK_NT, 0, st>>>(rf);
-            KERNEL_CHECK();
+            if (done0) {
+                fill_singleton_ranks(ix, valid, rank);
+            } else {
+                RankArgs rf = ra;
+                rf.scatter_all = 1;
+                rank_kernel<<<div_up_u(len, RK_TILE), RK_NT, 0, st>>>(rf);
+                KERNEL_CHECK();
+            }
             ix.timer.end(t);
             lr.valid = nullptr;
             rkA = keysA;
@@ -844,7 +888,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
             RankArgs rr{};
             rr.keys = rin; rr.vals = ain; rr.m = m; rr.gs = lo_bits; rr.keymask = ~0ull; rr.K0 = 0; rr.n = n;
             rr.rank = rank; rr.valid = nullptr; rr.scatter_all = 0; rr.sa_out = sa; rr.headbits = headbits;
-            rr.bwt = want_bwt ? ix.bwt.ptr : nullptr; rr.prev_shift = 0; rr.packed = ix.packed; rr.bits = b;
+            rr.bwt = bwt_rows; rr.prev_shift = 0; rr.packed = ix.packed; rr.bits = b;
             rr.primary = d_primary.ptr;
             rank_kernel<<<div_up_u(m, RK_TILE), RK_NT, 0, st>>>(rr);
             KERNEL_CHECK();
@@ -864,6 +908,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
     }
     CUDA_CHECK(cudaMemcpyAsync(&ix.primary, d_primary.ptr, 4, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
+    if (want_bwt && !bwt_in_sort) gather_bwt(ix);  // the element had no room for the preceding symbol
 }
 
 void build_suffix_array(DeviceIndex &ix, bool want_bwt) {

@@ -39,6 +39,16 @@ def texts():
         a, b = b, b + a
     out.append(("fibonacci_100000", np.array(b[:100000]), 3))
     out.append(("dna_tail_poly_a", np.concatenate([rng.integers(1, 5, 5000), np.ones(300, dtype=np.int64)]), 5))
+    # small repetitive texts: buckets fit one SM but whole bins hold equal keys (robust in-SM sort)
+    out.append(("unary_sigma2_3000", np.ones(3000, dtype=np.int64), 2))
+    out.append(("unary_sigma5_2500", np.full(2500, 2), 5))
+    out.append(("period3_3500", np.tile([2, 1, 3], 1200)[:3500], 5))
+    out.append(("period50_3900", np.tile(rng.integers(1, 5, 50), 80)[:3900], 5))
+    # a short suffix ("A$", padded with A) ties with a few long suffixes inside a run of A
+    out.append(("dna_short_tie", np.concatenate([rng.integers(1, 5, 3000), np.ones(14, dtype=np.int64),
+                                                 rng.integers(2, 5, 2000), [2, 1]]), 5))
+    out.append(("dna_short_tie2", np.concatenate([rng.integers(1, 5, 200000), np.ones(16, dtype=np.int64),
+                                                  rng.integers(2, 5, 2000), [1, 1, 1]]), 5))
     out.append(("dna_1M", rng.integers(1, 5, 1 << 20), 5))
     out.append(("repeat_rich_1M", np.tile(rng.integers(1, 5, 40000), 27)[: (1 << 20) - 3], 5))
     return out
@@ -47,15 +57,31 @@ def texts():
 TEXTS = texts()
 
 
-@pytest.mark.parametrize("radix_bits", [8, 10])
+# how round 0 (the initial K-symbol sort) runs: the default MSD bucket sort, the same with tiny
+# digits (three partition levels even on small texts) or many small buckets per tile, and the
+# LSD radix passes (also the path of texts whose buckets exceed one SM) at both digit widths
+ROUND0_MODES = {
+    "msd": {},
+    "msd_3level": {"B200SA_MSD_DMAX": "4", "B200SA_MSD_BB": "12"},
+    "msd_avg64": {"B200SA_MSD_AVG": "64"},
+    "lsd8": {"B200SA_ROUND0": "lsd", "B200SA_RADIX_BITS": "8"},
+    "lsd10": {"B200SA_ROUND0": "lsd", "B200SA_RADIX_BITS": "10"},
+}
+
+
+@pytest.mark.parametrize("mode", list(ROUND0_MODES))
 @pytest.mark.parametrize("case", TEXTS, ids=[t[0] for t in TEXTS])
-def test_suffix_array_tables_match_oracle(engine, oracle, ref, case, radix_bits, monkeypatch):
-    monkeypatch.setenv("B200SA_RADIX_BITS", str(radix_bits))
+def test_suffix_array_tables_match_oracle(engine, oracle, ref, case, mode, monkeypatch):
+    for k, v in ROUND0_MODES[mode].items():
+        monkeypatch.setenv(k, v)
     name, sym, sigma = case
     codes = np.concatenate([np.asarray(sym, dtype=np.uint8), np.zeros(1, np.uint8)])
     idx = engine.SuffixArrayIndex.build(codes[:-1], sigma, isa=True, lcp=True, bwt=True, occ=True)
     sa_exp = expected_sa(oracle, ref, codes, sigma)
     sa = idx.sa()
+    if name.startswith(("dna_", "sym", "byte_", "bin_")):
+        # random texts must really take the path under test (no silent fallback)
+        assert idx.stats()["round0_mode"] == (1 if mode.startswith("msd") else 0), (name, idx.stats())
     assert np.array_equal(sa, sa_exp), f"{name}: first mismatch at {np.nonzero(sa != sa_exp)[0][:5]}"
     assert np.array_equal(idx.isa(), oracle.inverse(sa_exp))
     lcp_exp = oracle.lcp(codes, sa_exp)
