@@ -111,6 +111,17 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# build stage (library timer name) -> the kernel it brackets
+STAGE_KERNELS = {
+    "msd_local_sort": "msd_local_sort_kernel (in-SM sort of the final buckets; emits SA, BWT rows, ranks of shared keys)",
+    "msd_part1": "msd_partition_kernel<FROM_TEXT> (level-1 partition, elements formed from the packed text)",
+    "msd_part": "msd_partition_kernel (level-2 partition of 8-byte elements)",
+    "msd_hist": "msd_hist_elems_kernel (level-2 digit histogram)",
+    "radix_pass0": "onesweep_pass_kernel (LSD round 0, one digit)",
+    "radix_pass": "onesweep_pass_kernel (doubling round, one digit)",
+}
+
+
 def load_traffic(kernel_key):
     """ncu dram bytes per launch of the dominant kernel, if a capture was summarised in profiles/."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -327,17 +338,20 @@ def gpu_arm(args, rank, local_rank, world):
         value = n / (ms_step / 1e3) / 1e6
         clocks = sampler.summary(t_wall0, t_wall1)
 
-        # roofline of the dominant kernel: one radix pass over (u64 key, u32 suffix) pairs
-        rp = stage_ms.get("radix_pass0", [1, 1.0, 0.0])
-        pass_ms = rp[1] / rp[0]
-        pass_bytes = 24.0 * (n + 1)
+        # roofline of the dominant kernel = the build stage with the largest share of the step; its
+        # algorithmic bytes per launch are what the library's stage timer records,
+        # its duration comes from CUDA events on the launching stream around that launch.
+        dom = max(stage_ms.items(), key=lambda kv: kv[1][1])
+        dname, (dlaunch, dms, dbytes) = dom[0], dom[1]
+        pass_ms = dms / dlaunch
+        pass_bytes = dbytes / dlaunch
         achieved = pass_bytes / (pass_ms / 1e3) / 1e9
-        traffic = load_traffic("radix_pass0")
-        roofline = {"bound": "hbm", "kernel": "onesweep_pass_kernel (initial sort, one 8-bit digit)",
+        traffic = load_traffic(dname)
+        roofline = {"bound": "hbm", "kernel": STAGE_KERNELS.get(dname, dname), "stage": dname,
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": pass_bytes, "avg_launch_ms": pass_ms,
-                    "launches_timed": rp[0]}
+                    "launches_timed": dlaunch, "share_of_step": dms / ms_total}
         model_bytes = 244.5 * n  # 237 B/char SA + 7.5 B/char BWT/C/O
         stages = {k: {"launches": v[0], "ms_per_step": v[1] / args.steps,
                       "algorithmic_GBps": (v[2] / v[1] / 1e6) if v[1] else None} for k, v in stage_ms.items()}

@@ -1,0 +1,76 @@
+"""Read sharding for batched exact search over a REPLICATED index (BASELINE configs[3]).
+
+The reference maps one read at a time (tools/readmappers/bwt_readmapper/bwt_readmapper.c:128-161);
+reads are independent, so the batched path splits them into contiguous shards, one per rank
+(one process per GPU), every rank searches its shard against its own copy of the index, and ONE
+collective gathers the fixed-width (L, R) pairs on rank 0.  No collective sits on the data path
+of the search itself.
+
+Nothing here computes: ``search_fn`` is the engine's device search (``SuffixArrayIndex.search_device``)
+in the product; the world_size-2 ``gloo`` tests on CPU plug the oracle in instead to check the
+partition / gather logic.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+
+def shard_bounds(total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of ``total`` reads for ``rank``: sizes differ by at most one,
+    the first ``total % world`` ranks take the extra read."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world: {rank}/{world}")
+    base, extra = divmod(int(total), world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def max_shard(total: int, world: int) -> int:
+    return -(-int(total) // world)
+
+
+class ShardedSearch:
+    """Searches this rank's shard and gathers all (L, R) pairs on ``dst``.
+
+    ``dist`` is ``torch.distributed`` (initialised, NCCL on GPUs / gloo in the CPU tests) or None
+    for a single process.  Buffers are allocated once; ``step()`` is what a bench step times.
+    """
+
+    def __init__(self, total_reads: int, read_len: int, device, dist=None, dst: int = 0):
+        import torch
+        self.torch = torch
+        self.dist = dist
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.dst = dst
+        self.total = int(total_reads)
+        self.m = int(read_len)
+        self.lo, self.hi = shard_bounds(self.total, self.world, self.rank)
+        self.count = self.hi - self.lo
+        self.cap = max_shard(self.total, self.world)  # gather needs equal-size pieces
+        self.LR = torch.zeros((2, self.cap), dtype=torch.int32, device=device)
+        self.gathered = None
+        if dist is not None and self.rank == dst:
+            self.gathered = [torch.empty((2, self.cap), dtype=torch.int32, device=device) for _ in range(self.world)]
+
+    def step(self, search_fn: Callable, reads) -> None:
+        """search_fn(reads, read_len, count, L_out, R_out) fills the first ``count`` slots."""
+        if self.count:
+            search_fn(reads, self.m, self.count, self.LR[0], self.LR[1])
+        if self.dist is not None:
+            self.dist.gather(self.LR, self.gathered, dst=self.dst)
+
+    def result(self) -> Optional[Tuple["object", "object"]]:
+        """(L, R) of all reads in input order on ``dst`` (int32 bit patterns of the uint32 values);
+        None on the other ranks."""
+        torch = self.torch
+        if self.dist is None:
+            return self.LR[0, :self.count], self.LR[1, :self.count]
+        if self.rank != self.dst:
+            return None
+        Ls, Rs = [], []
+        for g in range(self.world):
+            lo, hi = shard_bounds(self.total, self.world, g)
+            Ls.append(self.gathered[g][0, :hi - lo])
+            Rs.append(self.gathered[g][1, :hi - lo])
+        return torch.cat(Ls), torch.cat(Rs)

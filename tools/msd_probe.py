@@ -59,7 +59,7 @@ def run(n, nsym):
     bwt_a = view(a.device_ptr("bwt"), n + 1, torch.uint8).clone()
     pa = a.primary
     a.close()
-    if n <= (1 << 31):
+    if n <= (1 << 31) and not MSD_ONLY:
         b = build(text, n, nsym, "lsd")
         sa_b = view(b.device_ptr("sa"), n + 1, torch.int32)
         bwt_b = view(b.device_ptr("bwt"), n + 1, torch.uint8)
@@ -72,6 +72,8 @@ def run(n, nsym):
         b.close()
     sys.stdout.flush()
 
+
+MSD_ONLY = len(sys.argv) > 3 and sys.argv[3] == "msd"
 
 if __name__ == "__main__":
     sizes = [int(float(x)) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1 << 24]
