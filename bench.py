@@ -436,8 +436,10 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
     # search index: C + sampled O, plus SA / ISA / packed text for the unique-interval shortcut
     idx = build(textcmp=True)
     lib.b200sa_release_workspace(local_rank)
-    shard = total_reads // world
-    total_reads = shard * world
+    # contiguous shards of the read set, one per rank; one NCCL gather of (L, R) to rank 0 per step
+    from stralg_b200.shard import ShardedSearch
+    ss = ShardedSearch(total_reads, m, dev, dist)
+    shard = ss.count
 
     def gen_reads(count, seed):
         r = torch.empty(count * m, dtype=torch.uint8, device=dev)
@@ -446,15 +448,13 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
         return r
 
     reads = gen_reads(shard, SEED + 1 + rank * 7919)
-    LR = torch.empty((2, shard), dtype=torch.int32, device=dev)
-    gathered = None
-    if dist is not None and rank == 0:
-        gathered = [torch.empty((2, shard), dtype=torch.int32, device=dev) for _ in range(world)]
+    LR = ss.LR
+
+    def search_fn(r, mm, count, Lo, Ro):
+        idx.search_device(r, None, mm, count, Lo, Ro, stream)
 
     def step():
-        idx.search_device(reads, None, m, shard, LR[0], LR[1], stream)
-        if dist is not None:
-            dist.gather(LR, gathered, dst=0)
+        ss.step(search_fn, reads)
 
     def barrier():
         if dist is not None:
@@ -486,8 +486,8 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
     value = total_reads / (ms_step / 1e3)
 
     # steps actually executed per read -> algorithmic bytes (m + 2*steps*32 + 8)
-    Lh = LR[0].cpu().numpy().view(np.uint32)
-    Rh = LR[1].cpu().numpy().view(np.uint32)
+    Lh = LR[0, :shard].cpu().numpy().view(np.uint32)
+    Rh = LR[1, :shard].cpu().numpy().view(np.uint32)
     hit_frac = float((Rh > Lh).mean())
     # kernel-only timing of one rank's shard
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

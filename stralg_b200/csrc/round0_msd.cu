@@ -387,6 +387,172 @@ __global__ void __launch_bounds__(P_NT, 2) msd_partition_kernel(PartArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Level-1 partition straight from the packed text.  A tile is T1_TILE consecutive suffix starts;
+// its slice of the packed text (<= 8 KB) is staged in shared memory once, and a thread forms
+// T1_IPT CONSECUTIVE elements from one 128-bit window by shifting, instead of two global loads
+// per element.  Elements are not kept in registers across the digit scan: they are formed again
+// from the staged text when the tile is grouped by digit.
+// ---------------------------------------------------------------------------------------------
+static constexpr int T1_NT = 512;
+static constexpr int T1_IPT = 16;
+static constexpr int T1_TILE = T1_NT * T1_IPT;     // 8192 suffix starts
+static constexpr int T1_STAGE_MAX = T1_TILE * 8 / 64 + 4;
+static constexpr size_t T1_SMEM = (size_t)T1_TILE * 8 + (size_t)MSD_MAXBINS * 4 * 2 + (size_t)T1_TILE * 2 +
+                                  (size_t)T1_STAGE_MAX * 8 + 32 * 4;
+
+// exclusive prefix of `v` over a 512-thread block (wsum: 16 words of shared memory)
+__device__ __forceinline__ u32 block512_exclusive(u32 v, u32 *wsum) {
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    u32 incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    u32 ws = lane < 16 ? wsum[lane] : 0u;
+    u32 wi = ws;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= (unsigned)o) wi += t;
+    }
+    const u32 wbase = __shfl_sync(0xffffffffu, wi - ws, warp);
+    return wbase + incl - v;
+}
+
+struct Text1Args {
+    const u64 *packed;
+    u64 nwords;       // words readable in `packed` (data + zero padding)
+    u64 *out;
+    u32 len;
+    int bits, KB, pb;
+    int D, dshift;    // digit = key >> dshift
+    u64 restmask;     // rest = key & restmask
+    int rest_shift;   // 32 + pb
+    u32 *cursor;      // [1 << D] next free slot of every level-1 bucket
+};
+
+// 128-bit window (H:L) of the staged text starting at bit `off`
+__device__ __forceinline__ void stage_window(const u64 *st, u32 off, u64 &H, u64 &L) {
+    const u32 w = off >> 6, o = off & 63u;
+    const u64 w0 = st[w], w1 = st[w + 1], w2 = st[w + 2];
+    H = o ? (w0 << o) | (w1 >> (64 - o)) : w0;
+    L = o ? (w1 << o) | (w2 >> (64 - o)) : w1;
+}
+
+__global__ void __launch_bounds__(T1_NT, 2) msd_partition_text_kernel(Text1Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *buf = (u64 *)smem_raw;                   // [T1_TILE] elements grouped by digit
+    u64 *stage = buf + T1_TILE;                   // [T1_STAGE_MAX] packed text of the tile (one word of lead-in)
+    u32 *hist = (u32 *)(stage + T1_STAGE_MAX);    // [MAXBINS] counts, then tile-local offsets
+    u32 *gofs = hist + MSD_MAXBINS;               // [MAXBINS] global slot of the digit's run minus its tile offset
+    u16 *dig = (u16 *)(gofs + MSD_MAXBINS);       // [T1_TILE] digit of the element in slot i
+    u32 *wsum = (u32 *)(dig + T1_TILE);           // [32]
+
+    const u32 tid = threadIdx.x;
+    const u32 B = 1u << a.D;
+    const int b = a.bits;
+    const u64 begin = (u64)blockIdx.x * T1_TILE;
+    const u32 count = (u32)min((u64)T1_TILE, (u64)a.len - begin);
+
+    // ---- stage the tile's text: word k of `stage` is packed[begin*b/64 - 1 + k] ----
+    {
+        const u32 nstage = (u32)(T1_TILE / 64) * b + 4;
+        const u64 w0 = begin * (u64)b / 64;
+        for (u32 k = tid; k < nstage; k += T1_NT) {
+            const u64 w = w0 + k;  // index + 1
+            stage[k] = (w >= 1 && w - 1 < a.nwords) ? a.packed[w - 1] : 0ull;
+        }
+        for (u32 i = tid; i < B; i += T1_NT) hist[i] = 0;
+    }
+    __syncthreads();
+
+    // bit offset (inside `stage`) of the window of the thread's first position: it starts at the
+    // preceding symbol when that symbol is carried in the element, else at the position itself
+    const u32 lead = a.pb ? (u32)b : 0u;
+    const u32 i0 = tid * T1_IPT;
+    const u32 off0 = 64u + i0 * (u32)b - lead;
+    const int kshift = 64 - a.KB;
+
+    // ---- digits and slots inside the tile's digit groups (arbitrary order: MSD) ----
+    u32 ds[T1_IPT];
+#pragma unroll
+    for (int g = 0; g < T1_IPT / 8; ++g) {
+        u64 H, L;
+        stage_window(stage, off0 + (u32)(8 * g) * (u32)b, H, L);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int j = 8 * g + q;
+            const u32 sh = (u32)q * (u32)b;
+            const u64 win = sh ? (H << sh) | (L >> (64 - sh)) : H;
+            const u64 key = (win << lead) >> kshift;
+            ds[j] = 0;
+            if (i0 + j < count) {
+                const u32 d = (u32)(key >> a.dshift);
+                const u32 slot = atomicAdd(&hist[d], 1u);
+                ds[j] = d | (slot << 10);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- exclusive scan of the digit counts; reserve the runs in the level-1 buckets ----
+    {
+        constexpr int DPT = MSD_MAXBINS / T1_NT;  // 2
+        const u32 d0 = tid * DPT;
+        u32 c[DPT], g[DPT];
+        u32 sum = 0;
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) {
+            c[q] = d0 + q < B ? hist[d0 + q] : 0u;
+            sum += c[q];
+        }
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) {
+            g[q] = 0;
+            if (c[q]) g[q] = atomicAdd(&a.cursor[d0 + q], c[q]);
+        }
+        u32 run = block512_exclusive(sum, wsum);
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) {
+            if (d0 + q < B) {
+                hist[d0 + q] = run;
+                gofs[d0 + q] = g[q] - run;
+            }
+            run += c[q];
+        }
+    }
+    __syncthreads();
+
+    // ---- form the elements (again from the staged text) and group the tile by digit ----
+#pragma unroll
+    for (int g = 0; g < T1_IPT / 8; ++g) {
+        u64 H, L;
+        stage_window(stage, off0 + (u32)(8 * g) * (u32)b, H, L);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int j = 8 * g + q;
+            if (i0 + j < count) {
+                const u32 sh = (u32)q * (u32)b;
+                const u64 win = sh ? (H << sh) | (L >> (64 - sh)) : H;
+                const u64 key = (win << lead) >> kshift;
+                const u64 prev = a.pb ? win >> (64 - b) : 0ull;
+                const u32 d = ds[j] & 1023u;
+                const u32 pos = hist[d] + (ds[j] >> 10);
+                buf[pos] = ((key & a.restmask) << a.rest_shift) | (prev << 32) | (begin + i0 + j);
+                dig[pos] = (u16)d;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- consecutive threads write consecutive slots of a digit run ----
+    for (u32 i = tid; i < count; i += T1_NT) a.out[gofs[dig[i]] + i] = buf[i];
+}
+
+// ---------------------------------------------------------------------------------------------
 // Local-sort tiles: tile t owns the buckets whose first element lies in [t*TSZ, (t+1)*TSZ).
 // tile_first[t] = smallest bucket b with bstart[b] >= t*TSZ  (b in [0, nb]; bstart[nb] = len)
 // ---------------------------------------------------------------------------------------------
@@ -507,7 +673,8 @@ __global__ void __launch_bounds__(L3_NT, 2) msd_local_sort_kernel(L3Args a) {
     if (M == 0) return;
 
     if (tid == 0) misc[32] = 0;  // crowded flag
-    for (u32 i = tid; i < (u32)L3_CAP + 4; i += L3_NT) cnt[i] = 0;
+    // bins [0, M) are used; the blocked scan below reads up to 11 entries past bin M
+    for (u32 i = tid; i < min((u32)L3_CAP + 4u, M + 16u); i += L3_NT) cnt[i] = 0;
     l3_segments(a.bstart, b0, b1, E0, M, segmask, segpre, segtab, L3_NT);
     __syncthreads();
 
@@ -521,6 +688,7 @@ __global__ void __launch_bounds__(L3_NT, 2) msd_local_sort_kernel(L3Args a) {
     for (int j = 0; j < L3_IPT; ++j) {
         const u32 i = (u32)j * L3_NT + tid;
         meta[j] = 0;
+        if ((u32)j * L3_NT >= M) break;
         if (i < M) {
             const u64 e = src[i];
             const uint2 sg = segtab[seg_index(segmask, segpre, i)];
@@ -540,10 +708,11 @@ __global__ void __launch_bounds__(L3_NT, 2) msd_local_sort_kernel(L3Args a) {
     // ---- exclusive scan of the bin counts (blocked: thread owns L3_IPT consecutive bins) ----
     {
         uint4 *c4 = (uint4 *)(cnt + tid * L3_IPT);
+        const bool mine = tid * L3_IPT <= M;  // bins past M are empty (and were not zeroed)
         u32 v[L3_IPT];
 #pragma unroll
         for (int q = 0; q < L3_IPT / 4; ++q) {
-            uint4 x = c4[q];
+            uint4 x = mine ? c4[q] : make_uint4(0u, 0u, 0u, 0u);
             v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
         }
         u32 sum = 0;
@@ -565,8 +734,10 @@ __global__ void __launch_bounds__(L3_NT, 2) msd_local_sort_kernel(L3Args a) {
             v[q] = run;
             run += c;
         }
+        if (mine) {
 #pragma unroll
-        for (int q = 0; q < L3_IPT / 4; ++q) c4[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            for (int q = 0; q < L3_IPT / 4; ++q) c4[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
         if (tid == L3_NT - 1) cnt[L3_CAP] = run;
     }
     __syncthreads();
@@ -575,6 +746,7 @@ __global__ void __launch_bounds__(L3_NT, 2) msd_local_sort_kernel(L3Args a) {
 #pragma unroll
     for (int j = 0; j < L3_IPT; ++j) {
         const u32 i = (u32)j * L3_NT + tid;
+        if ((u32)j * L3_NT >= M) break;
         if (i < M) {
             const u64 e = src[i];
             const u32 bin = meta[j] & 8191u, slot = meta[j] >> 13;
@@ -586,27 +758,34 @@ __global__ void __launch_bounds__(L3_NT, 2) msd_local_sort_kernel(L3Args a) {
     __syncthreads();
 
     // ---- order inside every bin: final slot = bin start + number of smaller elements ----
+    // The high word of an element is [rest of key | preceding symbol]; inside a bucket its bits
+    // above `pb` order the elements, so the common case compares 32-bit words.  Equal keys
+    // (a short suffix next to its padded twin, or two long suffixes that stay active) are rare
+    // and take the tie-break loop.
+    const u32 *Xh = (const u32 *)X;
 #pragma unroll
     for (int j = 0; j < L3_IPT; ++j) {
         const u32 i = (u32)j * L3_NT + tid;
+        if ((u32)j * L3_NT >= M) break;
         if (i < M) {
             const u32 p0 = meta[j] & 8191u, slot = (meta[j] >> 13) & 63u, c = meta[j] >> 19;
             if (c == 1) {
                 perm[p0] = (u16)p0;
             } else {
-                const u64 e = X[p0 + slot];
-                const u64 ke = (e >> eshift) & remmask;
-                const u32 se = (u32)e;
-                const bool e_short = is_short_suffix(se, a.K, a.n);
-                u32 less = 0, active = 0;
+                const u32 ke = Xh[2 * (p0 + slot) + 1] >> a.pb;
+                u32 less = 0, eq = 0;
                 for (u32 q = 0; q < c; ++q) {
-                    if (q == slot) continue;
-                    const u64 o = X[p0 + q];
-                    const u64 ko = (o >> eshift) & remmask;
-                    if (ko < ke) {
-                        ++less;
-                    } else if (ko == ke) {
-                        const u32 so = (u32)o;
+                    const u32 ko = Xh[2 * (p0 + q) + 1] >> a.pb;
+                    less += ko < ke ? 1u : 0u;
+                    eq += ko == ke ? 1u : 0u;
+                }
+                u32 active = 0;
+                if (eq > 1) {
+                    const u32 se = Xh[2 * (p0 + slot)];
+                    const bool e_short = is_short_suffix(se, a.K, a.n);
+                    for (u32 q = 0; q < c; ++q) {
+                        if (q == slot || (Xh[2 * (p0 + q) + 1] >> a.pb) != ke) continue;
+                        const u32 so = Xh[2 * (p0 + q)];
                         if (is_short_suffix(so, a.K, a.n)) {
                             if (!e_short || so > se) ++less;   // short ones first, shortest first
                         } else if (!e_short) {
@@ -750,7 +929,7 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
 
     static bool configured = false;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_partition_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_local_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L3_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_local_sort_robust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
@@ -802,19 +981,26 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     }
     ix.timer.end(t);
 
+    {
+        Text1Args ta{};
+        ta.packed = ix.packed;
+        ta.nwords = nwords_data + 4;  // pack_text pads with 4 zero words
+        ta.out = r.bufA;
+        ta.len = len; ta.bits = b; ta.KB = pl.KB; ta.pb = pl.pb;
+        ta.D = pl.D[0];
+        ta.dshift = pl.KB - pl.D[0];
+        ta.restmask = ta.dshift >= 64 ? ~0ull : ((1ull << ta.dshift) - 1ull);
+        ta.rest_shift = 32 + pl.pb;
+        ta.cursor = cursor[0];
+        t = ix.timer.begin("msd_part1", (double)len * (8.0 + b / 8.0));
+        msd_partition_text_kernel<<<div_up_u(len, T1_TILE), T1_NT, T1_SMEM, st>>>(ta);
+        KERNEL_CHECK();
+        ix.timer.end(t);
+    }
     PartArgs pa{};
     pa.packed = ix.packed; pa.n = n; pa.len = len; pa.bits = b; pa.KB = pl.KB; pa.pb = pl.pb;
     pa.rest_shift = 32 + pl.pb;
-    pa.in = nullptr; pa.out = r.bufA;
-    pa.D = pl.D[0];
-    pa.dshift = pl.KB - pl.D[0];
-    pa.restmask = pa.dshift >= 64 ? ~0ull : ((1ull << pa.dshift) - 1ull);
-    pa.cursor = cursor[0];
-    pa.desc = nullptr; pa.d_ntiles = nullptr;
-    t = ix.timer.begin("msd_part1", (double)len * (8.0 + b / 8.0));
-    msd_partition_kernel<true><<<div_up_u(len, P_TILE), P_NT, P_SMEM, st>>>(pa);
-    KERNEL_CHECK();
-    ix.timer.end(t);
+    pa.restmask = 0;
 
     u64 *cur = r.bufA, *other = r.bufB;
     int consumed = pl.D[0];
