@@ -652,13 +652,17 @@ __device__ __forceinline__ void l3_emit(const L3Args &a, u32 g, u64 e, bool acti
     }
 }
 
-static constexpr size_t L3_SMEM = (size_t)L3_CAP * 8 + (size_t)(L3_CAP + 4) * 4 + (size_t)(L3_MASKW + 1) * 4 * 2 + 64 * 4;
+static constexpr size_t L3_SMEM = (size_t)L3_CAP * 8 + (size_t)(L3_CAP + 4) * 4 * 2 + (size_t)(L3_MASKW + 1) * 4 * 2 + 64 * 4;
+
+// sum of the four bytes of x
+__device__ __forceinline__ u32 bytesum(u32 x) { return __dp4a(x, 0x01010101u, 0u); }
 
 __global__ void __launch_bounds__(L3_NT, 2) msd_local_sort_kernel(L3Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *X = (u64 *)smem_raw;                         // [L3_CAP] elements grouped by bin
-    u32 *cnt = (u32 *)(X + L3_CAP);                   // [L3_CAP + 4] bin counts -> bin starts
-    u32 *segmask = cnt + (L3_CAP + 4);                // [MASKW + 1]
+    u32 *cnt = (u32 *)(X + L3_CAP);                   // [L3_CAP + 4] four byte-wide sub-bin counts per position
+    u32 *pre = cnt + (L3_CAP + 4);                    // [L3_CAP + 4] exclusive prefix of the per-position totals
+    u32 *segmask = pre + (L3_CAP + 4);                // [MASKW + 1]
     u32 *segpre = segmask + (L3_MASKW + 1);           // [MASKW + 1]
     u32 *misc = segpre + (L3_MASKW + 1);              // [64]
     uint2 *segtab = (uint2 *)X;                       // aliases X until the elements are scattered
@@ -682,7 +686,9 @@ __global__ void __launch_bounds__(L3_NT, 2) msd_local_sort_kernel(L3Args a) {
     const u64 remmask = a.R >= 64 ? ~0ull : ((1ull << a.R) - 1ull);
     const u64 *src = a.in + E0;
 
-    // ---- pass 1: bin = expected sorted position of the element inside its bucket ----
+    // ---- pass 1: bin = expected sorted position of the element inside its bucket, at a quarter
+    // of a position's resolution: the four sub-bins of a position are byte counters of one word
+    // (a crowded sub-bin declines the tile before a byte can overflow into its neighbour) ----
     u32 meta[L3_IPT];
 #pragma unroll
     for (int j = 0; j < L3_IPT; ++j) {
@@ -693,10 +699,11 @@ __global__ void __launch_bounds__(L3_NT, 2) msd_local_sort_kernel(L3Args a) {
             const u64 e = src[i];
             const uint2 sg = segtab[seg_index(segmask, segpre, i)];
             const u64 rem = (e >> eshift) & remmask;
-            const u32 bin = sg.x + (u32)((rem * (u64)sg.y) >> a.R);
-            const u32 slot = atomicAdd(&cnt[bin], 1u);
+            const u32 fb = (u32)((rem * (u64)(sg.y * 4u)) >> a.R);
+            const u32 word = sg.x + (fb >> 2), sub8 = (fb & 3u) * 8u;
+            const u32 slot = (atomicAdd(&cnt[word], 1u << sub8) >> sub8) & 255u;
             if (slot >= (u32)L3_CROWD) misc[32] = 1;
-            meta[j] = bin | (slot << 13);
+            meta[j] = word | (sub8 << 13) | (slot << 18);
         }
     }
     __syncthreads();
@@ -705,15 +712,16 @@ __global__ void __launch_bounds__(L3_NT, 2) msd_local_sort_kernel(L3Args a) {
         return;
     }
 
-    // ---- exclusive scan of the bin counts (blocked: thread owns L3_IPT consecutive bins) ----
+    // ---- exclusive scan of the per-position totals (blocked: thread owns L3_IPT consecutive positions) ----
     {
-        uint4 *c4 = (uint4 *)(cnt + tid * L3_IPT);
-        const bool mine = tid * L3_IPT <= M;  // bins past M are empty (and were not zeroed)
+        const uint4 *c4 = (const uint4 *)(cnt + tid * L3_IPT);
+        uint4 *p4 = (uint4 *)(pre + tid * L3_IPT);
+        const bool mine = tid * L3_IPT <= M;  // positions past M are empty (and were not zeroed)
         u32 v[L3_IPT];
 #pragma unroll
         for (int q = 0; q < L3_IPT / 4; ++q) {
             uint4 x = mine ? c4[q] : make_uint4(0u, 0u, 0u, 0u);
-            v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+            v[4 * q] = bytesum(x.x); v[4 * q + 1] = bytesum(x.y); v[4 * q + 2] = bytesum(x.z); v[4 * q + 3] = bytesum(x.w);
         }
         u32 sum = 0;
 #pragma unroll
@@ -726,8 +734,15 @@ __global__ void __launch_bounds__(L3_NT, 2) msd_local_sort_kernel(L3Args a) {
         }
         if (lane == 31) misc[warp] = incl;
         __syncthreads();
-        u32 run = incl - sum;
-        for (u32 w = 0; w < warp; ++w) run += misc[w];
+        // prefix over the 16 warp totals
+        u32 ws = lane < (u32)(L3_NT / 32) ? misc[lane] : 0u;
+        u32 wi = ws;
+#pragma unroll
+        for (int o = 1; o < L3_NT / 32; o <<= 1) {
+            u32 x = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= (unsigned)o) wi += x;
+        }
+        u32 run = __shfl_sync(0xffffffffu, wi - ws, warp) + incl - sum;
 #pragma unroll
         for (int q = 0; q < L3_IPT; ++q) {
             u32 c = v[q];
@@ -736,23 +751,24 @@ __global__ void __launch_bounds__(L3_NT, 2) msd_local_sort_kernel(L3Args a) {
         }
         if (mine) {
 #pragma unroll
-            for (int q = 0; q < L3_IPT / 4; ++q) c4[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            for (int q = 0; q < L3_IPT / 4; ++q) p4[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
-        if (tid == L3_NT - 1) cnt[L3_CAP] = run;
     }
     __syncthreads();
 
-    // ---- pass 2: elements (re-read: L2 hits) go to their bin ----
+    // ---- pass 2: elements (re-read: cache hits) go to their sub-bin ----
 #pragma unroll
     for (int j = 0; j < L3_IPT; ++j) {
         const u32 i = (u32)j * L3_NT + tid;
         if ((u32)j * L3_NT >= M) break;
         if (i < M) {
             const u64 e = src[i];
-            const u32 bin = meta[j] & 8191u, slot = meta[j] >> 13;
-            const u32 p0 = cnt[bin], p1 = cnt[bin + 1];
+            const u32 word = meta[j] & 8191u, sub8 = (meta[j] >> 13) & 31u, slot = meta[j] >> 18;
+            const u32 w = cnt[word];
+            const u32 p0 = pre[word] + bytesum(w & ((1u << sub8) - 1u));
+            const u32 c = (w >> sub8) & 255u;
             X[p0 + slot] = e;
-            meta[j] = p0 | (slot << 13) | ((p1 - p0) << 19);
+            meta[j] = p0 | (slot << 13) | (c << 19);
         }
     }
     __syncthreads();
