@@ -438,7 +438,7 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
     lib.b200sa_release_workspace(local_rank)
     # contiguous shards of the read set, one per rank; one NCCL gather of (L, R) to rank 0 per step
     from stralg_b200.shard import ShardedSearch
-    ss = ShardedSearch(total_reads, m, dev, dist)
+    ss = ShardedSearch(total_reads, m, dev, dist, chunks=args.gather_chunks if dist is not None else 1)
     shard = ss.count
 
     def gen_reads(count, seed):
@@ -448,7 +448,6 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
         return r
 
     reads = gen_reads(shard, SEED + 1 + rank * 7919)
-    LR = ss.LR
 
     def search_fn(r, mm, count, Lo, Ro):
         idx.search_device(r, None, mm, count, Lo, Ro, stream)
@@ -486,8 +485,10 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
     value = total_reads / (ms_step / 1e3)
 
     # steps actually executed per read -> algorithmic bytes (m + 2*steps*32 + 8)
-    Lh = LR[0, :shard].cpu().numpy().view(np.uint32)
-    Rh = LR[1, :shard].cpu().numpy().view(np.uint32)
+    Lt, Rt = ss.local_result()
+    Lh = Lt.cpu().numpy().view(np.uint32)
+    Rh = Rt.cpu().numpy().view(np.uint32)
+    LR = torch.empty((2, max(shard, 1)), dtype=torch.int32, device=dev)
     hit_frac = float((Rh > Lh).mean())
     # kernel-only timing of one rank's shard
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -543,7 +544,7 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
         "config": {"workload": "search: batched FM exact search, replicated 3 Gbp index (BASELINE configs[3])"
                    if n == N_FULL else "search: batched FM exact search, replicated index",
                    "n": n, "sigma": 5, "reads": total_reads, "read_len": m, "reads_per_gpu": shard,
-                   "miss_fraction": MISS_PER_1024 / 1024.0, "gather": "NCCL gather of (L,R) to rank 0" if world > 1
+                   "miss_fraction": MISS_PER_1024 / 1024.0, "gather": f"NCCL gather of (L,R) to rank 0, {ss.chunks} pieces per shard overlapped with the search" if world > 1
                    else "none (1 GPU)", "l2": "index (1.5 GB) and reads larger than L2"},
         "clocks": sampler.summary(tw0, tw1), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "kernel_only_patterns_per_s_per_gpu": shard / (kernel_ms / 1e3),
@@ -578,6 +579,8 @@ def main():
     ap.add_argument("--n", type=int, default=env_int("B200SA_BENCH_N", N_FULL))
     ap.add_argument("--reads", type=int, default=env_int("B200SA_BENCH_READS", READS_FULL))
     ap.add_argument("--e2e-reads", type=int, default=20_000_000)
+    ap.add_argument("--gather-chunks", type=int, default=4,
+                    help="N > 1: pieces per shard; the gather of a piece overlaps the search of the next")
     ap.add_argument("--cpu-sample", type=int, default=CPU_SAMPLE)
     ap.add_argument("--cpu-reads", type=int, default=1_000_000)
     ap.add_argument("--no-cpu", action="store_true")

@@ -179,6 +179,34 @@ __device__ __forceinline__ void st_relaxed_u64(u64 *p, u64 v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// ---- mbarrier + bulk asynchronous copy (TMA engine, 1-D) : global -> shared ----------------
+__device__ __forceinline__ u32 smem_addr_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(u64 *bar, u32 parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}" ::"r"(smem_addr_u32(bar)), "r"(parity) : "memory");
+}
+// bytes: multiple of 16; dst and src 16-byte aligned; completion is signalled on `bar`
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr_u32(bar))
+                 : "memory");
+}
+
 // Per-stage device timing (optional; enabled with B200SA_PROFILE).
 struct StageTimer {
     static const int MAX = 64;

@@ -41,6 +41,13 @@ static constexpr int L3_CROWD = 64;                // more elements than this in
 static constexpr int L3_MASKW = L3_CAP / 32;       // 192 words of segment-start bits
 static constexpr int RB_N = 8192;                  // robust kernel: bitonic network size
 
+static unsigned sm_count(int device) {
+    static int cached[64] = {0};
+    int &c = cached[device & 63];
+    if (!c) CUDA_CHECK(cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, device));
+    return (unsigned)c;
+}
+
 static int env_int2(const char *name, int dflt) {
     const char *v = getenv(name);
     return v && *v ? atoi(v) : dflt;
@@ -245,161 +252,6 @@ __global__ void __launch_bounds__(P_NT) msd_hist_elems_kernel(const u64 *__restr
         if (sh[i]) atomicAdd(&h[i], sh[i]);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Partition kernel: one tile of <= P_TILE elements is split by one digit.
-//   FROM_TEXT: the tile is P_TILE consecutive suffix starts, elements are formed from the packed
-//              text and the digit (the key's leading D bits) is not stored in the element.
-//   else     : elements come from the previous level; the digit sits at element bit `dshift`.
-// ---------------------------------------------------------------------------------------------
-struct PartArgs {
-    const u64 *in;
-    u64 *out;
-    const u64 *packed;
-    u32 n, len;
-    int bits, KB, pb;
-    int D;
-    int dshift;       // FROM_TEXT: digit = key >> dshift, rest = key & restmask; else digit = (e >> dshift) & (B-1)
-    u64 restmask;
-    int rest_shift;   // 32 + pb
-    u32 *cursor;      // [nparents << D] next free slot of every child bucket
-    const uint4 *desc;
-    const u32 *d_ntiles;
-};
-
-static constexpr size_t P_SMEM = (size_t)P_TILE * 8 + (size_t)MSD_MAXBINS * 4 * 2 + (size_t)P_TILE * 2 + 32 * 4;
-
-template <bool FROM_TEXT>
-__global__ void __launch_bounds__(P_NT, 2) msd_partition_kernel(PartArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *buf = (u64 *)smem_raw;                   // [P_TILE]
-    u32 *hist = (u32 *)(buf + P_TILE);            // [MAXBINS] counts, then tile-local offsets
-    u32 *gofs = hist + MSD_MAXBINS;               // [MAXBINS] global slot of the digit's run minus its tile offset
-    u16 *dig = (u16 *)(gofs + MSD_MAXBINS);       // [P_TILE] digit of the element in slot i (FROM_TEXT)
-    u32 *wsum = (u32 *)(dig + P_TILE);            // [32]
-
-    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const u32 B = 1u << a.D;
-    u64 begin;
-    u32 count, parent;
-    if (FROM_TEXT) {
-        begin = (u64)blockIdx.x * P_TILE;
-        count = (u32)min((u64)P_TILE, (u64)a.len - begin);
-        parent = 0;
-    } else {
-        if (blockIdx.x >= *a.d_ntiles) return;
-        const uint4 ds = a.desc[blockIdx.x];
-        begin = ds.x;
-        count = ds.y;
-        parent = ds.z;
-    }
-    for (u32 i = tid; i < B; i += P_NT) hist[i] = 0;
-    __syncthreads();
-
-    // ---- elements, digits, slot inside the tile's digit group (arbitrary order: MSD) ----
-    u64 e[P_IPT];
-    u32 ds[P_IPT];
-#pragma unroll
-    for (int j = 0; j < P_IPT; ++j) {
-        const u32 i = (u32)j * P_NT + tid;
-        ds[j] = 0;
-        e[j] = 0;
-        if (i < count) {
-            u32 d;
-            if (FROM_TEXT) {
-                const u32 p = (u32)(begin + i);
-                u64 key, prev = 0;
-                if (a.pb && p > 0) {
-                    u64 win = window_at(a.packed, (u64)p - 1, a.bits);
-                    prev = win >> (64 - a.bits);
-                    key = (win << a.bits) >> (64 - a.KB);
-                } else {
-                    key = window_at(a.packed, (u64)p, a.bits) >> (64 - a.KB);
-                }
-                d = (u32)(key >> a.dshift);
-                e[j] = ((key & a.restmask) << a.rest_shift) | (prev << 32) | (u64)p;
-            } else {
-                e[j] = ld_stream_u64(a.in + begin + i);
-                d = (u32)(e[j] >> a.dshift) & (B - 1);
-            }
-            u32 slot = atomicAdd(&hist[d], 1u);
-            ds[j] = d | (slot << 10);
-        }
-    }
-    __syncthreads();
-
-    // ---- exclusive scan of the digit counts; reserve the runs in the child buckets ----
-    {
-        constexpr int DPT = MSD_MAXBINS / P_NT;  // 2
-        const u32 d0 = tid * DPT;
-        u32 c[DPT];
-        u32 sum = 0;
-#pragma unroll
-        for (int q = 0; q < DPT; ++q) {
-            c[q] = d0 + q < B ? hist[d0 + q] : 0u;
-            sum += c[q];
-        }
-        u32 g[DPT];
-#pragma unroll
-        for (int q = 0; q < DPT; ++q) {
-            g[q] = 0;
-            if (c[q]) g[q] = atomicAdd(&a.cursor[(size_t)parent * B + d0 + q], c[q]);
-        }
-        u32 incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            u32 t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (unsigned)o) incl += t;
-        }
-        if (lane == 31) wsum[warp] = incl;
-        __syncthreads();
-        u32 run = incl - sum;
-        for (u32 w = 0; w < warp; ++w) run += wsum[w];
-#pragma unroll
-        for (int q = 0; q < DPT; ++q) {
-            if (d0 + q < B) {
-                hist[d0 + q] = run;
-                gofs[d0 + q] = g[q] - run;
-            }
-            run += c[q];
-        }
-    }
-    __syncthreads();
-
-    // ---- group the tile by digit in shared memory ----
-#pragma unroll
-    for (int j = 0; j < P_IPT; ++j) {
-        const u32 i = (u32)j * P_NT + tid;
-        if (i < count) {
-            const u32 d = ds[j] & 1023u;
-            const u32 pos = hist[d] + (ds[j] >> 10);
-            buf[pos] = e[j];
-            if (FROM_TEXT) dig[pos] = (u16)d;
-        }
-    }
-    __syncthreads();
-
-    // ---- consecutive threads write consecutive slots of a digit run ----
-    for (u32 i = tid; i < count; i += P_NT) {
-        const u64 v = buf[i];
-        const u32 d = FROM_TEXT ? (u32)dig[i] : ((u32)(v >> a.dshift) & (B - 1));
-        a.out[gofs[d] + i] = v;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Level-1 partition straight from the packed text.  A tile is T1_TILE consecutive suffix starts;
-// its slice of the packed text (<= 8 KB) is staged in shared memory once, and a thread forms
-// T1_IPT CONSECUTIVE elements from one 128-bit window by shifting, instead of two global loads
-// per element.  Elements are not kept in registers across the digit scan: they are formed again
-// from the staged text when the tile is grouped by digit.
-// ---------------------------------------------------------------------------------------------
-static constexpr int T1_NT = 512;
-static constexpr int T1_IPT = 16;
-static constexpr int T1_TILE = T1_NT * T1_IPT;     // 8192 suffix starts
-static constexpr int T1_STAGE_MAX = T1_TILE * 8 / 64 + 4;
-static constexpr size_t T1_SMEM = (size_t)T1_TILE * 8 + (size_t)MSD_MAXBINS * 4 * 2 + (size_t)T1_TILE * 2 +
-                                  (size_t)T1_STAGE_MAX * 8 + 32 * 4;
-
 // exclusive prefix of `v` over a 512-thread block (wsum: 16 words of shared memory)
 __device__ __forceinline__ u32 block512_exclusive(u32 v, u32 *wsum) {
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -421,6 +273,142 @@ __device__ __forceinline__ u32 block512_exclusive(u32 v, u32 *wsum) {
     const u32 wbase = __shfl_sync(0xffffffffu, wi - ws, warp);
     return wbase + incl - v;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Partition of a level >= 2: a tile of <= P_TILE elements written by the previous level is split
+// by the digit at element bit `dshift`.  Persistent CTAs (two per SM): while a tile is being
+// ranked, grouped and written out, the TMA engine copies the CTA's NEXT tile into the other half
+// of a shared-memory double buffer (cp.async.bulk + mbarrier), so no warp waits on HBM latency.
+// ---------------------------------------------------------------------------------------------
+struct PartArgs {
+    const u64 *in;
+    u64 *out;
+    int D;
+    int dshift;       // digit = (e >> dshift) & (B - 1)
+    u32 *cursor;      // [nparents << D] next free slot of every child bucket
+    const uint4 *desc;
+    const u32 *d_ntiles;
+};
+
+static constexpr int P_INB = P_TILE + 2;  // landing buffer: the copy starts at a 16-byte boundary
+static constexpr size_t P_SMEM = (size_t)P_INB * 8 * 2 + (size_t)P_TILE * 8 + (size_t)MSD_MAXBINS * 4 * 2 + 32 * 4 + 2 * 8;
+
+__global__ void __launch_bounds__(P_NT, 2) msd_partition_kernel(PartArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *inb = (u64 *)smem_raw;                   // [2][P_INB] landing buffers
+    u64 *buf = inb + 2 * P_INB;                   // [P_TILE] elements grouped by digit
+    u32 *hist = (u32 *)(buf + P_TILE);            // [MAXBINS] counts, then tile-local offsets
+    u32 *gofs = hist + MSD_MAXBINS;               // [MAXBINS] global slot of the digit's run minus its tile offset
+    u32 *wsum = gofs + MSD_MAXBINS;               // [32]
+    u64 *mbar = (u64 *)(wsum + 32);               // [2]
+
+    const u32 tid = threadIdx.x;
+    const u32 B = 1u << a.D;
+    const u32 ntiles = *a.d_ntiles;
+    if (blockIdx.x >= ntiles) return;
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+
+    // thread 0 owns the copies: tile -> landing buffer (from the 16-byte boundary at or below its start)
+    auto issue = [&](u32 tile, u32 stage) {
+        const uint4 ds = a.desc[tile];
+        const u32 a0 = ds.x & ~1u;
+        const u32 bytes = ((ds.x - a0 + ds.y + 1u) & ~1u) * 8u;
+        mbar_arrive_expect_tx(&mbar[stage], bytes);
+        bulk_copy_g2s(inb + stage * P_INB, a.in + a0, bytes, &mbar[stage]);
+    };
+    if (tid == 0) issue(blockIdx.x, 0);
+
+    u32 it = 0;
+    uint4 ds_next = a.desc[blockIdx.x];
+    for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const u32 stage = it & 1u;
+        const uint4 ds = ds_next;
+        if (tile + gridDim.x < ntiles) ds_next = a.desc[tile + gridDim.x];
+        const u32 count = ds.y, parent = ds.z;
+        const u64 *in = inb + stage * P_INB + (ds.x & 1u);
+        // the other landing buffer was last read before the barrier that ended the previous iteration
+        if (tid == 0 && tile + gridDim.x < ntiles) issue(tile + gridDim.x, stage ^ 1u);
+        for (u32 i = tid; i < B; i += P_NT) hist[i] = 0;
+        __syncthreads();
+        mbar_wait_parity(&mbar[stage], (it >> 1) & 1u);
+
+        // ---- digits and slots inside the tile's digit groups (arbitrary order: MSD) ----
+        u32 dsl[P_IPT];
+#pragma unroll
+        for (int j = 0; j < P_IPT; ++j) {
+            const u32 i = (u32)j * P_NT + tid;
+            dsl[j] = 0;
+            if (i < count) {
+                const u32 d = (u32)(in[i] >> a.dshift) & (B - 1);
+                dsl[j] = d | (atomicAdd(&hist[d], 1u) << 10);
+            }
+        }
+        __syncthreads();
+
+        // ---- exclusive scan of the digit counts; reserve the runs in the child buckets ----
+        {
+            constexpr int DPT = MSD_MAXBINS / P_NT;  // 2
+            const u32 d0 = tid * DPT;
+            u32 c[DPT], g[DPT];
+            u32 sum = 0;
+#pragma unroll
+            for (int q = 0; q < DPT; ++q) {
+                c[q] = d0 + q < B ? hist[d0 + q] : 0u;
+                sum += c[q];
+            }
+#pragma unroll
+            for (int q = 0; q < DPT; ++q) {
+                g[q] = 0;
+                if (c[q]) g[q] = atomicAdd(&a.cursor[(size_t)parent * B + d0 + q], c[q]);
+            }
+            u32 run = block512_exclusive(sum, wsum);
+#pragma unroll
+            for (int q = 0; q < DPT; ++q) {
+                if (d0 + q < B) {
+                    hist[d0 + q] = run;
+                    gofs[d0 + q] = g[q] - run;
+                }
+                run += c[q];
+            }
+        }
+        __syncthreads();
+
+        // ---- group the tile by digit in shared memory ----
+#pragma unroll
+        for (int j = 0; j < P_IPT; ++j) {
+            const u32 i = (u32)j * P_NT + tid;
+            if (i < count) buf[hist[dsl[j] & 1023u] + (dsl[j] >> 10)] = in[i];
+        }
+        __syncthreads();
+
+        // ---- consecutive threads write consecutive slots of a digit run ----
+        for (u32 i = tid; i < count; i += P_NT) {
+            const u64 v = buf[i];
+            a.out[gofs[(u32)(v >> a.dshift) & (B - 1)] + i] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Level-1 partition straight from the packed text.  A tile is T1_TILE consecutive suffix starts;
+// its slice of the packed text (<= 8 KB) is staged in shared memory once, and a thread forms
+// T1_IPT CONSECUTIVE elements from one 128-bit window by shifting, instead of two global loads
+// per element.  Elements are not kept in registers across the digit scan: they are formed again
+// from the staged text when the tile is grouped by digit.
+// ---------------------------------------------------------------------------------------------
+static constexpr int T1_NT = 512;
+static constexpr int T1_IPT = 16;
+static constexpr int T1_TILE = T1_NT * T1_IPT;     // 8192 suffix starts
+static constexpr int T1_STAGE_MAX = T1_TILE * 8 / 64 + 4;
+static constexpr size_t T1_SMEM = (size_t)T1_TILE * 8 + (size_t)MSD_MAXBINS * 4 * 2 + (size_t)T1_TILE * 2 +
+                                  (size_t)T1_STAGE_MAX * 8 + 32 * 4;
 
 struct Text1Args {
     const u64 *packed;
@@ -946,7 +934,7 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     static bool configured = false;
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
-        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_local_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L3_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_local_sort_robust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
         configured = true;
@@ -1014,10 +1002,6 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         ix.timer.end(t);
     }
     PartArgs pa{};
-    pa.packed = ix.packed; pa.n = n; pa.len = len; pa.bits = b; pa.KB = pl.KB; pa.pb = pl.pb;
-    pa.rest_shift = 32 + pl.pb;
-    pa.restmask = 0;
-
     u64 *cur = r.bufA, *other = r.bufB;
     int consumed = pl.D[0];
     for (int l = 1; l < pl.nlevels; ++l) {
@@ -1044,7 +1028,7 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         pa.cursor = cursor[l];
         pa.desc = desc; pa.d_ntiles = d_misc + 1;
         t = ix.timer.begin("msd_part", (double)len * 16.0);
-        msd_partition_kernel<false><<<grid, P_NT, P_SMEM, st>>>(pa);
+        msd_partition_kernel<<<std::min(grid, 2u * sm_count(ix.device)), P_NT, P_SMEM, st>>>(pa);
         KERNEL_CHECK();
         ix.timer.end(t);
         std::swap(cur, other);

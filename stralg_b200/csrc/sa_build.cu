@@ -714,7 +714,8 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
     DevBuf<u32> d_primary(1, st);
 
     // ---- workspace ----
-    u64 *keysA = ar.get<u64>(len), *keysB = ar.get<u64>(len);
+    // + 2: the bulk copies of round0_msd.cu read whole 16-byte units
+    u64 *keysA = ar.get<u64>((size_t)len + 2), *keysB = ar.get<u64>((size_t)len + 2);
     u32 *valsV = ar.get<u32>(len);
     u32 *rank = ar.get<u32>(len);
     size_t valid_words = ((size_t)len + 31) / 32 + 2;

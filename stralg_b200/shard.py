@@ -34,9 +34,13 @@ class ShardedSearch:
 
     ``dist`` is ``torch.distributed`` (initialised, NCCL on GPUs / gloo in the CPU tests) or None
     for a single process.  Buffers are allocated once; ``step()`` is what a bench step times.
+
+    The shard is processed in ``chunks`` pieces: the gather of piece k is issued asynchronously
+    (NCCL runs it on its own stream) and overlaps the search of piece k + 1, so only the last
+    piece's gather is exposed.
     """
 
-    def __init__(self, total_reads: int, read_len: int, device, dist=None, dst: int = 0):
+    def __init__(self, total_reads: int, read_len: int, device, dist=None, dst: int = 0, chunks: int = 1):
         import torch
         self.torch = torch
         self.dist = dist
@@ -48,29 +52,56 @@ class ShardedSearch:
         self.lo, self.hi = shard_bounds(self.total, self.world, self.rank)
         self.count = self.hi - self.lo
         self.cap = max_shard(self.total, self.world)  # gather needs equal-size pieces
-        self.LR = torch.zeros((2, self.cap), dtype=torch.int32, device=device)
+        self.chunks = max(1, min(int(chunks), self.cap)) if self.cap else 1
+        # piece k covers shard-local reads [k * piece, (k + 1) * piece), the same split on every rank
+        self.piece = -(-self.cap // self.chunks) if self.cap else 0
+        self.LR = [torch.zeros((2, self.piece), dtype=torch.int32, device=device) for _ in range(self.chunks)]
         self.gathered = None
         if dist is not None and self.rank == dst:
-            self.gathered = [torch.empty((2, self.cap), dtype=torch.int32, device=device) for _ in range(self.world)]
+            self.gathered = [[torch.empty((2, self.piece), dtype=torch.int32, device=device)
+                              for _ in range(self.world)] for _ in range(self.chunks)]
+
+    def piece_bounds(self, k: int, count: int) -> Tuple[int, int]:
+        lo = min(k * self.piece, count)
+        return lo, min(lo + self.piece, count)
 
     def step(self, search_fn: Callable, reads) -> None:
-        """search_fn(reads, read_len, count, L_out, R_out) fills the first ``count`` slots."""
-        if self.count:
-            search_fn(reads, self.m, self.count, self.LR[0], self.LR[1])
-        if self.dist is not None:
-            self.dist.gather(self.LR, self.gathered, dst=self.dst)
+        """search_fn(reads, read_len, count, L_out, R_out) fills the first ``count`` slots;
+        ``reads`` holds this rank's shard (count * read_len codes)."""
+        works = []
+        for k in range(self.chunks):
+            lo, hi = self.piece_bounds(k, self.count)
+            if hi > lo:
+                search_fn(reads[lo * self.m: hi * self.m], self.m, hi - lo, self.LR[k][0], self.LR[k][1])
+            if self.dist is not None:
+                works.append(self.dist.gather(self.LR[k], self.gathered[k] if self.gathered else None,
+                                              dst=self.dst, async_op=True))
+        for w in works:
+            w.wait()
+
+    def local_result(self):
+        """(L, R) of this rank's shard."""
+        torch = self.torch
+        Ls, Rs = [], []
+        for k in range(self.chunks):
+            lo, hi = self.piece_bounds(k, self.count)
+            Ls.append(self.LR[k][0, :hi - lo])
+            Rs.append(self.LR[k][1, :hi - lo])
+        return torch.cat(Ls), torch.cat(Rs)
 
     def result(self) -> Optional[Tuple["object", "object"]]:
         """(L, R) of all reads in input order on ``dst`` (int32 bit patterns of the uint32 values);
         None on the other ranks."""
         torch = self.torch
         if self.dist is None:
-            return self.LR[0, :self.count], self.LR[1, :self.count]
+            return self.local_result()
         if self.rank != self.dst:
             return None
         Ls, Rs = [], []
         for g in range(self.world):
-            lo, hi = shard_bounds(self.total, self.world, g)
-            Ls.append(self.gathered[g][0, :hi - lo])
-            Rs.append(self.gathered[g][1, :hi - lo])
+            glo, ghi = shard_bounds(self.total, self.world, g)
+            for k in range(self.chunks):
+                lo, hi = self.piece_bounds(k, ghi - glo)
+                Ls.append(self.gathered[k][g][0, :hi - lo])
+                Rs.append(self.gathered[k][g][1, :hi - lo])
         return torch.cat(Ls), torch.cat(Rs)

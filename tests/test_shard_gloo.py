@@ -42,7 +42,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, total, m, out_path):
+def _worker(rank, world, port, total, m, chunks, out_path):
     import torch
     import torch.distributed as dist
     from _oracle import Oracle
@@ -65,7 +65,7 @@ def _worker(rank, world, port, total, m, out_path):
         for q in np.nonzero(miss)[0]:
             reads[q * m:(q + 1) * m] = rng.integers(1, 5, m)
 
-        ss = ShardedSearch(total, m, "cpu", dist)
+        ss = ShardedSearch(total, m, "cpu", dist, chunks=chunks)
         assert (ss.lo, ss.hi) == shard_bounds(total, world, rank)
         mine = torch.from_numpy(reads[ss.lo * m: ss.hi * m].copy())
 
@@ -92,11 +92,11 @@ def _worker(rank, world, port, total, m, out_path):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,total", [(2, 1000), (2, 1001), (3, 1000), (2, 1)])
-def test_sharded_search_gather_gloo(tmp_path, world, total):
+@pytest.mark.parametrize("world,total,chunks", [(2, 1000, 1), (2, 1001, 4), (3, 1000, 3), (2, 1, 2)])
+def test_sharded_search_gather_gloo(tmp_path, world, total, chunks):
     import torch.multiprocessing as mp
     out = str(tmp_path / "res.txt")
-    mp.spawn(_worker, args=(world, _free_port(), total, 20, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), total, 20, chunks, out), nprocs=world, join=True)
     ok, hits = open(out).read().split()
     assert ok == "1"
     if total >= 1000:
