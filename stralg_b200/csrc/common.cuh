@@ -179,6 +179,11 @@ __device__ __forceinline__ void st_relaxed_u64(u64 *p, u64 v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// bulk prefetch of [src, src + bytes) into L2 (bytes: multiple of 16, src 16-byte aligned)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, u32 bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 // ---- mbarrier + bulk asynchronous copy (TMA engine, 1-D) : global -> shared ----------------
 __device__ __forceinline__ u32 smem_addr_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u64 *bar, u32 arrivals) {

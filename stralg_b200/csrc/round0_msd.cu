@@ -26,19 +26,21 @@
 
 namespace b200sa {
 
-static constexpr int MSD_MAXBINS = 1024;
+static constexpr int MSD_MAXBINS = 1024;           // digits of up to 10 bits
+static constexpr int P_MAXBINS = MSD_MAXBINS;
 // partition kernels
 static constexpr int P_NT = 512;
 static constexpr int P_IPT = 8;
 static constexpr int P_TILE = P_NT * P_IPT;  // 4096 elements
 // local sort
 static constexpr int L3_NT = 512;
-static constexpr int L3_IPT = 12;
-static constexpr int L3_CAP = L3_NT * L3_IPT;      // 6144 elements in shared memory
 static constexpr int L3_TSZ = 2048;                // a tile owns the buckets that START in its span
-static constexpr int L3_MAXB = L3_CAP - L3_TSZ;    // 4096: largest bucket the fast path accepts
-static constexpr int L3_CROWD = 64;                // more elements than this in one bin -> robust kernel
-static constexpr int L3_MASKW = L3_CAP / 32;       // 192 words of segment-start bits
+static constexpr int L3_MAXB = 4096;               // largest bucket the fast path accepts
+static constexpr int L3_CAP = L3_TSZ + L3_MAXB;    // 6144 elements of a tile in shared memory
+static constexpr int L3_IPT = L3_CAP / L3_NT;      // 12
+static constexpr int L3_CROWD = 64;                // more elements than this in one sub-bin -> robust kernel
+static constexpr int L3_MASKW = 192;               // words of segment-start bits (>= L3_CAP / 32, a multiple of 32)
+static_assert(L3_CAP % L3_NT == 0 && L3_MASKW * 32 >= L3_CAP && L3_MASKW % 32 == 0, "local-sort geometry");
 static constexpr int RB_N = 8192;                  // robust kernel: bitonic network size
 
 static unsigned sm_count(int device) {
@@ -60,6 +62,9 @@ bool msd_make_plan(u32 len, u32 sigma, int bits, MsdPlan &pl) {
     const char *mode = getenv("B200SA_ROUND0");
     if (mode && !strcmp(mode, "lsd")) return false;
     const int b = bits;
+    // Bucket bits: whole symbols (a digit never splits a symbol: with alphabets that do not fill
+    // their b bits the leading bits of a symbol carry no information), until an average bucket
+    // holds <= `target` suffixes.  At most 10 bits per level.
     int dmax = (b == 4 || b == 8) ? 8 : 10;
     dmax = env_int2("B200SA_MSD_DMAX", dmax);
     dmax = std::max(b, std::min(10, dmax / b * b));
@@ -141,7 +146,8 @@ __global__ void __launch_bounds__(256) msd_hist_text_kernel(const u64 *__restric
 
 // One CTA per parent bucket: child_start[p*B + d] = parent_start[p] + exclusive scan of the
 // parent's digit counts; the counts are replaced by the same values (they become the write
-// cursors of the partition kernel).  blockDim.x >= B, a multiple of 32.
+// cursors of the partition kernel).  blockDim.x = min(B, 1024) rounded up to a warp; a thread
+// owns B / blockDim.x consecutive digits.
 __global__ void __launch_bounds__(1024) msd_scan_children_kernel(u32 *__restrict__ hist,
                                                                  const u32 *__restrict__ parent_start, int D,
                                                                  u32 nparents, u32 len, u32 *__restrict__ child_start,
@@ -149,17 +155,21 @@ __global__ void __launch_bounds__(1024) msd_scan_children_kernel(u32 *__restrict
     __shared__ u32 wsum[32];
     __shared__ u32 wmax[32];
     const u32 B = 1u << D;
-    const u32 p = blockIdx.x, d = threadIdx.x;
-    const unsigned lane = d & 31u, warp = d >> 5, nwarps = blockDim.x >> 5;
-    const size_t at = (size_t)p * B + d;
-    u32 c = d < B ? hist[at] : 0u;
+    const u32 p = blockIdx.x, tid = threadIdx.x;
+    const unsigned lane = tid & 31u, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const u32 per = B > blockDim.x ? B / blockDim.x : 1u;  // 1 or 2
+    const u32 d0 = tid * per;
+    const size_t at = (size_t)p * B + d0;
+    u32 c0 = d0 < B ? hist[at] : 0u;
+    u32 c1 = (per > 1 && d0 + 1 < B) ? hist[at + 1] : 0u;
+    const u32 c = c0 + c1;
     u32 incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         u32 t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= (unsigned)o) incl += t;
     }
-    u32 mx = c;
+    u32 mx = max(c0, c1);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 31) wsum[warp] = incl;
@@ -167,12 +177,16 @@ __global__ void __launch_bounds__(1024) msd_scan_children_kernel(u32 *__restrict
     __syncthreads();
     u32 base = parent_start ? parent_start[p] : 0u;
     for (unsigned w = 0; w < warp; ++w) base += wsum[w];
-    if (d < B) {
+    if (d0 < B) {
         u32 st = base + incl - c;
         child_start[at] = st;
         hist[at] = st;
+        if (per > 1 && d0 + 1 < B) {
+            child_start[at + 1] = st + c0;
+            hist[at + 1] = st + c0;
+        }
     }
-    if (d == 0) {
+    if (tid == 0) {
         if (maxbucket) {
             u32 m = 0;
             for (unsigned w = 0; w < nwarps; ++w) m = max(m, wmax[w]);
@@ -236,7 +250,7 @@ __global__ void __launch_bounds__(P_NT) msd_hist_elems_kernel(const u64 *__restr
                                                               const u32 *__restrict__ d_ntiles, int D, int dshift,
                                                               u32 *__restrict__ hist) {
     if (blockIdx.x >= *d_ntiles) return;
-    __shared__ u32 sh[MSD_MAXBINS];
+    __shared__ u32 sh[P_MAXBINS];
     const u32 B = 1u << D;
     for (u32 i = threadIdx.x; i < B; i += P_NT) sh[i] = 0;
     __syncthreads();
@@ -291,15 +305,15 @@ struct PartArgs {
 };
 
 static constexpr int P_INB = P_TILE + 2;  // landing buffer: the copy starts at a 16-byte boundary
-static constexpr size_t P_SMEM = (size_t)P_INB * 8 * 2 + (size_t)P_TILE * 8 + (size_t)MSD_MAXBINS * 4 * 2 + 32 * 4 + 2 * 8;
+static constexpr size_t P_SMEM = (size_t)P_INB * 8 * 2 + (size_t)P_TILE * 8 + (size_t)P_MAXBINS * 4 * 2 + 32 * 4 + 2 * 8;
 
 __global__ void __launch_bounds__(P_NT, 2) msd_partition_kernel(PartArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *inb = (u64 *)smem_raw;                   // [2][P_INB] landing buffers
     u64 *buf = inb + 2 * P_INB;                   // [P_TILE] elements grouped by digit
     u32 *hist = (u32 *)(buf + P_TILE);            // [MAXBINS] counts, then tile-local offsets
-    u32 *gofs = hist + MSD_MAXBINS;               // [MAXBINS] global slot of the digit's run minus its tile offset
-    u32 *wsum = gofs + MSD_MAXBINS;               // [32]
+    u32 *gofs = hist + P_MAXBINS;                 // [MAXBINS] global slot of the digit's run minus its tile offset
+    u32 *wsum = gofs + P_MAXBINS;                 // [32]
     u64 *mbar = (u64 *)(wsum + 32);               // [2]
 
     const u32 tid = threadIdx.x;
@@ -353,7 +367,7 @@ __global__ void __launch_bounds__(P_NT, 2) msd_partition_kernel(PartArgs a) {
 
         // ---- exclusive scan of the digit counts; reserve the runs in the child buckets ----
         {
-            constexpr int DPT = MSD_MAXBINS / P_NT;  // 2
+            constexpr int DPT = P_MAXBINS / P_NT;  // 2
             const u32 d0 = tid * DPT;
             u32 c[DPT], g[DPT];
             u32 sum = 0;
@@ -567,6 +581,8 @@ struct L3Args {
     u32 *act, *act_count;
     u32 *primary;
     u32 *flagged, *nflagged;   // tiles the fast kernel declined (a crowded bin)
+    u32 ntiles;
+    int par_shift;     // bucket >> par_shift = its level-1 parent (0 with a single level)
 };
 
 __device__ __forceinline__ u32 seg_index(const u32 *segmask, const u32 *segpre, u32 i) {
@@ -586,7 +602,7 @@ __device__ __forceinline__ void l3_segments(const u32 *__restrict__ bstart, u32 
     }
     __syncthreads();
     if (tid < 32) {
-        constexpr int WPL = L3_MASKW / 32;  // 6 words per lane
+        constexpr int WPL = L3_MASKW / 32;  // words per lane
         u32 loc[WPL];
         u32 sum = 0;
 #pragma unroll
@@ -640,187 +656,220 @@ __device__ __forceinline__ void l3_emit(const L3Args &a, u32 g, u64 e, bool acti
     }
 }
 
-static constexpr size_t L3_SMEM = (size_t)L3_CAP * 8 + (size_t)(L3_CAP + 4) * 4 * 2 + (size_t)(L3_MASKW + 1) * 4 * 2 + 64 * 4;
+static constexpr int L3_CNTN = L3_CAP + 16;        // counters per tile (the blocked scan reads a little past bin M)
+static constexpr size_t L3_SMEM = (size_t)L3_CAP * 8 + (size_t)L3_CNTN * 4 + (size_t)L3_CNTN * 2 +
+                                  (size_t)(L3_MASKW + 1) * 4 * 2 + 64 * 4 + 8 * 4;
 
 // sum of the four bytes of x
 __device__ __forceinline__ u32 bytesum(u32 x) { return __dp4a(x, 0x01010101u, 0u); }
 
+// Persistent CTAs (two per SM).  While a tile is being ordered and written out, thread 0 walks
+// tile_first -> bucket_start for the CTA's NEXT tile and asks the TMA engine to pull that tile's
+// elements into L2 (cp.async.bulk.prefetch), so the chain of dependent loads is off every
+// warp's critical path and the next tile's first pass reads L2, not HBM.
 __global__ void __launch_bounds__(L3_NT, 2) msd_local_sort_kernel(L3Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *X = (u64 *)smem_raw;                         // [L3_CAP] elements grouped by bin
-    u32 *cnt = (u32 *)(X + L3_CAP);                   // [L3_CAP + 4] four byte-wide sub-bin counts per position
-    u32 *pre = cnt + (L3_CAP + 4);                    // [L3_CAP + 4] exclusive prefix of the per-position totals
-    u32 *segmask = pre + (L3_CAP + 4);                // [MASKW + 1]
+    u32 *cnt = (u32 *)(X + L3_CAP);                   // [L3_CNTN] four byte-wide sub-bin counts per position
+    u16 *pre = (u16 *)(cnt + L3_CNTN);                // [L3_CNTN] exclusive prefix of the per-position totals
+    u32 *segmask = (u32 *)(pre + L3_CNTN);            // [MASKW + 1]
     u32 *segpre = segmask + (L3_MASKW + 1);           // [MASKW + 1]
     u32 *misc = segpre + (L3_MASKW + 1);              // [64]
+    u32 *nxt = misc + 64;                             // [8] next tile: index, b0, b1, E0, M
     uint2 *segtab = (uint2 *)X;                       // aliases X until the elements are scattered
-    u16 *perm = (u16 *)cnt;                           // aliases cnt once the bin starts are consumed
-
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const u32 t = blockIdx.x;
-    const u32 b0 = a.tile_first[t], b1 = a.tile_first[t + 1];
-    if (b0 == b1) return;
-    const u32 E0 = a.bstart[b0], E1 = a.bstart[b1];
-    const u32 M = E1 - E0;
-    if (M == 0) return;
+    const u32 remmask = a.R >= 32 ? ~0u : ((1u << a.R) - 1u);
 
-    if (tid == 0) misc[32] = 0;  // crowded flag
-    // bins [0, M) are used; the blocked scan below reads up to 11 entries past bin M
-    for (u32 i = tid; i < min((u32)L3_CAP + 4u, M + 16u); i += L3_NT) cnt[i] = 0;
-    l3_segments(a.bstart, b0, b1, E0, M, segmask, segpre, segtab, L3_NT);
-    __syncthreads();
-
-    const int eshift = 32 + a.pb;
-    const u64 remmask = a.R >= 64 ? ~0ull : ((1ull << a.R) - 1ull);
-    const u64 *src = a.in + E0;
-
-    // ---- pass 1: bin = expected sorted position of the element inside its bucket, at a quarter
-    // of a position's resolution: the four sub-bins of a position are byte counters of one word
-    // (a crowded sub-bin declines the tile before a byte can overflow into its neighbour) ----
-    u32 meta[L3_IPT];
-#pragma unroll
-    for (int j = 0; j < L3_IPT; ++j) {
-        const u32 i = (u32)j * L3_NT + tid;
-        meta[j] = 0;
-        if ((u32)j * L3_NT >= M) break;
-        if (i < M) {
-            const u64 e = src[i];
-            const uint2 sg = segtab[seg_index(segmask, segpre, i)];
-            const u64 rem = (e >> eshift) & remmask;
-            const u32 fb = (u32)((rem * (u64)(sg.y * 4u)) >> a.R);
-            const u32 word = sg.x + (fb >> 2), sub8 = (fb & 3u) * 8u;
-            const u32 slot = (atomicAdd(&cnt[word], 1u << sub8) >> sub8) & 255u;
-            if (slot >= (u32)L3_CROWD) misc[32] = 1;
-            meta[j] = word | (sub8 << 13) | (slot << 18);
+    // thread 0: publish the CTA's next non-empty tile at or after `t` and start its prefetch
+    auto advance = [&](u32 t) {
+        u32 b0 = 0, b1 = 0, E0 = 0, M = 0;
+        for (; t < a.ntiles; t += gridDim.x) {
+            b0 = a.tile_first[t];
+            b1 = a.tile_first[t + 1];
+            if (b0 == b1) continue;
+            E0 = a.bstart[b0];
+            M = a.bstart[b1] - E0;
+            if (M) break;
         }
-    }
-    __syncthreads();
-    if (misc[32]) {
-        if (tid == 0) a.flagged[atomicAdd(a.nflagged, 1u)] = t;
-        return;
-    }
+        nxt[0] = t; nxt[1] = b0; nxt[2] = b1; nxt[3] = E0; nxt[4] = M;
+        if (t < a.ntiles) {
+            const u32 a0 = E0 & ~1u;
+            const u32 bytes = ((E0 - a0 + M + 1u) & ~1u) * 8u;
+            bulk_prefetch_l2(a.in + a0, bytes);
+        }
+    };
+    if (tid == 0) advance(blockIdx.x);
 
-    // ---- exclusive scan of the per-position totals (blocked: thread owns L3_IPT consecutive positions) ----
-    {
-        const uint4 *c4 = (const uint4 *)(cnt + tid * L3_IPT);
-        uint4 *p4 = (uint4 *)(pre + tid * L3_IPT);
-        const bool mine = tid * L3_IPT <= M;  // positions past M are empty (and were not zeroed)
-        u32 v[L3_IPT];
-#pragma unroll
-        for (int q = 0; q < L3_IPT / 4; ++q) {
-            uint4 x = mine ? c4[q] : make_uint4(0u, 0u, 0u, 0u);
-            v[4 * q] = bytesum(x.x); v[4 * q + 1] = bytesum(x.y); v[4 * q + 2] = bytesum(x.z); v[4 * q + 3] = bytesum(x.w);
-        }
-        u32 sum = 0;
-#pragma unroll
-        for (int q = 0; q < L3_IPT; ++q) sum += v[q];
-        u32 incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            u32 x = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (unsigned)o) incl += x;
-        }
-        if (lane == 31) misc[warp] = incl;
+    while (true) {
+        __syncthreads();  // `nxt` is published; the previous tile is completely written out
+        const u32 t = nxt[0], b0 = nxt[1], b1 = nxt[2], E0 = nxt[3], M = nxt[4];
+        if (t >= a.ntiles) break;
+        const u64 *src = a.in + E0;
+
+        if (tid == 0) misc[32] = 0;  // crowded flag
+        // bins [0, M) are used; the blocked scan below reads a few entries past bin M
+        for (u32 i = tid; i < min((u32)L3_CNTN, M + 16u); i += L3_NT) cnt[i] = 0;
+        l3_segments(a.bstart, b0, b1, E0, M, segmask, segpre, segtab, L3_NT);
         __syncthreads();
-        // prefix over the 16 warp totals
-        u32 ws = lane < (u32)(L3_NT / 32) ? misc[lane] : 0u;
-        u32 wi = ws;
-#pragma unroll
-        for (int o = 1; o < L3_NT / 32; o <<= 1) {
-            u32 x = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= (unsigned)o) wi += x;
-        }
-        u32 run = __shfl_sync(0xffffffffu, wi - ws, warp) + incl - sum;
-#pragma unroll
-        for (int q = 0; q < L3_IPT; ++q) {
-            u32 c = v[q];
-            v[q] = run;
-            run += c;
-        }
-        if (mine) {
-#pragma unroll
-            for (int q = 0; q < L3_IPT / 4; ++q) p4[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
-    }
-    __syncthreads();
 
-    // ---- pass 2: elements (re-read: cache hits) go to their sub-bin ----
+        // ---- pass 1: sub-bin = expected sorted position of the element inside its bucket at a
+        // quarter of a position's resolution; the four sub-bins of a position are byte counters
+        // of one word (a crowded sub-bin declines the tile before a byte can overflow) ----
+        u32 meta[L3_IPT];
+        u32 myslot = 0;
 #pragma unroll
-    for (int j = 0; j < L3_IPT; ++j) {
-        const u32 i = (u32)j * L3_NT + tid;
-        if ((u32)j * L3_NT >= M) break;
-        if (i < M) {
-            const u64 e = src[i];
-            const u32 word = meta[j] & 8191u, sub8 = (meta[j] >> 13) & 31u, slot = meta[j] >> 18;
-            const u32 w = cnt[word];
-            const u32 p0 = pre[word] + bytesum(w & ((1u << sub8) - 1u));
-            const u32 c = (w >> sub8) & 255u;
-            X[p0 + slot] = e;
-            meta[j] = p0 | (slot << 13) | (c << 19);
+        for (int j = 0; j < L3_IPT; ++j) {
+            const u32 i = (u32)j * L3_NT + tid;
+            meta[j] = 0;
+            if ((u32)j * L3_NT >= M) break;
+            if (i < M) {
+                const u32 hi = (u32)(src[i] >> 32);
+                const uint2 sg = segtab[seg_index(segmask, segpre, i)];
+                const u32 rem = (hi >> a.pb) & remmask;
+                const u32 fb = (u32)(((u64)rem * (u64)(sg.y * 4u)) >> a.R);
+                const u32 word = sg.x + (fb >> 2), sub8 = (fb & 3u) * 8u;
+                const u32 slot = (atomicAdd(&cnt[word], 1u << sub8) >> sub8) & 255u;
+                myslot = max(myslot, slot);
+                meta[j] = word | (sub8 << 13) | (slot << 18);
+            }
         }
-    }
-    __syncthreads();
-
-    // ---- order inside every bin: final slot = bin start + number of smaller elements ----
-    // The high word of an element is [rest of key | preceding symbol]; inside a bucket its bits
-    // above `pb` order the elements, so the common case compares 32-bit words.  Equal keys
-    // (a short suffix next to its padded twin, or two long suffixes that stay active) are rare
-    // and take the tie-break loop.
-    const u32 *Xh = (const u32 *)X;
 #pragma unroll
-    for (int j = 0; j < L3_IPT; ++j) {
-        const u32 i = (u32)j * L3_NT + tid;
-        if ((u32)j * L3_NT >= M) break;
-        if (i < M) {
-            const u32 p0 = meta[j] & 8191u, slot = (meta[j] >> 13) & 63u, c = meta[j] >> 19;
-            if (c == 1) {
-                perm[p0] = (u16)p0;
-            } else {
-                const u32 ke = Xh[2 * (p0 + slot) + 1] >> a.pb;
-                u32 less = 0, eq = 0;
-                for (u32 q = 0; q < c; ++q) {
-                    const u32 ko = Xh[2 * (p0 + q) + 1] >> a.pb;
-                    less += ko < ke ? 1u : 0u;
-                    eq += ko == ke ? 1u : 0u;
+        for (int o = 16; o > 0; o >>= 1) myslot = max(myslot, __shfl_xor_sync(0xffffffffu, myslot, o));
+        if (lane == 0 && myslot) atomicMax(&misc[32], myslot);
+        __syncthreads();
+        // W = largest sub-bin occupancy of the tile minus one: how far an element can stand from
+        // its sorted position once the tile is grouped by sub-bin
+        const u32 W = misc[32];
+        const bool crowded = W >= (u32)L3_CROWD;
+
+        if (!crowded) {
+            // ---- exclusive scan of the per-position totals (thread owns L3_IPT consecutive positions) ----
+            {
+                const u32 base = tid * L3_IPT;
+                const bool mine = base <= M;  // positions past M are empty (and were not zeroed)
+                u32 v[L3_IPT];
+                u32 sum = 0;
+#pragma unroll
+                for (int q = 0; q < L3_IPT; ++q) {
+                    v[q] = mine ? bytesum(cnt[base + q]) : 0u;
+                    sum += v[q];
                 }
-                u32 active = 0;
-                if (eq > 1) {
-                    const u32 se = Xh[2 * (p0 + slot)];
-                    const bool e_short = is_short_suffix(se, a.K, a.n);
-                    for (u32 q = 0; q < c; ++q) {
-                        if (q == slot || (Xh[2 * (p0 + q) + 1] >> a.pb) != ke) continue;
-                        const u32 so = Xh[2 * (p0 + q)];
-                        if (is_short_suffix(so, a.K, a.n)) {
-                            if (!e_short || so > se) ++less;   // short ones first, shortest first
-                        } else if (!e_short) {
-                            active = 1;                        // two long suffixes share the key
-                            if (q < slot) ++less;
-                        }
+                u32 incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    u32 x = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= (unsigned)o) incl += x;
+                }
+                if (lane == 31) misc[warp] = incl;
+                __syncthreads();
+                u32 ws = lane < (u32)(L3_NT / 32) ? misc[lane] : 0u;
+                u32 wi = ws;
+#pragma unroll
+                for (int o = 1; o < L3_NT / 32; o <<= 1) {
+                    u32 x = __shfl_up_sync(0xffffffffu, wi, o);
+                    if (lane >= (unsigned)o) wi += x;
+                }
+                u32 run = __shfl_sync(0xffffffffu, wi - ws, warp) + incl - sum;
+                if (mine) {
+#pragma unroll
+                    for (int q = 0; q < L3_IPT; ++q) {
+                        pre[base + q] = (u16)run;
+                        run += v[q];
                     }
                 }
-                perm[p0 + less] = (u16)((p0 + slot) | (active << 15));
             }
-        }
-    }
-    __syncthreads();
+            __syncthreads();
 
-    // ---- output in sorted order (coalesced) ----
-    for (u32 i = tid; i < ((M + 31u) & ~31u); i += L3_NT) {
-        if (i < M) {
-            const u32 v = perm[i];
-            const u64 e = X[v & 8191u];
-            const bool active = v >> 15;
-            u32 h = i;
-            if (active) {
-                const u64 ke = (e >> eshift) & remmask;
-                while (h > 0 && !((segmask[h >> 5] >> (h & 31u)) & 1u)) {
-                    const u32 v2 = perm[h - 1];
-                    if (!(v2 >> 15)) break;
-                    if (((X[v2 & 8191u] >> eshift) & remmask) != ke) break;
-                    --h;
+            // ---- pass 2: elements go to their sub-bin (any order inside it) ----
+#pragma unroll
+            for (int j = 0; j < L3_IPT; ++j) {
+                const u32 i = (u32)j * L3_NT + tid;
+                if ((u32)j * L3_NT >= M) break;
+                if (i < M) {
+                    const u32 word = meta[j] & 8191u, sub8 = (meta[j] >> 13) & 31u, slot = meta[j] >> 18;
+                    const u32 below = bytesum(cnt[word] & ((1u << sub8) - 1u));
+                    X[(u32)pre[word] + below + slot] = src[i];
                 }
             }
-            l3_emit(a, E0 + i, e, active, E0 + h);
+        }
+        __syncthreads();
+
+        if (tid == 0) {
+            if (crowded) a.flagged[atomicAdd(a.nflagged, 1u)] = t;
+            advance(t + gridDim.x);
+        }
+        if (crowded) continue;
+
+        // ---- pass 3, one thread per POSITION of the grouped tile.  Sub-bins are contiguous and
+        // ordered by key, so the sorted position of the element at p is p minus the larger keys
+        // among the W positions to its left plus the smaller keys among the W to its right
+        // (elements outside its sub-bin contribute nothing).  No per-element loop bounds: W is
+        // uniform over the tile.  The high word of an element is [rest of key | preceding
+        // symbol]; its bits above `pb` order the elements of all buckets under one level-1
+        // parent, so bucket boundaries need a check only in tiles that span two parents
+        // (always with a single level).  Equal keys (a short suffix next to its padded twin, or
+        // long suffixes that stay active) are rare and take the tie-break path. ----
+        const u32 *Xh = (const u32 *)X;
+        const bool segcheck = (b0 >> a.par_shift) != ((b1 - 1u) >> a.par_shift);
+        for (u32 p = tid; p < M; p += L3_NT) {
+            const u32 kp = Xh[2 * p + 1] >> a.pb;
+            u32 r = p;
+            bool eq = false, lv = true, rv = true;
+            for (u32 d = 1; d <= W; ++d) {
+                lv = lv && p >= d;
+                rv = rv && p + d < M;
+                if (segcheck) {
+                    const u32 xl = p - d + 1u, xr = p + d;  // a bucket starts here: the neighbour is beyond it
+                    if (lv && ((segmask[xl >> 5] >> (xl & 31u)) & 1u)) lv = false;
+                    if (rv && ((segmask[xr >> 5] >> (xr & 31u)) & 1u)) rv = false;
+                }
+                if (lv) {
+                    const u32 ko = Xh[2 * (p - d) + 1] >> a.pb;
+                    r -= ko > kp ? 1u : 0u;
+                    eq = eq || ko == kp;
+                }
+                if (rv) {
+                    const u32 ko = Xh[2 * (p + d) + 1] >> a.pb;
+                    r += ko < kp ? 1u : 0u;
+                    eq = eq || ko == kp;
+                }
+            }
+            const u64 e = X[p];
+            bool active = false;
+            u32 head = r;
+            if (eq) {
+                // final order among equal keys: short suffixes first, shortest (largest start)
+                // first; then the long ones in position order, which form an active group
+                const u32 se = (u32)e;
+                const bool e_short = is_short_suffix(se, a.K, a.n);
+                u32 longs_before = 0;
+                lv = rv = true;
+                for (u32 d = 1; d <= W; ++d) {
+                    lv = lv && p >= d;
+                    rv = rv && p + d < M;
+                    if (segcheck) {
+                        const u32 xl = p - d + 1u, xr = p + d;
+                        if (lv && ((segmask[xl >> 5] >> (xl & 31u)) & 1u)) lv = false;
+                        if (rv && ((segmask[xr >> 5] >> (xr & 31u)) & 1u)) rv = false;
+                    }
+                    if (lv && (Xh[2 * (p - d) + 1] >> a.pb) == kp) {
+                        const u32 so = Xh[2 * (p - d)];
+                        const bool o_short = is_short_suffix(so, a.K, a.n);
+                        // the left neighbour belongs AFTER this element
+                        if (o_short ? (e_short && so < se) : e_short) --r;
+                        if (!o_short && !e_short) { active = true; ++longs_before; }
+                    }
+                    if (rv && (Xh[2 * (p + d) + 1] >> a.pb) == kp) {
+                        const u32 so = Xh[2 * (p + d)];
+                        const bool o_short = is_short_suffix(so, a.K, a.n);
+                        // the right neighbour belongs BEFORE this element
+                        if (o_short ? (!e_short || so > se) : false) ++r;
+                        if (!o_short && !e_short) active = true;
+                    }
+                }
+                head = r - longs_before;
+            }
+            l3_emit(a, E0 + r, e, active, E0 + head);
         }
     }
 }
@@ -978,7 +1027,7 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         default: launch_hist_text<8>(ix, nwords_data, pl.D[0], cursor[0], st); break;
     }
     {
-        unsigned bd = std::max(32u, (unsigned)nb[0]);
+        unsigned bd = std::min(1024u, std::max(32u, (unsigned)nb[0]));
         msd_scan_children_kernel<<<1, bd, 0, st>>>(cursor[0], nullptr, pl.D[0], 1, len, start[0],
                                                    pl.nlevels == 1 ? d_misc : nullptr);
         KERNEL_CHECK();
@@ -1016,7 +1065,7 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         msd_hist_elems_kernel<<<grid, P_NT, 0, st>>>(cur, desc, d_misc + 1, pl.D[l], dshift, cursor[l]);
         KERNEL_CHECK();
         {
-            unsigned bd = std::max(32u, 1u << pl.D[l]);
+            unsigned bd = std::min(1024u, std::max(32u, 1u << pl.D[l]));
             msd_scan_children_kernel<<<nparents, bd, 0, st>>>(cursor[l], start[l - 1], pl.D[l], nparents, len, start[l],
                                                               l == pl.nlevels - 1 ? d_misc : nullptr);
             KERNEL_CHECK();
@@ -1049,12 +1098,14 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     L3Args la{};
     la.in = cur; la.bstart = start[last]; la.tile_first = tile_first; la.n = n;
     la.K = pl.K; la.pb = pl.pb; la.R = pl.R;
+    la.par_shift = pl.BB - pl.D[0];
     la.sa = ix.sa.ptr;
     la.bwt = (want_bwt && pl.pb) ? ix.bwt.ptr : nullptr;
     la.rank = r.rank; la.valid = r.valid; la.act = r.act; la.act_count = d_misc + 3;
     la.primary = r.d_primary;
     la.flagged = flagged; la.nflagged = d_misc + 4;
-    msd_local_sort_kernel<<<ntl3, L3_NT, L3_SMEM, st>>>(la);
+    la.ntiles = ntl3;
+    msd_local_sort_kernel<<<std::min(ntl3, 2u * sm_count(ix.device)), L3_NT, L3_SMEM, st>>>(la);
     KERNEL_CHECK();
     u32 hmisc[8];
     CUDA_CHECK(cudaMemcpyAsync(hmisc, d_misc, sizeof hmisc, cudaMemcpyDeviceToHost, st));
