@@ -717,13 +717,20 @@ __global__ void __launch_bounds__(L3_NT, 2) msd_local_sort_kernel(L3Args a) {
         // of one word (a crowded sub-bin declines the tile before a byte can overflow) ----
         u32 meta[L3_IPT];
         u32 myslot = 0;
+        // all loads of the pass are issued before the first shared-memory atomic (the high word of
+        // an element is all this pass needs)
+        const u32 *src_hi = (const u32 *)src + 1;
 #pragma unroll
         for (int j = 0; j < L3_IPT; ++j) {
             const u32 i = (u32)j * L3_NT + tid;
-            meta[j] = 0;
+            meta[j] = i < M ? src_hi[2 * i] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < L3_IPT; ++j) {
+            const u32 i = (u32)j * L3_NT + tid;
             if ((u32)j * L3_NT >= M) break;
             if (i < M) {
-                const u32 hi = (u32)(src[i] >> 32);
+                const u32 hi = meta[j];
                 const uint2 sg = segtab[seg_index(segmask, segpre, i)];
                 const u32 rem = (hi >> a.pb) & remmask;
                 const u32 fb = (u32)(((u64)rem * (u64)(sg.y * 4u)) >> a.R);
