@@ -402,6 +402,7 @@ __global__ void __launch_bounds__(P_NT, 2) msd_partition_kernel(PartArgs a) {
         __syncthreads();
 
         // ---- consecutive threads write consecutive slots of a digit run ----
+#pragma unroll 4
         for (u32 i = tid; i < count; i += P_NT) {
             const u64 v = buf[i];
             a.out[gofs[(u32)(v >> a.dshift) & (B - 1)] + i] = v;
@@ -444,6 +445,9 @@ __device__ __forceinline__ void stage_window(const u64 *st, u32 off, u64 &H, u64
     L = o ? (w1 << o) | (w2 >> (64 - o)) : w1;
 }
 
+// BITS = symbol width, HAS_PREV = the preceding symbol is carried in the element (pb == BITS):
+// compile-time so that every per-symbol shift is an immediate.
+template <int BITS, bool HAS_PREV>
 __global__ void __launch_bounds__(T1_NT, 2) msd_partition_text_kernel(Text1Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *buf = (u64 *)smem_raw;                   // [T1_TILE] elements grouped by digit
@@ -453,15 +457,16 @@ __global__ void __launch_bounds__(T1_NT, 2) msd_partition_text_kernel(Text1Args 
     u16 *dig = (u16 *)(gofs + MSD_MAXBINS);       // [T1_TILE] digit of the element in slot i
     u32 *wsum = (u32 *)(dig + T1_TILE);           // [32]
 
+    constexpr int b = BITS;
+    constexpr u32 lead = HAS_PREV ? (u32)BITS : 0u;
     const u32 tid = threadIdx.x;
     const u32 B = 1u << a.D;
-    const int b = a.bits;
     const u64 begin = (u64)blockIdx.x * T1_TILE;
     const u32 count = (u32)min((u64)T1_TILE, (u64)a.len - begin);
 
     // ---- stage the tile's text: word k of `stage` is packed[begin*b/64 - 1 + k] ----
     {
-        const u32 nstage = (u32)(T1_TILE / 64) * b + 4;
+        constexpr u32 nstage = (u32)(T1_TILE / 64) * b + 4;
         const u64 w0 = begin * (u64)b / 64;
         for (u32 k = tid; k < nstage; k += T1_NT) {
             const u64 w = w0 + k;  // index + 1
@@ -473,26 +478,27 @@ __global__ void __launch_bounds__(T1_NT, 2) msd_partition_text_kernel(Text1Args 
 
     // bit offset (inside `stage`) of the window of the thread's first position: it starts at the
     // preceding symbol when that symbol is carried in the element, else at the position itself
-    const u32 lead = a.pb ? (u32)b : 0u;
     const u32 i0 = tid * T1_IPT;
     const u32 off0 = 64u + i0 * (u32)b - lead;
     const int kshift = 64 - a.KB;
+    const int dsh = 32 - a.D;                           // digit = leading D bits of the key
+    const u32 restmask = (u32)a.restmask;               // KB - D <= 32 bits
 
     // ---- digits and slots inside the tile's digit groups (arbitrary order: MSD) ----
     u32 ds[T1_IPT];
 #pragma unroll
     for (int g = 0; g < T1_IPT / 8; ++g) {
         u64 H, L;
-        stage_window(stage, off0 + (u32)(8 * g) * (u32)b, H, L);
+        stage_window(stage, off0 + (u32)(8 * g * b), H, L);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int j = 8 * g + q;
-            const u32 sh = (u32)q * (u32)b;
+            const int sh = q * b;
             const u64 win = sh ? (H << sh) | (L >> (64 - sh)) : H;
-            const u64 key = (win << lead) >> kshift;
+            const u32 khi = (u32)((win << lead) >> 32);  // leading 32 bits of the key
             ds[j] = 0;
             if (i0 + j < count) {
-                const u32 d = (u32)(key >> a.dshift);
+                const u32 d = khi >> dsh;
                 const u32 slot = atomicAdd(&hist[d], 1u);
                 ds[j] = d | (slot << 10);
             }
@@ -528,22 +534,24 @@ __global__ void __launch_bounds__(T1_NT, 2) msd_partition_text_kernel(Text1Args 
     }
     __syncthreads();
 
-    // ---- form the elements (again from the staged text) and group the tile by digit ----
+    // ---- form the elements (again from the staged text) and group the tile by digit.  An
+    // element is two 32-bit words: [rest of key | preceding symbol] and the suffix start ----
+    const u32 p0 = (u32)begin + i0;
 #pragma unroll
     for (int g = 0; g < T1_IPT / 8; ++g) {
         u64 H, L;
-        stage_window(stage, off0 + (u32)(8 * g) * (u32)b, H, L);
+        stage_window(stage, off0 + (u32)(8 * g * b), H, L);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int j = 8 * g + q;
             if (i0 + j < count) {
-                const u32 sh = (u32)q * (u32)b;
+                const int sh = q * b;
                 const u64 win = sh ? (H << sh) | (L >> (64 - sh)) : H;
-                const u64 key = (win << lead) >> kshift;
-                const u64 prev = a.pb ? win >> (64 - b) : 0ull;
+                const u32 rest = (u32)((win << lead) >> kshift) & restmask;
+                const u32 hiw = HAS_PREV ? (rest << b) | (u32)(win >> (64 - b)) : rest;
                 const u32 d = ds[j] & 1023u;
                 const u32 pos = hist[d] + (ds[j] >> 10);
-                buf[pos] = ((key & a.restmask) << a.rest_shift) | (prev << 32) | (begin + i0 + j);
+                buf[pos] = ((u64)hiw << 32) | (u64)(p0 + (u32)j);
                 dig[pos] = (u16)d;
             }
         }
@@ -551,6 +559,7 @@ __global__ void __launch_bounds__(T1_NT, 2) msd_partition_text_kernel(Text1Args 
     __syncthreads();
 
     // ---- consecutive threads write consecutive slots of a digit run ----
+#pragma unroll 4
     for (u32 i = tid; i < count; i += T1_NT) a.out[gofs[dig[i]] + i] = buf[i];
 }
 
@@ -989,7 +998,14 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
 
     static bool configured = false;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_local_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L3_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_local_sort_robust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
@@ -1053,7 +1069,18 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         ta.rest_shift = 32 + pl.pb;
         ta.cursor = cursor[0];
         t = ix.timer.begin("msd_part1", (double)len * (8.0 + b / 8.0));
-        msd_partition_text_kernel<<<div_up_u(len, T1_TILE), T1_NT, T1_SMEM, st>>>(ta);
+        const unsigned g1 = div_up_u(len, T1_TILE);
+        const int which = (b == 1 ? 0 : b == 2 ? 1 : b == 4 ? 2 : 3) * 2 + (pl.pb ? 1 : 0);
+        switch (which) {
+            case 0: msd_partition_text_kernel<1, false><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
+            case 1: msd_partition_text_kernel<1, true><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
+            case 2: msd_partition_text_kernel<2, false><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
+            case 3: msd_partition_text_kernel<2, true><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
+            case 4: msd_partition_text_kernel<4, false><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
+            case 5: msd_partition_text_kernel<4, true><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
+            case 6: msd_partition_text_kernel<8, false><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
+            default: msd_partition_text_kernel<8, true><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
+        }
         KERNEL_CHECK();
         ix.timer.end(t);
     }
