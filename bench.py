@@ -122,11 +122,21 @@ STAGE_KERNELS = {
 }
 
 
-def load_traffic(kernel_key):
-    """ncu dram bytes per launch of the dominant kernel, if a capture was summarised in profiles/."""
+def load_traffic(kernel_key, n=None):
+    """ncu dram__bytes_read.sum + dram__bytes_write.sum of the kernel behind a build stage, per launch,
+    from the capture summarised in profiles/roofline_traffic.json (scaled linearly when this run's
+    text length differs from the captured one).  None when there is no capture for the stage."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
-        return json.load(open(p)).get(kernel_key)
+        ent = json.load(open(p)).get(kernel_key)
+        if ent is None:
+            return None
+        if isinstance(ent, dict):
+            v = float(ent["dram_bytes_per_launch"])
+            if n is not None and ent.get("n") and int(ent["n"]) != int(n):
+                v *= float(n) / float(ent["n"])
+            return v
+        return float(ent)
     except Exception:
         return None
 
@@ -346,7 +356,7 @@ def gpu_arm(args, rank, local_rank, world):
         pass_ms = dms / dlaunch
         pass_bytes = dbytes / dlaunch
         achieved = pass_bytes / (pass_ms / 1e3) / 1e9
-        traffic = load_traffic(dname)
+        traffic = load_traffic(dname, n)
         roofline = {"bound": "hbm", "kernel": STAGE_KERNELS.get(dname, dname), "stage": dname,
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src,

@@ -120,6 +120,13 @@ int b200sa_search_batch(const b200sa_index *idx, const uint8_t *patterns, const 
 int b200sa_search_device(const b200sa_index *idx, const uint8_t *d_patterns,
                          const uint64_t *d_offsets, uint32_t fixed_len, uint64_t npat,
                          uint32_t *d_L, uint32_t *d_R, void *stream);
+/* Measurement aid: the same search (DNA index, 8-byte aligned device patterns), run by a counting
+ * variant of the kernel.  counts[0] = 32-byte O-block loads, [1] = 8-byte pattern words,
+ * [2] = 8-byte packed-text words, [3] = 4-byte SA / ISA loads issued for the whole batch:
+ * the algorithmic bytes behind bench.py's search roofline.  Synchronises the stream. */
+int b200sa_search_traffic(const b200sa_index *idx, const uint8_t *d_patterns,
+                          const uint64_t *d_offsets, uint32_t fixed_len, uint64_t npat,
+                          uint32_t *d_L, uint32_t *d_R, uint64_t counts[4], void *stream);
 
 /* ---- locate (next_bwt_exact_match_iter, bwt.c:201-217) -------------------------------------
  * pos_off[npat + 1] receives a CSR; positions of pattern p are pos[pos_off[p] .. pos_off[p+1]),

@@ -361,6 +361,26 @@ int b200sa_search_device(const b200sa_index *idx, const uint8_t *d_patterns, con
     API_GUARD_END(nullptr)
 }
 
+int b200sa_search_traffic(const b200sa_index *idx, const uint8_t *d_patterns, const uint64_t *d_offsets,
+                          uint32_t fixed_len, uint64_t npat, uint32_t *d_L, uint32_t *d_R, uint64_t counts[4],
+                          void *stream) {
+    if (!idx || !counts || (npat && (!d_patterns || !d_L || !d_R))) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    if (idx->ix.occ_layout != OCC_DNA32 || (((uintptr_t)d_patterns) & 7))
+        return fail(B200SA_ERR_NOT_BUILT, "traffic counters exist for the DNA search kernel (8-byte aligned patterns) only", nullptr);
+    API_GUARD_BEGIN
+    CUDA_CHECK(cudaSetDevice(idx->ix.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf<unsigned long long> d(4, st);
+    CUDA_CHECK(cudaMemsetAsync(d.ptr, 0, 4 * sizeof(unsigned long long), st));
+    fm_search(idx->ix, d_patterns, d_offsets, fixed_len, npat, d_L, d_R, st, d.ptr);
+    unsigned long long h[4];
+    CUDA_CHECK(cudaMemcpyAsync(h, d.ptr, sizeof h, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int i = 0; i < 4; ++i) counts[i] = h[i];
+    return 0;
+    API_GUARD_END(nullptr)
+}
+
 int b200sa_search_batch(const b200sa_index *idx, const uint8_t *patterns, const uint64_t *offsets,
                         uint32_t fixed_len, uint64_t npat, uint32_t *L, uint32_t *R) {
     if (!idx || (npat && (!patterns || !L || !R))) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);

@@ -70,7 +70,7 @@ void occ_probe(const DeviceIndex &ix, const u8 *d_a, const u32 *d_i, u64 count, 
 void occ_dense(const DeviceIndex &ix, u32 *d_out);  // (len+1)*sigma entries, reference layout
 // fm_search.cu
 void fm_search(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fixed_len, u64 npat, u32 *d_L,
-               u32 *d_R, cudaStream_t st);
+               u32 *d_R, cudaStream_t st, unsigned long long *d_stats = nullptr);
 u64 fm_locate_count(const DeviceIndex &ix, const u32 *d_L, const u32 *d_R, u64 npat, u64 *d_pos_off,
                     cudaStream_t st);
 void fm_locate_fill(const DeviceIndex &ix, const u32 *d_L, const u32 *d_R, u64 npat, const u64 *d_pos_off,

@@ -116,13 +116,17 @@ struct TextCmp {
     const u64 *packed;  // 2-bit symbols, big-endian inside each word (sa_build.cu pack_kernel<2>)
 };
 
-template <int LM, bool SC>
+// STATS: count the memory operations of the batch (b200sa_search_traffic, a measurement aid):
+// stats[0] 32-byte O-block loads, [1] 8-byte pattern words, [2] 8-byte text words, [3] 4-byte SA/ISA loads.
+template <int LM, bool SC, bool STATS>
 __global__ void __launch_bounds__(256) fm_search_dna_kernel(OccView ov, CTable5 c5, TextCmp tc, u32 len,
                                                             const u8 *__restrict__ pat,
                                                             const u64 *__restrict__ off, u32 fixed_len, u64 npat,
-                                                            u32 *__restrict__ outL, u32 *__restrict__ outR) {
+                                                            u32 *__restrict__ outL, u32 *__restrict__ outR,
+                                                            unsigned long long *__restrict__ stats) {
     u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= npat) return;
+    u32 n_blk = 0, n_pw = 0, n_tw = 0, n_sa = 0;
     u64 begin = off ? off[q] : q * (u64)fixed_len;
     u64 m = off ? off[q + 1] - begin : (u64)fixed_len;
     u32 L = 0, R = len;
@@ -138,6 +142,7 @@ __global__ void __launch_bounds__(256) fm_search_dna_kernel(OccView ov, CTable5 
             // symbols pattern[i], pattern[i-1], ... one O lookup each, moving to ISA[s-1], ISA[s-2], ...
             // as long as they equal text[s-1], text[s-2], ...; compare them against the text instead.
             const u32 s = tc.sa[L];
+            if (STATS) ++n_sa;
             const u64 rem = (u64)i + 1;
             u64 k = 0;
             u64 tw = 0, tw_idx = ~0ull;
@@ -147,6 +152,7 @@ __global__ void __launch_bounds__(256) fm_search_dna_kernel(OccView ov, CTable5 
                 if ((addr & ~7ull) != word_addr) {
                     word_addr = addr & ~7ull;
                     word = *(const u64 *)(pat + word_addr);
+                    if (STATS) ++n_pw;
                 }
                 a = (u32)(word >> (8 * (addr & 7))) & 0xffu;
                 if (k >= (u64)s) break;  // suffix 0 is preceded by the sentinel only
@@ -154,6 +160,7 @@ __global__ void __launch_bounds__(256) fm_search_dna_kernel(OccView ov, CTable5 
                 if ((t >> 5) != tw_idx) {
                     tw_idx = t >> 5;
                     tw = tc.packed[tw_idx];
+                    if (STATS) ++n_tw;
                 }
                 u32 sym = (u32)(tw >> (62 - 2 * (t & 31))) & 3u;
                 if (a - 1u != sym) break;
@@ -162,6 +169,7 @@ __global__ void __launch_bounds__(256) fm_search_dna_kernel(OccView ov, CTable5 
             if (k == rem) {
                 L = tc.isa[s - (u32)rem];
                 R = L + 1;
+                if (STATS) ++n_sa;
             } else if (a - 1u > 3u || a >= ov.sigma) {
                 L = 1;
                 R = 0;
@@ -171,6 +179,10 @@ __global__ void __launch_bounds__(256) fm_search_dna_kernel(OccView ov, CTable5 
                 BlockRegs kb = load_dna_block<LM>(ov.blocks, Lk >> 6);
                 BlockRegs kb2 = kb;
                 if (((Lk + 1) >> 6) != (Lk >> 6)) kb2 = load_dna_block<LM>(ov.blocks, (Lk + 1) >> 6);
+                if (STATS) {
+                    n_sa += k ? 1u : 0u;
+                    n_blk += 1u + ((((Lk + 1) >> 6) != (Lk >> 6)) ? 1u : 0u);
+                }
                 L = c5.c[a] + rank_in_block(kb, a, Lk, ov.primary);
                 R = c5.c[a] + rank_in_block(kb2, a, Lk + 1, ov.primary);
             }
@@ -180,6 +192,7 @@ __global__ void __launch_bounds__(256) fm_search_dna_kernel(OccView ov, CTable5 
         if ((addr & ~7ull) != word_addr) {
             word_addr = addr & ~7ull;
             word = *(const u64 *)(pat + word_addr);
+            if (STATS) ++n_pw;
         }
         u32 a = (u32)(word >> (8 * (addr & 7))) & 0xffu;
         if (a - 1u > 3u || a >= ov.sigma) {
@@ -191,16 +204,23 @@ __global__ void __launch_bounds__(256) fm_search_dna_kernel(OccView ov, CTable5 
         BlockRegs kL = load_dna_block<LM>(ov.blocks, bL);
         BlockRegs kR = kL;
         if (bR != bL) kR = load_dna_block<LM>(ov.blocks, bR);
+        if (STATS) n_blk += bR != bL ? 2u : 1u;
         const u32 ca = c5.c[a];
         L = ca + rank_in_block(kL, a, L, ov.primary);
         R = ca + rank_in_block(kR, a, R, ov.primary);
     }
     outL[q] = L;
     outR[q] = R;
+    if (STATS) {
+        atomicAdd(&stats[0], (unsigned long long)n_blk);
+        atomicAdd(&stats[1], (unsigned long long)n_pw);
+        atomicAdd(&stats[2], (unsigned long long)n_tw);
+        atomicAdd(&stats[3], (unsigned long long)n_sa);
+    }
 }
 
 void fm_search(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fixed_len, u64 npat, u32 *d_L,
-               u32 *d_R, cudaStream_t st) {
+               u32 *d_R, cudaStream_t st, unsigned long long *d_stats) {
     if (!npat) return;
     OccView ov = occ_view(ix);
     CTable5 c5;
@@ -213,8 +233,12 @@ void fm_search(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fix
         static const bool no_sc = getenv("B200SA_SEARCH_NO_TEXTCMP") != nullptr;
         TextCmp tc{ix.sa.ptr, ix.isa.ptr, ix.text_packed.ptr};
         const bool sc = tc.sa && tc.isa && tc.packed && ix.pk.bits == 2 && !no_sc;
-#define LAUNCH_DNA(LM_, SC_) fm_search_dna_kernel<LM_, SC_><<<blocks, 256, 0, st>>>(ov, c5, tc, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R)
-        if (sc) {
+#define LAUNCH_DNA(LM_, SC_) fm_search_dna_kernel<LM_, SC_, false><<<blocks, 256, 0, st>>>(ov, c5, tc, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R, nullptr)
+        if (d_stats) {
+            // counting variant of the default configuration
+            if (sc) fm_search_dna_kernel<3, true, true><<<blocks, 256, 0, st>>>(ov, c5, tc, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R, d_stats);
+            else fm_search_dna_kernel<3, false, true><<<blocks, 256, 0, st>>>(ov, c5, tc, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R, d_stats);
+        } else if (sc) {
             if (lm == 0) LAUNCH_DNA(0, true); else LAUNCH_DNA(3, true);
         } else {
             switch (lm) {

@@ -34,12 +34,13 @@ static constexpr int P_IPT = 8;
 static constexpr int P_TILE = P_NT * P_IPT;  // 4096 elements
 // local sort
 static constexpr int L3_NT = 512;
-static constexpr int L3_TSZ = 2048;                // a tile owns the buckets that START in its span
-static constexpr int L3_MAXB = 4096;               // largest bucket the fast path accepts
-static constexpr int L3_CAP = L3_TSZ + L3_MAXB;    // 6144 elements of a tile in shared memory
-static constexpr int L3_IPT = L3_CAP / L3_NT;      // 12
+static constexpr int L3_TSZ = 1792;                // a tile owns the buckets that START in its span
+static constexpr int L3_MAXB = 3328;               // largest bucket the fast path accepts
+static constexpr int L3_CAP = L3_TSZ + L3_MAXB;    // 5120 elements of a tile in shared memory
+static constexpr int L3_IPT = L3_CAP / L3_NT;      // 10
+static constexpr int L3_CTAS = 3;                  // resident CTAs per SM
 static constexpr int L3_CROWD = 64;                // more elements than this in one sub-bin -> robust kernel
-static constexpr int L3_MASKW = 192;               // words of segment-start bits (>= L3_CAP / 32, a multiple of 32)
+static constexpr int L3_MASKW = 160;               // words of segment-start bits (>= L3_CAP / 32, a multiple of 32)
 static_assert(L3_CAP % L3_NT == 0 && L3_MASKW * 32 >= L3_CAP && L3_MASKW % 32 == 0, "local-sort geometry");
 static constexpr int RB_N = 8192;                  // robust kernel: bitonic network size
 
@@ -68,7 +69,7 @@ bool msd_make_plan(u32 len, u32 sigma, int bits, MsdPlan &pl) {
     int dmax = (b == 4 || b == 8) ? 8 : 10;
     dmax = env_int2("B200SA_MSD_DMAX", dmax);
     dmax = std::max(b, std::min(10, dmax / b * b));
-    const int target = std::max(1, env_int2("B200SA_MSD_AVG", 3400));
+    const int target = std::max(1, env_int2("B200SA_MSD_AVG", 3000));
     int BB = b;
     while (((u64)len >> BB) > (u64)target && BB + b <= 3 * dmax) BB += b;
     int forced = env_int2("B200SA_MSD_BB", 0);
@@ -676,7 +677,7 @@ __device__ __forceinline__ u32 bytesum(u32 x) { return __dp4a(x, 0x01010101u, 0u
 // tile_first -> bucket_start for the CTA's NEXT tile and asks the TMA engine to pull that tile's
 // elements into L2 (cp.async.bulk.prefetch), so the chain of dependent loads is off every
 // warp's critical path and the next tile's first pass reads L2, not HBM.
-__global__ void __launch_bounds__(L3_NT, 2) msd_local_sort_kernel(L3Args a) {
+__global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *X = (u64 *)smem_raw;                         // [L3_CAP] elements grouped by bin
     u32 *cnt = (u32 *)(X + L3_CAP);                   // [L3_CNTN] four byte-wide sub-bin counts per position
@@ -1139,7 +1140,7 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     la.primary = r.d_primary;
     la.flagged = flagged; la.nflagged = d_misc + 4;
     la.ntiles = ntl3;
-    msd_local_sort_kernel<<<std::min(ntl3, 2u * sm_count(ix.device)), L3_NT, L3_SMEM, st>>>(la);
+    msd_local_sort_kernel<<<std::min(ntl3, (unsigned)L3_CTAS * sm_count(ix.device)), L3_NT, L3_SMEM, st>>>(la);
     KERNEL_CHECK();
     u32 hmisc[8];
     CUDA_CHECK(cudaMemcpyAsync(hmisc, d_misc, sizeof hmisc, cudaMemcpyDeviceToHost, st));
