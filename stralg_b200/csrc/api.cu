@@ -103,17 +103,17 @@ __attribute__((visibility("hidden"))) static int build_into(b200sa_index *h, con
     cudaStream_t st = ix.stream;
     if (flags & B200SA_PROFILE) ix.timer.enable(st);
 
-    if (flags & B200SA_TEXT_ON_DEVICE) {
-        ix.text_ptr = codes;
-    } else {
-        ix.text.alloc((size_t)n + 1, st);
-        if (n) CUDA_CHECK(cudaMemcpyAsync(ix.text.ptr, codes, n, cudaMemcpyHostToDevice, st));
-        CUDA_CHECK(cudaMemsetAsync(ix.text.ptr + n, 0, 1, st));
-        ix.text_ptr = ix.text.ptr;
-    }
     // one build at a time per device: the workspace arena is shared and persistent
     std::lock_guard<std::mutex> arena_lock(g_arena_mu[device & 63]);
     Arena &arena = g_arena[device & 63];
+    if (flags & B200SA_TEXT_ON_DEVICE) {
+        ix.text_ptr = codes;
+    } else {
+        u8 *stage = (u8 *)arena.side_alloc((size_t)n + 1);
+        if (n) CUDA_CHECK(cudaMemcpyAsync(stage, codes, n, cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemsetAsync(stage + n, 0, 1, st));
+        ix.text_ptr = stage;
+    }
     arena.reset();
     arena.reserve_first(build_workspace_estimate(ix.len, ix.pk.bits));
     ix.arena = &arena;
@@ -204,9 +204,9 @@ int b200sa_extend(b200sa_index *idx, const uint8_t *codes, uint32_t flags) {
     if (flags & B200SA_TEXT_ON_DEVICE) {
         ix.text_ptr = codes;
     } else {
-        ix.text.alloc((size_t)ix.n + 1, st);
-        if (ix.n) CUDA_CHECK(cudaMemcpyAsync(ix.text.ptr, codes, ix.n, cudaMemcpyHostToDevice, st));
-        ix.text_ptr = ix.text.ptr;
+        u8 *stage = (u8 *)arena.side_alloc((size_t)ix.n + 1);
+        if (ix.n) CUDA_CHECK(cudaMemcpyAsync(stage, codes, ix.n, cudaMemcpyHostToDevice, st));
+        ix.text_ptr = stage;
     }
     DevBuf<int> d_err(1, st);
     CUDA_CHECK(cudaMemsetAsync(d_err.ptr, 0, 4, st));

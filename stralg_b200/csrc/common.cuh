@@ -130,15 +130,36 @@ struct Arena {
     void release_to(const Mark &m) {
         for (int i = 0; i < nchunks; ++i) chunks[i].top = i < m.n ? m.tops[i] : 0;
     }
+    // grow-only side buffer (staging of a host text): kept out of the stream-ordered pool so that
+    // the pool only ever sees the same sequence of output allocations, build after build
+    u8 *side = nullptr;
+    size_t side_cap = 0;
+    void *side_alloc(size_t bytes) {
+        if (bytes > side_cap) {
+            if (side) {
+                cudaDeviceSynchronize();
+                cudaFree(side);
+                side = nullptr;
+                side_cap = 0;
+            }
+            size_t cap = (bytes + ((size_t)1 << 20)) & ~(((size_t)1 << 20) - 1);
+            CUDA_CHECK(cudaMalloc((void **)&side, cap));
+            side_cap = cap;
+        }
+        return side;
+    }
     void release_all() {
-        if (nchunks) cudaDeviceSynchronize();
+        if (nchunks || side) cudaDeviceSynchronize();
         for (int i = 0; i < nchunks; ++i) cudaFree(chunks[i].base);
         nchunks = 0;
+        if (side) cudaFree(side);
+        side = nullptr;
+        side_cap = 0;
     }
     size_t reserved() const {
         size_t t = 0;
         for (int i = 0; i < nchunks; ++i) t += chunks[i].cap;
-        return t;
+        return t + side_cap;
     }
 };
 

@@ -48,30 +48,38 @@ __global__ void __launch_bounds__(256) pack_kernel(const u8 *__restrict__ text, 
         u64 t0 = w * CPW;
         u64 word = 0;
         if (t0 < n) {
-            const bool aligned = ((((uintptr_t)text) & 15) == 0);
+            // the CPW text bytes of this word, fetched with the widest loads (one 256-bit load for DNA)
+            __align__(32) u8 b[CPW];
+            const u8 *src = text + t0;
+            if (t0 + CPW <= n && ((((uintptr_t)src) & (CPW < 32 ? CPW - 1 : 31)) == 0)) {
+                if (CPW >= 32) {
 #pragma unroll
-            for (int c0 = 0; c0 < CPW; c0 += 16) {
-                __align__(16) u8 b[16];
-                u64 t = t0 + c0;
-                constexpr int CH = CPW < 16 ? CPW : 16;
-                if (CH == 16 && aligned && t + 16 <= n) {
-                    uint4 v = ld_stream_u128(text + t);
-                    *(uint4 *)b = v;
-                } else {
-#pragma unroll
-                    for (int q = 0; q < CH; ++q) b[q] = (t + q < n) ? text[t + q] : (u8)1;
-                }
-#pragma unroll
-                for (int q = 0; q < CH; ++q) {
-                    u32 code = b[q];
-                    u32 sym = 0;
-                    if (t + q < n) {
-                        if (code == 0 || code >= sigma) bad = true;
-                        sym = (code - 1) & ((1u << BITS) - 1);
-                        if (BITS > 2) atomicAdd(&sh_counts[code & 255], 1u);
+                    for (int h = 0; h < CPW / 32; ++h) {
+                        u64 x0, x1, x2, x3;
+                        asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                                     : "=l"(x0), "=l"(x1), "=l"(x2), "=l"(x3) : "l"(src + 32 * h));
+                        u64 *bw = (u64 *)(b + 32 * h);
+                        bw[0] = x0; bw[1] = x1; bw[2] = x2; bw[3] = x3;
                     }
-                    word |= (u64)sym << (64 - BITS - (c0 + q) * BITS);
+                } else if (CPW == 16) {
+                    *(uint4 *)b = ld_stream_u128(src);
+                } else {
+                    *(u64 *)b = ld_stream_u64((const u64 *)src);
                 }
+            } else {
+#pragma unroll
+                for (int q = 0; q < CPW; ++q) b[q] = (t0 + q < n) ? src[q] : (u8)1;
+            }
+#pragma unroll
+            for (int q = 0; q < CPW; ++q) {
+                u32 code = b[q];
+                u32 sym = 0;
+                if (t0 + q < n) {
+                    if (code == 0 || code >= sigma) bad = true;
+                    sym = (code - 1) & ((1u << BITS) - 1);
+                    if (BITS > 2) atomicAdd(&sh_counts[code & 255], 1u);
+                }
+                word |= (u64)sym << (64 - BITS - q * BITS);
             }
             if (BITS <= 2) {
                 // symbol counts straight from the packed word (padding symbols are 0)
@@ -245,9 +253,24 @@ __device__ __forceinline__ u32 lazy_rank_of(const LazyRank &lr, u32 t) {
         }
     } else {
         // the bucket is known from the leading bits; inside it the keys come from the text
-        const u64 bid = key >> (kb - lr.BB);
+        const int rbits = kb - lr.BB;
+        const u64 bid = key >> rbits;
         lo = lr.bstart[bid];
         hi = lr.bstart[bid + 1];
+        if (hi - lo > 96u && rbits > 0 && rbits <= 32) {
+            // the keys of a bucket spread over its remaining bits: two probes around the expected
+            // position narrow the search to one or two cache lines of the suffix array
+            const u64 rem = key & ((1ull << rbits) - 1ull);
+            const u32 g = lo + (u32)((rem * (u64)(hi - lo)) >> rbits);
+            const u32 p1 = g > lo + 32u ? g - 32u : lo;
+            if ((window_at(lr.packed, lr.sa0[p1], lr.bits) >> (64 - kb)) < key) lo = p1 + 1;
+            else hi = p1;
+            const u32 p2 = g + 32u;
+            if (p2 >= lo && p2 < hi) {
+                if ((window_at(lr.packed, lr.sa0[p2], lr.bits) >> (64 - kb)) < key) lo = p2 + 1;
+                else hi = p2;
+            }
+        }
         while (lo < hi) {
             u32 mid = lo + (hi - lo) / 2;
             u64 km = window_at(lr.packed, lr.sa0[mid], lr.bits) >> (64 - kb);

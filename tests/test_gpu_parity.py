@@ -241,3 +241,21 @@ def test_device_resident_text_and_synth(engine, oracle):
     assert np.array_equal(dL.cpu().numpy().view(np.uint32), L) and np.array_equal(dR.cpu().numpy().view(np.uint32), R)
     assert ((R > L).sum()) >= 850  # ~90 % of the reads are sampled from the text
     idx.close()
+    # the counting variant of the search kernel (b200sa_search_traffic) returns the same intervals and
+    # plausible operation counts, with and without the unique-interval shortcut
+    for textcmp in (False, True):
+        idx = engine.SuffixArrayIndex.build(text[:n], 5, textcmp=textcmp)
+        counts = (C.c_uint64 * 4)()
+        dL.zero_()
+        dR.zero_()
+        rc = lib.b200sa_search_traffic(idx._h, C.c_void_p(reads.data_ptr()), None, 30, 1000, C.c_void_p(dL.data_ptr()),
+                                       C.c_void_p(dR.data_ptr()), counts, None)
+        assert rc == 0
+        assert np.array_equal(dL.cpu().numpy().view(np.uint32), L) and np.array_equal(dR.cpu().numpy().view(np.uint32), R)
+        blocks, pwords, twords, sa_isa = [int(x) for x in counts]
+        assert 1000 * 5 <= blocks <= 1000 * 60 and 1000 <= pwords <= 1000 * 5
+        if textcmp:
+            assert twords > 0 and sa_isa > 0 and blocks < 1000 * 40
+        else:
+            assert twords == 0 and sa_isa == 0
+        idx.close()
