@@ -273,6 +273,9 @@ def run_reference_arm(args, rank):
 # GPU arm
 # =================================================================================================
 def gpu_arm(args, rank, local_rank, world):
+    # stdout carries the ONE JSON line only: libraries (NCCL's version banner) write to fd 1 too
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import stralg_b200
     lib = stralg_b200.load()
@@ -438,7 +441,8 @@ def gpu_arm(args, rank, local_rank, world):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
 
 
 def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n, dist, rank, world, peak, peak_src,
@@ -451,7 +455,8 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
     lib.b200sa_release_workspace(local_rank)
     # contiguous shards of the read set, one per rank; one NCCL gather of (L, R) to rank 0 per step
     from stralg_b200.shard import ShardedSearch
-    ss = ShardedSearch(total_reads, m, dev, dist, chunks=args.gather_chunks if dist is not None else 1)
+    ss = ShardedSearch(total_reads, m, dev, dist, chunks=args.gather_chunks if dist is not None else 1,
+                       transport=args.transport)
     shard = ss.count
 
     def gen_reads(count, seed):
@@ -496,6 +501,25 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
     ms_step = ms_total / args.steps
     launches = lib.b200sa_launch_count() - launches0
     value = total_reads / (ms_step / 1e3)
+
+    # N > 1: rank 0 re-creates every rank's reads (same seeded generator), searches them on its own index and
+    # compares with what the step delivered -- the whole sharded path checked bit for bit, outside the timed region
+    verified = None
+    if dist is not None:
+        if rank == 0:
+            Lall, Rall = ss.result()
+            verified = True
+            from stralg_b200.shard import shard_bounds
+            for g in range(world):
+                glo, ghi = shard_bounds(total_reads, world, g)
+                rg = gen_reads(ghi - glo, SEED + 1 + g * 7919)
+                Lg = torch.empty(ghi - glo, dtype=torch.int32, device=dev)
+                Rg = torch.empty(ghi - glo, dtype=torch.int32, device=dev)
+                idx.search_device(rg, None, m, ghi - glo, Lg, Rg, stream)
+                torch.cuda.synchronize()
+                verified = verified and bool(torch.equal(Lg, Lall[glo:ghi])) and bool(torch.equal(Rg, Rall[glo:ghi]))
+                del rg, Lg, Rg
+        dist.barrier()
 
     # steps actually executed per read -> algorithmic bytes (m + 2*steps*32 + 8)
     Lt, Rt = ss.local_result()
@@ -576,10 +600,13 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
         "config": {"workload": "search: batched FM exact search, replicated 3 Gbp index (BASELINE configs[3])"
                    if n == N_FULL else "search: batched FM exact search, replicated index",
                    "n": n, "sigma": 5, "reads": total_reads, "read_len": m, "reads_per_gpu": shard,
-                   "miss_fraction": MISS_PER_1024 / 1024.0, "gather": f"NCCL gather of (L,R) to rank 0, {ss.chunks} pieces per shard overlapped with the search" if world > 1
+                   "miss_fraction": MISS_PER_1024 / 1024.0, "gather": ("search kernels store (L,R) into rank 0's HBM through NVLink peer memory (symmetric memory) + one "
+                              "device-side barrier" if ss.transport == "p2p" else
+                              f"NCCL gather of (L,R) to rank 0, {ss.chunks} piece(s) per shard") if world > 1
                    else "none (1 GPU)", "l2": "index (1.5 GB) and reads larger than L2"},
         "clocks": sampler.summary(tw0, tw1), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "kernel_only_patterns_per_s_per_gpu": shard / (kernel_ms / 1e3),
+        "delivered_equals_single_gpu_search": verified,
     }
     if not args.no_cpu and rank == 0 and world == 1:
         ns = min(args.cpu_sample, n)
@@ -611,8 +638,10 @@ def main():
     ap.add_argument("--n", type=int, default=env_int("B200SA_BENCH_N", N_FULL))
     ap.add_argument("--reads", type=int, default=env_int("B200SA_BENCH_READS", READS_FULL))
     ap.add_argument("--e2e-reads", type=int, default=20_000_000)
-    ap.add_argument("--gather-chunks", type=int, default=4,
-                    help="N > 1: pieces per shard; the gather of a piece overlaps the search of the next")
+    ap.add_argument("--gather-chunks", type=int, default=1,
+                    help="N > 1, gather transport: pieces per shard whose gathers are issued asynchronously")
+    ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "gather"],
+                    help="N > 1: how (L, R) reach rank 0: kernel stores through NVLink peer memory, or one NCCL gather")
     ap.add_argument("--cpu-sample", type=int, default=CPU_SAMPLE)
     ap.add_argument("--cpu-reads", type=int, default=1_000_000)
     ap.add_argument("--no-cpu", action="store_true")
