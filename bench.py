@@ -313,9 +313,10 @@ def gpu_arm(args, rank, local_rank, world):
     assert lib.b200sa_synth_codes(C.c_void_p(text.data_ptr()), n, 4, SEED, local_rank, C.c_void_p(stream)) == 0
     torch.cuda.synchronize()
 
-    def build(profile=False, drop_sa=False, src=None, textcmp=False):
+    def build(profile=False, drop_sa=False, src=None, textcmp=False, ktable=False):
         return stralg_b200.SuffixArrayIndex.build(text[:n] if src is None else src, 5, occ=True, profile=profile,
-                                                  drop_sa=drop_sa, textcmp=textcmp, device=local_rank, stream=stream)
+                                                  drop_sa=drop_sa, textcmp=textcmp, ktable=ktable, device=local_rank,
+                                                  stream=stream)
 
     sampler = ClockSampler(local_rank)
     out = {}
@@ -451,7 +452,7 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
     total_reads = args.reads
     m = READ_LEN
     # search index: C + sampled O, plus SA / ISA / packed text for the unique-interval shortcut
-    idx = build(textcmp=True)
+    idx = build(textcmp=True, ktable=True)
     lib.b200sa_release_workspace(local_rank)
     # contiguous shards of the read set, one per rank; one NCCL gather of (L, R) to rank 0 per step
     from stralg_b200.shard import ShardedSearch

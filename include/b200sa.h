@@ -49,6 +49,11 @@ enum b200sa_error {
                                         (R - L == 1) by comparing the remaining pattern symbols with the
                                         text directly instead of one O lookup per symbol; results are
                                         identical to the plain recurrence (needs OCC, keeps SA)        */
+#define B200SA_BUILD_KTABLE 0x20u    /* DNA index (sigma <= 5): table of the (L, R) interval the recurrence of
+                                        bwt.c:185-195 reaches on every k-mer (k = 12, or less for short
+                                        texts); exact search starts from the entry of the pattern's last k
+                                        symbols instead of running those k steps; results are identical
+                                        (needs OCC)                                                      */
 #define B200SA_TEXT_ON_DEVICE 0x100u /* `codes` is a device pointer (borrowed during the call)  */
 #define B200SA_PROFILE 0x200u        /* record per-stage device times (b200sa_profile)          */
 #define B200SA_DROP_SA 0x400u        /* release the suffix array after the tables are built     */

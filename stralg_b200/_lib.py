@@ -21,6 +21,7 @@ BUILD_LCP = 0x2
 BUILD_BWT = 0x4
 BUILD_OCC = 0x8
 BUILD_TEXTCMP = 0x10
+BUILD_KTABLE = 0x20
 TEXT_ON_DEVICE = 0x100
 PROFILE = 0x200
 DROP_SA = 0x400

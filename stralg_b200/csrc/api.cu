@@ -145,6 +145,7 @@ __attribute__((visibility("hidden"))) static int build_into(b200sa_index *h, con
     }
     ix.packed = nullptr;
     ix.arena = nullptr;
+    if ((flags & B200SA_BUILD_KTABLE) && (flags & B200SA_BUILD_OCC)) build_ktable(ix);
     if ((flags & B200SA_DROP_SA) && !(flags & B200SA_BUILD_TEXTCMP)) ix.sa.release();
     CUDA_CHECK(cudaStreamSynchronize(st));
     if (flags & B200SA_PROFILE) {

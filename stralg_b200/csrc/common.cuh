@@ -94,7 +94,7 @@ struct Arena {
     void reserve_first(size_t bytes) {
         bytes = (bytes + ((size_t)64 << 20)) & ~(((size_t)1 << 20) - 1);
         if (nchunks > 0 && chunks[0].cap >= bytes) return;
-        release_all();
+        release_chunks();  // (the side buffer may already hold the staged text of this build)
         u8 *p = nullptr;
         CUDA_CHECK(cudaMalloc((void **)&p, bytes));
         chunks[0] = Chunk{p, bytes, 0};
@@ -148,10 +148,14 @@ struct Arena {
         }
         return side;
     }
-    void release_all() {
-        if (nchunks || side) cudaDeviceSynchronize();
+    void release_chunks() {
+        if (nchunks) cudaDeviceSynchronize();
         for (int i = 0; i < nchunks; ++i) cudaFree(chunks[i].base);
         nchunks = 0;
+    }
+    void release_all() {
+        release_chunks();
+        if (side) cudaDeviceSynchronize();
         if (side) cudaFree(side);
         side = nullptr;
         side_cap = 0;

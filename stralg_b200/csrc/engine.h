@@ -43,6 +43,8 @@ struct DeviceIndex {
     Arena *arena = nullptr; // per-device build workspace (valid during the build only)
     DevBuf<u32> sa, isa, lcp;
     DevBuf<u64> text_packed;  // kept copy of the packed text (B200SA_BUILD_TEXTCMP: search shortcut)
+    DevBuf<uint2> ktable;     // (L, R) after the recurrence on every k-mer (B200SA_BUILD_KTABLE)
+    int ktable_k = 0;
     DevBuf<u8> bwt;
     DevBuf<u32> c_table;    // sigma entries (device)
     u32 c_host[256];
@@ -69,6 +71,7 @@ void build_bwt_tables(DeviceIndex &ix, bool keep_bwt);
 void occ_probe(const DeviceIndex &ix, const u8 *d_a, const u32 *d_i, u64 count, u32 *d_out);
 void occ_dense(const DeviceIndex &ix, u32 *d_out);  // (len+1)*sigma entries, reference layout
 // fm_search.cu
+void build_ktable(DeviceIndex &ix);  // fills ix.ktable (DNA layout only)
 void fm_search(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fixed_len, u64 npat, u32 *d_L,
                u32 *d_R, cudaStream_t st, unsigned long long *d_stats = nullptr);
 u64 fm_locate_count(const DeviceIndex &ix, const u32 *d_L, const u32 *d_R, u64 npat, u64 *d_pos_off,

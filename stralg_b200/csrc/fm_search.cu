@@ -118,8 +118,36 @@ struct TextCmp {
 
 // STATS: count the memory operations of the batch (b200sa_search_traffic, a measurement aid):
 // stats[0] 32-byte O-block loads, [1] 8-byte pattern words, [2] 8-byte text words, [3] 4-byte SA/ISA loads.
+// k-mer seed table (B200SA_BUILD_KTABLE): tab[x] = the (L, R) the recurrence reaches on the k-mer
+// whose symbols, in the order the recurrence consumes them (last pattern symbol first), are the
+// base-4 digits of x, most significant first; an entry with L >= R is the interval at the step
+// that emptied it, i.e. the final answer of every pattern ending in that k-mer.
+struct KTable {
+    const uint2 *tab;
+    int k;
+};
+
+__global__ void __launch_bounds__(256) ktable_build_kernel(OccView ov, CTable5 c5, u32 len, int k, u32 entries,
+                                                           uint2 *__restrict__ tab) {
+    u32 x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= entries) return;
+    u32 L = 0, R = len;
+    for (int j = 0; j < k && L < R; ++j) {
+        const u32 a = ((x >> (2 * (k - 1 - j))) & 3u) + 1u;
+        if (a >= ov.sigma) {  // a letter the text does not have (the reference asserts, bwt.c:189-190)
+            L = 1;
+            R = 0;
+            break;
+        }
+        const u32 oL = occ_dna(ov, a, L), oR = occ_dna(ov, a, R);
+        L = c5.c[a] + oL;
+        R = c5.c[a] + oR;
+    }
+    tab[x] = make_uint2(L, R);
+}
+
 template <int LM, bool SC, bool STATS>
-__global__ void __launch_bounds__(256) fm_search_dna_kernel(OccView ov, CTable5 c5, TextCmp tc, u32 len,
+__global__ void __launch_bounds__(256) fm_search_dna_kernel(OccView ov, CTable5 c5, TextCmp tc, KTable kt, u32 len,
                                                             const u8 *__restrict__ pat,
                                                             const u64 *__restrict__ off, u32 fixed_len, u64 npat,
                                                             u32 *__restrict__ outL, u32 *__restrict__ outR,
@@ -136,7 +164,31 @@ __global__ void __launch_bounds__(256) fm_search_dna_kernel(OccView ov, CTable5 
     }
     u64 word = 0;
     u64 word_addr = ~0ull;
-    for (int64_t i = (int64_t)m - 1; i >= 0 && L < R; --i) {
+    int64_t i = (int64_t)m - 1;
+    if (kt.tab && m >= (u64)kt.k && L < R) {
+        // the last k symbols select the interval the first k steps would reach
+        u32 x = 0;
+        bool valid = true;
+        for (int j = 0; j < kt.k; ++j) {
+            u64 addr = begin + (u64)i - (u64)j;
+            if ((addr & ~7ull) != word_addr) {
+                word_addr = addr & ~7ull;
+                word = *(const u64 *)(pat + word_addr);
+                if (STATS) ++n_pw;
+            }
+            const u32 a = (u32)(word >> (8 * (addr & 7))) & 0xffu;
+            valid = valid && (a - 1u <= 3u);
+            x = (x << 2) | ((a - 1u) & 3u);
+        }
+        if (valid) {  // a byte outside 1..4 takes the stepwise path (it answers (1, 0) where it is reached)
+            const uint2 lr = kt.tab[x];
+            if (STATS) n_sa += 2;  // one 8-byte table entry
+            L = lr.x;
+            R = lr.y;
+            i -= kt.k;
+        }
+    }
+    for (; i >= 0 && L < R; --i) {
         if (SC && R - L == 1) {
             // One candidate suffix s = SA[L] is left.  The recurrence would now consume the remaining
             // symbols pattern[i], pattern[i-1], ... one O lookup each, moving to ISA[s-1], ISA[s-2], ...
@@ -232,12 +284,14 @@ void fm_search(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fix
         static const int lm = getenv("B200SA_SEARCH_LM") ? atoi(getenv("B200SA_SEARCH_LM")) : 3;
         static const bool no_sc = getenv("B200SA_SEARCH_NO_TEXTCMP") != nullptr;
         TextCmp tc{ix.sa.ptr, ix.isa.ptr, ix.text_packed.ptr};
+        static const bool no_kt = getenv("B200SA_SEARCH_NO_KTABLE") != nullptr;
+        KTable kt{no_kt ? nullptr : ix.ktable.ptr, ix.ktable_k};
         const bool sc = tc.sa && tc.isa && tc.packed && ix.pk.bits == 2 && !no_sc;
-#define LAUNCH_DNA(LM_, SC_) fm_search_dna_kernel<LM_, SC_, false><<<blocks, 256, 0, st>>>(ov, c5, tc, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R, nullptr)
+#define LAUNCH_DNA(LM_, SC_) fm_search_dna_kernel<LM_, SC_, false><<<blocks, 256, 0, st>>>(ov, c5, tc, kt, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R, nullptr)
         if (d_stats) {
             // counting variant of the default configuration
-            if (sc) fm_search_dna_kernel<3, true, true><<<blocks, 256, 0, st>>>(ov, c5, tc, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R, d_stats);
-            else fm_search_dna_kernel<3, false, true><<<blocks, 256, 0, st>>>(ov, c5, tc, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R, d_stats);
+            if (sc) fm_search_dna_kernel<3, true, true><<<blocks, 256, 0, st>>>(ov, c5, tc, kt, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R, d_stats);
+            else fm_search_dna_kernel<3, false, true><<<blocks, 256, 0, st>>>(ov, c5, tc, kt, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R, d_stats);
         } else if (sc) {
             if (lm == 0) LAUNCH_DNA(0, true); else LAUNCH_DNA(3, true);
         } else {
@@ -255,6 +309,24 @@ void fm_search(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fix
     else
         fm_search_kernel<2><<<blocks, 256, 0, st>>>(ov, c5, ix.c_table.ptr, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R);
     KERNEL_CHECK();
+}
+
+// k = 12 (16.7 M entries, 128 MB) for genome-scale texts, smaller while 4^k would exceed the text
+void build_ktable(DeviceIndex &ix) {
+    if (ix.occ_layout != OCC_DNA32) return;
+    int k = 12;
+    while (k > 0 && (1ull << (2 * k)) > (u64)ix.len) --k;
+    if (k < 4) return;
+    const u32 entries = 1u << (2 * k);
+    ix.ktable.alloc(entries, ix.stream);
+    ix.ktable_k = k;
+    OccView ov = occ_view(ix);
+    CTable5 c5;
+    for (int i = 0; i < 8; ++i) c5.c[i] = ix.c_host[i];
+    int t = ix.timer.begin("ktable", (double)entries * 8.0);
+    ktable_build_kernel<<<div_up_u(entries, 256), 256, 0, ix.stream>>>(ov, c5, ix.len, k, entries, ix.ktable.ptr);
+    KERNEL_CHECK();
+    ix.timer.end(t);
 }
 
 // ---- locate -----------------------------------------------------------------------------------

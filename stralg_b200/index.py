@@ -14,7 +14,7 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import (BUILD_BWT, BUILD_ISA, BUILD_LCP, BUILD_OCC, BUILD_TEXTCMP, DROP_SA, PROFILE, TEXT_ON_DEVICE, B200saError,
+from ._lib import (BUILD_BWT, BUILD_ISA, BUILD_KTABLE, BUILD_LCP, BUILD_OCC, BUILD_TEXTCMP, DROP_SA, PROFILE, TEXT_ON_DEVICE, B200saError,
                    Stats, check)
 
 
@@ -74,13 +74,14 @@ class SuffixArrayIndex:
 
     # ---- construction ---------------------------------------------------------------------
     @classmethod
-    def build(cls, codes, sigma: int, *, isa=False, lcp=False, bwt=False, occ=True, textcmp=False, drop_sa=False,
+    def build(cls, codes, sigma: int, *, isa=False, lcp=False, bwt=False, occ=True, textcmp=False, ktable=False,
+              drop_sa=False,
               profile=False, device: int = 0, stream: int = 0) -> "SuffixArrayIndex":
         """codes: remapped text WITHOUT the sentinel -- numpy uint8 array / bytes (host), or a
         CUDA uint8 torch tensor (device-resident, borrowed during the call)."""
         lib = _lib.load()
         flags = (BUILD_ISA if isa else 0) | (BUILD_LCP if lcp else 0) | (BUILD_BWT if bwt else 0) | \
-                (BUILD_OCC if occ else 0) | (BUILD_TEXTCMP if textcmp else 0) | (DROP_SA if drop_sa else 0) | (PROFILE if profile else 0)
+                (BUILD_OCC if occ else 0) | (BUILD_TEXTCMP if textcmp else 0) | (BUILD_KTABLE if ktable else 0) | (DROP_SA if drop_sa else 0) | (PROFILE if profile else 0)
         keep = None
         if _is_torch_tensor(codes):
             assert codes.is_cuda and codes.dtype.itemsize == 1 and codes.is_contiguous()

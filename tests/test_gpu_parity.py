@@ -145,16 +145,17 @@ def make_patterns(rng, codes, nsym, npat, mmin, mmax):
     return pat, off
 
 
-@pytest.mark.parametrize("textcmp", [False, True], ids=["plain", "textcmp"])
+@pytest.mark.parametrize("textcmp,ktable", [(False, False), (True, False), (False, True), (True, True)],
+                         ids=["plain", "textcmp", "ktable", "textcmp_ktable"])
 @pytest.mark.parametrize("n,nsym,mmax", [(1 << 20, 4, 24), (200000, 4, 40), (50000, 2, 30), (80000, 20, 6),
                                          (60000, 255, 4), (3000, 1, 50), (40000, 3, 200), (5000, 4, 300)])
-def test_batched_search_and_locate(engine, oracle, n, nsym, mmax, textcmp):
+def test_batched_search_and_locate(engine, oracle, n, nsym, mmax, textcmp, ktable):
     """(L, R) per pattern and the position sets against the restatement of bwt.c:164-217;
     config 1 of BASELINE.json is the first row (1 Mi random ACGT, 10 k patterns)."""
     rng = np.random.default_rng(n + nsym)
     codes = oracle.random_codes(n, nsym, seed=n)
     sigma = nsym + 1
-    idx = engine.SuffixArrayIndex.build(codes[:-1], sigma, textcmp=textcmp)
+    idx = engine.SuffixArrayIndex.build(codes[:-1], sigma, textcmp=textcmp, ktable=ktable)
     sa = idx.sa()
     bwt = oracle.bwt(codes, sa)
     ck = oracle.o_checkpoints(bwt, sigma, 64)
