@@ -132,6 +132,30 @@ void dealloc_bwt_exact_match_iter(struct bwt_exact_match_iter *iter);
 void bwt_exact_match_batch(struct bwt_table *bwt_table, const uint8_t *remapped_patterns,
                            const uint64_t *offsets, uint64_t npatterns, uint32_t *L, uint32_t *R);
 
+/* ---- index files: the reference's own on-disk layouts, byte for byte ----------
+ * Raw host-endian dumps without header (suffix_array.c:238-267, remap.c:168-201, bwt.c:425-503,
+ * serialise.c:7-49, string_utils.c:48-82).  A file written by either library is read by the other.
+ * Tables whose dense O the reference itself cannot size (u32 overflow, bwt.c:430) cannot be
+ * written in this format: write_bwt_table aborts with a message.  What is read back is host
+ * memory; the device index is rebuilt from the string on first use (same arrays by uniqueness). */
+void write_suffix_array(FILE *f, const struct suffix_array *sa);                      /* suffix_array.h:109 */
+void write_suffix_array_fname(const char *fname, const struct suffix_array *sa);      /* :113 */
+struct suffix_array *read_suffix_array(FILE *f, uint8_t *string);                     /* :118 */
+struct suffix_array *read_suffix_array_fname(const char *fname, uint8_t *string);     /* :123 */
+void write_remap_table(FILE *f, const struct remap_table *table);                     /* remap.h:89 */
+void write_remap_table_fname(const char *fname, const struct remap_table *table);     /* :93 */
+struct remap_table *read_remap_table(FILE *f);                                        /* :98 */
+struct remap_table *read_remap_table_fname(const char *fname);                        /* :102 */
+void write_bwt_table(FILE *f, const struct bwt_table *bwt_table);                     /* bwt.h:337 */
+void write_bwt_table_fname(const char *fname, const struct bwt_table *bwt_table);     /* :341 */
+struct bwt_table *read_bwt_table(FILE *f, struct suffix_array *sa, struct remap_table *remap_table);  /* :346 */
+struct bwt_table *read_bwt_table_fname(const char *fname, struct suffix_array *sa,
+                                       struct remap_table *remap_table);              /* :351 */
+void write_complete_bwt_info(FILE *f, const struct bwt_table *bwt_table);             /* serialise.h:23 */
+void write_complete_bwt_info_fname(const char *fname, const struct bwt_table *bwt_table);  /* :24 */
+struct bwt_table *read_complete_bwt_info(FILE *f);                                    /* :32 */
+struct bwt_table *read_complete_bwt_info_fname(const char *fname);                    /* :33 */
+
 #ifdef __cplusplus
 }
 #endif

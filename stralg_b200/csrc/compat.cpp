@@ -7,7 +7,7 @@
 // to its device-resident index so that later calls (compute_lcp, init_bwt_table, the exact
 // iterator) reuse the suffix array already in HBM.  Host-only pieces: the alphabet remap
 // (remap.c), the SA binary searches (suffix_array.c:90-233, kept on the host by design, SURVEY
-// 8a row a16) and the comparison helpers.
+// 8a row a16), the comparison helpers and the index-file readers / writers.
 #include "../../include/b200sa.h"
 #define STRALG_COMPAT_NO_MACROS
 #include "../../include/stralg_compat.h"
@@ -424,5 +424,147 @@ bool next_bwt_exact_match_iter(struct bwt_exact_match_iter *iter, struct bwt_exa
     return true;
 }
 void dealloc_bwt_exact_match_iter(struct bwt_exact_match_iter *) {}
+
+// ------------------------------------------------------------------------------------------------
+// Index files: the reference's raw layouts (no header, host endianness).  Host-side I/O only; a
+// structure read from a file has no device index yet -- index_of() rebuilds it from the string
+// the first time the GPU is needed, which yields the same arrays by uniqueness.
+// ------------------------------------------------------------------------------------------------
+static void must(bool ok, const char *what) {
+    if (!ok) {
+        fprintf(stderr, "stralg_b200: %s\n", what);
+        abort();
+    }
+}
+static FILE *open_or_die(const char *fname, const char *mode) {
+    FILE *f = fopen(fname, mode);
+    if (!f) {
+        fprintf(stderr, "stralg_b200: cannot open %s\n", fname);
+        abort();
+    }
+    return f;
+}
+
+void write_suffix_array(FILE *f, const struct suffix_array *sa) {  // suffix_array.c:238-241: length u32 entries
+    must(fwrite(sa->array, sizeof(uint32_t), sa->length, f) == sa->length, "write_suffix_array: short write");
+}
+void write_suffix_array_fname(const char *fname, const struct suffix_array *sa) {
+    FILE *f = open_or_die(fname, "wb");
+    write_suffix_array(f, sa);
+    fclose(f);
+}
+struct suffix_array *read_suffix_array(FILE *f, uint8_t *string) {  // suffix_array.c:250-257
+    struct suffix_array *sa = (struct suffix_array *)malloc(sizeof *sa);
+    sa->string = string;
+    sa->length = (uint32_t)strlen((const char *)string) + 1;
+    sa->array = (uint32_t *)malloc((size_t)sa->length * sizeof(uint32_t));
+    sa->inverse = nullptr;
+    sa->lcp = nullptr;
+    must(fread(sa->array, sizeof(uint32_t), sa->length, f) == sa->length, "read_suffix_array: short read");
+    return sa;
+}
+struct suffix_array *read_suffix_array_fname(const char *fname, uint8_t *string) {
+    FILE *f = open_or_die(fname, "rb");
+    struct suffix_array *sa = read_suffix_array(f, string);
+    fclose(f);
+    return sa;
+}
+
+void write_remap_table(FILE *f, const struct remap_table *t) {  // remap.c:168-173: the raw struct
+    must(fwrite(t, sizeof(struct remap_table), 1, f) == 1, "write_remap_table: short write");
+}
+void write_remap_table_fname(const char *fname, const struct remap_table *t) {
+    FILE *f = open_or_die(fname, "wb");
+    write_remap_table(f, t);
+    fclose(f);
+}
+struct remap_table *read_remap_table(FILE *f) {
+    struct remap_table *t = (struct remap_table *)malloc(sizeof *t);
+    must(fread(t, sizeof(struct remap_table), 1, f) == 1, "read_remap_table: short read");
+    return t;
+}
+struct remap_table *read_remap_table_fname(const char *fname) {
+    FILE *f = open_or_die(fname, "rb");
+    struct remap_table *t = read_remap_table(f);
+    fclose(f);
+    return t;
+}
+
+// bwt.c:425-440: C[sigma], O[sigma * (length + 1)], bool has_ro, RO[...] when present
+void write_bwt_table(FILE *f, const struct bwt_table *tbl) {
+    const uint32_t sigma = tbl->remap_table->alphabet_size;
+    const uint64_t o_entries = (uint64_t)sigma * ((uint64_t)tbl->sa->length + 1);
+    must(tbl->o_table != nullptr && o_entries <= 0xFFFFFFFFull,
+         "write_bwt_table: the dense O table of this text does not fit the reference's format (bwt.c:430)");
+    must(fwrite(tbl->c_table, sizeof(uint32_t), sigma, f) == sigma, "write_bwt_table: short write");
+    must(fwrite(tbl->o_table, sizeof(uint32_t), o_entries, f) == o_entries, "write_bwt_table: short write");
+    const bool has_ro = tbl->ro_table != nullptr;
+    must(fwrite(&has_ro, sizeof(bool), 1, f) == 1, "write_bwt_table: short write");
+    if (has_ro) must(fwrite(tbl->ro_table, sizeof(uint32_t), o_entries, f) == o_entries, "write_bwt_table: short write");
+}
+void write_bwt_table_fname(const char *fname, const struct bwt_table *tbl) {
+    FILE *f = open_or_die(fname, "wb");
+    write_bwt_table(f, tbl);
+    fclose(f);
+}
+static void read_dense(FILE *f, uint32_t sigma, uint32_t length, uint32_t **table, uint32_t ***rows) {
+    const uint64_t o_entries = (uint64_t)sigma * ((uint64_t)length + 1);
+    *table = (uint32_t *)malloc(o_entries * sizeof(uint32_t));
+    must(fread(*table, sizeof(uint32_t), o_entries, f) == o_entries, "read_bwt_table: short read");
+    *rows = (uint32_t **)malloc(((size_t)length + 1) * sizeof(uint32_t *));
+    for (uint64_t i = 0; i <= length; ++i) (*rows)[i] = *table + i * sigma;
+}
+struct bwt_table *read_bwt_table(FILE *f, struct suffix_array *sa, struct remap_table *remap_table) {  // bwt.c:451-492
+    struct bwt_table *tbl = (struct bwt_table *)malloc(sizeof *tbl);
+    const uint32_t sigma = remap_table->alphabet_size;
+    tbl->remap_table = remap_table;
+    tbl->sa = sa;
+    tbl->c_table = (uint32_t *)malloc((size_t)sigma * sizeof(uint32_t));
+    must(fread(tbl->c_table, sizeof(uint32_t), sigma, f) == sigma, "read_bwt_table: short read");
+    read_dense(f, sigma, sa->length, &tbl->o_table, &tbl->o_indices);
+    tbl->ro_table = nullptr;
+    tbl->ro_indices = nullptr;
+    bool has_ro = false;
+    must(fread(&has_ro, sizeof(bool), 1, f) == 1, "read_bwt_table: short read");
+    if (has_ro) read_dense(f, sigma, sa->length, &tbl->ro_table, &tbl->ro_indices);
+    return tbl;
+}
+struct bwt_table *read_bwt_table_fname(const char *fname, struct suffix_array *sa, struct remap_table *remap_table) {
+    FILE *f = open_or_die(fname, "rb");
+    struct bwt_table *tbl = read_bwt_table(f, sa, remap_table);
+    fclose(f);
+    return tbl;
+}
+
+// serialise.c:7-18: [u32 n][n bytes of the remapped string] SA remap_table bwt_table
+void write_complete_bwt_info(FILE *f, const struct bwt_table *tbl) {
+    const struct suffix_array *sa = tbl->sa;
+    const uint32_t n = sa->length - 1;  // string_utils.c:48-52 (write_string_len)
+    must(fwrite(&n, sizeof n, 1, f) == 1 && fwrite(sa->string, 1, n, f) == n, "write_complete_bwt_info: short write");
+    write_suffix_array(f, sa);
+    write_remap_table(f, tbl->remap_table);
+    write_bwt_table(f, tbl);
+}
+void write_complete_bwt_info_fname(const char *fname, const struct bwt_table *tbl) {
+    FILE *f = open_or_die(fname, "wb");
+    write_complete_bwt_info(f, tbl);
+    fclose(f);
+}
+struct bwt_table *read_complete_bwt_info(FILE *f) {  // serialise.c:29-41; the table owns everything it read
+    uint32_t n = 0;
+    must(fread(&n, sizeof n, 1, f) == 1, "read_complete_bwt_info: short read");
+    uint8_t *str = (uint8_t *)malloc((size_t)n + 1);  // string_utils.c:73-82 (read_string_len)
+    must(fread(str, 1, n, f) == n, "read_complete_bwt_info: short read");
+    str[n] = 0;
+    struct suffix_array *sa = read_suffix_array(f, str);
+    struct remap_table *rt = read_remap_table(f);
+    return read_bwt_table(f, sa, rt);
+}
+struct bwt_table *read_complete_bwt_info_fname(const char *fname) {
+    FILE *f = open_or_die(fname, "rb");
+    struct bwt_table *tbl = read_complete_bwt_info(f);
+    fclose(f);
+    return tbl;
+}
 
 }  // extern "C"

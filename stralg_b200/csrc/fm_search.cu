@@ -11,6 +11,7 @@
 #include "engine.h"
 #include "occ.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace b200sa {
@@ -315,6 +316,7 @@ void fm_search(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fix
 void build_ktable(DeviceIndex &ix) {
     if (ix.occ_layout != OCC_DNA32) return;
     int k = 12;
+    if (const char *e = getenv("B200SA_KTABLE_K")) k = std::max(4, std::min(15, atoi(e)));
     while (k > 0 && (1ull << (2 * k)) > (u64)ix.len) --k;
     if (k < 4) return;
     const u32 entries = 1u << (2 * k);

@@ -48,6 +48,23 @@ def bind_extra(lib):
     lib.equivalent_bwt_tables.restype = C.c_bool
     lib.identical_suffix_arrays.argtypes = [C.POINTER(RefSuffixArray), C.POINTER(RefSuffixArray)]
     lib.identical_suffix_arrays.restype = C.c_bool
+    # index files (suffix_array.h:109-123, remap.h:89-102, bwt.h:337-351, serialise.h:23-33)
+    lib.write_suffix_array_fname.argtypes = [C.c_char_p, C.POINTER(RefSuffixArray)]
+    lib.write_suffix_array_fname.restype = None
+    lib.read_suffix_array_fname.argtypes = [C.c_char_p, u8p]
+    lib.read_suffix_array_fname.restype = C.POINTER(RefSuffixArray)
+    lib.write_remap_table_fname.argtypes = [C.c_char_p, C.POINTER(RefRemapTable)]
+    lib.write_remap_table_fname.restype = None
+    lib.read_remap_table_fname.argtypes = [C.c_char_p]
+    lib.read_remap_table_fname.restype = C.POINTER(RefRemapTable)
+    lib.write_bwt_table_fname.argtypes = [C.c_char_p, C.POINTER(RefBwtTable)]
+    lib.write_bwt_table_fname.restype = None
+    lib.read_bwt_table_fname.argtypes = [C.c_char_p, C.POINTER(RefSuffixArray), C.POINTER(RefRemapTable)]
+    lib.read_bwt_table_fname.restype = C.POINTER(RefBwtTable)
+    lib.write_complete_bwt_info_fname.argtypes = [C.c_char_p, C.POINTER(RefBwtTable)]
+    lib.write_complete_bwt_info_fname.restype = None
+    lib.read_complete_bwt_info_fname.argtypes = [C.c_char_p]
+    lib.read_complete_bwt_info_fname.restype = C.POINTER(RefBwtTable)
     return lib
 
 
@@ -153,6 +170,61 @@ def test_bound_searches_against_reference(compat, ref, oracle):
                 while lib.next_sa_match(C.byref(it), C.byref(m)):
                     acc.append(m.position)
             assert got == exp and len(got) >= 1
+
+
+def table_arrays(tbl):
+    tc = tbl.contents
+    sigma = tc.remap_table.contents.alphabet_size
+    n1 = tc.sa.contents.length
+    out = {"string": bytes(np.ctypeslib.as_array(tc.sa.contents.string, shape=(n1,))),
+           "sa": np.ctypeslib.as_array(tc.sa.contents.array, shape=(n1,)).copy(),
+           "remap": bytes(tc.remap_table.contents),
+           "c": np.ctypeslib.as_array(tc.c_table, shape=(sigma,)).copy(),
+           "o": np.ctypeslib.as_array(tc.o_table, shape=(n1 + 1, sigma)).copy(),
+           "ro": np.ctypeslib.as_array(tc.ro_table, shape=(n1 + 1, sigma)).copy() if tc.ro_table else None}
+    return out
+
+
+def same_tables(a, b):
+    return all((a[k] is None and b[k] is None) or np.array_equal(a[k], b[k]) if isinstance(a[k], np.ndarray) or a[k] is None
+               else a[k] == b[k] for k in a)
+
+
+def test_index_files_interoperate_with_the_reference(compat, ref, tmp_path):
+    """the on-disk layouts of serialise.c:7-49 / bwt.c:425-503 / suffix_array.c:238-267 /
+    remap.c:168-201 (tests/stralg/serialise_test.c round trip).  Host-only: the reference builds the tables,
+    each library writes them, the files are byte-identical and each library reads the other's file."""
+    if ref is None:
+        pytest.skip("oracle/_ref/libstralg_ref.so not present")
+    bind_extra(ref.lib)
+    for raw, rev in ((b"acgtadtadadfasdfing", False), (b"mississippi", True), (b"a", False)):
+        tbl = ref.lib.build_complete_table(C.cast(cbuf(raw), u8p), rev)
+        f_ref, f_our = str(tmp_path / "ref.bwt").encode(), str(tmp_path / "our.bwt").encode()
+        ref.lib.write_complete_bwt_info_fname(f_ref, tbl)
+        compat.write_complete_bwt_info_fname(f_our, tbl)  # same struct layouts: the shim writes the reference's table
+        assert open(f_ref, "rb").read() == open(f_our, "rb").read()
+        exp = table_arrays(tbl)
+        got_our = compat.read_complete_bwt_info_fname(f_ref)
+        got_ref = ref.lib.read_complete_bwt_info_fname(f_our)
+        assert same_tables(exp, table_arrays(got_our)) and same_tables(exp, table_arrays(got_ref))
+        assert bool(got_our.contents.ro_table) == rev
+        # the O(a, i) macro path of a table read from a file: o_indices[i][a]
+        n1, sigma = len(raw) + 1, exp["c"].shape[0]
+        for i in (0, n1 // 2, n1):
+            assert np.ctypeslib.as_array(got_our.contents.o_indices[i], shape=(sigma,)).tolist() == exp["o"][i].tolist()
+        # the piecewise files
+        fs, fr, fb = (str(tmp_path / n).encode() for n in ("x.sa", "x.remap", "x.tbl"))
+        compat.write_suffix_array_fname(fs, tbl.contents.sa)
+        compat.write_remap_table_fname(fr, tbl.contents.remap_table)
+        compat.write_bwt_table_fname(fb, tbl)
+        sa2 = ref.lib.read_suffix_array_fname(fs, tbl.contents.sa.contents.string)
+        rt2 = ref.lib.read_remap_table_fname(fr)
+        tb2 = ref.lib.read_bwt_table_fname(fb, sa2, rt2)
+        assert same_tables(exp, table_arrays(tb2))
+        sa3 = compat.read_suffix_array_fname(fs, tbl.contents.sa.contents.string)
+        rt3 = compat.read_remap_table_fname(fr)
+        tb3 = compat.read_bwt_table_fname(fb, sa3, rt3)
+        assert same_tables(exp, table_arrays(tb3))
 
 
 # ---- GPU -------------------------------------------------------------------------------------------
@@ -272,6 +344,37 @@ def test_match_test_c(compat, engine, golden):
         compat.dealloc_bwt_table(C.byref(tbl))
         for sa in sas:
             compat.free_suffix_array(sa)
+
+
+@pytest.mark.gpu
+def test_serialise_test_c(compat, engine, ref, tmp_path):
+    """tests/stralg/serialise_test.c:13-43: build_complete_table -> file -> read back -> equivalent tables, with the
+    tables built on the GPU; the table read from the file then serves the exact iterator (its device index is
+    rebuilt from the string on first use)."""
+    raw = b"acgtadtadadfasdfing"
+    tbl = compat.build_complete_table(C.cast(cbuf(raw), u8p), False)
+    fname = str(tmp_path / "index.bwttables").encode()
+    compat.write_complete_bwt_info_fname(fname, tbl)
+    back = compat.read_complete_bwt_info_fname(fname)
+    assert compat.equivalent_bwt_tables(tbl, back)
+    assert same_tables(table_arrays(tbl), table_arrays(back))
+    if ref is not None:
+        bind_extra(ref.lib)
+        theirs = ref.lib.build_complete_table(C.cast(cbuf(raw), u8p), False)
+        fref = str(tmp_path / "ref.bwttables").encode()
+        ref.lib.write_complete_bwt_info_fname(fref, theirs)
+        assert open(fref, "rb").read() == open(fname, "rb").read()  # a GPU-built index file == the reference's
+    for pat in (b"ad", b"tad", b"a", b"ing", b"gg"):
+        pm = C.create_string_buffer(len(pat) + 1)
+        assert compat.remap(C.cast(pm, u8p), C.cast(cbuf(pat), u8p), back.contents.remap_table)
+        bit, bm = RefExactIter(), RefExactMatch()
+        compat.init_bwt_exact_match_iter(C.byref(bit), back, C.cast(pm, u8p))
+        got = []
+        while compat.next_bwt_exact_match_iter(C.byref(bit), C.byref(bm)):
+            got.append(bm.pos)
+        assert sorted(got) == naive_positions(raw, pat)
+    compat.completely_free_bwt_table(back)
+    compat.completely_free_bwt_table(tbl)
 
 
 @pytest.mark.gpu
