@@ -689,6 +689,7 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
     uint2 *segtab = (uint2 *)X;                       // aliases X until the elements are scattered
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const u32 remmask = a.R >= 32 ? ~0u : ((1u << a.R) - 1u);
+    const u32 remsh = a.R > 0 ? 32u - (u32)a.R : 0u;  // R == 0: every key of a bucket is equal, rem == 0
 
     // thread 0: publish the CTA's next non-empty tile at or after `t` and start its prefetch
     auto advance = [&](u32 t) {
@@ -710,17 +711,31 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
     };
     if (tid == 0) advance(blockIdx.x);
 
+    // the counters of the first tile (later tiles: zeroed again right after their last use)
+    for (u32 i = tid; i < (u32)L3_CNTN; i += L3_NT) cnt[i] = 0;
+    if (tid == 0) misc[32] = 0;  // largest slot seen in the tile
+
     while (true) {
-        __syncthreads();  // `nxt` is published; the previous tile is completely written out
+        __syncthreads();  // `nxt` is published, the counters are zero, the previous tile has left X
         const u32 t = nxt[0], b0 = nxt[1], b1 = nxt[2], E0 = nxt[3], M = nxt[4];
         if (t >= a.ntiles) break;
         const u64 *src = a.in + E0;
-
-        if (tid == 0) misc[32] = 0;  // crowded flag
-        // bins [0, M) are used; the blocked scan below reads a few entries past bin M
-        for (u32 i = tid; i < min((u32)L3_CNTN, M + 16u); i += L3_NT) cnt[i] = 0;
-        l3_segments(a.bstart, b0, b1, E0, M, segmask, segpre, segtab, L3_NT);
-        __syncthreads();
+        // bucket boundaries need a look only in tiles that span two level-1 parents (pass 3)
+        const bool segcheck = (b0 >> a.par_shift) != ((b1 - 1u) >> a.par_shift);
+        // Common case: a handful of buckets under one parent -- every thread keeps their
+        // (start, size) in registers and nothing about segments goes through shared memory.
+        const bool few = (b1 - b0 <= 4u) && !segcheck;
+        u32 e1 = M, e2 = M, e3 = M, e4 = M;  // tile-local starts of buckets b0+1 .. b0+4 (M: none)
+        if (few) {
+            const u32 nbk = b1 - b0;
+            if (nbk > 1u) e1 = a.bstart[b0 + 1] - E0;
+            if (nbk > 2u) e2 = a.bstart[b0 + 2] - E0;
+            if (nbk > 3u) e3 = a.bstart[b0 + 3] - E0;
+        } else {
+            l3_segments(a.bstart, b0, b1, E0, M, segmask, segpre, segtab, L3_NT);
+            __syncthreads();
+        }
+        (void)e4;
 
         // ---- pass 1: sub-bin = expected sorted position of the element inside its bucket at a
         // quarter of a position's resolution; the four sub-bins of a position are byte counters
@@ -741,9 +756,16 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
             if ((u32)j * L3_NT >= M) break;
             if (i < M) {
                 const u32 hi = meta[j];
-                const uint2 sg = segtab[seg_index(segmask, segpre, i)];
+                uint2 sg;
+                if (few) {
+                    sg.x = i >= e3 ? e3 : i >= e2 ? e2 : i >= e1 ? e1 : 0u;
+                    sg.y = (i >= e3 ? M : i >= e2 ? e3 : i >= e1 ? e2 : e1) - sg.x;
+                } else {
+                    sg = segtab[seg_index(segmask, segpre, i)];
+                }
                 const u32 rem = (hi >> a.pb) & remmask;
-                const u32 fb = (u32)(((u64)rem * (u64)(sg.y * 4u)) >> a.R);
+                // (rem * 4 * size) >> R as one high multiply (rem < 2^R, R <= 32)
+                const u32 fb = __umulhi(rem << remsh, sg.y * 4u);
                 const u32 word = sg.x + (fb >> 2), sub8 = (fb & 3u) * 8u;
                 const u32 slot = (atomicAdd(&cnt[word], 1u << sub8) >> sub8) & 255u;
                 myslot = max(myslot, slot);
@@ -811,7 +833,10 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
         }
         __syncthreads();
 
+        // the counters were last read above: zero them for the CTA's next tile
+        for (u32 i = tid; i < min((u32)L3_CNTN, M + 16u); i += L3_NT) cnt[i] = 0;
         if (tid == 0) {
+            misc[32] = 0;
             if (crowded) a.flagged[atomicAdd(a.nflagged, 1u)] = t;
             advance(t + gridDim.x);
         }
@@ -827,7 +852,6 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
         // (always with a single level).  Equal keys (a short suffix next to its padded twin, or
         // long suffixes that stay active) are rare and take the tie-break path. ----
         const u32 *Xh = (const u32 *)X;
-        const bool segcheck = (b0 >> a.par_shift) != ((b1 - 1u) >> a.par_shift);
         for (u32 p = tid; p < M; p += L3_NT) {
             const u32 kp = Xh[2 * p + 1] >> a.pb;
             u32 r = p;
