@@ -667,7 +667,8 @@ __device__ __forceinline__ void l3_emit(const L3Args &a, u32 g, u64 e, bool acti
 }
 
 static constexpr int L3_CNTN = L3_CAP + 16;        // counters per tile (the blocked scan reads a little past bin M)
-static constexpr size_t L3_SMEM = (size_t)L3_CAP * 8 + (size_t)L3_CNTN * 4 + (size_t)L3_CNTN * 2 +
+static constexpr int L3_PAD = L3_CROWD;             // guard elements on both sides of X (the ordering window never exceeds it)
+static constexpr size_t L3_SMEM = (size_t)(L3_CAP + 2 * L3_PAD) * 8 + (size_t)L3_CNTN * 4 + (size_t)L3_CNTN * 2 +
                                   (size_t)(L3_MASKW + 1) * 4 * 2 + 64 * 4 + 8 * 4;
 
 // sum of the four bytes of x
@@ -679,8 +680,8 @@ __device__ __forceinline__ u32 bytesum(u32 x) { return __dp4a(x, 0x01010101u, 0u
 // warp's critical path and the next tile's first pass reads L2, not HBM.
 __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *X = (u64 *)smem_raw;                         // [L3_CAP] elements grouped by bin
-    u32 *cnt = (u32 *)(X + L3_CAP);                   // [L3_CNTN] four byte-wide sub-bin counts per position
+    u64 *X = (u64 *)smem_raw + L3_PAD;                // [-PAD, CAP + PAD) elements grouped by bin, guards around them
+    u32 *cnt = (u32 *)(X + L3_CAP + L3_PAD);          // [L3_CNTN] four byte-wide sub-bin counts per position
     u16 *pre = (u16 *)(cnt + L3_CNTN);                // [L3_CNTN] exclusive prefix of the per-position totals
     u32 *segmask = (u32 *)(pre + L3_CNTN);            // [MASKW + 1]
     u32 *segpre = segmask + (L3_MASKW + 1);           // [MASKW + 1]
@@ -713,6 +714,8 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
 
     // the counters of the first tile (later tiles: zeroed again right after their last use)
     for (u32 i = tid; i < (u32)L3_CNTN; i += L3_NT) cnt[i] = 0;
+    // left guards: the smallest key, never "larger than" an element (pass 3)
+    if (tid < (u32)L3_PAD) X[-(int)tid - 1] = 0ull;
     if (tid == 0) misc[32] = 0;  // largest slot seen in the tile
 
     while (true) {
@@ -830,6 +833,8 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
                     X[(u32)pre[word] + below + slot] = src[i];
                 }
             }
+            // right guards: the largest key, never "smaller than" an element
+            if (tid < W) X[M + tid] = ~0ull;
         }
         __syncthreads();
 
@@ -852,29 +857,43 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
         // (always with a single level).  Equal keys (a short suffix next to its padded twin, or
         // long suffixes that stay active) are rare and take the tie-break path. ----
         const u32 *Xh = (const u32 *)X;
+        const u32 pbmask = (1u << a.pb) - 1u;
         for (u32 p = tid; p < M; p += L3_NT) {
-            const u32 kp = Xh[2 * p + 1] >> a.pb;
+            const u32 hp = Xh[2 * p + 1];
             u32 r = p;
-            bool eq = false, lv = true, rv = true;
-            for (u32 d = 1; d <= W; ++d) {
-                lv = lv && p >= d;
-                rv = rv && p + d < M;
-                if (segcheck) {
+            bool eq = false;
+            if (!segcheck) {
+                // keys compared as raw high words: a > (b | mask) <=> (a >> pb) > (b >> pb), and
+                // a < (b & ~mask) likewise; the guards on both sides of X make bounds checks unnecessary
+                const u32 hp_hi = hp | pbmask, hp_lo = hp & ~pbmask;
+                for (u32 d = 1; d <= W; ++d) {
+                    const u32 hl = Xh[2 * (int)(p - d) + 1], hr = Xh[2 * (p + d) + 1];
+                    r -= hl > hp_hi ? 1u : 0u;
+                    r += hr < hp_lo ? 1u : 0u;
+                    eq = eq || ((hl ^ hp) <= pbmask) || ((hr ^ hp) <= pbmask);
+                }
+            } else {
+                const u32 kp = hp >> a.pb;
+                bool lv = true, rv = true;
+                for (u32 d = 1; d <= W; ++d) {
+                    lv = lv && p >= d;
+                    rv = rv && p + d < M;
                     const u32 xl = p - d + 1u, xr = p + d;  // a bucket starts here: the neighbour is beyond it
                     if (lv && ((segmask[xl >> 5] >> (xl & 31u)) & 1u)) lv = false;
                     if (rv && ((segmask[xr >> 5] >> (xr & 31u)) & 1u)) rv = false;
-                }
-                if (lv) {
-                    const u32 ko = Xh[2 * (p - d) + 1] >> a.pb;
-                    r -= ko > kp ? 1u : 0u;
-                    eq = eq || ko == kp;
-                }
-                if (rv) {
-                    const u32 ko = Xh[2 * (p + d) + 1] >> a.pb;
-                    r += ko < kp ? 1u : 0u;
-                    eq = eq || ko == kp;
+                    if (lv) {
+                        const u32 ko = Xh[2 * (p - d) + 1] >> a.pb;
+                        r -= ko > kp ? 1u : 0u;
+                        eq = eq || ko == kp;
+                    }
+                    if (rv) {
+                        const u32 ko = Xh[2 * (p + d) + 1] >> a.pb;
+                        r += ko < kp ? 1u : 0u;
+                        eq = eq || ko == kp;
+                    }
                 }
             }
+            const u32 kp = hp >> a.pb;
             const u64 e = X[p];
             bool active = false;
             u32 head = r;
@@ -884,7 +903,7 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
                 const u32 se = (u32)e;
                 const bool e_short = is_short_suffix(se, a.K, a.n);
                 u32 longs_before = 0;
-                lv = rv = true;
+                bool lv = true, rv = true;
                 for (u32 d = 1; d <= W; ++d) {
                     lv = lv && p >= d;
                     rv = rv && p + d < M;
