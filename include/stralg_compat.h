@@ -156,6 +156,27 @@ void write_complete_bwt_info_fname(const char *fname, const struct bwt_table *bw
 struct bwt_table *read_complete_bwt_info(FILE *f);                                    /* :32 */
 struct bwt_table *read_complete_bwt_info_fname(const char *fname);                    /* :33 */
 
+/* ---- reads in, SAM out: `bwt_readmapper -d 0`, batched --------------------------
+ * The reference maps one read at a time (map_read, tools/readmappers/bwt_readmapper/bwt_readmapper.c:
+ * 128-161): for every FASTQ record (bioinf/fastq.c:16-34), for every reference record in list order,
+ * remap the read with that record's table (skipped when remap() returns NULL), enumerate the matches
+ * and print one SAM line each (bioinf/sam.c:4-10; position 1-based, CIGAR "<m>M").  With zero edits
+ * its approximate iterator yields exactly the interval of the exact iterator, in suffix-array order.
+ * bwt_map_fastq_exact does the same for a whole FASTQ stream, `batch_reads` reads per GPU batch
+ * (one backward-search launch per batch and record); the output is byte-identical to the
+ * reference tool's.  Returns the number of SAM lines written. */
+uint64_t bwt_map_fastq_exact(FILE *fastq, FILE *samfile, uint32_t nrecords, const char *const *record_names,
+                             struct bwt_table *const *tables, uint64_t batch_reads);
+/* The multi-record index file of `bwt_readmapper -p` (bwt_readmapper.c:48-61): [u32 records], then per
+ * record [u32 len][name incl. NUL] (string_utils.c:48-65) + write_complete_bwt_info.  The tool writes
+ * the FASTA records in REVERSE file order (bioinf/fasta.c:131 prepends) and maps in the reverse of
+ * the order read (bwt_readmapper.c:107 prepends again).  read_bwt_tables_file returns file order;
+ * names[i] and tables[i] are malloc'd (free the arrays with free(), tables with
+ * completely_free_bwt_table). */
+void write_bwt_tables_file(const char *fname, uint32_t nrecords, const char *const *record_names,
+                           struct bwt_table *const *tables);
+uint32_t read_bwt_tables_file(const char *fname, char ***record_names, struct bwt_table ***tables);
+
 #ifdef __cplusplus
 }
 #endif

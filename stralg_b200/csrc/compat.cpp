@@ -17,7 +17,9 @@
 #include <string.h>
 
 #include <mutex>
+#include <string>
 #include <unordered_map>
+#include <vector>
 
 namespace {
 
@@ -565,6 +567,126 @@ struct bwt_table *read_complete_bwt_info_fname(const char *fname) {
     struct bwt_table *tbl = read_complete_bwt_info(f);
     fclose(f);
     return tbl;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reads in, SAM out: the loop of bwt_readmapper -d 0 with the backward searches batched on the GPU
+// ------------------------------------------------------------------------------------------------
+namespace {
+const int kFastqLine = 2048;  // MAX_STRING_LEN, bioinf/fastq.h:9
+
+// one line without its newline, the way next_fastq_record takes it (fgets + strtok(..., "\n"))
+bool fastq_line(FILE *f, char *buf, std::string *out, int skip) {
+    if (!fgets(buf, kFastqLine, f)) return false;
+    char *p = buf + skip;
+    while (*p == '\n') ++p;  // strtok skips leading delimiters
+    size_t n = strcspn(p, "\n");
+    out->assign(p, n);
+    return true;
+}
+}  // namespace
+
+uint64_t bwt_map_fastq_exact(FILE *fastq, FILE *samfile, uint32_t nrecords, const char *const *record_names,
+                             struct bwt_table *const *tables, uint64_t batch_reads) {
+    if (batch_reads == 0) batch_reads = 1u << 20;
+    std::vector<char> line(kFastqLine + 1);
+    std::vector<std::string> names, seqs, quals;
+    std::vector<uint8_t> pat;
+    std::vector<uint64_t> off;
+    std::vector<uint32_t> which;
+    std::vector<std::vector<uint32_t>> Ls(nrecords), Rs(nrecords);
+    uint64_t lines = 0;
+    bool more = true;
+    while (more) {
+        names.clear(); seqs.clear(); quals.clear();
+        while (names.size() < batch_reads) {
+            std::string name, seq, plus, qual;
+            if (!fastq_line(fastq, line.data(), &name, 1)) {  // name: the text after '@'
+                more = false;
+                break;
+            }
+            fastq_line(fastq, line.data(), &seq, 0);
+            fastq_line(fastq, line.data(), &plus, 0);
+            fastq_line(fastq, line.data(), &qual, 0);
+            names.push_back(name); seqs.push_back(seq); quals.push_back(qual);
+        }
+        const size_t nreads = names.size();
+        if (!nreads) break;
+        // one batched backward search per reference record; (1, 0) marks a read that record skips
+        for (uint32_t r = 0; r < nrecords; ++r) {
+            struct remap_table *rt = tables[r]->remap_table;
+            pat.clear(); off.assign(1, 0); which.clear();
+            Ls[r].assign(nreads, 1); Rs[r].assign(nreads, 0);
+            for (size_t q = 0; q < nreads; ++q) {
+                const std::string &sq = seqs[q];
+                if (sq.empty()) continue;
+                const size_t at = pat.size();
+                pat.resize(at + sq.size());
+                bool ok = true;
+                for (size_t k = 0; k < sq.size() && ok; ++k) {
+                    const signed char c = rt->table[(unsigned char)sq[k]];
+                    ok = c > 0;  // remap() returns NULL on a letter without a code (remap.c:80-84)
+                    pat[at + k] = (uint8_t)c;
+                }
+                if (!ok) {
+                    pat.resize(at);
+                    continue;
+                }
+                off.push_back(pat.size());
+                which.push_back((uint32_t)q);
+            }
+            if (which.empty()) continue;
+            std::vector<uint32_t> L(which.size()), R(which.size());
+            bwt_exact_match_batch(tables[r], pat.data(), off.data(), which.size(), L.data(), R.data());
+            for (size_t k = 0; k < which.size(); ++k) {
+                Ls[r][which[k]] = L[k];
+                Rs[r][which[k]] = R[k];
+            }
+        }
+        // SAM lines in the reference's order: reads, then records, then suffix-array order
+        for (size_t q = 0; q < nreads; ++q)
+            for (uint32_t r = 0; r < nrecords; ++r) {
+                const uint32_t *sa = tables[r]->sa->array;
+                for (uint32_t i = Ls[r][q]; i < Rs[r][q]; ++i) {
+                    fprintf(samfile, "%s\t0\t%s\t%u\t0\t%zuM\t*\t0\t0\t%s\t%s\n", names[q].c_str(), record_names[r],
+                            sa[i] + 1, seqs[q].size(), seqs[q].c_str(), quals[q].c_str());
+                    ++lines;
+                }
+            }
+    }
+    return lines;
+}
+
+void write_bwt_tables_file(const char *fname, uint32_t nrecords, const char *const *record_names,
+                           struct bwt_table *const *tables) {
+    FILE *f = open_or_die(fname, "wb");
+    must(fwrite(&nrecords, sizeof nrecords, 1, f) == 1, "write_bwt_tables_file: short write");
+    for (uint32_t r = 0; r < nrecords; ++r) {
+        const uint32_t len = (uint32_t)strlen(record_names[r]) + 1;  // write_string: the NUL is stored
+        must(fwrite(&len, sizeof len, 1, f) == 1 && fwrite(record_names[r], 1, len, f) == len,
+             "write_bwt_tables_file: short write");
+        write_complete_bwt_info(f, tables[r]);
+    }
+    fclose(f);
+}
+
+uint32_t read_bwt_tables_file(const char *fname, char ***record_names, struct bwt_table ***tables) {
+    FILE *f = open_or_die(fname, "rb");
+    uint32_t nrecords = 0;
+    must(fread(&nrecords, sizeof nrecords, 1, f) == 1, "read_bwt_tables_file: short read");
+    *record_names = (char **)malloc((size_t)nrecords * sizeof(char *));
+    *tables = (struct bwt_table **)malloc((size_t)nrecords * sizeof(struct bwt_table *));
+    for (uint32_t r = 0; r < nrecords; ++r) {
+        uint32_t len = 0;
+        must(fread(&len, sizeof len, 1, f) == 1, "read_bwt_tables_file: short read");
+        char *name = (char *)malloc((size_t)len + 1);
+        must(fread(name, 1, len, f) == len, "read_bwt_tables_file: short read");
+        name[len] = 0;
+        (*record_names)[r] = name;
+        (*tables)[r] = read_complete_bwt_info(f);
+    }
+    fclose(f);
+    return nrecords;
 }
 
 }  // extern "C"

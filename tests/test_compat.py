@@ -68,6 +68,20 @@ def bind_extra(lib):
     return lib
 
 
+def bind_mapper(lib):
+    """The batched read mapper and the multi-record index file (ours, not in the reference library)."""
+    lib.bwt_map_fastq_exact.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p),
+                                        C.POINTER(C.POINTER(RefBwtTable)), C.c_uint64]
+    lib.bwt_map_fastq_exact.restype = C.c_uint64
+    lib.write_bwt_tables_file.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p),
+                                          C.POINTER(C.POINTER(RefBwtTable))]
+    lib.write_bwt_tables_file.restype = None
+    lib.read_bwt_tables_file.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_char_p)),
+                                         C.POINTER(C.POINTER(C.POINTER(RefBwtTable)))]
+    lib.read_bwt_tables_file.restype = C.c_uint32
+    return lib
+
+
 @pytest.fixture(scope="module")
 def compat():
     assert os.path.exists(COMPAT_SO), "libstralg_b200.so missing: run __graft_entry__.build()"
@@ -375,6 +389,68 @@ def test_serialise_test_c(compat, engine, ref, tmp_path):
         assert sorted(got) == naive_positions(raw, pat)
     compat.completely_free_bwt_table(back)
     compat.completely_free_bwt_table(tbl)
+
+
+def read_fasta(path):
+    recs, name, seq = [], None, []
+    for ln in open(path):
+        ln = ln.strip()
+        if ln.startswith(">"):
+            if name is not None:
+                recs.append((name, "".join(seq)))
+            name, seq = ln[1:].strip(), []
+        elif ln:
+            seq.append(ln)
+    recs.append((name, "".join(seq)))
+    return recs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch_reads", [0, 7])
+def test_readmapper_exact_matches_reference_tool(compat, engine, tmp_path, batch_reads):
+    """`bwt_readmapper -p` + `bwt_readmapper -d 0` (tools/readmappers/bwt_readmapper/
+    bwt_readmapper.c:16-67, 128-161) against the golden files the reference tool produced
+    (tests/golden/make_readmapper_golden.py): the index file is byte-identical (sha256), the SAM output is
+    byte-identical, with the tables built and the reads searched on the GPU."""
+    import hashlib
+    import json
+    gdir = os.path.join(ROOT, "tests", "golden", "readmapper")
+    meta = json.load(open(os.path.join(gdir, "meta.json")))
+    bind_mapper(compat)
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    recs = read_fasta(os.path.join(gdir, "ref.fa"))
+    assert [r[0] for r in recs] == ["chrA", "chrB"]
+    # -p: records in reverse FASTA order (bioinf/fasta.c:131), tables with the reverse O table (bwt_readmapper.c:58)
+    order = recs[::-1]
+    tbls = [compat.build_complete_table(C.cast(cbuf(seq.encode()), u8p), True) for _, seq in order]
+    names = (C.c_char_p * len(order))(*[n.encode() for n, _ in order])
+    tarr = (C.POINTER(RefBwtTable) * len(order))(*tbls)
+    fname = str(tmp_path / "ref.fa.bwttables").encode()
+    compat.write_bwt_tables_file(fname, len(order), names, tarr)
+    blob = open(fname, "rb").read()
+    assert len(blob) == meta["bwttables_bytes"]
+    assert hashlib.sha256(blob).hexdigest() == meta["bwttables_sha256"]
+    for t in tbls:
+        compat.completely_free_bwt_table(t)
+    # -d 0: read the file back, map in the reverse of the file order (bwt_readmapper.c:107)
+    rnames, rtabs = C.POINTER(C.c_char_p)(), C.POINTER(C.POINTER(RefBwtTable))()
+    nrec = compat.read_bwt_tables_file(fname, C.byref(rnames), C.byref(rtabs))
+    assert nrec == 2 and [rnames[i] for i in range(nrec)] == [b"chrB", b"chrA"]
+    mnames = (C.c_char_p * nrec)(*[rnames[i] for i in reversed(range(nrec))])
+    mtabs = (C.POINTER(RefBwtTable) * nrec)(*[rtabs[i] for i in reversed(range(nrec))])
+    fq = libc.fopen(os.path.join(gdir, "reads.fq").encode(), b"r")
+    out_path = str(tmp_path / "out.sam").encode()
+    out = libc.fopen(out_path, b"w")
+    nlines = compat.bwt_map_fastq_exact(fq, out, nrec, mnames, mtabs, batch_reads)
+    libc.fclose(fq)
+    libc.fclose(out)
+    assert nlines == meta["sam_lines"]
+    assert open(out_path, "rb").read() == open(os.path.join(gdir, "expected.sam"), "rb").read()
+    for i in range(nrec):
+        compat.completely_free_bwt_table(rtabs[i])
 
 
 @pytest.mark.gpu
