@@ -431,6 +431,32 @@ def gpu_arm(args, rank, local_rank, world):
                       "whole_build_frac_of_peak": model_bytes / (ms_step / 1e3) / 1e9 / peak},
             "cpu_baseline": cpu_baseline, "stages": stages,
         }
+        # BASELINE configs[1]: SA + LCP of a 256 Mi random ACGT text (device-resident, same timing rules)
+        try:
+            n2 = min(1 << 28, n)
+            for _ in range(2):
+                stralg_b200.SuffixArrayIndex.build(text[:n2], 5, occ=False, lcp=True, device=local_rank,
+                                                   stream=stream).close()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            c0.record()
+            reps2 = 3
+            lcp_stages = {}
+            for _ in range(reps2):
+                i2 = stralg_b200.SuffixArrayIndex.build(text[:n2], 5, occ=False, lcp=True, profile=True,
+                                                        device=local_rank, stream=stream)
+                for name, ms, by in i2.profile():
+                    lcp_stages[name] = lcp_stages.get(name, 0.0) + ms / reps2
+                i2.close()
+            c1.record()
+            torch.cuda.synchronize()
+            ms2 = c0.elapsed_time(c1) / reps2
+            out["config2_sa_lcp"] = {"workload": "SA + LCP of random ACGT (BASELINE configs[1])", "n": n2,
+                                     "ms_per_build": ms2, "Mchars_per_s": n2 / (ms2 / 1e3) / 1e6,
+                                     "lcp_stage_ms": {k: round(v, 3) for k, v in lcp_stages.items()
+                                                      if k.startswith(("phi", "plcp", "lcp", "inverse"))}}
+        except Exception as ex:
+            out["config2_sa_lcp"] = {"error": str(ex)[:200]}
         if not args.no_search:
             out["search"] = search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n, None, 0, 1,
                                          peak, peak_src, build)

@@ -43,7 +43,8 @@ def test_fullsize_properties(engine):
     text = torch.empty(n + 1, dtype=torch.uint8, device=dev)
     assert lib.b200sa_synth_codes(C.c_void_p(text.data_ptr()), n, 4, 424242, 0, None) == 0
     torch.cuda.synchronize()
-    idx = engine.SuffixArrayIndex.build(text[:n], 5, isa=False, bwt=True, occ=True)
+    # the search index of bench.py: unique-interval shortcut + 12-mer seed table on top of the O table
+    idx = engine.SuffixArrayIndex.build(text[:n], 5, isa=False, bwt=True, occ=True, textcmp=True, ktable=True)
     lib.b200sa_release_workspace(0)  # give the memory back before torch needs it
     length = n + 1
     st = idx.stats()
@@ -164,4 +165,66 @@ def test_fullsize_properties(engine):
     inner = hq[(R[hq] < length)]
     assert not bool(matches(R[inner], inner).any())
     # misses: a random 100-mer does not occur (checked through the count of exact hits being 0)
+    idx.close()
+
+
+def test_config2_sa_and_lcp_256M(engine):
+    """BASELINE.json configs[1]: SA + LCP of a 256 Mi random ACGT text.  SA through the permutation +
+    adjacent-order checker; LCP (stralg/suffix_array.c:64-85) on a sample of two million rows against a
+    direct symbol-by-symbol comparison of the two suffixes, plus lcp[0] == 0."""
+    import torch
+    lib = engine.load()
+    n = int(float(os.environ.get("B200SA_CONFIG2_N", 1 << 28)))
+    dev = torch.device("cuda", 0)
+    text = torch.empty(n + 1, dtype=torch.uint8, device=dev)
+    assert lib.b200sa_synth_codes(C.c_void_p(text.data_ptr()), n, 4, 77, 0, None) == 0
+    torch.cuda.synchronize()
+    idx = engine.SuffixArrayIndex.build(text[:n], 5, lcp=True, occ=False)
+    lib.b200sa_release_workspace(0)
+    length = n + 1
+
+    def view(ptr, count):
+        iface = {"shape": (count,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+
+        class Holder:
+            __cuda_array_interface__ = iface
+        return torch.as_tensor(Holder(), device=dev)
+
+    sa = view(idx.device_ptr("sa"), length)
+    lcp = view(idx.device_ptr("lcp"), length)
+    isa = torch.empty(length, dtype=torch.int32, device=dev)
+    for lo in range(0, length, CHUNK):
+        hi = min(length, lo + CHUNK)
+        s = sa[lo:hi].long() & 0xFFFFFFFF
+        isa[s] = torch.arange(lo, hi, device=dev, dtype=torch.int64).to(torch.int32)
+    for lo in range(0, length, CHUNK):
+        hi = min(length, lo + CHUNK)
+        s = sa[lo:hi].long() & 0xFFFFFFFF
+        assert bool(((isa[s].long() & 0xFFFFFFFF) == torch.arange(lo, hi, device=dev)).all()), "SA is not a permutation"
+    for lo in range(1, length, CHUNK):
+        hi = min(length, lo + CHUNK)
+        a = sa[lo - 1:hi - 1].long() & 0xFFFFFFFF
+        b = sa[lo:hi].long() & 0xFFFFFFFF
+        ra = isa[torch.clamp(a + 1, max=n)].long() & 0xFFFFFFFF
+        rb = isa[torch.clamp(b + 1, max=n)].long() & 0xFFFFFFFF
+        ok = (text[a] < text[b]) | ((text[a] == text[b]) & (ra < rb))
+        assert bool(ok.all()), "suffixes out of order"
+    del isa
+    assert int(lcp[0]) == 0
+    g = torch.Generator(device="cpu").manual_seed(5)
+    rows = torch.cat([torch.arange(1, 2001), torch.randint(1, length, (2_000_000,), generator=g)]).to(dev)
+    a = sa[rows - 1].long() & 0xFFFFFFFF
+    b = sa[rows].long() & 0xFFFFFFFF
+    l = torch.zeros_like(a)
+    active = torch.ones_like(a, dtype=torch.bool)
+    for _ in range(96):
+        eq = text[torch.clamp(a + l, max=n)] == text[torch.clamp(b + l, max=n)]
+        active = active & eq
+        if not bool(active.any()):
+            break
+        l = l + active.long()
+    assert not bool(active.any()), "a sampled LCP exceeds 96 on random DNA"
+    got = lcp[rows].long() & 0xFFFFFFFF
+    assert bool((got == l).all()), "LCP mismatch"
+    print(f"[config2] n = {n}, max sampled lcp = {int(l.max())}, stats = {idx.stats()}")
     idx.close()
