@@ -14,6 +14,7 @@
 //   plcp tile_last/scan/fill   "copy last defined value" scan -> v[i] everywhere
 //   lcp_gather            lcp[r] = v[sa[r]] - sa[r]
 #include "engine.h"
+#include "round0_msd.cuh"  // window_at
 
 namespace b200sa {
 
@@ -244,11 +245,64 @@ __global__ void __launch_bounds__(256) lcp_gather_kernel(const u32 *__restrict__
     lcp[r] = r ? v[s] - s : 0u;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Direct path for texts without long repeats: row r compares the suffixes SA[r-1] and SA[r] on the
+// packed text, 64 bits per step (two random word pairs per row instead of the Phi scatter, the
+// PLCP pass and the final gather).  A comparison still running after DIRECT_CAP symbols raises
+// `overflow`; the caller then runs the Phi / PLCP pipeline, whose cost does not depend on the
+// LCP values.  The unique sentinel ends every comparison (stralg/suffix_array.c:73-84): the
+// common prefix cannot pass the end of the shorter suffix.
+// ---------------------------------------------------------------------------------------------
+static constexpr u32 DIRECT_CAP = 4096;
+
+__global__ void __launch_bounds__(256) lcp_direct_kernel(const u64 *__restrict__ packed, int bits, u32 n,
+                                                         const u32 *__restrict__ sa, u32 len,
+                                                         u32 *__restrict__ lcp, int *__restrict__ overflow) {
+    const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= len) return;
+    if (r == 0) {
+        lcp[0] = 0;
+        return;
+    }
+    const u32 a = sa[r - 1], b = sa[r];
+    const u32 lim = n - max(a, b);  // symbols the shorter suffix has before the sentinel
+    const u32 spw = 64u / (u32)bits;
+    u32 l = 0;
+    while (l < lim) {
+        const u64 x = window_at(packed, (u64)a + l, bits) ^ window_at(packed, (u64)b + l, bits);
+        if (x) {
+            l += (u32)__clzll((long long)x) / (u32)bits;
+            break;
+        }
+        l += spw;
+        if (l >= DIRECT_CAP) {
+            *overflow = 1;
+            break;
+        }
+    }
+    lcp[r] = min(l, lim);
+}
+
 void build_lcp(DeviceIndex &ix) {
     cudaStream_t st = ix.stream;
     const u32 len = ix.len, n = ix.n;
     const int bits = ix.pk.bits;
     Arena &ar = *ix.arena;
+    // texts that needed few doubling rounds have no long repeats to speak of: try the direct path
+    static const bool no_direct = getenv("B200SA_LCP_NO_DIRECT") != nullptr;
+    if (!no_direct && ix.stats.rounds <= 3) {
+        ix.lcp.alloc(len, st);
+        int *d_over = ar.get<int>(1);
+        CUDA_CHECK(cudaMemsetAsync(d_over, 0, 4, st));
+        int t = ix.timer.begin("lcp_direct", (double)len * 12.0);
+        lcp_direct_kernel<<<div_up_u(len, 256), 256, 0, st>>>(ix.packed, bits, n, ix.sa.ptr, len, ix.lcp.ptr, d_over);
+        KERNEL_CHECK();
+        ix.timer.end(t);
+        int over = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&over, d_over, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (!over) return;
+    }
     u32 *phi = ar.get<u32>(len), *v = ar.get<u32>(len);
     int t = ix.timer.begin("lcp_phi", (double)len * 8.0);
     phi_kernel<<<div_up_u(len, 256), 256, 0, st>>>(ix.sa.ptr, len, phi);
@@ -280,7 +334,7 @@ void build_lcp(DeviceIndex &ix) {
     KERNEL_CHECK();
     ix.timer.end(t);
 
-    ix.lcp.alloc(len, st);
+    if (!ix.lcp.ptr) ix.lcp.alloc(len, st);
     t = ix.timer.begin("lcp_gather", (double)len * 12.0);
     lcp_gather_kernel<<<div_up_u(len, 256), 256, 0, st>>>(ix.sa.ptr, v, len, ix.lcp.ptr);
     KERNEL_CHECK();
