@@ -72,6 +72,8 @@ struct b200sa_stats {
     uint64_t occ_bytes;
     uint32_t round0_mode;  /* initial sort: 0 = LSD radix passes, 1 = MSD bucket sort of 8-byte elements */
     uint32_t bucket_bits;  /* bucket sort: leading key bits that select a bucket */
+    uint32_t sa_sample_rate; /* b200sa_sample_sa: text-position sampling rate of the sampled SA, 0 = none */
+    uint32_t sa_resident;    /* 1 while the full suffix array is held in HBM */
 };
 
 /* ---- construction ------------------------------------------------------------------------
@@ -143,6 +145,27 @@ int b200sa_locate_batch(const b200sa_index *idx, const uint32_t *L, const uint32
 int b200sa_locate_device(const b200sa_index *idx, const uint32_t *d_L, const uint32_t *d_R,
                          uint64_t npat, uint64_t *d_pos_off, uint32_t *d_pos,
                          uint64_t pos_capacity, uint64_t *total, void *stream);
+
+/* Same, with the positions of every pattern in ascending order: the order the reference's tests
+ * compare in (tests/stralg/match_test.c:608 sorts the iterator's output before checking it). */
+int b200sa_locate_batch_sorted(const b200sa_index *idx, const uint32_t *L, const uint32_t *R,
+                               uint64_t npat, uint64_t *pos_off, uint32_t *pos,
+                               uint64_t pos_capacity, uint64_t *total);
+/* Sorts the positions of every pattern of an existing CSR in place (device buffers). */
+int b200sa_sort_positions_device(const b200sa_index *idx, uint64_t npat, const uint64_t *d_pos_off,
+                                 uint64_t total, uint32_t *d_pos, void *stream);
+
+/* ---- sampled suffix array ------------------------------------------------
+ * Keeps SA[r] only for the rows whose suffix starts at a multiple of `rate` (a bitmap with rank
+ * directory + the sampled values: 0.25 + 4/rate bytes per row instead of 4); every other entry
+ * is recovered by at most rate - 1 LF steps over the O table (stralg_b200/csrc/locate.cu), so
+ * next_bwt_exact_match_iter's positions (bwt.c:201-217) come out identical.  With drop_sa != 0
+ * the full array is released (12 GB at 3 Gbp) and locate uses the sampled one.  Needs OCC. */
+int b200sa_sample_sa(b200sa_index *idx, uint32_t rate, int drop_sa);
+/* out[q] = SA[rows[q]] (struct suffix_array.array[rows[q]]), host buffers; force_sampled != 0
+ * answers through the sampled array even when the full one is resident. */
+int b200sa_sa_lookup(const b200sa_index *idx, const uint32_t *rows, uint64_t count, uint32_t *out,
+                     int force_sampled);
 
 /* ---- synthetic inputs on the device (bench / tests; mirrors performance/suffix_array_search.c:13-32)
  * d_text must hold n + 1 bytes; symbols are 1 + hash(seed + i) % nsym, d_text[n] = 0. */

@@ -38,6 +38,7 @@ class Stats(C.Structure):
         ("k0", C.c_uint32), ("radix_bits", C.c_uint32), ("passes0", C.c_uint32), ("occ_layout", C.c_uint32),
         ("sorted_total", C.c_uint64), ("passes_elems", C.c_uint64), ("occ_bytes", C.c_uint64),
         ("round0_mode", C.c_uint32), ("bucket_bits", C.c_uint32),
+        ("sa_sample_rate", C.c_uint32), ("sa_resident", C.c_uint32),
     ]
 
 
@@ -77,6 +78,12 @@ SIGNATURES = {
                                       C.c_void_p, C.c_uint64, u64p]),
     "b200sa_locate_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                        C.c_void_p, C.c_uint64, u64p, C.c_void_p]),
+    "b200sa_locate_batch_sorted": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                             C.c_void_p, C.c_uint64, u64p]),
+    "b200sa_sort_positions_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
+                                               C.c_void_p]),
+    "b200sa_sample_sa": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int]),
+    "b200sa_sa_lookup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]),
     "b200sa_synth_codes": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]),
     "b200sa_synth_reads": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32,
                                      C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]),

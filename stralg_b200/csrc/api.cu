@@ -74,6 +74,17 @@ static void use_device(int device) {
     }
 }
 
+static bool can_locate(const b200sa_index *idx) {
+    return idx->ix.sa.ptr || (idx->ix.ssa_rate && idx->ix.occ_layout != OCC_NONE);
+}
+// positions through the full suffix array when it is resident, else through the sampled one
+static void locate_fill_any(const DeviceIndex &ix, const u32 *d_L, const u32 *d_R, u64 npat, const u64 *d_pos_off,
+                            u64 total, u32 *d_pos, cudaStream_t st) {
+    static const bool force_ssa = getenv("B200SA_LOCATE_SAMPLED") != nullptr;
+    if (ix.sa.ptr && !(force_ssa && ix.ssa_rate)) fm_locate_fill(ix, d_L, d_R, npat, d_pos_off, total, d_pos, st);
+    else fm_locate_fill_ssa(ix, d_L, npat, d_pos_off, total, d_pos, st);
+}
+
 #pragma GCC visibility push(default)
 extern "C" {
 
@@ -251,6 +262,8 @@ int b200sa_stats(const b200sa_index *idx, struct b200sa_stats *out) {
     out->occ_bytes = ix.occ.bytes();
     out->round0_mode = ix.stats.round0_mode;
     out->bucket_bits = ix.stats.bucket_bits;
+    out->sa_sample_rate = ix.ssa_rate;
+    out->sa_resident = ix.sa.ptr ? 1u : 0u;
     return 0;
 }
 
@@ -411,7 +424,7 @@ int b200sa_search_batch(const b200sa_index *idx, const uint8_t *patterns, const 
 int b200sa_locate_device(const b200sa_index *idx, const uint32_t *d_L, const uint32_t *d_R, uint64_t npat,
                          uint64_t *d_pos_off, uint32_t *d_pos, uint64_t pos_capacity, uint64_t *total, void *stream) {
     if (!idx || !d_pos_off || (npat && (!d_L || !d_R))) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
-    if (!idx->ix.sa.ptr) return fail(B200SA_ERR_NOT_BUILT, "suffix array was dropped (B200SA_DROP_SA)", nullptr);
+    if (!can_locate(idx)) return fail(B200SA_ERR_NOT_BUILT, "no suffix array to locate with (dropped and not sampled)", nullptr);
     API_GUARD_BEGIN
     CUDA_CHECK(cudaSetDevice(idx->ix.device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -419,16 +432,28 @@ int b200sa_locate_device(const b200sa_index *idx, const uint32_t *d_L, const uin
     if (total) *total = t;
     if (d_pos) {
         if (t > pos_capacity) return fail(B200SA_ERR_BAD_ARGUMENT, "position buffer too small", nullptr);
-        fm_locate_fill(idx->ix, d_L, d_R, npat, d_pos_off, t, d_pos, st);
+        locate_fill_any(idx->ix, d_L, d_R, npat, d_pos_off, t, d_pos, st);
     }
     return 0;
     API_GUARD_END(nullptr)
 }
 
-int b200sa_locate_batch(const b200sa_index *idx, const uint32_t *L, const uint32_t *R, uint64_t npat,
-                        uint64_t *pos_off, uint32_t *pos, uint64_t pos_capacity, uint64_t *total) {
+int b200sa_sort_positions_device(const b200sa_index *idx, uint64_t npat, const uint64_t *d_pos_off, uint64_t total,
+                                 uint32_t *d_pos, void *stream) {
+    if (!idx || !d_pos_off || (total && !d_pos)) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    if (total > 0xFFFFFFFFull || npat > 0xFFFFFFFFull)
+        return fail(B200SA_ERR_TOO_LARGE, "more than 2^32 - 1 positions or patterns in one batch", nullptr);
+    API_GUARD_BEGIN
+    CUDA_CHECK(cudaSetDevice(idx->ix.device));
+    sort_positions(idx->ix, npat, d_pos_off, total, d_pos, (cudaStream_t)stream);
+    return 0;
+    API_GUARD_END(nullptr)
+}
+
+__attribute__((visibility("hidden"))) static int locate_batch_impl(const b200sa_index *idx, const uint32_t *L, const uint32_t *R, uint64_t npat,
+                        uint64_t *pos_off, uint32_t *pos, uint64_t pos_capacity, uint64_t *total, bool sorted) {
     if (!idx || !pos_off || (npat && (!L || !R))) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
-    if (!idx->ix.sa.ptr) return fail(B200SA_ERR_NOT_BUILT, "suffix array was dropped (B200SA_DROP_SA)", nullptr);
+    if (!can_locate(idx)) return fail(B200SA_ERR_NOT_BUILT, "no suffix array to locate with (dropped and not sampled)", nullptr);
     API_GUARD_BEGIN
     const DeviceIndex &ix = idx->ix;
     CUDA_CHECK(cudaSetDevice(ix.device));
@@ -445,9 +470,56 @@ int b200sa_locate_batch(const b200sa_index *idx, const uint32_t *L, const uint32
     if (pos && t) {
         if (t > pos_capacity) return fail(B200SA_ERR_BAD_ARGUMENT, "position buffer too small", nullptr);
         DevBuf<u32> dpos(t, st);
-        fm_locate_fill(ix, dL.ptr, dR.ptr, npat, doff.ptr, t, dpos.ptr, st);
+        locate_fill_any(ix, dL.ptr, dR.ptr, npat, doff.ptr, t, dpos.ptr, st);
+        if (sorted) {
+            if (t > 0xFFFFFFFFull) return fail(B200SA_ERR_TOO_LARGE, "more than 2^32 - 1 positions in one batch", nullptr);
+            sort_positions(ix, npat, doff.ptr, t, dpos.ptr, st);
+        }
         CUDA_CHECK(cudaMemcpyAsync(pos, dpos.ptr, t * 4, cudaMemcpyDeviceToHost, st));
     }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    return 0;
+    API_GUARD_END(nullptr)
+}
+
+int b200sa_locate_batch(const b200sa_index *idx, const uint32_t *L, const uint32_t *R, uint64_t npat,
+                        uint64_t *pos_off, uint32_t *pos, uint64_t pos_capacity, uint64_t *total) {
+    return locate_batch_impl(idx, L, R, npat, pos_off, pos, pos_capacity, total, false);
+}
+int b200sa_locate_batch_sorted(const b200sa_index *idx, const uint32_t *L, const uint32_t *R, uint64_t npat,
+                               uint64_t *pos_off, uint32_t *pos, uint64_t pos_capacity, uint64_t *total) {
+    return locate_batch_impl(idx, L, R, npat, pos_off, pos, pos_capacity, total, true);
+}
+
+int b200sa_sample_sa(b200sa_index *idx, uint32_t rate, int drop_sa) {
+    if (!idx || rate < 1) return fail(B200SA_ERR_BAD_ARGUMENT, "null index or sampling rate 0", nullptr);
+    DeviceIndex &ix = idx->ix;
+    if (!ix.sa.ptr) return fail(B200SA_ERR_NOT_BUILT, "suffix array was dropped (B200SA_DROP_SA)", nullptr);
+    if (ix.occ_layout == OCC_NONE) return fail(B200SA_ERR_NOT_BUILT, "the sampled suffix array needs the O table (B200SA_BUILD_OCC)", nullptr);
+    API_GUARD_BEGIN
+    use_device(ix.device);
+    build_sampled_sa(ix, rate);
+    if (drop_sa && !(idx->flags & B200SA_BUILD_TEXTCMP)) ix.sa.release();
+    CUDA_CHECK(cudaStreamSynchronize(ix.stream));
+    return 0;
+    API_GUARD_END(nullptr)
+}
+
+int b200sa_sa_lookup(const b200sa_index *idx, const uint32_t *rows, uint64_t count, uint32_t *out, int force_sampled) {
+    if (!idx || (count && (!rows || !out))) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    const DeviceIndex &ix = idx->ix;
+    if (force_sampled ? !ix.ssa_rate : !can_locate(idx))
+        return fail(B200SA_ERR_NOT_BUILT, "no (sampled) suffix array", nullptr);
+    for (uint64_t q = 0; q < count; ++q)
+        if (rows[q] >= ix.len) return fail(B200SA_ERR_BAD_ARGUMENT, "row out of range", nullptr);
+    if (!count) return 0;
+    API_GUARD_BEGIN
+    CUDA_CHECK(cudaSetDevice(ix.device));
+    cudaStream_t st = ix.stream;
+    DevBuf<u32> dr(count, st), dout(count, st);
+    CUDA_CHECK(cudaMemcpyAsync(dr.ptr, rows, count * 4, cudaMemcpyHostToDevice, st));
+    sa_lookup_rows(ix, dr.ptr, count, dout.ptr, force_sampled != 0, st);
+    CUDA_CHECK(cudaMemcpyAsync(out, dout.ptr, count * 4, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     return 0;
     API_GUARD_END(nullptr)

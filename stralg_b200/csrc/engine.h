@@ -45,6 +45,9 @@ struct DeviceIndex {
     DevBuf<u64> text_packed;  // kept copy of the packed text (B200SA_BUILD_TEXTCMP: search shortcut)
     DevBuf<uint2> ktable;     // (L, R) after the recurrence on every k-mer (B200SA_BUILD_KTABLE)
     int ktable_k = 0;
+    DevBuf<uint4> ssa_marks;  // sampled suffix array (locate.cu): 16 bytes per 64 rows
+    DevBuf<u32> ssa_vals;     // SA values of the sampled rows
+    u32 ssa_rate = 0;         // 0: none
     DevBuf<u8> bwt;
     DevBuf<u32> c_table;    // sigma entries (device)
     u32 c_host[256];
@@ -78,6 +81,13 @@ u64 fm_locate_count(const DeviceIndex &ix, const u32 *d_L, const u32 *d_R, u64 n
                     cudaStream_t st);
 void fm_locate_fill(const DeviceIndex &ix, const u32 *d_L, const u32 *d_R, u64 npat, const u64 *d_pos_off,
                     u64 total, u32 *d_pos, cudaStream_t st);
+// locate.cu
+void build_sampled_sa(DeviceIndex &ix, u32 rate);  // fills ix.ssa_* from ix.sa
+void fm_locate_fill_ssa(const DeviceIndex &ix, const u32 *d_L, u64 npat, const u64 *d_pos_off, u64 total,
+                        u32 *d_pos, cudaStream_t st);
+void sa_lookup_rows(const DeviceIndex &ix, const u32 *d_rows, u64 count, u32 *d_out, bool force_sampled,
+                    cudaStream_t st);
+void sort_positions(const DeviceIndex &ix, u64 npat, const u64 *d_pos_off, u64 total, u32 *d_pos, cudaStream_t st);
 // synth.cu
 void synth_codes(u8 *d_text, u64 n, u32 nsym, u64 seed, cudaStream_t st);
 void synth_reads(const u8 *d_text, u64 n, u32 nsym, u8 *d_reads, u64 nreads, u32 m, u32 miss_per_1024,

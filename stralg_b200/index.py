@@ -193,20 +193,34 @@ class SuffixArrayIndex:
         return int(L[0]), int(R[0])
 
     # ---- locate (next_bwt_exact_match_iter, bwt.c:201-217) -------------------------------------
-    def locate(self, L, R) -> Tuple[np.ndarray, np.ndarray]:
-        """CSR (offsets[npat + 1], positions) in suffix-array order, like the reference iterator."""
+    def locate(self, L, R, sorted: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+        """CSR (offsets[npat + 1], positions) in suffix-array order, like the reference iterator;
+        ``sorted=True`` orders the positions of every pattern ascending (match_test.c:608)."""
         L = np.ascontiguousarray(L, dtype=np.uint32)
         R = np.ascontiguousarray(R, dtype=np.uint32)
         npat = len(L)
         off = np.empty(npat + 1, dtype=np.uint64)
         total = C.c_uint64(0)
         lib = _lib.load()
-        check(lib.b200sa_locate_batch(self._h, _np_ptr(L), _np_ptr(R), npat, _np_ptr(off), None, 0, C.byref(total)))
+        fn = lib.b200sa_locate_batch_sorted if sorted else lib.b200sa_locate_batch
+        check(fn(self._h, _np_ptr(L), _np_ptr(R), npat, _np_ptr(off), None, 0, C.byref(total)))
         pos = np.empty(total.value, dtype=np.uint32)
         if total.value:
-            check(lib.b200sa_locate_batch(self._h, _np_ptr(L), _np_ptr(R), npat, _np_ptr(off), _np_ptr(pos),
-                                          total.value, C.byref(total)))
+            check(fn(self._h, _np_ptr(L), _np_ptr(R), npat, _np_ptr(off), _np_ptr(pos), total.value, C.byref(total)))
         return off, pos
+
+    # ---- sampled suffix array (SURVEY 8f rank 3) -----------------------------------------------
+    def sample_sa(self, rate: int = 32, drop_sa: bool = False) -> None:
+        """Keep SA only at text positions that are multiples of ``rate``; with ``drop_sa`` the full
+        array is released and locate walks LF to the nearest sampled row (same positions)."""
+        check(_lib.load().b200sa_sample_sa(self._h, rate, 1 if drop_sa else 0))
+
+    def sa_lookup(self, rows, force_sampled: bool = False) -> np.ndarray:
+        """SA[rows] (``sa->array[i]`` of suffix_array.h:10-20) without copying the whole array."""
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        out = np.empty(len(rows), dtype=np.uint32)
+        check(_lib.load().b200sa_sa_lookup(self._h, _np_ptr(rows), len(rows), _np_ptr(out), 1 if force_sampled else 0))
+        return out
 
     def exact_matches(self, pattern_codes) -> np.ndarray:
         """All match positions of one pattern in SA order (the iterator loop of match_test.c:599-603)."""
