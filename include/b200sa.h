@@ -167,6 +167,31 @@ int b200sa_sample_sa(b200sa_index *idx, uint32_t rate, int drop_sa);
 int b200sa_sa_lookup(const b200sa_index *idx, const uint32_t *rows, uint64_t count, uint32_t *out,
                      int force_sampled);
 
+/* ---- batched approximate search -------------------------------------------
+ * Replaces init_bwt_approx_iter / next_bwt_approx_match (bwt.h:246-333, bwt.c:226-409): all
+ * intervals whose suffixes match the pattern within `max_edits` edits (substitutions, insertions,
+ * deletions), per pattern in the order the reference's depth-first recursion reports them,
+ * duplicates included, each with its matched text length and CIGAR (cigar.c:8-31).
+ * `rev_idx` (may be NULL) is an index (B200SA_BUILD_OCC) of the REVERSED text: it provides the
+ * reference's D table (bwt.c:319-337), which only prunes -- results are the same without it.
+ * `d_table` (may be NULL) passes a precomputed D table instead: one byte per pattern symbol, laid
+ * out like `patterns`.  Positions: b200sa_locate_batch over the returned (L, R) arrays; the
+ * reference reports position SA[L..R) for every interval in turn (bwt.c:384-401).
+ * Accessors return host arrays owned by the result (valid until b200sa_approx_free). */
+typedef struct b200sa_approx_result b200sa_approx_result;
+b200sa_approx_result *b200sa_approx_batch(const b200sa_index *idx, const b200sa_index *rev_idx,
+                                          const uint8_t *d_table, const uint8_t *patterns,
+                                          const uint64_t *offsets, uint32_t fixed_len, uint64_t npat,
+                                          int max_edits, enum b200sa_error *err);
+uint64_t b200sa_approx_hits(const b200sa_approx_result *r);              /* intervals in total   */
+const uint64_t *b200sa_approx_hit_offsets(const b200sa_approx_result *r);/* npat + 1 (CSR)       */
+const uint32_t *b200sa_approx_L(const b200sa_approx_result *r);
+const uint32_t *b200sa_approx_R(const b200sa_approx_result *r);
+const uint32_t *b200sa_approx_match_length(const b200sa_approx_result *r);
+const uint64_t *b200sa_approx_cigar_offsets(const b200sa_approx_result *r); /* hits + 1          */
+const char *b200sa_approx_cigars(const b200sa_approx_result *r);  /* NUL-terminated, back to back */
+void b200sa_approx_free(b200sa_approx_result *r);
+
 /* ---- synthetic inputs on the device (bench / tests; mirrors performance/suffix_array_search.c:13-32)
  * d_text must hold n + 1 bytes; symbols are 1 + hash(seed + i) % nsym, d_text[n] = 0. */
 int b200sa_synth_codes(uint8_t *d_text, uint64_t n, uint32_t nsym, uint64_t seed, int device,

@@ -17,6 +17,7 @@
 #define _GNU_SOURCE
 #include <pthread.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -479,4 +480,156 @@ void oracle_ref_search_threads(void *init_fn, void *table, const uint8_t *pat, u
     }
     for (uint32_t t = 0; t < threads; ++t)
         pthread_join(tid[t], 0);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Approximate (edit distance <= d) backward search.  Follows stralg/bwt.c:226-299 (the
+ * recursion), :302-382 (D table over the reversed text's O table + the first level, which has
+ * no deletions and no D-table test) and stralg/cigar.c:8-31 (run-length CIGAR).
+ *
+ * The search walks the pattern from its last symbol to its first.  A node is (L, R, i, matched
+ * length, edits left).  Children, in this order: for every letter a = 1..sigma-1 a match /
+ * substitution step (cost 0 if a == pattern[i] else 1) to (C[a]+O(a,L), C[a]+O(a,R), i-1);
+ * then one insertion step (pattern symbol skipped: same interval, i-1, cost 1); then for every
+ * letter a deletion step (interval narrowed by a, same i, cost 1).  A node is abandoned when
+ * edits_left < D[i] (D[i] = lower bound on the edits pattern[0..i] needs), children with an
+ * empty interval are not visited, and a node with i < 0 is a hit: (L, R, matched length) plus
+ * the operations of its path in pattern order, run-length encoded.  Hits are reported in the
+ * order the depth-first walk meets them; duplicates (same interval, other CIGAR) are kept.
+ *
+ * Dense O tables in the reference layout (o[i*sigma + a], i in [0, len]); ro may be NULL (no
+ * D table: every D[i] = 0, same hits, more work).
+ * ------------------------------------------------------------------------------------------ */
+struct oracle_approx_out {
+    uint64_t nhits, cap;
+    uint32_t *L, *R, *mlen;
+    uint64_t *cig_off;   /* nhits + 1 */
+    char *cigars;        /* NUL-terminated strings, back to back */
+    uint64_t cig_bytes, cig_cap;
+};
+
+struct approx_ctx {
+    const uint32_t *c, *o;
+    uint32_t sigma;
+    const uint8_t *pat;
+    const int *dtab;
+    char *ops;  /* operations of the current path, first = the step taken on the LAST symbol */
+    struct oracle_approx_out *out;
+};
+
+static void approx_hit(struct approx_ctx *x, uint32_t L, uint32_t R, uint32_t mlen, int depth)
+{
+    struct oracle_approx_out *o = x->out;
+    if (o->nhits == o->cap) {
+        o->cap = o->cap ? 2 * o->cap : 16;
+        o->L = realloc(o->L, o->cap * 4);
+        o->R = realloc(o->R, o->cap * 4);
+        o->mlen = realloc(o->mlen, o->cap * 4);
+        o->cig_off = realloc(o->cig_off, (o->cap + 1) * 8);
+    }
+    /* worst case: every operation its own run of up to 10 digits + letter */
+    uint64_t need = o->cig_bytes + (uint64_t)depth * 12 + 2;
+    if (need > o->cig_cap) {
+        o->cig_cap = 2 * need;
+        o->cigars = realloc(o->cigars, o->cig_cap);
+    }
+    o->L[o->nhits] = L;
+    o->R[o->nhits] = R;
+    o->mlen[o->nhits] = mlen;
+    o->cig_off[o->nhits] = o->cig_bytes;
+    char *w = o->cigars + o->cig_bytes;
+    for (int k = depth - 1; k >= 0;) { /* pattern order = path reversed */
+        int run = 1;
+        while (k - run >= 0 && x->ops[k - run] == x->ops[k])
+            ++run;
+        w += sprintf(w, "%d%c", run, x->ops[k]);
+        k -= run;
+    }
+    *w++ = 0;
+    o->cig_bytes = (uint64_t)(w - o->cigars);
+    o->nhits++;
+    o->cig_off[o->nhits] = o->cig_bytes;
+}
+
+static void approx_node(struct approx_ctx *x, uint32_t L, uint32_t R, int i, uint32_t mlen, int left,
+                        int depth, int root)
+{
+    if (!root) {
+        int need = (i >= 0 && x->dtab) ? x->dtab[i] : 0;
+        if (left < need)
+            return;
+        if (i < 0) {
+            approx_hit(x, L, R, mlen, depth);
+            return;
+        }
+    }
+    const uint32_t s = x->sigma;
+    for (uint32_t a = 1; a < s; ++a) {
+        int cost = a == x->pat[i] ? 0 : 1;
+        uint32_t l2 = x->c[a] + x->o[(uint64_t)L * s + a], r2 = x->c[a] + x->o[(uint64_t)R * s + a];
+        if (left - cost < 0 || l2 >= r2)
+            continue;
+        x->ops[depth] = 'M';
+        approx_node(x, l2, r2, i - 1, mlen + 1, left - cost, depth + 1, 0);
+    }
+    x->ops[depth] = 'I';
+    approx_node(x, L, R, i - 1, mlen, left - 1, depth + 1, 0);
+    if (root)
+        return;
+    for (uint32_t a = 1; a < s; ++a) {
+        uint32_t l2 = x->c[a] + x->o[(uint64_t)L * s + a], r2 = x->c[a] + x->o[(uint64_t)R * s + a];
+        if (l2 >= r2)
+            continue;
+        x->ops[depth] = 'D';
+        approx_node(x, l2, r2, i, mlen + 1, left - 1, depth + 1, 0);
+    }
+}
+
+/* D table, stralg/bwt.c:319-337: forward over the pattern with the reversed text's O table */
+void oracle_approx_dtable(const uint32_t *c, const uint32_t *ro, uint32_t sigma, uint32_t len,
+                          const uint8_t *pat, uint32_t m, int *dtab)
+{
+    uint32_t L = 0, R = len;
+    int need = 0;
+    for (uint32_t i = 0; i < m; ++i) {
+        uint8_t a = pat[i];
+        L = c[a] + ro[(uint64_t)L * sigma + a];
+        R = c[a] + ro[(uint64_t)R * sigma + a];
+        if (L >= R) {
+            ++need;
+            L = 0;
+            R = len;
+        }
+        dtab[i] = need;
+    }
+}
+
+void oracle_approx_dense(const uint32_t *c, const uint32_t *o, const uint32_t *ro, uint32_t sigma,
+                         uint32_t len, const uint8_t *pat, uint32_t m, int max_edits,
+                         struct oracle_approx_out *out)
+{
+    memset(out, 0, sizeof *out);
+    out->cig_off = malloc(8);
+    out->cig_off[0] = 0;
+    if (m == 0)
+        return;
+    int *dtab = 0;
+    if (ro) {
+        dtab = malloc((size_t)m * sizeof(int));
+        oracle_approx_dtable(c, ro, sigma, len, pat, m, dtab);
+    }
+    struct approx_ctx x = {c, o, sigma, pat, dtab, malloc((size_t)m + (size_t)max_edits + 4), out};
+    approx_node(&x, 0, len, (int)m - 1, 0, max_edits, 0, 1);
+    free(x.ops);
+    free(dtab);
+}
+
+void oracle_approx_free(struct oracle_approx_out *out)
+{
+    free(out->L);
+    free(out->R);
+    free(out->mlen);
+    free(out->cig_off);
+    free(out->cigars);
+    memset(out, 0, sizeof *out);
 }

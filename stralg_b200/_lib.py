@@ -84,6 +84,16 @@ SIGNATURES = {
                                                C.c_void_p]),
     "b200sa_sample_sa": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int]),
     "b200sa_sa_lookup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]),
+    "b200sa_approx_batch": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                         C.c_uint64, C.c_int, C.POINTER(C.c_int)]),
+    "b200sa_approx_hits": (C.c_uint64, [C.c_void_p]),
+    "b200sa_approx_hit_offsets": (u64p, [C.c_void_p]),
+    "b200sa_approx_L": (u32p, [C.c_void_p]),
+    "b200sa_approx_R": (u32p, [C.c_void_p]),
+    "b200sa_approx_match_length": (u32p, [C.c_void_p]),
+    "b200sa_approx_cigar_offsets": (u64p, [C.c_void_p]),
+    "b200sa_approx_cigars": (C.POINTER(C.c_char), [C.c_void_p]),
+    "b200sa_approx_free": (None, [C.c_void_p]),
     "b200sa_synth_codes": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]),
     "b200sa_synth_reads": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32,
                                      C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]),

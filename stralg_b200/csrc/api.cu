@@ -5,6 +5,8 @@
 #include <mutex>
 #include <new>
 #include <string.h>
+#include <algorithm>
+#include <vector>
 
 using namespace b200sa;
 
@@ -524,6 +526,139 @@ int b200sa_sa_lookup(const b200sa_index *idx, const uint32_t *rows, uint64_t cou
     return 0;
     API_GUARD_END(nullptr)
 }
+
+// ---- approximate search ------------------------------------------------------------------------
+struct b200sa_approx_result {
+    std::vector<uint64_t> hit_off;   // npat + 1
+    std::vector<uint32_t> L, R, mlen;
+    std::vector<uint64_t> cig_off;   // nhits + 1
+    std::vector<char> cigars;        // NUL-terminated, back to back
+};
+
+b200sa_approx_result *b200sa_approx_batch(const b200sa_index *idx, const b200sa_index *rev_idx,
+                                          const uint8_t *d_table, const uint8_t *patterns, const uint64_t *offsets,
+                                          uint32_t fixed_len, uint64_t npat, int max_edits, enum b200sa_error *err) {
+    if (!idx || (npat && !patterns) || max_edits < 0 || max_edits > 255) {
+        fail(B200SA_ERR_BAD_ARGUMENT, "null argument or max_edits outside 0..255", err);
+        return nullptr;
+    }
+    const DeviceIndex &ix = idx->ix;
+    if (ix.occ_layout == OCC_NONE) {
+        fail(B200SA_ERR_NOT_BUILT, "O table was not requested at build time", err);
+        return nullptr;
+    }
+    if (rev_idx && (rev_idx->ix.occ_layout == OCC_NONE || rev_idx->ix.len != ix.len || rev_idx->ix.sigma != ix.sigma ||
+                    rev_idx->ix.device != ix.device)) {
+        fail(B200SA_ERR_BAD_ARGUMENT, "the reverse index must be an O-table index of the reversed text on the same device", err);
+        return nullptr;
+    }
+    uint64_t total = offsets ? offsets[npat] : (uint64_t)fixed_len * npat;
+    uint32_t max_m = fixed_len;
+    if (offsets) {
+        max_m = 0;
+        for (uint64_t q = 0; q < npat; ++q) {
+            if (offsets[q + 1] < offsets[q]) {
+                fail(B200SA_ERR_BAD_ARGUMENT, "pattern offsets must not decrease", err);
+                return nullptr;
+            }
+            uint64_t m = offsets[q + 1] - offsets[q];
+            if (m > max_m) max_m = (uint32_t)std::min<uint64_t>(m, 0xFFFFFFFFull);
+        }
+    }
+    if (max_m > 65000u) {
+        fail(B200SA_ERR_TOO_LARGE, "approximate search takes patterns of up to 65000 symbols", err);
+        return nullptr;
+    }
+    b200sa_approx_result *res = new (std::nothrow) b200sa_approx_result();
+    if (!res) {
+        fail(B200SA_ERR_OUT_OF_MEMORY, "host allocation failed", err);
+        return nullptr;
+    }
+    try {
+        CUDA_CHECK(cudaSetDevice(ix.device));
+        cudaStream_t st = ix.stream;
+        res->hit_off.assign(npat + 1, 0);
+        res->cig_off.assign(1, 0);
+        if (npat) {
+            DevBuf<u8> dp(total + 16, st), ddt;
+            DevBuf<u64> doff, d_hit_off(npat + 1, st), d_ops_off(npat + 1, st);
+            if (total) CUDA_CHECK(cudaMemcpyAsync(dp.ptr, patterns, total, cudaMemcpyHostToDevice, st));
+            if (offsets) {
+                doff.alloc(npat + 1, st);
+                CUDA_CHECK(cudaMemcpyAsync(doff.ptr, offsets, (npat + 1) * 8, cudaMemcpyHostToDevice, st));
+            }
+            if (d_table) {
+                ddt.alloc(total + 16, st);
+                if (total) CUDA_CHECK(cudaMemcpyAsync(ddt.ptr, d_table, total, cudaMemcpyHostToDevice, st));
+            } else if (rev_idx) {
+                ddt.alloc(total + 16, st);
+                approx_dtable(rev_idx->ix, dp.ptr, doff.ptr, fixed_len, npat, ddt.ptr, st);
+            }
+            u64 hits = 0, ops = 0;
+            approx_count(ix, dp.ptr, doff.ptr, fixed_len, npat, max_m, ddt.ptr, max_edits, d_hit_off.ptr, d_ops_off.ptr,
+                         &hits, &ops, st);
+            CUDA_CHECK(cudaMemcpyAsync(res->hit_off.data(), d_hit_off.ptr, (npat + 1) * 8, cudaMemcpyDeviceToHost, st));
+            res->L.resize(hits);
+            res->R.resize(hits);
+            res->mlen.resize(hits);
+            std::vector<uint64_t> hops(hits + 1, 0);
+            std::vector<char> opbuf(ops + 1, 0);
+            if (hits) {
+                DevBuf<u32> dL(hits, st), dR(hits, st), dM(hits, st);
+                DevBuf<u64> dho(hits, st);
+                DevBuf<char> dops(ops + 1, st);
+                approx_emit(ix, dp.ptr, doff.ptr, fixed_len, npat, max_m, ddt.ptr, max_edits, d_hit_off.ptr, d_ops_off.ptr,
+                            dL.ptr, dR.ptr, dM.ptr, dho.ptr, dops.ptr, st);
+                CUDA_CHECK(cudaMemcpyAsync(res->L.data(), dL.ptr, hits * 4, cudaMemcpyDeviceToHost, st));
+                CUDA_CHECK(cudaMemcpyAsync(res->R.data(), dR.ptr, hits * 4, cudaMemcpyDeviceToHost, st));
+                CUDA_CHECK(cudaMemcpyAsync(res->mlen.data(), dM.ptr, hits * 4, cudaMemcpyDeviceToHost, st));
+                CUDA_CHECK(cudaMemcpyAsync(hops.data(), dho.ptr, hits * 8, cudaMemcpyDeviceToHost, st));
+                CUDA_CHECK(cudaMemcpyAsync(opbuf.data(), dops.ptr, ops, cudaMemcpyDeviceToHost, st));
+            }
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            hops[hits] = ops;
+            // operations -> run-length CIGAR (stralg/cigar.c:8-31), one NUL-terminated string per hit
+            res->cig_off.resize(hits + 1);
+            res->cigars.reserve(ops + hits + 16);
+            for (u64 h = 0; h < hits; ++h) {
+                res->cig_off[h] = res->cigars.size();
+                u64 k = hops[h];
+                const u64 e = hops[h + 1];
+                while (k < e) {
+                    u64 r = k;
+                    while (r < e && opbuf[r] == opbuf[k]) ++r;
+                    char num[24];
+                    int w = snprintf(num, sizeof num, "%llu", (unsigned long long)(r - k));
+                    res->cigars.insert(res->cigars.end(), num, num + w);
+                    res->cigars.push_back(opbuf[k]);
+                    k = r;
+                }
+                res->cigars.push_back('\0');
+            }
+            res->cig_off[hits] = res->cigars.size();
+        }
+        ok(err);
+        return res;
+    } catch (const CudaFailure &e) {
+        cudaGetLastError();
+        fail(code_of(e.code), e.what(), err);
+    } catch (const std::bad_alloc &) {
+        fail(B200SA_ERR_OUT_OF_MEMORY, "host allocation failed", err);
+    } catch (const std::exception &e) {
+        fail(B200SA_ERR_INTERNAL, e.what(), err);
+    }
+    delete res;
+    return nullptr;
+}
+
+uint64_t b200sa_approx_hits(const b200sa_approx_result *r) { return r ? r->L.size() : 0; }
+const uint64_t *b200sa_approx_hit_offsets(const b200sa_approx_result *r) { return r ? r->hit_off.data() : nullptr; }
+const uint32_t *b200sa_approx_L(const b200sa_approx_result *r) { return r ? r->L.data() : nullptr; }
+const uint32_t *b200sa_approx_R(const b200sa_approx_result *r) { return r ? r->R.data() : nullptr; }
+const uint32_t *b200sa_approx_match_length(const b200sa_approx_result *r) { return r ? r->mlen.data() : nullptr; }
+const uint64_t *b200sa_approx_cigar_offsets(const b200sa_approx_result *r) { return r ? r->cig_off.data() : nullptr; }
+const char *b200sa_approx_cigars(const b200sa_approx_result *r) { return r ? r->cigars.data() : nullptr; }
+void b200sa_approx_free(b200sa_approx_result *r) { delete r; }
 
 int b200sa_synth_codes(uint8_t *d_text, uint64_t n, uint32_t nsym, uint64_t seed, int device, void *stream) {
     if (!d_text || nsym < 1 || nsym > 255) return fail(B200SA_ERR_BAD_ARGUMENT, "bad argument", nullptr);

@@ -88,6 +88,15 @@ void fm_locate_fill_ssa(const DeviceIndex &ix, const u32 *d_L, u64 npat, const u
 void sa_lookup_rows(const DeviceIndex &ix, const u32 *d_rows, u64 count, u32 *d_out, bool force_sampled,
                     cudaStream_t st);
 void sort_positions(const DeviceIndex &ix, u64 npat, const u64 *d_pos_off, u64 total, u32 *d_pos, cudaStream_t st);
+// approx.cu
+void approx_dtable(const DeviceIndex &rev, const u8 *d_pat, const u64 *d_off, u32 fixed_len, u64 npat, u8 *d_dtab,
+                   cudaStream_t st);
+void approx_count(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fixed_len, u64 npat, u32 max_m,
+                  const u8 *d_dtab, int max_edits, u64 *d_hit_off, u64 *d_ops_off, u64 *hits, u64 *ops,
+                  cudaStream_t st);
+void approx_emit(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fixed_len, u64 npat, u32 max_m,
+                 const u8 *d_dtab, int max_edits, const u64 *d_hit_off, const u64 *d_ops_off, u32 *d_L, u32 *d_R,
+                 u32 *d_mlen, u64 *d_hit_ops_off, char *d_ops, cudaStream_t st);
 // synth.cu
 void synth_codes(u8 *d_text, u64 n, u32 nsym, u64 seed, cudaStream_t st);
 void synth_reads(const u8 *d_text, u64 n, u32 nsym, u8 *d_reads, u64 nreads, u32 m, u32 miss_per_1024,

@@ -209,6 +209,49 @@ class SuffixArrayIndex:
             check(fn(self._h, _np_ptr(L), _np_ptr(R), npat, _np_ptr(off), _np_ptr(pos), total.value, C.byref(total)))
         return off, pos
 
+    # ---- approximate search (init_bwt_approx_iter / next_bwt_approx_match, bwt.c:226-409) -------
+    def approx_search(self, patterns, offsets=None, fixed_len: int = 0, max_edits: int = 1,
+                      rev: "Optional[SuffixArrayIndex]" = None, d_table=None) -> dict:
+        """All intervals within ``max_edits`` edits, per pattern in the reference's report order.
+        ``rev``: index of the reversed text (the reference's RO table -> D table pruning).
+        Returns dict(offsets[npat+1], L, R, match_length, cigars[list of str])."""
+        lib = _lib.load()
+        pat = np.ascontiguousarray(patterns, dtype=np.uint8)
+        if offsets is not None:
+            off = np.ascontiguousarray(offsets, dtype=np.uint64)
+            npat = len(off) - 1
+            offp = _np_ptr(off)
+        else:
+            assert fixed_len > 0
+            npat = pat.size // fixed_len
+            offp = None
+        dt = None
+        if d_table is not None:
+            dt = np.ascontiguousarray(d_table, dtype=np.uint8)
+            assert dt.size == pat.size
+        err = C.c_int(0)
+        r = lib.b200sa_approx_batch(self._h, rev._h if rev is not None else None, _np_ptr(dt) if dt is not None else None,
+                                    _np_ptr(pat), offp, fixed_len, npat, max_edits, C.byref(err))
+        if not r:
+            raise B200saError(err.value, lib.b200sa_last_error().decode())
+        r = C.c_void_p(r)
+        try:
+            nh = int(lib.b200sa_approx_hits(r))
+            hoff = np.ctypeslib.as_array(lib.b200sa_approx_hit_offsets(r), shape=(npat + 1,)).copy()
+            if nh:
+                L = np.ctypeslib.as_array(lib.b200sa_approx_L(r), shape=(nh,)).copy()
+                R = np.ctypeslib.as_array(lib.b200sa_approx_R(r), shape=(nh,)).copy()
+                ml = np.ctypeslib.as_array(lib.b200sa_approx_match_length(r), shape=(nh,)).copy()
+                coff = np.ctypeslib.as_array(lib.b200sa_approx_cigar_offsets(r), shape=(nh + 1,))
+                raw = C.string_at(lib.b200sa_approx_cigars(r), int(coff[nh]))
+                cig = [x.decode() for x in raw.split(b"\0")[:-1]]
+            else:
+                L = R = ml = np.zeros(0, np.uint32)
+                cig = []
+        finally:
+            lib.b200sa_approx_free(r)
+        return {"offsets": hoff, "L": L, "R": R, "match_length": ml, "cigars": cig}
+
     # ---- sampled suffix array (SURVEY 8f rank 3) -----------------------------------------------
     def sample_sa(self, rate: int = 32, drop_sa: bool = False) -> None:
         """Keep SA only at text positions that are multiples of ``rate``; with ``drop_sa`` the full

@@ -36,6 +36,12 @@ def build_oracle():
     subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True, stdout=subprocess.DEVNULL)
 
 
+class OracleApproxOut(C.Structure):  # struct oracle_approx_out (oracle/stralg_oracle.c)
+    _fields_ = [("nhits", C.c_uint64), ("cap", C.c_uint64), ("L", u32p), ("R", u32p), ("mlen", u32p),
+                ("cig_off", u64p), ("cigars", C.POINTER(C.c_char)), ("cig_bytes", C.c_uint64),
+                ("cig_cap", C.c_uint64)]
+
+
 class OracleRemap(C.Structure):
     _fields_ = [("alphabet_size", C.c_uint32), ("table", C.c_int16 * 256), ("rev", C.c_int16 * 256)]
 
@@ -157,6 +163,39 @@ class Oracle:
                                _p(pos, u32p))
         return off, pos
 
+    # --- approximate search (bwt.c:226-382) ---------------------------------------------
+    def approx(self, c, o, ro, length, pattern, max_edits):
+        """One pattern against dense tables o / ro (ro may be None: no D table).
+        Returns (L, R, match_length, [cigar, ...]) in the order the reference reports intervals."""
+        out = OracleApproxOut()
+        pat = np.ascontiguousarray(pattern, dtype=np.uint8)
+        c = np.ascontiguousarray(c, dtype=np.uint32)
+        o = np.ascontiguousarray(o, dtype=np.uint32)
+        rop = None
+        if ro is not None:
+            ro = np.ascontiguousarray(ro, dtype=np.uint32)
+            rop = _p(ro, u32p)
+        self.lib.oracle_approx_dense(_p(c, u32p), _p(o, u32p), rop, C.c_uint32(o.shape[1]), C.c_uint32(length),
+                                     _p(pat, u8p), C.c_uint32(len(pat)), C.c_int(max_edits), C.byref(out))
+        n = int(out.nhits)
+        L = np.ctypeslib.as_array(out.L, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+        R = np.ctypeslib.as_array(out.R, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+        ml = np.ctypeslib.as_array(out.mlen, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+        raw = C.string_at(out.cigars, int(out.cig_bytes)) if n else b""
+        cig = [x.decode() for x in raw.split(b"\0")[:-1]]
+        self.lib.oracle_approx_free(C.byref(out))
+        assert len(cig) == n
+        return L, R, ml, cig
+
+    def approx_dtable(self, c, ro, length, pattern):
+        pat = np.ascontiguousarray(pattern, dtype=np.uint8)
+        c = np.ascontiguousarray(c, dtype=np.uint32)
+        ro = np.ascontiguousarray(ro, dtype=np.uint32)
+        d = np.zeros(len(pat), dtype=np.int32)
+        self.lib.oracle_approx_dtable(_p(c, u32p), _p(ro, u32p), C.c_uint32(ro.shape[1]), C.c_uint32(length),
+                                      _p(pat, u8p), C.c_uint32(len(pat)), d.ctypes.data_as(C.POINTER(C.c_int)))
+        return d
+
     def random_codes(self, n, nsym=4, seed=0):
         out = np.empty(n + 1, dtype=np.uint8)
         self.lib.oracle_random_codes(_p(out, u8p), C.c_uint64(n), C.c_uint32(nsym), C.c_uint64(seed))
@@ -184,6 +223,26 @@ class RefExactIter(C.Structure):  # stralg/bwt.h:168-173
 
 class RefExactMatch(C.Structure):  # stralg/bwt.h:180-182
     _fields_ = [("pos", C.c_uint32)]
+
+
+class RefIndexVector(C.Structure):  # stralg/vectors.h:29-33
+    _fields_ = [("data", u32p), ("size", C.c_uint32), ("used", C.c_uint32)]
+
+
+class RefStringVector(C.Structure):  # stralg/vectors.h:153-157
+    _fields_ = [("data", C.POINTER(C.c_char_p)), ("size", C.c_uint32), ("used", C.c_uint32)]
+
+
+class RefApproxIter(C.Structure):  # stralg/bwt.h:246-259
+    _fields_ = [("bwt_table", C.POINTER(RefBwtTable)), ("remapped_pattern", u8p),
+                ("L", C.c_uint32), ("R", C.c_uint32), ("next_interval", C.c_uint32),
+                ("Ls", RefIndexVector), ("Rs", RefIndexVector), ("cigars", RefStringVector),
+                ("match_lengths", RefIndexVector), ("m", C.c_uint32), ("edits_buf", C.c_char_p),
+                ("D_table", C.POINTER(C.c_int))]
+
+
+class RefApproxMatch(C.Structure):  # stralg/bwt.h:277-281
+    _fields_ = [("cigar", C.c_char_p), ("position", C.c_uint32), ("match_length", C.c_uint32)]
 
 
 def bind_stralg_api(lib):
@@ -219,6 +278,13 @@ def bind_stralg_api(lib):
     lib.init_bwt_exact_match_iter.restype = None
     lib.next_bwt_exact_match_iter.argtypes = [C.POINTER(RefExactIter), C.POINTER(RefExactMatch)]
     lib.next_bwt_exact_match_iter.restype = C.c_bool
+    if hasattr(lib, "init_bwt_approx_iter"):
+        lib.init_bwt_approx_iter.argtypes = [C.POINTER(RefApproxIter), C.POINTER(RefBwtTable), u8p, C.c_int]
+        lib.init_bwt_approx_iter.restype = None
+        lib.next_bwt_approx_match.argtypes = [C.POINTER(RefApproxIter), C.POINTER(RefApproxMatch)]
+        lib.next_bwt_approx_match.restype = C.c_bool
+        lib.dealloc_bwt_approx_iter.argtypes = [C.POINTER(RefApproxIter)]
+        lib.dealloc_bwt_approx_iter.restype = None
     lib.lower_bound_k.restype = C.c_uint32
     lib.lower_bound_k.argtypes = [sap, C.c_uint32, C.c_uint8, C.c_uint32, C.c_uint32]
     lib.upper_bound_k.restype = C.c_uint32
@@ -265,10 +331,11 @@ class Ref:
         self.lib.free_suffix_array(sa)
         return arr, isa, lcp
 
-    def tables(self, raw: bytes):
-        """build_complete_table (bwt.c:134-161) -> dict(codes, sigma, sa, c, o[(len+1), sigma], handle)."""
+    def tables(self, raw: bytes, include_reverse: bool = False):
+        """build_complete_table (bwt.c:134-161) -> dict(codes, sigma, sa, c, o[(len+1), sigma], handle)
+        (+ ro with include_reverse)."""
         buf = C.create_string_buffer(raw, len(raw) + 1)
-        t = self.lib.build_complete_table(C.cast(buf, u8p), False)
+        t = self.lib.build_complete_table(C.cast(buf, u8p), include_reverse)
         tc = t.contents
         sa = tc.sa.contents
         n1 = sa.length
@@ -282,6 +349,7 @@ class Ref:
             "c": np.ctypeslib.as_array(tc.c_table, shape=(sigma,)).copy(),
             "o": np.ctypeslib.as_array(tc.o_table, shape=(n1 + 1, sigma)).copy(),
             "table": np.array(list(tc.remap_table.contents.table), dtype=np.int16),
+            "ro": np.ctypeslib.as_array(tc.ro_table, shape=(n1 + 1, sigma)).copy() if include_reverse else None,
         }
 
     def exact_matches(self, handle, codes_pattern: np.ndarray):
@@ -295,6 +363,25 @@ class Ref:
         while self.lib.next_bwt_exact_match_iter(C.byref(it), C.byref(m)):
             pos.append(m.pos)
         return L, R, np.array(pos, dtype=np.uint32)
+
+    def approx_matches(self, handle, codes_pattern: np.ndarray, edits: int):
+        """init_bwt_approx_iter / next_bwt_approx_match (bwt.c:302-409): the interval list
+        (L, R, match_length, cigar) in report order, and every (position, cigar, match_length)
+        the iterator yields."""
+        it = RefApproxIter()
+        m = RefApproxMatch()
+        pat = np.concatenate([np.asarray(codes_pattern, dtype=np.uint8), np.zeros(1, np.uint8)])
+        self.lib.init_bwt_approx_iter(C.byref(it), handle, _p(pat, u8p), C.c_int(edits))
+        k = it.Ls.used
+        L = np.array([it.Ls.data[j] for j in range(k)], dtype=np.uint32)
+        R = np.array([it.Rs.data[j] for j in range(k)], dtype=np.uint32)
+        ml = np.array([it.match_lengths.data[j] for j in range(k)], dtype=np.uint32)
+        cig = [it.cigars.data[j].decode() for j in range(k)]
+        hits = []
+        while self.lib.next_bwt_approx_match(C.byref(it), C.byref(m)):
+            hits.append((int(m.position), m.cigar.decode(), int(m.match_length)))
+        self.lib.dealloc_bwt_approx_iter(C.byref(it))
+        return L, R, ml, cig, hits
 
     def free_tables(self, handle):
         self.lib.completely_free_bwt_table(handle)
