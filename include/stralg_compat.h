@@ -132,6 +132,42 @@ void dealloc_bwt_exact_match_iter(struct bwt_exact_match_iter *iter);
 void bwt_exact_match_batch(struct bwt_table *bwt_table, const uint8_t *remapped_patterns,
                            const uint64_t *offsets, uint64_t npatterns, uint32_t *L, uint32_t *R);
 
+/* bwt.h:246-333 -- approximate-match iterator.  Layouts are the reference's
+ * (vectors.h:29-33, 153-157; bwt.h:246-259, 277-281); callers stack-allocate the iterator.
+ * init runs the whole D-table-pruned search (bwt.c:226-382) on the GPU and fills Ls / Rs /
+ * match_lengths / cigars in the reference's report order; next walks them (bwt.c:384-401). */
+struct index_vector {
+    uint32_t *data;
+    uint32_t size;
+    uint32_t used;
+};
+struct string_vector {
+    uint8_t **data;
+    uint32_t size;
+    uint32_t used;
+};
+struct bwt_approx_iter {
+    struct bwt_table *bwt_table;
+    const uint8_t *remapped_pattern;
+    uint32_t L, R, next_interval;
+    struct index_vector Ls;
+    struct index_vector Rs;
+    struct string_vector cigars;
+    struct index_vector match_lengths;
+    uint32_t m;
+    char *edits_buf;
+    int *D_table;
+};
+struct bwt_approx_match {
+    const char *cigar;
+    uint32_t position;
+    uint32_t match_length;
+};
+void init_bwt_approx_iter(struct bwt_approx_iter *iter, struct bwt_table *bwt_table,
+                          const uint8_t *remapped_pattern, int edits);             /* bwt.h:290-295 */
+bool next_bwt_approx_match(struct bwt_approx_iter *iter, struct bwt_approx_match *match); /* :311-314 */
+void dealloc_bwt_approx_iter(struct bwt_approx_iter *iter);                        /* :329-331 */
+
 /* ---- index files: the reference's own on-disk layouts, byte for byte ----------
  * Raw host-endian dumps without header (suffix_array.c:238-267, remap.c:168-201, bwt.c:425-503,
  * serialise.c:7-49, string_utils.c:48-82).  A file written by either library is read by the other.
@@ -167,6 +203,12 @@ struct bwt_table *read_complete_bwt_info_fname(const char *fname);              
  * reference tool's.  Returns the number of SAM lines written. */
 uint64_t bwt_map_fastq_exact(FILE *fastq, FILE *samfile, uint32_t nrecords, const char *const *record_names,
                              struct bwt_table *const *tables, uint64_t batch_reads);
+/* `bwt_readmapper -d <edits>` for any edit distance: the approximate search of every batch runs as
+ * one GPU call per reference record (b200sa_approx_batch, D table from the table's RO rows when it
+ * has them, bwt.c:319-337), SAM lines in the tool's order (reads, records, intervals in report
+ * order, positions in suffix-array order) with the tool's CIGARs.  Byte-identical to the tool. */
+uint64_t bwt_map_fastq(FILE *fastq, FILE *samfile, uint32_t nrecords, const char *const *record_names,
+                       struct bwt_table *const *tables, int edits, uint64_t batch_reads);
 /* The multi-record index file of `bwt_readmapper -p` (bwt_readmapper.c:48-61): [u32 records], then per
  * record [u32 len][name incl. NUL] (string_utils.c:48-65) + write_complete_bwt_info.  The tool writes
  * the FASTA records in REVERSE file order (bioinf/fasta.c:131 prepends) and maps in the reverse of

@@ -428,6 +428,104 @@ bool next_bwt_exact_match_iter(struct bwt_exact_match_iter *iter, struct bwt_exa
 void dealloc_bwt_exact_match_iter(struct bwt_exact_match_iter *) {}
 
 // ------------------------------------------------------------------------------------------------
+// approximate search (bwt.c:226-409): the recursion runs on the GPU for a whole batch of patterns
+// ------------------------------------------------------------------------------------------------
+namespace {
+// D table from the dense RO rows (bwt.c:319-337), one byte per pattern symbol
+void host_d_table(const struct bwt_table *tbl, const uint8_t *pat, uint64_t m, uint8_t *out) {
+    const uint32_t sigma = tbl->remap_table->alphabet_size, len = tbl->sa->length;
+    uint32_t L = 0, R = len, need = 0;
+    for (uint64_t i = 0; i < m; ++i) {
+        const uint8_t a = pat[i];
+        if (a == 0 || a >= sigma) {
+            L = 1;
+            R = 0;
+        } else {
+            L = tbl->c_table[a] + tbl->ro_indices[L][a];
+            R = tbl->c_table[a] + tbl->ro_indices[R][a];
+        }
+        if (L >= R) {
+            ++need;
+            L = 0;
+            R = len;
+        }
+        out[i] = (uint8_t)(need > 255 ? 255 : need);
+    }
+}
+
+b200sa_approx_result *approx_batch(struct bwt_table *tbl, const uint8_t *patterns, const uint64_t *offsets,
+                                   uint64_t npatterns, int edits, const char *who) {
+    b200sa_index *idx = index_of(tbl->sa, tbl->remap_table->alphabet_size, true);
+    if (b200sa_extend(idx, tbl->sa->string, B200SA_BUILD_OCC)) die(who);
+    std::vector<uint8_t> dt;
+    if (tbl->ro_indices) {
+        dt.resize(offsets[npatterns] + 1);
+        for (uint64_t q = 0; q < npatterns; ++q)
+            host_d_table(tbl, patterns + offsets[q], offsets[q + 1] - offsets[q], dt.data() + offsets[q]);
+    }
+    enum b200sa_error err;
+    b200sa_approx_result *r = b200sa_approx_batch(idx, nullptr, tbl->ro_indices ? dt.data() : nullptr, patterns, offsets,
+                                                  0, npatterns, edits, &err);
+    if (!r) die(who);
+    return r;
+}
+}  // namespace
+
+void init_bwt_approx_iter(struct bwt_approx_iter *iter, struct bwt_table *tbl, const uint8_t *remapped_pattern,
+                          int edits) {
+    const uint64_t m = strlen((const char *)remapped_pattern);
+    const uint64_t off[2] = {0, m};
+    b200sa_approx_result *r = approx_batch(tbl, remapped_pattern, off, 1, edits < 0 ? 0 : edits, "init_bwt_approx_iter");
+    const uint64_t k = edits < 0 ? 0 : b200sa_approx_hits(r);
+    iter->bwt_table = tbl;
+    iter->remapped_pattern = remapped_pattern;
+    iter->m = (uint32_t)m;
+    iter->edits_buf = nullptr;
+    iter->D_table = nullptr;
+    struct index_vector *vecs[3] = {&iter->Ls, &iter->Rs, &iter->match_lengths};
+    const uint32_t *src[3] = {b200sa_approx_L(r), b200sa_approx_R(r), b200sa_approx_match_length(r)};
+    for (int v = 0; v < 3; ++v) {
+        vecs[v]->data = (uint32_t *)malloc((k ? k : 1) * sizeof(uint32_t));
+        vecs[v]->size = (uint32_t)(k ? k : 1);
+        vecs[v]->used = (uint32_t)k;
+        if (k) memcpy(vecs[v]->data, src[v], k * sizeof(uint32_t));
+    }
+    iter->cigars.data = (uint8_t **)malloc((k ? k : 1) * sizeof(uint8_t *));
+    iter->cigars.size = (uint32_t)(k ? k : 1);
+    iter->cigars.used = (uint32_t)k;
+    const uint64_t *coff = b200sa_approx_cigar_offsets(r);
+    const char *cig = b200sa_approx_cigars(r);
+    for (uint64_t h = 0; h < k; ++h) iter->cigars.data[h] = (uint8_t *)strdup(cig + coff[h]);
+    b200sa_approx_free(r);
+    iter->L = (uint32_t)m;  // bwt.c:379-381: start before the first interval
+    iter->R = 0;
+    iter->next_interval = 0;
+}
+
+bool next_bwt_approx_match(struct bwt_approx_iter *iter, struct bwt_approx_match *match) {
+    if (iter->L >= iter->R) {
+        if (iter->next_interval >= iter->Ls.used) return false;
+        iter->L = iter->Ls.data[iter->next_interval];
+        iter->R = iter->Rs.data[iter->next_interval];
+        iter->next_interval++;
+    }
+    match->cigar = (const char *)iter->cigars.data[iter->next_interval - 1];
+    match->match_length = iter->match_lengths.data[iter->next_interval - 1];
+    match->position = iter->bwt_table->sa->array[iter->L++];
+    return true;
+}
+
+void dealloc_bwt_approx_iter(struct bwt_approx_iter *iter) {
+    free(iter->Ls.data);
+    free(iter->Rs.data);
+    free(iter->match_lengths.data);
+    for (uint32_t h = 0; h < iter->cigars.used; ++h) free(iter->cigars.data[h]);
+    free(iter->cigars.data);
+    free(iter->edits_buf);
+    free(iter->D_table);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Index files: the reference's raw layouts (no header, host endianness).  Host-side I/O only; a
 // structure read from a file has no device index yet -- index_of() rebuilds it from the string
 // the first time the GPU is needed, which yields the same arrays by uniqueness.
@@ -588,7 +686,15 @@ bool fastq_line(FILE *f, char *buf, std::string *out, int skip) {
 
 uint64_t bwt_map_fastq_exact(FILE *fastq, FILE *samfile, uint32_t nrecords, const char *const *record_names,
                              struct bwt_table *const *tables, uint64_t batch_reads) {
-    if (batch_reads == 0) batch_reads = 1u << 20;
+    return bwt_map_fastq(fastq, samfile, nrecords, record_names, tables, 0, batch_reads);
+}
+
+uint64_t bwt_map_fastq(FILE *fastq, FILE *samfile, uint32_t nrecords, const char *const *record_names,
+                       struct bwt_table *const *tables, int edits, uint64_t batch_reads) {
+    if (batch_reads == 0) batch_reads = edits > 0 ? 1u << 16 : 1u << 20;
+    // per record and read: the read's intervals are hits [hit_lo, hit_hi) of that record's result
+    std::vector<b200sa_approx_result *> results(nrecords, nullptr);
+    std::vector<std::vector<uint64_t>> hit_lo(nrecords), hit_hi(nrecords);
     std::vector<char> line(kFastqLine + 1);
     std::vector<std::string> names, seqs, quals;
     std::vector<uint8_t> pat;
@@ -636,6 +742,17 @@ uint64_t bwt_map_fastq_exact(FILE *fastq, FILE *samfile, uint32_t nrecords, cons
                 which.push_back((uint32_t)q);
             }
             if (which.empty()) continue;
+            if (edits > 0) {
+                results[r] = approx_batch(tables[r], pat.data(), off.data(), which.size(), edits, "bwt_map_fastq");
+                const uint64_t *ho = b200sa_approx_hit_offsets(results[r]);
+                hit_lo[r].assign(nreads, 0);
+                hit_hi[r].assign(nreads, 0);
+                for (size_t k = 0; k < which.size(); ++k) {
+                    hit_lo[r][which[k]] = ho[k];
+                    hit_hi[r][which[k]] = ho[k + 1];
+                }
+                continue;
+            }
             std::vector<uint32_t> L(which.size()), R(which.size());
             bwt_exact_match_batch(tables[r], pat.data(), off.data(), which.size(), L.data(), R.data());
             for (size_t k = 0; k < which.size(); ++k) {
@@ -647,12 +764,29 @@ uint64_t bwt_map_fastq_exact(FILE *fastq, FILE *samfile, uint32_t nrecords, cons
         for (size_t q = 0; q < nreads; ++q)
             for (uint32_t r = 0; r < nrecords; ++r) {
                 const uint32_t *sa = tables[r]->sa->array;
+                if (edits > 0) {
+                    if (!results[r]) continue;
+                    const uint32_t *aL = b200sa_approx_L(results[r]), *aR = b200sa_approx_R(results[r]);
+                    const uint64_t *coff = b200sa_approx_cigar_offsets(results[r]);
+                    const char *cig = b200sa_approx_cigars(results[r]);
+                    for (uint64_t h = hit_lo[r][q]; h < hit_hi[r][q]; ++h)
+                        for (uint32_t i = aL[h]; i < aR[h]; ++i) {
+                            fprintf(samfile, "%s\t0\t%s\t%u\t0\t%s\t*\t0\t0\t%s\t%s\n", names[q].c_str(),
+                                    record_names[r], sa[i] + 1, cig + coff[h], seqs[q].c_str(), quals[q].c_str());
+                            ++lines;
+                        }
+                    continue;
+                }
                 for (uint32_t i = Ls[r][q]; i < Rs[r][q]; ++i) {
                     fprintf(samfile, "%s\t0\t%s\t%u\t0\t%zuM\t*\t0\t0\t%s\t%s\n", names[q].c_str(), record_names[r],
                             sa[i] + 1, seqs[q].size(), seqs[q].c_str(), quals[q].c_str());
                     ++lines;
                 }
             }
+        for (uint32_t r = 0; r < nrecords; ++r) {
+            b200sa_approx_free(results[r]);
+            results[r] = nullptr;
+        }
     }
     return lines;
 }

@@ -6,7 +6,7 @@ Run in the build container only (needs /root/reference and gcc):
 The reference's `bwt_readmapper` (tools/readmappers/bwt_readmapper/bwt_readmapper.c) is compiled
 from the sources where they lie into a scratch directory, run with `-p` on a seeded synthetic
 two-record FASTA and with `-d 0` on a seeded FASTQ (exact matching through its approximate
-iterator with zero edits, bwt_readmapper.c:128-161).  Committed: the two input files, the SAM
+iterator with zero edits, bwt_readmapper.c:128-161), then with `-d 1` / `-d 2` on the longer reads.  Committed: the two input files, the SAM
 output, and the sha256 + size of the `.bwttables` file `-p` wrote (the file itself is 0.5 MB).
 """
 import hashlib
@@ -70,10 +70,25 @@ def main():
     sam = subprocess.run([exe, "-d", "0", work, fastq], check=True, stderr=subprocess.DEVNULL,
                          stdout=subprocess.PIPE).stdout
     open(os.path.join(OUT, "expected.sam"), "wb").write(sam)
+    # approximate matching (edit distance 1 and 2) on the reads of at least 16 / 24 symbols: the
+    # tool's D-table-pruned recursion, every (position, CIGAR) in its report order
+    approx = {}
+    lines = open(fastq).read().split("\n")
+    for d, minlen in ((1, 16), (2, 24)):
+        sub = os.path.join(OUT, f"reads_d{d}.fq")
+        with open(sub, "w") as f:
+            for k in range(0, len(lines) - 3, 4):
+                if len(lines[k + 1]) >= minlen:
+                    f.write("\n".join(lines[k:k + 4]) + "\n")
+        out = subprocess.run([exe, "-d", str(d), work, sub], check=True, stderr=subprocess.DEVNULL,
+                             stdout=subprocess.PIPE).stdout
+        open(os.path.join(OUT, f"expected_d{d}.sam"), "wb").write(out)
+        approx[f"d{d}_sam_lines"] = out.count(b"\n")
     tables = open(work + ".bwttables", "rb").read()
     json.dump({"bwttables_sha256": hashlib.sha256(tables).hexdigest(), "bwttables_bytes": len(tables),
-               "sam_lines": sam.count(b"\n"),
-               "command": "bwt_readmapper -p ref.fa; bwt_readmapper -d 0 ref.fa reads.fq"},
+               "sam_lines": sam.count(b"\n"), **approx,
+               "command": "bwt_readmapper -p ref.fa; bwt_readmapper -d 0 ref.fa reads.fq; "
+                          "bwt_readmapper -d 1 ref.fa reads_d1.fq; bwt_readmapper -d 2 ref.fa reads_d2.fq"},
               open(os.path.join(OUT, "meta.json"), "w"), indent=1)
     print(f"{sam.count(10)} SAM lines, .bwttables {len(tables)} bytes")
     shutil.rmtree(tmp)

@@ -13,7 +13,7 @@ from conftest import ROOT
 def declared_symbols():
     text = open(os.path.join(ROOT, "include", "b200sa.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(b200sa_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(b200sa_[A-Za-z0-9_]+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol():

@@ -73,6 +73,9 @@ def bind_mapper(lib):
     lib.bwt_map_fastq_exact.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p),
                                         C.POINTER(C.POINTER(RefBwtTable)), C.c_uint64]
     lib.bwt_map_fastq_exact.restype = C.c_uint64
+    lib.bwt_map_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p),
+                                  C.POINTER(C.POINTER(RefBwtTable)), C.c_int, C.c_uint64]
+    lib.bwt_map_fastq.restype = C.c_uint64
     lib.write_bwt_tables_file.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p),
                                           C.POINTER(C.POINTER(RefBwtTable))]
     lib.write_bwt_tables_file.restype = None
@@ -451,6 +454,74 @@ def test_readmapper_exact_matches_reference_tool(compat, engine, tmp_path, batch
     assert open(out_path, "rb").read() == open(os.path.join(gdir, "expected.sam"), "rb").read()
     for i in range(nrec):
         compat.completely_free_bwt_table(rtabs[i])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("edits,batch_reads", [(1, 0), (1, 5), (2, 0)])
+def test_readmapper_approx_matches_reference_tool(compat, engine, tmp_path, edits, batch_reads):
+    """SURVEY 8f rank 4 end to end: `bwt_readmapper -d 1` / `-d 2` (map_read, bwt_readmapper.c:128-161,
+    through init_bwt_approx_iter / next_bwt_approx_match) against the SAM files the reference tool wrote:
+    every (read, record, position, CIGAR) line, in the tool's order, byte for byte."""
+    import json
+    gdir = os.path.join(ROOT, "tests", "golden", "readmapper")
+    meta = json.load(open(os.path.join(gdir, "meta.json")))
+    bind_mapper(compat)
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    recs = read_fasta(os.path.join(gdir, "ref.fa"))
+    # the tool maps against the records in FASTA order (two prepends cancel, bwt_readmapper.c:48-61, 107)
+    tbls = [compat.build_complete_table(C.cast(cbuf(seq.encode()), u8p), True) for _, seq in recs]
+    names = (C.c_char_p * len(recs))(*[n.encode() for n, _ in recs])
+    tarr = (C.POINTER(RefBwtTable) * len(recs))(*tbls)
+    fq = libc.fopen(os.path.join(gdir, f"reads_d{edits}.fq").encode(), b"r")
+    out_path = str(tmp_path / "out.sam").encode()
+    out = libc.fopen(out_path, b"w")
+    nlines = compat.bwt_map_fastq(fq, out, len(recs), names, tarr, edits, batch_reads)
+    libc.fclose(fq)
+    libc.fclose(out)
+    assert nlines == meta[f"d{edits}_sam_lines"]
+    assert open(out_path, "rb").read() == open(os.path.join(gdir, f"expected_d{edits}.sam"), "rb").read()
+    for t in tbls:
+        compat.completely_free_bwt_table(t)
+
+
+@pytest.mark.gpu
+def test_compat_approx_iterator_matches_reference(compat, engine, ref):
+    """init_bwt_approx_iter / next_bwt_approx_match / dealloc_bwt_approx_iter with the reference's struct
+    layouts: same (position, cigar, match_length) sequence as the unmodified reference on mississippi
+    (the string of tests/stralg/bwt_test.c) and a random DNA text, with and without the RO table."""
+    from _oracle import RefApproxIter, RefApproxMatch
+    if ref is None:
+        pytest.skip("oracle/_ref/libstralg_ref.so did not travel with this snapshot")
+    compat.init_bwt_approx_iter.argtypes = [C.POINTER(RefApproxIter), C.POINTER(RefBwtTable), u8p, C.c_int]
+    compat.init_bwt_approx_iter.restype = None
+    compat.next_bwt_approx_match.argtypes = [C.POINTER(RefApproxIter), C.POINTER(RefApproxMatch)]
+    compat.next_bwt_approx_match.restype = C.c_bool
+    compat.dealloc_bwt_approx_iter.argtypes = [C.POINTER(RefApproxIter)]
+    compat.dealloc_bwt_approx_iter.restype = None
+    rng = np.random.default_rng(5)
+    for raw in (b"mississippi", bytes(rng.choice(list(b"acgt"), 900).tolist())):
+        for with_ro in (True, False):
+            tbl = compat.build_complete_table(C.cast(cbuf(raw), u8p), with_ro)
+            rt = ref.tables(raw, include_reverse=with_ro)
+            pats = [b"ssi", b"is", b"mississippi", b"ppi"] if raw == b"mississippi" else \
+                   [raw[s:s + m] for s, m in ((0, 5), (100, 9), (500, 12), (880, 7))]
+            for p in pats:
+                pm = C.create_string_buffer(len(p) + 1)
+                assert compat.remap(C.cast(pm, u8p), C.cast(cbuf(p), u8p), tbl.contents.remap_table)
+                codes = np.frombuffer(pm.raw[:len(p)], dtype=np.uint8)
+                for d in (0, 1, 2):
+                    it, m = RefApproxIter(), RefApproxMatch()
+                    compat.init_bwt_approx_iter(C.byref(it), tbl, C.cast(pm, u8p), d)
+                    got = []
+                    while compat.next_bwt_approx_match(C.byref(it), C.byref(m)):
+                        got.append((int(m.position), m.cigar.decode(), int(m.match_length)))
+                    compat.dealloc_bwt_approx_iter(C.byref(it))
+                    assert got == ref.approx_matches(rt["handle"], codes, d)[4], (raw[:12], p, d, with_ro)
+            ref.free_tables(rt["handle"])
+            compat.completely_free_bwt_table(tbl)
 
 
 @pytest.mark.gpu
