@@ -167,6 +167,17 @@ int b200sa_sample_sa(b200sa_index *idx, uint32_t rate, int drop_sa);
 int b200sa_sa_lookup(const b200sa_index *idx, const uint32_t *rows, uint64_t count, uint32_t *out,
                      int force_sampled);
 
+/* ---- native index file (large n) --------------------------------------------
+ * The reference's own files (write_complete_bwt_info, serialise.c:7-49; served by the shim) hold the
+ * dense O table and u32 element counts (bwt.c:430) and cannot represent a 3 Gbp index.  This
+ * format stores what is resident in HBM: a fixed header (magic "B200SAIX", version, byte-order
+ * mark, n, sigma, primary, C table, O layout) followed by tagged sections {tag[8], element bytes,
+ * count, raw array}: SA, ISA, LCP, BWT, OCC (sampled O blocks), TEXT (packed text), KTABLE,
+ * SSAMARK / SSAVAL (sampled suffix array).  b200sa_load returns an index that answers search /
+ * locate / approximate search exactly like the one that was saved, without rebuilding. */
+int b200sa_save(const b200sa_index *idx, const char *path);
+b200sa_index *b200sa_load(const char *path, int device, void *stream, enum b200sa_error *err);
+
 /* ---- batched approximate search -------------------------------------------
  * Replaces init_bwt_approx_iter / next_bwt_approx_match (bwt.h:246-333, bwt.c:226-409): all
  * intervals whose suffixes match the pattern within `max_edits` edits (substitutions, insertions,

@@ -84,6 +84,8 @@ SIGNATURES = {
                                                C.c_void_p]),
     "b200sa_sample_sa": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int]),
     "b200sa_sa_lookup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]),
+    "b200sa_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "b200sa_load": (C.c_void_p, [C.c_char_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "b200sa_approx_batch": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                          C.c_uint64, C.c_int, C.POINTER(C.c_int)]),
     "b200sa_approx_hits": (C.c_uint64, [C.c_void_p]),

@@ -76,6 +76,73 @@ static void use_device(int device) {
     }
 }
 
+// ---- native index file ---------------------------------------------------------------------------
+// [header][section]*: the header carries the scalars, every section is {tag, element size, count}
+// + the raw device array, padded to 8 bytes.  Host-endian like the reference's own dumps
+// (suffix_array.c:238-241); `endian` lets a reader on the other byte order refuse the file.
+namespace {
+struct IndexFileHeader {
+    char magic[8];          // "B200SAIX"
+    uint32_t version;       // 1
+    uint32_t endian;        // 0x01020304 as written by the producer
+    uint64_t n;
+    uint32_t sigma, primary;
+    uint32_t occ_layout, occ_block_bytes;
+    uint64_t occ_blocks;
+    uint32_t ktable_k, ssa_rate;
+    uint32_t flags, nsections;
+    uint32_t pack_bits, reserved;
+    uint32_t c_table[256];
+    uint64_t sym_counts[256];
+    BuildStats stats;
+};
+struct SectionHeader {
+    char tag[8];
+    uint64_t elem_bytes, count;
+};
+const size_t kIoChunk = (size_t)64 << 20;
+
+struct Section {
+    const char *tag;
+    const void *dptr;
+    size_t elem, count;
+};
+
+void write_section(FILE *f, const Section &sc, std::vector<char> &buf, cudaStream_t st) {
+    SectionHeader sh{};
+    strncpy(sh.tag, sc.tag, 8);
+    sh.elem_bytes = sc.elem;
+    sh.count = sc.count;
+    if (fwrite(&sh, sizeof sh, 1, f) != 1) throw std::runtime_error("index file: short write");
+    const size_t bytes = sc.elem * sc.count;
+    for (size_t at = 0; at < bytes; at += kIoChunk) {
+        const size_t k = std::min(kIoChunk, bytes - at);
+        CUDA_CHECK(cudaMemcpyAsync(buf.data(), (const char *)sc.dptr + at, k, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (fwrite(buf.data(), 1, k, f) != k) throw std::runtime_error("index file: short write");
+    }
+    const char zeros[8] = {0};
+    if (bytes % 8 && fwrite(zeros, 1, 8 - bytes % 8, f) != 8 - bytes % 8) throw std::runtime_error("index file: short write");
+}
+
+template <typename T>
+void read_section(FILE *f, const SectionHeader &sh, DevBuf<T> &dst, size_t expect_count, std::vector<char> &buf,
+                  cudaStream_t st) {
+    if (sh.elem_bytes != sizeof(T) || sh.count != expect_count)
+        throw std::runtime_error(std::string("index file: section ") + std::string(sh.tag, strnlen(sh.tag, 8)) +
+                                 " has an unexpected shape");
+    dst.alloc(sh.count, st);
+    const size_t bytes = sh.elem_bytes * sh.count;
+    for (size_t at = 0; at < bytes; at += kIoChunk) {
+        const size_t k = std::min(kIoChunk, bytes - at);
+        if (fread(buf.data(), 1, k, f) != k) throw std::runtime_error("index file: truncated section");
+        CUDA_CHECK(cudaMemcpyAsync((char *)dst.ptr + at, buf.data(), k, cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    if (bytes % 8 && fseek(f, (long)(8 - bytes % 8), SEEK_CUR) != 0) throw std::runtime_error("index file: truncated section");
+}
+}  // namespace
+
 static bool can_locate(const b200sa_index *idx) {
     return idx->ix.sa.ptr || (idx->ix.ssa_rate && idx->ix.occ_layout != OCC_NONE);
 }
@@ -452,7 +519,7 @@ int b200sa_sort_positions_device(const b200sa_index *idx, uint64_t npat, const u
     API_GUARD_END(nullptr)
 }
 
-__attribute__((visibility("hidden"))) static int locate_batch_impl(const b200sa_index *idx, const uint32_t *L, const uint32_t *R, uint64_t npat,
+static int locate_batch_impl(const b200sa_index *idx, const uint32_t *L, const uint32_t *R, uint64_t npat,
                         uint64_t *pos_off, uint32_t *pos, uint64_t pos_capacity, uint64_t *total, bool sorted) {
     if (!idx || !pos_off || (npat && (!L || !R))) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
     if (!can_locate(idx)) return fail(B200SA_ERR_NOT_BUILT, "no suffix array to locate with (dropped and not sampled)", nullptr);
@@ -525,6 +592,164 @@ int b200sa_sa_lookup(const b200sa_index *idx, const uint32_t *rows, uint64_t cou
     CUDA_CHECK(cudaStreamSynchronize(st));
     return 0;
     API_GUARD_END(nullptr)
+}
+
+// ---- native index file: b200sa_save / b200sa_load (layout above, next to the helpers) ----
+
+int b200sa_save(const b200sa_index *idx, const char *path) {
+    if (!idx || !path) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    const DeviceIndex &ix = idx->ix;
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(B200SA_ERR_BAD_ARGUMENT, std::string("cannot open ") + path + " for writing", nullptr);
+    try {
+        CUDA_CHECK(cudaSetDevice(ix.device));
+        cudaStream_t st = ix.stream;
+        const size_t words = ((size_t)ix.len + ix.pk.cpw - 1) / ix.pk.cpw + 4;
+        std::vector<Section> secs;
+        if (ix.sa.ptr) secs.push_back({"SA", ix.sa.ptr, 4, ix.len});
+        if (ix.isa.ptr) secs.push_back({"ISA", ix.isa.ptr, 4, ix.len});
+        if (ix.lcp.ptr) secs.push_back({"LCP", ix.lcp.ptr, 4, ix.len});
+        if (ix.bwt.ptr) secs.push_back({"BWT", ix.bwt.ptr, 1, ix.bwt.count});
+        if (ix.occ.ptr) secs.push_back({"OCC", ix.occ.ptr, 1, ix.occ.count});
+        if (ix.text_packed.ptr) secs.push_back({"TEXT", ix.text_packed.ptr, 8, words});
+        if (ix.ktable.ptr) secs.push_back({"KTABLE", ix.ktable.ptr, 8, ix.ktable.count});
+        if (ix.ssa_rate) {
+            secs.push_back({"SSAMARK", ix.ssa_marks.ptr, 16, ix.ssa_marks.count});
+            secs.push_back({"SSAVAL", ix.ssa_vals.ptr, 4, ix.ssa_vals.count});
+        }
+        IndexFileHeader h{};
+        memcpy(h.magic, "B200SAIX", 8);
+        h.version = 1;
+        h.endian = 0x01020304u;
+        h.n = ix.n;
+        h.sigma = ix.sigma;
+        h.primary = ix.primary;
+        h.occ_layout = (uint32_t)ix.occ_layout;
+        h.occ_block_bytes = ix.occ_block_bytes;
+        h.occ_blocks = ix.occ_blocks;
+        h.ktable_k = (uint32_t)ix.ktable_k;
+        h.ssa_rate = ix.ssa_rate;
+        h.flags = idx->flags & (B200SA_BUILD_ISA | B200SA_BUILD_LCP | B200SA_BUILD_BWT | B200SA_BUILD_OCC |
+                                B200SA_BUILD_TEXTCMP | B200SA_BUILD_KTABLE | B200SA_DROP_SA);
+        h.nsections = (uint32_t)secs.size();
+        h.pack_bits = (uint32_t)ix.pk.bits;
+        memcpy(h.c_table, ix.c_host, sizeof h.c_table);
+        memcpy(h.sym_counts, ix.sym_counts_host, sizeof h.sym_counts);
+        h.stats = ix.stats;
+        if (fwrite(&h, sizeof h, 1, f) != 1) throw std::runtime_error("index file: short write");
+        std::vector<char> buf(kIoChunk);
+        for (const Section &sc : secs) write_section(f, sc, buf, st);
+        if (fclose(f) != 0) {
+            f = nullptr;
+            throw std::runtime_error("index file: close failed");
+        }
+        return 0;
+    } catch (const CudaFailure &e) {
+        if (f) fclose(f);
+        cudaGetLastError();
+        return fail(code_of(e.code), e.what(), nullptr);
+    } catch (const std::bad_alloc &) {
+        if (f) fclose(f);
+        return fail(B200SA_ERR_OUT_OF_MEMORY, "host allocation failed", nullptr);
+    } catch (const std::exception &e) {
+        if (f) fclose(f);
+        return fail(B200SA_ERR_INTERNAL, e.what(), nullptr);
+    }
+}
+
+b200sa_index *b200sa_load(const char *path, int device, void *stream, enum b200sa_error *err) {
+    if (!path) {
+        fail(B200SA_ERR_BAD_ARGUMENT, "null path", err);
+        return nullptr;
+    }
+    FILE *f = fopen(path, "rb");
+    if (!f) {
+        fail(B200SA_ERR_BAD_ARGUMENT, std::string("cannot open ") + path, err);
+        return nullptr;
+    }
+    b200sa_index *h = new (std::nothrow) b200sa_index();
+    if (!h) {
+        fclose(f);
+        fail(B200SA_ERR_OUT_OF_MEMORY, "host allocation failed", err);
+        return nullptr;
+    }
+    try {
+        use_device(device);
+        IndexFileHeader fh;
+        if (fread(&fh, sizeof fh, 1, f) != 1 || memcmp(fh.magic, "B200SAIX", 8) != 0)
+            throw std::invalid_argument("not a b200sa index file");
+        if (fh.endian != 0x01020304u) throw std::invalid_argument("index file was written on the other byte order");
+        if (fh.version != 1) throw std::invalid_argument("unsupported index file version");
+        if (fh.n > 0xFFFFFFFEull || fh.sigma < 1 || fh.sigma > 256 || fh.primary > fh.n)
+            throw std::invalid_argument("index file header is inconsistent");
+        DeviceIndex &ix = h->ix;
+        cudaStream_t st = (cudaStream_t)stream;
+        ix.stream = st;
+        ix.device = device;
+        ix.n = (u32)fh.n;
+        ix.len = ix.n + 1;
+        ix.sigma = fh.sigma;
+        ix.pk = packing_for_sigma(fh.sigma);
+        if ((uint32_t)ix.pk.bits != fh.pack_bits) throw std::invalid_argument("index file header is inconsistent");
+        ix.primary = fh.primary;
+        ix.occ_layout = (OccLayout)fh.occ_layout;
+        ix.occ_block_bytes = fh.occ_block_bytes;
+        ix.occ_blocks = fh.occ_blocks;
+        ix.ktable_k = (int)fh.ktable_k;
+        ix.stats = fh.stats;
+        h->flags = fh.flags;
+        memcpy(ix.c_host, fh.c_table, sizeof fh.c_table);
+        memcpy(ix.sym_counts_host, fh.sym_counts, sizeof fh.sym_counts);
+        ix.c_table.alloc(ix.sigma, st);
+        CUDA_CHECK(cudaMemcpyAsync(ix.c_table.ptr, ix.c_host, (size_t)ix.sigma * 4, cudaMemcpyHostToDevice, st));
+        const size_t words = ((size_t)ix.len + ix.pk.cpw - 1) / ix.pk.cpw + 4;
+        const size_t bwt_bytes = (((size_t)ix.len + 63) / 64 + 1) * 64;
+        std::vector<char> buf(kIoChunk);
+        bool have_occ = false, have_marks = false, have_vals = false;
+        for (uint32_t k = 0; k < fh.nsections; ++k) {
+            SectionHeader sh;
+            if (fread(&sh, sizeof sh, 1, f) != 1) throw std::invalid_argument("index file: truncated");
+            const std::string tag(sh.tag, strnlen(sh.tag, 8));
+            if (tag == "SA") read_section(f, sh, ix.sa, ix.len, buf, st);
+            else if (tag == "ISA") read_section(f, sh, ix.isa, ix.len, buf, st);
+            else if (tag == "LCP") read_section(f, sh, ix.lcp, ix.len, buf, st);
+            else if (tag == "BWT") read_section(f, sh, ix.bwt, bwt_bytes, buf, st);
+            else if (tag == "OCC") {
+                read_section(f, sh, ix.occ, (size_t)fh.occ_blocks * fh.occ_block_bytes, buf, st);
+                have_occ = true;
+            } else if (tag == "TEXT") read_section(f, sh, ix.text_packed, words, buf, st);
+            else if (tag == "KTABLE") read_section(f, sh, ix.ktable, (size_t)1 << (2 * fh.ktable_k), buf, st);
+            else if (tag == "SSAMARK") {
+                read_section(f, sh, ix.ssa_marks, ((size_t)ix.len + 63) / 64, buf, st);
+                have_marks = true;
+            } else if (tag == "SSAVAL") {
+                if (!fh.ssa_rate) throw std::invalid_argument("index file header is inconsistent");
+                read_section(f, sh, ix.ssa_vals, (size_t)ix.n / fh.ssa_rate + 1, buf, st);
+                have_vals = true;
+            } else
+                throw std::invalid_argument("index file: unknown section " + tag);
+        }
+        if ((ix.occ_layout != OCC_NONE) != have_occ || (fh.ssa_rate != 0) != (have_marks && have_vals) ||
+            (fh.ktable_k != 0) != (ix.ktable.ptr != nullptr))
+            throw std::invalid_argument("index file: sections do not match the header");
+        ix.ssa_rate = fh.ssa_rate;
+        fclose(f);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        ok(err);
+        return h;
+    } catch (const CudaFailure &e) {
+        cudaGetLastError();
+        fail(code_of(e.code), e.what(), err);
+    } catch (const std::bad_alloc &) {
+        fail(B200SA_ERR_OUT_OF_MEMORY, "host allocation failed", err);
+    } catch (const std::invalid_argument &e) {
+        fail(B200SA_ERR_BAD_ARGUMENT, e.what(), err);
+    } catch (const std::exception &e) {
+        fail(B200SA_ERR_INTERNAL, e.what(), err);
+    }
+    fclose(f);
+    b200sa_free(h);
+    return nullptr;
 }
 
 // ---- approximate search ------------------------------------------------------------------------

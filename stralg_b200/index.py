@@ -98,6 +98,19 @@ class SuffixArrayIndex:
             raise B200saError(err.value, lib.b200sa_last_error().decode())
         return cls(h, device)
 
+    # ---- native index file (include/b200sa.h: b200sa_save / b200sa_load) ------------------------
+    def save(self, path: str) -> None:
+        check(_lib.load().b200sa_save(self._h, str(path).encode()))
+
+    @classmethod
+    def load(cls, path: str, device: int = 0, stream: int = 0) -> "SuffixArrayIndex":
+        lib = _lib.load()
+        err = C.c_int(0)
+        h = lib.b200sa_load(str(path).encode(), device, C.c_void_p(stream), C.byref(err))
+        if not h:
+            raise B200saError(err.value, lib.b200sa_last_error().decode())
+        return cls(h, device)
+
     def close(self):
         if self._h:
             _lib.load().b200sa_free(self._h)
