@@ -635,6 +635,70 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
         "kernel_only_patterns_per_s_per_gpu": shard / (kernel_ms / 1e3),
         "delivered_equals_single_gpu_search": verified,
     }
+    if world == 1 and not args.no_extras:
+        # ---- locate: positions of the first reads through the full suffix array and
+        # through the sampled one (LF walk), device buffers, CUDA events; results compared bit for bit
+        try:
+            nloc = min(shard, args.locate_reads)
+            Ld, Rd = LR[0][:nloc].contiguous(), LR[1][:nloc].contiguous()
+            poff = torch.empty(nloc + 1, dtype=torch.int64, device=dev)
+            total = idx.locate_device(Ld, Rd, nloc, poff, None, 0, stream)
+            pos_full = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+            pos_ssa = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+            loc = {"reads": nloc, "positions": total}
+            t_b0, t_b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_b0.record()
+            idx.sample_sa(args.sa_rate, drop_sa=False)
+            t_b1.record()
+            torch.cuda.synchronize()
+            loc["sample_build_ms"] = t_b0.elapsed_time(t_b1)
+            loc["sa_sample_rate"] = args.sa_rate
+            for name, buf, env in (("full_sa", pos_full, None), ("sampled_sa", pos_ssa, "1")):
+                if env:
+                    os.environ["B200SA_LOCATE_SAMPLED"] = env
+                else:
+                    os.environ.pop("B200SA_LOCATE_SAMPLED", None)
+                idx.locate_device(Ld, Rd, nloc, poff, buf, total, stream)  # warm-up
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(args.steps):
+                    idx.locate_device(Ld, Rd, nloc, poff, buf, total, stream)
+                a1.record()
+                torch.cuda.synchronize()
+                ms = a0.elapsed_time(a1) / args.steps
+                loc[name] = {"ms": ms, "positions_per_s": total / (ms / 1e3)}
+            os.environ.pop("B200SA_LOCATE_SAMPLED", None)
+            loc["sampled_equals_full"] = bool(torch.equal(pos_full, pos_ssa))
+            loc["bytes_per_row"] = {"full_sa": 4.0, "sampled_sa": 0.25 + 4.0 / args.sa_rate}
+            res_locate = loc
+            del pos_full, pos_ssa, poff
+        except Exception as ex:
+            res_locate = {"error": str(ex)[:200]}
+        # ---- approximate search: edit distance 1 through the host API (reads in, interval
+        # lists + CIGARs out), D table from an index of the reversed text
+        try:
+            na = min(shard, args.approx_reads)
+            rev_text = torch.flip(text[:n], dims=[0]).contiguous()
+            rev = build(src=rev_text, drop_sa=True)
+            del rev_text
+            h_reads = reads[: na * m].cpu().numpy()
+            ap = {}
+            for d in (1, 2) if args.approx_d2 else (1,):
+                cnt = na if d == 1 else max(1, na // 20)
+                idx.approx_search(h_reads[: min(cnt, 1000) * m], fixed_len=m, max_edits=d, rev=rev)  # warm-up
+                t0 = time.perf_counter()
+                r = idx.approx_search(h_reads[: cnt * m], fixed_len=m, max_edits=d, rev=rev)
+                dt = time.perf_counter() - t0
+                ap[f"d{d}"] = {"reads": cnt, "seconds": dt, "reads_per_s": cnt / dt, "intervals": int(len(r["L"])),
+                               "reads_with_a_match": int((np.diff(r["offsets"].astype(np.int64)) > 0).sum())}
+            ap["api"] = "b200sa_approx_batch (host reads in; intervals, matched lengths and CIGARs out)"
+            ap["read_len"] = m
+            rev.close()
+            res_approx = ap
+        except Exception as ex:
+            res_approx = {"error": str(ex)[:200]}
+        res["locate"] = res_locate
+        res["approx"] = res_approx
     if not args.no_cpu and rank == 0 and world == 1:
         ns = min(args.cpu_sample, n)
         sample = np.concatenate([text[:ns].cpu().numpy(), np.zeros(1, np.uint8)])
@@ -673,6 +737,11 @@ def main():
     ap.add_argument("--cpu-reads", type=int, default=1_000_000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-search", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the locate / approximate-search lines")
+    ap.add_argument("--locate-reads", type=int, default=20_000_000)
+    ap.add_argument("--sa-rate", type=int, default=32)
+    ap.add_argument("--approx-reads", type=int, default=200_000)
+    ap.add_argument("--approx-d2", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     args.warmup_ref = min(args.warmup, 1)

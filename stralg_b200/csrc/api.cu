@@ -6,6 +6,7 @@
 #include <new>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 using namespace b200sa;
@@ -149,7 +150,7 @@ static bool can_locate(const b200sa_index *idx) {
 // positions through the full suffix array when it is resident, else through the sampled one
 static void locate_fill_any(const DeviceIndex &ix, const u32 *d_L, const u32 *d_R, u64 npat, const u64 *d_pos_off,
                             u64 total, u32 *d_pos, cudaStream_t st) {
-    static const bool force_ssa = getenv("B200SA_LOCATE_SAMPLED") != nullptr;
+    const bool force_ssa = getenv("B200SA_LOCATE_SAMPLED") != nullptr;  // measurement aid (bench.py)
     if (ix.sa.ptr && !(force_ssa && ix.ssa_rate)) fm_locate_fill(ix, d_L, d_R, npat, d_pos_off, total, d_pos, st);
     else fm_locate_fill_ssa(ix, d_L, npat, d_pos_off, total, d_pos, st);
 }
@@ -819,15 +820,23 @@ b200sa_approx_result *b200sa_approx_batch(const b200sa_index *idx, const b200sa_
                 ddt.alloc(total + 16, st);
                 approx_dtable(rev_idx->ix, dp.ptr, doff.ptr, fixed_len, npat, ddt.ptr, st);
             }
+            const bool dbg = getenv("B200SA_APPROX_DEBUG") != nullptr;
+            auto now = [&]() {
+                if (dbg) cudaStreamSynchronize(st);
+                return std::chrono::steady_clock::now();
+            };
+            auto t_a = now();
             u64 hits = 0, ops = 0;
             approx_count(ix, dp.ptr, doff.ptr, fixed_len, npat, max_m, ddt.ptr, max_edits, d_hit_off.ptr, d_ops_off.ptr,
                          &hits, &ops, st);
             CUDA_CHECK(cudaMemcpyAsync(res->hit_off.data(), d_hit_off.ptr, (npat + 1) * 8, cudaMemcpyDeviceToHost, st));
+            auto t_b = now();
             res->L.resize(hits);
             res->R.resize(hits);
             res->mlen.resize(hits);
-            std::vector<uint64_t> hops(hits + 1, 0);
-            std::vector<char> opbuf(ops + 1, 0);
+            // the emitting pass writes the run-length CIGAR strings (stralg/cigar.c:8-31) themselves
+            res->cig_off.assign(hits + 1, 0);
+            res->cigars.assign(ops + 1, 0);
             if (hits) {
                 DevBuf<u32> dL(hits, st), dR(hits, st), dM(hits, st);
                 DevBuf<u64> dho(hits, st);
@@ -837,30 +846,21 @@ b200sa_approx_result *b200sa_approx_batch(const b200sa_index *idx, const b200sa_
                 CUDA_CHECK(cudaMemcpyAsync(res->L.data(), dL.ptr, hits * 4, cudaMemcpyDeviceToHost, st));
                 CUDA_CHECK(cudaMemcpyAsync(res->R.data(), dR.ptr, hits * 4, cudaMemcpyDeviceToHost, st));
                 CUDA_CHECK(cudaMemcpyAsync(res->mlen.data(), dM.ptr, hits * 4, cudaMemcpyDeviceToHost, st));
-                CUDA_CHECK(cudaMemcpyAsync(hops.data(), dho.ptr, hits * 8, cudaMemcpyDeviceToHost, st));
-                CUDA_CHECK(cudaMemcpyAsync(opbuf.data(), dops.ptr, ops, cudaMemcpyDeviceToHost, st));
+                CUDA_CHECK(cudaMemcpyAsync(res->cig_off.data(), dho.ptr, hits * 8, cudaMemcpyDeviceToHost, st));
+                CUDA_CHECK(cudaMemcpyAsync(res->cigars.data(), dops.ptr, ops, cudaMemcpyDeviceToHost, st));
             }
             CUDA_CHECK(cudaStreamSynchronize(st));
-            hops[hits] = ops;
-            // operations -> run-length CIGAR (stralg/cigar.c:8-31), one NUL-terminated string per hit
-            res->cig_off.resize(hits + 1);
-            res->cigars.reserve(ops + hits + 16);
-            for (u64 h = 0; h < hits; ++h) {
-                res->cig_off[h] = res->cigars.size();
-                u64 k = hops[h];
-                const u64 e = hops[h + 1];
-                while (k < e) {
-                    u64 r = k;
-                    while (r < e && opbuf[r] == opbuf[k]) ++r;
-                    char num[24];
-                    int w = snprintf(num, sizeof num, "%llu", (unsigned long long)(r - k));
-                    res->cigars.insert(res->cigars.end(), num, num + w);
-                    res->cigars.push_back(opbuf[k]);
-                    k = r;
-                }
-                res->cigars.push_back('\0');
+            auto t_c = now();
+            res->cig_off[hits] = ops;
+            if (dbg) {
+                auto t_d = now();
+                auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+                    return std::chrono::duration<double, std::milli>(b - a).count();
+                };
+                fprintf(stderr, "b200sa_approx_batch: %llu patterns, %llu hits: count pass %.2f ms, emit pass + copies %.2f ms, "
+                        "host tail %.2f ms\n", (unsigned long long)npat, (unsigned long long)hits, ms(t_a, t_b), ms(t_b, t_c),
+                        ms(t_c, t_d));
             }
-            res->cig_off[hits] = res->cigars.size();
         }
         ok(err);
         return res;

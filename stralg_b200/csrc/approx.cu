@@ -15,7 +15,7 @@
 // in the reference's report order.  Conditions that make the reference return immediately from a
 // child (edits_left < D, empty interval) are tested BEFORE the O lookups of that child -- they
 // have no side effects, so the hit list is unchanged.  The walk runs twice: a counting pass
-// (hits and operation characters per pattern), an exclusive scan, and an emitting pass that
+// (hits and CIGAR bytes per pattern), an exclusive scan, and an emitting pass that
 // writes every hit at its final offset -- no atomics, deterministic output.
 //
 // D table (bwt.c:319-337): forward over the pattern with the O table of the REVERSED text (a
@@ -41,13 +41,13 @@ struct ApproxArgs {
     u32 max_depth;
     // counting pass
     u32 *hit_count;        // per pattern
-    u64 *ops_count;        // per pattern
+    u64 *ops_count;        // per pattern: bytes of CIGAR text (NULs included)
     // emitting pass
     const u64 *hit_off;    // per pattern (exclusive scan of hit_count), [npat] = total
     const u64 *ops_off;    // per pattern (exclusive scan of ops_count)
     u32 *out_L, *out_R, *out_mlen;
-    u64 *out_ops_off;      // per hit: start of its operations in out_ops
-    char *out_ops;         // operations in pattern order ('M', 'I', 'D')
+    u64 *out_ops_off;      // per hit: start of its CIGAR in out_ops
+    char *out_ops;         // CIGAR strings (NUL-terminated), one per hit
 };
 
 // frame: x = L, y = R, z = (i + 1) | edits_left << 16 | op << 24, w = cursor | matched length << 16
@@ -61,7 +61,7 @@ __device__ __forceinline__ u32 occ_sym(const OccView &ov, u32 a, u32 i) {
 }
 
 template <int LAYOUT, bool EMIT>
-__global__ void __launch_bounds__(128) approx_walk_kernel(ApproxArgs A) {
+__global__ void __launch_bounds__(128, 8) approx_walk_kernel(ApproxArgs A) {
     __shared__ u32 c_sh[256];
     for (u32 k = threadIdx.x; k < 256; k += blockDim.x) c_sh[k] = k < A.sigma ? A.c_dev[k] : 0;
     __syncthreads();
@@ -131,27 +131,41 @@ __global__ void __launch_bounds__(128) approx_walk_kernel(ApproxArgs A) {
             }
             const u32 cm = mlen + (cop != 1 ? 1u : 0u);
             if (ci < 0) {
-                // a hit: the path is the operations of frames 1..depth plus this step
+                // a hit.  Its path, in pattern order (= reversed): this step, the current node's own step,
+                // then the steps of the parked frames from the top down to frame 1; run-length encoded
+                // into the CIGAR text the reference builds with sprintf("%d%c") (cigar.c:17-31).
                 const u32 plen = depth + 1;
+                auto path_op = [&](u32 k) -> u32 {
+                    return k == 0 ? cop : k == 1 ? op : ((stk[(u64)(depth + 1 - k) * lanes].z >> 24) & 3u);
+                };
+                char *w = EMIT ? A.out_ops + ops_at + nops : nullptr;
+                u32 bytes = 0;
+                for (u32 k = 0; k < plen;) {
+                    const u32 o = path_op(k);
+                    u32 run = 1;
+                    while (k + run < plen && path_op(k + run) == o) ++run;
+                    const u32 digits = run >= 10000u ? 5u : run >= 1000u ? 4u : run >= 100u ? 3u : run >= 10u ? 2u : 1u;
+                    if (EMIT) {
+                        u32 v = run;
+                        for (u32 dgt = digits; dgt-- > 0;) {
+                            w[bytes + dgt] = (char)('0' + v % 10u);
+                            v /= 10u;
+                        }
+                        w[bytes + digits] = o == 0 ? 'M' : o == 1 ? 'I' : 'D';
+                    }
+                    bytes += digits + 1u;
+                    k += run;
+                }
                 if (EMIT) {
+                    w[bytes] = '\0';
                     const u64 h = hit_at + nhits;
                     A.out_L[h] = cL;
                     A.out_R[h] = cR;
                     A.out_mlen[h] = cm;
                     A.out_ops_off[h] = ops_at + nops;
-                    char *w = A.out_ops + ops_at + nops;
-                    // pattern order = path reversed: this step first, then the frames from the top down
-                    w[0] = cop == 0 ? 'M' : cop == 1 ? 'I' : 'D';
-                    if (depth >= 1) {
-                        w[1] = op == 0 ? 'M' : op == 1 ? 'I' : 'D';  // the current node's own step
-                        for (u32 f = depth - 1; f >= 1; --f) {
-                            const u32 fop = (stk[(u64)f * lanes].z >> 24) & 3u;
-                            w[depth + 1 - f] = fop == 0 ? 'M' : fop == 1 ? 'I' : 'D';
-                        }
-                    }
                 }
                 ++nhits;
-                nops += plen;
+                nops += bytes + 1u;
                 continue;
             }
             // descend: park the current node, the child becomes current

@@ -278,6 +278,15 @@ class SuffixArrayIndex:
         check(_lib.load().b200sa_sa_lookup(self._h, _np_ptr(rows), len(rows), _np_ptr(out), 1 if force_sampled else 0))
         return out
 
+    def locate_device(self, d_L, d_R, npat: int, d_pos_off, d_pos=None, capacity: int = 0, stream: int = 0) -> int:
+        """Device buffers (torch CUDA tensors): fills d_pos_off[npat + 1] and, when given, d_pos; returns
+        the number of positions."""
+        total = C.c_uint64(0)
+        check(_lib.load().b200sa_locate_device(
+            self._h, C.c_void_p(d_L.data_ptr()), C.c_void_p(d_R.data_ptr()), npat, C.c_void_p(d_pos_off.data_ptr()),
+            C.c_void_p(d_pos.data_ptr()) if d_pos is not None else None, capacity, C.byref(total), C.c_void_p(stream)))
+        return int(total.value)
+
     def exact_matches(self, pattern_codes) -> np.ndarray:
         """All match positions of one pattern in SA order (the iterator loop of match_test.c:599-603)."""
         L, R = self.search_one(pattern_codes)
