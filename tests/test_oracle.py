@@ -110,3 +110,56 @@ def test_synth_generators_are_deterministic(oracle):
         oracle.lib.oracle_synth_codes(buf.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint64(1000), C.c_uint32(4),
                                       C.c_uint64(42))
     assert np.array_equal(a, b) and a[-1] == 0 and a[:-1].min() >= 1 and a[:-1].max() <= 4
+
+
+def test_oracle_approx_vs_reference_iterator(oracle, ref):
+    """Pins the restatement of bwt.c:226-382 to the unmodified reference: interval list, matched
+    lengths and CIGARs, in report order, with and without the reverse (RO / D table) tables; and the
+    D table only prunes (same result either way)."""
+    if ref is None:
+        pytest.skip("oracle/_ref/libstralg_ref.so not present")
+    rng = np.random.default_rng(1)
+    intervals = 0
+    for trial in range(12):
+        n = int(rng.integers(5, 400))
+        nsym = int(rng.integers(1, 5))
+        raw = bytes(rng.choice(list(b"acgt"[:nsym]), n).tolist())
+        for rev in (True, False):
+            t = ref.tables(raw, rev)
+            for q in range(6):
+                m = int(rng.integers(1, 12))
+                if q % 2 and n > m:
+                    s = int(rng.integers(0, n - m))
+                    pc = t["codes"][s:s + m].copy()
+                    if m > 2:
+                        pc[int(rng.integers(0, m))] = 1 + int(rng.integers(0, t["sigma"] - 1))
+                else:
+                    pc = rng.integers(1, t["sigma"], m).astype(np.uint8) if t["sigma"] > 1 else np.ones(m, np.uint8)
+                for d in (0, 1, 2):
+                    L, R, ml, cig, hits = ref.approx_matches(t["handle"], pc, d)
+                    L2, R2, ml2, cig2 = oracle.approx(t["c"], t["o"], t["ro"], t["len"], pc, d)
+                    assert np.array_equal(L, L2) and np.array_equal(R, R2) and np.array_equal(ml, ml2) and cig == cig2
+                    if rev:
+                        L3, R3, ml3, cig3 = oracle.approx(t["c"], t["o"], None, t["len"], pc, d)
+                        assert np.array_equal(L, L3) and np.array_equal(R, R3) and cig == cig3
+                    # the iterator yields SA[L..R) of every interval in turn (bwt.c:384-401)
+                    exp = [(int(t["sa"][i]), cig[k], int(ml[k])) for k in range(len(L)) for i in range(int(L[k]), int(R[k]))]
+                    assert hits == exp
+                    intervals += len(L)
+            ref.free_tables(t["handle"])
+    assert intervals > 1000
+
+
+def test_oracle_approx_known_answers(oracle):
+    """mississippi, pattern "ssi": zero edits is the exact interval with CIGAR 3M; one edit adds the
+    substitutions / insertions / deletions the reference's tool reports."""
+    codes, sigma, table = oracle.remap(b"mississippi")
+    sa = oracle.sa(codes)
+    bwt = oracle.bwt(codes, sa)
+    c, o = oracle.c_table(codes, sigma), oracle.o_table(bwt, sigma)
+    p = oracle.remap_pattern(table, b"ssi")
+    L, R, ml, cig = oracle.approx(c, o, None, len(codes), p, 0)
+    assert cig == ["3M"] and ml.tolist() == [3] and sorted(sa[int(L[0]):int(R[0])].tolist()) == [2, 5]
+    L, R, ml, cig = oracle.approx(c, o, None, len(codes), p, 1)
+    assert "3M" in cig and "1I2M" in cig and any("D" in x for x in cig)
+    assert all(int(l) < int(r) for l, r in zip(L, R))
