@@ -9,10 +9,10 @@
 // (bwt.c:349-377).  A node with edits_left < D[i] is abandoned (bwt.c:237-240), empty intervals
 // are not entered, and i < 0 is a hit: (L, R, matched length, operations of the path).
 //
-// Here one lane owns one pattern and runs that walk with an explicit stack of 16-byte frames in
-// HBM (frame f of lane t at [f * lanes + t], so a warp's pushes and pops are coalesced); children
-// are generated from a cursor in exactly the reference's order, so the hits of a pattern come out
-// in the reference's report order.  Conditions that make the reference return immediately from a
+// Here a group of 16 lanes owns one pattern and runs that walk with an explicit stack of 16-byte
+// frames in HBM (frame f of pattern t at [f * patterns + t]); the children of a node are evaluated
+// by the lanes side by side and taken in exactly the reference's order, so the hits of a pattern
+// come out in the reference's report order.  Conditions that make the reference return immediately from a
 // child (edits_left < D, empty interval) are tested BEFORE the O lookups of that child -- they
 // have no side effects, so the hit list is unchanged.  The walk runs twice: a counting pass
 // (hits and CIGAR bytes per pattern), an exclusive scan, and an emitting pass that
@@ -60,13 +60,29 @@ __device__ __forceinline__ u32 occ_sym(const OccView &ov, u32 a, u32 i) {
     return LAYOUT == 1 ? occ_dna(ov, a, i) : occ_byte(ov, a, i);
 }
 
+// One GROUP of 16 lanes owns one pattern (two patterns per warp).  The node state is uniform over
+// the group; lane j evaluates child j of the current node (its edit cost, the D-table test and the
+// two O lookups), a ballot gives the viable children, and they are taken in the reference's order:
+//   * a child with i < 0 is a hit;
+//   * a child with no edits left can only continue by exact matching (every other step costs an
+//     edit): its whole subtree is the chain pattern[i], pattern[i-1], ... which is run inline,
+//     without touching the stack, and ends in at most one hit;
+//   * any other child is entered: the current node is parked in the stack with the index of its
+//     next child, and re-evaluated when the walk comes back to it.
+// sigma - 1 <= 7 letters fit one evaluation (2 (sigma-1) + 1 <= 15 children); larger alphabets take
+// their children 16 at a time.
+static constexpr int AG = 16;  // lanes per pattern
+
 template <int LAYOUT, bool EMIT>
 __global__ void __launch_bounds__(128, 8) approx_walk_kernel(ApproxArgs A) {
     __shared__ u32 c_sh[256];
     for (u32 k = threadIdx.x; k < 256; k += blockDim.x) c_sh[k] = k < A.sigma ? A.c_dev[k] : 0;
     __syncthreads();
-    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 t = ((u64)blockIdx.x * blockDim.x + threadIdx.x) / AG;  // group = pattern of this launch
     if (t >= A.count) return;
+    const u32 gl = threadIdx.x & (AG - 1);                  // lane inside the group
+    const u32 gshift = (threadIdx.x & 31u) & ~(u32)(AG - 1);  // first warp lane of the group
+    const u32 gmask = 0xffffu << gshift;
     const u64 q = A.first + t;
     const u64 begin = A.off ? A.off[q] : q * (u64)A.fixed_len;
     const u32 m = A.off ? (u32)(A.off[q + 1] - begin) : A.fixed_len;
@@ -84,7 +100,7 @@ __global__ void __launch_bounds__(128, 8) approx_walk_kernel(ApproxArgs A) {
         ops_at = A.ops_off[q];
     }
     if (m == 0 || nsym == 0) {
-        if (!EMIT) {
+        if (!EMIT && gl == 0) {
             A.hit_count[q] = 0;
             A.ops_count[q] = 0;
         }
@@ -96,56 +112,105 @@ __global__ void __launch_bounds__(128, 8) approx_walk_kernel(ApproxArgs A) {
     int i = (int)m - 1, left = A.max_edits;
     u32 depth = 0;  // frames below the current one
     while (true) {
-        bool descended = false;
-        // children of the current node, from `cursor` on
         const u32 nchildren = depth == 0 ? nsym + 1 : 2 * nsym + 1;
-        while (cursor < nchildren) {
-            const u32 cidx = cursor++;
-            u32 a, cop;
-            int ci, cleft;
-            if (cidx < nsym) {  // match / substitution
-                a = cidx + 1;
-                cop = 0;
-                ci = i - 1;
-                cleft = left - (a == (u32)p[i] ? 0 : 1);
-            } else if (cidx == nsym) {  // insertion: the pattern symbol is skipped
-                a = 0;
-                cop = 1;
-                ci = i - 1;
-                cleft = left - 1;
-            } else {  // deletion: a text symbol is skipped
-                a = cidx - nsym;
-                cop = 2;
-                ci = i;
-                cleft = left - 1;
-            }
-            if (cleft < 0) continue;
+        if (cursor >= nchildren) {
+            if (depth == 0) break;
+            --depth;
+            const uint4 f = stk[(u64)depth * lanes];
+            L = f.x; R = f.y;
+            i = (int)(f.z & 0xffffu) - 1;
+            left = (int)((f.z >> 16) & 0xffu);
+            op = (f.z >> 24) & 3u;
+            cursor = f.w & 0xffffu;
+            mlen = f.w >> 16;
+            continue;
+        }
+        // ---- lane gl evaluates child cb + gl ----
+        const u32 cb = cursor & ~(u32)(AG - 1);
+        const u32 cidx = cb + gl;
+        u32 a, cop;
+        int ci, cleft;
+        if (cidx < nsym) {  // match / substitution
+            a = cidx + 1;
+            cop = 0;
+            ci = i - 1;
+            cleft = left - (a == (u32)p[i] ? 0 : 1);
+        } else if (cidx == nsym) {  // insertion: the pattern symbol is skipped
+            a = 0;
+            cop = 1;
+            ci = i - 1;
+            cleft = left - 1;
+        } else {  // deletion: a text symbol is skipped
+            a = cidx - nsym;
+            cop = 2;
+            ci = i;
+            cleft = left - 1;
+        }
+        bool viable = cidx >= cursor && cidx < nchildren && cleft >= 0;
+        if (viable) {
             const int need = (ci >= 0 && dt) ? (int)dt[ci] : 0;
-            if (cleft < need) continue;
-            u32 cL = L, cR = R;
-            if (a) {
-                const u32 ca = c_sh[a];
-                cL = ca + occ_sym<LAYOUT>(A.ov, a, L);
-                cR = ca + occ_sym<LAYOUT>(A.ov, a, R);
-                if (cL >= cR) continue;
+            viable = cleft >= need;
+        }
+        u32 cL = L, cR = R;
+        if (viable && a) {
+            const u32 ca = c_sh[a];
+            cL = ca + occ_sym<LAYOUT>(A.ov, a, L);
+            cR = ca + occ_sym<LAYOUT>(A.ov, a, R);
+            viable = cL < cR;
+        }
+        u32 vmask = (__ballot_sync(gmask, viable) >> gshift) & 0xffffu;
+        bool descended = false;
+        while (vmask) {
+            const int j = __ffs((int)vmask) - 1;
+            vmask &= vmask - 1u;
+            const int src = (int)gshift + j;
+            u32 bL = __shfl_sync(gmask, cL, src), bR = __shfl_sync(gmask, cR, src);
+            int bi = __shfl_sync(gmask, ci, src);
+            const int bleft = __shfl_sync(gmask, cleft, src);
+            const u32 bop = __shfl_sync(gmask, cop, src);
+            u32 bm = mlen + (bop != 1 ? 1u : 0u);
+            u32 chain = 0;  // exact steps taken below the child (no edits left)
+            bool hit = bi < 0;
+            if (!hit && bleft == 0) {
+                // only exact matching can follow: run the chain (every lane of the group alike)
+                hit = true;
+                while (bi >= 0) {
+                    const u32 x = p[bi];
+                    if ((dt && dt[bi] > 0) || x == 0 || x > nsym) {
+                        hit = false;
+                        break;
+                    }
+                    const u32 ca = c_sh[x];
+                    const u32 nl = ca + occ_sym<LAYOUT>(A.ov, x, bL), nr = ca + occ_sym<LAYOUT>(A.ov, x, bR);
+                    if (nl >= nr) {
+                        hit = false;
+                        break;
+                    }
+                    bL = nl; bR = nr;
+                    --bi;
+                    ++chain;
+                }
+                if (!hit) continue;
+                bm += chain;
             }
-            const u32 cm = mlen + (cop != 1 ? 1u : 0u);
-            if (ci < 0) {
-                // a hit.  Its path, in pattern order (= reversed): this step, the current node's own step,
-                // then the steps of the parked frames from the top down to frame 1; run-length encoded
-                // into the CIGAR text the reference builds with sprintf("%d%c") (cigar.c:17-31).
-                const u32 plen = depth + 1;
+            if (hit) {
+                // The path in pattern order (= reversed): the chain's matches, the child's step, the
+                // current node's own step, then the parked frames from the top down to frame 1;
+                // run-length encoded into the CIGAR text of cigar.c:17-31 (sprintf("%d%c")).
+                const u32 plen = depth + 1 + chain;
                 auto path_op = [&](u32 k) -> u32 {
-                    return k == 0 ? cop : k == 1 ? op : ((stk[(u64)(depth + 1 - k) * lanes].z >> 24) & 3u);
+                    if (k < chain) return 0u;
+                    k -= chain;
+                    return k == 0 ? bop : k == 1 ? op : ((stk[(u64)(depth + 1 - k) * lanes].z >> 24) & 3u);
                 };
                 char *w = EMIT ? A.out_ops + ops_at + nops : nullptr;
                 u32 bytes = 0;
                 for (u32 k = 0; k < plen;) {
                     const u32 o = path_op(k);
-                    u32 run = 1;
+                    u32 run = (o == 0 && k < chain) ? chain - k : 1u;
                     while (k + run < plen && path_op(k + run) == o) ++run;
                     const u32 digits = run >= 10000u ? 5u : run >= 1000u ? 4u : run >= 100u ? 3u : run >= 10u ? 2u : 1u;
-                    if (EMIT) {
+                    if (EMIT && gl == 0) {
                         u32 v = run;
                         for (u32 dgt = digits; dgt-- > 0;) {
                             w[bytes + dgt] = (char)('0' + v % 10u);
@@ -156,37 +221,29 @@ __global__ void __launch_bounds__(128, 8) approx_walk_kernel(ApproxArgs A) {
                     bytes += digits + 1u;
                     k += run;
                 }
-                if (EMIT) {
+                if (EMIT && gl == 0) {
                     w[bytes] = '\0';
                     const u64 h = hit_at + nhits;
-                    A.out_L[h] = cL;
-                    A.out_R[h] = cR;
-                    A.out_mlen[h] = cm;
+                    A.out_L[h] = bL;
+                    A.out_R[h] = bR;
+                    A.out_mlen[h] = bm;
                     A.out_ops_off[h] = ops_at + nops;
                 }
                 ++nhits;
                 nops += bytes + 1u;
                 continue;
             }
-            // descend: park the current node, the child becomes current
-            stk[(u64)depth * lanes] = make_frame(L, R, i, left, op, cursor, mlen);
+            // enter the child: park the current node with the index of its next child
+            if (gl == 0) stk[(u64)depth * lanes] = make_frame(L, R, i, left, op, cb + (u32)j + 1u, mlen);
+            __syncwarp(gmask);
             ++depth;
-            L = cL; R = cR; i = ci; left = cleft; op = cop; cursor = 0; mlen = cm;
+            L = bL; R = bR; i = bi; left = bleft; op = bop; cursor = 0; mlen = bm;
             descended = true;
             break;
         }
-        if (descended) continue;
-        if (depth == 0) break;
-        --depth;
-        const uint4 f = stk[(u64)depth * lanes];
-        L = f.x; R = f.y;
-        i = (int)(f.z & 0xffffu) - 1;
-        left = (int)((f.z >> 16) & 0xffu);
-        op = (f.z >> 24) & 3u;
-        cursor = f.w & 0xffffu;
-        mlen = f.w >> 16;
+        if (!descended) cursor = cb + AG;
     }
-    if (!EMIT) {
+    if (!EMIT && gl == 0) {
         A.hit_count[q] = nhits;
         A.ops_count[q] = nops;
     }
@@ -295,7 +352,7 @@ static void launch_walk(const DeviceIndex &ix, ApproxArgs &A, bool emit, u64 npa
     for (u64 first = 0; first < npat; first += chunk) {
         A.first = first;
         A.count = std::min(chunk, npat - first);
-        const unsigned blocks = div_up_u(A.count, 128);
+        const unsigned blocks = div_up_u(A.count * AG, 128);
         if (ix.occ_layout == OCC_DNA32) {
             if (emit) approx_walk_kernel<1, true><<<blocks, 128, 0, st>>>(A);
             else approx_walk_kernel<1, false><<<blocks, 128, 0, st>>>(A);
