@@ -267,6 +267,30 @@ __global__ void __launch_bounds__(P_NT) msd_hist_elems_kernel(const u64 *__restr
         if (sh[i]) atomicAdd(&h[i], sh[i]);
 }
 
+// exclusive prefix of `v` over an NT-thread block (wsum: NT / 32 words of shared memory)
+template <int NT>
+__device__ __forceinline__ u32 block_exclusive(u32 v, u32 *wsum) {
+    constexpr int NW = NT / 32;
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    u32 incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    u32 ws = lane < (u32)NW ? wsum[lane] : 0u;
+    u32 wi = ws;
+#pragma unroll
+    for (int o = 1; o < NW; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= (unsigned)o) wi += t;
+    }
+    const u32 wbase = __shfl_sync(0xffffffffu, wi - ws, warp);
+    return wbase + incl - v;
+}
+
 // exclusive prefix of `v` over a 512-thread block (wsum: 16 words of shared memory)
 __device__ __forceinline__ u32 block512_exclusive(u32 v, u32 *wsum) {
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -308,7 +332,9 @@ struct PartArgs {
 static constexpr int P_INB = P_TILE + 2;  // landing buffer: the copy starts at a 16-byte boundary
 static constexpr size_t P_SMEM = (size_t)P_INB * 8 * 2 + (size_t)P_TILE * 8 + (size_t)P_MAXBINS * 4 * 2 + 32 * 4 + 2 * 8;
 
-__global__ void __launch_bounds__(P_NT, 2) msd_partition_kernel(PartArgs a) {
+template <int NT = P_NT>
+__global__ void __launch_bounds__(NT, 2) msd_partition_kernel(PartArgs a) {
+    constexpr int IPT = P_TILE / NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *inb = (u64 *)smem_raw;                   // [2][P_INB] landing buffers
     u64 *buf = inb + 2 * P_INB;                   // [P_TILE] elements grouped by digit
@@ -349,15 +375,15 @@ __global__ void __launch_bounds__(P_NT, 2) msd_partition_kernel(PartArgs a) {
         const u64 *in = inb + stage * P_INB + (ds.x & 1u);
         // the other landing buffer was last read before the barrier that ended the previous iteration
         if (tid == 0 && tile + gridDim.x < ntiles) issue(tile + gridDim.x, stage ^ 1u);
-        for (u32 i = tid; i < B; i += P_NT) hist[i] = 0;
+        for (u32 i = tid; i < B; i += NT) hist[i] = 0;
         __syncthreads();
         mbar_wait_parity(&mbar[stage], (it >> 1) & 1u);
 
         // ---- digits and slots inside the tile's digit groups (arbitrary order: MSD) ----
-        u32 dsl[P_IPT];
+        u32 dsl[IPT];
 #pragma unroll
-        for (int j = 0; j < P_IPT; ++j) {
-            const u32 i = (u32)j * P_NT + tid;
+        for (int j = 0; j < IPT; ++j) {
+            const u32 i = (u32)j * NT + tid;
             dsl[j] = 0;
             if (i < count) {
                 const u32 d = (u32)(in[i] >> a.dshift) & (B - 1);
@@ -368,7 +394,7 @@ __global__ void __launch_bounds__(P_NT, 2) msd_partition_kernel(PartArgs a) {
 
         // ---- exclusive scan of the digit counts; reserve the runs in the child buckets ----
         {
-            constexpr int DPT = P_MAXBINS / P_NT;  // 2
+            constexpr int DPT = P_MAXBINS / NT;
             const u32 d0 = tid * DPT;
             u32 c[DPT], g[DPT];
             u32 sum = 0;
@@ -382,7 +408,7 @@ __global__ void __launch_bounds__(P_NT, 2) msd_partition_kernel(PartArgs a) {
                 g[q] = 0;
                 if (c[q]) g[q] = atomicAdd(&a.cursor[(size_t)parent * B + d0 + q], c[q]);
             }
-            u32 run = block512_exclusive(sum, wsum);
+            u32 run = block_exclusive<NT>(sum, wsum);
 #pragma unroll
             for (int q = 0; q < DPT; ++q) {
                 if (d0 + q < B) {
@@ -396,15 +422,15 @@ __global__ void __launch_bounds__(P_NT, 2) msd_partition_kernel(PartArgs a) {
 
         // ---- group the tile by digit in shared memory ----
 #pragma unroll
-        for (int j = 0; j < P_IPT; ++j) {
-            const u32 i = (u32)j * P_NT + tid;
+        for (int j = 0; j < IPT; ++j) {
+            const u32 i = (u32)j * NT + tid;
             if (i < count) buf[hist[dsl[j] & 1023u] + (dsl[j] >> 10)] = in[i];
         }
         __syncthreads();
 
         // ---- consecutive threads write consecutive slots of a digit run ----
 #pragma unroll 4
-        for (u32 i = tid; i < count; i += P_NT) {
+        for (u32 i = tid; i < count; i += NT) {
             const u64 v = buf[i];
             a.out[gofs[(u32)(v >> a.dshift) & (B - 1)] + i] = v;
         }
@@ -448,47 +474,49 @@ __device__ __forceinline__ void stage_window(const u64 *st, u32 off, u64 &H, u64
 
 // BITS = symbol width, HAS_PREV = the preceding symbol is carried in the element (pb == BITS):
 // compile-time so that every per-symbol shift is an immediate.
-template <int BITS, bool HAS_PREV>
-__global__ void __launch_bounds__(T1_NT, 2) msd_partition_text_kernel(Text1Args a) {
+template <int BITS, bool HAS_PREV, int NT = T1_NT, int IPT = T1_IPT, int CTAS = 2>
+__global__ void __launch_bounds__(NT, CTAS) msd_partition_text_kernel(Text1Args a) {
+    constexpr int TILE = NT * IPT;
+    constexpr int STAGE_MAX = TILE * 8 / 64 + 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *buf = (u64 *)smem_raw;                   // [T1_TILE] elements grouped by digit
-    u64 *stage = buf + T1_TILE;                   // [T1_STAGE_MAX] packed text of the tile (one word of lead-in)
-    u32 *hist = (u32 *)(stage + T1_STAGE_MAX);    // [MAXBINS] counts, then tile-local offsets
+    u64 *buf = (u64 *)smem_raw;                   // [TILE] elements grouped by digit
+    u64 *stage = buf + TILE;                   // [STAGE_MAX] packed text of the tile (one word of lead-in)
+    u32 *hist = (u32 *)(stage + STAGE_MAX);    // [MAXBINS] counts, then tile-local offsets
     u32 *gofs = hist + MSD_MAXBINS;               // [MAXBINS] global slot of the digit's run minus its tile offset
-    u16 *dig = (u16 *)(gofs + MSD_MAXBINS);       // [T1_TILE] digit of the element in slot i
-    u32 *wsum = (u32 *)(dig + T1_TILE);           // [32]
+    u16 *dig = (u16 *)(gofs + MSD_MAXBINS);       // [TILE] digit of the element in slot i
+    u32 *wsum = (u32 *)(dig + TILE);           // [32]
 
     constexpr int b = BITS;
     constexpr u32 lead = HAS_PREV ? (u32)BITS : 0u;
     const u32 tid = threadIdx.x;
     const u32 B = 1u << a.D;
-    const u64 begin = (u64)blockIdx.x * T1_TILE;
-    const u32 count = (u32)min((u64)T1_TILE, (u64)a.len - begin);
+    const u64 begin = (u64)blockIdx.x * TILE;
+    const u32 count = (u32)min((u64)TILE, (u64)a.len - begin);
 
     // ---- stage the tile's text: word k of `stage` is packed[begin*b/64 - 1 + k] ----
     {
-        constexpr u32 nstage = (u32)(T1_TILE / 64) * b + 4;
+        constexpr u32 nstage = (u32)(TILE / 64) * b + 4;
         const u64 w0 = begin * (u64)b / 64;
-        for (u32 k = tid; k < nstage; k += T1_NT) {
+        for (u32 k = tid; k < nstage; k += NT) {
             const u64 w = w0 + k;  // index + 1
             stage[k] = (w >= 1 && w - 1 < a.nwords) ? a.packed[w - 1] : 0ull;
         }
-        for (u32 i = tid; i < B; i += T1_NT) hist[i] = 0;
+        for (u32 i = tid; i < B; i += NT) hist[i] = 0;
     }
     __syncthreads();
 
     // bit offset (inside `stage`) of the window of the thread's first position: it starts at the
     // preceding symbol when that symbol is carried in the element, else at the position itself
-    const u32 i0 = tid * T1_IPT;
+    const u32 i0 = tid * IPT;
     const u32 off0 = 64u + i0 * (u32)b - lead;
     const int kshift = 64 - a.KB;
     const int dsh = 32 - a.D;                           // digit = leading D bits of the key
     const u32 restmask = (u32)a.restmask;               // KB - D <= 32 bits
 
     // ---- digits and slots inside the tile's digit groups (arbitrary order: MSD) ----
-    u32 ds[T1_IPT];
+    u32 ds[IPT];
 #pragma unroll
-    for (int g = 0; g < T1_IPT / 8; ++g) {
+    for (int g = 0; g < IPT / 8; ++g) {
         u64 H, L;
         stage_window(stage, off0 + (u32)(8 * g * b), H, L);
 #pragma unroll
@@ -508,8 +536,9 @@ __global__ void __launch_bounds__(T1_NT, 2) msd_partition_text_kernel(Text1Args 
     __syncthreads();
 
     // ---- exclusive scan of the digit counts; reserve the runs in the level-1 buckets ----
+    u32 gsub[MSD_MAXBINS / NT], gres[MSD_MAXBINS / NT];
     {
-        constexpr int DPT = MSD_MAXBINS / T1_NT;  // 2
+        constexpr int DPT = MSD_MAXBINS / NT;
         const u32 d0 = tid * DPT;
         u32 c[DPT], g[DPT];
         u32 sum = 0;
@@ -523,13 +552,12 @@ __global__ void __launch_bounds__(T1_NT, 2) msd_partition_text_kernel(Text1Args 
             g[q] = 0;
             if (c[q]) g[q] = atomicAdd(&a.cursor[d0 + q], c[q]);
         }
-        u32 run = block512_exclusive(sum, wsum);
+        u32 run = block_exclusive<NT>(sum, wsum);
 #pragma unroll
         for (int q = 0; q < DPT; ++q) {
-            if (d0 + q < B) {
-                hist[d0 + q] = run;
-                gofs[d0 + q] = g[q] - run;
-            }
+            if (d0 + q < B) hist[d0 + q] = run;
+            gsub[q] = run;
+            gres[q] = g[q];
             run += c[q];
         }
     }
@@ -539,7 +567,7 @@ __global__ void __launch_bounds__(T1_NT, 2) msd_partition_text_kernel(Text1Args 
     // element is two 32-bit words: [rest of key | preceding symbol] and the suffix start ----
     const u32 p0 = (u32)begin + i0;
 #pragma unroll
-    for (int g = 0; g < T1_IPT / 8; ++g) {
+    for (int g = 0; g < IPT / 8; ++g) {
         u64 H, L;
         stage_window(stage, off0 + (u32)(8 * g * b), H, L);
 #pragma unroll
@@ -557,11 +585,19 @@ __global__ void __launch_bounds__(T1_NT, 2) msd_partition_text_kernel(Text1Args 
             }
         }
     }
+    // the reserved global slots are first needed now: the round trip of the reservation (a global
+    // atomic per digit) ran behind the grouping above
+    {
+        const u32 d0 = tid * (MSD_MAXBINS / NT);
+#pragma unroll
+        for (int q = 0; q < MSD_MAXBINS / NT; ++q)
+            if (d0 + q < B) gofs[d0 + q] = gres[q] - gsub[q];
+    }
     __syncthreads();
 
     // ---- consecutive threads write consecutive slots of a digit run ----
 #pragma unroll 4
-    for (u32 i = tid; i < count; i += T1_NT) a.out[gofs[dig[i]] + i] = buf[i];
+    for (u32 i = tid; i < count; i += NT) a.out[gofs[dig[i]] + i] = buf[i];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1033,6 +1069,21 @@ static void launch_hist_text(const DeviceIndex &ix, u64 nwords_data, int D, u32 
     KERNEL_CHECK();
 }
 
+template <int NT, int IPT>
+static constexpr size_t t1_smem() {
+    return (size_t)NT * IPT * 8 + (size_t)MSD_MAXBINS * 4 * 2 + (size_t)NT * IPT * 2 + (size_t)(NT * IPT * 8 / 64 + 4) * 8 + 32 * 4;
+}
+template <int NT, int IPT, int CTAS>
+static void launch_t1_variant(const Text1Args &ta, u32 len, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<2, true, NT, IPT, CTAS>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t1_smem<NT, IPT>()));
+        configured = true;
+    }
+    msd_partition_text_kernel<2, true, NT, IPT, CTAS><<<div_up_u(len, NT * IPT), NT, t1_smem<NT, IPT>(), st>>>(ta);
+}
+
 bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     cudaStream_t st = ix.stream;
     Arena &ar = *ix.arena;
@@ -1050,7 +1101,8 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
-        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_local_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L3_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_local_sort_robust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
         configured = true;
@@ -1119,7 +1171,19 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
             case 0: msd_partition_text_kernel<1, false><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
             case 1: msd_partition_text_kernel<1, true><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
             case 2: msd_partition_text_kernel<2, false><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
-            case 3: msd_partition_text_kernel<2, true><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
+            case 3: {
+                static const int variant = env_int2("B200SA_T1_VARIANT", 0);
+                switch (variant) {
+                    case 1: launch_t1_variant<512, 8, 3>(ta, len, st); break;
+                    case 2: launch_t1_variant<256, 16, 4>(ta, len, st); break;
+                    case 3: launch_t1_variant<1024, 8, 2>(ta, len, st); break;
+                    case 4: launch_t1_variant<512, 8, 4>(ta, len, st); break;
+                    case 5: launch_t1_variant<256, 8, 7>(ta, len, st); break;
+                    case 6: launch_t1_variant<1024, 16, 1>(ta, len, st); break;
+                    default: msd_partition_text_kernel<2, true><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
+                }
+                break;
+            }
             case 4: msd_partition_text_kernel<4, false><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
             case 5: msd_partition_text_kernel<4, true><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
             case 6: msd_partition_text_kernel<8, false><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
@@ -1155,7 +1219,9 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         pa.cursor = cursor[l];
         pa.desc = desc; pa.d_ntiles = d_misc + 1;
         t = ix.timer.begin("msd_part", (double)len * 16.0);
-        msd_partition_kernel<<<std::min(grid, 2u * sm_count(ix.device)), P_NT, P_SMEM, st>>>(pa);
+        static const int p_variant = env_int2("B200SA_P_VARIANT", 0);
+        if (p_variant == 1) msd_partition_kernel<1024><<<std::min(grid, 2u * sm_count(ix.device)), 1024, P_SMEM, st>>>(pa);
+        else msd_partition_kernel<512><<<std::min(grid, 2u * sm_count(ix.device)), 512, P_SMEM, st>>>(pa);
         KERNEL_CHECK();
         ix.timer.end(t);
         std::swap(cur, other);
