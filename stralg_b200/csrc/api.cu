@@ -465,6 +465,10 @@ int b200sa_search_traffic(const b200sa_index *idx, const uint8_t *d_patterns, co
     API_GUARD_END(nullptr)
 }
 
+// Host buffers in, host (L, R) out.  The batch is cut into pieces that alternate between two
+// internal streams: while the kernel of one piece runs, the patterns of the next cross PCIe and the
+// results of the previous one return (pinned host memory makes the copies truly asynchronous;
+// pageable memory still works, staged by the driver).
 int b200sa_search_batch(const b200sa_index *idx, const uint8_t *patterns, const uint64_t *offsets,
                         uint32_t fixed_len, uint64_t npat, uint32_t *L, uint32_t *R) {
     if (!idx || (npat && (!patterns || !L || !R))) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
@@ -474,18 +478,60 @@ int b200sa_search_batch(const b200sa_index *idx, const uint8_t *patterns, const 
     const DeviceIndex &ix = idx->ix;
     CUDA_CHECK(cudaSetDevice(ix.device));
     cudaStream_t st = ix.stream;
-    uint64_t total = offsets ? offsets[npat] : (uint64_t)fixed_len * npat;
+    const uint64_t total = offsets ? offsets[npat] : (uint64_t)fixed_len * npat;
     DevBuf<u8> dp(total + 16, st);  // padded: the DNA kernel reads whole aligned 8-byte words
     DevBuf<u64> doff;
     DevBuf<u32> dL(npat, st), dR(npat, st);
-    if (total) CUDA_CHECK(cudaMemcpyAsync(dp.ptr, patterns, total, cudaMemcpyHostToDevice, st));
     if (offsets) {
         doff.alloc(npat + 1, st);
         CUDA_CHECK(cudaMemcpyAsync(doff.ptr, offsets, (npat + 1) * 8, cudaMemcpyHostToDevice, st));
     }
-    fm_search(ix, dp.ptr, offsets ? doff.ptr : nullptr, fixed_len, npat, dL.ptr, dR.ptr, st);
-    CUDA_CHECK(cudaMemcpyAsync(L, dL.ptr, npat * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaMemcpyAsync(R, dR.ptr, npat * 4, cudaMemcpyDeviceToHost, st));
+    // pieces of ~64 MB of pattern bytes, cut at multiples of 8 patterns of a fixed length that keep
+    // every piece's first byte 8-byte aligned (variable-length patterns share one base pointer)
+    const uint64_t piece_bytes = (uint64_t)64 << 20;
+    uint64_t per = npat;
+    if (total > 2 * piece_bytes) {
+        const uint64_t avg = std::max<uint64_t>(1, total / npat);
+        per = std::max<uint64_t>(1024, (piece_bytes / avg) & ~(uint64_t)7);
+    }
+    if (per >= npat) {
+        if (total) CUDA_CHECK(cudaMemcpyAsync(dp.ptr, patterns, total, cudaMemcpyHostToDevice, st));
+        fm_search(ix, dp.ptr, offsets ? doff.ptr : nullptr, fixed_len, npat, dL.ptr, dR.ptr, st);
+        CUDA_CHECK(cudaMemcpyAsync(L, dL.ptr, npat * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(R, dR.ptr, npat * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        return 0;
+    }
+    struct Lanes {
+        cudaStream_t s[2] = {nullptr, nullptr};
+        cudaEvent_t ready = nullptr;
+        ~Lanes() {
+            for (auto x : s)
+                if (x) cudaStreamDestroy(x);
+            if (ready) cudaEventDestroy(ready);
+        }
+    } lanes;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&lanes.s[0], cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&lanes.s[1], cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&lanes.ready, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventRecord(lanes.ready, st));  // the buffers (and the offsets) are allocated / copied in `st`
+    CUDA_CHECK(cudaStreamWaitEvent(lanes.s[0], lanes.ready, 0));
+    CUDA_CHECK(cudaStreamWaitEvent(lanes.s[1], lanes.ready, 0));
+    uint64_t k = 0;
+    for (uint64_t q0 = 0; q0 < npat; q0 += per, ++k) {
+        const uint64_t q1 = std::min(npat, q0 + per);
+        cudaStream_t ls = lanes.s[k & 1];
+        const uint64_t b0 = offsets ? offsets[q0] : q0 * fixed_len, b1 = offsets ? offsets[q1] : q1 * fixed_len;
+        if (b1 > b0) CUDA_CHECK(cudaMemcpyAsync(dp.ptr + b0, patterns + b0, b1 - b0, cudaMemcpyHostToDevice, ls));
+        if (offsets)  // absolute offsets: same pattern base, the piece's slice of the offset array
+            fm_search(ix, dp.ptr, doff.ptr + q0, 0, q1 - q0, dL.ptr + q0, dR.ptr + q0, ls);
+        else
+            fm_search(ix, dp.ptr + b0, nullptr, fixed_len, q1 - q0, dL.ptr + q0, dR.ptr + q0, ls);
+        CUDA_CHECK(cudaMemcpyAsync(L + q0, dL.ptr + q0, (q1 - q0) * 4, cudaMemcpyDeviceToHost, ls));
+        CUDA_CHECK(cudaMemcpyAsync(R + q0, dR.ptr + q0, (q1 - q0) * 4, cudaMemcpyDeviceToHost, ls));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(lanes.s[0]));
+    CUDA_CHECK(cudaStreamSynchronize(lanes.s[1]));
     CUDA_CHECK(cudaStreamSynchronize(st));
     return 0;
     API_GUARD_END(nullptr)

@@ -260,3 +260,44 @@ def test_device_resident_text_and_synth(engine, oracle):
         else:
             assert twords == 0 and sa_isa == 0
         idx.close()
+
+
+def test_host_batch_pipelined_pieces_equal_single_launch(engine, oracle):
+    """b200sa_search_batch cuts a large host batch into pieces that alternate between two streams
+    (copies overlap the kernels); the result must equal one launch over device-resident reads.
+    140 MB of patterns: fixed-length and variable-length (absolute offsets) entry points."""
+    import ctypes as C
+    import torch
+    n, m, npat = 1 << 20, 100, 1_400_000
+    codes = oracle.random_codes(n, 4, seed=99)
+    idx = engine.SuffixArrayIndex.build(codes[:-1], 5, textcmp=True, ktable=True)
+    lib = engine.load()
+    text = torch.from_numpy(codes).cuda()
+    reads = torch.empty(npat * m, dtype=torch.uint8, device="cuda")
+    assert lib.b200sa_synth_reads(C.c_void_p(text.data_ptr()), n, 4, C.c_void_p(reads.data_ptr()), npat, m, 102, 7,
+                                  0, None) == 0
+    Ld = torch.empty(npat, dtype=torch.int32, device="cuda")
+    Rd = torch.empty(npat, dtype=torch.int32, device="cuda")
+    idx.search_device(reads, None, m, npat, Ld, Rd)
+    torch.cuda.synchronize()
+    Le, Re = Ld.cpu().numpy().view(np.uint32), Rd.cpu().numpy().view(np.uint32)
+    h = reads.cpu().numpy()
+    L, R = idx.search(h, fixed_len=m)
+    assert np.array_equal(L, Le) and np.array_equal(R, Re) and (R > L).mean() > 0.8
+    # variable lengths: drop a different number of leading symbols from every read
+    cut = (np.arange(npat) % 7).astype(np.uint64)
+    off = np.zeros(npat + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(m - cut)
+    keep = np.ones(npat * m, dtype=bool)
+    for c in range(1, 7):
+        rows = np.nonzero(cut == c)[0]
+        for j in range(c):
+            keep[rows * m + j] = False
+    hv = h[keep]
+    assert hv.size == int(off[-1])
+    Lv, Rv = idx.search(hv, off)
+    dv, doff = torch.from_numpy(hv).cuda(), torch.from_numpy(off.view(np.int64)).cuda()
+    idx.search_device(dv, doff, 0, npat, Ld, Rd)
+    torch.cuda.synchronize()
+    assert np.array_equal(Lv, Ld.cpu().numpy().view(np.uint32)) and np.array_equal(Rv, Rd.cpu().numpy().view(np.uint32))
+    idx.close()
