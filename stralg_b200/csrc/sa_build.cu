@@ -289,14 +289,96 @@ __device__ __forceinline__ u32 lazy_rank_of(const LazyRank &lr, u32 t) {
 
 // make_keys_round: key = (rank[s] << lo_bits) | rank[s + h] for the active suffixes.
 // Active suffixes share their first h symbols with another suffix, hence s + h <= n.
+//
+// After the bucketed round 0 the rank of a retired (singleton) suffix t is the index p of its bucket
+// with sa0[p] == t: singleton positions are final, so no key has to be compared -- the VALUE t is
+// looked for.  The keys of a bucket spread evenly over its remaining bits, so p lies within a few
+// dozen entries of the interpolated index g; eight lanes read one 128-byte segment of the suffix
+// array per step (a uint4 each), starting at g's segment and widening to both sides.  One pass over
+// a warp's 32 queries = 8 rounds of 4 concurrent group scans, typically one or two steps each.
+__device__ __forceinline__ u32 scan_bucket_for(const u32 *__restrict__ sa0, u32 len, u32 t, u32 blo, u32 bhi, u32 g,
+                                               u32 gmask, u32 gbase, u32 lane, bool &ok) {
+    const u32 seglo = blo >> 5, seghi = (bhi - 1u) >> 5, seg0 = min(max(g >> 5, seglo), seghi);
+    const u32 nseg = seghi - seglo + 1u;
+    ok = false;
+    u32 pos = 0;
+    for (u32 k = 0; k < 2u * nseg + 2u; ++k) {
+        const u32 dist = (k + 1u) >> 1;
+        const bool left = (k & 1u) != 0u;
+        if (left ? seg0 < seglo + dist : seg0 + dist > seghi) continue;
+        const u32 sg = left ? seg0 - dist : seg0 + dist;
+        const u32 e0 = sg * 32u + (lane & 7u) * 4u;
+        u32 v[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (e0 + 4u <= len) {
+            const uint4 x = *(const uint4 *)(sa0 + e0);
+            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (e0 + q < len) v[q] = sa0[e0 + q];
+        }
+        u32 mine = 0xffffffffu;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (v[q] == t && e0 + q >= blo && e0 + q < bhi) mine = e0 + q;
+        const u32 bal = (__ballot_sync(gmask, mine != 0xffffffffu) >> gbase) & 0xffu;
+        if (bal) {
+            pos = __shfl_sync(gmask, mine, (int)gbase + __ffs((int)bal) - 1);
+            ok = true;
+            break;
+        }
+    }
+    return pos;
+}
+
 __global__ void __launch_bounds__(256) make_keys_round_kernel(const u32 *__restrict__ act, u32 m, LazyRank lr, u64 h,
                                                               int lo_bits, u64 *__restrict__ keys) {
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
-        u32 s = act[j];
-        u64 t = (u64)s + h;
-        u64 lo = t < lr.len ? (u64)lazy_rank_of(lr, (u32)t) : 0ull;
-        keys[j] = ((u64)lr.rank[s] << lo_bits) | lo;
+    const u64 stride = (u64)gridDim.x * blockDim.x;  // a multiple of 32: warps stay together
+    const u32 lane = threadIdx.x & 31u, gbase = lane & ~7u, gmask = 0xffu << gbase;
+    for (u64 base = (u64)blockIdx.x * blockDim.x + threadIdx.x - lane; base < m; base += stride) {
+        const u64 j = base + lane;
+        u32 s = 0, t32 = 0, blo = 0, bhi = 0, g = 0;
+        u64 lo = 0;
+        bool need = false;
+        if (j < m) {
+            s = act[j];
+            const u64 t = (u64)s + h;
+            if (t < lr.len) {
+                t32 = (u32)t;
+                if (lr.valid == nullptr || ((lr.valid[t32 >> 5] >> (t32 & 31u)) & 1u)) {
+                    lo = lr.rank[t32];
+                } else if (lr.keys0) {
+                    lo = lazy_rank_of(lr, t32);
+                } else {
+                    const int kb = lr.K * lr.bits, rbits = kb - lr.BB;
+                    const u64 key = window_at(lr.packed, t32, lr.bits) >> (64 - kb);
+                    const u64 bid = rbits > 0 ? key >> rbits : key;
+                    blo = lr.bstart[bid];
+                    bhi = lr.bstart[bid + 1];
+                    const u64 rem = rbits > 0 ? key & ((1ull << rbits) - 1ull) : 0ull;
+                    const u64 size = bhi - blo;
+                    g = blo + (u32)(rbits <= 0 ? 0ull : rbits <= 32 ? (rem * size) >> rbits : ((rem >> (rbits - 32)) * size) >> 32);
+                    need = true;
+                }
+            }
+        }
+        if (__any_sync(0xffffffffu, need)) {
+#pragma unroll 1
+            for (int r = 0; r < 8; ++r) {
+                const int src = (int)gbase + r;
+                const bool nd = __shfl_sync(0xffffffffu, (int)need, src) != 0;
+                const u32 qt = __shfl_sync(0xffffffffu, t32, src);
+                const u32 qlo = __shfl_sync(0xffffffffu, blo, src), qhi = __shfl_sync(0xffffffffu, bhi, src);
+                const u32 qg = __shfl_sync(0xffffffffu, g, src);
+                if (nd) {  // uniform over the group of eight
+                    bool ok;
+                    const u32 pos = scan_bucket_for(lr.sa0, lr.len, qt, qlo, qhi, qg, gmask, gbase, lane, ok);
+                    if ((int)lane == src) lo = ok ? (u64)pos : (u64)lazy_rank_of(lr, qt);
+                }
+                __syncwarp();
+            }
+        }
+        if (j < m) keys[j] = ((u64)lr.rank[s] << lo_bits) | lo;
     }
 }
 
