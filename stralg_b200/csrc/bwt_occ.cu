@@ -66,20 +66,39 @@ __global__ void __launch_bounds__(OD_NT) occ_dna_count_kernel(const u8 *__restri
     if (b < nblocks) {
         const uint4 *src = (const uint4 *)(bwt + b * 64);
         u64 w[2] = {0, 0};
+        u32 zero_rows = 0;  // rows holding code 0 (the sentinel row, padding after the last row): packed as 0
+        const u64 ones = 0x0101010101010101ull, high = 0x8080808080808080ull;
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-            uint4 x = ld_stream_u128(src + v);
-            u32 words[4] = {x.x, x.y, x.z, x.w};
+            const uint4 x = ld_stream_u128(src + v);
+            const u64 half[2] = {((u64)x.y << 32) | x.x, ((u64)x.w << 32) | x.z};
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                u32 code = (words[q >> 2] >> (8 * (q & 3))) & 0xffu;
-                int k = v * 16 + q;
-                u32 sym = code ? code - 1 : 0;
-#pragma unroll
-                for (int x4 = 0; x4 < 4; ++x4) cnt[x4] += (code == (u32)(x4 + 1));
-                w[k >> 5] |= (u64)(sym & 3u) << (2 * (k & 31));
+            for (int hh = 0; hh < 2; ++hh) {
+                // eight rows at a time: symbol = code - 1 (rows with code 0 are patched to code 1 first),
+                // row k of the block at bits [2k, 2k+1] of word k / 32
+                u64 c8 = half[hh];
+                const u64 low7 = 0x7f7f7f7f7f7f7f7full;
+                const u64 z = ~(((c8 & low7) + low7) | c8) & high;  // 0x80 exactly in the bytes that are zero
+                if (z) {
+                    c8 |= z >> 7;  // 0 -> 1
+                    zero_rows += (u32)__popcll(z);
+                }
+                u64 y = (c8 - ones) & 0x0303030303030303ull;
+                y = (y | (y >> 6)) & 0x000F000F000F000Full;
+                y = (y | (y >> 12)) & 0x000000FF000000FFull;
+                y = (y | (y >> 24)) & 0xFFFFull;
+                const int k0 = v * 16 + hh * 8;
+                w[k0 >> 5] |= y << (2 * (k0 & 31));
             }
         }
+#pragma unroll
+        for (u32 c = 0; c < 4; ++c) {
+            const u64 p = c * 0x5555555555555555ull;
+            const u64 y0 = w[0] ^ p, y1 = w[1] ^ p;
+            cnt[c] = (u32)__popcll(~(y0 | (y0 >> 1)) & 0x5555555555555555ull) +
+                     (u32)__popcll(~(y1 | (y1 >> 1)) & 0x5555555555555555ull);
+        }
+        cnt[0] -= zero_rows;  // they are not occurrences of code 1
         DnaBlock blk;
         blk.cnt[0] = cnt[0]; blk.cnt[1] = cnt[1]; blk.cnt[2] = cnt[2]; blk.cnt[3] = cnt[3];
         blk.bits[0] = w[0];

@@ -246,23 +246,49 @@ __global__ void __launch_bounds__(256) msd_tile_desc_kernel(const u32 *__restric
     }
 }
 
-// digit histogram of one level >= 2 (per parent), from the elements the previous level wrote
+// digit histogram of one level >= 2 (per parent), from the elements the previous level wrote.
+// A CTA takes a CONTIGUOUS range of tiles: consecutive tiles mostly share their parent, so the
+// shared-memory counts are added to the parent's global row only when the parent changes (a few
+// million global atomics for the whole level instead of one per tile and digit).
 __global__ void __launch_bounds__(P_NT) msd_hist_elems_kernel(const u64 *__restrict__ in, const uint4 *__restrict__ desc,
                                                               const u32 *__restrict__ d_ntiles, int D, int dshift,
                                                               u32 *__restrict__ hist) {
-    if (blockIdx.x >= *d_ntiles) return;
+    const u32 ntiles = *d_ntiles;
+    const u32 per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const u32 t0 = blockIdx.x * per, t1 = min(ntiles, t0 + per);
+    if (t0 >= t1) return;
     __shared__ u32 sh[P_MAXBINS];
     const u32 B = 1u << D;
     for (u32 i = threadIdx.x; i < B; i += P_NT) sh[i] = 0;
     __syncthreads();
-    const uint4 ds = desc[blockIdx.x];
-    const u64 *src = in + ds.x;
-    for (u32 i = threadIdx.x; i < ds.y; i += P_NT) {
-        u64 e = ld_stream_u64(src + i);
-        atomicAdd(&sh[(u32)(e >> dshift) & (B - 1)], 1u);
+    u32 parent = desc[t0].z;
+    uint4 ds = desc[t0];
+    for (u32 t = t0; t < t1; ++t) {
+        const uint4 nx = t + 1 < t1 ? desc[t + 1] : ds;
+        if (ds.z != parent) {  // uniform over the CTA
+            __syncthreads();
+            u32 *h = hist + (size_t)parent * B;
+            for (u32 i = threadIdx.x; i < B; i += P_NT) {
+                if (sh[i]) atomicAdd(&h[i], sh[i]);
+                sh[i] = 0;
+            }
+            __syncthreads();
+            parent = ds.z;
+        }
+        const u64 *src = in + ds.x;
+        // four loads in flight per thread before the first shared atomic
+        for (u32 i = threadIdx.x; i < ds.y; i += 4 * P_NT) {
+            u64 e[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) e[q] = i + q * P_NT < ds.y ? ld_stream_u64(src + i + q * P_NT) : 0ull;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (i + q * P_NT < ds.y) atomicAdd(&sh[(u32)(e[q] >> dshift) & (B - 1)], 1u);
+        }
+        ds = nx;
     }
     __syncthreads();
-    u32 *h = hist + (size_t)ds.z * B;
+    u32 *h = hist + (size_t)parent * B;
     for (u32 i = threadIdx.x; i < B; i += P_NT)
         if (sh[i]) atomicAdd(&h[i], sh[i]);
 }
@@ -1204,7 +1230,7 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         msd_tile_desc_kernel<<<div_up_u(nparents, 8), 256, 0, st>>>(start[l - 1], nparents, tile_off, desc);
         KERNEL_CHECK();
         const unsigned grid = (unsigned)desc_cap;
-        msd_hist_elems_kernel<<<grid, P_NT, 0, st>>>(cur, desc, d_misc + 1, pl.D[l], dshift, cursor[l]);
+        msd_hist_elems_kernel<<<std::min(grid, 4u * sm_count(ix.device)), P_NT, 0, st>>>(cur, desc, d_misc + 1, pl.D[l], dshift, cursor[l]);
         KERNEL_CHECK();
         {
             unsigned bd = std::min(1024u, std::max(32u, 1u << pl.D[l]));

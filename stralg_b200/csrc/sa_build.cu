@@ -42,12 +42,41 @@ __global__ void __launch_bounds__(256) pack_kernel(const u8 *__restrict__ text, 
     __shared__ u32 sh_counts[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sh_counts[i] = 0;
     __syncthreads();
-    u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     bool bad = false;
-    if (w < nwords) {
+    // grid-stride: a block's symbol counts reach the global counters once, not once per 256 words
+    for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (u64)gridDim.x * blockDim.x) {
         u64 t0 = w * CPW;
         u64 word = 0;
-        if (t0 < n) {
+        if (BITS == 2 && t0 + CPW <= n && ((((uintptr_t)(text + t0)) & 31) == 0)) {
+            // DNA fast path: 32 codes in one 256-bit load, packed eight at a time without a byte loop
+            u64 x[4];
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                         : "=l"(x[0]), "=l"(x[1]), "=l"(x[2]), "=l"(x[3]) : "l"(text + t0));
+            const u64 ones = 0x0101010101010101ull, high = 0x8080808080808080ull;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const u64 v = x[h];
+                // a code is valid when it is in 1..sigma-1: no byte >= 128, none zero, none >= sigma
+                const u64 zero = (v - ones) & ~v & high;
+                const u64 big = (v | (v + ones * (u64)(0x80u - sigma))) & high;
+                if (zero | big) bad = true;
+                // symbols = code - 1, first text byte to the most significant end
+                const u32 lo32 = (u32)v, hi32 = (u32)(v >> 32);
+                u64 y = ((u64)__byte_perm(lo32, 0, 0x0123) << 32) | (u64)__byte_perm(hi32, 0, 0x0123);
+                y = (y - ones) & 0x0303030303030303ull;
+                y = (y | (y >> 6)) & 0x000F000F000F000Full;
+                y = (y | (y >> 12)) & 0x000000FF000000FFull;
+                y = (y | (y >> 24)) & 0xFFFFull;
+                word |= y << (48 - 16 * h);
+            }
+#pragma unroll
+            for (u32 c = 0; c < 4; ++c) {
+                const u64 yy = word ^ (c * 0x5555555555555555ull);
+                const u32 cx = (u32)__popcll(~(yy | (yy >> 1)) & 0x5555555555555555ull);
+                const u32 tot = __reduce_add_sync(__activemask(), cx);
+                if ((threadIdx.x & 31u) == (u32)(__ffs((int)__activemask()) - 1) && tot) atomicAdd(&sh_counts[c + 1], tot);
+            }
+        } else if (t0 < n) {
             // the CPW text bytes of this word, fetched with the widest loads (one 256-bit load for DNA)
             __align__(32) u8 b[CPW];
             const u8 *src = text + t0;
@@ -738,7 +767,7 @@ void pack_text(DeviceIndex &ix, int *d_err) {
     unsigned long long *counts = ix.arena->get<unsigned long long>(256);
     CUDA_CHECK(cudaMemsetAsync(counts, 0, 256 * 8, st));
     int tid = ix.timer.begin("pack_text", (double)ix.len * (1.0 + b / 8.0));
-    unsigned blocks = div_up_u(nwords, 256);
+    unsigned blocks = std::max(1u, std::min(div_up_u(nwords, 256), 148u * 8u));
     switch (b) {
         case 1: pack_kernel<1><<<blocks, 256, 0, st>>>(ix.text_ptr, ix.n, ix.sigma, nwords, ix.packed, counts, d_err); break;
         case 2: pack_kernel<2><<<blocks, 256, 0, st>>>(ix.text_ptr, ix.n, ix.sigma, nwords, ix.packed, counts, d_err); break;
