@@ -742,14 +742,16 @@ __device__ __forceinline__ u32 bytesum(u32 x) { return __dp4a(x, 0x01010101u, 0u
 // warp's critical path and the next tile's first pass reads L2, not HBM.
 __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *X = (u64 *)smem_raw + L3_PAD;                // [-PAD, CAP + PAD) elements grouped by bin, guards around them
-    u32 *cnt = (u32 *)(X + L3_CAP + L3_PAD);          // [L3_CNTN] four byte-wide sub-bin counts per position
+    // elements grouped by bin, as two word arrays (neighbouring high words sit in neighbouring banks):
+    u32 *Xhi = (u32 *)smem_raw + L3_PAD;              // [-PAD, CAP + PAD) [rest of key | preceding symbol], guards around
+    u32 *Xlo = Xhi + L3_CAP + L3_PAD;                 // [0, CAP + PAD) suffix starts
+    u32 *cnt = Xlo + L3_CAP + L3_PAD;                 // [L3_CNTN] four byte-wide sub-bin counts per position
     u16 *pre = (u16 *)(cnt + L3_CNTN);                // [L3_CNTN] exclusive prefix of the per-position totals
     u32 *segmask = (u32 *)(pre + L3_CNTN);            // [MASKW + 1]
     u32 *segpre = segmask + (L3_MASKW + 1);           // [MASKW + 1]
     u32 *misc = segpre + (L3_MASKW + 1);              // [64]
     u32 *nxt = misc + 64;                             // [8] next tile: index, b0, b1, E0, M
-    uint2 *segtab = (uint2 *)X;                       // aliases X until the elements are scattered
+    uint2 *segtab = (uint2 *)Xhi;                     // aliases the element arrays until the elements are scattered
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const u32 remmask = a.R >= 32 ? ~0u : ((1u << a.R) - 1u);
     const u32 remsh = a.R > 0 ? 32u - (u32)a.R : 0u;  // R == 0: every key of a bucket is equal, rem == 0
@@ -777,7 +779,7 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
     // the counters of the first tile (later tiles: zeroed again right after their last use)
     for (u32 i = tid; i < (u32)L3_CNTN; i += L3_NT) cnt[i] = 0;
     // left guards: the smallest key, never "larger than" an element (pass 3)
-    if (tid < (u32)L3_PAD) X[-(int)tid - 1] = 0ull;
+    if (tid < (u32)L3_PAD) Xhi[-(int)tid - 1] = 0u;
     if (tid == 0) misc[32] = 0;  // largest slot seen in the tile
 
     while (true) {
@@ -892,11 +894,14 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
                 if (i < M) {
                     const u32 word = meta[j] & 8191u, sub8 = (meta[j] >> 13) & 31u, slot = meta[j] >> 18;
                     const u32 below = bytesum(cnt[word] & ((1u << sub8) - 1u));
-                    X[(u32)pre[word] + below + slot] = src[i];
+                    const u64 e = src[i];
+                    const u32 at = (u32)pre[word] + below + slot;
+                    Xhi[at] = (u32)(e >> 32);
+                    Xlo[at] = (u32)e;
                 }
             }
             // right guards: the largest key, never "smaller than" an element
-            if (tid < W) X[M + tid] = ~0ull;
+            if (tid < W) Xhi[M + tid] = ~0u;
         }
         __syncthreads();
 
@@ -918,10 +923,9 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
         // parent, so bucket boundaries need a check only in tiles that span two parents
         // (always with a single level).  Equal keys (a short suffix next to its padded twin, or
         // long suffixes that stay active) are rare and take the tie-break path. ----
-        const u32 *Xh = (const u32 *)X;
         const u32 pbmask = (1u << a.pb) - 1u;
         for (u32 p = tid; p < M; p += L3_NT) {
-            const u32 hp = Xh[2 * p + 1];
+            const u32 hp = Xhi[p];
             u32 r = p;
             bool eq = false;
             if (!segcheck) {
@@ -929,7 +933,7 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
                 // a < (b & ~mask) likewise; the guards on both sides of X make bounds checks unnecessary
                 const u32 hp_hi = hp | pbmask, hp_lo = hp & ~pbmask;
                 for (u32 d = 1; d <= W; ++d) {
-                    const u32 hl = Xh[2 * (int)(p - d) + 1], hr = Xh[2 * (p + d) + 1];
+                    const u32 hl = Xhi[(int)(p - d)], hr = Xhi[p + d];
                     r -= hl > hp_hi ? 1u : 0u;
                     r += hr < hp_lo ? 1u : 0u;
                     eq = eq || ((hl ^ hp) <= pbmask) || ((hr ^ hp) <= pbmask);
@@ -944,19 +948,19 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
                     if (lv && ((segmask[xl >> 5] >> (xl & 31u)) & 1u)) lv = false;
                     if (rv && ((segmask[xr >> 5] >> (xr & 31u)) & 1u)) rv = false;
                     if (lv) {
-                        const u32 ko = Xh[2 * (p - d) + 1] >> a.pb;
+                        const u32 ko = Xhi[p - d] >> a.pb;
                         r -= ko > kp ? 1u : 0u;
                         eq = eq || ko == kp;
                     }
                     if (rv) {
-                        const u32 ko = Xh[2 * (p + d) + 1] >> a.pb;
+                        const u32 ko = Xhi[p + d] >> a.pb;
                         r += ko < kp ? 1u : 0u;
                         eq = eq || ko == kp;
                     }
                 }
             }
             const u32 kp = hp >> a.pb;
-            const u64 e = X[p];
+            const u64 e = ((u64)hp << 32) | (u64)Xlo[p];
             bool active = false;
             u32 head = r;
             if (eq) {
@@ -974,15 +978,15 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
                         if (lv && ((segmask[xl >> 5] >> (xl & 31u)) & 1u)) lv = false;
                         if (rv && ((segmask[xr >> 5] >> (xr & 31u)) & 1u)) rv = false;
                     }
-                    if (lv && (Xh[2 * (p - d) + 1] >> a.pb) == kp) {
-                        const u32 so = Xh[2 * (p - d)];
+                    if (lv && (Xhi[p - d] >> a.pb) == kp) {
+                        const u32 so = Xlo[p - d];
                         const bool o_short = is_short_suffix(so, a.K, a.n);
                         // the left neighbour belongs AFTER this element
                         if (o_short ? (e_short && so < se) : e_short) --r;
                         if (!o_short && !e_short) { active = true; ++longs_before; }
                     }
-                    if (rv && (Xh[2 * (p + d) + 1] >> a.pb) == kp) {
-                        const u32 so = Xh[2 * (p + d)];
+                    if (rv && (Xhi[p + d] >> a.pb) == kp) {
+                        const u32 so = Xlo[p + d];
                         const bool o_short = is_short_suffix(so, a.K, a.n);
                         // the right neighbour belongs BEFORE this element
                         if (o_short ? (!e_short || so > se) : false) ++r;
