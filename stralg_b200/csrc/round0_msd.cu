@@ -475,8 +475,7 @@ static constexpr int T1_NT = 512;
 static constexpr int T1_IPT = 16;
 static constexpr int T1_TILE = T1_NT * T1_IPT;     // 8192 suffix starts
 static constexpr int T1_STAGE_MAX = T1_TILE * 8 / 64 + 4;
-static constexpr size_t T1_SMEM = (size_t)T1_TILE * 8 + (size_t)MSD_MAXBINS * 4 * 2 + (size_t)T1_TILE * 2 +
-                                  (size_t)T1_STAGE_MAX * 8 + 32 * 4;
+static constexpr size_t T1_SMEM = (size_t)T1_TILE * 8 + (size_t)MSD_MAXBINS * 4 * 2 + (size_t)T1_STAGE_MAX * 8 + 32 * 4;
 
 struct Text1Args {
     const u64 *packed;
@@ -509,8 +508,8 @@ __global__ void __launch_bounds__(NT, CTAS) msd_partition_text_kernel(Text1Args 
     u64 *stage = buf + TILE;                   // [STAGE_MAX] packed text of the tile (one word of lead-in)
     u32 *hist = (u32 *)(stage + STAGE_MAX);    // [MAXBINS] counts, then tile-local offsets
     u32 *gofs = hist + MSD_MAXBINS;               // [MAXBINS] global slot of the digit's run minus its tile offset
-    u16 *dig = (u16 *)(gofs + MSD_MAXBINS);       // [TILE] digit of the element in slot i
-    u32 *wsum = (u32 *)(dig + TILE);           // [32]
+    u32 *wsum = gofs + MSD_MAXBINS;               // [32]
+    static_assert(TILE <= (1 << 14) && MSD_MAXBINS <= (1 << 10), "tile-local low word: 14 bits of position, 10 of digit");
 
     constexpr int b = BITS;
     constexpr u32 lead = HAS_PREV ? (u32)BITS : 0u;
@@ -591,7 +590,6 @@ __global__ void __launch_bounds__(NT, CTAS) msd_partition_text_kernel(Text1Args 
 
     // ---- form the elements (again from the staged text) and group the tile by digit.  An
     // element is two 32-bit words: [rest of key | preceding symbol] and the suffix start ----
-    const u32 p0 = (u32)begin + i0;
 #pragma unroll
     for (int g = 0; g < IPT / 8; ++g) {
         u64 H, L;
@@ -606,8 +604,9 @@ __global__ void __launch_bounds__(NT, CTAS) msd_partition_text_kernel(Text1Args 
                 const u32 hiw = HAS_PREV ? (rest << b) | (u32)(win >> (64 - b)) : rest;
                 const u32 d = ds[j] & 1023u;
                 const u32 pos = hist[d] + (ds[j] >> 10);
-                buf[pos] = ((u64)hiw << 32) | (u64)(p0 + (u32)j);
-                dig[pos] = (u16)d;
+                // in shared memory the low word is [digit : 10 | position in the tile : 14]; the
+                // write-out turns it into the suffix start
+                buf[pos] = ((u64)hiw << 32) | (u64)((d << 14) | (i0 + (u32)j));
             }
         }
     }
@@ -622,8 +621,13 @@ __global__ void __launch_bounds__(NT, CTAS) msd_partition_text_kernel(Text1Args 
     __syncthreads();
 
     // ---- consecutive threads write consecutive slots of a digit run ----
+    const u32 begin32 = (u32)begin;
 #pragma unroll 4
-    for (u32 i = tid; i < count; i += NT) a.out[gofs[dig[i]] + i] = buf[i];
+    for (u32 i = tid; i < count; i += NT) {
+        const u64 v = buf[i];
+        const u32 lo = (u32)v;
+        a.out[gofs[lo >> 14] + i] = (v & 0xffffffff00000000ull) | (u64)(begin32 + (lo & 16383u));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1101,7 +1105,7 @@ static void launch_hist_text(const DeviceIndex &ix, u64 nwords_data, int D, u32 
 
 template <int NT, int IPT>
 static constexpr size_t t1_smem() {
-    return (size_t)NT * IPT * 8 + (size_t)MSD_MAXBINS * 4 * 2 + (size_t)NT * IPT * 2 + (size_t)(NT * IPT * 8 / 64 + 4) * 8 + 32 * 4;
+    return (size_t)NT * IPT * 8 + (size_t)MSD_MAXBINS * 4 * 2 + (size_t)(NT * IPT * 8 / 64 + 4) * 8 + 32 * 4;
 }
 template <int NT, int IPT, int CTAS>
 static void launch_t1_variant(const Text1Args &ta, u32 len, cudaStream_t st) {
@@ -1210,6 +1214,7 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
                     case 4: launch_t1_variant<512, 8, 4>(ta, len, st); break;
                     case 5: launch_t1_variant<256, 8, 7>(ta, len, st); break;
                     case 6: launch_t1_variant<1024, 16, 1>(ta, len, st); break;
+                    case 7: launch_t1_variant<512, 16, 3>(ta, len, st); break;
                     default: msd_partition_text_kernel<2, true><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
                 }
                 break;
