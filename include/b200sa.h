@@ -111,6 +111,13 @@ int b200sa_copy_bwt(const b200sa_index *idx, uint8_t *host);
 int b200sa_copy_c_table(const b200sa_index *idx, uint32_t *host /* sigma entries */);
 /* The sampled O table as stored (b200sa_stats.occ_bytes bytes; layout in stralg_b200/csrc/occ.cuh). */
 int b200sa_copy_occ(const b200sa_index *idx, uint8_t *host);
+/* Asynchronous variant: enqueues the copy of one table on `stream` (a cudaStream_t) and returns;
+ * `host` should be pinned memory, and the index must stay alive until the stream has passed the
+ * copy.  Lets a caller that builds index after index overlap the transfer of one result with the
+ * construction of the next (bench.py's end-to-end loop). */
+enum b200sa_table { B200SA_TABLE_SA = 0, B200SA_TABLE_ISA = 1, B200SA_TABLE_LCP = 2, B200SA_TABLE_BWT = 3,
+                    B200SA_TABLE_OCC = 4 };
+int b200sa_copy_async(const b200sa_index *idx, int what, void *host, void *stream);
 /* Dense O table in the reference layout o[i * sigma + a], i in [0, len] (bwt.c:47-65).
  * Fails with B200SA_ERR_TOO_LARGE where the reference's own u32 size computation overflows. */
 int b200sa_copy_o_dense(const b200sa_index *idx, uint32_t *host /* (len + 1) * sigma */);

@@ -63,6 +63,7 @@ SIGNATURES = {
     "b200sa_copy_bwt": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200sa_copy_c_table": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200sa_copy_occ": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200sa_copy_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "b200sa_launch_count": (C.c_uint64, []),
     "b200sa_workspace_bytes": (C.c_uint64, [C.c_int]),
     "b200sa_release_workspace": (C.c_int, [C.c_int]),

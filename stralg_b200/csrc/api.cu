@@ -380,6 +380,27 @@ int b200sa_copy_bwt(const b200sa_index *idx, uint8_t *host) {
 int b200sa_copy_occ(const b200sa_index *idx, uint8_t *host) {
     return copy_out(idx, idx ? idx->ix.occ.ptr : nullptr, host, idx ? idx->ix.occ.bytes() : 0, "O table");
 }
+// Asynchronous copy of one table into caller-owned (pinned) host memory, ordered on `stream`.
+int b200sa_copy_async(const b200sa_index *idx, int what, void *host, void *stream) {
+    if (!idx || !host) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    const DeviceIndex &ix = idx->ix;
+    const void *src = nullptr;
+    size_t bytes = 0;
+    switch (what) {
+        case B200SA_TABLE_SA: src = ix.sa.ptr; bytes = (size_t)ix.len * 4; break;
+        case B200SA_TABLE_ISA: src = ix.isa.ptr; bytes = (size_t)ix.len * 4; break;
+        case B200SA_TABLE_LCP: src = ix.lcp.ptr; bytes = (size_t)ix.len * 4; break;
+        case B200SA_TABLE_BWT: src = ix.bwt.ptr; bytes = (size_t)ix.len; break;
+        case B200SA_TABLE_OCC: src = ix.occ.ptr; bytes = ix.occ.bytes(); break;
+        default: return fail(B200SA_ERR_BAD_ARGUMENT, "unknown table", nullptr);
+    }
+    if (!src) return fail(B200SA_ERR_NOT_BUILT, "table was not requested at build time (or was dropped)", nullptr);
+    API_GUARD_BEGIN
+    CUDA_CHECK(cudaSetDevice(ix.device));
+    CUDA_CHECK(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return 0;
+    API_GUARD_END(nullptr)
+}
 uint64_t b200sa_launch_count(void) { return b200sa::g_kernel_launches; }
 uint64_t b200sa_workspace_bytes(int device) { return g_arena[device & 63].reserved(); }
 int b200sa_release_workspace(int device) {
