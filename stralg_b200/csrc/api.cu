@@ -52,6 +52,41 @@ static enum b200sa_error code_of(cudaError_t e) {
         return fail(B200SA_ERR_INTERNAL, e.what(), errptr);                      \
     }
 
+namespace b200sa {
+__global__ void read_back_kernel(const u32 *__restrict__ src, u32 *__restrict__ dst, u32 words) {
+    for (u32 i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+}
+namespace {
+struct Mailbox {  // one per host thread and device: 4 KB of mapped pinned memory
+    u32 *host[64] = {};
+    u32 *dev[64] = {};
+    ~Mailbox() {
+        for (auto p : host)
+            if (p) cudaFreeHost(p);
+    }
+};
+thread_local Mailbox t_mailbox;
+}  // namespace
+void read_back(void *dst, const void *dev_src, size_t bytes, cudaStream_t st) {
+    int device = 0;
+    CUDA_CHECK(cudaGetDevice(&device));
+    Mailbox &mb = t_mailbox;
+    if (bytes > 4096 || (bytes & 3) || device < 0 || device >= 64) {  // not a mailbox case: plain copy
+        CUDA_CHECK(cudaMemcpyAsync(dst, dev_src, bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        return;
+    }
+    if (!mb.host[device]) {
+        CUDA_CHECK(cudaHostAlloc((void **)&mb.host[device], 4096, cudaHostAllocMapped));
+        CUDA_CHECK(cudaHostGetDevicePointer((void **)&mb.dev[device], mb.host[device], 0));
+    }
+    read_back_kernel<<<1, 64, 0, st>>>((const u32 *)dev_src, mb.dev[device], (u32)(bytes / 4));
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    memcpy(dst, mb.host[device], bytes);
+}
+}  // namespace b200sa
+
 static Arena g_arena[64];
 static std::mutex g_arena_mu[64];
 
@@ -203,8 +238,7 @@ __attribute__((visibility("hidden"))) static int build_into(b200sa_index *h, con
     CUDA_CHECK(cudaMemsetAsync(d_err.ptr, 0, 4, st));
     pack_text(ix, d_err.ptr);
     int herr = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&herr, d_err.ptr, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    read_back(&herr, d_err.ptr, 4, st);
     if (herr) {
         ix.arena = nullptr;
         return fail(B200SA_ERR_BAD_SYMBOL, "text holds a code outside 1..sigma-1", err);
@@ -359,7 +393,10 @@ static int copy_out(const b200sa_index *idx, const void *dptr, void *host, size_
     if (!dptr) return fail(B200SA_ERR_NOT_BUILT, std::string(what) + " was not requested at build time", nullptr);
     API_GUARD_BEGIN
     CUDA_CHECK(cudaSetDevice(idx->ix.device));
-    CUDA_CHECK(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, idx->ix.stream));
+    const size_t piece = (size_t)32 << 20;  // (pieces measured faster than one multi-gigabyte copy: 57 vs 52 GB/s)
+    for (size_t at = 0; at < bytes; at += piece)
+        CUDA_CHECK(cudaMemcpyAsync((char *)host + at, (const char *)dptr + at, std::min(piece, bytes - at),
+                                   cudaMemcpyDeviceToHost, idx->ix.stream));
     CUDA_CHECK(cudaStreamSynchronize(idx->ix.stream));
     return 0;
     API_GUARD_END(nullptr)
@@ -397,7 +434,12 @@ int b200sa_copy_async(const b200sa_index *idx, int what, void *host, void *strea
     if (!src) return fail(B200SA_ERR_NOT_BUILT, "table was not requested at build time (or was dropped)", nullptr);
     API_GUARD_BEGIN
     CUDA_CHECK(cudaSetDevice(ix.device));
-    CUDA_CHECK(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    // in pieces: the device-to-host copy engine serves one copy at a time, and a build running next to
+    // this transfer reads a few words back per stage -- those must not queue behind gigabytes
+    const size_t piece = (size_t)32 << 20;
+    for (size_t at = 0; at < bytes; at += piece)
+        CUDA_CHECK(cudaMemcpyAsync((char *)host + at, (const char *)src + at, std::min(piece, bytes - at),
+                                   cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return 0;
     API_GUARD_END(nullptr)
 }

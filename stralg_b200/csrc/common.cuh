@@ -169,6 +169,13 @@ struct Arena {
 
 static inline unsigned div_up_u(u64 a, u64 b) { return (unsigned)((a + b - 1) / b); }
 
+// Small device-to-host read-back (<= 4 KB, a multiple of 4 bytes) that stays off the copy engines: a
+// one-warp kernel stores the words into mapped pinned host memory, the stream is synchronised, the
+// words are handed to `dst`.  The copy engines serve transfers in submission order, so a build that
+// runs next to a multi-gigabyte device-to-host transfer (b200sa_copy_async) would otherwise wait
+// for it every time it looks at a counter.  Defined in api.cu.
+void read_back(void *dst, const void *dev_src, size_t bytes, cudaStream_t st);
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;

@@ -1265,8 +1265,7 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
 
     // ---- do the buckets fit one SM? ----
     u32 maxbucket = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&maxbucket, d_misc, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    read_back(&maxbucket, d_misc, 4, st);
     if (maxbucket > (u32)L3_MAXB) return false;
 
     // ---- in-SM sort of every bucket, outputs of round 0 ----
@@ -1287,13 +1286,11 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     msd_local_sort_kernel<<<std::min(ntl3, (unsigned)L3_CTAS * sm_count(ix.device)), L3_NT, L3_SMEM, st>>>(la);
     KERNEL_CHECK();
     u32 hmisc[8];
-    CUDA_CHECK(cudaMemcpyAsync(hmisc, d_misc, sizeof hmisc, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    read_back(hmisc, d_misc, sizeof hmisc, st);
     if (hmisc[4]) {
         msd_local_sort_robust_kernel<<<hmisc[4], L3_NT, RB_SMEM, st>>>(la);
         KERNEL_CHECK();
-        CUDA_CHECK(cudaMemcpyAsync(hmisc, d_misc, sizeof hmisc, cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        read_back(hmisc, d_misc, sizeof hmisc, st);
     }
     ix.timer.end(t);
 

@@ -777,8 +777,7 @@ void pack_text(DeviceIndex &ix, int *d_err) {
     KERNEL_CHECK();
     ix.timer.end(tid);
     unsigned long long hc[256];
-    CUDA_CHECK(cudaMemcpyAsync(hc, counts, sizeof hc, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    read_back(hc, counts, sizeof hc, st);
     // C table (stralg/bwt.c:35-45): the sentinel is the single occurrence of code 0
     for (int i = 0; i < 256; ++i) ix.sym_counts_host[i] = hc[i];
     ix.sym_counts_host[0] = 1;
@@ -813,8 +812,7 @@ static u32 count_active(const u8 *headbits, u32 m, u32 *tile_counts, unsigned lo
     scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_counts, ntiles, d_total);
     KERNEL_CHECK();
     unsigned long long total = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    read_back(&total, d_total, 8, st);
     return (u32)total;
 }
 static void scatter_active(const u8 *headbits, const u32 *vals, u32 m, const u32 *tile_offsets, u32 *out,
@@ -1002,8 +1000,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
             t = ix.timer.begin("round_hist", (double)m * 8.0);
             S::histogram(rkA, m, 0, key_bits, npass, hist, st);
             S::scan(hist, m, npass, uniform, st);
-            CUDA_CHECK(cudaMemcpyAsync(huniform, uniform, (size_t)npass * 4, cudaMemcpyDeviceToHost, st));
-            CUDA_CHECK(cudaStreamSynchronize(st));
+            read_back(huniform, uniform, (size_t)npass * 4, st);
             ix.timer.end(t);
             u64 *rin = rkA, *rout = rkB;
             u32 *ain = act, *aout = act2;
@@ -1041,8 +1038,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 throw std::runtime_error("prefix doubling failed to converge (internal error)");
         }
     }
-    CUDA_CHECK(cudaMemcpyAsync(&ix.primary, d_primary.ptr, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    read_back(&ix.primary, d_primary.ptr, 4, st);
     if (want_bwt && !bwt_in_sort) gather_bwt(ix);  // the element had no room for the preceding symbol
 }
 
