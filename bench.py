@@ -435,7 +435,7 @@ def gpu_arm(args, rank, local_rank, world):
                 t_ser.append(time.perf_counter() - t0)
                 idx.close()
             serial = float(np.mean(t_ser[1:]))
-            e_steps = max(args.steps, 4) if nbuf == 2 else max(1, min(args.steps, 2))
+            e_steps = max(args.steps, 6) if nbuf == 2 else max(1, min(args.steps, 2))
             copy_stream = torch.cuda.Stream(device=dev)
             cs = copy_stream.cuda_stream
             def run_steps(count):

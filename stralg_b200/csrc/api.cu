@@ -2,6 +2,7 @@
 #include "../../include/b200sa.h"
 #include "engine.h"
 
+#include <map>
 #include <mutex>
 #include <new>
 #include <string.h>
@@ -84,6 +85,63 @@ void read_back(void *dst, const void *dev_src, size_t bytes, cudaStream_t st) {
     KERNEL_CHECK();
     CUDA_CHECK(cudaStreamSynchronize(st));
     memcpy(dst, mb.host[device], bytes);
+}
+}  // namespace b200sa
+
+namespace b200sa {
+namespace {
+std::mutex g_cache_mu;
+std::multimap<std::pair<int, size_t>, void *> g_cache;  // (device, bytes) -> free block
+}  // namespace
+void *output_cache_get(size_t bytes) {
+    int device = 0;
+    CUDA_CHECK(cudaGetDevice(&device));
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        auto it = g_cache.find({device, bytes});
+        if (it != g_cache.end()) {
+            void *p = it->second;
+            g_cache.erase(it);
+            return p;
+        }
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation) {  // give the cached blocks back and try once more
+        cudaGetLastError();
+        output_cache_purge(device);
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) throw CudaFailure(e, "cudaMalloc (output table)", __FILE__, __LINE__);
+    return p;
+}
+void output_cache_put(void *ptr, size_t bytes) {
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess) device = at.device;
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    // keep at most two blocks of a size (one index alive + one being built) and 40 GB per device; the
+    // rest goes back to the driver
+    size_t held = 0;
+    for (auto &kv : g_cache)
+        if (kv.first.first == device) held += kv.first.second;
+    if (g_cache.count({device, bytes}) >= 2 || held + bytes > ((size_t)40 << 30)) {
+        cudaFree(ptr);
+        return;
+    }
+    g_cache.insert({{device, bytes}, ptr});
+}
+void output_cache_purge(int device) {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    for (auto it = g_cache.begin(); it != g_cache.end();) {
+        if (it->first.first == device) {
+            cudaFree(it->second);
+            it = g_cache.erase(it);
+        } else {
+            ++it;
+        }
+    }
 }
 }  // namespace b200sa
 
@@ -255,7 +313,7 @@ __attribute__((visibility("hidden"))) static int build_into(b200sa_index *h, con
     if (flags & B200SA_BUILD_OCC) build_bwt_tables(ix, flags & B200SA_BUILD_BWT);
     if (flags & B200SA_BUILD_TEXTCMP) {
         size_t words = ((size_t)ix.len + ix.pk.cpw - 1) / ix.pk.cpw + 4;
-        ix.text_packed.alloc(words, st);
+        ix.text_packed.alloc_output(words, st);
         CUDA_CHECK(cudaMemcpyAsync(ix.text_packed.ptr, ix.packed, words * 8, cudaMemcpyDeviceToDevice, st));
     }
     ix.packed = nullptr;
@@ -450,6 +508,7 @@ int b200sa_release_workspace(int device) {
     CUDA_CHECK(cudaSetDevice(device));
     std::lock_guard<std::mutex> lock(g_arena_mu[device & 63]);
     g_arena[device & 63].release_all();
+    output_cache_purge(device);
     return 0;
     API_GUARD_END(nullptr)
 }

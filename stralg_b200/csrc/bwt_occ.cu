@@ -41,7 +41,7 @@ void gather_bwt(DeviceIndex &ix) {
     cudaStream_t st = ix.stream;
     size_t bwt_bytes = (((size_t)ix.len + 63) / 64 + 1) * 64;
     if (!ix.bwt.ptr) {
-        ix.bwt.alloc(bwt_bytes, st);
+        ix.bwt.alloc_output(bwt_bytes, st);
         CUDA_CHECK(cudaMemsetAsync(ix.bwt.ptr + (bwt_bytes - 128), 0, 128, st));
     }
     DevBuf<u32> d_primary(1, st);
@@ -276,7 +276,7 @@ void build_bwt_tables(DeviceIndex &ix, bool keep_bwt) {
     if (ix.sigma <= 5) {
         ix.occ_layout = OCC_DNA32;
         ix.occ_block_bytes = 32;
-        ix.occ.alloc(nblocks * 32, st);
+        ix.occ.alloc_output(nblocks * 32, st);
         u32 ntiles = div_up_u(nblocks, OD_NT);
         DevBuf<u32> tile_counts((size_t)ntiles * 4, st);
         occ_dna_count_kernel<<<ntiles, OD_NT, 0, st>>>(bwt.ptr, nblocks, (DnaBlock *)ix.occ.ptr, tile_counts.ptr);
@@ -289,7 +289,7 @@ void build_bwt_tables(DeviceIndex &ix, bool keep_bwt) {
         ix.occ_layout = OCC_BYTE;
         u32 hdr_words = ((ix.sigma - 1) + 3) & ~3u;
         ix.occ_block_bytes = hdr_words * 4 + 64;
-        ix.occ.alloc(nblocks * ix.occ_block_bytes, st);
+        ix.occ.alloc_output(nblocks * ix.occ_block_bytes, st);
         u32 ntiles = div_up_u(nblocks, OB_BLOCKS);
         DevBuf<u32> tile_counts((size_t)ntiles * (ix.sigma - 1), st);
         occ_byte_count_kernel<<<ntiles, 256, 0, st>>>(bwt.ptr, len, nblocks, ix.sigma, hdr_words, ix.occ_block_bytes,

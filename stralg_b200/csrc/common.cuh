@@ -35,6 +35,11 @@ extern unsigned long long g_kernel_launches;
         CUDA_CHECK(cudaGetLastError());     \
     } while (0)
 
+// exact-size cache of large device blocks (api.cu); get throws CudaFailure when the device is out of memory
+void *output_cache_get(size_t bytes);
+void output_cache_put(void *ptr, size_t bytes);
+void output_cache_purge(int device);
+
 // Stream-ordered device buffer.  The default mempool keeps freed blocks (release threshold is
 // raised to "never" in api.cu), so steady-state builds do not pay cudaMalloc.
 template <typename T>
@@ -42,16 +47,21 @@ struct DevBuf {
     T *ptr = nullptr;
     size_t count = 0;
     cudaStream_t stream = 0;
+    bool cached = false;
     DevBuf() {}
     DevBuf(size_t n, cudaStream_t s) { alloc(n, s); }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : ptr(o.ptr), count(o.count), stream(o.stream) { o.ptr = nullptr; o.count = 0; }
+    DevBuf(DevBuf &&o) noexcept : ptr(o.ptr), count(o.count), stream(o.stream), cached(o.cached) {
+        o.ptr = nullptr;
+        o.count = 0;
+        o.cached = false;
+    }
     DevBuf &operator=(DevBuf &&o) noexcept {
         if (this != &o) {
             release();
-            ptr = o.ptr; count = o.count; stream = o.stream;
-            o.ptr = nullptr; o.count = 0;
+            ptr = o.ptr; count = o.count; stream = o.stream; cached = o.cached;
+            o.ptr = nullptr; o.count = 0; o.cached = false;
         }
         return *this;
     }
@@ -61,15 +71,41 @@ struct DevBuf {
         count = n;
         if (n) CUDA_CHECK(cudaMallocAsync((void **)&ptr, n * sizeof(T), s));
     }
+    // For the large tables an index OWNS (SA, BWT, O, ISA, LCP ...): blocks come from an exact-size
+    // cache of plain device allocations (output_cache_get / _put, api.cu) instead of the
+    // stream-ordered pool.  The pool reuses freed memory well only while the same sequence of
+    // requests repeats; a caller that keeps one index alive while the next is built (transfer of
+    // one result next to the construction of the next) breaks that sequence, and the pool then maps
+    // gigabytes of fresh memory in the middle of a build.  Exact sizes repeat from build to build.
+    void alloc_output(size_t n, cudaStream_t s) {
+        release();
+        stream = s;
+        count = n;
+        if (n * sizeof(T) < ((size_t)1 << 20)) {  // small tables: the pool is fine
+            if (n) CUDA_CHECK(cudaMallocAsync((void **)&ptr, n * sizeof(T), s));
+        } else {
+            ptr = (T *)output_cache_get(n * sizeof(T));
+            cached = true;
+        }
+    }
     void release() {
-        if (ptr) cudaFreeAsync(ptr, stream);
+        if (ptr) {
+            if (cached) {
+                cudaStreamSynchronize(stream);  // an index is released by its owner: its work is done
+                output_cache_put(ptr, count * sizeof(T));
+            } else {
+                cudaFreeAsync(ptr, stream);
+            }
+        }
         ptr = nullptr;
         count = 0;
+        cached = false;
     }
     T *detach() {
         T *p = ptr;
         ptr = nullptr;
         count = 0;
+        cached = false;
         return p;
     }
     ~DevBuf() { release(); }
@@ -79,6 +115,21 @@ struct DevBuf {
 // Build workspace: a few large device allocations that persist across builds (per device) and
 // are carved with a bump pointer, so a steady-state build issues no cudaMalloc at all and the
 // driver never has to re-map physical pages between differently sized requests.
+// cudaMalloc that gives the cached output blocks back before it reports out-of-memory
+static inline void *malloc_or_purge(size_t bytes) {
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        int device = 0;
+        cudaGetDevice(&device);
+        output_cache_purge(device);
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) throw CudaFailure(e, "cudaMalloc", __FILE__, __LINE__);
+    return p;
+}
+
 struct Arena {
     struct Chunk {
         u8 *base;
@@ -95,8 +146,7 @@ struct Arena {
         bytes = (bytes + ((size_t)64 << 20)) & ~(((size_t)1 << 20) - 1);
         if (nchunks > 0 && chunks[0].cap >= bytes) return;
         release_chunks();  // (the side buffer may already hold the staged text of this build)
-        u8 *p = nullptr;
-        CUDA_CHECK(cudaMalloc((void **)&p, bytes));
+        u8 *p = (u8 *)malloc_or_purge(bytes);
         chunks[0] = Chunk{p, bytes, 0};
         nchunks = 1;
     }
@@ -110,8 +160,7 @@ struct Arena {
             }
         if (nchunks == MAX_CHUNKS) throw std::runtime_error("workspace arena exhausted");
         size_t cap = (bytes + ((size_t)256 << 20)) & ~(((size_t)1 << 20) - 1);
-        u8 *p = nullptr;
-        CUDA_CHECK(cudaMalloc((void **)&p, cap));
+        u8 *p = (u8 *)malloc_or_purge(cap);
         chunks[nchunks] = Chunk{p, cap, bytes};
         return chunks[nchunks++].base;
     }
@@ -143,7 +192,7 @@ struct Arena {
                 side_cap = 0;
             }
             size_t cap = (bytes + ((size_t)1 << 20)) & ~(((size_t)1 << 20) - 1);
-            CUDA_CHECK(cudaMalloc((void **)&side, cap));
+            side = (u8 *)malloc_or_purge(cap);
             side_cap = cap;
         }
         return side;

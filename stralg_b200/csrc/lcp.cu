@@ -291,7 +291,7 @@ void build_lcp(DeviceIndex &ix) {
     // texts that needed few doubling rounds have no long repeats to speak of: try the direct path
     static const bool no_direct = getenv("B200SA_LCP_NO_DIRECT") != nullptr;
     if (!no_direct && ix.stats.rounds <= 3) {
-        ix.lcp.alloc(len, st);
+        ix.lcp.alloc_output(len, st);
         int *d_over = ar.get<int>(1);
         CUDA_CHECK(cudaMemsetAsync(d_over, 0, 4, st));
         int t = ix.timer.begin("lcp_direct", (double)len * 12.0);
@@ -334,7 +334,7 @@ void build_lcp(DeviceIndex &ix) {
     KERNEL_CHECK();
     ix.timer.end(t);
 
-    if (!ix.lcp.ptr) ix.lcp.alloc(len, st);
+    if (!ix.lcp.ptr) ix.lcp.alloc_output(len, st);
     t = ix.timer.begin("lcp_gather", (double)len * 12.0);
     lcp_gather_kernel<<<div_up_u(len, 256), 256, 0, st>>>(ix.sa.ptr, v, len, ix.lcp.ptr);
     KERNEL_CHECK();

@@ -837,10 +837,10 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
     ix.stats.sorted_total = len;
 
     // ---- outputs (stream-ordered allocations that outlive the build) ----
-    ix.sa.alloc(len, st);
+    ix.sa.alloc_output(len, st);
     size_t bwt_bytes = (((size_t)len + 63) / 64 + 1) * 64;
     if (want_bwt) {
-        ix.bwt.alloc(bwt_bytes, st);
+        ix.bwt.alloc_output(bwt_bytes, st);
         CUDA_CHECK(cudaMemsetAsync(ix.bwt.ptr + (bwt_bytes - 128), 0, 128, st));
     }
     DevBuf<u32> d_primary(1, st);
@@ -1056,7 +1056,7 @@ __global__ void __launch_bounds__(256) inverse_kernel(const u32 *__restrict__ sa
 }
 
 void build_inverse(DeviceIndex &ix) {
-    ix.isa.alloc(ix.len, ix.stream);
+    ix.isa.alloc_output(ix.len, ix.stream);
     int t = ix.timer.begin("inverse", (double)ix.len * 8.0);
     inverse_kernel<<<div_up_u(ix.len, 256), 256, 0, ix.stream>>>(ix.sa.ptr, ix.len, ix.isa.ptr);
     KERNEL_CHECK();
