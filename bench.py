@@ -141,6 +141,17 @@ def load_traffic(kernel_key, n=None):
         return None
 
 
+def search_traffic(reads):
+    """ncu DRAM bytes of the search kernel for `reads` reads of this workload (captured at 10^8 reads on
+    the 3 Gbp index, profiles/r1_search_dram_3g.csv; per-read traffic does not depend on the batch size)."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        ent = json.load(open(p))["fm_search"]
+        return float(ent["dram_bytes_per_launch"]) * float(reads) / float(ent["reads"])
+    except Exception:
+        return None
+
+
 # =================================================================================================
 # reference arm / cpu baseline (the only place bench.py touches oracle/)
 # =================================================================================================
@@ -662,7 +673,7 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
     survey_gbps = survey_bytes_per_read * shard / (kernel_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "kernel": "fm_search_dna_kernel (one lane per read, unique intervals finished by "
                 "text comparison)", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic("fm_search"),
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": search_traffic(shard),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": issued_bytes,
                 "avg_launch_ms": kernel_ms, "hit_fraction": hit_frac,
                 "ops_per_read": {"o_block_loads_32B": counts[0] / shard, "pattern_words_8B": counts[1] / shard,

@@ -15,7 +15,8 @@ m = 100
 text = torch.empty(n + 1, dtype=torch.uint8, device="cuda")
 lib.b200sa_synth_codes(C.c_void_p(text.data_ptr()), n, 4, 12345, 0, None)
 tc = os.environ.get('PROBE_TEXTCMP', '1') == '1'
-idx = stralg_b200.SuffixArrayIndex.build(text[:n], 5, occ=True, drop_sa=not tc, textcmp=tc)
+kt = os.environ.get('PROBE_KTABLE', '1') == '1'
+idx = stralg_b200.SuffixArrayIndex.build(text[:n], 5, occ=True, drop_sa=not tc, textcmp=tc, ktable=kt)
 reads = torch.empty(nreads * m, dtype=torch.uint8, device="cuda")
 lib.b200sa_synth_reads(C.c_void_p(text.data_ptr()), n, 4, C.c_void_p(reads.data_ptr()), nreads, m, 102, 7, 0, None)
 L = torch.empty(nreads, dtype=torch.int32, device="cuda")
