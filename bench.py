@@ -5,6 +5,7 @@
 
 N = 1  -> workload "build": SA + BWT + C + sampled O of a 3 Gbp synthetic DNA text (BASELINE.json
           configs[2]; the text is resident in HBM before the timed region).  value = Mchars/s.
+          (`scaling_series` repeats the N = 1 point of the search series at the top level.)
           The same line carries `search` (FM exact search of 100-bp reads at 1 GPU),
           `roofline` (dominant kernel = one radix pass of the initial sort), `e2e` (host buffers
           through the C ABI, copies inside the timed region) and `cpu_baseline` (the unmodified
@@ -554,10 +555,18 @@ def gpu_arm(args, rank, local_rank, world):
         if not args.no_search:
             out["search"] = search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n, None, 0, 1,
                                          peak, peak_src, build)
+            # BASELINE.json's metric has two parts: the build on 1 GPU (this line's `value`) and the search at
+            # 1/2/4/8 GPUs (the `value` of the N > 1 lines).  The N = 1 point of the SEARCH series is repeated
+            # here at the top level so that a scaling table can be read off the lines of one run.
+            out["scaling_series"] = {"metric": METRIC_SEARCH, "unit": "patterns/s", "n_gpus": 1,
+                                     "value": out["search"]["value"],
+                                     "note": "compare with `value` of the --gpus 2/4/8 lines (same 10^8 reads, strong scaling)"}
     else:
         res = search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n, dist, rank, world, peak,
                            peak_src, build)
         out = res
+        out["scaling_series"] = {"metric": METRIC_SEARCH, "unit": "patterns/s", "n_gpus": world, "value": res["value"],
+                                 "note": "the N = 1 point of this series is `scaling_series.value` of the --gpus 1 line"}
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -936,12 +936,14 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
                 // keys compared as raw high words: a > (b | mask) <=> (a >> pb) > (b >> pb), and
                 // a < (b & ~mask) likewise; the guards on both sides of X make bounds checks unnecessary
                 const u32 hp_hi = hp | pbmask, hp_lo = hp & ~pbmask;
+                u32 near = 0xffffffffu;  // smallest difference to a neighbour's word: <= pbmask means an equal key
                 for (u32 d = 1; d <= W; ++d) {
                     const u32 hl = Xhi[(int)(p - d)], hr = Xhi[p + d];
                     r -= hl > hp_hi ? 1u : 0u;
                     r += hr < hp_lo ? 1u : 0u;
-                    eq = eq || ((hl ^ hp) <= pbmask) || ((hr ^ hp) <= pbmask);
+                    near = min(near, min(hl ^ hp, hr ^ hp));
                 }
+                eq = near <= pbmask;
             } else {
                 const u32 kp = hp >> a.pb;
                 bool lv = true, rv = true;
