@@ -159,55 +159,59 @@ __global__ void __launch_bounds__(128, 8) approx_walk_kernel(ApproxArgs A) {
             viable = cL < cR;
         }
         u32 vmask = (__ballot_sync(gmask, viable) >> gshift) & 0xffffu;
-        bool descended = false;
-        while (vmask) {
-            const int j = __ffs((int)vmask) - 1;
-            vmask &= vmask - 1u;
-            const int src = (int)gshift + j;
-            u32 bL = __shfl_sync(gmask, cL, src), bR = __shfl_sync(gmask, cR, src);
-            int bi = __shfl_sync(gmask, ci, src);
-            const int bleft = __shfl_sync(gmask, cleft, src);
-            const u32 bop = __shfl_sync(gmask, cop, src);
-            u32 bm = mlen + (bop != 1 ? 1u : 0u);
-            u32 chain = 0;  // exact steps taken below the child (no edits left)
-            bool hit = bi < 0;
-            if (!hit && bleft == 0) {
-                // only exact matching can follow: run the chain (every lane of the group alike)
-                hit = true;
-                while (bi >= 0) {
-                    const u32 x = p[bi];
-                    if ((dt && dt[bi] > 0) || x == 0 || x > nsym) {
-                        hit = false;
-                        break;
-                    }
-                    const u32 ca = c_sh[x];
-                    const u32 nl = ca + occ_sym<LAYOUT>(A.ov, x, bL), nr = ca + occ_sym<LAYOUT>(A.ov, x, bR);
-                    if (nl >= nr) {
-                        hit = false;
-                        break;
-                    }
-                    bL = nl; bR = nr;
-                    --bi;
-                    ++chain;
+        // Children that still have edits left must be entered; every viable child ahead of the first
+        // of them is a hit (i < 0) or a zero-edit chain.  The chains of those children run side by side,
+        // lane j walking pattern[i], pattern[i-1], ... for child j; the children behind the first one to
+        // enter are looked at again when the walk returns to this node.
+        const u32 dmask = (__ballot_sync(gmask, viable && ci >= 0 && cleft > 0) >> gshift) & 0xffffu;
+        const u32 first_enter = dmask ? (u32)__ffs((int)dmask) - 1u : (u32)AG;
+        u32 chain = 0;  // exact steps taken below this lane's child (no edits left)
+        bool lane_hit = viable && gl < first_enter && ci < 0;
+        if (viable && gl < first_enter && ci >= 0) {  // cleft == 0 here
+            lane_hit = true;
+            while (ci >= 0) {
+                const u32 x = p[ci];
+                if ((dt && dt[ci] > 0) || x == 0 || x > nsym) {
+                    lane_hit = false;
+                    break;
                 }
-                if (!hit) continue;
-                bm += chain;
+                const u32 ca = c_sh[x];
+                const u32 nl = ca + occ_sym<LAYOUT>(A.ov, x, cL), nr = ca + occ_sym<LAYOUT>(A.ov, x, cR);
+                if (nl >= nr) {
+                    lane_hit = false;
+                    break;
+                }
+                cL = nl; cR = nr;
+                --ci;
+                ++chain;
             }
-            if (hit) {
+        }
+        __syncwarp(gmask);
+        u32 hmask = (__ballot_sync(gmask, lane_hit) >> gshift) & 0xffffu;
+        // hits of the children ahead of the first one to enter, in child order
+        while (hmask) {
+            const int j = __ffs((int)hmask) - 1;
+            hmask &= hmask - 1u;
+            const int src = (int)gshift + j;
+            const u32 bL = __shfl_sync(gmask, cL, src), bR = __shfl_sync(gmask, cR, src);
+            const u32 bop = __shfl_sync(gmask, cop, src);
+            const u32 bchain = __shfl_sync(gmask, chain, src);
+            const u32 bm = mlen + (bop != 1 ? 1u : 0u) + bchain;
+            {
                 // The path in pattern order (= reversed): the chain's matches, the child's step, the
                 // current node's own step, then the parked frames from the top down to frame 1;
                 // run-length encoded into the CIGAR text of cigar.c:17-31 (sprintf("%d%c")).
-                const u32 plen = depth + 1 + chain;
+                const u32 plen = depth + 1 + bchain;
                 auto path_op = [&](u32 k) -> u32 {
-                    if (k < chain) return 0u;
-                    k -= chain;
+                    if (k < bchain) return 0u;
+                    k -= bchain;
                     return k == 0 ? bop : k == 1 ? op : ((stk[(u64)(depth + 1 - k) * lanes].z >> 24) & 3u);
                 };
                 char *w = EMIT ? A.out_ops + ops_at + nops : nullptr;
                 u32 bytes = 0;
                 for (u32 k = 0; k < plen;) {
                     const u32 o = path_op(k);
-                    u32 run = (o == 0 && k < chain) ? chain - k : 1u;
+                    u32 run = (o == 0 && k < bchain) ? bchain - k : 1u;
                     while (k + run < plen && path_op(k + run) == o) ++run;
                     const u32 digits = run >= 10000u ? 5u : run >= 1000u ? 4u : run >= 100u ? 3u : run >= 10u ? 2u : 1u;
                     if (EMIT && gl == 0) {
@@ -231,17 +235,22 @@ __global__ void __launch_bounds__(128, 8) approx_walk_kernel(ApproxArgs A) {
                 }
                 ++nhits;
                 nops += bytes + 1u;
-                continue;
             }
-            // enter the child: park the current node with the index of its next child
-            if (gl == 0) stk[(u64)depth * lanes] = make_frame(L, R, i, left, op, cb + (u32)j + 1u, mlen);
+        }
+        if (first_enter < (u32)AG) {
+            // enter that child: park the current node with the index of its next child
+            const int src = (int)(gshift + first_enter);
+            const u32 bL = __shfl_sync(gmask, cL, src), bR = __shfl_sync(gmask, cR, src);
+            const int bi = __shfl_sync(gmask, ci, src), bleft = __shfl_sync(gmask, cleft, src);
+            const u32 bop = __shfl_sync(gmask, cop, src);
+            if (gl == 0) stk[(u64)depth * lanes] = make_frame(L, R, i, left, op, cb + first_enter + 1u, mlen);
             __syncwarp(gmask);
             ++depth;
-            L = bL; R = bR; i = bi; left = bleft; op = bop; cursor = 0; mlen = bm;
-            descended = true;
-            break;
+            mlen += bop != 1 ? 1u : 0u;
+            L = bL; R = bR; i = bi; left = bleft; op = bop; cursor = 0;
+        } else {
+            cursor = cb + AG;
         }
-        if (!descended) cursor = cb + AG;
     }
     if (!EMIT && gl == 0) {
         A.hit_count[q] = nhits;
