@@ -552,6 +552,46 @@ def gpu_arm(args, rank, local_rank, world):
                                                       if k.startswith(("phi", "plcp", "lcp", "inverse"))}}
         except Exception as ex:
             out["config2_sa_lcp"] = {"error": str(ex)[:200]}
+        # BASELINE configs[0]: SA + LCP + BWT + C/O of a 1 Mi random ACGT text and exact search of 10 k random
+        # 20-mers (the reference's own performance/ harness case): small-input latency, host buffers in and out
+        try:
+            n1 = min(1 << 20, n)
+            h1 = text[:n1].cpu().numpy()
+            rng = np.random.default_rng(1)
+            starts = rng.integers(0, n1 - 20, 10000)
+            pats = np.concatenate([h1[s0:s0 + 20] if k % 2 else rng.integers(1, 5, 20).astype(np.uint8)
+                                   for k, s0 in enumerate(starts)])
+            tb, ts = [], []
+            for it in range(6):
+                t0 = time.perf_counter()
+                i1 = stralg_b200.SuffixArrayIndex.build(h1, 5, lcp=True, bwt=True, occ=True, device=local_rank,
+                                                        stream=stream)
+                sa1 = i1.sa()
+                lcp1 = i1.lcp()
+                t1 = time.perf_counter()
+                L1, R1 = i1.search(pats, fixed_len=20)
+                _, pos1 = i1.locate(L1, R1)
+                t2 = time.perf_counter()
+                i1.close()
+                if it:
+                    tb.append(t1 - t0)
+                    ts.append(t2 - t1)
+            c1 = {"workload": "SA + LCP + BWT + C/O of 1 Mi random ACGT, then exact search + locate of 10 k 20-mers "
+                              "(BASELINE configs[0]); host buffers in and out, wall clock",
+                  "n": n1, "build_ms": float(np.median(tb)) * 1e3, "search_locate_ms": float(np.median(ts)) * 1e3,
+                  "matches": int(len(pos1))}
+            if not args.no_cpu:
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                import _oracle
+                if _oracle.Ref.available():
+                    ref = _oracle.Ref()
+                    cz = np.concatenate([h1, np.zeros(1, np.uint8)])
+                    t0 = time.perf_counter()
+                    ref.sa_lcp(cz, 5)
+                    c1["cpu_reference_sa_lcp_ms"] = (time.perf_counter() - t0) * 1e3
+            out["config1_small"] = c1
+        except Exception as ex:
+            out["config1_small"] = {"error": str(ex)[:200]}
         if not args.no_search:
             out["search"] = search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n, None, 0, 1,
                                          peak, peak_src, build)
