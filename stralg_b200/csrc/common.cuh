@@ -295,7 +295,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, u32 by
 
 // Per-stage device timing (optional; enabled with B200SA_PROFILE).
 struct StageTimer {
-    static const int MAX = 64;
+    static const int MAX = 1024;
     cudaEvent_t ev[MAX][2];
     const char *name[MAX];
     double bytes[MAX];

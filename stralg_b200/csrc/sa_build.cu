@@ -430,19 +430,40 @@ static constexpr int RK_TILE = RK_NT * RK_IPT;
 __device__ __forceinline__ u64 group_of(u64 key, int gs) { return gs >= 64 ? 0ull : key >> gs; }
 
 // first index f <= start such that ((keys[f..start] & mask) >> gs) all equal x
+// Warp-cooperative (all 32 lanes of one warp call it with the same arguments; the result is uniform).
+// The list is sorted, so "key == x" is false ... false true ... true on [0, start]: one step probes
+// the 32 positions start - 2^l at once, the following steps split the remaining range 33 ways, so a
+// run of a billion equal keys costs seven dependent round trips instead of sixty.
 __device__ u32 gallop_first_equal(const u64 *__restrict__ keys, u32 start, u64 x, int gs, u64 mask) {
-    u64 lo = start;
-    u64 step = 1;
-    while (lo >= step && ((keys[lo - step] & mask) >> gs) == x) {
-        lo -= step;
-        step <<= 1;
+    const u32 lane = threadIdx.x & 31u;
+    // step 1: exponentially spaced probes below `start`
+    const u64 off = 1ull << lane;  // 2^lane (lane 31: 2^31)
+    bool eq = false;
+    if (off <= (u64)start) eq = ((keys[(u64)start - off] & mask) >> gs) == x;
+    const u32 eqm = __ballot_sync(0xffffffffu, eq);
+    // lanes 0 .. t-1 see equal keys, lane t is the first that does not (or runs below index 0)
+    const int t = __ffs((int)~eqm) - 1;  // ~eqm is non-zero unless all 32 probes matched
+    u64 good = t > 0 ? (u64)start - (1ull << (t - 1)) : (u64)start;           // known equal
+    int64_t bad = (t >= 0 && (1ull << t) <= (u64)start) ? (int64_t)((u64)start - (1ull << t)) : -1;  // known different (or -1)
+    if (t < 0) {  // every probe matched (start >= 2^31): the run begins somewhere in [0, start - 2^31]
+        good = (u64)start - (1ull << 31);
+        bad = -1;
     }
-    int64_t bad = lo >= step ? (int64_t)(lo - step) : -1;
-    int64_t good = (int64_t)lo;
-    while (good - bad > 1) {
-        int64_t mid = bad + (good - bad) / 2;
-        if (((keys[mid] & mask) >> gs) == x) good = mid;
-        else bad = mid;
+    // step 2: 33-way splits of (bad, good)
+    while ((int64_t)good - bad > 1) {
+        const u64 span = (u64)((int64_t)good - bad);  // candidates bad+1 .. good-1 are unknown
+        const u64 idx = (u64)(bad + 1) + (span - 1) * (u64)lane / 32u;  // lane 0: bad + 1, spread up to good - 1
+        const bool e2 = idx < good && ((keys[idx] & mask) >> gs) == x;
+        const u32 m2 = __ballot_sync(0xffffffffu, e2);
+        if (m2) {
+            const int f = __ffs((int)m2) - 1;  // first lane that sees x: the run starts at or before its index
+            const u64 gi = (u64)(bad + 1) + (span - 1) * (u64)f / 32u;
+            if (f > 0) bad = (int64_t)((u64)(bad + 1) + (span - 1) * (u64)(f - 1) / 32u);
+            good = gi;
+        } else {
+            // no probe below `good` sees x: everything up to the last probe is different
+            bad = (int64_t)((u64)(bad + 1) + (span - 1) * 31u / 32u);
+        }
     }
     return (u32)good;
 }
@@ -552,24 +573,28 @@ __global__ void __launch_bounds__(RK_NT) rank_kernel(RankArgs a) {
     }
     if (!a.scatter_all && j0 < m) a.headbits[j0 >> 3] = (u8)bits;
 
-    // ---- carry-in for the tile (only when its first element does not start a bucket) ----
-    if (tid == 0) {
+    // ---- carry-in for the tile (only when its first element does not start a bucket): the first
+    // warp looks for the head of the run that reaches into the tile ----
+    if (warp == 0) {
         u32 cs = 0, cb = 0;  // global index of the head for the tile's first element
-        if (tile_base > 0 && tile_base < m) {
-            bool first_is_hs = bits & 1u;
-            bool first_is_hb = hb_idx[0] != 0;
+        if (tile_base > 0 && tile_base < m) {  // uniform over the block
+            const bool first_is_hs = __shfl_sync(0xffffffffu, (int)(bits & 1u), 0) != 0;
+            const bool first_is_hb = __shfl_sync(0xffffffffu, (int)(hb_idx[0] != 0), 0) != 0;
+            const u64 k0 = __shfl_sync(0xffffffffu, k[0], 0);
             if (!first_is_hs) {
-                u32 f = gallop_first_equal(keys, (u32)tile_base, k[0] & mask, 0, mask);
+                u32 f = gallop_first_equal(keys, (u32)tile_base, k0 & mask, 0, mask);
                 if (K0 > 0) {
                     // short suffixes stand first inside an equal-key run and are singletons
                     while ((u64)vals[f] + (u64)K0 > (u64)n) ++f;
                 }
                 cs = f;
             }
-            if (!first_is_hb && gs < 64) cb = gallop_first_equal(keys, (u32)tile_base, (k[0] & mask) >> gs, gs, mask);
+            if (!first_is_hb && gs < 64) cb = gallop_first_equal(keys, (u32)tile_base, (k0 & mask) >> gs, gs, mask);
         }
-        carry_s = cs;
-        carry_b = cb;
+        if (lane == 0) {
+            carry_s = cs;
+            carry_b = cb;
+        }
     }
 
     // ---- block-wide "last head so far" (max-scan; indices grow with position) ----

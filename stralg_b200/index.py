@@ -169,7 +169,7 @@ class SuffixArrayIndex:
 
     def profile(self):
         """[(stage, ms, algorithmic_bytes)] of the build (needs profile=True)."""
-        cap = 64
+        cap = 1024
         names = (C.c_char_p * cap)()
         ms = (C.c_float * cap)()
         by = (C.c_double * cap)()

@@ -87,7 +87,8 @@ if __name__ == "__main__":
         agg = {}
         for name, ms, by in idx.profile():
             agg[name] = agg.get(name, 0.0) + ms
-        top = sorted(agg.items(), key=lambda kv: -kv[1])[:5]
+        top = sorted(agg.items(), key=lambda kv: -kv[1])[:9]
+        top.append(('ALL_STAGES', sum(agg.values())))
         lib.b200sa_release_workspace(0)
         sa = view(idx.device_ptr("sa"), n + 1, 4)
         ok = check_sa(text, sa, n)
