@@ -30,15 +30,23 @@ __global__ void __launch_bounds__(512) hist_kernel(const u64 *__restrict__ keys,
     for (int i = threadIdx.x; i < npass * BINS; i += blockDim.x) sh_hist[i] = 0;
     __syncthreads();
     const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        u64 k = ld_stream_u64(keys + i) >> begin_bit;
-        int bits_left = end_bit - begin_bit;
+    // four keys in flight per thread before the first shared atomic
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 4 * stride) {
+        u64 kk[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) kk[q] = i + q * stride < n ? ld_stream_u64(keys + i + q * stride) : 0ull;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (i + q * stride >= n) break;
+            u64 k = kk[q] >> begin_bit;
+            int bits_left = end_bit - begin_bit;
 #pragma unroll 1
-        for (int p = 0; p < npass; ++p) {
-            u32 mask = bits_left >= RB ? (u32)(BINS - 1) : ((1u << bits_left) - 1u);
-            atomicAdd(&sh_hist[p * BINS + ((u32)k & mask)], 1u);
-            k >>= RB;
-            bits_left -= RB;
+            for (int p = 0; p < npass; ++p) {
+                u32 mask = bits_left >= RB ? (u32)(BINS - 1) : ((1u << bits_left) - 1u);
+                atomicAdd(&sh_hist[p * BINS + ((u32)k & mask)], 1u);
+                k >>= RB;
+                bits_left -= RB;
+            }
         }
     }
     __syncthreads();

@@ -759,12 +759,21 @@ __global__ void __launch_bounds__(CP_NT) scatter_active_kernel(const u8 *__restr
     __syncthreads();
     u32 wb = 0;
     for (unsigned w = 0; w < (threadIdx.x >> 5); ++w) wb += wsum[w];
-    u32 o = tile_offsets[blockIdx.x] + wb + incl - c;
-    u64 base = word * 64;
-    while (mask) {
-        int b = __ffsll((long long)mask) - 1;
-        mask &= mask - 1;
-        out[o++] = vals[base + b];
+    const u32 o = tile_offsets[blockIdx.x] + wb + incl - c;
+    // the warp walks its 32 words together: lane l takes element l (then 32 + l) of the word, so the
+    // reads of `vals` and the writes of the survivors are coalesced
+    const u32 lane = lane_id();
+    const u32 lt = lanemask_lt();
+    const u64 word0 = word - lane;
+#pragma unroll 4
+    for (int w = 0; w < 32; ++w) {
+        const u64 mw = __shfl_sync(0xffffffffu, mask, w);
+        const u32 ow = __shfl_sync(0xffffffffu, o, w);
+        if (!mw) continue;
+        const u64 bw = (word0 + (u64)w) * 64;
+        const u32 lo = (u32)mw, hi = (u32)(mw >> 32);
+        if ((lo >> lane) & 1u) out[ow + (u32)__popc(lo & lt)] = vals[bw + lane];
+        if ((hi >> lane) & 1u) out[ow + (u32)__popc(lo) + (u32)__popc(hi & lt)] = vals[bw + 32 + lane];
     }
 }
 
