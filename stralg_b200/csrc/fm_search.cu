@@ -189,120 +189,10 @@ __global__ void __launch_bounds__(256) fm_search_dna_kernel(OccView ov, CTable5 
             i -= kt.k;
         }
     }
-    for (; i >= 0 && L < R; --i) {
-        if (SC && R - L == 1) {
-            // One candidate suffix s = SA[L] is left.  The recurrence would now consume the remaining
-            // symbols pattern[i], pattern[i-1], ... one O lookup each, moving to ISA[s-1], ISA[s-2], ...
-            // as long as they equal text[s-1], text[s-2], ...; compare them against the text instead.
-            const u32 s = tc.sa[L];
-            if (STATS) ++n_sa;
-            const u64 rem = (u64)i + 1;
-            u64 k = 0;
-            u64 tw = 0, tw_idx = ~0ull;
-            u32 a = 0;
-            // Eight symbols per step while at least eight are left on both sides: the pattern bytes
-            // pattern[i-k-7 .. i-k] (an unaligned 8-byte window, byte-swapped so that pattern[i-k]
-            // comes first) are packed to 16 bits and compared with the 16 bits of packed text that
-            // hold text[s-1-k-7 .. s-1-k]; the first difference, in the order the recurrence would
-            // meet the symbols, ends the run.  The scalar loop below takes over from there (it finds
-            // the failing symbol at once, or finishes a tail shorter than eight).
-            {
-                const u64 ones = 0x0101010101010101ull;
-                u64 plo = 0, phi = 0, pbase = ~0ull;  // aligned pattern words at pbase and pbase + 8
-                while (rem - k >= 8 && (u64)s - k >= 8) {
-                    const u64 first = begin + (u64)i - k - 7;  // address of pattern[i-k-7]
-                    const u64 base8 = first & ~7ull;
-                    const u32 sh = (u32)(first & 7u) * 8u;
-                    if (base8 != pbase) {
-                        phi = (pbase != ~0ull && base8 + 8 == pbase) ? plo : (sh ? *(const u64 *)(pat + base8 + 8) : 0ull);
-                        plo = *(const u64 *)(pat + base8);
-                        if (STATS) n_pw += (pbase != ~0ull && base8 + 8 == pbase) ? 1u : (sh ? 2u : 1u);
-                        pbase = base8;
-                    }
-                    const u64 P = sh ? (plo >> sh) | (phi << (64u - sh)) : plo;  // byte j = pattern[i-k-7+j]
-                    const u64 v = P - ones;
-                    if (v & 0xFCFCFCFCFCFCFCFCull) break;  // a byte outside 1..4: the scalar loop decides
-                    // byte-swap (pattern[i-k] to the low end), then squeeze the 2-bit symbols together
-                    u64 y = ((u64)__byte_perm((u32)v, 0, 0x0123) << 32) | (u64)__byte_perm((u32)(v >> 32), 0, 0x0123);
-                    y &= 0x0303030303030303ull;
-                    y = (y | (y >> 6)) & 0x000F000F000F000Full;
-                    y = (y | (y >> 12)) & 0x000000FF000000FFull;
-                    y = (y | (y >> 24)) & 0xFFFFull;  // bits 2j..2j+1 = pattern[i-k-j] - 1
-                    // text[s-1-k-j] for j = 0..7 in the same order: position t = s-1-k sits lowest
-                    const u64 t = (u64)s - 1 - k;
-                    const u64 w = t >> 5;
-                    const u32 tsh = 62u - 2u * (u32)(t & 31u);
-                    if (w != tw_idx) {
-                        tw_idx = w;
-                        tw = tc.packed[w];
-                        if (STATS) ++n_tw;
-                    }
-                    u64 T = tw >> tsh;
-                    if ((t & 31u) < 7u) {  // the field runs into the previous word
-                        const u64 prev = tc.packed[w - 1];
-                        if (STATS) ++n_tw;
-                        T |= prev << (64u - tsh);
-                        // going on downwards, the previous word is the next current one
-                        tw_idx = w - 1;
-                        tw = prev;
-                    }
-                    const u32 d = (u32)((T ^ y) & 0xFFFFull);
-                    if (d) {
-                        k += (u64)((__ffs((int)d) - 1) >> 1);
-                        break;
-                    }
-                    k += 8;
-                }
-                // hand the pattern word the scalar loop will ask for first over to its one-word cache
-                if (pbase != ~0ull && k < rem) {
-                    const u64 need = (begin + (u64)i - k) & ~7ull;
-                    if (need == pbase) {
-                        word_addr = need;
-                        word = plo;
-                    }
-                }
-            }
-            while (k < rem) {
-                u64 addr = begin + (u64)i - k;
-                if ((addr & ~7ull) != word_addr) {
-                    word_addr = addr & ~7ull;
-                    word = *(const u64 *)(pat + word_addr);
-                    if (STATS) ++n_pw;
-                }
-                a = (u32)(word >> (8 * (addr & 7))) & 0xffu;
-                if (k >= (u64)s) break;  // suffix 0 is preceded by the sentinel only
-                u64 t = (u64)s - 1 - k;
-                if ((t >> 5) != tw_idx) {
-                    tw_idx = t >> 5;
-                    tw = tc.packed[tw_idx];
-                    if (STATS) ++n_tw;
-                }
-                u32 sym = (u32)(tw >> (62 - 2 * (t & 31))) & 3u;
-                if (a - 1u != sym) break;
-                ++k;
-            }
-            if (k == rem) {
-                L = tc.isa[s - (u32)rem];
-                R = L + 1;
-                if (STATS) ++n_sa;
-            } else if (a - 1u > 3u || a >= ov.sigma) {
-                L = 1;
-                R = 0;
-            } else {
-                // the step that fails: BWT[Lk] != a, so both ranks coincide and the interval is empty
-                const u32 Lk = k ? tc.isa[s - (u32)k] : L;
-                BlockRegs kb = load_dna_block<LM>(ov.blocks, Lk >> 6);
-                BlockRegs kb2 = kb;
-                if (((Lk + 1) >> 6) != (Lk >> 6)) kb2 = load_dna_block<LM>(ov.blocks, (Lk + 1) >> 6);
-                if (STATS) {
-                    n_sa += k ? 1u : 0u;
-                    n_blk += 1u + ((((Lk + 1) >> 6) != (Lk >> 6)) ? 1u : 0u);
-                }
-                L = c5.c[a] + rank_in_block(kb, a, Lk, ov.primary);
-                R = c5.c[a] + rank_in_block(kb2, a, Lk + 1, ov.primary);
-            }
-            break;
-        }
+    // O steps until the pattern is used up, the interval is empty, or (SC) a single candidate is left:
+    // the lanes of a warp reach that point after different numbers of steps, and run the comparison
+    // below together, once
+    for (; i >= 0 && L < R && !(SC && R - L == 1); --i) {
         u64 addr = begin + (u64)i;
         if ((addr & ~7ull) != word_addr) {
             word_addr = addr & ~7ull;
@@ -323,6 +213,118 @@ __global__ void __launch_bounds__(256) fm_search_dna_kernel(OccView ov, CTable5 
         const u32 ca = c5.c[a];
         L = ca + rank_in_block(kL, a, L, ov.primary);
         R = ca + rank_in_block(kR, a, R, ov.primary);
+    }
+    if (SC && i >= 0 && R - L == 1) {
+        // One candidate suffix s = SA[L] is left.  The recurrence would now consume the remaining
+        // symbols pattern[i], pattern[i-1], ... one O lookup each, moving to ISA[s-1], ISA[s-2], ...
+        // as long as they equal text[s-1], text[s-2], ...; compare them against the text instead.
+        const u32 s = tc.sa[L];
+        if (STATS) ++n_sa;
+        const u64 rem = (u64)i + 1;
+        u64 k = 0;
+        u64 tw = 0, tw_idx = ~0ull;
+        u32 a = 0;
+        // Eight symbols per step while at least eight are left on both sides: the pattern bytes
+        // pattern[i-k-7 .. i-k] (an unaligned 8-byte window, byte-swapped so that pattern[i-k]
+        // comes first) are packed to 16 bits and compared with the 16 bits of packed text that
+        // hold text[s-1-k-7 .. s-1-k]; the first difference, in the order the recurrence would
+        // meet the symbols, ends the run.  The scalar loop below takes over from there (it finds
+        // the failing symbol at once, or finishes a tail shorter than eight).
+        {
+            const u64 ones = 0x0101010101010101ull;
+            u64 plo = 0, phi = 0, pbase = ~0ull;  // aligned pattern words at pbase and pbase + 8
+            while (rem - k >= 8 && (u64)s - k >= 8) {
+                const u64 first = begin + (u64)i - k - 7;  // address of pattern[i-k-7]
+                const u64 base8 = first & ~7ull;
+                const u32 sh = (u32)(first & 7u) * 8u;
+                if (base8 != pbase) {
+                    phi = (pbase != ~0ull && base8 + 8 == pbase) ? plo : (sh ? *(const u64 *)(pat + base8 + 8) : 0ull);
+                    plo = *(const u64 *)(pat + base8);
+                    if (STATS) n_pw += (pbase != ~0ull && base8 + 8 == pbase) ? 1u : (sh ? 2u : 1u);
+                    pbase = base8;
+                }
+                const u64 P = sh ? (plo >> sh) | (phi << (64u - sh)) : plo;  // byte j = pattern[i-k-7+j]
+                const u64 v = P - ones;
+                if (v & 0xFCFCFCFCFCFCFCFCull) break;  // a byte outside 1..4: the scalar loop decides
+                // byte-swap (pattern[i-k] to the low end), then squeeze the 2-bit symbols together
+                u64 y = ((u64)__byte_perm((u32)v, 0, 0x0123) << 32) | (u64)__byte_perm((u32)(v >> 32), 0, 0x0123);
+                y &= 0x0303030303030303ull;
+                y = (y | (y >> 6)) & 0x000F000F000F000Full;
+                y = (y | (y >> 12)) & 0x000000FF000000FFull;
+                y = (y | (y >> 24)) & 0xFFFFull;  // bits 2j..2j+1 = pattern[i-k-j] - 1
+                // text[s-1-k-j] for j = 0..7 in the same order: position t = s-1-k sits lowest
+                const u64 t = (u64)s - 1 - k;
+                const u64 w = t >> 5;
+                const u32 tsh = 62u - 2u * (u32)(t & 31u);
+                if (w != tw_idx) {
+                    tw_idx = w;
+                    tw = tc.packed[w];
+                    if (STATS) ++n_tw;
+                }
+                u64 T = tw >> tsh;
+                if ((t & 31u) < 7u) {  // the field runs into the previous word
+                    const u64 prev = tc.packed[w - 1];
+                    if (STATS) ++n_tw;
+                    T |= prev << (64u - tsh);
+                    // going on downwards, the previous word is the next current one
+                    tw_idx = w - 1;
+                    tw = prev;
+                }
+                const u32 d = (u32)((T ^ y) & 0xFFFFull);
+                if (d) {
+                    k += (u64)((__ffs((int)d) - 1) >> 1);
+                    break;
+                }
+                k += 8;
+            }
+            // hand the pattern word the scalar loop will ask for first over to its one-word cache
+            if (pbase != ~0ull && k < rem) {
+                const u64 need = (begin + (u64)i - k) & ~7ull;
+                if (need == pbase) {
+                    word_addr = need;
+                    word = plo;
+                }
+            }
+        }
+        while (k < rem) {
+            u64 addr = begin + (u64)i - k;
+            if ((addr & ~7ull) != word_addr) {
+                word_addr = addr & ~7ull;
+                word = *(const u64 *)(pat + word_addr);
+                if (STATS) ++n_pw;
+            }
+            a = (u32)(word >> (8 * (addr & 7))) & 0xffu;
+            if (k >= (u64)s) break;  // suffix 0 is preceded by the sentinel only
+            u64 t = (u64)s - 1 - k;
+            if ((t >> 5) != tw_idx) {
+                tw_idx = t >> 5;
+                tw = tc.packed[tw_idx];
+                if (STATS) ++n_tw;
+            }
+            u32 sym = (u32)(tw >> (62 - 2 * (t & 31))) & 3u;
+            if (a - 1u != sym) break;
+            ++k;
+        }
+        if (k == rem) {
+            L = tc.isa[s - (u32)rem];
+            R = L + 1;
+            if (STATS) ++n_sa;
+        } else if (a - 1u > 3u || a >= ov.sigma) {
+            L = 1;
+            R = 0;
+        } else {
+            // the step that fails: BWT[Lk] != a, so both ranks coincide and the interval is empty
+            const u32 Lk = k ? tc.isa[s - (u32)k] : L;
+            BlockRegs kb = load_dna_block<LM>(ov.blocks, Lk >> 6);
+            BlockRegs kb2 = kb;
+            if (((Lk + 1) >> 6) != (Lk >> 6)) kb2 = load_dna_block<LM>(ov.blocks, (Lk + 1) >> 6);
+            if (STATS) {
+                n_sa += k ? 1u : 0u;
+                n_blk += 1u + ((((Lk + 1) >> 6) != (Lk >> 6)) ? 1u : 0u);
+            }
+            L = c5.c[a] + rank_in_block(kb, a, Lk, ov.primary);
+            R = c5.c[a] + rank_in_block(kb2, a, Lk + 1, ov.primary);
+        }
     }
     outL[q] = L;
     outR[q] = R;
