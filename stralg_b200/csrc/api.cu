@@ -262,7 +262,7 @@ int b200sa_device_count(void) {
     return n;
 }
 
-__attribute__((visibility("hidden"))) static int build_into(b200sa_index *h, const uint8_t *codes, uint64_t n, uint32_t sigma, uint32_t flags, int device,
+static int build_into(b200sa_index *h, const uint8_t *codes, uint64_t n, uint32_t sigma, uint32_t flags, int device,
                       void *stream, enum b200sa_error *err) {
     API_GUARD_BEGIN
     use_device(device);
