@@ -50,8 +50,8 @@ enum b200sa_error {
                                         text directly instead of one O lookup per symbol; results are
                                         identical to the plain recurrence (needs OCC, keeps SA)        */
 #define B200SA_BUILD_KTABLE 0x20u    /* DNA index (sigma <= 5): table of the (L, R) interval the recurrence of
-                                        bwt.c:185-195 reaches on every k-mer (k = 12, or less for short
-                                        texts); exact search starts from the entry of the pattern's last k
+                                        bwt.c:185-195 reaches on every k-mer (the largest k <= 15 whose table
+                                        stays under 3 bytes per text symbol: 15 at 3 Gbp); exact search starts from the entry of the pattern's last k
                                         symbols instead of running those k steps; results are identical
                                         (needs OCC)                                                      */
 #define B200SA_TEXT_ON_DEVICE 0x100u /* `codes` is a device pointer (borrowed during the call)  */
