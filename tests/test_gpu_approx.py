@@ -140,3 +140,36 @@ def test_approx_edge_cases(engine, oracle):
     with pytest.raises(engine.B200saError):
         idx.approx_search(p, np.array([0, 3], np.uint64), max_edits=300)
     idx.close()
+
+
+def test_approx_matches_golden(engine, oracle):
+    """tests/golden/approx_golden.json: the reference iterator's output on its own test strings
+    (match_test.c:682-696, mississippi) at d = 0, 1, 2 -- interval list, matched lengths, CIGARs and every
+    yielded (position, CIGAR, length), in order; with the D table from a reverse index and without."""
+    import json
+    import os
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "approx_golden.json")))
+    by_text = {}
+    for c in cases:
+        by_text.setdefault(c["text"], []).append(c)
+    for text, cs in by_text.items():
+        codes, sigma, _ = oracle.remap(text.encode())
+        idx = engine.SuffixArrayIndex.build(codes[:-1], sigma)
+        rev = engine.SuffixArrayIndex.build(codes[:-1][::-1].copy(), sigma, drop_sa=True)
+        sa = idx.sa()
+        for d in (0, 1, 2):
+            group = [c for c in cs if c["edits"] == d]
+            pat = np.concatenate([np.array(c["codes"], np.uint8) for c in group])
+            off = np.zeros(len(group) + 1, dtype=np.uint64)
+            off[1:] = np.cumsum([len(c["codes"]) for c in group])
+            for use_rev in (rev, None):
+                res = idx.approx_search(pat, off, max_edits=d, rev=use_rev)
+                for q, c in enumerate(group):
+                    a, b = int(res["offsets"][q]), int(res["offsets"][q + 1])
+                    assert res["L"][a:b].tolist() == c["L"] and res["R"][a:b].tolist() == c["R"], c
+                    assert res["match_length"][a:b].tolist() == c["match_length"] and res["cigars"][a:b] == c["cigars"], c
+                    hits = [[int(sa[i]), res["cigars"][h], int(res["match_length"][h])]
+                            for h in range(a, b) for i in range(int(res["L"][h]), int(res["R"][h]))]
+                    assert hits == c["hits"], c
+        idx.close()
+        rev.close()

@@ -164,3 +164,26 @@ def test_oracle_approx_known_answers(oracle):
     # (values confirmed against the reference iterator by the test above)
     assert cig == ["3M", "1I2M", "1M1I1M", "2M1I"] and ml.tolist() == [3, 2, 2, 2]
     assert L.tolist() == [10, 8, 8, 10] and R.tolist() == [12, 10, 10, 12]
+
+
+def test_oracle_approx_matches_golden(oracle):
+    """tests/golden/approx_golden.json (the reference's iterator on its own test strings, d = 0..2):
+    the restatement reproduces interval list, matched lengths, CIGARs and every yielded hit, in order,
+    with the D table (reverse O table) and without it."""
+    import json
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "approx_golden.json")))
+    assert len(cases) > 200
+    tables = {}
+    for c in cases:
+        if c["text"] not in tables:
+            codes, sigma, _ = oracle.remap(c["text"].encode())
+            sa = oracle.sa(codes)
+            rcodes = np.concatenate([codes[:-1][::-1], np.zeros(1, np.uint8)])
+            tables[c["text"]] = (codes, sa, oracle.c_table(codes, sigma), oracle.o_table(oracle.bwt(codes, sa), sigma),
+                                 oracle.o_table(oracle.bwt(rcodes, oracle.sa(rcodes)), sigma))
+        codes, sa, ct, o, ro = tables[c["text"]]
+        for use_ro in (ro, None):
+            L, R, ml, cig = oracle.approx(ct, o, use_ro, len(codes), np.array(c["codes"], np.uint8), c["edits"])
+            assert L.tolist() == c["L"] and R.tolist() == c["R"] and ml.tolist() == c["match_length"] and cig == c["cigars"], c
+        hits = [[int(sa[i]), cig[k], int(ml[k])] for k in range(len(L)) for i in range(int(L[k]), int(R[k]))]
+        assert hits == c["hits"], c
