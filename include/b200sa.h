@@ -74,6 +74,10 @@ struct b200sa_stats {
     uint32_t bucket_bits;  /* bucket sort: leading key bits that select a bucket */
     uint32_t sa_sample_rate; /* b200sa_sample_sa: text-position sampling rate of the sampled SA, 0 = none */
     uint32_t sa_resident;    /* 1 while the full suffix array is held in HBM */
+    uint32_t shallow_buckets; /* bucket sort: buckets too large for one SM, handed to the doubling rounds unsorted
+                                 as groups that share bucket_bits leading key bits (repeats, poly-A runs) */
+    uint32_t reserved0;
+    uint64_t shallow_elems;   /* suffixes in them (upper bound) */
 };
 
 /* ---- construction ------------------------------------------------------------------------

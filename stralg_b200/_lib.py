@@ -39,6 +39,7 @@ class Stats(C.Structure):
         ("sorted_total", C.c_uint64), ("passes_elems", C.c_uint64), ("occ_bytes", C.c_uint64),
         ("round0_mode", C.c_uint32), ("bucket_bits", C.c_uint32),
         ("sa_sample_rate", C.c_uint32), ("sa_resident", C.c_uint32),
+        ("shallow_buckets", C.c_uint32), ("reserved0", C.c_uint32), ("shallow_elems", C.c_uint64),
     ]
 
 

@@ -426,6 +426,9 @@ int b200sa_stats(const b200sa_index *idx, struct b200sa_stats *out) {
     out->bucket_bits = ix.stats.bucket_bits;
     out->sa_sample_rate = ix.ssa_rate;
     out->sa_resident = ix.sa.ptr ? 1u : 0u;
+    out->shallow_buckets = ix.stats.shallow_buckets;
+    out->reserved0 = 0;
+    out->shallow_elems = ix.stats.shallow_elems;
     return 0;
 }
 
@@ -788,7 +791,7 @@ int b200sa_save(const b200sa_index *idx, const char *path) {
         }
         IndexFileHeader h{};
         memcpy(h.magic, "B200SAIX", 8);
-        h.version = 1;
+        h.version = 2;
         h.endian = 0x01020304u;
         h.n = ix.n;
         h.sigma = ix.sigma;
@@ -848,9 +851,21 @@ b200sa_index *b200sa_load(const char *path, int device, void *stream, enum b200s
         if (fread(&fh, sizeof fh, 1, f) != 1 || memcmp(fh.magic, "B200SAIX", 8) != 0)
             throw std::invalid_argument("not a b200sa index file");
         if (fh.endian != 0x01020304u) throw std::invalid_argument("index file was written on the other byte order");
-        if (fh.version != 1) throw std::invalid_argument("unsupported index file version");
+        if (fh.version != 2) throw std::invalid_argument("unsupported index file version");
         if (fh.n > 0xFFFFFFFEull || fh.sigma < 1 || fh.sigma > 256 || fh.primary > fh.n)
             throw std::invalid_argument("index file header is inconsistent");
+        // every layout field is checked before a kernel may index with it
+        {
+            const uint64_t blocks = (fh.n + 1) / 64 + 1;  // build_bwt_tables: len / 64 + 1
+            const uint32_t hdr_words = ((fh.sigma - 1) + 3u) & ~3u;
+            bool good = fh.occ_layout <= 2;
+            if (fh.occ_layout == 1) good = good && fh.sigma <= 5 && fh.occ_block_bytes == 32;
+            if (fh.occ_layout == 2) good = good && fh.sigma > 5 && fh.occ_block_bytes == hdr_words * 4 + 64;
+            if (fh.occ_layout != 0) good = good && fh.occ_blocks == blocks;
+            if (fh.occ_layout == 0) good = good && fh.occ_blocks == 0;
+            good = good && fh.ktable_k <= 15 && (fh.ktable_k == 0 || fh.occ_layout == 1);
+            if (!good) throw std::invalid_argument("index file header is inconsistent (O-table layout / k-mer table)");
+        }
         DeviceIndex &ix = h->ix;
         cudaStream_t st = (cudaStream_t)stream;
         ix.stream = st;
@@ -903,6 +918,7 @@ b200sa_index *b200sa_load(const char *path, int device, void *stream, enum b200s
             throw std::invalid_argument("index file: sections do not match the header");
         ix.ssa_rate = fh.ssa_rate;
         fclose(f);
+        f = nullptr;
         CUDA_CHECK(cudaStreamSynchronize(st));
         ok(err);
         return h;
@@ -916,7 +932,7 @@ b200sa_index *b200sa_load(const char *path, int device, void *stream, enum b200s
     } catch (const std::exception &e) {
         fail(B200SA_ERR_INTERNAL, e.what(), err);
     }
-    fclose(f);
+    if (f) fclose(f);
     b200sa_free(h);
     return nullptr;
 }

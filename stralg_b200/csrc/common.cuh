@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 
@@ -217,6 +218,22 @@ struct Arena {
 };
 
 static inline unsigned div_up_u(u64 a, u64 b) { return (unsigned)((a + b - 1) / b); }
+
+// cudaFuncSetAttribute (the opt-in for more than 48 KB of dynamic shared memory) is per device, i.e.
+// per context: a process that builds on several devices has to repeat it on each one.  first()
+// is true exactly once per CUDA device (the current one when `device` < 0).
+struct PerDeviceOnce {
+    bool done[64] = {};
+    std::mutex mu;
+    bool first(int device = -1) {
+        if (device < 0) CUDA_CHECK(cudaGetDevice(&device));
+        std::lock_guard<std::mutex> lock(mu);
+        bool &d = done[device & 63];
+        if (d) return false;
+        d = true;
+        return true;
+    }
+};
 
 // Small device-to-host read-back (<= 4 KB, a multiple of 4 bytes) that stays off the copy engines: a
 // one-warp kernel stores the words into mapped pinned host memory, the stream is synchronised, the

@@ -26,6 +26,8 @@ struct BuildStats {
     u64 passes_elems;    // sum over all radix passes of elements moved
     u32 round0_mode;     // 0: LSD radix passes, 1: MSD bucket sort (round0_msd.cu)
     u32 bucket_bits;     // MSD: leading key bits that select a bucket
+    u32 shallow_buckets; // MSD: oversize buckets emitted unsorted as groups of depth bucket_bits / bits
+    u64 shallow_elems;   // suffixes in them
 };
 
 // Occurrence-table layouts

@@ -319,12 +319,10 @@ struct Sorter {
     static void launch_pass(const u64 *kin, const u32 *vin, u64 *kout, u32 *vout, u32 n, int shift, u32 mask,
                             const u32 *digit_base, u64 *lookback, u32 *ticket, cudaStream_t st) {
         typedef PassCfg<RB, NT, IPT> Cfg;
-        static bool configured = false;
-        if (!configured) {
+        static PerDeviceOnce once;
+        if (once.first())
             CUDA_CHECK(cudaFuncSetAttribute(onesweep_pass_kernel<RB, NT, IPT>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-            configured = true;
-        }
         unsigned tiles = div_up_u(n, Cfg::TILE);
         CUDA_CHECK(cudaMemsetAsync(lookback, 0, (size_t)tiles * BINS * 8, st));
         CUDA_CHECK(cudaMemsetAsync(ticket, 0, 4, st));
@@ -334,11 +332,10 @@ struct Sorter {
     }
 
     static void configure() {
-        static bool done = false;
-        if (done) return;
-        CUDA_CHECK(cudaFuncSetAttribute(hist_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        8 * BINS * 4));
-        done = true;
+        static PerDeviceOnce once;
+        if (once.first())
+            CUDA_CHECK(cudaFuncSetAttribute(hist_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            8 * BINS * 4));
     }
 
     // Generic all-pass histogram over existing keys.  hist must hold npass*BINS u32.

@@ -80,6 +80,7 @@ bool msd_make_plan(u32 len, u32 sigma, int bits, MsdPlan &pl) {
     for (int i = 0; i < nl; ++i) pl.D[i] = b * (syms / nl + (i < syms % nl ? 1 : 0));
     pl.nlevels = nl;
     pl.BB = BB;
+    pl.dmax = dmax;
 
     int log2len = 0;
     while ((1ull << log2len) < (u64)len) ++log2len;
@@ -657,6 +658,7 @@ struct L3Args {
     u32 *act, *act_count;
     u32 *primary;
     u32 *flagged, *nflagged;   // tiles the fast kernel declined (a crowded bin)
+    u32 *big, *nbig;           // tiles that hold a bucket too large for one SM (msd_bigtile_kernel)
     u32 ntiles;
     int par_shift;     // bucket >> par_shift = its level-1 parent (0 with a single level)
 };
@@ -769,6 +771,10 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
             if (b0 == b1) continue;
             E0 = a.bstart[b0];
             M = a.bstart[b1] - E0;
+            if (M > (u32)L3_CAP) {  // holds an oversize bucket: left to msd_bigtile_kernel
+                a.big[atomicAdd(a.nbig, 1u)] = t;
+                continue;
+            }
             if (M) break;
         }
         nxt[0] = t; nxt[1] = b0; nxt[2] = b1; nxt[3] = E0; nxt[4] = M;
@@ -1010,18 +1016,14 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
 // pairs.  composite = [segment : 13 | remaining key : 32 | long : 1 | n - s for short suffixes : 8]
 static constexpr size_t RB_SMEM = (size_t)RB_N * 8 * 2 + (size_t)(L3_MASKW + 1) * 4 * 2 + 64;
 
-__global__ void __launch_bounds__(L3_NT, 1) msd_local_sort_robust_kernel(L3Args a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+// orders the buckets [b0, b1) (M = their elements, <= L3_CAP) and emits them; all threads of the CTA
+__device__ void robust_sort_range(const L3Args &a, u32 b0, u32 b1, unsigned char *smem_raw) {
     u64 *SK = (u64 *)smem_raw;            // [RB_N]
     u64 *XV = SK + RB_N;                  // [RB_N]
     u32 *segmask = (u32 *)(XV + RB_N);
     u32 *segpre = segmask + (L3_MASKW + 1);
     uint2 *segtab = (uint2 *)XV;          // only while the composites are formed
-
-    if (blockIdx.x >= *a.nflagged) return;
     const u32 tid = threadIdx.x;
-    const u32 t = a.flagged[blockIdx.x];
-    const u32 b0 = a.tile_first[t], b1 = a.tile_first[t + 1];
     const u32 E0 = a.bstart[b0], E1 = a.bstart[b1];
     const u32 M = E1 - E0;
     l3_segments(a.bstart, b0, b1, E0, M, segmask, segpre, segtab, L3_NT);
@@ -1079,6 +1081,169 @@ __global__ void __launch_bounds__(L3_NT, 1) msd_local_sort_robust_kernel(L3Args 
     }
 }
 
+__global__ void __launch_bounds__(L3_NT, 1) msd_local_sort_robust_kernel(L3Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (blockIdx.x >= *a.nflagged) return;
+    const u32 t = a.flagged[blockIdx.x];
+    robust_sort_range(a, a.tile_first[t], a.tile_first[t + 1], smem_raw);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Oversize buckets.  A bucket that one SM cannot order in shared memory (more than L3_MAXB
+// suffixes share its BB leading key bits: poly-A, tandem and interspersed repeats of a genome) is
+// not sorted at all in round 0: it is emitted as ONE group of suffixes that are known to share
+// d0 = BB / bits symbols -- rank = first row of the bucket, every member active -- and the doubling
+// rounds, which then start at h = d0 instead of K, order it together with the groups of equal
+// K-symbol keys.  The at most d0 - 1 suffixes shorter than d0 symbols (their key is padded with the
+// smallest symbol) stand first in their bucket, shortest first (strcmp order,
+// stralg/suffix_array.c:26-30); they are final after round 0 and are moved there by
+// msd_fix_shorts_kernel.  The other buckets of a tile that holds an oversize bucket are ordered by
+// the bitonic network of the robust kernel, in batches that fit shared memory.
+// ---------------------------------------------------------------------------------------------
+struct OverArgs {
+    uint4 *list;         // {first row, suffixes, bucket, short suffixes in it} per oversize bucket
+    u32 *count;
+    const u32 *shortb;   // [32] bucket of suffix n - j for j < d0, 0xffffffff beyond
+    u32 d0;
+    u32 *fix, *nfix;     // short suffixes met in oversize buckets: {row, suffix, first row of the bucket, -}
+};
+
+__global__ void msd_short_buckets_kernel(const u64 *__restrict__ packed, u32 n, int bits, int BB, u32 d0,
+                                         u32 *__restrict__ shortb) {
+    const u32 j = threadIdx.x;
+    u32 v = 0xffffffffu;
+    if (j < d0 && j <= n) v = (u32)(window_at(packed, (u64)(n - j), bits) >> (64 - BB));
+    shortb[j] = v;
+}
+
+// out[0] = buckets with more than maxb suffixes, out[1] = suffixes in them
+__global__ void __launch_bounds__(256) msd_count_oversize_kernel(const u32 *__restrict__ bstart, u64 nb, u32 maxb,
+                                                                 unsigned long long *__restrict__ out) {
+    const u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 c = 0;
+    if (b < nb) {
+        c = bstart[b + 1] - bstart[b];
+        if (c <= maxb) c = 0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, c != 0);
+    if (!m) return;
+    unsigned long long sum = c;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31u) == 0) {
+        atomicAdd(&out[0], (unsigned long long)__popc(m));
+        atomicAdd(&out[1], sum);
+    }
+}
+
+__global__ void __launch_bounds__(L3_NT, 1) msd_bigtile_kernel(L3Args a, OverArgs o) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (blockIdx.x >= *a.nbig) return;
+    const u32 t = a.big[blockIdx.x];
+    const u32 b0 = a.tile_first[t], b1 = a.tile_first[t + 1];
+    u32 bb = b0;
+    while (bb < b1) {  // uniform over the CTA
+        const u32 s0 = a.bstart[bb], c = a.bstart[bb + 1] - s0;
+        if (c == 0) {
+            ++bb;
+            continue;
+        }
+        if (c > (u32)L3_MAXB) {
+            if (threadIdx.x == 0) {
+                u32 k = 0;
+                for (u32 j = 0; j < 32; ++j) k += o.shortb[j] == bb ? 1u : 0u;
+                o.list[atomicAdd(o.count, 1u)] = make_uint4(s0, c, bb, k);
+            }
+            ++bb;
+            continue;
+        }
+        u32 be = bb + 1, M = c;
+        while (be < b1) {
+            const u32 c2 = a.bstart[be + 1] - a.bstart[be];
+            if (c2 > (u32)L3_MAXB || M + c2 > (u32)L3_CAP) break;
+            M += c2;
+            ++be;
+        }
+        robust_sort_range(a, bb, be, smem_raw);
+        __syncthreads();
+        bb = be;
+    }
+}
+
+__global__ void __launch_bounds__(256) msd_emit_shallow_kernel(L3Args a, OverArgs o) {
+    const u32 nov = *o.count;
+    constexpr u32 CH = 256 * 8;  // suffixes per chunk
+    for (u32 i = 0; i < nov; ++i) {
+        const uint4 en = o.list[i];
+        const u32 nch = (en.y + CH - 1) / CH;
+        // a bucket of a few chunks is taken by one CTA, a large one is spread over the grid
+        u32 c0 = blockIdx.x, cstep = gridDim.x;
+        if (nch <= 32) {
+            if (i % gridDim.x != blockIdx.x) continue;
+            c0 = 0;
+            cstep = 1;
+        }
+        for (u32 ch = c0; ch < nch; ch += cstep) {
+#pragma unroll 2
+            for (u32 q = 0; q < 8; ++q) {
+                const u32 j = ch * CH + q * 256 + threadIdx.x;
+                if (j < en.y) {
+                    const u32 g = en.x + j;
+                    const u64 e = ld_stream_u64(a.in + g);
+                    const u32 s = (u32)e;
+                    const bool sh = (u64)s + (u64)o.d0 > (u64)a.n;
+                    if (sh) {
+                        const u32 slot = atomicAdd(o.nfix, 1u);
+                        if (slot < 32) {
+                            o.fix[4 * slot] = g;
+                            o.fix[4 * slot + 1] = s;
+                            o.fix[4 * slot + 2] = en.x;
+                        }
+                    }
+                    l3_emit(a, g, e, !sh, en.x + en.w);
+                }
+            }
+        }
+    }
+}
+
+// one thread: the (at most d0 - 1) short suffixes of the oversize buckets swap places with whatever
+// stands in the first rows of their bucket
+__global__ void msd_fix_shorts_kernel(L3Args a, OverArgs o) {
+    const u32 nf = min(*o.nfix, 32u);
+    u32 pos[32], sv[32], st[32], tgt[32];
+    for (u32 i = 0; i < nf; ++i) {
+        pos[i] = o.fix[4 * i];
+        sv[i] = o.fix[4 * i + 1];
+        st[i] = o.fix[4 * i + 2];
+    }
+    for (u32 i = 0; i < nf; ++i) {
+        u32 c = 0;
+        for (u32 j = 0; j < nf; ++j) c += (st[j] == st[i] && sv[j] > sv[i]) ? 1u : 0u;
+        tgt[i] = st[i] + c;  // shortest (largest start) first
+    }
+    for (u32 i = 0; i < nf; ++i) {
+        const u32 p = pos[i], q = tgt[i];
+        if (p != q) {
+            const u32 x = a.sa[q];
+            a.sa[q] = sv[i];
+            a.sa[p] = x;
+            if (a.bwt) {
+                const u8 xb = a.bwt[q];
+                a.bwt[q] = a.bwt[p];
+                a.bwt[p] = xb;
+            }
+            if (x == 0) *a.primary = p;
+            for (u32 j = 0; j < nf; ++j)
+                if (j != i && pos[j] == q) pos[j] = p;
+            pos[i] = q;
+        }
+        a.rank[sv[i]] = q;
+        a.valid[sv[i] >> 5] |= 1u << (sv[i] & 31u);
+        if (sv[i] == 0) *a.primary = q;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fill_singleton_ranks_kernel(const u32 *__restrict__ sa, u32 len,
                                                                    const u32 *__restrict__ valid, u32 *__restrict__ rank) {
@@ -1111,24 +1276,22 @@ static constexpr size_t t1_smem() {
 }
 template <int NT, int IPT, int CTAS>
 static void launch_t1_variant(const Text1Args &ta, u32 len, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.first())
         CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<2, true, NT, IPT, CTAS>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t1_smem<NT, IPT>()));
-        configured = true;
-    }
     msd_partition_text_kernel<2, true, NT, IPT, CTAS><<<div_up_u(len, NT * IPT), NT, t1_smem<NT, IPT>(), st>>>(ta);
 }
 
 bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     cudaStream_t st = ix.stream;
     Arena &ar = *ix.arena;
-    const MsdPlan &pl = r.plan;
+    MsdPlan &pl = r.plan;  // a partition level may be added below
     const u32 n = ix.n, len = ix.len;
     const int b = ix.pk.bits;
 
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.first(ix.device)) {
         CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
@@ -1141,38 +1304,74 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         CUDA_CHECK(cudaFuncSetAttribute(msd_partition_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_local_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L3_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_local_sort_robust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
-        configured = true;
+        CUDA_CHECK(cudaFuncSetAttribute(msd_bigtile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
     }
 
-    // ---- tables ----
+    // ---- tables (those of a level are carved when the level is reached: one may be added) ----
     u64 nb[3] = {0, 0, 0};  // buckets after level l
-    {
-        u64 acc = 1;
-        for (int l = 0; l < pl.nlevels; ++l) {
-            acc <<= pl.D[l];
-            nb[l] = acc;
-        }
-    }
-    u32 *start[3], *cursor[3];
-    for (int l = 0; l < pl.nlevels; ++l) {
+    u32 *start[3] = {nullptr, nullptr, nullptr}, *cursor[3] = {nullptr, nullptr, nullptr};
+    auto level_tables = [&](int l) {
+        nb[l] = (l ? nb[l - 1] : 1ull) << pl.D[l];
         start[l] = ar.get<u32>(nb[l] + 1);
         cursor[l] = ar.get<u32>(nb[l]);
         CUDA_CHECK(cudaMemsetAsync(cursor[l], 0, nb[l] * 4, st));
-    }
-    u32 *d_misc = ar.get<u32>(8);  // 0: max final bucket, 1: tiles of the current level, 3: actives, 4: declined tiles
+    };
+    // 0: max final bucket, 1: tiles of the current level, 3: actives, 4: declined tiles, 5: big tiles,
+    // 6: oversize buckets, 7: short suffixes met in them
+    u32 *d_misc = ar.get<u32>(8);
     CUDA_CHECK(cudaMemsetAsync(d_misc, 0, 8 * 4, st));
+    unsigned long long *d_over = ar.get<unsigned long long>(2);
+    r.shallow_buckets = 0;
+    r.shallow_elems = 0;
+    r.depth0 = (u32)pl.K;
+    r.levels_added = 0;
+
+    // Once the bucket sizes of the last planned level are known (before that level moves anything): do
+    // the buckets fit one SM?
+    //   * all do: go on (uniform texts);
+    //   * buckets that do not hold more than 1/64 of the text and the key has bits left: one more
+    //     partition level (texts with a skewed k-mer spectrum, e.g. real genomes, where the planned
+    //     average says little about the common k-mers);
+    //   * what is still too large afterwards is emitted unsorted as shallow groups (see OverArgs) --
+    //     unless that is more than 1/8 of the text (periodic texts: every bucket), where the caller's
+    //     LSD path, whose keys are K symbols deep instead of BB / bits, is the better start.
+    enum { GO, MORE, FALLBACK };
+    auto decide = [&](const u32 *final_start, u64 nbuckets) -> int {
+        u32 maxbucket = 0;
+        read_back(&maxbucket, d_misc, 4, st);
+        if (maxbucket <= (u32)L3_MAXB) return GO;
+        if (env_int2("B200SA_MSD_NO_OVERSIZE", 0)) return FALLBACK;
+        CUDA_CHECK(cudaMemsetAsync(d_over, 0, 16, st));
+        msd_count_oversize_kernel<<<div_up_u(nbuckets, 256), 256, 0, st>>>(final_start, nbuckets, (u32)L3_MAXB, d_over);
+        KERNEL_CHECK();
+        unsigned long long h[2];
+        read_back(h, d_over, 16, st);
+        const int more_frac = std::max(1, env_int2("B200SA_MSD_MORE_FRAC", 64));
+        const int bbmax = env_int2("B200SA_MSD_BBMAX", 26);
+        int room = std::min(std::min(pl.dmax, pl.R), bbmax - pl.BB) / b * b;
+        if (h[1] > (unsigned long long)len / (unsigned)more_frac && pl.nlevels < 3 && room >= b) {
+            pl.D[pl.nlevels++] = room;
+            pl.BB += room;
+            pl.R -= room;
+            ++r.levels_added;
+            CUDA_CHECK(cudaMemsetAsync(d_misc, 0, 4, st));
+            return MORE;
+        }
+        const int frac = std::max(1, env_int2("B200SA_MSD_OVER_FRAC", 8));
+        if (h[1] > (unsigned long long)len / (unsigned)frac) return FALLBACK;
+        r.shallow_elems = h[1];  // (an upper bound: such a bucket is still sorted when its whole tile fits)
+        return GO;
+    };
+
     const u32 ntl3 = div_up_u(len, L3_TSZ);
     u32 *tile_first = ar.get<u32>((size_t)ntl3 + 2);
     u32 *flagged = ar.get<u32>((size_t)ntl3 + 1);
-    size_t max_parents = pl.nlevels > 1 ? nb[pl.nlevels - 2] : 1;
-    size_t desc_cap = (size_t)div_up_u(len, P_TILE) + max_parents + 1;
-    uint4 *desc = pl.nlevels > 1 ? ar.get<uint4>(desc_cap) : nullptr;
-    u32 *tile_off = pl.nlevels > 1 ? ar.get<u32>(max_parents + 2) : nullptr;
-
+    u32 *bigtiles = ar.get<u32>((size_t)ntl3 + 1);
     const size_t valid_words = ((size_t)len + 31) / 32 + 2;
     CUDA_CHECK(cudaMemsetAsync(r.valid, 0, valid_words * 4, st));
 
     // ---- level 1: from the text ----
+    level_tables(0);
     const u64 nwords_data = ((u64)len + ix.pk.cpw - 1) / ix.pk.cpw;
     int t = ix.timer.begin("msd_hist1", (double)len * b / 8.0);
     switch (b) {
@@ -1188,6 +1387,7 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         KERNEL_CHECK();
     }
     ix.timer.end(t);
+    if (pl.nlevels == 1 && decide(start[0], nb[0]) == FALLBACK) return false;
 
     {
         Text1Args ta{};
@@ -1233,14 +1433,19 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     u64 *cur = r.bufA, *other = r.bufB;
     int consumed = pl.D[0];
     for (int l = 1; l < pl.nlevels; ++l) {
+        level_tables(l);
         const u32 nparents = (u32)nb[l - 1];
         const int dshift = 32 + pl.pb + (pl.KB - consumed - pl.D[l]);
+        // tiles of this level (a tile never straddles two parents)
+        const size_t desc_cap = (size_t)div_up_u(len, P_TILE) + nparents + 1;
+        uint4 *desc = ar.get<uint4>(desc_cap);
+        u32 *tile_off = ar.get<u32>((size_t)nparents + 2);
         t = ix.timer.begin("msd_hist", (double)len * 8.0);
         msd_tile_offsets_kernel<<<1, 1024, 0, st>>>(start[l - 1], nparents, tile_off, d_misc + 1);
         KERNEL_CHECK();
         msd_tile_desc_kernel<<<div_up_u(nparents, 8), 256, 0, st>>>(start[l - 1], nparents, tile_off, desc);
         KERNEL_CHECK();
-        const unsigned grid = (unsigned)desc_cap;
+        const unsigned grid = (unsigned)std::min<size_t>(desc_cap, 0x7fffffffu);
         msd_hist_elems_kernel<<<std::min(grid, 4u * sm_count(ix.device)), P_NT, 0, st>>>(cur, desc, d_misc + 1, pl.D[l], dshift, cursor[l]);
         KERNEL_CHECK();
         {
@@ -1250,6 +1455,8 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
             KERNEL_CHECK();
         }
         ix.timer.end(t);
+        // (MORE extends pl.nlevels: the loop then runs one more level after this one)
+        if (l == pl.nlevels - 1 && decide(start[l], nb[l]) == FALLBACK) return false;
         pa.in = cur; pa.out = other;
         pa.D = pl.D[l];
         pa.dshift = dshift;
@@ -1265,11 +1472,6 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         consumed += pl.D[l];
     }
 
-    // ---- do the buckets fit one SM? ----
-    u32 maxbucket = 0;
-    read_back(&maxbucket, d_misc, 4, st);
-    if (maxbucket > (u32)L3_MAXB) return false;
-
     // ---- in-SM sort of every bucket, outputs of round 0 ----
     const int last = pl.nlevels - 1;
     t = ix.timer.begin("msd_local_sort", (double)len * (8.0 + 4.0 + (want_bwt && pl.pb ? 1.0 : 0.0)));
@@ -1284,6 +1486,7 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     la.rank = r.rank; la.valid = r.valid; la.act = r.act; la.act_count = d_misc + 3;
     la.primary = r.d_primary;
     la.flagged = flagged; la.nflagged = d_misc + 4;
+    la.big = bigtiles; la.nbig = d_misc + 5;
     la.ntiles = ntl3;
     msd_local_sort_kernel<<<std::min(ntl3, (unsigned)L3_CTAS * sm_count(ix.device)), L3_NT, L3_SMEM, st>>>(la);
     KERNEL_CHECK();
@@ -1295,6 +1498,31 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         read_back(hmisc, d_misc, sizeof hmisc, st);
     }
     ix.timer.end(t);
+    if (hmisc[5]) {
+        // tiles with an oversize bucket: their other buckets are ordered by the bitonic network, the
+        // oversize ones are emitted as shallow groups
+        t = ix.timer.begin("msd_oversize", (double)r.shallow_elems * (8.0 + 4.0 + 4.0 + 4.0));
+        OverArgs oa{};
+        oa.list = ar.get<uint4>((size_t)len / (size_t)L3_MAXB + 2);
+        oa.count = d_misc + 6;
+        u32 *shortb = ar.get<u32>(32);
+        oa.shortb = shortb;
+        oa.d0 = (u32)(pl.BB / b);
+        oa.fix = ar.get<u32>(4 * 32);
+        oa.nfix = d_misc + 7;
+        msd_short_buckets_kernel<<<1, 32, 0, st>>>(ix.packed, n, b, pl.BB, oa.d0, shortb);
+        KERNEL_CHECK();
+        msd_bigtile_kernel<<<hmisc[5], L3_NT, RB_SMEM, st>>>(la, oa);
+        KERNEL_CHECK();
+        msd_emit_shallow_kernel<<<8u * sm_count(ix.device), 256, 0, st>>>(la, oa);
+        KERNEL_CHECK();
+        msd_fix_shorts_kernel<<<1, 1, 0, st>>>(la, oa);
+        KERNEL_CHECK();
+        read_back(hmisc, d_misc, sizeof hmisc, st);
+        r.shallow_buckets = hmisc[6];
+        if (hmisc[6]) r.depth0 = oa.d0;
+        ix.timer.end(t);
+    }
 
     r.bucket_start = start[last];
     r.m = hmisc[3];

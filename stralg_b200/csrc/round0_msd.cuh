@@ -23,6 +23,7 @@ struct MsdPlan {
     int KB;            // K * bits
     int pb;            // bits of the preceding symbol carried in an element (0: BWT is gathered afterwards)
     int R;             // key bits left for the in-SM sort = KB - BB
+    int dmax;          // largest digit a partition level takes (a multiple of the symbol width)
 };
 
 struct Round0Msd {
@@ -36,14 +37,20 @@ struct Round0Msd {
     MsdPlan plan;
     const u32 *bucket_start;  // 2^BB + 1 entries (workspace arena)
     u32 m;                    // number of active suffixes written to act
+    u32 depth0;               // symbols every active group is known to share: K, or BB / bits when oversize
+                              // buckets were emitted unsorted as shallow groups
+    u32 levels_added;         // partition levels added to the plan because of a skewed bucket histogram
+    u32 shallow_buckets;      // oversize buckets emitted as shallow groups
+    u64 shallow_elems;        // suffixes in them
     bool bwt_written;         // BWT rows were emitted by the sort (else gather them from the final SA)
 };
 
 // Plans the levels for this text; false when the bucketed sort does not apply (e.g. disabled).
 bool msd_make_plan(u32 len, u32 sigma, int bits, MsdPlan &plan);
 
-// Sorts all suffixes by their first K symbols.  Returns false (nothing usable written) when a
-// bucket exceeds what one SM sorts in shared memory; the caller then runs the LSD path.
+// Sorts all suffixes by their first K symbols.  Buckets that exceed what one SM sorts in shared
+// memory are emitted unsorted as shallow groups (depth0 < K); returns false (nothing usable written)
+// only when such buckets hold more than 1/8 of the text: the caller then runs the LSD path.
 bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r);
 
 // rank[sa[g]] = g for every suffix whose valid bit is clear (dense doubling rounds)

@@ -904,6 +904,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
 
     // ---- round 0, preferred: MSD bucket sort of 8-byte elements (round0_msd.cu) ----
     bool done0 = false;
+    u32 depth0 = 0;  // symbols every active group shares after round 0 (0: K)
     {
         Round0Msd r0{};
         if (msd_make_plan(len, ix.sigma, b, r0.plan)) {
@@ -923,6 +924,9 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 ix.stats.round0_mode = 1;
                 ix.stats.bucket_bits = r0.plan.BB;
                 ix.stats.passes_elems = (u64)len * r0.plan.nlevels;
+                ix.stats.shallow_buckets = r0.shallow_buckets;
+                ix.stats.shallow_elems = r0.shallow_buckets ? r0.shallow_elems : 0;
+                depth0 = r0.depth0;
             } else {
                 ar.release_to(mk);
             }
@@ -1020,7 +1024,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
         act2 = ar.get<u32>(m);
         const int lo_bits = std::max(1, log2len);
         const int key_bits = std::min(64, 2 * lo_bits);
-        u64 h = (u64)K;
+        u64 h = depth0 ? (u64)depth0 : (u64)K;
         u32 huniform[8];
         while (m > 0) {
             ix.stats.rounds++;

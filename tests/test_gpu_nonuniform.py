@@ -1,0 +1,197 @@
+"""Non-uniform texts (BASELINE.json configs[4]; SURVEY 8(d) C3 repeat-rich / C5).
+
+The reference's constructors are input-insensitive (stralg/sa_is.c:340-441 is linear on any text;
+performance/suffix_array_construction.c:81-184 times "Equal" strings next to random ones), so the
+bucketed round 0 must not depend on a flat k-mer spectrum:
+
+* a bucket too large for one SM (poly-A runs, tandem / interspersed repeats) is emitted as a shallow
+  group and ordered by the doubling rounds (round0_msd.cu: OverArgs),
+* a skewed spectrum (real DNA) adds a partition level,
+* only texts whose oversize buckets hold more than 1/8 of the suffixes take the LSD path.
+
+Small sizes: SA / ISA / LCP / BWT bit-exact against the reference's SA-IS (oracle/_ref) or the
+restatement.  Large sizes (256 Mi repeat-rich, 2^30 a^n): the suffix-array checker of
+stralg_b200/texts.py, independent of the product kernels.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _skewed(rng, n, p):
+    return rng.choice(np.arange(1, len(p) + 1), size=n, p=p).astype(np.uint8)
+
+
+def nonuniform_texts():
+    from stralg_b200 import texts as T
+    rng = np.random.default_rng(4242)
+    out = []
+    base = rng.integers(1, 5, 1 << 20).astype(np.uint8)
+    # poly-A in the middle and at the very end: the A^k bucket is oversize and holds the short suffixes
+    t = base.copy()
+    t[400000:420000] = 1
+    t[-5000:] = 1
+    out.append(("polyA_mid_end_1M", t, 5))
+    # the same with the run ending one symbol before the end, and a (CA)^k tandem repeat
+    t = base.copy()
+    t[-9000:-1] = 1
+    t[100000:130000] = np.tile([2, 1], 15000)
+    out.append(("polyA_tandemCA_1M", t, 5))
+    # three copies of a 60 k block and twenty of a 4 k block (deep repeats, few copies)
+    t = base.copy()
+    blk = t[5000:65000].copy()
+    t[300000:360000] = blk
+    t[700000:760000] = blk
+    small = t[900000:904000].copy()
+    for k in range(20):
+        t[20000 * k + 1000: 20000 * k + 5000] = small
+    out.append(("block_copies_1M", t, 5))
+    # skewed symbol distribution (70 % A): the planned average bucket says little, a level is added
+    out.append(("skewed_70A_1M", _skewed(rng, 1 << 20, [0.7, 0.1, 0.1, 0.1]), 5))
+    out.append(("skewed_97A_300k", _skewed(rng, 300000, [0.97, 0.01, 0.01, 0.01]), 5))
+    # real DNA: the genome sample, once and tiled with 1.6 % point mutations
+    hg = T.hg38_base()
+    out.append(("hg38_sample_500k", hg, 5))
+    tiled = np.tile(hg[:200000], 6)
+    mut = rng.random(len(tiled)) < 1 / 64
+    tiled[mut] = (tiled[mut] - 1 + rng.integers(1, 4, int(mut.sum()))) % 4 + 1
+    out.append(("hg38_tiled_mut_1200k", tiled.astype(np.uint8), 5))
+    # other alphabets: binary with long runs, 16 letters with one dominant letter
+    runs = np.repeat(rng.integers(1, 3, 40000), rng.integers(1, 60, 40000))[:600000].astype(np.uint8)
+    out.append(("binary_runs_600k", runs, 3))
+    out.append(("sym16_skewed_500k", _skewed(rng, 500000, [0.85] + [0.01] * 15), 17))
+    out.append(("byte_skewed_400k", _skewed(rng, 400000, [0.9] + [0.1 / 254] * 254), 256))
+    return out
+
+
+TEXTS = None
+
+
+def _texts():
+    global TEXTS
+    if TEXTS is None:
+        TEXTS = {t[0]: t for t in nonuniform_texts()}
+    return TEXTS
+
+
+NAMES = ["polyA_mid_end_1M", "polyA_tandemCA_1M", "block_copies_1M", "skewed_70A_1M", "skewed_97A_300k",
+         "hg38_sample_500k", "hg38_tiled_mut_1200k", "binary_runs_600k", "sym16_skewed_500k", "byte_skewed_400k"]
+
+# default plan; never add a level (everything oversize becomes a shallow group, however much it is);
+# always add a level when one bucket is oversize; tiny buckets (many segments per tile) with shallow groups
+MODES = {
+    "default": {},
+    "shallow_only": {"B200SA_MSD_MORE_FRAC": "1", "B200SA_MSD_OVER_FRAC": "1"},
+    "more_levels": {"B200SA_MSD_MORE_FRAC": "100000000", "B200SA_MSD_OVER_FRAC": "1"},
+    "avg64_shallow": {"B200SA_MSD_AVG": "64", "B200SA_MSD_MORE_FRAC": "1", "B200SA_MSD_OVER_FRAC": "1"},
+}
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+@pytest.mark.parametrize("name", NAMES)
+def test_nonuniform_tables_match_oracle(engine, oracle, ref, name, mode, monkeypatch):
+    for k, v in MODES[mode].items():
+        monkeypatch.setenv(k, v)
+    _, sym, sigma = _texts()[name]
+    codes = np.concatenate([np.asarray(sym, dtype=np.uint8), np.zeros(1, np.uint8)])
+    idx = engine.SuffixArrayIndex.build(codes[:-1], sigma, isa=True, lcp=True, bwt=True, occ=True)
+    st = idx.stats()
+    if mode != "default":
+        # OVER_FRAC = 1: nothing may fall back to the LSD path
+        assert st["round0_mode"] == 1, (name, mode, st)
+    sa_exp = ref.sa(codes, sigma, "sa_is") if ref is not None else oracle.sa(codes)
+    sa = idx.sa()
+    assert np.array_equal(sa, sa_exp), f"{name}/{mode}: SA differs at {np.nonzero(sa != sa_exp)[0][:5]}, stats {st}"
+    assert np.array_equal(idx.isa(), oracle.inverse(sa_exp))
+    lcp_exp = oracle.lcp(codes, sa_exp)
+    lcp = idx.lcp()
+    assert np.array_equal(lcp, lcp_exp), f"{name}/{mode}: LCP differs at {np.nonzero(lcp != lcp_exp)[0][:5]}"
+    bwt_exp = oracle.bwt(codes, sa_exp)
+    assert np.array_equal(idx.bwt(), bwt_exp), f"{name}/{mode}: BWT differs"
+    assert idx.primary == int(np.nonzero(sa_exp == 0)[0][0])
+    ck = oracle.o_checkpoints(bwt_exp, sigma, 64)
+    rng = np.random.default_rng(3)
+    qa = rng.integers(0, sigma, 3000).astype(np.uint8)
+    qi = rng.integers(0, len(sa) + 1, 3000).astype(np.uint32)
+    assert np.array_equal(idx.occ(qa, qi), oracle.o_probe(bwt_exp, ck, sigma, 64, qa, qi))
+    print(f"[nonuniform] {name}/{mode}: {st}")
+    idx.close()
+
+
+def test_shallow_groups_are_taken(engine):
+    """The poly-A text must really go through the shallow-group path (no silent LSD fallback), and the
+    skewed one must really get a level added."""
+    _, sym, sigma = _texts()["polyA_mid_end_1M"]
+    idx = engine.SuffixArrayIndex.build(np.asarray(sym, dtype=np.uint8), sigma)
+    st = idx.stats()
+    assert st["round0_mode"] == 1 and st["shallow_buckets"] >= 1, st
+    idx.close()
+    _, sym, sigma = _texts()["skewed_70A_1M"]
+    idx = engine.SuffixArrayIndex.build(np.asarray(sym, dtype=np.uint8), sigma)
+    st2 = idx.stats()
+    assert st2["round0_mode"] == 1 and st2["passes0"] >= 2, st2
+    idx.close()
+
+
+def test_two_devices_one_process(engine):
+    """the opt-in for > 48 KB of dynamic shared memory is per device; a process that
+    builds on a second GPU must not fail.  Runs only where two devices are visible."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one visible device")
+    rng = np.random.default_rng(5)
+    sym = rng.integers(1, 5, 300000).astype(np.uint8)
+    a = engine.SuffixArrayIndex.build(sym, 5, device=0)
+    b = engine.SuffixArrayIndex.build(sym, 5, device=1)
+    assert np.array_equal(a.sa(), b.sa())
+    a.close()
+    b.close()
+
+
+# ---- large sizes: properties -----------------------------------------------------------------------
+def _build_and_check(engine, text, n, sigma, label, **kw):
+    import time
+    import torch
+    from stralg_b200 import texts as T
+    lib = engine.load()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    idx = engine.SuffixArrayIndex.build(text[:n], sigma, occ=False, **kw)
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    st = idx.stats()
+    lib.b200sa_release_workspace(0)
+    sa = T.device_view(idx.device_ptr("sa"), n + 1, 4)
+    ok, why = T.check_suffix_array(text, sa, n)
+    print(f"[nonuniform-large] {label}: n = {n}, build {dt * 1e3:.0f} ms ({n / dt / 1e6:.0f} Mchar/s), stats = {st}")
+    assert ok, (label, why, st)
+    idx.close()
+    return st, dt
+
+
+def test_repeat_rich_256M(engine):
+    """SURVEY 8(d) C3 repeat-rich variant at 256 Mi: copies of random 300-6 000 bp segments (10 % of the text
+    duplicated).  Must stay on the bucketed round 0."""
+    import torch
+    from stralg_b200 import texts as T
+    lib = engine.load()
+    n = int(float(os.environ.get("B200SA_NONUNIFORM_N", 1 << 28)))
+    text = T.random_codes(lib, n, 4, 31337)
+    info = T.add_repeats(text, n)
+    torch.cuda.synchronize()
+    st, _ = _build_and_check(engine, text, n, 5, f"repeat-rich {info}")
+    assert st["round0_mode"] == 1, st
+
+
+def test_unary_2pow30(engine):
+    """Config 5 (C5b): a^n at n = 2^30, the worst-case doubling depth."""
+    import torch
+    from stralg_b200 import texts as T
+    free, _ = torch.cuda.mem_get_info()
+    n = int(float(os.environ.get("B200SA_UNARY_N", (1 << 30) if free > 100e9 else (1 << 26))))
+    text, sigma = T.stress_text(engine.load(), "unary", n)
+    st, _ = _build_and_check(engine, text, n, sigma, "a^n")
+    assert st["rounds"] >= 20 or n < (1 << 30)
