@@ -5,7 +5,7 @@
  * stralg's suffix_array.h / bwt.h would call (reference file:line cited per entry point; paths
  * are relative to the stralg checkout).  Plain pointers and sizes only, no CUDA or torch types.
  * The reference-named shims (sa_is_construction, compute_lcp, init_bwt_table,
- * init_bwt_exact_match_iter, ...) live in include/stralg_compat/ and are implemented on top of
+ * init_bwt_exact_match_iter, ...) are declared in include/stralg_compat.h and implemented on top of
  * this header by libstralg_b200.so.
  *
  * Conventions (stralg README.md:106-134, stralg/error.h:7-21): an `enum b200sa_error *err`
@@ -138,6 +138,26 @@ int b200sa_search_batch(const b200sa_index *idx, const uint8_t *patterns, const 
 int b200sa_search_device(const b200sa_index *idx, const uint8_t *d_patterns,
                          const uint64_t *d_offsets, uint32_t fixed_len, uint64_t npat,
                          uint32_t *d_L, uint32_t *d_R, void *stream);
+/* ---- packed reads (DNA index, sigma <= 5) ---------------------------------------------------------
+ * The consuming application streams FASTQ (bioinf/fastq.c:16-34, bwt_readmapper.c:128-161): reads are
+ * short, of one length, over ACGT.  Packed, a read of read_len bases is read_len 2-bit symbols
+ * (code - 1), four to a byte, the FIRST base in the two most significant bits of its byte; read q
+ * starts at byte q * stride_bytes (stride_bytes >= ceil(read_len / 4); 0 selects exactly that).
+ * A quarter of the bytes over PCIe and through the kernel; (L, R) are bit-identical to
+ * b200sa_search_batch on the unpacked reads.  The device variant reads whole aligned 8-byte words:
+ * d_packed must be 8-byte aligned and readable up to the next 8-byte boundary after the last read.
+ * b200sa_pack_reads / _device convert one-byte-per-base codes (1..4; anything else fails with
+ * B200SA_ERR_BAD_SYMBOL -- the reference skips such reads, remap.c:80-84, bwt_readmapper.c:136-142). */
+int b200sa_search_batch_packed(const b200sa_index *idx, const uint8_t *packed, uint32_t read_len,
+                               uint32_t stride_bytes, uint64_t npat, uint32_t *L, uint32_t *R);
+int b200sa_search_device_packed(const b200sa_index *idx, const uint8_t *d_packed, uint32_t read_len,
+                                uint32_t stride_bytes, uint64_t npat, uint32_t *d_L, uint32_t *d_R,
+                                void *stream);
+int b200sa_pack_reads(const uint8_t *codes, uint32_t read_len, uint32_t stride_bytes, uint64_t npat,
+                      uint8_t *packed);
+int b200sa_pack_reads_device(const uint8_t *d_codes, uint32_t read_len, uint32_t stride_bytes,
+                             uint64_t npat, uint8_t *d_packed, int device, void *stream);
+
 /* Measurement aid: the same search (DNA index, 8-byte aligned device patterns), run by a counting
  * variant of the kernel.  counts[0] = 32-byte O-block loads, [1] = 8-byte pattern words,
  * [2] = 8-byte packed-text words, [3] = 4-byte SA / ISA loads issued for the whole batch:
@@ -145,6 +165,10 @@ int b200sa_search_device(const b200sa_index *idx, const uint8_t *d_patterns,
 int b200sa_search_traffic(const b200sa_index *idx, const uint8_t *d_patterns,
                           const uint64_t *d_offsets, uint32_t fixed_len, uint64_t npat,
                           uint32_t *d_L, uint32_t *d_R, uint64_t counts[4], void *stream);
+/* the same for packed reads (counts[1] = 8-byte words of packed reads) */
+int b200sa_search_traffic_packed(const b200sa_index *idx, const uint8_t *d_packed, uint32_t read_len,
+                                 uint32_t stride_bytes, uint64_t npat, uint32_t *d_L, uint32_t *d_R,
+                                 uint64_t counts[4], void *stream);
 
 /* ---- locate (next_bwt_exact_match_iter, bwt.c:201-217) -------------------------------------
  * pos_off[npat + 1] receives a CSR; positions of pattern p are pos[pos_off[p] .. pos_off[p+1]),

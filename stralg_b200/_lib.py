@@ -76,6 +76,15 @@ SIGNATURES = {
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200sa_search_traffic": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64,
                                         C.c_void_p, C.c_void_p, u64p, C.c_void_p]),
+    "b200sa_search_batch_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64,
+                                             C.c_void_p, C.c_void_p]),
+    "b200sa_search_device_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64,
+                                              C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200sa_search_traffic_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64,
+                                               C.c_void_p, C.c_void_p, u64p, C.c_void_p]),
+    "b200sa_pack_reads": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]),
+    "b200sa_pack_reads_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_int,
+                                           C.c_void_p]),
     "b200sa_locate_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                       C.c_void_p, C.c_uint64, u64p]),
     "b200sa_locate_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,

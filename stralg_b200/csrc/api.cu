@@ -148,17 +148,37 @@ void output_cache_purge(int device) {
 static Arena g_arena[64];
 static std::mutex g_arena_mu[64];
 
+namespace b200sa {
+namespace {
+std::mutex g_pool_mu;
+cudaMemPool_t g_pool[64] = {};
+}  // namespace
+cudaMemPool_t library_pool() {
+    int device = 0;
+    CUDA_CHECK(cudaGetDevice(&device));
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    cudaMemPool_t &p = g_pool[device & 63];
+    if (!p) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        CUDA_CHECK(cudaMemPoolCreate(&p, &props));
+        uint64_t never = UINT64_MAX;
+        CUDA_CHECK(cudaMemPoolSetAttribute(p, cudaMemPoolAttrReleaseThreshold, &never));
+    }
+    return p;
+}
+}  // namespace b200sa
+
 static void use_device(int device) {
     CUDA_CHECK(cudaSetDevice(device));
     static std::mutex mu;
-    static bool pool_set[64] = {};
+    static bool once[64] = {};
     std::lock_guard<std::mutex> lock(mu);
-    if (device >= 0 && device < 64 && !pool_set[device]) {
-        cudaMemPool_t pool;
-        CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t never = UINT64_MAX;
-        CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never));
-        if (const char *g = getenv("B200SA_L2_FETCH")) {
+    if (device >= 0 && device < 64 && !once[device]) {
+        if (const char *g = getenv("B200SA_L2_FETCH")) {  // measurement aid
             size_t before = 0;
             cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
             cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
@@ -166,9 +186,68 @@ static void use_device(int device) {
             cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
             fprintf(stderr, "b200sa: L2 fetch granularity %zu -> %zu (%s)\n", before, after, cudaGetErrorString(e));
         }
-        pool_set[device] = true;
+        once[device] = true;
     }
 }
+
+// Restores the caller's current device when an entry point returns (the library must not
+// silently switch the device of the process that hosts it).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            cudaGetLastError();
+            prev = -1;
+        }
+        CUDA_CHECK(cudaSetDevice(device));
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// Per-device staging for the host-buffer search entry points: two non-blocking streams and grow-only
+// device buffers, created once -- a call costs no cudaMalloc / stream creation in the steady state.
+struct SearchLanes {
+    std::mutex mu;
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t ready = nullptr;
+    u8 *patterns = nullptr;
+    size_t pat_cap = 0;
+    u32 *L = nullptr, *R = nullptr;
+    size_t lr_cap = 0;
+    void reserve(size_t pat_bytes, size_t npat) {
+        if (!s[0]) {
+            CUDA_CHECK(cudaStreamCreateWithFlags(&s[0], cudaStreamNonBlocking));
+            CUDA_CHECK(cudaStreamCreateWithFlags(&s[1], cudaStreamNonBlocking));
+            CUDA_CHECK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        }
+        if (pat_bytes > pat_cap) {
+            if (patterns) CUDA_CHECK(cudaFree(patterns));
+            patterns = nullptr;
+            pat_cap = (pat_bytes + ((size_t)1 << 20)) & ~(((size_t)1 << 20) - 1);
+            patterns = (u8 *)malloc_or_purge(pat_cap);
+        }
+        if (npat > lr_cap) {
+            if (L) CUDA_CHECK(cudaFree(L));
+            if (R) CUDA_CHECK(cudaFree(R));
+            L = R = nullptr;
+            lr_cap = (npat + 4095) & ~(size_t)4095;
+            L = (u32 *)malloc_or_purge(lr_cap * 4);
+            R = (u32 *)malloc_or_purge(lr_cap * 4);
+        }
+    }
+    void release() {
+        if (patterns) cudaFree(patterns);
+        if (L) cudaFree(L);
+        if (R) cudaFree(R);
+        patterns = nullptr;
+        L = R = nullptr;
+        pat_cap = lr_cap = 0;
+    }
+};
+static SearchLanes g_lanes[64];
+static SearchLanes &search_lanes(int device) { return g_lanes[device & 63]; }
 
 // ---- native index file ---------------------------------------------------------------------------
 // [header][section]*: the header carries the scalars, every section is {tag, element size, count}
@@ -265,6 +344,7 @@ int b200sa_device_count(void) {
 static int build_into(b200sa_index *h, const uint8_t *codes, uint64_t n, uint32_t sigma, uint32_t flags, int device,
                       void *stream, enum b200sa_error *err) {
     API_GUARD_BEGIN
+    DeviceGuard guard(device);
     use_device(device);
     DeviceIndex &ix = h->ix;
     ix.stream = (cudaStream_t)stream;
@@ -368,6 +448,7 @@ int b200sa_extend(b200sa_index *idx, const uint8_t *codes, uint32_t flags) {
     const bool need_bwt = ((flags & B200SA_BUILD_BWT) && !ix.bwt.ptr) || need_occ;
     if (!need_isa && !need_lcp && !need_bwt) return 0;
     API_GUARD_BEGIN
+    DeviceGuard guard(ix.device);
     use_device(ix.device);
     cudaStream_t st = ix.stream;
     std::lock_guard<std::mutex> arena_lock(g_arena_mu[ix.device & 63]);
@@ -384,7 +465,27 @@ int b200sa_extend(b200sa_index *idx, const uint8_t *codes, uint32_t flags) {
     }
     DevBuf<int> d_err(1, st);
     CUDA_CHECK(cudaMemsetAsync(d_err.ptr, 0, 4, st));
+    // the text must be the one the suffix array was built from: same symbol counts, no bad code
+    // (pack_text recomputes the C table; the index keeps its own until the text has been accepted)
+    u32 c_saved[256];
+    u64 counts_saved[256];
+    memcpy(c_saved, ix.c_host, sizeof c_saved);
+    memcpy(counts_saved, ix.sym_counts_host, sizeof counts_saved);
+    DevBuf<u32> c_table_saved = std::move(ix.c_table);
     pack_text(ix, d_err.ptr);
+    int herr = 0;
+    read_back(&herr, d_err.ptr, 4, st);
+    const bool same_text = memcmp(counts_saved, ix.sym_counts_host, sizeof counts_saved) == 0;
+    if (herr || !same_text) {
+        memcpy(ix.c_host, c_saved, sizeof c_saved);
+        memcpy(ix.sym_counts_host, counts_saved, sizeof counts_saved);
+        ix.c_table = std::move(c_table_saved);
+        ix.text_ptr = nullptr;
+        ix.packed = nullptr;
+        ix.arena = nullptr;
+        if (herr) return fail(B200SA_ERR_BAD_SYMBOL, "text holds a code outside 1..sigma-1", nullptr);
+        return fail(B200SA_ERR_BAD_ARGUMENT, "b200sa_extend: not the text this index was built from (symbol counts differ)", nullptr);
+    }
     ix.text.release();
     ix.text_ptr = nullptr;
     if (need_isa) build_inverse(ix);
@@ -404,8 +505,11 @@ int b200sa_extend(b200sa_index *idx, const uint8_t *codes, uint32_t flags) {
 
 void b200sa_free(b200sa_index *idx) {
     if (!idx) return;
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
     cudaSetDevice(idx->ix.device);
     delete idx;
+    if (prev >= 0) cudaSetDevice(prev);
 }
 
 int b200sa_stats(const b200sa_index *idx, struct b200sa_stats *out) {
@@ -453,7 +557,7 @@ static int copy_out(const b200sa_index *idx, const void *dptr, void *host, size_
     if (!idx || !host) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
     if (!dptr) return fail(B200SA_ERR_NOT_BUILT, std::string(what) + " was not requested at build time", nullptr);
     API_GUARD_BEGIN
-    CUDA_CHECK(cudaSetDevice(idx->ix.device));
+    DeviceGuard guard(idx->ix.device);
     const size_t piece = (size_t)32 << 20;  // (pieces measured faster than one multi-gigabyte copy: 57 vs 52 GB/s)
     for (size_t at = 0; at < bytes; at += piece)
         CUDA_CHECK(cudaMemcpyAsync((char *)host + at, (const char *)dptr + at, std::min(piece, bytes - at),
@@ -494,7 +598,7 @@ int b200sa_copy_async(const b200sa_index *idx, int what, void *host, void *strea
     }
     if (!src) return fail(B200SA_ERR_NOT_BUILT, "table was not requested at build time (or was dropped)", nullptr);
     API_GUARD_BEGIN
-    CUDA_CHECK(cudaSetDevice(ix.device));
+    DeviceGuard guard(ix.device);
     // in pieces: the device-to-host copy engine serves one copy at a time, and a build running next to
     // this transfer reads a few words back per stage -- those must not queue behind gigabytes
     const size_t piece = (size_t)32 << 20;
@@ -508,10 +612,17 @@ uint64_t b200sa_launch_count(void) { return b200sa::g_kernel_launches; }
 uint64_t b200sa_workspace_bytes(int device) { return g_arena[device & 63].reserved(); }
 int b200sa_release_workspace(int device) {
     API_GUARD_BEGIN
-    CUDA_CHECK(cudaSetDevice(device));
+    DeviceGuard guard(device);
     std::lock_guard<std::mutex> lock(g_arena_mu[device & 63]);
     g_arena[device & 63].release_all();
     output_cache_purge(device);
+    cudaDeviceSynchronize();
+    cudaMemPoolTrimTo(library_pool(), 0);
+    {
+        SearchLanes &ln = search_lanes(device);
+        std::lock_guard<std::mutex> l2(ln.mu);
+        ln.release();
+    }
     return 0;
     API_GUARD_END(nullptr)
 }
@@ -529,7 +640,7 @@ int b200sa_copy_o_dense(const b200sa_index *idx, uint32_t *host) {
     if (entries * 4 > 0xFFFFFFFFull)
         return fail(B200SA_ERR_TOO_LARGE, "dense O table exceeds the reference's u32 byte size (bwt.c:50)", nullptr);
     API_GUARD_BEGIN
-    CUDA_CHECK(cudaSetDevice(ix.device));
+    DeviceGuard guard(ix.device);
     DevBuf<u32> d(entries, ix.stream);
     occ_dense(ix, d.ptr);
     CUDA_CHECK(cudaMemcpyAsync(host, d.ptr, entries * 4, cudaMemcpyDeviceToHost, ix.stream));
@@ -546,7 +657,7 @@ int b200sa_occ(const b200sa_index *idx, const uint8_t *a, const uint32_t *i, uin
         if (a[q] >= ix.sigma || i[q] > ix.len) return fail(B200SA_ERR_BAD_ARGUMENT, "O(a,i) query out of range", nullptr);
     if (!count) return 0;
     API_GUARD_BEGIN
-    CUDA_CHECK(cudaSetDevice(ix.device));
+    DeviceGuard guard(ix.device);
     cudaStream_t st = ix.stream;
     DevBuf<u8> da(count, st);
     DevBuf<u32> di(count, st), dout(count, st);
@@ -564,7 +675,7 @@ int b200sa_search_device(const b200sa_index *idx, const uint8_t *d_patterns, con
     if (!idx || (npat && (!d_patterns || !d_L || !d_R))) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
     if (idx->ix.occ_layout == OCC_NONE) return fail(B200SA_ERR_NOT_BUILT, "O table was not requested at build time", nullptr);
     API_GUARD_BEGIN
-    CUDA_CHECK(cudaSetDevice(idx->ix.device));
+    DeviceGuard guard(idx->ix.device);
     fm_search(idx->ix, d_patterns, d_offsets, fixed_len, npat, d_L, d_R, (cudaStream_t)stream);
     return 0;
     API_GUARD_END(nullptr)
@@ -577,7 +688,7 @@ int b200sa_search_traffic(const b200sa_index *idx, const uint8_t *d_patterns, co
     if (idx->ix.occ_layout != OCC_DNA32 || (((uintptr_t)d_patterns) & 7))
         return fail(B200SA_ERR_NOT_BUILT, "traffic counters exist for the DNA search kernel (8-byte aligned patterns) only", nullptr);
     API_GUARD_BEGIN
-    CUDA_CHECK(cudaSetDevice(idx->ix.device));
+    DeviceGuard guard(idx->ix.device);
     cudaStream_t st = (cudaStream_t)stream;
     DevBuf<unsigned long long> d(4, st);
     CUDA_CHECK(cudaMemsetAsync(d.ptr, 0, 4 * sizeof(unsigned long long), st));
@@ -590,10 +701,27 @@ int b200sa_search_traffic(const b200sa_index *idx, const uint8_t *d_patterns, co
     API_GUARD_END(nullptr)
 }
 
-// Host buffers in, host (L, R) out.  The batch is cut into pieces that alternate between two
-// internal streams: while the kernel of one piece runs, the patterns of the next cross PCIe and the
-// results of the previous one return (pinned host memory makes the copies truly asynchronous;
-// pageable memory still works, staged by the driver).
+// Host buffers in, host (L, R) out.
+//  * A handful of short patterns (the reference's one-pattern iterator, bwt.c:164-199, through the
+//    drop-in): the patterns are written into mapped pinned memory, one kernel reads them there and
+//    stores (L, R) next to them -- one launch and one stream synchronisation, no cudaMemcpy.
+//  * Otherwise the batch is cut into pieces that alternate between two internal streams: while the
+//    kernel of one piece runs, the patterns of the next cross PCIe and the results of the previous
+//    one return (pinned host memory makes the copies truly asynchronous; pageable memory still
+//    works, staged by the driver).  Streams and device staging persist per device (SearchLanes).
+namespace {
+struct SearchMailbox {  // per host thread and device: 8 KB of mapped pinned memory
+    u8 *host[64] = {};
+    u8 *dev[64] = {};
+    ~SearchMailbox() {
+        for (auto p : host)
+            if (p) cudaFreeHost(p);
+    }
+};
+thread_local SearchMailbox t_search_mailbox;
+const size_t kMailPat = 4096, kMailOff = 4096, kMailL = 4096 + 65 * 8, kMailR = kMailL + 64 * 4, kMailBytes = 8192;
+}  // namespace
+
 int b200sa_search_batch(const b200sa_index *idx, const uint8_t *patterns, const uint64_t *offsets,
                         uint32_t fixed_len, uint64_t npat, uint32_t *L, uint32_t *R) {
     if (!idx || (npat && (!patterns || !L || !R))) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
@@ -601,12 +729,35 @@ int b200sa_search_batch(const b200sa_index *idx, const uint8_t *patterns, const 
     if (!npat) return 0;
     API_GUARD_BEGIN
     const DeviceIndex &ix = idx->ix;
-    CUDA_CHECK(cudaSetDevice(ix.device));
+    DeviceGuard guard(ix.device);
     cudaStream_t st = ix.stream;
     const uint64_t total = offsets ? offsets[npat] : (uint64_t)fixed_len * npat;
-    DevBuf<u8> dp(total + 16, st);  // padded: the DNA kernel reads whole aligned 8-byte words
+    if (npat <= 64 && total + 16 <= kMailPat && ix.device >= 0 && ix.device < 64) {
+        SearchMailbox &mb = t_search_mailbox;
+        if (!mb.host[ix.device]) {
+            CUDA_CHECK(cudaHostAlloc((void **)&mb.host[ix.device], kMailBytes, cudaHostAllocMapped));
+            CUDA_CHECK(cudaHostGetDevicePointer((void **)&mb.dev[ix.device], mb.host[ix.device], 0));
+        }
+        u8 *h = mb.host[ix.device], *d = mb.dev[ix.device];
+        const uint64_t base = offsets ? offsets[0] : 0;
+        memcpy(h, patterns + base, (size_t)(total - base));
+        memset(h + (total - base), 0, 16);
+        uint64_t *ho = (uint64_t *)(h + kMailOff);
+        if (offsets)
+            for (uint64_t q = 0; q <= npat; ++q) ho[q] = offsets[q] - base;
+        fm_search(ix, d, offsets ? (const u64 *)(d + kMailOff) : nullptr, fixed_len, npat, (u32 *)(d + kMailL),
+                  (u32 *)(d + kMailR), st);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        memcpy(L, h + kMailL, npat * 4);
+        memcpy(R, h + kMailR, npat * 4);
+        return 0;
+    }
+    SearchLanes &ln = search_lanes(ix.device);
+    std::lock_guard<std::mutex> lock(ln.mu);
+    ln.reserve(total + 16, npat);
+    u8 *dp = ln.patterns;
+    u32 *dL = ln.L, *dR = ln.R;
     DevBuf<u64> doff;
-    DevBuf<u32> dL(npat, st), dR(npat, st);
     if (offsets) {
         doff.alloc(npat + 1, st);
         CUDA_CHECK(cudaMemcpyAsync(doff.ptr, offsets, (npat + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -619,45 +770,156 @@ int b200sa_search_batch(const b200sa_index *idx, const uint8_t *patterns, const 
         const uint64_t avg = std::max<uint64_t>(1, total / npat);
         per = std::max<uint64_t>(1024, (piece_bytes / avg) & ~(uint64_t)7);
     }
-    if (per >= npat) {
-        if (total) CUDA_CHECK(cudaMemcpyAsync(dp.ptr, patterns, total, cudaMemcpyHostToDevice, st));
-        fm_search(ix, dp.ptr, offsets ? doff.ptr : nullptr, fixed_len, npat, dL.ptr, dR.ptr, st);
-        CUDA_CHECK(cudaMemcpyAsync(L, dL.ptr, npat * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaMemcpyAsync(R, dR.ptr, npat * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
-        return 0;
-    }
-    struct Lanes {
-        cudaStream_t s[2] = {nullptr, nullptr};
-        cudaEvent_t ready = nullptr;
-        ~Lanes() {
-            for (auto x : s)
-                if (x) cudaStreamDestroy(x);
-            if (ready) cudaEventDestroy(ready);
-        }
-    } lanes;
-    CUDA_CHECK(cudaStreamCreateWithFlags(&lanes.s[0], cudaStreamNonBlocking));
-    CUDA_CHECK(cudaStreamCreateWithFlags(&lanes.s[1], cudaStreamNonBlocking));
-    CUDA_CHECK(cudaEventCreateWithFlags(&lanes.ready, cudaEventDisableTiming));
-    CUDA_CHECK(cudaEventRecord(lanes.ready, st));  // the buffers (and the offsets) are allocated / copied in `st`
-    CUDA_CHECK(cudaStreamWaitEvent(lanes.s[0], lanes.ready, 0));
-    CUDA_CHECK(cudaStreamWaitEvent(lanes.s[1], lanes.ready, 0));
+    CUDA_CHECK(cudaEventRecord(ln.ready, st));  // (the offsets are copied in `st`)
+    CUDA_CHECK(cudaStreamWaitEvent(ln.s[0], ln.ready, 0));
+    CUDA_CHECK(cudaStreamWaitEvent(ln.s[1], ln.ready, 0));
     uint64_t k = 0;
     for (uint64_t q0 = 0; q0 < npat; q0 += per, ++k) {
         const uint64_t q1 = std::min(npat, q0 + per);
-        cudaStream_t ls = lanes.s[k & 1];
+        cudaStream_t ls = ln.s[k & 1];
         const uint64_t b0 = offsets ? offsets[q0] : q0 * fixed_len, b1 = offsets ? offsets[q1] : q1 * fixed_len;
-        if (b1 > b0) CUDA_CHECK(cudaMemcpyAsync(dp.ptr + b0, patterns + b0, b1 - b0, cudaMemcpyHostToDevice, ls));
+        if (b1 > b0) CUDA_CHECK(cudaMemcpyAsync(dp + b0, patterns + b0, b1 - b0, cudaMemcpyHostToDevice, ls));
         if (offsets)  // absolute offsets: same pattern base, the piece's slice of the offset array
-            fm_search(ix, dp.ptr, doff.ptr + q0, 0, q1 - q0, dL.ptr + q0, dR.ptr + q0, ls);
+            fm_search(ix, dp, doff.ptr + q0, 0, q1 - q0, dL + q0, dR + q0, ls);
         else
-            fm_search(ix, dp.ptr + b0, nullptr, fixed_len, q1 - q0, dL.ptr + q0, dR.ptr + q0, ls);
-        CUDA_CHECK(cudaMemcpyAsync(L + q0, dL.ptr + q0, (q1 - q0) * 4, cudaMemcpyDeviceToHost, ls));
-        CUDA_CHECK(cudaMemcpyAsync(R + q0, dR.ptr + q0, (q1 - q0) * 4, cudaMemcpyDeviceToHost, ls));
+            fm_search(ix, dp + b0, nullptr, fixed_len, q1 - q0, dL + q0, dR + q0, ls);
+        CUDA_CHECK(cudaMemcpyAsync(L + q0, dL + q0, (q1 - q0) * 4, cudaMemcpyDeviceToHost, ls));
+        CUDA_CHECK(cudaMemcpyAsync(R + q0, dR + q0, (q1 - q0) * 4, cudaMemcpyDeviceToHost, ls));
     }
-    CUDA_CHECK(cudaStreamSynchronize(lanes.s[0]));
-    CUDA_CHECK(cudaStreamSynchronize(lanes.s[1]));
+    CUDA_CHECK(cudaStreamSynchronize(ln.s[0]));
+    CUDA_CHECK(cudaStreamSynchronize(ln.s[1]));
     CUDA_CHECK(cudaStreamSynchronize(st));
+    return 0;
+    API_GUARD_END(nullptr)
+}
+
+// ---- packed reads ---------------------------------------------------------------------------------
+static int packed_args_ok(const b200sa_index *idx, uint32_t read_len, uint32_t &stride) {
+    if (!idx) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    if (idx->ix.occ_layout != OCC_DNA32)
+        return fail(B200SA_ERR_NOT_BUILT, "packed reads need a DNA index (sigma <= 5) with the O table", nullptr);
+    if (read_len == 0) return fail(B200SA_ERR_BAD_ARGUMENT, "empty reads", nullptr);
+    const uint32_t need = (read_len + 3u) / 4u;
+    if (stride == 0) stride = need;
+    if (stride < need) return fail(B200SA_ERR_BAD_ARGUMENT, "stride_bytes smaller than ceil(read_len / 4)", nullptr);
+    return 0;
+}
+
+int b200sa_search_device_packed(const b200sa_index *idx, const uint8_t *d_packed, uint32_t read_len, uint32_t stride,
+                                uint64_t npat, uint32_t *d_L, uint32_t *d_R, void *stream) {
+    if (int rc = packed_args_ok(idx, read_len, stride)) return rc;
+    if (npat && (!d_packed || !d_L || !d_R)) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    if (((uintptr_t)d_packed) & 7) return fail(B200SA_ERR_BAD_ARGUMENT, "packed reads must be 8-byte aligned", nullptr);
+    API_GUARD_BEGIN
+    DeviceGuard guard(idx->ix.device);
+    fm_search_packed(idx->ix, d_packed, read_len, stride, npat, d_L, d_R, (cudaStream_t)stream);
+    return 0;
+    API_GUARD_END(nullptr)
+}
+
+int b200sa_search_traffic_packed(const b200sa_index *idx, const uint8_t *d_packed, uint32_t read_len, uint32_t stride,
+                                 uint64_t npat, uint32_t *d_L, uint32_t *d_R, uint64_t counts[4], void *stream) {
+    if (int rc = packed_args_ok(idx, read_len, stride)) return rc;
+    if (!counts || (npat && (!d_packed || !d_L || !d_R))) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    if (((uintptr_t)d_packed) & 7) return fail(B200SA_ERR_BAD_ARGUMENT, "packed reads must be 8-byte aligned", nullptr);
+    API_GUARD_BEGIN
+    DeviceGuard guard(idx->ix.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf<unsigned long long> d(4, st);
+    CUDA_CHECK(cudaMemsetAsync(d.ptr, 0, 4 * sizeof(unsigned long long), st));
+    fm_search_packed(idx->ix, d_packed, read_len, stride, npat, d_L, d_R, st, d.ptr);
+    unsigned long long h[4];
+    CUDA_CHECK(cudaMemcpyAsync(h, d.ptr, sizeof h, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int i = 0; i < 4; ++i) counts[i] = h[i];
+    return 0;
+    API_GUARD_END(nullptr)
+}
+
+int b200sa_pack_reads(const uint8_t *codes, uint32_t read_len, uint32_t stride, uint64_t npat, uint8_t *packed) {
+    if ((npat && (!codes || !packed)) || read_len == 0) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    const uint32_t need = (read_len + 3u) / 4u;
+    if (stride == 0) stride = need;
+    if (stride < need) return fail(B200SA_ERR_BAD_ARGUMENT, "stride_bytes smaller than ceil(read_len / 4)", nullptr);
+    bool bad = false;
+    for (uint64_t q = 0; q < npat; ++q) {
+        const uint8_t *r = codes + q * (uint64_t)read_len;
+        uint8_t *o = packed + q * (uint64_t)stride;
+        for (uint32_t b = 0; b < stride; ++b) {
+            uint32_t v = 0;
+            for (uint32_t x = 0; x < 4; ++x) {
+                const uint32_t j = 4 * b + x;
+                uint32_t sym = 0;
+                if (j < read_len) {
+                    const uint32_t c = r[j];
+                    bad |= (c - 1u) > 3u;
+                    sym = (c - 1u) & 3u;
+                }
+                v |= sym << (6u - 2u * x);
+            }
+            o[b] = (uint8_t)v;
+        }
+    }
+    if (bad) return fail(B200SA_ERR_BAD_SYMBOL, "a read holds a code outside 1..4", nullptr);
+    return 0;
+}
+
+int b200sa_pack_reads_device(const uint8_t *d_codes, uint32_t read_len, uint32_t stride, uint64_t npat,
+                             uint8_t *d_packed, int device, void *stream) {
+    if ((npat && (!d_codes || !d_packed)) || read_len == 0) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    const uint32_t need = (read_len + 3u) / 4u;
+    if (stride == 0) stride = need;
+    if (stride < need) return fail(B200SA_ERR_BAD_ARGUMENT, "stride_bytes smaller than ceil(read_len / 4)", nullptr);
+    API_GUARD_BEGIN
+    DeviceGuard guard(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf<int> d_err(1, st);
+    CUDA_CHECK(cudaMemsetAsync(d_err.ptr, 0, 4, st));
+    pack_reads(d_codes, read_len, stride, npat, d_packed, d_err.ptr, st);
+    int herr = 0;
+    read_back(&herr, d_err.ptr, 4, st);
+    if (herr) return fail(B200SA_ERR_BAD_SYMBOL, "a read holds a code outside 1..4", nullptr);
+    return 0;
+    API_GUARD_END(nullptr)
+}
+
+// Host packed reads in, host (L, R) out: pieces of ~16 MB of packed reads alternate between two
+// internal streams, so that while the kernel of one piece runs the next piece crosses PCIe and the
+// results of the previous one return (pinned host memory makes the copies truly asynchronous).
+int b200sa_search_batch_packed(const b200sa_index *idx, const uint8_t *packed, uint32_t read_len, uint32_t stride,
+                               uint64_t npat, uint32_t *L, uint32_t *R) {
+    if (int rc = packed_args_ok(idx, read_len, stride)) return rc;
+    if (npat && (!packed || !L || !R)) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    if (!npat) return 0;
+    API_GUARD_BEGIN
+    const DeviceIndex &ix = idx->ix;
+    DeviceGuard guard(ix.device);
+    cudaStream_t st = ix.stream;
+    const uint64_t total = (uint64_t)stride * npat;
+    // a piece starts at a multiple of 8 reads, hence (any stride) at a multiple of 8 bytes
+    uint64_t per = npat;
+    const uint64_t piece_bytes = (uint64_t)16 << 20;
+    if (total > 2 * piece_bytes) per = std::max<uint64_t>(1024, (piece_bytes / stride) & ~(uint64_t)7);
+    SearchLanes &ln = search_lanes(ix.device);
+    std::lock_guard<std::mutex> lock(ln.mu);
+    ln.reserve(total + 16, npat);
+    u8 *dp = ln.patterns;
+    u32 *dL = ln.L, *dR = ln.R;
+    CUDA_CHECK(cudaEventRecord(ln.ready, st));
+    CUDA_CHECK(cudaStreamWaitEvent(ln.s[0], ln.ready, 0));
+    CUDA_CHECK(cudaStreamWaitEvent(ln.s[1], ln.ready, 0));
+    uint64_t k = 0;
+    for (uint64_t q0 = 0; q0 < npat; q0 += per, ++k) {
+        const uint64_t q1 = std::min(npat, q0 + per);
+        cudaStream_t ls = ln.s[k & 1];
+        const uint64_t b0 = q0 * stride, b1 = q1 * stride;
+        CUDA_CHECK(cudaMemcpyAsync(dp + b0, packed + b0, b1 - b0, cudaMemcpyHostToDevice, ls));
+        fm_search_packed(ix, dp + b0, read_len, stride, q1 - q0, dL + q0, dR + q0, ls);
+        CUDA_CHECK(cudaMemcpyAsync(L + q0, dL + q0, (q1 - q0) * 4, cudaMemcpyDeviceToHost, ls));
+        CUDA_CHECK(cudaMemcpyAsync(R + q0, dR + q0, (q1 - q0) * 4, cudaMemcpyDeviceToHost, ls));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(ln.s[0]));
+    CUDA_CHECK(cudaStreamSynchronize(ln.s[1]));
     return 0;
     API_GUARD_END(nullptr)
 }
@@ -667,7 +929,7 @@ int b200sa_locate_device(const b200sa_index *idx, const uint32_t *d_L, const uin
     if (!idx || !d_pos_off || (npat && (!d_L || !d_R))) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
     if (!can_locate(idx)) return fail(B200SA_ERR_NOT_BUILT, "no suffix array to locate with (dropped and not sampled)", nullptr);
     API_GUARD_BEGIN
-    CUDA_CHECK(cudaSetDevice(idx->ix.device));
+    DeviceGuard guard(idx->ix.device);
     cudaStream_t st = (cudaStream_t)stream;
     u64 t = fm_locate_count(idx->ix, d_L, d_R, npat, d_pos_off, st);
     if (total) *total = t;
@@ -685,7 +947,7 @@ int b200sa_sort_positions_device(const b200sa_index *idx, uint64_t npat, const u
     if (total > 0xFFFFFFFFull || npat > 0xFFFFFFFFull)
         return fail(B200SA_ERR_TOO_LARGE, "more than 2^32 - 1 positions or patterns in one batch", nullptr);
     API_GUARD_BEGIN
-    CUDA_CHECK(cudaSetDevice(idx->ix.device));
+    DeviceGuard guard(idx->ix.device);
     sort_positions(idx->ix, npat, d_pos_off, total, d_pos, (cudaStream_t)stream);
     return 0;
     API_GUARD_END(nullptr)
@@ -697,7 +959,7 @@ static int locate_batch_impl(const b200sa_index *idx, const uint32_t *L, const u
     if (!can_locate(idx)) return fail(B200SA_ERR_NOT_BUILT, "no suffix array to locate with (dropped and not sampled)", nullptr);
     API_GUARD_BEGIN
     const DeviceIndex &ix = idx->ix;
-    CUDA_CHECK(cudaSetDevice(ix.device));
+    DeviceGuard guard(ix.device);
     cudaStream_t st = ix.stream;
     DevBuf<u32> dL(npat ? npat : 1, st), dR(npat ? npat : 1, st);
     DevBuf<u64> doff(npat + 1, st);
@@ -738,6 +1000,7 @@ int b200sa_sample_sa(b200sa_index *idx, uint32_t rate, int drop_sa) {
     if (!ix.sa.ptr) return fail(B200SA_ERR_NOT_BUILT, "suffix array was dropped (B200SA_DROP_SA)", nullptr);
     if (ix.occ_layout == OCC_NONE) return fail(B200SA_ERR_NOT_BUILT, "the sampled suffix array needs the O table (B200SA_BUILD_OCC)", nullptr);
     API_GUARD_BEGIN
+    DeviceGuard guard(ix.device);
     use_device(ix.device);
     build_sampled_sa(ix, rate);
     if (drop_sa && !(idx->flags & B200SA_BUILD_TEXTCMP)) ix.sa.release();
@@ -755,7 +1018,7 @@ int b200sa_sa_lookup(const b200sa_index *idx, const uint32_t *rows, uint64_t cou
         if (rows[q] >= ix.len) return fail(B200SA_ERR_BAD_ARGUMENT, "row out of range", nullptr);
     if (!count) return 0;
     API_GUARD_BEGIN
-    CUDA_CHECK(cudaSetDevice(ix.device));
+    DeviceGuard guard(ix.device);
     cudaStream_t st = ix.stream;
     DevBuf<u32> dr(count, st), dout(count, st);
     CUDA_CHECK(cudaMemcpyAsync(dr.ptr, rows, count * 4, cudaMemcpyHostToDevice, st));
@@ -774,7 +1037,7 @@ int b200sa_save(const b200sa_index *idx, const char *path) {
     FILE *f = fopen(path, "wb");
     if (!f) return fail(B200SA_ERR_BAD_ARGUMENT, std::string("cannot open ") + path + " for writing", nullptr);
     try {
-        CUDA_CHECK(cudaSetDevice(ix.device));
+        DeviceGuard guard(ix.device);
         cudaStream_t st = ix.stream;
         const size_t words = ((size_t)ix.len + ix.pk.cpw - 1) / ix.pk.cpw + 4;
         std::vector<Section> secs;
@@ -846,6 +1109,7 @@ b200sa_index *b200sa_load(const char *path, int device, void *stream, enum b200s
         return nullptr;
     }
     try {
+        DeviceGuard guard(device);
         use_device(device);
         IndexFileHeader fh;
         if (fread(&fh, sizeof fh, 1, f) != 1 || memcmp(fh.magic, "B200SAIX", 8) != 0)
@@ -985,7 +1249,7 @@ b200sa_approx_result *b200sa_approx_batch(const b200sa_index *idx, const b200sa_
         return nullptr;
     }
     try {
-        CUDA_CHECK(cudaSetDevice(ix.device));
+        DeviceGuard guard(ix.device);
         cudaStream_t st = ix.stream;
         res->hit_off.assign(npat + 1, 0);
         res->cig_off.assign(1, 0);
@@ -1072,7 +1336,7 @@ void b200sa_approx_free(b200sa_approx_result *r) { delete r; }
 int b200sa_synth_codes(uint8_t *d_text, uint64_t n, uint32_t nsym, uint64_t seed, int device, void *stream) {
     if (!d_text || nsym < 1 || nsym > 255) return fail(B200SA_ERR_BAD_ARGUMENT, "bad argument", nullptr);
     API_GUARD_BEGIN
-    CUDA_CHECK(cudaSetDevice(device));
+    DeviceGuard guard(device);
     synth_codes(d_text, n, nsym, seed, (cudaStream_t)stream);
     return 0;
     API_GUARD_END(nullptr)
@@ -1082,7 +1346,7 @@ int b200sa_synth_reads(const uint8_t *d_text, uint64_t n, uint32_t nsym, uint8_t
                        uint32_t m, uint32_t miss_per_1024, uint64_t seed, int device, void *stream) {
     if (!d_text || !d_reads || nsym < 1 || nsym > 255) return fail(B200SA_ERR_BAD_ARGUMENT, "bad argument", nullptr);
     API_GUARD_BEGIN
-    CUDA_CHECK(cudaSetDevice(device));
+    DeviceGuard guard(device);
     synth_reads(d_text, n, nsym, d_reads, nreads, m, miss_per_1024, seed, (cudaStream_t)stream);
     return 0;
     API_GUARD_END(nullptr)

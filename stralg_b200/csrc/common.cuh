@@ -37,12 +37,16 @@ extern unsigned long long g_kernel_launches;
     } while (0)
 
 // exact-size cache of large device blocks (api.cu); get throws CudaFailure when the device is out of memory
+// the library's own stream-ordered memory pool of the current device (api.cu): freed blocks are kept
+// (release threshold "never"), and the process's default pool -- shared with every other
+// cudaMallocAsync user, e.g. torch's async allocator -- is left alone
+cudaMemPool_t library_pool();
 void *output_cache_get(size_t bytes);
 void output_cache_put(void *ptr, size_t bytes);
 void output_cache_purge(int device);
 
-// Stream-ordered device buffer.  The default mempool keeps freed blocks (release threshold is
-// raised to "never" in api.cu), so steady-state builds do not pay cudaMalloc.
+// Stream-ordered device buffer from the library's own pool, which keeps freed blocks (release
+// threshold "never", api.cu), so steady-state builds do not pay cudaMalloc.
 template <typename T>
 struct DevBuf {
     T *ptr = nullptr;
@@ -70,7 +74,7 @@ struct DevBuf {
         release();
         stream = s;
         count = n;
-        if (n) CUDA_CHECK(cudaMallocAsync((void **)&ptr, n * sizeof(T), s));
+        if (n) CUDA_CHECK(cudaMallocFromPoolAsync((void **)&ptr, n * sizeof(T), library_pool(), s));
     }
     // For the large tables an index OWNS (SA, BWT, O, ISA, LCP ...): blocks come from an exact-size
     // cache of plain device allocations (output_cache_get / _put, api.cu) instead of the
@@ -83,7 +87,7 @@ struct DevBuf {
         stream = s;
         count = n;
         if (n * sizeof(T) < ((size_t)1 << 20)) {  // small tables: the pool is fine
-            if (n) CUDA_CHECK(cudaMallocAsync((void **)&ptr, n * sizeof(T), s));
+            if (n) CUDA_CHECK(cudaMallocFromPoolAsync((void **)&ptr, n * sizeof(T), library_pool(), s));
         } else {
             ptr = (T *)output_cache_get(n * sizeof(T));
             cached = true;

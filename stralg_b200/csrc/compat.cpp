@@ -60,6 +60,18 @@ int device_id() {
     return e && *e ? atoi(e) : 0;
 }
 
+// STRALG_B200_TRACE=1: at exit, one line on stderr with the number of calls the drop-in served (how a
+// test that runs the reference's own binaries knows which library did the work)
+struct Trace {
+    unsigned long constructions = 0, tables = 0, exact_iters = 0, approx_iters = 0;
+    ~Trace() {
+        const char *e = getenv("STRALG_B200_TRACE");
+        if (e && *e && *e != '0')
+            fprintf(stderr, "stralg_b200: served constructions=%lu tables=%lu exact_iters=%lu approx_iters=%lu\n",
+                    constructions, tables, exact_iters, approx_iters);
+    }
+} g_trace;
+
 // One GPU constructor behind the four reference names.
 struct suffix_array *construct(uint8_t *string, uint32_t sigma, const char *who) {
     struct suffix_array *sa = (struct suffix_array *)malloc(sizeof *sa);
@@ -70,6 +82,7 @@ struct suffix_array *construct(uint8_t *string, uint32_t sigma, const char *who)
     sa->inverse = nullptr;
     sa->lcp = nullptr;
     enum b200sa_error err;
+    ++g_trace.constructions;
     b200sa_index *idx = b200sa_build(string, n, sigma, 0, device_id(), nullptr, &err);
     if (!idx) die(who);
     if (b200sa_copy_sa(idx, sa->array)) die(who);
@@ -327,6 +340,7 @@ void init_bwt_table(struct bwt_table *tbl, struct suffix_array *sa, struct suffi
     const uint32_t sigma = remap_table->alphabet_size;
     tbl->remap_table = remap_table;
     tbl->sa = sa;
+    ++g_trace.tables;
     b200sa_index *idx = index_of(sa, sigma, true);
     if (b200sa_extend(idx, sa->string, B200SA_BUILD_OCC)) die("init_bwt_table");
     tbl->c_table = (uint32_t *)calloc(sigma, sizeof(uint32_t));
@@ -412,6 +426,7 @@ void bwt_exact_match_batch(struct bwt_table *tbl, const uint8_t *patterns, const
 void init_bwt_exact_match_iter(struct bwt_exact_match_iter *iter, struct bwt_table *tbl,
                                const uint8_t *remapped_pattern) {
     iter->sa = tbl->sa;
+    ++g_trace.exact_iters;
     const uint64_t off[2] = {0, (uint64_t)strlen((const char *)remapped_pattern)};
     uint32_t L = 0, R = 0;
     bwt_exact_match_batch(tbl, remapped_pattern, off, 1, &L, &R);
@@ -475,6 +490,7 @@ void init_bwt_approx_iter(struct bwt_approx_iter *iter, struct bwt_table *tbl, c
                           int edits) {
     const uint64_t m = strlen((const char *)remapped_pattern);
     const uint64_t off[2] = {0, m};
+    ++g_trace.approx_iters;
     b200sa_approx_result *r = approx_batch(tbl, remapped_pattern, off, 1, edits < 0 ? 0 : edits, "init_bwt_approx_iter");
     const uint64_t k = edits < 0 ? 0 : b200sa_approx_hits(r);
     iter->bwt_table = tbl;

@@ -28,6 +28,7 @@ struct BuildStats {
     u32 bucket_bits;     // MSD: leading key bits that select a bucket
     u32 shallow_buckets; // MSD: oversize buckets emitted unsorted as groups of depth bucket_bits / bits
     u64 shallow_elems;   // suffixes in them
+    u64 lazy_lookups;    // ranks of retired suffixes recovered on demand by the doubling rounds
 };
 
 // Occurrence-table layouts
@@ -79,6 +80,10 @@ void occ_dense(const DeviceIndex &ix, u32 *d_out);  // (len+1)*sigma entries, re
 void build_ktable(DeviceIndex &ix);  // fills ix.ktable (DNA layout only)
 void fm_search(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fixed_len, u64 npat, u32 *d_L,
                u32 *d_R, cudaStream_t st, unsigned long long *d_stats = nullptr);
+// packed reads: 2 bits per base, four to a byte, first base in the high bits; read q at q * stride bytes
+void fm_search_packed(const DeviceIndex &ix, const u8 *d_packed, u32 m, u32 stride, u64 npat, u32 *d_L, u32 *d_R,
+                      cudaStream_t st, unsigned long long *d_stats = nullptr);
+void pack_reads(const u8 *d_codes, u32 m, u32 stride, u64 npat, u8 *d_out, int *d_err, cudaStream_t st);
 u64 fm_locate_count(const DeviceIndex &ix, const u32 *d_L, const u32 *d_R, u64 npat, u64 *d_pos_off,
                     cudaStream_t st);
 void fm_locate_fill(const DeviceIndex &ix, const u32 *d_L, const u32 *d_R, u64 npat, const u64 *d_pos_off,

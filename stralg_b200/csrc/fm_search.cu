@@ -336,6 +336,196 @@ __global__ void __launch_bounds__(256) fm_search_dna_kernel(OccView ov, CTable5 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed reads.  A read of m bases is m 2-bit symbols (code - 1), four to a
+// byte, the FIRST base in the two most significant bits of its byte (the order of the packed text,
+// sa_build.cu pack_kernel<2>, so that pattern and text fields compare with one XOR); read q starts
+// at byte q * stride.  A quarter of the bytes over PCIe and through the kernel, and the text
+// comparison of the unique-interval shortcut takes up to 32 symbols per step.  Same recurrence,
+// same (L, R) -- including the interval at the step that emptied it -- as fm_search_dna_kernel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 bswap64(u64 v) {
+    return ((u64)__byte_perm((u32)v, 0, 0x0123) << 32) | (u64)__byte_perm((u32)(v >> 32), 0, 0x0123);
+}
+
+// the `nbits` (2..64, even) bits of a big-endian bit stream that END just before bit `endbit`
+// (endbit >= nbits), right-aligned.  SWAP: the stream is stored as bytes (reads), else as u64 words (text)
+template <bool SWAP>
+__device__ __forceinline__ u64 bits_ending(const u64 *__restrict__ words, u64 endbit, u32 nbits, u64 &c_idx, u64 &c_word,
+                                           u32 &loads) {
+    const u64 last = endbit - 1;           // last bit wanted
+    const u64 wi = last >> 6;
+    if (wi != c_idx) {
+        c_idx = wi;
+        c_word = SWAP ? bswap64(words[wi]) : words[wi];
+        ++loads;
+    }
+    const u32 used = (u32)(last & 63u) + 1u;  // bits of word wi up to and including `last`
+    u64 v = c_word >> (64u - used);
+    if (used < nbits) {                        // the field starts in the previous word
+        const u64 prev = SWAP ? bswap64(words[wi - 1]) : words[wi - 1];
+        ++loads;
+        v |= prev << used;
+        // going on downwards, the previous word is the next current one
+        c_idx = wi - 1;
+        c_word = prev;
+    }
+    return nbits >= 64 ? v : (v & ((1ull << nbits) - 1ull));
+}
+
+template <bool SC, bool STATS>
+__global__ void __launch_bounds__(256) fm_search_dna_packed_kernel(OccView ov, CTable5 c5, TextCmp tc, KTable kt, u32 len,
+                                                                   const u64 *__restrict__ pw, u32 m, u32 stride,
+                                                                   u64 npat, u32 *__restrict__ outL,
+                                                                   u32 *__restrict__ outR,
+                                                                   unsigned long long *__restrict__ stats) {
+    const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npat) return;
+    u32 n_blk = 0, n_pw = 0, n_tw = 0, n_sa = 0;
+    const u64 bitbase = q * (u64)stride * 8ull;  // bit offset of base 0 of the read
+    u32 L = 0, R = len;
+    if (m > len) {
+        L = 1;
+        R = 0;
+    }
+    u64 p_idx = ~0ull, p_word = 0;
+    int64_t i = (int64_t)m - 1;
+    if (kt.tab && m >= (u32)kt.k && L < R) {
+        // the last k bases, the last one most significant (the order the recurrence consumes them)
+        const u64 w = bits_ending<true>(pw, bitbase + 2ull * m, 2u * (u32)kt.k, p_idx, p_word, n_pw);
+        u32 r = __brev((u32)w) >> (32 - 2 * kt.k);                // pairs reversed, bits inside a pair swapped
+        r = ((r & 0x55555555u) << 1) | ((r >> 1) & 0x55555555u);
+        const uint2 lr = kt.tab[r];
+        if (STATS) n_sa += 2;
+        L = lr.x;
+        R = lr.y;
+        i -= kt.k;
+    }
+    for (; i >= 0 && L < R && !(SC && R - L == 1); --i) {
+        const u32 a = (u32)bits_ending<true>(pw, bitbase + 2ull * (u64)i + 2ull, 2u, p_idx, p_word, n_pw) + 1u;
+        if (a >= ov.sigma) {
+            L = 1;
+            R = 0;
+            break;
+        }
+        const u32 bL = L >> 6, bR = R >> 6;
+        BlockRegs kL = load_dna_block<3>(ov.blocks, bL);
+        BlockRegs kR = kL;
+        if (bR != bL) kR = load_dna_block<3>(ov.blocks, bR);
+        if (STATS) n_blk += bR != bL ? 2u : 1u;
+        const u32 ca = c5.c[a];
+        L = ca + rank_in_block(kL, a, L, ov.primary);
+        R = ca + rank_in_block(kR, a, R, ov.primary);
+    }
+    if (SC && i >= 0 && R - L == 1) {
+        // one candidate suffix s = SA[L]: the remaining bases pattern[0..i] must equal text[s-1-i .. s-1]
+        const u32 s = tc.sa[L];
+        if (STATS) ++n_sa;
+        const u32 rem = (u32)i + 1u;
+        u32 k = 0;  // bases matched so far, from pattern[i] / text[s-1] downwards
+        u64 t_idx = ~0ull, t_word = 0;
+        bool mismatch = false;
+        while (k < rem) {
+            const u32 c = min(32u, min(rem - k, s - k));  // bases compared in this step
+            if (c == 0) {  // the text is used up: the next base meets the sentinel
+                mismatch = true;
+                break;
+            }
+            const u64 P = bits_ending<true>(pw, bitbase + 2ull * (u64)(i - k) + 2ull, 2u * c, p_idx, p_word, n_pw);
+            const u64 T = bits_ending<false>(tc.packed, 2ull * (u64)(s - k), 2u * c, t_idx, t_word, n_tw);
+            const u64 d = P ^ T;
+            if (d) {
+                k += (u32)((__ffsll((long long)d) - 1) >> 1);
+                mismatch = true;
+                break;
+            }
+            k += c;
+        }
+        if (!mismatch) {
+            L = tc.isa[s - rem];
+            R = L + 1;
+            if (STATS) ++n_sa;
+        } else {
+            const u32 a = (u32)bits_ending<true>(pw, bitbase + 2ull * (u64)(i - k) + 2ull, 2u, p_idx, p_word, n_pw) + 1u;
+            if (a >= ov.sigma) {
+                L = 1;
+                R = 0;
+            } else {
+                // the step that fails: BWT[Lk] != a, so both ranks coincide and the interval is empty
+                const u32 Lk = k ? tc.isa[s - k] : L;
+                BlockRegs kb = load_dna_block<3>(ov.blocks, Lk >> 6);
+                BlockRegs kb2 = kb;
+                if (((Lk + 1) >> 6) != (Lk >> 6)) kb2 = load_dna_block<3>(ov.blocks, (Lk + 1) >> 6);
+                if (STATS) {
+                    n_sa += k ? 1u : 0u;
+                    n_blk += 1u + ((((Lk + 1) >> 6) != (Lk >> 6)) ? 1u : 0u);
+                }
+                L = c5.c[a] + rank_in_block(kb, a, Lk, ov.primary);
+                R = c5.c[a] + rank_in_block(kb2, a, Lk + 1, ov.primary);
+            }
+        }
+    }
+    outL[q] = L;
+    outR[q] = R;
+    if (STATS) {
+        atomicAdd(&stats[0], (unsigned long long)n_blk);
+        atomicAdd(&stats[1], (unsigned long long)n_pw);
+        atomicAdd(&stats[2], (unsigned long long)n_tw);
+        atomicAdd(&stats[3], (unsigned long long)n_sa);
+    }
+}
+
+// codes 1..4 (one byte per base, read q at q * m) -> packed reads (read q at q * stride bytes)
+__global__ void __launch_bounds__(256) pack_reads_kernel(const u8 *__restrict__ codes, u32 m, u32 stride, u64 npat,
+                                                         u8 *__restrict__ out, int *__restrict__ err) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per output byte
+    if (t >= npat * (u64)stride) return;
+    const u64 q = t / stride;
+    const u32 j0 = (u32)(t % stride) * 4u;
+    u32 v = 0;
+#pragma unroll
+    for (u32 x = 0; x < 4; ++x) {
+        u32 sym = 0;
+        if (j0 + x < m) {
+            const u32 c = codes[q * (u64)m + j0 + x];
+            if (c - 1u > 3u) *err = 1;
+            sym = (c - 1u) & 3u;
+        }
+        v |= sym << (6u - 2u * x);
+    }
+    out[t] = (u8)v;
+}
+
+void pack_reads(const u8 *d_codes, u32 m, u32 stride, u64 npat, u8 *d_out, int *d_err, cudaStream_t st) {
+    if (!npat) return;
+    pack_reads_kernel<<<div_up_u(npat * (u64)stride, 256), 256, 0, st>>>(d_codes, m, stride, npat, d_out, d_err);
+    KERNEL_CHECK();
+}
+
+void fm_search_packed(const DeviceIndex &ix, const u8 *d_packed, u32 m, u32 stride, u64 npat, u32 *d_L, u32 *d_R,
+                      cudaStream_t st, unsigned long long *d_stats) {
+    if (!npat) return;
+    OccView ov = occ_view(ix);
+    CTable5 c5;
+    for (int i = 0; i < 8; ++i) c5.c[i] = ix.c_host[i];
+    const unsigned blocks = div_up_u(npat, 256);
+    static const bool no_sc = getenv("B200SA_SEARCH_NO_TEXTCMP") != nullptr;
+    static const bool no_kt = getenv("B200SA_SEARCH_NO_KTABLE") != nullptr;
+    TextCmp tc{ix.sa.ptr, ix.isa.ptr, ix.text_packed.ptr};
+    KTable kt{no_kt ? nullptr : ix.ktable.ptr, ix.ktable_k};
+    const bool sc = tc.sa && tc.isa && tc.packed && ix.pk.bits == 2 && !no_sc;
+    const u64 *pw = (const u64 *)d_packed;
+    if (d_stats) {
+        if (sc) fm_search_dna_packed_kernel<true, true><<<blocks, 256, 0, st>>>(ov, c5, tc, kt, ix.len, pw, m, stride, npat, d_L, d_R, d_stats);
+        else fm_search_dna_packed_kernel<false, true><<<blocks, 256, 0, st>>>(ov, c5, tc, kt, ix.len, pw, m, stride, npat, d_L, d_R, d_stats);
+    } else if (sc) {
+        fm_search_dna_packed_kernel<true, false><<<blocks, 256, 0, st>>>(ov, c5, tc, kt, ix.len, pw, m, stride, npat, d_L, d_R, nullptr);
+    } else {
+        fm_search_dna_packed_kernel<false, false><<<blocks, 256, 0, st>>>(ov, c5, tc, kt, ix.len, pw, m, stride, npat, d_L, d_R, nullptr);
+    }
+    KERNEL_CHECK();
+}
+
 void fm_search(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fixed_len, u64 npat, u32 *d_L,
                u32 *d_R, cudaStream_t st, unsigned long long *d_stats) {
     if (!npat) return;

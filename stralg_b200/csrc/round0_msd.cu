@@ -654,8 +654,10 @@ struct L3Args {
     int K, pb, R;
     u32 *sa;
     u8 *bwt;           // may be null
-    u32 *rank, *valid;
-    u32 *act, *act_count;
+    u32 *rank;         // rank[s] = first row of the group of s, written for suffixes whose key is shared
+                       // (everything else stays RANK_NONE: its rank is its row, recovered on demand)
+    u32 *grow;         // [len] by ROW: the same group head, for the rows of such suffixes
+    u32 *actbits;      // bit per row: the suffix in this row shares its key with another one ("active")
     u32 *primary;
     u32 *flagged, *nflagged;   // tiles the fast kernel declined (a crowded bin)
     u32 *big, *nbig;           // tiles that hold a bucket too large for one SM (msd_bigtile_kernel)
@@ -716,28 +718,28 @@ __device__ __forceinline__ bool is_short_suffix(u32 s, int K, u32 n) { return (u
 
 // emits one sorted position: SA, BWT row, and for members of a group of equal long keys the
 // group rank, the valid bit and a slot in the active list (warp-aggregated append)
-__device__ __forceinline__ void l3_emit(const L3Args &a, u32 g, u64 e, bool active, u32 group_head) {
+// emits one sorted position: SA, BWT row, and for members of a group of equal long keys the group
+// head (by suffix and by row) and the row's bit in the active bitmap.  `sbits` = the tile's slice of
+// that bitmap in shared memory, bit (g - gbase) (fast kernel); null: straight to global memory.
+__device__ __forceinline__ void l3_emit(const L3Args &a, u32 g, u64 e, bool active, u32 group_head, u32 *sbits = nullptr,
+                                        u32 gbase = 0) {
     const u32 s = (u32)e;
     a.sa[g] = s;
     if (a.bwt) a.bwt[g] = s ? (u8)(((u32)(e >> 32) & ((1u << a.pb) - 1u)) + 1u) : (u8)0;
     if (s == 0) *a.primary = g;
-    const unsigned am = __ballot_sync(__activemask(), active);
     if (active) {
         a.rank[s] = group_head;
-        atomicOr(&a.valid[s >> 5], 1u << (s & 31u));
-        const unsigned lane = threadIdx.x & 31u;
-        const int leader = __ffs(am) - 1;
-        u32 base = 0;
-        if ((int)lane == leader) base = atomicAdd(a.act_count, (u32)__popc(am));
-        base = __shfl_sync(am, base, leader);
-        a.act[base + (u32)__popc(am & ((1u << lane) - 1u))] = s;
+        a.grow[g] = group_head;
+        if (sbits) atomicOr(&sbits[(g - gbase) >> 5], 1u << ((g - gbase) & 31u));
+        else atomicOr(&a.actbits[g >> 5], 1u << (g & 31u));
     }
 }
 
 static constexpr int L3_CNTN = L3_CAP + 16;        // counters per tile (the blocked scan reads a little past bin M)
 static constexpr int L3_PAD = L3_CROWD;             // guard elements on both sides of X (the ordering window never exceeds it)
+static constexpr int L3_ABW = L3_MASKW + 2;         // words of the tile's slice of the active bitmap (any alignment)
 static constexpr size_t L3_SMEM = (size_t)(L3_CAP + 2 * L3_PAD) * 8 + (size_t)L3_CNTN * 4 + (size_t)L3_CNTN * 2 +
-                                  (size_t)(L3_MASKW + 1) * 4 * 2 + 64 * 4 + 8 * 4;
+                                  (size_t)(L3_MASKW + 1) * 4 * 2 + 64 * 4 + 8 * 4 + (size_t)L3_ABW * 4;
 
 // sum of the four bytes of x
 __device__ __forceinline__ u32 bytesum(u32 x) { return __dp4a(x, 0x01010101u, 0u); }
@@ -757,6 +759,7 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
     u32 *segpre = segmask + (L3_MASKW + 1);           // [MASKW + 1]
     u32 *misc = segpre + (L3_MASKW + 1);              // [64]
     u32 *nxt = misc + 64;                             // [8] next tile: index, b0, b1, E0, M
+    u32 *abits = nxt + 8;                             // [L3_ABW] active bits of the tile's rows, global word alignment
     uint2 *segtab = (uint2 *)Xhi;                     // aliases the element arrays until the elements are scattered
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const u32 remmask = a.R >= 32 ? ~0u : ((1u << a.R) - 1u);
@@ -791,9 +794,26 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
     // left guards: the smallest key, never "larger than" an element (pass 3)
     if (tid < (u32)L3_PAD) Xhi[-(int)tid - 1] = 0u;
     if (tid == 0) misc[32] = 0;  // largest slot seen in the tile
+    for (u32 i = tid; i < (u32)L3_ABW; i += L3_NT) abits[i] = 0;
+    u32 prevE0 = 0, prevM = 0;   // rows of the previous tile whose active bits still sit in `abits`
 
     while (true) {
         __syncthreads();  // `nxt` is published, the counters are zero, the previous tile has left X
+        if (prevM) {
+            // the previous tile's slice of the active bitmap: interior words are owned by the tile, the
+            // first and the last one may be shared with its neighbours
+            const u32 w0 = prevE0 >> 5, nw = ((prevE0 & 31u) + prevM + 31u) >> 5;
+            for (u32 i = tid; i < nw; i += L3_NT) {
+                const u32 v = abits[i];
+                abits[i] = 0;
+                if (i == 0 || i + 1 == nw) {
+                    if (v) atomicOr(&a.actbits[w0 + i], v);
+                } else {
+                    a.actbits[w0 + i] = v;
+                }
+            }
+            prevM = 0;
+        }
         const u32 t = nxt[0], b0 = nxt[1], b1 = nxt[2], E0 = nxt[3], M = nxt[4];
         if (t >= a.ntiles) break;
         const u64 *src = a.in + E0;
@@ -923,6 +943,8 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
             advance(t + gridDim.x);
         }
         if (crowded) continue;
+        prevE0 = E0;
+        prevM = M;
 
         // ---- pass 3, one thread per POSITION of the grouped tile.  Sub-bins are contiguous and
         // ordered by key, so the sorted position of the element at p is p minus the larger keys
@@ -1007,7 +1029,7 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
                 }
                 head = r - longs_before;
             }
-            l3_emit(a, E0 + r, e, active, E0 + head);
+            l3_emit(a, E0 + r, e, active, E0 + head, abits, E0 & ~31u);
         }
     }
 }
@@ -1238,23 +1260,22 @@ __global__ void msd_fix_shorts_kernel(L3Args a, OverArgs o) {
                 if (j != i && pos[j] == q) pos[j] = p;
             pos[i] = q;
         }
-        a.rank[sv[i]] = q;
-        a.valid[sv[i] >> 5] |= 1u << (sv[i] & 31u);
+        a.rank[sv[i]] = q;  // (materialised, not active: nothing looks for it inside the unsorted bucket)
         if (sv[i] == 0) *a.primary = q;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
+// rows whose active bit is clear hold suffixes that are final: their rank is their row
 __global__ void __launch_bounds__(256) fill_singleton_ranks_kernel(const u32 *__restrict__ sa, u32 len,
-                                                                   const u32 *__restrict__ valid, u32 *__restrict__ rank) {
+                                                                   const u32 *__restrict__ actbits, u32 *__restrict__ rank) {
     u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= len) return;
-    u32 s = sa[g];
-    if (!((valid[s >> 5] >> (s & 31u)) & 1u)) rank[s] = (u32)g;
+    if (!((actbits[g >> 5] >> (g & 31u)) & 1u)) rank[sa[g]] = (u32)g;
 }
 
-void fill_singleton_ranks(const DeviceIndex &ix, const u32 *valid, u32 *rank) {
-    fill_singleton_ranks_kernel<<<div_up_u(ix.len, 256), 256, 0, ix.stream>>>(ix.sa.ptr, ix.len, valid, rank);
+void fill_singleton_ranks(const DeviceIndex &ix, const u32 *actbits, u32 *rank) {
+    fill_singleton_ranks_kernel<<<div_up_u(ix.len, 256), 256, 0, ix.stream>>>(ix.sa.ptr, ix.len, actbits, rank);
     KERNEL_CHECK();
 }
 
@@ -1316,7 +1337,7 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         cursor[l] = ar.get<u32>(nb[l]);
         CUDA_CHECK(cudaMemsetAsync(cursor[l], 0, nb[l] * 4, st));
     };
-    // 0: max final bucket, 1: tiles of the current level, 3: actives, 4: declined tiles, 5: big tiles,
+    // 0: max final bucket, 1: tiles of the current level, 4: declined tiles, 5: big tiles,
     // 6: oversize buckets, 7: short suffixes met in them
     u32 *d_misc = ar.get<u32>(8);
     CUDA_CHECK(cudaMemsetAsync(d_misc, 0, 8 * 4, st));
@@ -1367,8 +1388,9 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     u32 *tile_first = ar.get<u32>((size_t)ntl3 + 2);
     u32 *flagged = ar.get<u32>((size_t)ntl3 + 1);
     u32 *bigtiles = ar.get<u32>((size_t)ntl3 + 1);
-    const size_t valid_words = ((size_t)len + 31) / 32 + 2;
-    CUDA_CHECK(cudaMemsetAsync(r.valid, 0, valid_words * 4, st));
+    // no row is active, no rank is materialised
+    CUDA_CHECK(cudaMemsetAsync(r.actbits, 0, (((size_t)len + 31) / 32 + 2) * 4, st));
+    CUDA_CHECK(cudaMemsetAsync(r.rank, 0xff, (size_t)len * 4, st));
 
     // ---- level 1: from the text ----
     level_tables(0);
@@ -1483,7 +1505,8 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     la.par_shift = pl.BB - pl.D[0];
     la.sa = ix.sa.ptr;
     la.bwt = (want_bwt && pl.pb) ? ix.bwt.ptr : nullptr;
-    la.rank = r.rank; la.valid = r.valid; la.act = r.act; la.act_count = d_misc + 3;
+    la.rank = r.rank; la.actbits = r.actbits;
+    la.grow = (u32 *)other;  // the ping-pong buffer the elements do NOT sit in is free
     la.primary = r.d_primary;
     la.flagged = flagged; la.nflagged = d_misc + 4;
     la.big = bigtiles; la.nbig = d_misc + 5;
@@ -1525,7 +1548,7 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     }
 
     r.bucket_start = start[last];
-    r.m = hmisc[3];
+    r.grow = la.grow;
     r.bwt_written = la.bwt != nullptr;
     return true;
 }

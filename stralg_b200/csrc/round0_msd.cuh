@@ -29,14 +29,13 @@ struct MsdPlan {
 struct Round0Msd {
     // workspace handed in by the caller
     u64 *bufA, *bufB;  // len elements each
-    u32 *act;          // len entries: receives the active suffixes
-    u32 *rank;         // len entries
-    u32 *valid;        // (len + 31) / 32 + 2 words, zeroed by round0_msd
+    u32 *rank;         // len entries: RANK_NONE, except for suffixes that share their key (group head)
+    u32 *actbits;      // (len + 31) / 32 + 2 words: bit per ROW whose suffix shares its key ("active")
     u32 *d_primary;    // 1 word
     // results
     MsdPlan plan;
     const u32 *bucket_start;  // 2^BB + 1 entries (workspace arena)
-    u32 m;                    // number of active suffixes written to act
+    const u32 *grow;          // [len] by row: group head of the active rows (lives in bufA or bufB)
     u32 depth0;               // symbols every active group is known to share: K, or BB / bits when oversize
                               // buckets were emitted unsorted as shallow groups
     u32 levels_added;         // partition levels added to the plan because of a skewed bucket histogram
@@ -53,7 +52,10 @@ bool msd_make_plan(u32 len, u32 sigma, int bits, MsdPlan &plan);
 // only when such buckets hold more than 1/8 of the text: the caller then runs the LSD path.
 bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r);
 
-// rank[sa[g]] = g for every suffix whose valid bit is clear (dense doubling rounds)
-void fill_singleton_ranks(const DeviceIndex &ix, const u32 *valid, u32 *rank);
+// not materialised: the rank of the suffix is its row in the round-0 order
+static constexpr u32 RANK_NONE = 0xffffffffu;
+
+// rank[sa[g]] = g for every row whose active bit is clear (dense doubling rounds)
+void fill_singleton_ranks(const DeviceIndex &ix, const u32 *actbits, u32 *rank);
 
 }  // namespace b200sa

@@ -248,15 +248,15 @@ __global__ void __launch_bounds__(256) make_keys0_kernel(const u64 *__restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-// Lazy ranks.  After round 0 only suffixes in non-singleton buckets ("active") get rank[] written
-// and their bit set in `valid`.  The rank of any other suffix t is its position in the round-0
+// Lazy ranks.  After round 0 only suffixes in non-singleton buckets ("active") get rank[] written;
+// every other entry holds RANK_NONE.  The rank of such a suffix t is its position in the round-0
 // order, recovered on demand by a binary search of its K-symbol key in the sorted key array.
 // Short suffixes (window reaches the sentinel) stand first inside an equal-key run, shortest
 // first, and are singletons; a long singleton stands right after them.
 // ---------------------------------------------------------------------------------------------
 struct LazyRank {
     const u32 *rank;
-    const u32 *valid;      // null: rank[] is complete (dense mode)
+    bool sparse;           // rank[t] == RANK_NONE: not materialised (false: rank[] is complete, dense mode)
     const u64 *keys0;      // round-0 sorted keys (LSD round 0); null after the bucketed round 0
     const u32 *bstart;     // bucketed round 0: start of every bucket (2^BB + 1 entries)
     int BB;                // bucketed round 0: leading key bits that select the bucket
@@ -268,7 +268,10 @@ struct LazyRank {
 };
 
 __device__ __forceinline__ u32 lazy_rank_of(const LazyRank &lr, u32 t) {
-    if (lr.valid == nullptr || ((lr.valid[t >> 5] >> (t & 31)) & 1u)) return lr.rank[t];
+    {
+        const u32 r = lr.rank[t];
+        if (!lr.sparse || r != RANK_NONE) return r;
+    }
     const int kb = lr.K * lr.bits;
     const u64 key = window_at(lr.packed, t, lr.bits) >> (64 - kb);
     u32 lo, hi;  // first index with key(index) >= key
@@ -360,10 +363,12 @@ __device__ __forceinline__ u32 scan_bucket_for(const u32 *__restrict__ sa0, u32 
     return pos;
 }
 
-__global__ void __launch_bounds__(256) make_keys_round_kernel(const u32 *__restrict__ act, u32 m, LazyRank lr, u64 h,
-                                                              int lo_bits, u64 *__restrict__ keys) {
+__global__ void __launch_bounds__(256) make_keys_round_kernel(const u32 *__restrict__ act, const u32 *__restrict__ grp,
+                                                              u32 m, LazyRank lr, u64 h, int lo_bits,
+                                                              u64 *__restrict__ keys, u32 *__restrict__ lazy_count) {
     const u64 stride = (u64)gridDim.x * blockDim.x;  // a multiple of 32: warps stay together
     const u32 lane = threadIdx.x & 31u, gbase = lane & ~7u, gmask = 0xffu << gbase;
+    u32 nlazy = 0;
     for (u64 base = (u64)blockIdx.x * blockDim.x + threadIdx.x - lane; base < m; base += stride) {
         const u64 j = base + lane;
         u32 s = 0, t32 = 0, blo = 0, bhi = 0, g = 0;
@@ -374,10 +379,12 @@ __global__ void __launch_bounds__(256) make_keys_round_kernel(const u32 *__restr
             const u64 t = (u64)s + h;
             if (t < lr.len) {
                 t32 = (u32)t;
-                if (lr.valid == nullptr || ((lr.valid[t32 >> 5] >> (t32 & 31u)) & 1u)) {
-                    lo = lr.rank[t32];
+                const u32 rt = lr.rank[t32];
+                if (!lr.sparse || rt != RANK_NONE) {
+                    lo = rt;
                 } else if (lr.keys0) {
                     lo = lazy_rank_of(lr, t32);
+                    ++nlazy;
                 } else {
                     const int kb = lr.K * lr.bits, rbits = kb - lr.BB;
                     const u64 key = window_at(lr.packed, t32, lr.bits) >> (64 - kb);
@@ -388,6 +395,7 @@ __global__ void __launch_bounds__(256) make_keys_round_kernel(const u32 *__restr
                     const u64 size = bhi - blo;
                     g = blo + (u32)(rbits <= 0 ? 0ull : rbits <= 32 ? (rem * size) >> rbits : ((rem >> (rbits - 32)) * size) >> 32);
                     need = true;
+                    ++nlazy;
                 }
             }
         }
@@ -407,8 +415,11 @@ __global__ void __launch_bounds__(256) make_keys_round_kernel(const u32 *__restr
                 __syncwarp();
             }
         }
-        if (j < m) keys[j] = ((u64)lr.rank[s] << lo_bits) | lo;
+        if (j < m) keys[j] = ((u64)grp[j] << lo_bits) | lo;
     }
+    // ranks that had to be recovered: the host moves to complete ranks when they become many
+    nlazy = __reduce_add_sync(0xffffffffu, nlazy);
+    if (lane == 0 && nlazy) atomicAdd(lazy_count, nlazy);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -477,7 +488,7 @@ struct RankArgs {
     int K0;          // round 0: symbols in the key; 0 in later rounds
     u32 n;
     u32 *rank;
-    u32 *valid;      // round 0, lazy mode: bitmap of suffixes whose rank[] is maintained
+    u32 *newgrp;     // [m] by sorted index: the new rank (= first row of the element's new group)
     int scatter_all; // round 0, dense mode: write every rank, touch nothing else
     u32 *sa_out;     // later rounds
     u8 *headbits;
@@ -641,16 +652,16 @@ __global__ void __launch_bounds__(RK_NT) rank_kernel(RankArgs a) {
             if (a.scatter_all) {
                 a.rank[s[q]] = newrank;
             } else {
-                if (active) {
-                    a.rank[s[q]] = newrank;
-                    atomicOr(&a.valid[s[q] >> 5], 1u << (s[q] & 31));
-                }
+                if (active) a.rank[s[q]] = newrank;
+                a.newgrp[j] = newrank;
                 bwt8 |= ((k[q] >> a.prev_shift) & 0xffull) << (8 * q);
                 if (s[q] == 0) *a.primary = (u32)j;
             }
         } else {
             u32 pos = (u32)(hi + (j - jb));
-            a.rank[s[q]] = newrank;
+            // every member holds the group head as its rank: the members that stay in front keep it
+            if (newrank != (u32)hi) a.rank[s[q]] = newrank;
+            a.newgrp[j] = newrank;
             a.sa_out[pos] = s[q];
             if (s[q] == 0) {
                 *a.primary = pos;
@@ -696,11 +707,20 @@ __device__ __forceinline__ u64 active_mask(const u8 *__restrict__ headbits, u64 
     return (~singleton) & valid;
 }
 
+// bits of a plain bitmap (bit per element, padded like headbits)
+__device__ __forceinline__ u64 raw_mask(const u8 *__restrict__ bits, u64 word, u32 m) {
+    const u64 base = word * 64;
+    if (base >= m) return 0;
+    const u64 valid = (m - base >= 64) ? ~0ull : ((1ull << (m - base)) - 1ull);
+    return ((const u64 *)bits)[word] & valid;
+}
+
+template <bool RAW>
 __global__ void __launch_bounds__(CP_NT) count_active_kernel(const u8 *__restrict__ headbits, u32 m,
                                                              u32 *__restrict__ tile_counts) {
     __shared__ u32 wsum[CP_NT / 32];
     u64 word = (u64)blockIdx.x * CP_NT + threadIdx.x;
-    u32 c = __popcll(active_mask(headbits, word, m));
+    u32 c = __popcll(RAW ? raw_mask(headbits, word, m) : active_mask(headbits, word, m));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (lane_id() == 0) wsum[threadIdx.x >> 5] = c;
@@ -741,13 +761,16 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(u32 *__restrict__ coun
     if (threadIdx.x == 0) *total = carry;
 }
 
+// RAW: `headbits` is the bitmap of the elements to keep (bit per element), not a head bitmap
+template <bool RAW>
 __global__ void __launch_bounds__(CP_NT) scatter_active_kernel(const u8 *__restrict__ headbits,
-                                                               const u32 *__restrict__ vals, u32 m,
+                                                               const u32 *__restrict__ vals,
+                                                               const u32 *__restrict__ grp_in, u32 m,
                                                                const u32 *__restrict__ tile_offsets,
-                                                               u32 *__restrict__ out) {
+                                                               u32 *__restrict__ out, u32 *__restrict__ grp_out) {
     __shared__ u32 wsum[CP_NT / 32];
     u64 word = (u64)blockIdx.x * CP_NT + threadIdx.x;
-    u64 mask = active_mask(headbits, word, m);
+    u64 mask = RAW ? raw_mask(headbits, word, m) : active_mask(headbits, word, m);
     u32 c = __popcll(mask);
     u32 incl = c;
 #pragma unroll
@@ -772,8 +795,16 @@ __global__ void __launch_bounds__(CP_NT) scatter_active_kernel(const u8 *__restr
         if (!mw) continue;
         const u64 bw = (word0 + (u64)w) * 64;
         const u32 lo = (u32)mw, hi = (u32)(mw >> 32);
-        if ((lo >> lane) & 1u) out[ow + (u32)__popc(lo & lt)] = vals[bw + lane];
-        if ((hi >> lane) & 1u) out[ow + (u32)__popc(lo) + (u32)__popc(hi & lt)] = vals[bw + 32 + lane];
+        if ((lo >> lane) & 1u) {
+            const u32 at = ow + (u32)__popc(lo & lt);
+            out[at] = vals[bw + lane];
+            grp_out[at] = grp_in[bw + lane];
+        }
+        if ((hi >> lane) & 1u) {
+            const u32 at = ow + (u32)__popc(lo) + (u32)__popc(hi & lt);
+            out[at] = vals[bw + 32 + lane];
+            grp_out[at] = grp_in[bw + 32 + lane];
+        }
     }
 }
 
@@ -838,10 +869,13 @@ static void launch_cmer_hist(const DeviceIndex &ix, u64 nwords_data, u32 *hist, 
     KERNEL_CHECK();
 }
 
-// headbits -> compacted list of still-active suffixes (in current SA order); returns the count
-static u32 count_active(const u8 *headbits, u32 m, u32 *tile_counts, unsigned long long *d_total, cudaStream_t st) {
+// bitmap -> compacted list of still-active suffixes (in current SA order) and their group heads;
+// returns the count.  RAW: the bitmap marks the elements to keep; else it marks bucket heads and an
+// element is kept unless it is a singleton.
+template <bool RAW>
+static u32 count_active(const u8 *bits, u32 m, u32 *tile_counts, unsigned long long *d_total, cudaStream_t st) {
     u32 ntiles = div_up_u(m, CP_TILE);
-    count_active_kernel<<<ntiles, CP_NT, 0, st>>>(headbits, m, tile_counts);
+    count_active_kernel<RAW><<<ntiles, CP_NT, 0, st>>>(bits, m, tile_counts);
     KERNEL_CHECK();
     scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_counts, ntiles, d_total);
     KERNEL_CHECK();
@@ -849,10 +883,37 @@ static u32 count_active(const u8 *headbits, u32 m, u32 *tile_counts, unsigned lo
     read_back(&total, d_total, 8, st);
     return (u32)total;
 }
-static void scatter_active(const u8 *headbits, const u32 *vals, u32 m, const u32 *tile_offsets, u32 *out,
-                           cudaStream_t st) {
-    scatter_active_kernel<<<div_up_u(m, CP_TILE), CP_NT, 0, st>>>(headbits, vals, m, tile_offsets, out);
+template <bool RAW>
+static void scatter_active(const u8 *bits, const u32 *vals, const u32 *grp_in, u32 m, const u32 *tile_offsets, u32 *out,
+                           u32 *grp_out, cudaStream_t st) {
+    scatter_active_kernel<RAW><<<div_up_u(m, CP_TILE), CP_NT, 0, st>>>(bits, vals, grp_in, m, tile_offsets, out, grp_out);
     KERNEL_CHECK();
+}
+
+// LSD round 0: rows that are not singletons, from the head bitmap (one thread per 64 rows)
+__global__ void __launch_bounds__(256) heads_to_actbits_kernel(const u8 *__restrict__ headbits, u32 m,
+                                                               u64 *__restrict__ actbits64, u64 nwords) {
+    const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < nwords) actbits64[w] = active_mask(headbits, w, m);
+}
+
+// BWT rows (stralg/bwt.c:13-20) of the rows that were active after round 0, from the final suffix
+// array: the doubling rounds over large active sets do not maintain them (one gather per moved row and
+// round); their rows are exactly the rows whose bit is set here.
+__global__ void __launch_bounds__(256) bwt_fix_kernel(const u32 *__restrict__ actbits, const u32 *__restrict__ sa, u32 len,
+                                                      const u64 *__restrict__ packed, int bits, u8 *__restrict__ bwt,
+                                                      u32 *__restrict__ primary) {
+    const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= len || !((actbits[r >> 5] >> (r & 31u)) & 1u)) return;
+    const u32 s = sa[r];
+    if (s == 0) {
+        bwt[r] = 0;
+        *primary = (u32)r;
+    } else {
+        const u64 bitpos = (u64)(s - 1) * bits;
+        const u64 w = packed[bitpos >> 6];
+        bwt[r] = (u8)(((w >> (64 - bits - (unsigned)(bitpos & 63))) & ((1u << bits) - 1u)) + 1u);
+    }
 }
 
 template <int RB>
@@ -884,36 +945,38 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
     u64 *keysA = ar.get<u64>((size_t)len + 2), *keysB = ar.get<u64>((size_t)len + 2);
     u32 *valsV = ar.get<u32>(len);
     u32 *rank = ar.get<u32>(len);
-    size_t valid_words = ((size_t)len + 31) / 32 + 2;
-    u32 *valid = ar.get<u32>(valid_words);
+    const size_t act_words64 = ((size_t)len + 63) / 64 + 2;
+    u32 *actbits = (u32 *)ar.get<u64>(act_words64);  // bit per row: active after round 0
     u64 *lookback = ar.get<u64>(S::lookback_words(len));
     u32 *hist = ar.get<u32>((size_t)8 * BINS), *uniform = ar.get<u32>(8), *ticket = ar.get<u32>(1);
     size_t hb_bytes = (((size_t)len + 63) / 64 + 2) * 8;
     u8 *headbits = ar.get<u8>(hb_bytes);
     u32 *tile_counts = ar.get<u32>(div_up_u(len, CP_TILE) + 1);
     unsigned long long *d_total = ar.get<unsigned long long>(1);
+    u32 *d_lazy = ar.get<u32>(1);
 
     u32 *sa = ix.sa.ptr;
     u32 m = 0;           // suffixes whose round-0 key is shared with another suffix
-    u32 *act = valsV;    // ... listed here
+    u32 *act = valsV;    // ... listed here, in suffix-array order, each with the first row of its group
+    u32 *grp = nullptr;
     int K = 0;
     bool bwt_in_sort = true;  // BWT rows ride along with the sort (else: gathered from the final SA)
     LazyRank lr{};
-    lr.rank = rank; lr.valid = valid; lr.sa0 = sa; lr.packed = ix.packed; lr.n = n; lr.len = len; lr.bits = b;
+    lr.rank = rank; lr.sparse = true; lr.sa0 = sa; lr.packed = ix.packed; lr.n = n; lr.len = len; lr.bits = b;
     int t;
 
     // ---- round 0, preferred: MSD bucket sort of 8-byte elements (round0_msd.cu) ----
     bool done0 = false;
     u32 depth0 = 0;  // symbols every active group shares after round 0 (0: K)
+    u64 *rk_free[2] = {nullptr, nullptr};  // large buffers that are dead after round 0 (round keys go there)
     {
         Round0Msd r0{};
         if (msd_make_plan(len, ix.sigma, b, r0.plan)) {
             Arena::Mark mk = ar.mark();
-            r0.bufA = keysA; r0.bufB = keysB; r0.act = valsV; r0.rank = rank; r0.valid = valid;
+            r0.bufA = keysA; r0.bufB = keysB; r0.rank = rank; r0.actbits = actbits;
             r0.d_primary = d_primary.ptr;
             done0 = round0_msd(ix, want_bwt, r0);
             if (done0) {
-                m = r0.m;
                 K = r0.plan.K;
                 bwt_in_sort = r0.bwt_written;
                 lr.keys0 = nullptr; lr.bstart = r0.bucket_start; lr.BB = r0.plan.BB; lr.K = K;
@@ -927,6 +990,16 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 ix.stats.shallow_buckets = r0.shallow_buckets;
                 ix.stats.shallow_elems = r0.shallow_buckets ? r0.shallow_elems : 0;
                 depth0 = r0.depth0;
+                // the active rows, in row order, with their group heads
+                t = ix.timer.begin("compact0", (double)len * 0.125);
+                m = count_active<true>((const u8 *)actbits, len, tile_counts, d_total, st);
+                if (m) {
+                    grp = ar.get<u32>(m);
+                    scatter_active<true>((const u8 *)actbits, sa, r0.grow, len, tile_counts, act, grp, st);
+                }
+                ix.timer.end(t);
+                rk_free[0] = keysA;
+                rk_free[1] = keysB;
             } else {
                 ar.release_to(mk);
             }
@@ -977,12 +1050,13 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
             std::swap(vin, vout);
         }
         const u64 *keys0 = kin;  // vin == ix.sa.ptr
+        u32 *newgrp0 = (u32 *)kout;  // (the other key buffer is free: new ranks by sorted index)
 
         t = ix.timer.begin("rank0", (double)len * 16.0);
         CUDA_CHECK(cudaMemsetAsync(headbits, 0, hb_bytes, st));
-        CUDA_CHECK(cudaMemsetAsync(valid, 0, valid_words * 4, st));
+        CUDA_CHECK(cudaMemsetAsync(rank, 0xff, (size_t)len * 4, st));  // nothing materialised yet
         ra.keys = keys0; ra.vals = sa; ra.m = len; ra.gs = 64; ra.keymask = keymask0; ra.K0 = K; ra.n = n;
-        ra.rank = rank; ra.valid = valid; ra.scatter_all = 0; ra.sa_out = nullptr; ra.headbits = headbits;
+        ra.rank = rank; ra.newgrp = newgrp0; ra.scatter_all = 0; ra.sa_out = nullptr; ra.headbits = headbits;
         ra.bwt = want_bwt ? ix.bwt.ptr : nullptr; ra.prev_shift = pshift; ra.packed = ix.packed; ra.bits = b;
         ra.primary = d_primary.ptr;
         rank_kernel<<<div_up_u(len, RK_TILE), RK_NT, 0, st>>>(ra);
@@ -990,48 +1064,50 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
         ix.timer.end(t);
 
         t = ix.timer.begin("compact0", (double)len * 0.125);
-        m = count_active(headbits, len, tile_counts, d_total, st);
-        if (m) scatter_active(headbits, sa, len, tile_counts, act, st);  // valsV is free once the sort is done
+        m = count_active<false>(headbits, len, tile_counts, d_total, st);
+        if (m) {
+            grp = ar.get<u32>(m);
+            scatter_active<false>(headbits, sa, newgrp0, len, tile_counts, act, grp, st);  // valsV is free once the sort is done
+            heads_to_actbits_kernel<<<div_up_u(act_words64 - 2, 256), 256, 0, st>>>(headbits, len, (u64 *)actbits, act_words64 - 2);
+            KERNEL_CHECK();
+        }
         ix.timer.end(t);
         lr.keys0 = keys0; lr.keymask = keymask0; lr.K = K;
+        rk_free[0] = kout;  // (keys0 stays: lazy ranks are looked up in it)
     }
 
     // ---- doubling rounds over the active set ----
     u8 *bwt_rows = (want_bwt && bwt_in_sort) ? ix.bwt.ptr : nullptr;
+    bool need_bwt_fix = false;
     if (m) {
-        const bool dense = (u64)m * 8 > (u64)len;
-        u32 *act2 = nullptr;
-        u64 *rkA, *rkB;
-        if (dense) {
-            // most suffixes are still active: materialise every rank, then the round-0 buffers are dead
-            t = ix.timer.begin("rank0_fill", (double)len * 16.0);
-            if (done0) {
-                fill_singleton_ranks(ix, valid, rank);
-            } else {
-                RankArgs rf = ra;
-                rf.scatter_all = 1;
-                rank_kernel<<<div_up_u(len, RK_TILE), RK_NT, 0, st>>>(rf);
-                KERNEL_CHECK();
-            }
-            ix.timer.end(t);
-            lr.valid = nullptr;
-            rkA = keysA;
-            rkB = keysB;
-        } else {
-            rkA = ar.get<u64>(m);
-            rkB = ar.get<u64>(m);
+        // complete ranks ("dense") from the start when most suffixes are active; otherwise ranks of
+        // retired suffixes are recovered on demand, until a round needs many of them
+        auto go_dense = [&]() {
+            int tt = ix.timer.begin("rank0_fill", (double)len * 16.0);
+            fill_singleton_ranks(ix, actbits, rank);
+            ix.timer.end(tt);
+            lr.sparse = false;
+        };
+        if ((u64)m * 2 > (u64)len) {
+            go_dense();
+            if (!done0) rk_free[1] = const_cast<u64 *>(lr.keys0);  // the sorted round-0 keys are dead now
         }
-        act2 = ar.get<u32>(m);
+        u64 *rkA = rk_free[0] ? rk_free[0] : ar.get<u64>(m);
+        u64 *rkB = rk_free[1] ? rk_free[1] : ar.get<u64>(m);
+        u32 *act2 = ar.get<u32>(m), *grp2 = ar.get<u32>(m);
+        u32 *newgrp = ar.get<u32>(m);
         const int lo_bits = std::max(1, log2len);
         const int key_bits = std::min(64, 2 * lo_bits);
         u64 h = depth0 ? (u64)depth0 : (u64)K;
         u32 huniform[8];
+        const u32 bwt_small = std::max(1u, len / (u32)std::max(1, env_int("B200SA_BWT_ROUND_FRAC", 32)));
         while (m > 0) {
             ix.stats.rounds++;
             ix.stats.sorted_total += m;
-            t = ix.timer.begin("round_keys", (double)m * 20.0);
+            t = ix.timer.begin("round_keys", (double)m * 16.0);
+            CUDA_CHECK(cudaMemsetAsync(d_lazy, 0, 4, st));
             make_keys_round_kernel<<<std::max(1u, std::min(div_up_u(m, 256 * 4), 148u * 16u)), 256, 0, st>>>(
-                act, m, lr, h, lo_bits, rkA);
+                act, grp, m, lr, h, lo_bits, rkA, d_lazy);
             KERNEL_CHECK();
             ix.timer.end(t);
             int npass = (key_bits + RB - 1) / RB;
@@ -1052,29 +1128,47 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 std::swap(rin, rout);
                 std::swap(ain, aout);
             }
-            t = ix.timer.begin("round_rank", (double)m * 24.0);
+            t = ix.timer.begin("round_rank", (double)m * 20.0);
             size_t hbm = (((size_t)m + 63) / 64 + 2) * 8;
             CUDA_CHECK(cudaMemsetAsync(headbits, 0, hbm, st));
             RankArgs rr{};
             rr.keys = rin; rr.vals = ain; rr.m = m; rr.gs = lo_bits; rr.keymask = ~0ull; rr.K0 = 0; rr.n = n;
-            rr.rank = rank; rr.valid = nullptr; rr.scatter_all = 0; rr.sa_out = sa; rr.headbits = headbits;
-            rr.bwt = bwt_rows; rr.prev_shift = 0; rr.packed = ix.packed; rr.bits = b;
+            rr.rank = rank; rr.newgrp = newgrp; rr.scatter_all = 0; rr.sa_out = sa; rr.headbits = headbits;
+            // BWT rows of moved suffixes: one gather per element and round -- kept in the rounds while the
+            // active set is small, otherwise one pass over the rows of round 0's active set at the end
+            rr.bwt = m <= bwt_small ? bwt_rows : nullptr;
+            if (bwt_rows && !rr.bwt) need_bwt_fix = true;
+            rr.prev_shift = 0; rr.packed = ix.packed; rr.bits = b;
             rr.primary = d_primary.ptr;
             rank_kernel<<<div_up_u(m, RK_TILE), RK_NT, 0, st>>>(rr);
             KERNEL_CHECK();
             ix.timer.end(t);
             // next active set goes to whichever value buffer does not hold the sorted list
             t = ix.timer.begin("compact", (double)m * 4.0);
-            u32 m2 = count_active(headbits, m, tile_counts, d_total, st);
-            if (m2) scatter_active(headbits, ain, m, tile_counts, aout, st);
+            u32 m2 = count_active<false>(headbits, m, tile_counts, d_total, st);
+            if (m2) scatter_active<false>(headbits, ain, newgrp, m, tile_counts, aout, grp2, st);
             ix.timer.end(t);
+            u32 nlazy = 0;
+            read_back(&nlazy, d_lazy, 4, st);
+            ix.stats.lazy_lookups += nlazy;
             act = aout;
             act2 = ain;
+            std::swap(grp, grp2);
             m = m2;
             h *= 2;
             if (h > (u64)len * 2 + 2 && m > 0)
                 throw std::runtime_error("prefix doubling failed to converge (internal error)");
+            // a lookup costs several random accesses, completing the ranks one random store per suffix
+            if (m > 0 && lr.sparse && (u64)nlazy * (u64)std::max(1, env_int("B200SA_DENSE_FACTOR", 12)) > (u64)len) {
+                go_dense();
+            }
         }
+    }
+    if (need_bwt_fix) {
+        t = ix.timer.begin("bwt_fix", (double)len * 0.125);
+        bwt_fix_kernel<<<div_up_u(len, 256), 256, 0, st>>>(actbits, sa, len, ix.packed, b, ix.bwt.ptr, d_primary.ptr);
+        KERNEL_CHECK();
+        ix.timer.end(t);
     }
     read_back(&ix.primary, d_primary.ptr, 4, st);
     if (want_bwt && !bwt_in_sort) gather_bwt(ix);  // the element had no room for the preceding symbol

@@ -200,6 +200,22 @@ class SuffixArrayIndex:
             C.c_void_p(d_offsets.data_ptr()) if d_offsets is not None else None, fixed_len, npat,
             C.c_void_p(d_L.data_ptr()), C.c_void_p(d_R.data_ptr()), C.c_void_p(stream)))
 
+    def search_packed(self, packed, read_len: int, npat: int, stride_bytes: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+        """Packed reads (2 bits per base, see ``pack_reads``) in host memory -> host (L, R)."""
+        pk = np.ascontiguousarray(packed, dtype=np.uint8)
+        L = np.empty(npat, dtype=np.uint32)
+        R = np.empty(npat, dtype=np.uint32)
+        check(_lib.load().b200sa_search_batch_packed(self._h, _np_ptr(pk), read_len, stride_bytes, npat, _np_ptr(L),
+                                                     _np_ptr(R)))
+        return L, R
+
+    def search_device_packed(self, d_packed, read_len: int, npat: int, d_L, d_R, stride_bytes: int = 0,
+                             stream: int = 0):
+        """Packed reads in device memory (torch CUDA tensor, 8-byte aligned); asynchronous on ``stream``."""
+        check(_lib.load().b200sa_search_device_packed(
+            self._h, C.c_void_p(d_packed.data_ptr()), read_len, stride_bytes, npat, C.c_void_p(d_L.data_ptr()),
+            C.c_void_p(d_R.data_ptr()), C.c_void_p(stream)))
+
     def search_one(self, pattern_codes) -> Tuple[int, int]:
         p = np.ascontiguousarray(pattern_codes, dtype=np.uint8)
         L, R = self.search(p, np.array([0, len(p)], dtype=np.uint64))
@@ -292,6 +308,18 @@ class SuffixArrayIndex:
         L, R = self.search_one(pattern_codes)
         _, pos = self.locate([L], [R])
         return pos
+
+
+def pack_reads(codes, read_len: int, stride_bytes: int = 0) -> np.ndarray:
+    """One-byte-per-base codes 1..4 (reads of ``read_len`` bases back to back) -> 2-bit packed reads:
+    four bases per byte, the first base in the two most significant bits; read q starts at byte
+    q * stride (default ceil(read_len / 4)).  Eight zero bytes of padding follow the last read."""
+    c = np.ascontiguousarray(codes, dtype=np.uint8)
+    npat = c.size // read_len
+    stride = stride_bytes or (read_len + 3) // 4
+    out = np.zeros(npat * stride + 8, dtype=np.uint8)
+    check(_lib.load().b200sa_pack_reads(_np_ptr(c), read_len, stride, npat, _np_ptr(out)))
+    return out
 
 
 # ---- reference-named constructors -----------------------------------------------------------------

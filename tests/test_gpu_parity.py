@@ -301,3 +301,97 @@ def test_host_batch_pipelined_pieces_equal_single_launch(engine, oracle):
     torch.cuda.synchronize()
     assert np.array_equal(Lv, Ld.cpu().numpy().view(np.uint32)) and np.array_equal(Rv, Rd.cpu().numpy().view(np.uint32))
     idx.close()
+
+
+@pytest.mark.parametrize("textcmp,ktable", [(False, False), (True, False), (False, True), (True, True)],
+                         ids=["plain", "textcmp", "ktable", "textcmp_ktable"])
+@pytest.mark.parametrize("n,m,stride", [(1 << 20, 100, 0), (1 << 20, 101, 32), (300000, 37, 0), (300000, 3, 0),
+                                        (50000, 1, 0), (200000, 250, 64), (3000, 64, 0), (1 << 20, 32, 8)])
+def test_packed_reads_equal_byte_reads(engine, oracle, n, m, stride, textcmp, ktable):
+    """b200sa_search_batch_packed / _device_packed (2 bits per base) return the (L, R)
+    of b200sa_search_batch on the same reads (bwt.c:164-199), hits, misses and near-misses alike; the
+    restatement pins the byte API in test_batched_search_and_locate."""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(n + m)
+    codes = oracle.random_codes(n, 4, seed=n + 1)
+    idx = engine.SuffixArrayIndex.build(codes[:-1], 5, textcmp=textcmp, ktable=ktable)
+    npat = 20000
+    starts = rng.integers(0, n - m + 1, npat)
+    reads = np.stack([codes[s:s + m] for s in starts]).astype(np.uint8)
+    reads[::5] = rng.integers(1, 5, (len(reads[::5]), m))            # random reads: misses
+    for q in range(1, npat, 3):                                      # near-misses: one base changed
+        j = int(rng.integers(0, m))
+        reads[q, j] = 1 + reads[q, j] % 4
+    reads[7] = codes[:m]                                             # the text's first bases (suffix 0)
+    reads[8] = codes[n - m:n]                                        # its last bases
+    flat = reads.reshape(-1)
+    L, R = idx.search(flat, fixed_len=m)
+    if m >= 20:
+        assert 0.2 < float((R > L).mean()) < 0.9
+    packed = engine.pack_reads(flat, m, stride)
+    Lp, Rp = idx.search_packed(packed, m, npat, stride)
+    assert np.array_equal(Lp, L) and np.array_equal(Rp, R), np.nonzero((Lp != L) | (Rp != R))[0][:10]
+    # device entry points: pack on the device, search there
+    lib = engine.load()
+    d_codes = torch.from_numpy(flat).cuda()
+    st = stride or (m + 3) // 4
+    d_packed = torch.zeros(npat * st + 8, dtype=torch.uint8, device="cuda")
+    assert lib.b200sa_pack_reads_device(C.c_void_p(d_codes.data_ptr()), m, st, npat, C.c_void_p(d_packed.data_ptr()),
+                                        0, None) == 0
+    assert np.array_equal(d_packed.cpu().numpy(), packed[: npat * st + 8])
+    dL = torch.empty(npat, dtype=torch.int32, device="cuda")
+    dR = torch.empty(npat, dtype=torch.int32, device="cuda")
+    idx.search_device_packed(d_packed, m, npat, dL, dR, st)
+    torch.cuda.synchronize()
+    assert np.array_equal(dL.cpu().numpy().view(np.uint32), L) and np.array_equal(dR.cpu().numpy().view(np.uint32), R)
+    counts = (C.c_uint64 * 4)()
+    assert lib.b200sa_search_traffic_packed(idx._h, C.c_void_p(d_packed.data_ptr()), m, st, npat,
+                                            C.c_void_p(dL.data_ptr()), C.c_void_p(dR.data_ptr()), counts, None) == 0
+    assert np.array_equal(dL.cpu().numpy().view(np.uint32), L) and counts[0] > 0 and counts[1] > 0
+    idx.close()
+
+
+def test_packed_reads_reject_bad_input(engine, oracle):
+    codes = oracle.random_codes(5000, 4, seed=3)
+    idx = engine.SuffixArrayIndex.build(codes[:-1], 5)
+    with pytest.raises(engine.B200saError) as e:
+        engine.pack_reads(np.array([1, 2, 5, 1], dtype=np.uint8), 4)
+    assert e.value.code == 3
+    with pytest.raises(engine.B200saError) as e:
+        idx.search_packed(np.zeros(16, np.uint8), 8, 1, stride_bytes=1)
+    assert e.value.code == 2
+    idx.close()
+    big = engine.SuffixArrayIndex.build(oracle.random_codes(5000, 20, seed=3)[:-1], 21)
+    with pytest.raises(engine.B200saError) as e:
+        big.search_packed(np.zeros(16, np.uint8), 8, 1)
+    assert e.value.code == 5
+    big.close()
+
+
+def test_one_pattern_mailbox_path(engine, oracle):
+    """A handful of short patterns take the mapped-memory path of b200sa_search_batch (one launch, no
+    cudaMemcpy): same intervals as a large batch of the same patterns."""
+    rng = np.random.default_rng(12)
+    n = 200000
+    codes = oracle.random_codes(n, 4, seed=77)
+    for textcmp, ktable in ((False, False), (True, True)):
+        idx = engine.SuffixArrayIndex.build(codes[:-1], 5, textcmp=textcmp, ktable=ktable)
+        pats, lens = [], rng.integers(1, 120, 300)
+        for k, m in enumerate(lens):
+            s = int(rng.integers(0, n - m))
+            p = codes[s:s + m].copy()
+            if k % 3 == 0:
+                p[int(rng.integers(0, m))] = 1 + int(rng.integers(0, 4))
+            pats.append(p)
+        off = np.zeros(len(pats) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(lens)
+        Lb, Rb = idx.search(np.concatenate(pats), off)
+        for k, p in enumerate(pats):
+            assert idx.search_one(p) == (int(Lb[k]), int(Rb[k])), k
+        # up to 64 patterns at once, offsets not starting at 0
+        L8, R8 = idx.search(np.concatenate(pats[:8]), off[:9])
+        assert np.array_equal(L8, Lb[:8]) and np.array_equal(R8, Rb[:8])
+        L9, R9 = idx.search(np.concatenate(pats), off[5:14])
+        assert np.array_equal(L9, Lb[5:13]) and np.array_equal(R9, Rb[5:13])
+        idx.close()
