@@ -76,8 +76,11 @@ struct b200sa_stats {
     uint32_t sa_resident;    /* 1 while the full suffix array is held in HBM */
     uint32_t shallow_buckets; /* bucket sort: buckets too large for one SM, handed to the doubling rounds unsorted
                                  as groups that share bucket_bits leading key bits (repeats, poly-A runs) */
-    uint32_t reserved0;
+    uint32_t chain_rounds;    /* doubling rounds that ordered groups by their chain offset (the distance to the
+                                 position where the copies of a repeat part) instead of the doubling offset */
     uint64_t shallow_elems;   /* suffixes in them (upper bound) */
+    uint64_t chain_elems;     /* suffixes in groups that "continued", summed over those rounds */
+    uint64_t lazy_lookups;    /* ranks of retired suffixes recovered on demand */
 };
 
 /* ---- construction ------------------------------------------------------------------------
@@ -157,6 +160,18 @@ int b200sa_pack_reads(const uint8_t *codes, uint32_t read_len, uint32_t stride_b
                       uint8_t *packed);
 int b200sa_pack_reads_device(const uint8_t *d_codes, uint32_t read_len, uint32_t stride_bytes,
                              uint64_t npat, uint8_t *d_packed, int device, void *stream);
+
+/* ---- multi-GPU search behind the C ABI (one process, several devices) ------------------
+ * The index is replicated, the reads are split into contiguous shards, one per replica, nothing is
+ * exchanged on the data path of the search; the (L, R) pairs of every shard are stored by the search
+ * kernel itself into the result array in the FIRST replica's HBM through NVLink peer memory (or, where
+ * peer access is unavailable, copied from each device), and return to the host from there.
+ * b200sa_replicate copies an index to another device (peer copies of the tables it holds) instead of
+ * rebuilding it there.  (L, R) are those of b200sa_search_batch_packed on one device. */
+b200sa_index *b200sa_replicate(const b200sa_index *src, int device, void *stream, enum b200sa_error *err);
+int b200sa_search_sharded_packed(const b200sa_index *const *replicas, int nreplicas, const uint8_t *packed,
+                                 uint32_t read_len, uint32_t stride_bytes, uint64_t npat, uint32_t *L,
+                                 uint32_t *R);
 
 /* Measurement aid: the same search (DNA index, 8-byte aligned device patterns), run by a counting
  * variant of the kernel.  counts[0] = 32-byte O-block loads, [1] = 8-byte pattern words,

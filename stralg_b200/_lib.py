@@ -39,7 +39,8 @@ class Stats(C.Structure):
         ("sorted_total", C.c_uint64), ("passes_elems", C.c_uint64), ("occ_bytes", C.c_uint64),
         ("round0_mode", C.c_uint32), ("bucket_bits", C.c_uint32),
         ("sa_sample_rate", C.c_uint32), ("sa_resident", C.c_uint32),
-        ("shallow_buckets", C.c_uint32), ("reserved0", C.c_uint32), ("shallow_elems", C.c_uint64),
+        ("shallow_buckets", C.c_uint32), ("chain_rounds", C.c_uint32), ("shallow_elems", C.c_uint64),
+        ("chain_elems", C.c_uint64), ("lazy_lookups", C.c_uint64),
     ]
 
 
@@ -82,6 +83,9 @@ SIGNATURES = {
                                               C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200sa_search_traffic_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64,
                                                C.c_void_p, C.c_void_p, u64p, C.c_void_p]),
+    "b200sa_replicate": (C.c_void_p, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "b200sa_search_sharded_packed": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_uint32, C.c_uint32,
+                                               C.c_uint64, C.c_void_p, C.c_void_p]),
     "b200sa_pack_reads": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]),
     "b200sa_pack_reads_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_int,
                                            C.c_void_p]),

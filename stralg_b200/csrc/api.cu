@@ -3,6 +3,7 @@
 #include "engine.h"
 
 #include <map>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string.h>
@@ -327,6 +328,14 @@ static void locate_fill_any(const DeviceIndex &ix, const u32 *d_L, const u32 *d_
     else fm_locate_fill_ssa(ix, d_L, npat, d_pos_off, total, d_pos, st);
 }
 
+template <typename T>
+static void replicate_buf(const DevBuf<T> &src, int src_dev, DevBuf<T> &dst, int dst_dev, cudaStream_t st, bool output) {
+    if (!src.ptr) return;
+    if (output) dst.alloc_output(src.count, st);
+    else dst.alloc(src.count, st);
+    CUDA_CHECK(cudaMemcpyPeerAsync(dst.ptr, dst_dev, src.ptr, src_dev, src.count * sizeof(T), st));
+}
+
 #pragma GCC visibility push(default)
 extern "C" {
 
@@ -531,8 +540,10 @@ int b200sa_stats(const b200sa_index *idx, struct b200sa_stats *out) {
     out->sa_sample_rate = ix.ssa_rate;
     out->sa_resident = ix.sa.ptr ? 1u : 0u;
     out->shallow_buckets = ix.stats.shallow_buckets;
-    out->reserved0 = 0;
+    out->chain_rounds = ix.stats.chain_rounds;
     out->shallow_elems = ix.stats.shallow_elems;
+    out->chain_elems = ix.stats.chain_elems;
+    out->lazy_lookups = ix.stats.lazy_lookups;
     return 0;
 }
 
@@ -920,6 +931,148 @@ int b200sa_search_batch_packed(const b200sa_index *idx, const uint8_t *packed, u
     }
     CUDA_CHECK(cudaStreamSynchronize(ln.s[0]));
     CUDA_CHECK(cudaStreamSynchronize(ln.s[1]));
+    return 0;
+    API_GUARD_END(nullptr)
+}
+
+// ---- several devices in one process ------------------------------------------------------------------
+b200sa_index *b200sa_replicate(const b200sa_index *src, int device, void *stream, enum b200sa_error *err) {
+    if (!src) {
+        fail(B200SA_ERR_BAD_ARGUMENT, "null argument", err);
+        return nullptr;
+    }
+    b200sa_index *h = new (std::nothrow) b200sa_index();
+    if (!h) {
+        fail(B200SA_ERR_OUT_OF_MEMORY, "host allocation failed", err);
+        return nullptr;
+    }
+    try {
+        {
+            DeviceGuard gs(src->ix.device);
+            CUDA_CHECK(cudaStreamSynchronize(src->ix.stream));  // the source tables are complete
+        }
+        DeviceGuard guard(device);
+        use_device(device);
+        const DeviceIndex &a = src->ix;
+        DeviceIndex &ix = h->ix;
+        cudaStream_t st = (cudaStream_t)stream;
+        ix.stream = st;
+        ix.device = device;
+        ix.n = a.n; ix.len = a.len; ix.sigma = a.sigma; ix.pk = a.pk;
+        ix.primary = a.primary;
+        ix.occ_layout = a.occ_layout; ix.occ_blocks = a.occ_blocks; ix.occ_block_bytes = a.occ_block_bytes;
+        ix.ktable_k = a.ktable_k; ix.ssa_rate = a.ssa_rate;
+        ix.stats = a.stats;
+        h->flags = src->flags;
+        memcpy(ix.c_host, a.c_host, sizeof ix.c_host);
+        memcpy(ix.sym_counts_host, a.sym_counts_host, sizeof ix.sym_counts_host);
+        const int sd = a.device;
+        replicate_buf(a.sa, sd, ix.sa, device, st, true);
+        replicate_buf(a.isa, sd, ix.isa, device, st, true);
+        replicate_buf(a.lcp, sd, ix.lcp, device, st, true);
+        replicate_buf(a.bwt, sd, ix.bwt, device, st, true);
+        replicate_buf(a.occ, sd, ix.occ, device, st, true);
+        replicate_buf(a.text_packed, sd, ix.text_packed, device, st, true);
+        replicate_buf(a.ktable, sd, ix.ktable, device, st, false);
+        replicate_buf(a.ssa_marks, sd, ix.ssa_marks, device, st, false);
+        replicate_buf(a.ssa_vals, sd, ix.ssa_vals, device, st, false);
+        replicate_buf(a.c_table, sd, ix.c_table, device, st, false);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        ok(err);
+        return h;
+    } catch (const CudaFailure &e) {
+        cudaGetLastError();
+        fail(code_of(e.code), e.what(), err);
+    } catch (const std::exception &e) {
+        fail(B200SA_ERR_INTERNAL, e.what(), err);
+    }
+    b200sa_free(h);
+    return nullptr;
+}
+
+int b200sa_search_sharded_packed(const b200sa_index *const *replicas, int nrep, const uint8_t *packed,
+                                 uint32_t read_len, uint32_t stride, uint64_t npat, uint32_t *L, uint32_t *R) {
+    if (!replicas || nrep < 1 || nrep > 64) return fail(B200SA_ERR_BAD_ARGUMENT, "bad replica list", nullptr);
+    for (int g = 0; g < nrep; ++g) {
+        if (!replicas[g]) return fail(B200SA_ERR_BAD_ARGUMENT, "null replica", nullptr);
+        if (replicas[g]->ix.len != replicas[0]->ix.len || replicas[g]->ix.primary != replicas[0]->ix.primary)
+            return fail(B200SA_ERR_BAD_ARGUMENT, "replicas are not copies of one index", nullptr);
+        for (int k = 0; k < g; ++k)
+            if (replicas[k]->ix.device == replicas[g]->ix.device)
+                return fail(B200SA_ERR_BAD_ARGUMENT, "two replicas on one device", nullptr);
+    }
+    if (int rc = packed_args_ok(replicas[0], read_len, stride)) return rc;
+    if (npat && (!packed || !L || !R)) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
+    if (!npat) return 0;
+    if (nrep == 1) return b200sa_search_batch_packed(replicas[0], packed, read_len, stride, npat, L, R);
+    API_GUARD_BEGIN
+    int prev = -1;
+    cudaGetDevice(&prev);
+    struct Restore {
+        int d;
+        ~Restore() { if (d >= 0) cudaSetDevice(d); }
+    } restore{prev};
+    const int dev0 = replicas[0]->ix.device;
+    // shards: contiguous, boundaries at multiples of 8 reads (every shard's first byte 8-byte aligned)
+    std::vector<uint64_t> lo(nrep + 1);
+    const uint64_t per = ((npat + nrep - 1) / nrep + 7) & ~(uint64_t)7;
+    for (int g = 0; g <= nrep; ++g) lo[g] = std::min(npat, per * (uint64_t)g);
+    // result array in the first replica's HBM
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (int g = 0; g < nrep; ++g) locks.emplace_back(search_lanes(replicas[g]->ix.device).mu);
+    CUDA_CHECK(cudaSetDevice(dev0));
+    SearchLanes &l0 = search_lanes(dev0);
+    l0.reserve((lo[1] - lo[0]) * stride + 16, npat);
+    std::vector<cudaEvent_t> done(nrep, nullptr);
+    std::vector<char> direct(nrep, 0);
+    for (int g = 0; g < nrep; ++g) {
+        const int dev = replicas[g]->ix.device;
+        CUDA_CHECK(cudaSetDevice(dev));
+        SearchLanes &ln = search_lanes(dev);
+        const uint64_t cnt = lo[g + 1] - lo[g];
+        if (g) ln.reserve(cnt * stride + 16, cnt);
+        else ln.reserve(cnt * stride + 16, npat);
+        u32 *outL = ln.L, *outR = ln.R;
+        if (g) {
+            int can = 0;
+            CUDA_CHECK(cudaDeviceCanAccessPeer(&can, dev, dev0));
+            if (can) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(dev0, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (e != cudaSuccess) can = 0, cudaGetLastError();
+            }
+            if (can) {  // the kernel stores this shard's (L, R) straight into the first replica's HBM
+                outL = l0.L + lo[g];
+                outR = l0.R + lo[g];
+                direct[g] = 1;
+            }
+        }
+        cudaStream_t ls = ln.s[0];
+        if (cnt) {
+            CUDA_CHECK(cudaMemcpyAsync(ln.patterns, packed + lo[g] * stride, cnt * stride, cudaMemcpyHostToDevice, ls));
+            fm_search_packed(replicas[g]->ix, ln.patterns, read_len, stride, cnt, outL, outR, ls);
+            if (g && !direct[g]) {
+                CUDA_CHECK(cudaMemcpyAsync(L + lo[g], outL, cnt * 4, cudaMemcpyDeviceToHost, ls));
+                CUDA_CHECK(cudaMemcpyAsync(R + lo[g], outR, cnt * 4, cudaMemcpyDeviceToHost, ls));
+            }
+        }
+        CUDA_CHECK(cudaEventCreateWithFlags(&done[g], cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventRecord(done[g], ls));
+    }
+    // the first replica's stream waits for every peer's kernel, then the result goes home in one piece per range
+    CUDA_CHECK(cudaSetDevice(dev0));
+    for (int g = 1; g < nrep; ++g) CUDA_CHECK(cudaStreamWaitEvent(l0.s[0], done[g], 0));
+    for (int g = 0; g < nrep; ++g) {
+        const uint64_t cnt = lo[g + 1] - lo[g];
+        if (!cnt || (g && !direct[g])) continue;
+        CUDA_CHECK(cudaMemcpyAsync(L + lo[g], l0.L + lo[g], cnt * 4, cudaMemcpyDeviceToHost, l0.s[0]));
+        CUDA_CHECK(cudaMemcpyAsync(R + lo[g], l0.R + lo[g], cnt * 4, cudaMemcpyDeviceToHost, l0.s[0]));
+    }
+    for (int g = 0; g < nrep; ++g) {
+        CUDA_CHECK(cudaSetDevice(replicas[g]->ix.device));
+        CUDA_CHECK(cudaStreamSynchronize(search_lanes(replicas[g]->ix.device).s[0]));
+        cudaEventDestroy(done[g]);
+    }
     return 0;
     API_GUARD_END(nullptr)
 }

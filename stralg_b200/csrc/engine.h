@@ -29,6 +29,8 @@ struct BuildStats {
     u32 shallow_buckets; // MSD: oversize buckets emitted unsorted as groups of depth bucket_bits / bits
     u64 shallow_elems;   // suffixes in them
     u64 lazy_lookups;    // ranks of retired suffixes recovered on demand by the doubling rounds
+    u32 chain_rounds;    // doubling rounds that used chain offsets (sa_build.cu: chain_flags_kernel)
+    u64 chain_elems;     // suffixes whose group "continued", summed over those rounds
 };
 
 // Occurrence-table layouts

@@ -1256,6 +1256,15 @@ __global__ void msd_fix_shorts_kernel(L3Args a, OverArgs o) {
                 a.bwt[p] = xb;
             }
             if (x == 0) *a.primary = p;
+            // the active bit and the group head are kept by ROW: they move with the suffix
+            const bool x_active = (a.actbits[q >> 5] >> (q & 31u)) & 1u;  // (x may be another short suffix)
+            if (x_active) {
+                a.actbits[p >> 5] |= 1u << (p & 31u);
+                a.grow[p] = a.grow[q];
+            } else {
+                a.actbits[p >> 5] &= ~(1u << (p & 31u));
+            }
+            a.actbits[q >> 5] &= ~(1u << (q & 31u));
             for (u32 j = 0; j < nf; ++j)
                 if (j != i && pos[j] == q) pos[j] = p;
             pos[i] = q;

@@ -365,6 +365,8 @@ __device__ __forceinline__ u32 scan_bucket_for(const u32 *__restrict__ sa0, u32 
 
 __global__ void __launch_bounds__(256) make_keys_round_kernel(const u32 *__restrict__ act, const u32 *__restrict__ grp,
                                                               u32 m, LazyRank lr, u64 h, int lo_bits,
+                                                              const u8 *__restrict__ cslot,
+                                                              const u32 *__restrict__ chainkey,
                                                               u64 *__restrict__ keys, u32 *__restrict__ lazy_count) {
     const u64 stride = (u64)gridDim.x * blockDim.x;  // a multiple of 32: warps stay together
     const u32 lane = threadIdx.x & 31u, gbase = lane & ~7u, gmask = 0xffu << gbase;
@@ -374,10 +376,18 @@ __global__ void __launch_bounds__(256) make_keys_round_kernel(const u32 *__restr
         u32 s = 0, t32 = 0, blo = 0, bhi = 0, g = 0;
         u64 lo = 0;
         bool need = false;
+        bool chained = false;
         if (j < m) {
             s = act[j];
+            if (cslot && cslot[j]) {  // the group continues: its chain offset, when it reaches at least h
+                const u32 ck = chainkey[s];
+                if (ck != RANK_NONE) {
+                    lo = ck;
+                    chained = true;
+                }
+            }
             const u64 t = (u64)s + h;
-            if (t < lr.len) {
+            if (!chained && t < lr.len) {
                 t32 = (u32)t;
                 const u32 rt = lr.rank[t32];
                 if (!lr.sparse || rt != RANK_NONE) {
@@ -420,6 +430,233 @@ __global__ void __launch_bounds__(256) make_keys_round_kernel(const u32 *__restr
     // ranks that had to be recovered: the host moves to complete ranks when they become many
     nlazy = __reduce_add_sync(0xffffffffu, nlazy);
     if (lane == 0 && nlazy) atomicAdd(lazy_count, nlazy);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chain offsets.  Plain doubling orders a group by the ranks h symbols ahead, h doubling per round:
+// two copies of a 6 000-symbol segment stay tied for eight rounds, all of their suffixes sorted again
+// in every one of them.  But whether a group G splits at all is visible one symbol ahead: if every
+// member's successor lies in ONE group G' ("G continues": all rank[s+1] equal), the members of G are
+// ordered exactly like their successors in G' -- and so on along the text, until a group does not
+// continue.  d(s) = 1 + d(s+1) while the group of s continues, 1 where it does not, is a property of
+// the group (by induction over the chain), the members of G share at least K - 1 + d symbols, and
+// ordering G by rank[s + d] is valid and reaches straight to the position where the copies part.
+// A group uses its chain offset only when d >= h (the round's doubling offset), so the doubling
+// invariant -- groups that stay tied share 2h symbols -- still holds and texts that chains do not
+// help (a^n: the one group never "continues", its last member's successor is a singleton) run as
+// before.  Three steps: chain_flags (suffix-array order: does the group continue?), chain_keys (text
+// order: distance to the end of the chain, rank there), and make_keys_round takes the chain key
+// where there is one.
+// ---------------------------------------------------------------------------------------------
+static constexpr int CF_NT = 256, CF_IPT = 8, CF_TILE = CF_NT * CF_IPT;
+static constexpr u32 CHAIN_CAP = 1u << 16;  // longest offset taken from a chain (longer chains: the cap itself)
+
+__global__ void __launch_bounds__(CF_NT) chain_flags_kernel(const u32 *__restrict__ act, const u32 *__restrict__ grp, u32 m,
+                                                            const u32 *__restrict__ rank, u8 *__restrict__ cslot,
+                                                            u8 *__restrict__ cont8, u32 *__restrict__ ncont) {
+    __shared__ u32 hq[CF_TILE];    // rank[s + 1] of the group head at this tile-local index
+    __shared__ u32 flag[CF_TILE];  // group (by head index): still "continues"
+    __shared__ u32 wmax[CF_NT / 32];
+    __shared__ u32 bcount;
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u64 tile_base = (u64)blockIdx.x * CF_TILE;
+    const u64 j0 = tile_base + (u64)tid * CF_IPT;
+    if (tid == 0) bcount = 0;
+    u32 s[CF_IPT], g[CF_IPT], q1[CF_IPT], hidx[CF_IPT];
+    u32 gprev = 0;
+    const bool has_prev = j0 > 0 && j0 < m;
+    if (has_prev) gprev = grp[j0 - 1];
+#pragma unroll
+    for (int q = 0; q < CF_IPT; ++q) {
+        const u64 j = j0 + q;
+        s[q] = j < m ? act[j] : 0u;
+        g[q] = j < m ? grp[j] : 0u;
+    }
+#pragma unroll
+    for (int q = 0; q < CF_IPT; ++q) q1[q] = j0 + q < m ? rank[s[q] + 1u] : RANK_NONE;
+    // tile-local index + 1 of the latest group head at or before each element (0: none in this thread yet)
+    u32 run = 0;
+    {
+        u32 pg = gprev;
+#pragma unroll
+        for (int q = 0; q < CF_IPT; ++q) {
+            const u64 j = j0 + q;
+            const bool head = j < m && (j == 0 || g[q] != pg);
+            if (head) run = (u32)(j - tile_base) + 1u;
+            hidx[q] = run;
+            pg = g[q];
+        }
+    }
+    // a thread's first element is a head iff its group differs from the previous element's; for the
+    // tile's very first element (no look at the previous tile needed: grp[j0 - 1] was read) as well
+    u32 ex = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, ex, o);
+        if (lane >= (u32)o) ex = max(ex, t);
+    }
+    if (lane == 31) wmax[warp] = ex;
+    u32 pre = __shfl_up_sync(0xffffffffu, ex, 1);
+    if (lane == 0) pre = 0;
+    __syncthreads();
+    for (u32 w = 0; w < warp; ++w) pre = max(pre, wmax[w]);
+#pragma unroll
+    for (int q = 0; q < CF_IPT; ++q)
+        if (hidx[q] == 0) hidx[q] = pre;  // 0: the group began in an earlier tile
+    // heads publish their successor's rank
+#pragma unroll
+    for (int q = 0; q < CF_IPT; ++q) {
+        const u64 j = j0 + q;
+        if (j < m && hidx[q] == (u32)(j - tile_base) + 1u) {
+            hq[hidx[q] - 1u] = q1[q];
+            flag[hidx[q] - 1u] = q1[q] != RANK_NONE ? 1u : 0u;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < CF_IPT; ++q) {
+        const u64 j = j0 + q;
+        if (j < m && hidx[q] && q1[q] != hq[hidx[q] - 1u]) flag[hidx[q] - 1u] = 0u;
+    }
+    // the tile's last group must end inside the tile
+    if (tid == CF_NT - 1 || j0 + CF_IPT >= m) {
+        const u64 last = min((u64)m, tile_base + CF_TILE) - 1;  // last element of the tile
+        if (last >= j0 && last < j0 + CF_IPT) {
+            const int q = (int)(last - j0);
+            if (last + 1 < m && grp[last + 1] == g[q] && hidx[q]) flag[hidx[q] - 1u] = 0u;
+        }
+    }
+    __syncthreads();
+    u32 mine = 0;
+#pragma unroll
+    for (int q = 0; q < CF_IPT; ++q) {
+        const u64 j = j0 + q;
+        if (j < m) {
+            const bool c = hidx[q] && flag[hidx[q] - 1u];
+            cslot[j] = c ? 1 : 0;
+            if (c) {
+                cont8[s[q]] = 1;
+                ++mine;
+            }
+        }
+    }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if (lane == 0 && mine) atomicAdd(&bcount, mine);
+    __syncthreads();
+    if (tid == 0 && bcount) atomicAdd(ncont, bcount);
+}
+
+// text order: for every position s whose group continues, e = the first position >= s whose group does
+// not, d = e - s + 1 (capped); chainkey[s] = rank of suffix s + d when d >= h, RANK_NONE otherwise
+static constexpr int CK_NT = 256, CK_BPT = 16, CK_TILE = CK_NT * CK_BPT;
+
+__global__ void __launch_bounds__(CK_NT) chain_keys_kernel(const u8 *__restrict__ cont8, u32 len, LazyRank lr, u64 h,
+                                                           u32 *__restrict__ chainkey, u32 *__restrict__ lazy_count) {
+    __shared__ u32 RK[CK_TILE];       // rank of suffix e + 1 for chain ends e inside the tile
+    __shared__ u32 wmin[CK_NT / 32];
+    __shared__ u32 beyond[2];         // first position >= end of tile whose group does not continue; its successor's rank
+    __shared__ u8 lastb[CK_NT];       // last byte of every thread's chunk
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u64 T0 = (u64)blockIdx.x * CK_TILE;
+    const u64 p0 = T0 + (u64)tid * CK_BPT;
+    // (cont8 is padded with zeros far beyond len: no bounds checks on the loads)
+    const uint4 v = *(const uint4 *)(cont8 + p0);
+    const u32 w[4] = {v.x, v.y, v.z, v.w};
+    u32 bits = 0;  // bit i: the group of position p0 + i continues
+#pragma unroll
+    for (int i = 0; i < CK_BPT; ++i) bits |= ((w[i >> 2] >> (8 * (i & 3))) & 1u) << i;
+    lastb[tid] = (u8)((bits >> (CK_BPT - 1)) & 1u);
+    const u32 any = __syncthreads_or((int)bits);
+    if (!any) return;  // nothing continues in this tile
+    // first position of the chunk (relative to T0) whose bit is clear, or none
+    const u32 zeros = ~bits & 0xffffu;
+    const u32 NONEPOS = 0xffffffffu;
+    u32 firstz = zeros ? tid * CK_BPT + (u32)(__ffs((int)zeros) - 1) : NONEPOS;
+    // suffix-min over the threads after this one
+    u32 sm = firstz;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_down_sync(0xffffffffu, sm, o);
+        if (lane + (u32)o < 32u) sm = min(sm, t);
+    }
+    if (lane == 0) wmin[warp] = sm;
+    u32 after = __shfl_down_sync(0xffffffffu, sm, 1);  // min over the later threads of this warp
+    if (lane == 31) after = NONEPOS;
+    __syncthreads();
+    for (u32 ww = warp + 1; ww < CK_NT / 32; ++ww) after = min(after, wmin[ww]);
+    // the chain that runs out of the tile: warp 0 looks for its end (at most CHAIN_CAP positions ahead)
+    if (warp == 0) {
+        u32 found = NONEPOS;
+        if (lastb[CK_NT - 1]) {
+            for (u32 it = 0; it < CHAIN_CAP / 256u + 1u && found == NONEPOS; ++it) {
+                const u64 at = T0 + CK_TILE + (u64)(it * 32u + lane) * 8u;
+                const u64 x = *(const u64 *)(cont8 + at);
+                const u64 z = ~x & 0x0101010101010101ull;
+                const u32 b = __ballot_sync(0xffffffffu, z != 0);
+                if (b) {
+                    const int l0 = __ffs((int)b) - 1;
+                    const u64 zz = __shfl_sync(0xffffffffu, z, l0);
+                    found = (u32)(CK_TILE + (it * 32u + (u32)l0) * 8u + (u32)((__ffsll((long long)zz) - 1) >> 3));
+                }
+            }
+        }
+        if (lane == 0) {
+            beyond[0] = found;  // relative to T0; NONEPOS: the chain is longer than the cap
+            u32 rk = RANK_NONE;
+            if (found != NONEPOS && T0 + found + 1 < lr.len) {
+                const u32 t = (u32)(T0 + found + 1);
+                if (lr.sparse && lr.rank[t] == RANK_NONE) atomicAdd(lazy_count, 1u);
+                rk = lazy_rank_of(lr, t);
+            }
+            beyond[1] = rk;
+        }
+    }
+    // chain ends inside the chunk: position e with a clear bit whose predecessor's bit is set
+    {
+        const u32 prevbit = tid ? (u32)lastb[tid - 1] : 0u;
+        u32 ends = zeros & ((bits << 1) | prevbit);
+        u32 nl = 0;
+        while (ends) {
+            const int i = __ffs((int)ends) - 1;
+            ends &= ends - 1;
+            const u64 e = p0 + (u64)i;
+            u32 rk = RANK_NONE;
+            if (e + 1 < lr.len) {
+                if (lr.sparse && lr.rank[e + 1] == RANK_NONE) ++nl;
+                rk = lazy_rank_of(lr, (u32)(e + 1));
+            }
+            RK[tid * CK_BPT + i] = rk;
+        }
+        if (nl) atomicAdd(lazy_count, nl);
+    }
+    __syncthreads();
+    if (!bits) return;
+    const u32 bz = beyond[0];
+    u32 nextz = after != NONEPOS ? after : bz;  // first clear position after this chunk (relative to T0)
+    // walk the chunk backwards
+    u32 out[CK_BPT];
+#pragma unroll
+    for (int i = CK_BPT - 1; i >= 0; --i) {
+        const u32 rel = tid * CK_BPT + (u32)i;
+        out[i] = RANK_NONE;
+        if ((bits >> i) & 1u) {
+            u32 d, key;
+            if (nextz == NONEPOS || nextz - rel + 1u > CHAIN_CAP) {
+                // capped: the target is itself inside the chain (an active suffix, its rank is materialised)
+                d = CHAIN_CAP;
+                key = lr.rank[T0 + rel + d];
+            } else {
+                d = nextz - rel + 1u;
+                key = nextz < (u32)CK_TILE ? RK[nextz] : beyond[1];
+            }
+            if ((u64)d >= h) out[i] = key;
+        } else {
+            nextz = rel;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < CK_BPT; ++i)
+        if ((bits >> i) & 1u) chainkey[p0 + i] = out[i];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1101,13 +1338,47 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
         u64 h = depth0 ? (u64)depth0 : (u64)K;
         u32 huniform[8];
         const u32 bwt_small = std::max(1u, len / (u32)std::max(1, env_int("B200SA_BWT_ROUND_FRAC", 32)));
+        // chain offsets (see chain_flags_kernel): tried while the active set is a noticeable part of the
+        // text, dropped for good once a round finds few groups that continue
+        bool chain_on = env_int("B200SA_CHAIN", 1) != 0;
+        u8 *cont8 = nullptr, *cslot = nullptr;
+        u32 *chainkey = nullptr, *d_ncont = nullptr;
+        const size_t cont_bytes = (size_t)len + 2 * (size_t)CHAIN_CAP + 8192;
         while (m > 0) {
             ix.stats.rounds++;
             ix.stats.sorted_total += m;
-            t = ix.timer.begin("round_keys", (double)m * 16.0);
             CUDA_CHECK(cudaMemsetAsync(d_lazy, 0, 4, st));
+            bool use_chain = false;
+            if (chain_on && h <= (u64)CHAIN_CAP && (u64)m * (u64)std::max(1, env_int("B200SA_CHAIN_MIN_FRAC", 64)) >= (u64)len) {
+                t = ix.timer.begin("chain_flags", (double)m * 13.0 + (double)len);
+                if (!cont8) {
+                    cont8 = ar.get<u8>(cont_bytes);
+                    chainkey = ar.get<u32>(len);
+                    cslot = ar.get<u8>(m);  // (m only shrinks)
+                    d_ncont = ar.get<u32>(1);
+                }
+                CUDA_CHECK(cudaMemsetAsync(cont8, 0, cont_bytes, st));
+                CUDA_CHECK(cudaMemsetAsync(d_ncont, 0, 4, st));
+                chain_flags_kernel<<<div_up_u(m, CF_TILE), CF_NT, 0, st>>>(act, grp, m, rank, cslot, cont8, d_ncont);
+                KERNEL_CHECK();
+                u32 ncont = 0;
+                read_back(&ncont, d_ncont, 4, st);
+                ix.timer.end(t);
+                if ((u64)ncont * 8 >= (u64)m) {
+                    t = ix.timer.begin("chain_keys", (double)len + (double)ncont * 4.0);
+                    chain_keys_kernel<<<div_up_u(len, CK_TILE), CK_NT, 0, st>>>(cont8, len, lr, h, chainkey, d_lazy);
+                    KERNEL_CHECK();
+                    ix.timer.end(t);
+                    use_chain = true;
+                    ix.stats.chain_rounds++;
+                    ix.stats.chain_elems += ncont;
+                } else {
+                    chain_on = false;
+                }
+            }
+            t = ix.timer.begin("round_keys", (double)m * 16.0);
             make_keys_round_kernel<<<std::max(1u, std::min(div_up_u(m, 256 * 4), 148u * 16u)), 256, 0, st>>>(
-                act, grp, m, lr, h, lo_bits, rkA, d_lazy);
+                act, grp, m, lr, h, lo_bits, use_chain ? cslot : nullptr, chainkey, rkA, d_lazy);
             KERNEL_CHECK();
             ix.timer.end(t);
             int npass = (key_bits + RB - 1) / RB;

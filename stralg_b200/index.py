@@ -111,6 +111,15 @@ class SuffixArrayIndex:
             raise B200saError(err.value, lib.b200sa_last_error().decode())
         return cls(h, device)
 
+    def replicate(self, device: int, stream: int = 0) -> "SuffixArrayIndex":
+        """A copy of this index on another device of the same process (peer copies, no rebuild)."""
+        lib = _lib.load()
+        err = C.c_int(0)
+        h = lib.b200sa_replicate(self._h, device, C.c_void_p(stream), C.byref(err))
+        if not h:
+            raise B200saError(err.value, lib.b200sa_last_error().decode())
+        return SuffixArrayIndex(h, device)
+
     def close(self):
         if self._h:
             _lib.load().b200sa_free(self._h)
@@ -320,6 +329,18 @@ def pack_reads(codes, read_len: int, stride_bytes: int = 0) -> np.ndarray:
     out = np.zeros(npat * stride + 8, dtype=np.uint8)
     check(_lib.load().b200sa_pack_reads(_np_ptr(c), read_len, stride, npat, _np_ptr(out)))
     return out
+
+
+def search_sharded_packed(replicas, packed, read_len: int, npat: int, stride_bytes: int = 0):
+    """b200sa_search_sharded_packed: one process, one replica of the index per device, the packed reads
+    split into contiguous shards; (L, R) of all reads in input order."""
+    pk = np.ascontiguousarray(packed, dtype=np.uint8)
+    L = np.empty(npat, dtype=np.uint32)
+    R = np.empty(npat, dtype=np.uint32)
+    arr = (C.c_void_p * len(replicas))(*[r._h for r in replicas])
+    check(_lib.load().b200sa_search_sharded_packed(arr, len(replicas), _np_ptr(pk), read_len, stride_bytes, npat,
+                                                   _np_ptr(L), _np_ptr(R)))
+    return L, R
 
 
 # ---- reference-named constructors -----------------------------------------------------------------

@@ -87,6 +87,10 @@ MODES = {
     "shallow_only": {"B200SA_MSD_MORE_FRAC": "1", "B200SA_MSD_OVER_FRAC": "1"},
     "more_levels": {"B200SA_MSD_MORE_FRAC": "100000000", "B200SA_MSD_OVER_FRAC": "1"},
     "avg64_shallow": {"B200SA_MSD_AVG": "64", "B200SA_MSD_MORE_FRAC": "1", "B200SA_MSD_OVER_FRAC": "1"},
+    # chain offsets (sa_build.cu chain_flags_kernel) on every round however small the active set / never
+    "chain_always": {"B200SA_CHAIN_MIN_FRAC": "100000000"},
+    "chain_always_shallow": {"B200SA_CHAIN_MIN_FRAC": "100000000", "B200SA_MSD_MORE_FRAC": "1", "B200SA_MSD_OVER_FRAC": "1"},
+    "chain_off": {"B200SA_CHAIN": "0"},
 }
 
 
@@ -99,7 +103,7 @@ def test_nonuniform_tables_match_oracle(engine, oracle, ref, name, mode, monkeyp
     codes = np.concatenate([np.asarray(sym, dtype=np.uint8), np.zeros(1, np.uint8)])
     idx = engine.SuffixArrayIndex.build(codes[:-1], sigma, isa=True, lcp=True, bwt=True, occ=True)
     st = idx.stats()
-    if mode != "default":
+    if "B200SA_MSD_OVER_FRAC" in MODES[mode]:
         # OVER_FRAC = 1: nothing may fall back to the LSD path
         assert st["round0_mode"] == 1, (name, mode, st)
     sa_exp = ref.sa(codes, sigma, "sa_is") if ref is not None else oracle.sa(codes)
@@ -149,6 +153,34 @@ def test_two_devices_one_process(engine):
     assert np.array_equal(a.sa(), b.sa())
     a.close()
     b.close()
+
+
+def test_sharded_search_behind_the_c_abi(engine, oracle):
+    """b200sa_replicate + b200sa_search_sharded_packed (one process, one replica per
+    device, contiguous read shards, (L, R) stored into the first replica's HBM by the search kernels):
+    equal to the single-device search.  With one visible device the single-replica path is checked."""
+    import torch
+    ndev = min(torch.cuda.device_count(), 4)
+    n, m, npat = 1 << 20, 100, 200003
+    codes = oracle.random_codes(n, 4, seed=5)
+    idx = engine.SuffixArrayIndex.build(codes[:-1], 5, textcmp=True, ktable=True)
+    rng = np.random.default_rng(9)
+    starts = rng.integers(0, n - m, npat)
+    reads = np.stack([codes[s:s + m] for s in starts]).astype(np.uint8)
+    reads[::7] = rng.integers(1, 5, (len(reads[::7]), m))
+    packed = engine.pack_reads(reads.reshape(-1), m)
+    L, R = idx.search_packed(packed, m, npat)
+    reps = [idx] + [idx.replicate(d) for d in range(1, ndev)]
+    for k in range(1, ndev):
+        assert np.array_equal(reps[k].sa_lookup(np.arange(0, n, 997, dtype=np.uint32)),
+                              idx.sa_lookup(np.arange(0, n, 997, dtype=np.uint32)))
+    for use in range(1, ndev + 1):
+        Ls, Rs = engine.search_sharded_packed(reps[:use], packed, m, npat)
+        assert np.array_equal(Ls, L) and np.array_equal(Rs, R), use
+    print(f"[sharded-c] {ndev} device(s): (L, R) of {npat} reads equal to the single-device search")
+    for r in reps[1:]:
+        r.close()
+    idx.close()
 
 
 # ---- large sizes: properties -----------------------------------------------------------------------

@@ -66,6 +66,9 @@ ROUND0_MODES = {
     "msd_avg64": {"B200SA_MSD_AVG": "64"},
     "lsd8": {"B200SA_ROUND0": "lsd", "B200SA_RADIX_BITS": "8"},
     "lsd10": {"B200SA_ROUND0": "lsd", "B200SA_RADIX_BITS": "10"},
+    # chain offsets in every doubling round, however small the active set (default: only large ones)
+    "msd_chain": {"B200SA_CHAIN_MIN_FRAC": "100000000"},
+    "lsd8_chain": {"B200SA_ROUND0": "lsd", "B200SA_RADIX_BITS": "8", "B200SA_CHAIN_MIN_FRAC": "100000000"},
 }
 
 
