@@ -7,12 +7,19 @@ N = 1  -> workload "build": SA + BWT + C + sampled O of a 3 Gbp synthetic DNA te
           configs[2]; the text is resident in HBM before the timed region).  value = Mchars/s.
           (`scaling_series` repeats the N = 1 point of the search series at the top level.)
           The same line carries `search` (FM exact search of 100-bp reads at 1 GPU),
-          `roofline` (dominant kernel = one radix pass of the initial sort), `e2e` (host buffers
-          through the C ABI, copies inside the timed region) and `cpu_baseline` (the unmodified
-          reference on the box's host cores, bounded sample).
+          `roofline` (dominant kernel of the build), `e2e` (host buffers through the C ABI, copies
+          inside the timed region), `cpu_baseline` (the unmodified reference on the box's host
+          cores, bounded sample), and the same build on NON-UNIFORM texts, each verified with the
+          suffix-array checker: `build_repeat_rich` (SURVEY 8(d) C3 repeat-rich), `build_hg38_like`
+          (the reference's genome sample tiled with mutations), `config5_stress` (BASELINE
+          configs[4]: five texts at 2^30), plus `compat` (numbers through libstralg_b200.so, the
+          reference's own function names).
 N > 1  -> workload "search" (BASELINE.json configs[3]): the index is replicated (every rank builds
-          it), 100 M reads are split over the ranks (strong scaling), (L, R) pairs are gathered
-          on rank 0 with NCCL inside the timed region.  value = patterns/s, whole job.
+          it), 100 M 2-bit packed reads are split over the ranks (strong scaling), (L, R) pairs
+          reach rank 0 inside the timed region.  value = patterns/s, whole job.
+Launched by torch.distributed.run with ONE rank (the N = 1 point of a scaling series) the line's
+headline is the search metric as well (build nested as `build`), so that efficiency v_N / (N v_1)
+is computable from the lines of one series.
 --impl reference times the reference's own CPU implementation (oracle/_ref, else the oracle
 port) on a bounded sample of the same workload; rank 0 only.
 
@@ -259,7 +266,8 @@ def host_synth(n, nsym, seed):
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    workload = args.workload if args.workload != "auto" else ("build" if args.gpus == 1 else "search")
+    under_torchrun = "TORCHELASTIC_RUN_ID" in os.environ or ("RANK" in os.environ and "LOCAL_RANK" in os.environ)
+    workload = args.workload if args.workload != "auto" else ("build" if (args.gpus == 1 and not under_torchrun) else "search")
     cores = os.cpu_count() or 1
     n = min(args.cpu_sample, args.n)
     codes, o = host_synth(n, 4, SEED)
@@ -308,6 +316,203 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+
+def numa_pin(local_rank):
+    """Run this process (and allocate its pinned staging) on the CPUs next to its GPU: VERDICT r1 found all
+    ranks of the 8-GPU run on NUMA node 0.  Best effort; returns what was done."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # 00000000:1B:00.0 -> 0000:1b:00.0
+            bus = bus[4:]
+        base = f"/sys/bus/pci/devices/{bus}"
+        node = open(base + "/numa_node").read().strip()
+        cpus = open(base + "/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return {"numa_node": node, "cpus": cpus}
+    except Exception as ex:
+        return {"error": str(ex)[:120]}
+
+
+def timed_build(stralg_b200, torch, src, sigma, local_rank, stream, reps=2, **kw):
+    """Best of `reps` device-timed builds of one text; returns (ms, stats, stage ms, index of the last build)."""
+    best, idx = None, None
+    for _ in range(reps):
+        if idx is not None:
+            idx.close()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        idx = stralg_b200.SuffixArrayIndex.build(src, sigma, profile=True, device=local_rank, stream=stream, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if best is None or ms < best[0]:
+            agg = {}
+            for name, sms, _ in idx.profile():
+                agg[name] = agg.get(name, 0.0) + sms
+            best = (ms, idx.stats(), agg)
+        if ms > 1000.0:
+            break
+    return best[0], best[1], best[2], idx
+
+
+def nonuniform_builds(args, lib, stralg_b200, torch, local_rank, stream, n):
+    """the same build on texts that are NOT uniform -- SURVEY 8(d)'s repeat-rich C3 variant,
+    a genome-like text (the reference's hg38 sample tiled with point mutations) and the five config-5 stress texts
+    at 2^30 (BASELINE configs[4]) -- each verified with the suffix-array checker of stralg_b200/texts.py
+    (permutation + adjacent order: pins the array uniquely), independent of the product kernels."""
+    from stralg_b200 import texts as T
+    out = {}
+
+    def one(label, make, nn, sigma_hint=None, occ=True, reps=2):
+        try:
+            text, sigma, info = make()
+            ms, st, stages, idx = timed_build(stralg_b200, torch, text[:nn], sigma, local_rank, stream, reps=reps, occ=occ)
+            lib.b200sa_release_workspace(local_rank)
+            sa = T.device_view(idx.device_ptr("sa"), nn + 1, 4, local_rank)
+            ok, why = T.check_suffix_array(text, sa, nn)
+            idx.close()
+            top = sorted(stages.items(), key=lambda kv: -kv[1])[:6]
+            rec = {"n": nn, "sigma": sigma, "ms_per_build": ms, "Mchars_per_s": nn / (ms / 1e3) / 1e6,
+                   "doubling_rounds": st["rounds"], "round0_mode": st["round0_mode"], "partition_levels": st["passes0"],
+                   "k0": st["k0"], "shallow_buckets": st["shallow_buckets"], "chain_rounds": st["chain_rounds"],
+                   "sorted_total_over_len": st["sorted_total"] / (nn + 1), "sa_verified": ok, "checker": why,
+                   "tables": "SA + BWT + C + sampled O" if occ else "SA",
+                   "top_stages_ms": {k: round(v, 2) for k, v in top}}
+            rec.update(info)
+            del text, sa
+            torch.cuda.empty_cache()
+            return rec
+        except Exception as ex:
+            torch.cuda.empty_cache()
+            return {"error": str(ex)[:300]}
+
+    def make_repeat():
+        t = T.random_codes(lib, n, 4, SEED, local_rank)
+        return t, 5, {"text": "random ACGT + copies of random 300-6000 bp segments (SURVEY 8d, C3 repeat-rich)",
+                      **T.add_repeats(t, n)}
+
+    def make_hg38():
+        return T.hg38_like(n, local_rank, mut_inv=64), 5, {
+            "text": "hg38-10000.fa sample (499 950 bp) tiled to n with 1/64 point mutations per copy"}
+
+    out["build_repeat_rich"] = one("repeat", make_repeat, n)
+    out["build_hg38_like"] = one("hg38", make_hg38, n, reps=1)
+    n5 = min(1 << 30, n)
+    stress = {}
+    names = {"byte": "C5a random bytes 1..255", "unary": "C5b a^n", "acgt4": "C5c (ACGT)^(n/4)",
+             "period1000": "C5d period-1000 random block", "fib": "C5e Fibonacci string"}
+    for kind in T.STRESS_KINDS:
+        def mk(kind=kind):
+            t, sigma = T.stress_text(lib, kind, n5, local_rank)
+            return t, sigma, {"text": names[kind]}
+        stress[kind] = one(kind, mk, n5, occ=False, reps=1)
+    out["config5_stress"] = stress
+    return out
+
+
+def compat_bench(args, n_text_avail):
+    """numbers THROUGH the drop-in library (libstralg_b200.so, the reference's own names):
+    build_complete_table (bwt.c:134-161) on 2^24 and 2^28 symbols including the copies into malloc'd host arrays,
+    and the protocol of performance/suffix_array_search.c:122-143 (n = 10^6, m = 100, one iterator per pattern,
+    patterns sampled from the text), next to the unmodified reference on one host core."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+    so = os.path.join(ROOT, "stralg_b200", "lib", "libstralg_b200.so")
+    shim = _oracle.bind_stralg_api(C.CDLL(so))
+    shim.bwt_exact_match_loop.restype = C.c_uint64
+    shim.bwt_exact_match_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64]
+    o = _oracle.Oracle()
+    ref = _oracle.Ref() if _oracle.Ref.available() else None
+    res = {"library": "stralg_b200/lib/libstralg_b200.so"}
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+    def ascii_text(n, seed):
+        codes, _ = host_synth(n, 4, seed)
+        t = letters[codes[:-1] - 1]
+        return np.concatenate([t, np.zeros(1, np.uint8)])
+
+    # ---- build_complete_table ----
+    for logn in (24, 28):
+        n = 1 << logn
+        if n > n_text_avail:
+            continue
+        txt = ascii_text(n, SEED + logn)
+        ts = []
+        for it in range(3 if logn == 24 else 2):
+            t0 = time.perf_counter()
+            tab = shim.build_complete_table(txt.ctypes.data_as(_oracle.u8p), False)
+            ts.append(time.perf_counter() - t0)
+            shim.completely_free_bwt_table(tab)
+        rec = {"n": n, "seconds": float(min(ts)), "Mchars_per_s": n / min(ts) / 1e6,
+               "includes": "remap + H2D + GPU build + D2H of SA (and of the dense O table where it is representable) "
+                           "into malloc'd host arrays"}
+        if ref is not None and logn == 24 and not args.no_cpu:
+            t0 = time.perf_counter()
+            tab = ref.lib.build_complete_table(txt.ctypes.data_as(_oracle.u8p), False)
+            rec["reference_seconds"] = time.perf_counter() - t0
+            rec["reference_Mchars_per_s"] = n / rec["reference_seconds"] / 1e6
+            ref.lib.completely_free_bwt_table(tab)
+        elif logn == 28:
+            rec["reference"] = "not runnable: the reference's dense O size overflows uint32 at this length (bwt.c:50)"
+        res[f"build_complete_table_2p{logn}"] = rec
+        del txt
+
+    # ---- one iterator per pattern ----
+    n, m = 1_000_000, 100
+    txt = ascii_text(n, SEED + 99)
+    rng = np.random.default_rng(3)
+    for npat in (200, 20000):
+        starts = rng.integers(0, n - m, npat)
+        tab = shim.build_complete_table(txt.ctypes.data_as(_oracle.u8p), False)
+        rt = tab.contents.remap_table.contents
+        codes = np.frombuffer(bytes(rt.table), dtype=np.int8)[txt[:-1]].astype(np.uint8)
+        pats = np.zeros((npat, m + 1), dtype=np.uint8)
+        for k, s0 in enumerate(starts):
+            pats[k, :m] = codes[s0:s0 + m]
+        ts = []
+        for it in range(4):
+            t0 = time.perf_counter()
+            hits = shim.bwt_exact_match_loop(tab, pats.ctypes.data_as(C.c_void_p), m, npat)
+            ts.append(time.perf_counter() - t0)
+        rec = {"n": n, "m": m, "patterns": npat, "matches": int(hits), "seconds": float(min(ts[1:])),
+               "patterns_per_s": npat / min(ts[1:]), "us_per_pattern": min(ts[1:]) / npat * 1e6,
+               "path": "init_bwt_exact_match_iter -> one-pattern b200sa_search_batch through mapped pinned memory "
+                       "(one kernel launch + one stream synchronisation per pattern); positions from the host copy of SA"}
+        shim.completely_free_bwt_table(tab)
+        if ref is not None and not args.no_cpu:
+            rtab = ref.lib.build_complete_table(txt.ctypes.data_as(_oracle.u8p), False)
+            o.lib.oracle_ref_iter_loop.restype = C.c_uint64
+            o.lib.oracle_ref_iter_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64]
+            fi = C.cast(ref.lib.init_bwt_exact_match_iter, C.c_void_p)
+            fn = C.cast(ref.lib.next_bwt_exact_match_iter, C.c_void_p)
+            tr = []
+            for it in range(4):
+                t0 = time.perf_counter()
+                rh = o.lib.oracle_ref_iter_loop(fi, fn, rtab, pats.ctypes.data_as(C.c_void_p), m, npat)
+                tr.append(time.perf_counter() - t0)
+            rec["reference_patterns_per_s"] = npat / min(tr[1:])
+            rec["reference_us_per_pattern"] = min(tr[1:]) / npat * 1e6
+            rec["reference_matches"] = int(rh)
+            rec["same_matches"] = int(rh) == int(hits)
+            ref.lib.completely_free_bwt_table(rtab)
+        res[f"iterator_per_pattern_{npat}"] = rec
+    res["note"] = ("a single dependent chain of ~100 random lookups per pattern is latency-bound: the CPU's cache "
+                   "beats a kernel launch per pattern; the batched entry points (bwt_exact_match_batch, "
+                   "b200sa_search_batch[_packed]) are the ones that use the GPU")
+    return res
+
+
 # =================================================================================================
 # GPU arm
 # =================================================================================================
@@ -325,7 +530,11 @@ def gpu_arm(args, rank, local_rank, world):
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
-    workload = args.workload if args.workload != "auto" else ("build" if world == 1 else "search")
+    # launched by torch.distributed.run (the driver's scaling series), one rank included: the line's headline is the
+    # SEARCH metric at every N, so that a scaling efficiency can be computed from the per-N values; the build
+    # (BASELINE configs[2]) is then nested as `build`.  Plain `python bench.py` (N = 1): the build is the headline.
+    under_torchrun = "TORCHELASTIC_RUN_ID" in os.environ or ("RANK" in os.environ and "LOCAL_RANK" in os.environ)
+    workload = args.workload if args.workload != "auto" else ("build" if (world == 1 and not under_torchrun) else "search")
     stream = torch.cuda.current_stream().cuda_stream
     peak, peak_src = measured_peak()
 
@@ -592,6 +801,15 @@ def gpu_arm(args, rank, local_rank, world):
             out["config1_small"] = c1
         except Exception as ex:
             out["config1_small"] = {"error": str(ex)[:200]}
+        torch.cuda.empty_cache()
+        if not args.no_nonuniform:
+            out.update(nonuniform_builds(args, lib, stralg_b200, torch, local_rank, stream, n))
+        if not args.no_compat:
+            try:
+                lib.b200sa_release_workspace(local_rank)
+                out["compat"] = compat_bench(args, n)
+            except Exception as ex:
+                out["compat"] = {"error": str(ex)[:300]}
         if not args.no_search:
             out["search"] = search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n, None, 0, 1,
                                          peak, peak_src, build)
@@ -602,9 +820,24 @@ def gpu_arm(args, rank, local_rank, world):
                                      "value": out["search"]["value"],
                                      "note": "compare with `value` of the --gpus 2/4/8 lines (same 10^8 reads, strong scaling)"}
     else:
+        nested_build = None
+        if world == 1:
+            for _ in range(2):
+                build().close()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for _ in range(3):
+                build().close()
+            b1.record()
+            torch.cuda.synchronize()
+            bms = b0.elapsed_time(b1) / 3
+            nested_build = {"metric": METRIC_BUILD, "value": n / (bms / 1e3) / 1e6, "unit": "Mchars/s", "ms_per_step": bms,
+                            "n": n, "note": "the full build line is what `python bench.py --gpus 1` prints"}
         res = search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n, dist, rank, world, peak,
                            peak_src, build)
         out = res
+        if nested_build:
+            out["build"] = nested_build
         out["scaling_series"] = {"metric": METRIC_SEARCH, "unit": "patterns/s", "n_gpus": world, "value": res["value"],
                                  "note": "the N = 1 point of this series is `scaling_series.value` of the --gpus 1 line"}
     if dist is not None:
@@ -617,16 +850,19 @@ def gpu_arm(args, rank, local_rank, world):
 
 def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n, dist, rank, world, peak, peak_src,
                  build):
-    """Replicated index, reads split over ranks, (L, R) gathered on rank 0 (NCCL) in the timed region."""
+    """Replicated index, reads split over ranks, (L, R) delivered on rank 0 in the timed region.  The reads are
+    2-bit packed (b200sa_search_device_packed / _batch_packed); the one-byte-per-base entry
+    points are measured beside them (`byte_api`)."""
     total_reads = args.reads
     m = READ_LEN
+    stride = (m + 3) // 4
+    chk = stralg_b200._lib.check
     # search index: C + sampled O, plus SA / ISA / packed text for the unique-interval shortcut
     idx = build(textcmp=True, ktable=True)
     lib.b200sa_release_workspace(local_rank)
-    # contiguous shards of the read set, one per rank; one NCCL gather of (L, R) to rank 0 per step
+    # contiguous shards of the read set, one per rank; (L, R) reach rank 0 inside the step
     from stralg_b200.shard import ShardedSearch
-    ss = ShardedSearch(total_reads, m, dev, dist, chunks=args.gather_chunks if dist is not None else 1,
-                       transport=args.transport)
+    ss = ShardedSearch(total_reads, stride, dev, dist, chunks=1, transport=args.transport)
     shard = ss.count
 
     def gen_reads(count, seed):
@@ -635,13 +871,20 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
                                       MISS_PER_1024, seed, local_rank, C.c_void_p(stream)) == 0
         return r
 
-    reads = gen_reads(shard, SEED + 1 + rank * 7919)
+    def pack(r, count):
+        p = torch.zeros(count * stride + 8, dtype=torch.uint8, device=dev)
+        chk(lib.b200sa_pack_reads_device(C.c_void_p(r.data_ptr()), m, stride, count, C.c_void_p(p.data_ptr()), local_rank,
+                                         C.c_void_p(stream)))
+        return p
 
-    def search_fn(r, mm, count, Lo, Ro):
-        idx.search_device(r, None, mm, count, Lo, Ro, stream)
+    reads = gen_reads(shard, SEED + 1 + rank * 7919)
+    preads = pack(reads, shard)
+
+    def search_fn(r, _stride, count, Lo, Ro):
+        idx.search_device_packed(r, m, count, Lo, Ro, stride, stream)
 
     def step():
-        ss.step(search_fn, reads)
+        ss.step(search_fn, preads)
 
     def barrier():
         if dist is not None:
@@ -672,8 +915,9 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
     launches = lib.b200sa_launch_count() - launches0
     value = total_reads / (ms_step / 1e3)
 
-    # N > 1: rank 0 re-creates every rank's reads (same seeded generator), searches them on its own index and
-    # compares with what the step delivered -- the whole sharded path checked bit for bit, outside the timed region
+    # N > 1: rank 0 re-creates every rank's reads (same seeded generator), searches them on its own index through
+    # the BYTE entry point and compares with what the step delivered -- the sharded packed path checked bit for
+    # bit against the other kernel, outside the timed region
     verified = None
     if dist is not None:
         if rank == 0:
@@ -691,77 +935,97 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
                 del rg, Lg, Rg
         dist.barrier()
 
-    # steps actually executed per read -> algorithmic bytes (m + 2*steps*32 + 8)
     Lt, Rt = ss.local_result()
     Lh = Lt.cpu().numpy().view(np.uint32)
     Rh = Rt.cpu().numpy().view(np.uint32)
     LR = torch.empty((2, max(shard, 1)), dtype=torch.int32, device=dev)
     hit_frac = float((Rh > Lh).mean())
-    # kernel-only timing of one rank's shard
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for _ in range(args.steps):
-        idx.search_device(reads, None, m, shard, LR[0], LR[1], stream)
-    k1.record()
-    torch.cuda.synchronize()
-    kernel_ms = k0.elapsed_time(k1) / args.steps
-    # algorithmic bytes of the launch = the memory operations the kernel issues for this batch, counted
-    # by the counting variant of the same kernel (b200sa_search_traffic): 32-byte O-block loads, 8-byte
-    # pattern and packed-text words, 4-byte SA / ISA loads, plus the 8-byte (L, R) result per read.
-    # SURVEY 8(d)'s per-read model (m + 2*steps*32 + 8 with steps = m for a hit) is reported beside it:
-    # the unique-interval shortcut replaces most O steps of a hit by a text comparison, so the kernel
-    # moves far fewer bytes than that model.
+
+    def time_kernel(fn):
+        fn()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(args.steps):
+            fn()
+        k1.record()
+        torch.cuda.synchronize()
+        return k0.elapsed_time(k1) / args.steps
+
+    # kernel-only timing of one rank's shard, both read formats; the byte kernel's (L, R) must equal the packed one's
+    kernel_ms = time_kernel(lambda: idx.search_device_packed(preads, m, shard, LR[0], LR[1], stride, stream))
+    byte_ms = time_kernel(lambda: idx.search_device(reads, None, m, shard, LR[0], LR[1], stream))
+    same_as_bytes = bool(torch.equal(LR[0][:shard], Lt)) and bool(torch.equal(LR[1][:shard], Rt))
+    # algorithmic bytes of the launch = the memory operations the kernel issues for this batch, counted by the
+    # counting variant of the same kernel: 32-byte O-block loads, 8-byte words of packed reads and packed text,
+    # 4-byte SA / ISA loads (8 per k-mer table entry), plus the 8-byte (L, R) result per read.
     counts = (C.c_uint64 * 4)()
-    stralg_b200._lib.check(lib.b200sa_search_traffic(idx._h, C.c_void_p(reads.data_ptr()), None, m, shard,
-                                                     C.c_void_p(LR[0].data_ptr()), C.c_void_p(LR[1].data_ptr()),
-                                                     counts, C.c_void_p(stream)))
+    chk(lib.b200sa_search_traffic_packed(idx._h, C.c_void_p(preads.data_ptr()), m, stride, shard,
+                                         C.c_void_p(LR[0].data_ptr()), C.c_void_p(LR[1].data_ptr()), counts,
+                                         C.c_void_p(stream)))
     issued_bytes = 32.0 * counts[0] + 8.0 * counts[1] + 8.0 * counts[2] + 4.0 * counts[3] + 8.0 * shard
     achieved = issued_bytes / (kernel_ms / 1e3) / 1e9
     miss_steps = 16.0
     survey_bytes_per_read = hit_frac * (m + 2 * m * 32 + 8) + (1 - hit_frac) * (m + 2 * miss_steps * 32 + 8)
     survey_gbps = survey_bytes_per_read * shard / (kernel_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "fm_search_dna_kernel (one lane per read, unique intervals finished by "
-                "text comparison)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": "fm_search_dna_packed_kernel (one lane per read, 2-bit packed reads, k-mer seed "
+                "table, unique intervals finished by a 32-symbols-per-step text comparison)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": search_traffic(shard),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": issued_bytes,
                 "avg_launch_ms": kernel_ms, "hit_fraction": hit_frac,
-                "ops_per_read": {"o_block_loads_32B": counts[0] / shard, "pattern_words_8B": counts[1] / shard,
-                                 "text_words_8B": counts[2] / shard, "sa_isa_loads_4B": counts[3] / shard},
+                "ops_per_read": {"o_block_loads_32B": counts[0] / shard, "read_words_8B": counts[1] / shard,
+                                 "text_words_8B": counts[2] / shard, "sa_isa_ktable_loads_4B": counts[3] / shard},
                 "survey_model": {"bytes_per_read": survey_bytes_per_read, "GBps": survey_gbps,
                                  "frac": survey_gbps / peak,
                                  "note": "SURVEY 8(d) bytes of the plain recurrence (every step two 32-byte O "
                                          "fetches); random accesses, bounded by sector rate rather than bytes"}}
 
-    # e2e: host reads in, host (L, R) out through b200sa_search_batch
-    e2e = None
+    # e2e: host reads in, host (L, R) out through the C ABI, pinned host buffers allocated next to the GPU
+    numa = numa_pin(local_rank)
+    e2e, e2e_bytes = None, None
     try:
         e_reads = min(shard, args.e2e_reads)
-        h_reads = torch.empty(e_reads * m, dtype=torch.uint8, pin_memory=True)
-        h_reads.copy_(reads[: e_reads * m])
+        hp = torch.empty(e_reads * stride + 8, dtype=torch.uint8, pin_memory=True)
+        hp.copy_(preads[: e_reads * stride + 8])
         hL = torch.empty(e_reads, dtype=torch.int32, pin_memory=True)
         hR = torch.empty(e_reads, dtype=torch.int32, pin_memory=True)
         torch.cuda.synchronize()
-        ts = []
-        for it in range(3):
+
+        def timed_calls(fn):
+            ts = []
+            for it in range(4):
+                if dist is not None:
+                    dist.barrier()
+                t0 = time.perf_counter()
+                fn()
+                dt = time.perf_counter() - t0
+                if it > 0:
+                    ts.append(dt)
+            dt = float(np.mean(ts))
             if dist is not None:
-                dist.barrier()
-            t0 = time.perf_counter()
-            stralg_b200._lib.check(lib.b200sa_search_batch(idx._h, C.c_void_p(h_reads.data_ptr()), None, m, e_reads,
-                                                           C.c_void_p(hL.data_ptr()), C.c_void_p(hR.data_ptr())))
-            dt = time.perf_counter() - t0
-            if it > 0:
-                ts.append(dt)
-        dt = float(np.mean(ts))
-        if dist is not None:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": e_reads * world / dt, "unit": "patterns/s", "h2d_bytes_per_step": int(e_reads * m),
-               "d2h_bytes_per_step": int(e_reads * 8), "reads_per_rank": e_reads,
-               "api": "b200sa_search_batch (pinned host reads in, host (L, R) out), all ranks concurrently"}
-        del h_reads
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return dt
+
+        dt = timed_calls(lambda: chk(lib.b200sa_search_batch_packed(idx._h, C.c_void_p(hp.data_ptr()), m, stride, e_reads,
+                                                                    C.c_void_p(hL.data_ptr()), C.c_void_p(hR.data_ptr()))))
+        e2e_ok = bool(np.array_equal(hL.numpy().view(np.uint32), Lh[:e_reads]))
+        e2e = {"value": e_reads * world / dt, "unit": "patterns/s", "h2d_bytes_per_step": int(e_reads * stride),
+               "d2h_bytes_per_step": int(e_reads * 8), "reads_per_rank": e_reads, "equals_device_result": e2e_ok,
+               "numa": numa,
+               "api": "b200sa_search_batch_packed (pinned host packed reads in, host (L, R) out), all ranks concurrently"}
+        del hp
+        hb = torch.empty(e_reads * m, dtype=torch.uint8, pin_memory=True)
+        hb.copy_(reads[: e_reads * m])
+        torch.cuda.synchronize()
+        dtb = timed_calls(lambda: chk(lib.b200sa_search_batch(idx._h, C.c_void_p(hb.data_ptr()), None, m, e_reads,
+                                                              C.c_void_p(hL.data_ptr()), C.c_void_p(hR.data_ptr()))))
+        e2e_bytes = {"value": e_reads * world / dtb, "unit": "patterns/s", "h2d_bytes_per_step": int(e_reads * m),
+                     "d2h_bytes_per_step": int(e_reads * 8),
+                     "api": "b200sa_search_batch (one byte per base)"}
+        del hb
     except Exception as ex:
-        e2e = {"value": None, "unit": "patterns/s", "error": str(ex)[:200]}
+        e2e = e2e or {"value": None, "unit": "patterns/s", "error": str(ex)[:200]}
 
     res = {
         "metric": METRIC_SEARCH, "value": value, "unit": "patterns/s", "n_gpus": world, "steps": args.steps,
@@ -770,12 +1034,15 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
         "config": {"workload": "search: batched FM exact search, replicated 3 Gbp index (BASELINE configs[3])"
                    if n == N_FULL else "search: batched FM exact search, replicated index",
                    "n": n, "sigma": 5, "reads": total_reads, "read_len": m, "reads_per_gpu": shard,
+                   "read_format": "2 bits per base, 25 bytes per 100-bp read",
                    "miss_fraction": MISS_PER_1024 / 1024.0, "gather": ("search kernels store (L,R) into rank 0's HBM through NVLink peer memory (symmetric memory) + one "
                               "device-side barrier" if ss.transport == "p2p" else
                               f"NCCL gather of (L,R) to rank 0, {ss.chunks} piece(s) per shard") if world > 1
-                   else "none (1 GPU)", "l2": "index (1.5 GB) and reads larger than L2"},
+                   else "none (1 GPU)", "l2": "index (1.5 GB O + 8.6 GB k-mer table) and reads larger than L2"},
         "clocks": sampler.summary(tw0, tw1), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "kernel_only_patterns_per_s_per_gpu": shard / (kernel_ms / 1e3),
+        "byte_api": {"kernel_only_patterns_per_s_per_gpu": shard / (byte_ms / 1e3), "kernel_ms": byte_ms,
+                     "same_intervals_as_packed": same_as_bytes, "e2e": e2e_bytes},
         "delivered_equals_single_gpu_search": verified,
     }
     if world == 1 and not args.no_extras:
@@ -861,10 +1128,15 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
                                  hr.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint64(npat), C.c_uint32(m),
                                  C.c_uint32(MISS_PER_1024), C.c_uint64(SEED + 1))
         cores = os.cpu_count() or 1
+        what = (f"{{}} reads x {m} bp against the first {ns} symbols (the reference's dense O cannot be built beyond "
+                f"~214 M rows, bwt.c:50)")
         dt, kind, _, _ = cpu_reference_search(sample, 5, hr, m, cores)
         res["cpu_baseline"] = {"value": npat / dt, "unit": "patterns/s", "cores": cores, "kind": kind,
-                               "sample": f"{npat} reads x {m} bp against the first {ns} symbols (the reference's "
-                                         f"dense O cannot be built beyond ~214 M rows, bwt.c:50)"}
+                               "sample": what.format(npat)}
+        n1 = max(1, npat // 8)  # one core AND all cores
+        dt1, kind1, _, _ = cpu_reference_search(sample, 5, hr[: n1 * m], m, 1)
+        res["cpu_baseline_1core"] = {"value": n1 / dt1, "unit": "patterns/s", "cores": 1, "kind": kind1,
+                                     "sample": what.format(n1)}
     idx.close()
     return res
 
@@ -888,6 +1160,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-search", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the locate / approximate-search lines")
+    ap.add_argument("--no-nonuniform", action="store_true", help="skip the repeat-rich / genome-like / config-5 builds")
+    ap.add_argument("--no-compat", action="store_true", help="skip the numbers through libstralg_b200.so")
     ap.add_argument("--locate-reads", type=int, default=20_000_000)
     ap.add_argument("--sa-rate", type=int, default=32)
     ap.add_argument("--approx-reads", type=int, default=200_000)

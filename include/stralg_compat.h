@@ -131,6 +131,9 @@ void dealloc_bwt_exact_match_iter(struct bwt_exact_match_iter *iter);
  * read (tools/readmappers/bwt_readmapper/bwt_readmapper.c:128-161 maps one read at a time). */
 void bwt_exact_match_batch(struct bwt_table *bwt_table, const uint8_t *remapped_patterns,
                            const uint64_t *offsets, uint64_t npatterns, uint32_t *L, uint32_t *R);
+/* Measurement aid: one iterator per pattern (the loop of performance/suffix_array_search.c:127-141) over
+ * npat NUL-terminated remapped patterns laid out with a stride of m + 1 bytes; returns the matches. */
+uint64_t bwt_exact_match_loop(struct bwt_table *tbl, const uint8_t *patterns, uint32_t m, uint64_t npat);
 
 /* bwt.h:246-333 -- approximate-match iterator.  Layouts are the reference's
  * (vectors.h:29-33, 153-157; bwt.h:246-259, 277-281); callers stack-allocate the iterator.

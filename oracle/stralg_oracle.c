@@ -482,6 +482,26 @@ void oracle_ref_search_threads(void *init_fn, void *table, const uint8_t *pat, u
         pthread_join(tid[t], 0);
 }
 
+/* One iterator per pattern, every match fetched: the timing loop of the reference's own harness
+ * (performance/suffix_array_search.c:127-141) around ITS functions (pointers into oracle/_ref);
+ * patterns are NUL-terminated, stride m + 1.  bench.py's cpu_baseline leg of `compat`. */
+typedef int (*ref_next_fn)(struct ref_exact_iter *, uint32_t *);
+uint64_t oracle_ref_iter_loop(void *init_fn, void *next_fn, void *table, const uint8_t *patterns, uint32_t m,
+                              uint64_t npat)
+{
+    ref_init_fn init = (ref_init_fn)init_fn;
+    ref_next_fn next = (ref_next_fn)next_fn;
+    uint64_t hits = 0;
+    for (uint64_t q = 0; q < npat; ++q) {
+        struct ref_exact_iter it;
+        uint32_t pos;
+        init(&it, table, patterns + q * ((uint64_t)m + 1));
+        while (next(&it, &pos) & 1)
+            ++hits;
+    }
+    return hits;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Approximate (edit distance <= d) backward search.  Follows stralg/bwt.c:226-299 (the
  * recursion), :302-382 (D table over the reversed text's O table + the first level, which has

@@ -435,6 +435,21 @@ void init_bwt_exact_match_iter(struct bwt_exact_match_iter *iter, struct bwt_tab
     iter->i = L;
 }
 
+// Measurement aid (bench.py `compat`): the loop of performance/suffix_array_search.c:127-141 -- ONE
+// iterator per pattern, every match fetched -- over `npat` NUL-terminated remapped patterns laid out
+// with a stride of m + 1 bytes.  Returns the number of matches.
+uint64_t bwt_exact_match_loop(struct bwt_table *tbl, const uint8_t *patterns, uint32_t m, uint64_t npat) {
+    uint64_t hits = 0;
+    for (uint64_t q = 0; q < npat; ++q) {
+        struct bwt_exact_match_iter it;
+        struct bwt_exact_match mt;
+        init_bwt_exact_match_iter(&it, tbl, patterns + q * ((uint64_t)m + 1));
+        while (next_bwt_exact_match_iter(&it, &mt)) ++hits;
+        dealloc_bwt_exact_match_iter(&it);
+    }
+    return hits;
+}
+
 bool next_bwt_exact_match_iter(struct bwt_exact_match_iter *iter, struct bwt_exact_match *match) {
     if (iter->i < 0 || iter->i >= (int64_t)iter->R) return false;
     match->pos = iter->sa->array[iter->i++];

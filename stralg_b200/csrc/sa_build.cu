@@ -449,8 +449,13 @@ __global__ void __launch_bounds__(256) make_keys_round_kernel(const u32 *__restr
 // where there is one.
 // ---------------------------------------------------------------------------------------------
 static constexpr int CF_NT = 256, CF_IPT = 8, CF_TILE = CF_NT * CF_IPT;
-static constexpr u32 CHAIN_CAP = 1u << 16;  // longest offset taken from a chain (longer chains: the cap itself)
+static constexpr int CF_STEP = CF_TILE - 512;  // a tile OWNS the groups whose head lies in its first CF_STEP elements
+static constexpr u32 CHAIN_CAP = 1u << 16;     // longest offset taken from a chain (longer chains: the cap itself)
 
+// Tiles overlap: tile t loads the list elements [t * CF_STEP, t * CF_STEP + CF_TILE) and decides for the
+// groups whose head lies in the first CF_STEP of them, so a group of up to 512 members is seen as a whole by
+// exactly one tile wherever it lies (a group cut by a tile border would break every chain that runs through it).
+// cslot[] and cont8[] are zeroed by the caller; only "continues" is written.
 __global__ void __launch_bounds__(CF_NT) chain_flags_kernel(const u32 *__restrict__ act, const u32 *__restrict__ grp, u32 m,
                                                             const u32 *__restrict__ rank, u8 *__restrict__ cslot,
                                                             u8 *__restrict__ cont8, u32 *__restrict__ ncont) {
@@ -459,7 +464,8 @@ __global__ void __launch_bounds__(CF_NT) chain_flags_kernel(const u32 *__restric
     __shared__ u32 wmax[CF_NT / 32];
     __shared__ u32 bcount;
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const u64 tile_base = (u64)blockIdx.x * CF_TILE;
+    const u64 tile_base = (u64)blockIdx.x * CF_STEP;
+    const u64 tile_end = min((u64)m, tile_base + CF_TILE);  // one past the last element loaded
     const u64 j0 = tile_base + (u64)tid * CF_IPT;
     if (tid == 0) bcount = 0;
     u32 s[CF_IPT], g[CF_IPT], q1[CF_IPT], hidx[CF_IPT];
@@ -487,8 +493,6 @@ __global__ void __launch_bounds__(CF_NT) chain_flags_kernel(const u32 *__restric
             pg = g[q];
         }
     }
-    // a thread's first element is a head iff its group differs from the previous element's; for the
-    // tile's very first element (no look at the previous tile needed: grp[j0 - 1] was read) as well
     u32 ex = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -502,7 +506,7 @@ __global__ void __launch_bounds__(CF_NT) chain_flags_kernel(const u32 *__restric
     for (u32 w = 0; w < warp; ++w) pre = max(pre, wmax[w]);
 #pragma unroll
     for (int q = 0; q < CF_IPT; ++q)
-        if (hidx[q] == 0) hidx[q] = pre;  // 0: the group began in an earlier tile
+        if (hidx[q] == 0) hidx[q] = pre;  // 0: the group began before this tile
     // heads publish their successor's rank
 #pragma unroll
     for (int q = 0; q < CF_IPT; ++q) {
@@ -518,26 +522,21 @@ __global__ void __launch_bounds__(CF_NT) chain_flags_kernel(const u32 *__restric
         const u64 j = j0 + q;
         if (j < m && hidx[q] && q1[q] != hq[hidx[q] - 1u]) flag[hidx[q] - 1u] = 0u;
     }
-    // the tile's last group must end inside the tile
-    if (tid == CF_NT - 1 || j0 + CF_IPT >= m) {
-        const u64 last = min((u64)m, tile_base + CF_TILE) - 1;  // last element of the tile
-        if (last >= j0 && last < j0 + CF_IPT) {
-            const int q = (int)(last - j0);
-            if (last + 1 < m && grp[last + 1] == g[q] && hidx[q]) flag[hidx[q] - 1u] = 0u;
-        }
+    // the last group loaded must end inside the loaded range
+    if (tile_end > j0 && tile_end - 1 < j0 + CF_IPT) {
+        const int q = (int)(tile_end - 1 - j0);
+        if (tile_end < m && grp[tile_end] == g[q] && hidx[q]) flag[hidx[q] - 1u] = 0u;
     }
     __syncthreads();
     u32 mine = 0;
 #pragma unroll
     for (int q = 0; q < CF_IPT; ++q) {
         const u64 j = j0 + q;
-        if (j < m) {
-            const bool c = hidx[q] && flag[hidx[q] - 1u];
-            cslot[j] = c ? 1 : 0;
-            if (c) {
-                cont8[s[q]] = 1;
-                ++mine;
-            }
+        // owned: the head lies in the first CF_STEP elements of the tile
+        if (j < m && hidx[q] && hidx[q] <= (u32)CF_STEP && flag[hidx[q] - 1u]) {
+            cslot[j] = 1;
+            cont8[s[q]] = 1;
+            ++mine;
         }
     }
     mine = __reduce_add_sync(0xffffffffu, mine);
@@ -1358,13 +1357,16 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                     d_ncont = ar.get<u32>(1);
                 }
                 CUDA_CHECK(cudaMemsetAsync(cont8, 0, cont_bytes, st));
+                CUDA_CHECK(cudaMemsetAsync(cslot, 0, m, st));
                 CUDA_CHECK(cudaMemsetAsync(d_ncont, 0, 4, st));
-                chain_flags_kernel<<<div_up_u(m, CF_TILE), CF_NT, 0, st>>>(act, grp, m, rank, cslot, cont8, d_ncont);
+                chain_flags_kernel<<<div_up_u(m, CF_STEP), CF_NT, 0, st>>>(act, grp, m, rank, cslot, cont8, d_ncont);
                 KERNEL_CHECK();
                 u32 ncont = 0;
                 read_back(&ncont, d_ncont, 4, st);
                 ix.timer.end(t);
-                if ((u64)ncont * 8 >= (u64)m) {
+                // worth it when most groups continue (copies of long segments); texts whose groups are large and
+                // shallow (many diverged copies) gain nothing from it
+                if ((u64)ncont * (u64)std::max(1, env_int("B200SA_CHAIN_USE_FRAC", 2)) >= (u64)m) {
                     t = ix.timer.begin("chain_keys", (double)len + (double)ncont * 4.0);
                     chain_keys_kernel<<<div_up_u(len, CK_TILE), CK_NT, 0, st>>>(cont8, len, lr, h, chainkey, d_lazy);
                     KERNEL_CHECK();

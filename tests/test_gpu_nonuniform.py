@@ -88,8 +88,8 @@ MODES = {
     "more_levels": {"B200SA_MSD_MORE_FRAC": "100000000", "B200SA_MSD_OVER_FRAC": "1"},
     "avg64_shallow": {"B200SA_MSD_AVG": "64", "B200SA_MSD_MORE_FRAC": "1", "B200SA_MSD_OVER_FRAC": "1"},
     # chain offsets (sa_build.cu chain_flags_kernel) on every round however small the active set / never
-    "chain_always": {"B200SA_CHAIN_MIN_FRAC": "100000000"},
-    "chain_always_shallow": {"B200SA_CHAIN_MIN_FRAC": "100000000", "B200SA_MSD_MORE_FRAC": "1", "B200SA_MSD_OVER_FRAC": "1"},
+    "chain_always": {"B200SA_CHAIN_MIN_FRAC": "100000000", "B200SA_CHAIN_USE_FRAC": "100000000"},
+    "chain_always_shallow": {"B200SA_CHAIN_MIN_FRAC": "100000000", "B200SA_CHAIN_USE_FRAC": "100000000", "B200SA_MSD_MORE_FRAC": "1", "B200SA_MSD_OVER_FRAC": "1"},
     "chain_off": {"B200SA_CHAIN": "0"},
 }
 

@@ -67,8 +67,8 @@ ROUND0_MODES = {
     "lsd8": {"B200SA_ROUND0": "lsd", "B200SA_RADIX_BITS": "8"},
     "lsd10": {"B200SA_ROUND0": "lsd", "B200SA_RADIX_BITS": "10"},
     # chain offsets in every doubling round, however small the active set (default: only large ones)
-    "msd_chain": {"B200SA_CHAIN_MIN_FRAC": "100000000"},
-    "lsd8_chain": {"B200SA_ROUND0": "lsd", "B200SA_RADIX_BITS": "8", "B200SA_CHAIN_MIN_FRAC": "100000000"},
+    "msd_chain": {"B200SA_CHAIN_MIN_FRAC": "100000000", "B200SA_CHAIN_USE_FRAC": "100000000"},
+    "lsd8_chain": {"B200SA_ROUND0": "lsd", "B200SA_RADIX_BITS": "8", "B200SA_CHAIN_MIN_FRAC": "100000000", "B200SA_CHAIN_USE_FRAC": "100000000"},
 }
 
 
