@@ -93,7 +93,9 @@ b200sa_index *b200sa_build(const uint8_t *codes, uint64_t n, uint32_t sigma, uin
 /* Adds tables that were not requested at build time to an existing index (the reference's lazy
  * compute_inverse / compute_lcp, suffix_array.c:55-85, and init_bwt_table over an existing
  * suffix array, bwt.c:22-89).  `codes` is the same text again (host, or device with
- * B200SA_TEXT_ON_DEVICE); flags is a subset of B200SA_BUILD_{ISA,LCP,BWT,OCC}. */
+ * B200SA_TEXT_ON_DEVICE); flags is a subset of B200SA_BUILD_{ISA,LCP,BWT,OCC,TEXTCMP,KTABLE}.  Fails with
+ * B200SA_ERR_BAD_SYMBOL / _BAD_ARGUMENT (index untouched) when `codes` holds a code outside
+ * 1..sigma-1 or is not the text the index was built from (symbol counts differ). */
 int b200sa_extend(b200sa_index *idx, const uint8_t *codes, uint32_t flags);
 void b200sa_free(b200sa_index *idx);
 const char *b200sa_last_error(void);

@@ -451,11 +451,14 @@ int b200sa_extend(b200sa_index *idx, const uint8_t *codes, uint32_t flags) {
     if (!idx || (!codes && idx->ix.n)) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
     DeviceIndex &ix = idx->ix;
     if (!ix.sa.ptr) return fail(B200SA_ERR_NOT_BUILT, "suffix array was dropped (B200SA_DROP_SA)", nullptr);
-    const bool need_isa = (flags & B200SA_BUILD_ISA) && !ix.isa.ptr;
+    const bool need_textcmp = (flags & B200SA_BUILD_TEXTCMP) && !ix.text_packed.ptr && ix.pk.bits == 2;
+    const bool need_isa = ((flags & B200SA_BUILD_ISA) || need_textcmp) && !ix.isa.ptr;
     const bool need_lcp = (flags & B200SA_BUILD_LCP) && !ix.lcp.ptr;
     const bool need_occ = (flags & B200SA_BUILD_OCC) && ix.occ_layout == OCC_NONE;
     const bool need_bwt = ((flags & B200SA_BUILD_BWT) && !ix.bwt.ptr) || need_occ;
-    if (!need_isa && !need_lcp && !need_bwt) return 0;
+    const bool need_ktable = (flags & B200SA_BUILD_KTABLE) && !ix.ktable.ptr && ix.sigma <= 5 &&
+                             (need_occ || ix.occ_layout == OCC_DNA32);
+    if (!need_isa && !need_lcp && !need_bwt && !need_textcmp && !need_ktable) return 0;
     API_GUARD_BEGIN
     DeviceGuard guard(ix.device);
     use_device(ix.device);
@@ -504,10 +507,18 @@ int b200sa_extend(b200sa_index *idx, const uint8_t *codes, uint32_t flags) {
         if (!had_bwt) gather_bwt(ix);
         if (need_occ) build_bwt_tables(ix, had_bwt || (flags & B200SA_BUILD_BWT));
     }
+    if (need_textcmp) {
+        size_t words = ((size_t)ix.len + ix.pk.cpw - 1) / ix.pk.cpw + 4;
+        ix.text_packed.alloc_output(words, st);
+        CUDA_CHECK(cudaMemcpyAsync(ix.text_packed.ptr, ix.packed, words * 8, cudaMemcpyDeviceToDevice, st));
+    }
     ix.packed = nullptr;
     ix.arena = nullptr;
+    if (need_ktable) build_ktable(ix);
     CUDA_CHECK(cudaStreamSynchronize(st));
     idx->flags |= flags & (B200SA_BUILD_ISA | B200SA_BUILD_LCP | B200SA_BUILD_BWT | B200SA_BUILD_OCC);
+    if (ix.text_packed.ptr) idx->flags |= B200SA_BUILD_TEXTCMP;
+    if (ix.ktable.ptr) idx->flags |= B200SA_BUILD_KTABLE;
     return 0;
     API_GUARD_END(nullptr)
 }

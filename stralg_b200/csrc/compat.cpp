@@ -419,7 +419,10 @@ bool equivalent_bwt_tables(struct bwt_table *t1, struct bwt_table *t2) {
 void bwt_exact_match_batch(struct bwt_table *tbl, const uint8_t *patterns, const uint64_t *offsets,
                            uint64_t npatterns, uint32_t *L, uint32_t *R) {
     b200sa_index *idx = index_of(tbl->sa, tbl->remap_table->alphabet_size, true);
-    if (b200sa_extend(idx, tbl->sa->string, B200SA_BUILD_OCC)) die("bwt_exact_match_batch");
+    // (first search on this table: also the k-mer seed table and the text-comparison shortcut -- they cut the
+    // chain of dependent lookups of one pattern from its length to about a dozen)
+    if (b200sa_extend(idx, tbl->sa->string, B200SA_BUILD_OCC | B200SA_BUILD_TEXTCMP | B200SA_BUILD_KTABLE))
+        die("bwt_exact_match_batch");
     if (b200sa_search_batch(idx, patterns, offsets, 0, npatterns, L, R)) die("bwt_exact_match_batch");
 }
 

@@ -652,6 +652,8 @@ struct L3Args {
     const u32 *tile_first;
     u32 n;
     int K, pb, R;
+    const u64 *packed; // packed text (ties of equal K-symbol keys are broken by the NEXT 64 bits where that decides)
+    int bits;
     u32 *sa;
     u8 *bwt;           // may be null
     u32 *rank;         // rank[s] = first row of the group of s, written for suffixes whose key is shared
@@ -1003,6 +1005,7 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
                 const u32 se = (u32)e;
                 const bool e_short = is_short_suffix(se, a.K, a.n);
                 u32 longs_before = 0;
+                u32 oth[3], noth = 0;  // the other long suffixes with this key (their number may exceed 3)
                 bool lv = true, rv = true;
                 for (u32 d = 1; d <= W; ++d) {
                     lv = lv && p >= d;
@@ -1017,17 +1020,48 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
                         const bool o_short = is_short_suffix(so, a.K, a.n);
                         // the left neighbour belongs AFTER this element
                         if (o_short ? (e_short && so < se) : e_short) --r;
-                        if (!o_short && !e_short) { active = true; ++longs_before; }
+                        if (!o_short && !e_short) {
+                            active = true;
+                            ++longs_before;
+                            if (noth < 3u) oth[noth] = so;
+                            ++noth;
+                        }
                     }
                     if (rv && (Xhi[p + d] >> a.pb) == kp) {
                         const u32 so = Xlo[p + d];
                         const bool o_short = is_short_suffix(so, a.K, a.n);
                         // the right neighbour belongs BEFORE this element
                         if (o_short ? (!e_short || so > se) : false) ++r;
-                        if (!o_short && !e_short) active = true;
+                        if (!o_short && !e_short) {
+                            active = true;
+                            if (noth < 3u) oth[noth] = so;
+                            ++noth;
+                        }
                     }
                 }
                 head = r - longs_before;
+                // Two to four long suffixes with the same K symbols (chance collisions of a random text, the
+                // ends of repeats): the next 64 bits of text decide at once, unless two of them agree there too
+                // or one of the windows reaches the end of the text -- then the group goes to the doubling rounds.
+                if (active && noth <= 3u && a.packed) {
+                    const u32 span = 64u / (u32)a.bits;
+                    u64 ext[4];
+                    bool decided = (u64)se + (u64)a.K + span <= (u64)a.n;
+                    ext[0] = decided ? window_at(a.packed, (u64)se + (u64)a.K, a.bits) : 0ull;
+                    for (u32 x = 0; x < noth && decided; ++x) {
+                        decided = (u64)oth[x] + (u64)a.K + span <= (u64)a.n;
+                        if (decided) ext[x + 1] = window_at(a.packed, (u64)oth[x] + (u64)a.K, a.bits);
+                    }
+                    u32 smaller = 0;
+                    for (u32 x = 0; x <= noth && decided; ++x)
+                        for (u32 y = x + 1; y <= noth; ++y)
+                            if (ext[x] == ext[y]) decided = false;
+                    if (decided) {
+                        for (u32 x = 1; x <= noth; ++x) smaller += ext[x] < ext[0] ? 1u : 0u;
+                        r = head + smaller;
+                        active = false;
+                    }
+                }
             }
             l3_emit(a, E0 + r, e, active, E0 + head, abits, E0 & ~31u);
         }
@@ -1313,6 +1347,25 @@ static void launch_t1_variant(const Text1Args &ta, u32 len, cudaStream_t st) {
     msd_partition_text_kernel<2, true, NT, IPT, CTAS><<<div_up_u(len, NT * IPT), NT, t1_smem<NT, IPT>(), st>>>(ta);
 }
 
+namespace {
+struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream &side_stream(int device) {
+    static SideStream per_device[64];
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    SideStream &x = per_device[device & 63];
+    if (!x.s) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming));
+    }
+    return x;
+}
+}  // namespace
+
 bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     cudaStream_t st = ix.stream;
     Arena &ar = *ix.arena;
@@ -1397,9 +1450,19 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     u32 *tile_first = ar.get<u32>((size_t)ntl3 + 2);
     u32 *flagged = ar.get<u32>((size_t)ntl3 + 1);
     u32 *bigtiles = ar.get<u32>((size_t)ntl3 + 1);
-    // no row is active, no rank is materialised
+    // no row is active, no rank is materialised.  The 4 bytes per suffix of "not materialised" are written by a
+    // side stream while the partition levels run (they leave HBM bandwidth unused); the in-SM sort waits for it.
     CUDA_CHECK(cudaMemsetAsync(r.actbits, 0, (((size_t)len + 31) / 32 + 2) * 4, st));
-    CUDA_CHECK(cudaMemsetAsync(r.rank, 0xff, (size_t)len * 4, st));
+    SideStream &side = side_stream(ix.device);
+    CUDA_CHECK(cudaEventRecord(side.fork, st));
+    CUDA_CHECK(cudaStreamWaitEvent(side.s, side.fork, 0));
+    CUDA_CHECK(cudaMemsetAsync(r.rank, 0xff, (size_t)len * 4, side.s));
+    CUDA_CHECK(cudaEventRecord(side.join, side.s));
+    struct JoinGuard {  // every way out of this function (fallback included) waits for the side stream
+        cudaStream_t st;
+        cudaEvent_t ev;
+        ~JoinGuard() { cudaStreamWaitEvent(st, ev, 0); }
+    } join_guard{st, side.join};
 
     // ---- level 1: from the text ----
     level_tables(0);
@@ -1511,6 +1574,7 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     L3Args la{};
     la.in = cur; la.bstart = start[last]; la.tile_first = tile_first; la.n = n;
     la.K = pl.K; la.pb = pl.pb; la.R = pl.R;
+    la.packed = env_int2("B200SA_NO_EXT_TIEBREAK", 0) ? nullptr : ix.packed; la.bits = b;
     la.par_shift = pl.BB - pl.D[0];
     la.sa = ix.sa.ptr;
     la.bwt = (want_bwt && pl.pb) ? ix.bwt.ptr : nullptr;
@@ -1520,6 +1584,7 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     la.flagged = flagged; la.nflagged = d_misc + 4;
     la.big = bigtiles; la.nbig = d_misc + 5;
     la.ntiles = ntl3;
+    CUDA_CHECK(cudaStreamWaitEvent(st, side.join, 0));
     msd_local_sort_kernel<<<std::min(ntl3, (unsigned)L3_CTAS * sm_count(ix.device)), L3_NT, L3_SMEM, st>>>(la);
     KERNEL_CHECK();
     u32 hmisc[8];

@@ -1019,6 +1019,7 @@ __global__ void __launch_bounds__(CP_NT) scatter_active_kernel(const u8 *__restr
     u32 wb = 0;
     for (unsigned w = 0; w < (threadIdx.x >> 5); ++w) wb += wsum[w];
     const u32 o = tile_offsets[blockIdx.x] + wb + incl - c;
+    if (!__any_sync(0xffffffffu, mask != 0)) return;  // (most warps of a sparse bitmap)
     // the warp walks its 32 words together: lane l takes element l (then 32 + l) of the word, so the
     // reads of `vals` and the writes of the survivors are coalesced
     const u32 lane = lane_id();
