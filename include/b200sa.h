@@ -81,6 +81,7 @@ struct b200sa_stats {
     uint64_t shallow_elems;   /* suffixes in them (upper bound) */
     uint64_t chain_elems;     /* suffixes in groups that "continued", summed over those rounds */
     uint64_t lazy_lookups;    /* ranks of retired suffixes recovered on demand */
+    uint64_t resolved_small;  /* suffixes in groups of 2..4 equal initial keys decided by the next 64 bits of text */
 };
 
 /* ---- construction ------------------------------------------------------------------------

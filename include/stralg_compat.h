@@ -131,6 +131,10 @@ void dealloc_bwt_exact_match_iter(struct bwt_exact_match_iter *iter);
  * read (tools/readmappers/bwt_readmapper/bwt_readmapper.c:128-161 maps one read at a time). */
 void bwt_exact_match_batch(struct bwt_table *bwt_table, const uint8_t *remapped_patterns,
                            const uint64_t *offsets, uint64_t npatterns, uint32_t *L, uint32_t *R);
+/* The same for reads of ONE length over a DNA alphabet, packed to 2 bits per base (four bases per byte, first
+ * base in the high bits, read q at byte q * stride_bytes; b200sa.h: b200sa_pack_reads). */
+void bwt_exact_match_batch_packed(struct bwt_table *bwt_table, const uint8_t *packed_reads, uint32_t read_len,
+                                  uint32_t stride_bytes, uint64_t nreads, uint32_t *L, uint32_t *R);
 /* Measurement aid: one iterator per pattern (the loop of performance/suffix_array_search.c:127-141) over
  * npat NUL-terminated remapped patterns laid out with a stride of m + 1 bytes; returns the matches. */
 uint64_t bwt_exact_match_loop(struct bwt_table *tbl, const uint8_t *patterns, uint32_t m, uint64_t npat);

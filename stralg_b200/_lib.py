@@ -40,7 +40,7 @@ class Stats(C.Structure):
         ("round0_mode", C.c_uint32), ("bucket_bits", C.c_uint32),
         ("sa_sample_rate", C.c_uint32), ("sa_resident", C.c_uint32),
         ("shallow_buckets", C.c_uint32), ("chain_rounds", C.c_uint32), ("shallow_elems", C.c_uint64),
-        ("chain_elems", C.c_uint64), ("lazy_lookups", C.c_uint64),
+        ("chain_elems", C.c_uint64), ("lazy_lookups", C.c_uint64), ("resolved_small", C.c_uint64),
     ]
 
 

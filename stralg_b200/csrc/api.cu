@@ -555,6 +555,7 @@ int b200sa_stats(const b200sa_index *idx, struct b200sa_stats *out) {
     out->shallow_elems = ix.stats.shallow_elems;
     out->chain_elems = ix.stats.chain_elems;
     out->lazy_lookups = ix.stats.lazy_lookups;
+    out->resolved_small = ix.stats.resolved_small;
     return 0;
 }
 

@@ -31,6 +31,7 @@ struct BuildStats {
     u64 lazy_lookups;    // ranks of retired suffixes recovered on demand by the doubling rounds
     u32 chain_rounds;    // doubling rounds that used chain offsets (sa_build.cu: chain_flags_kernel)
     u64 chain_elems;     // suffixes whose group "continued", summed over those rounds
+    u32 resolved_small;  // suffixes in groups of 2..4 equal keys that the next 64 bits of text decided after round 0
 };
 
 // Occurrence-table layouts

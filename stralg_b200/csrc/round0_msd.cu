@@ -652,8 +652,6 @@ struct L3Args {
     const u32 *tile_first;
     u32 n;
     int K, pb, R;
-    const u64 *packed; // packed text (ties of equal K-symbol keys are broken by the NEXT 64 bits where that decides)
-    int bits;
     u32 *sa;
     u8 *bwt;           // may be null
     u32 *rank;         // rank[s] = first row of the group of s, written for suffixes whose key is shared
@@ -1005,7 +1003,6 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
                 const u32 se = (u32)e;
                 const bool e_short = is_short_suffix(se, a.K, a.n);
                 u32 longs_before = 0;
-                u32 oth[3], noth = 0;  // the other long suffixes with this key (their number may exceed 3)
                 bool lv = true, rv = true;
                 for (u32 d = 1; d <= W; ++d) {
                     lv = lv && p >= d;
@@ -1020,48 +1017,17 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
                         const bool o_short = is_short_suffix(so, a.K, a.n);
                         // the left neighbour belongs AFTER this element
                         if (o_short ? (e_short && so < se) : e_short) --r;
-                        if (!o_short && !e_short) {
-                            active = true;
-                            ++longs_before;
-                            if (noth < 3u) oth[noth] = so;
-                            ++noth;
-                        }
+                        if (!o_short && !e_short) { active = true; ++longs_before; }
                     }
                     if (rv && (Xhi[p + d] >> a.pb) == kp) {
                         const u32 so = Xlo[p + d];
                         const bool o_short = is_short_suffix(so, a.K, a.n);
                         // the right neighbour belongs BEFORE this element
                         if (o_short ? (!e_short || so > se) : false) ++r;
-                        if (!o_short && !e_short) {
-                            active = true;
-                            if (noth < 3u) oth[noth] = so;
-                            ++noth;
-                        }
+                        if (!o_short && !e_short) active = true;
                     }
                 }
                 head = r - longs_before;
-                // Two to four long suffixes with the same K symbols (chance collisions of a random text, the
-                // ends of repeats): the next 64 bits of text decide at once, unless two of them agree there too
-                // or one of the windows reaches the end of the text -- then the group goes to the doubling rounds.
-                if (active && noth <= 3u && a.packed) {
-                    const u32 span = 64u / (u32)a.bits;
-                    u64 ext[4];
-                    bool decided = (u64)se + (u64)a.K + span <= (u64)a.n;
-                    ext[0] = decided ? window_at(a.packed, (u64)se + (u64)a.K, a.bits) : 0ull;
-                    for (u32 x = 0; x < noth && decided; ++x) {
-                        decided = (u64)oth[x] + (u64)a.K + span <= (u64)a.n;
-                        if (decided) ext[x + 1] = window_at(a.packed, (u64)oth[x] + (u64)a.K, a.bits);
-                    }
-                    u32 smaller = 0;
-                    for (u32 x = 0; x <= noth && decided; ++x)
-                        for (u32 y = x + 1; y <= noth; ++y)
-                            if (ext[x] == ext[y]) decided = false;
-                    if (decided) {
-                        for (u32 x = 1; x <= noth; ++x) smaller += ext[x] < ext[0] ? 1u : 0u;
-                        r = head + smaller;
-                        active = false;
-                    }
-                }
             }
             l3_emit(a, E0 + r, e, active, E0 + head, abits, E0 & ~31u);
         }
@@ -1574,7 +1540,6 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     L3Args la{};
     la.in = cur; la.bstart = start[last]; la.tile_first = tile_first; la.n = n;
     la.K = pl.K; la.pb = pl.pb; la.R = pl.R;
-    la.packed = env_int2("B200SA_NO_EXT_TIEBREAK", 0) ? nullptr : ix.packed; la.bits = b;
     la.par_shift = pl.BB - pl.D[0];
     la.sa = ix.sa.ptr;
     la.bwt = (want_bwt && pl.pb) ? ix.bwt.ptr : nullptr;

@@ -1153,6 +1153,75 @@ __global__ void __launch_bounds__(256) bwt_fix_kernel(const u32 *__restrict__ ac
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small groups decided by the text.  After round 0 of a text without long repeats the active set is a
+// sprinkle of groups of two to four suffixes that share their K symbols by chance (3 Gbp of random
+// ACGT: 8 million suffixes, 0.27 %); a doubling round for them costs gathers with recovered ranks, a
+// radix sort and a scatter.  One look at the next 64 bits of text (32 symbols of DNA) decides almost
+// all of them: a member's final row is the group's first row plus the members with a smaller
+// extension.  A group is decided only as a whole (all extensions differ, none reaches the end of the
+// text); the rest stays active.  Run only while the active set is small -- in a repeat-rich text the
+// members of a group agree for thousands of symbols and the loads would be wasted.
+// keep8[j] = 1: element j stays active.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resolve_small_groups_kernel(const u32 *__restrict__ act, const u32 *__restrict__ grp,
+                                                                   u32 m, const u64 *__restrict__ packed, int bits, int K,
+                                                                   u32 n, u32 *__restrict__ sa, u32 *__restrict__ rank,
+                                                                   u8 *__restrict__ bwt, u32 *__restrict__ primary,
+                                                                   u8 *__restrict__ keep8) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const u32 g = grp[j], s = act[j];
+    // members: list elements j - nl .. j + nr (the list is grouped; a group has at least two members)
+    u32 nl = 0, nr = 0;
+    while (nl < 4u && j >= (u64)nl + 1 && grp[j - nl - 1] == g) ++nl;
+    while (nr < 4u && j + nr + 1 < m && grp[j + nr + 1] == g) ++nr;
+    bool decided = nl + nr + 1u <= 4u;
+    const u32 span = 64u / (u32)bits;
+    u32 smaller = 0;
+    if (decided) {
+        u64 ext[4];
+        const u32 size = nl + nr + 1u;
+        for (u32 x = 0; x < size && decided; ++x) {
+            const u32 t = act[j - nl + x];
+            decided = (u64)t + (u64)K + span <= (u64)n;
+            if (decided) ext[x] = window_at(packed, (u64)t + (u64)K, bits);
+        }
+        for (u32 x = 0; x < size && decided; ++x)
+            for (u32 y = x + 1; y < size; ++y)
+                if (ext[x] == ext[y]) decided = false;
+        if (decided)
+            for (u32 x = 0; x < size; ++x) smaller += ext[x] < ext[nl] ? 1u : 0u;
+    }
+    keep8[j] = decided ? 0 : 1;
+    if (decided) {
+        const u32 row = g + smaller;
+        sa[row] = s;
+        rank[s] = row;
+        if (s == 0) *primary = row;
+        if (bwt) {
+            u8 c = 0;
+            if (s) {
+                const u64 bitpos = (u64)(s - 1) * bits;
+                const u64 w = packed[bitpos >> 6];
+                c = (u8)(((w >> (64 - bits - (unsigned)(bitpos & 63))) & ((1u << bits) - 1u)) + 1u);
+            }
+            bwt[row] = c;
+        }
+    }
+}
+
+// bytes (0 / 1) -> bitmap words, one thread per 64 elements
+__global__ void __launch_bounds__(256) bytes_to_bits_kernel(const u8 *__restrict__ b8, u32 m, u64 *__restrict__ bits64,
+                                                            u64 nwords) {
+    const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwords) return;
+    u64 v = 0;
+    const u64 base = w * 64;
+    for (u32 i = 0; i < 64 && base + i < m; ++i) v |= (u64)(b8[base + i] & 1u) << i;
+    bits64[w] = v;
+}
+
 template <int RB>
 static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
     typedef rs::Sorter<RB> S;
@@ -1316,6 +1385,26 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
     // ---- doubling rounds over the active set ----
     u8 *bwt_rows = (want_bwt && bwt_in_sort) ? ix.bwt.ptr : nullptr;
     bool need_bwt_fix = false;
+    if (m && (u64)m * 64 <= (u64)len && b <= 8 && !env_int("B200SA_NO_EXT_TIEBREAK", 0)) {
+        // a small active set: groups of two to four chance collisions are decided by the next 64 bits of text
+        t = ix.timer.begin("resolve_small", (double)m * 40.0);
+        u8 *keep8 = ar.get<u8>((size_t)m + 64);
+        u32 *act_r = ar.get<u32>(m), *grp_r = ar.get<u32>(m);
+        resolve_small_groups_kernel<<<div_up_u(m, 256), 256, 0, st>>>(act, grp, m, ix.packed, b, K, n, sa, rank, bwt_rows,
+                                                                      d_primary.ptr, keep8);
+        KERNEL_CHECK();
+        const u64 kw = ((u64)m + 63) / 64;
+        CUDA_CHECK(cudaMemsetAsync(headbits, 0, (kw + 2) * 8, st));
+        bytes_to_bits_kernel<<<div_up_u(kw, 256), 256, 0, st>>>(keep8, m, (u64 *)headbits, kw);
+        KERNEL_CHECK();
+        const u32 m2 = count_active<true>(headbits, m, tile_counts, d_total, st);
+        if (m2) scatter_active<true>(headbits, act, grp, m, tile_counts, act_r, grp_r, st);
+        ix.stats.resolved_small = m - m2;
+        act = act_r;
+        grp = grp_r;
+        m = m2;
+        ix.timer.end(t);
+    }
     if (m) {
         // complete ranks ("dense") from the start when most suffixes are active; otherwise ranks of
         // retired suffixes are recovered on demand, until a round needs many of them

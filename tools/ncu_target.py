@@ -39,6 +39,15 @@ else:
         idx.search_device(r, None, m, reads_n, L, R)
         idx.search_device_packed(p, m, reads_n, L, R, stride)
     torch.cuda.synchronize()
+    for name, fn in (("byte", lambda: idx.search_device(r, None, m, reads_n, L, R)),
+                     ("packed", lambda: idx.search_device_packed(p, m, reads_n, L, R, stride))):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"{name} kernel: {e0.elapsed_time(e1) / 5:.3f} ms for {reads_n} reads (L2_FETCH={os.environ.get('B200SA_L2_FETCH')})")
     idx.close()
 torch.cuda.synchronize()
 print("done", what, n)
