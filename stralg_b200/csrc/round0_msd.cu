@@ -654,9 +654,8 @@ struct L3Args {
     int K, pb, R;
     u32 *sa;
     u8 *bwt;           // may be null
-    u32 *rank;         // rank[s] = first row of the group of s, written for suffixes whose key is shared
-                       // (everything else stays RANK_NONE: its rank is its row, recovered on demand)
-    u32 *grow;         // [len] by ROW: the same group head, for the rows of such suffixes
+    u32 *short_rank;   // [1 + 2 * 32]: count, then (suffix, row) of the short suffixes of oversize buckets
+    u32 *grow;         // [len] by ROW: first row of the group, for the rows of suffixes whose key is shared
     u32 *actbits;      // bit per row: the suffix in this row shares its key with another one ("active")
     u32 *primary;
     u32 *flagged, *nflagged;   // tiles the fast kernel declined (a crowded bin)
@@ -728,8 +727,7 @@ __device__ __forceinline__ void l3_emit(const L3Args &a, u32 g, u64 e, bool acti
     if (a.bwt) a.bwt[g] = s ? (u8)(((u32)(e >> 32) & ((1u << a.pb) - 1u)) + 1u) : (u8)0;
     if (s == 0) *a.primary = g;
     if (active) {
-        a.rank[s] = group_head;
-        a.grow[g] = group_head;
+        a.grow[g] = group_head;  // (rank[s] is written from the compacted list of active rows, sa_build.cu)
         if (sbits) atomicOr(&sbits[(g - gbase) >> 5], 1u << ((g - gbase) & 31u));
         else atomicOr(&a.actbits[g >> 5], 1u << (g & 31u));
     }
@@ -1244,6 +1242,7 @@ __global__ void msd_fix_shorts_kernel(L3Args a, OverArgs o) {
         for (u32 j = 0; j < nf; ++j) c += (st[j] == st[i] && sv[j] > sv[i]) ? 1u : 0u;
         tgt[i] = st[i] + c;  // shortest (largest start) first
     }
+    a.short_rank[0] = nf;
     for (u32 i = 0; i < nf; ++i) {
         const u32 p = pos[i], q = tgt[i];
         if (p != q) {
@@ -1269,7 +1268,9 @@ __global__ void msd_fix_shorts_kernel(L3Args a, OverArgs o) {
                 if (j != i && pos[j] == q) pos[j] = p;
             pos[i] = q;
         }
-        a.rank[sv[i]] = q;  // (materialised, not active: nothing looks for it inside the unsorted bucket)
+        // its rank is materialised by the caller (nothing can look for it inside the unsorted bucket)
+        a.short_rank[1 + 2 * i] = sv[i];
+        a.short_rank[2 + 2 * i] = q;
         if (sv[i] == 0) *a.primary = q;
     }
 }
@@ -1312,25 +1313,6 @@ static void launch_t1_variant(const Text1Args &ta, u32 len, cudaStream_t st) {
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t1_smem<NT, IPT>()));
     msd_partition_text_kernel<2, true, NT, IPT, CTAS><<<div_up_u(len, NT * IPT), NT, t1_smem<NT, IPT>(), st>>>(ta);
 }
-
-namespace {
-struct SideStream {
-    cudaStream_t s = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
-};
-SideStream &side_stream(int device) {
-    static SideStream per_device[64];
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lock(mu);
-    SideStream &x = per_device[device & 63];
-    if (!x.s) {
-        CUDA_CHECK(cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking));
-        CUDA_CHECK(cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming));
-        CUDA_CHECK(cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming));
-    }
-    return x;
-}
-}  // namespace
 
 bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     cudaStream_t st = ix.stream;
@@ -1416,19 +1398,10 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     u32 *tile_first = ar.get<u32>((size_t)ntl3 + 2);
     u32 *flagged = ar.get<u32>((size_t)ntl3 + 1);
     u32 *bigtiles = ar.get<u32>((size_t)ntl3 + 1);
-    // no row is active, no rank is materialised.  The 4 bytes per suffix of "not materialised" are written by a
-    // side stream while the partition levels run (they leave HBM bandwidth unused); the in-SM sort waits for it.
+    // no row is active
     CUDA_CHECK(cudaMemsetAsync(r.actbits, 0, (((size_t)len + 31) / 32 + 2) * 4, st));
-    SideStream &side = side_stream(ix.device);
-    CUDA_CHECK(cudaEventRecord(side.fork, st));
-    CUDA_CHECK(cudaStreamWaitEvent(side.s, side.fork, 0));
-    CUDA_CHECK(cudaMemsetAsync(r.rank, 0xff, (size_t)len * 4, side.s));
-    CUDA_CHECK(cudaEventRecord(side.join, side.s));
-    struct JoinGuard {  // every way out of this function (fallback included) waits for the side stream
-        cudaStream_t st;
-        cudaEvent_t ev;
-        ~JoinGuard() { cudaStreamWaitEvent(st, ev, 0); }
-    } join_guard{st, side.join};
+    r.short_rank = ar.get<u32>(1 + 2 * 32);
+    CUDA_CHECK(cudaMemsetAsync(r.short_rank, 0, 4, st));
 
     // ---- level 1: from the text ----
     level_tables(0);
@@ -1543,13 +1516,12 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     la.par_shift = pl.BB - pl.D[0];
     la.sa = ix.sa.ptr;
     la.bwt = (want_bwt && pl.pb) ? ix.bwt.ptr : nullptr;
-    la.rank = r.rank; la.actbits = r.actbits;
+    la.short_rank = r.short_rank; la.actbits = r.actbits;
     la.grow = (u32 *)other;  // the ping-pong buffer the elements do NOT sit in is free
     la.primary = r.d_primary;
     la.flagged = flagged; la.nflagged = d_misc + 4;
     la.big = bigtiles; la.nbig = d_misc + 5;
     la.ntiles = ntl3;
-    CUDA_CHECK(cudaStreamWaitEvent(st, side.join, 0));
     msd_local_sort_kernel<<<std::min(ntl3, (unsigned)L3_CTAS * sm_count(ix.device)), L3_NT, L3_SMEM, st>>>(la);
     KERNEL_CHECK();
     u32 hmisc[8];

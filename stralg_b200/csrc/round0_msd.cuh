@@ -29,13 +29,14 @@ struct MsdPlan {
 struct Round0Msd {
     // workspace handed in by the caller
     u64 *bufA, *bufB;  // len elements each
-    u32 *rank;         // len entries: RANK_NONE, except for suffixes that share their key (group head)
     u32 *actbits;      // (len + 31) / 32 + 2 words: bit per ROW whose suffix shares its key ("active")
     u32 *d_primary;    // 1 word
     // results
     MsdPlan plan;
     const u32 *bucket_start;  // 2^BB + 1 entries (workspace arena)
     const u32 *grow;          // [len] by row: group head of the active rows (lives in bufA or bufB)
+    u32 *short_rank;          // [1 + 2 * 32] count, then (suffix, final row) of the short suffixes of oversize buckets:
+                              // their ranks must be materialised by the caller (workspace arena)
     u32 depth0;               // symbols every active group is known to share: K, or BB / bits when oversize
                               // buckets were emitted unsorted as shallow groups
     u32 levels_added;         // partition levels added to the plan because of a skewed bucket histogram

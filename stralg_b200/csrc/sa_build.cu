@@ -951,12 +951,16 @@ __device__ __forceinline__ u64 raw_mask(const u8 *__restrict__ bits, u64 word, u
     return ((const u64 *)bits)[word] & valid;
 }
 
+// a block takes `sub` consecutive sub-tiles of CP_NT words (long bitmaps: fewer, larger tiles for the scan)
 template <bool RAW>
-__global__ void __launch_bounds__(CP_NT) count_active_kernel(const u8 *__restrict__ headbits, u32 m,
+__global__ void __launch_bounds__(CP_NT) count_active_kernel(const u8 *__restrict__ headbits, u32 m, u32 sub,
                                                              u32 *__restrict__ tile_counts) {
     __shared__ u32 wsum[CP_NT / 32];
-    u64 word = (u64)blockIdx.x * CP_NT + threadIdx.x;
-    u32 c = __popcll(RAW ? raw_mask(headbits, word, m) : active_mask(headbits, word, m));
+    u32 c = 0;
+    for (u32 q = 0; q < sub; ++q) {
+        const u64 word = ((u64)blockIdx.x * sub + q) * CP_NT + threadIdx.x;
+        c += __popcll(RAW ? raw_mask(headbits, word, m) : active_mask(headbits, word, m));
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (lane_id() == 0) wsum[threadIdx.x >> 5] = c;
@@ -1001,46 +1005,54 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(u32 *__restrict__ coun
 template <bool RAW>
 __global__ void __launch_bounds__(CP_NT) scatter_active_kernel(const u8 *__restrict__ headbits,
                                                                const u32 *__restrict__ vals,
-                                                               const u32 *__restrict__ grp_in, u32 m,
+                                                               const u32 *__restrict__ grp_in, u32 m, u32 sub,
                                                                const u32 *__restrict__ tile_offsets,
                                                                u32 *__restrict__ out, u32 *__restrict__ grp_out) {
     __shared__ u32 wsum[CP_NT / 32];
-    u64 word = (u64)blockIdx.x * CP_NT + threadIdx.x;
-    u64 mask = RAW ? raw_mask(headbits, word, m) : active_mask(headbits, word, m);
-    u32 c = __popcll(mask);
-    u32 incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane_id() >= (unsigned)o) incl += t;
-    }
-    if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    u32 wb = 0;
-    for (unsigned w = 0; w < (threadIdx.x >> 5); ++w) wb += wsum[w];
-    const u32 o = tile_offsets[blockIdx.x] + wb + incl - c;
-    if (!__any_sync(0xffffffffu, mask != 0)) return;  // (most warps of a sparse bitmap)
-    // the warp walks its 32 words together: lane l takes element l (then 32 + l) of the word, so the
-    // reads of `vals` and the writes of the survivors are coalesced
+    u32 base = tile_offsets[blockIdx.x];
     const u32 lane = lane_id();
     const u32 lt = lanemask_lt();
-    const u64 word0 = word - lane;
-#pragma unroll 4
-    for (int w = 0; w < 32; ++w) {
-        const u64 mw = __shfl_sync(0xffffffffu, mask, w);
-        const u32 ow = __shfl_sync(0xffffffffu, o, w);
-        if (!mw) continue;
-        const u64 bw = (word0 + (u64)w) * 64;
-        const u32 lo = (u32)mw, hi = (u32)(mw >> 32);
-        if ((lo >> lane) & 1u) {
-            const u32 at = ow + (u32)__popc(lo & lt);
-            out[at] = vals[bw + lane];
-            grp_out[at] = grp_in[bw + lane];
+    for (u32 q = 0; q < sub; ++q) {
+        const u64 word = ((u64)blockIdx.x * sub + q) * CP_NT + threadIdx.x;
+        const u64 mask = RAW ? raw_mask(headbits, word, m) : active_mask(headbits, word, m);
+        const u32 c = __popcll(mask);
+        u32 incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
         }
-        if ((hi >> lane) & 1u) {
-            const u32 at = ow + (u32)__popc(lo) + (u32)__popc(hi & lt);
-            out[at] = vals[bw + 32 + lane];
-            grp_out[at] = grp_in[bw + 32 + lane];
+        if (lane == 31) wsum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        u32 wb = 0, total = 0;
+        for (unsigned w = 0; w < CP_NT / 32; ++w) {
+            if (w < (threadIdx.x >> 5)) wb += wsum[w];
+            total += wsum[w];
+        }
+        const u32 o = base + wb + incl - c;
+        base += total;
+        __syncthreads();  // wsum is rewritten by the next sub-tile
+        if (!__any_sync(0xffffffffu, mask != 0)) continue;  // (most warps of a sparse bitmap)
+        // the warp walks its 32 words together: lane l takes element l (then 32 + l) of the word, so the
+        // reads of `vals` and the writes of the survivors are coalesced
+        const u64 word0 = word - lane;
+#pragma unroll 4
+        for (int w = 0; w < 32; ++w) {
+            const u64 mw = __shfl_sync(0xffffffffu, mask, w);
+            const u32 ow = __shfl_sync(0xffffffffu, o, w);
+            if (!mw) continue;
+            const u64 bw = (word0 + (u64)w) * 64;
+            const u32 lo = (u32)mw, hi = (u32)(mw >> 32);
+            if ((lo >> lane) & 1u) {
+                const u32 at = ow + (u32)__popc(lo & lt);
+                out[at] = vals[bw + lane];
+                grp_out[at] = grp_in[bw + lane];
+            }
+            if ((hi >> lane) & 1u) {
+                const u32 at = ow + (u32)__popc(lo) + (u32)__popc(hi & lt);
+                out[at] = vals[bw + 32 + lane];
+                grp_out[at] = grp_in[bw + 32 + lane];
+            }
         }
     }
 }
@@ -1109,10 +1121,12 @@ static void launch_cmer_hist(const DeviceIndex &ix, u64 nwords_data, u32 *hist, 
 // bitmap -> compacted list of still-active suffixes (in current SA order) and their group heads;
 // returns the count.  RAW: the bitmap marks the elements to keep; else it marks bucket heads and an
 // element is kept unless it is a singleton.
+static u32 compaction_sub(u32 m) { return m > (1u << 26) ? 8u : 1u; }
 template <bool RAW>
 static u32 count_active(const u8 *bits, u32 m, u32 *tile_counts, unsigned long long *d_total, cudaStream_t st) {
-    u32 ntiles = div_up_u(m, CP_TILE);
-    count_active_kernel<RAW><<<ntiles, CP_NT, 0, st>>>(bits, m, tile_counts);
+    const u32 sub = compaction_sub(m);
+    u32 ntiles = div_up_u(m, (u64)CP_TILE * sub);
+    count_active_kernel<RAW><<<ntiles, CP_NT, 0, st>>>(bits, m, sub, tile_counts);
     KERNEL_CHECK();
     scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_counts, ntiles, d_total);
     KERNEL_CHECK();
@@ -1123,7 +1137,9 @@ static u32 count_active(const u8 *bits, u32 m, u32 *tile_counts, unsigned long l
 template <bool RAW>
 static void scatter_active(const u8 *bits, const u32 *vals, const u32 *grp_in, u32 m, const u32 *tile_offsets, u32 *out,
                            u32 *grp_out, cudaStream_t st) {
-    scatter_active_kernel<RAW><<<div_up_u(m, CP_TILE), CP_NT, 0, st>>>(bits, vals, grp_in, m, tile_offsets, out, grp_out);
+    const u32 sub = compaction_sub(m);
+    scatter_active_kernel<RAW><<<div_up_u(m, (u64)CP_TILE * sub), CP_NT, 0, st>>>(bits, vals, grp_in, m, sub, tile_offsets,
+                                                                                   out, grp_out);
     KERNEL_CHECK();
 }
 
@@ -1162,11 +1178,11 @@ __global__ void __launch_bounds__(256) bwt_fix_kernel(const u32 *__restrict__ ac
 // extension.  A group is decided only as a whole (all extensions differ, none reaches the end of the
 // text); the rest stays active.  Run only while the active set is small -- in a repeat-rich text the
 // members of a group agree for thousands of symbols and the loads would be wasted.
-// keep8[j] = 1: element j stays active.
+// keep8[j] = 1: element j stays active.  rowout[j]: the rank to materialise for element j.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) resolve_small_groups_kernel(const u32 *__restrict__ act, const u32 *__restrict__ grp,
                                                                    u32 m, const u64 *__restrict__ packed, int bits, int K,
-                                                                   u32 n, u32 *__restrict__ sa, u32 *__restrict__ rank,
+                                                                   u32 n, u32 *__restrict__ sa, u32 *__restrict__ rowout,
                                                                    u8 *__restrict__ bwt, u32 *__restrict__ primary,
                                                                    u8 *__restrict__ keep8) {
     const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1194,10 +1210,10 @@ __global__ void __launch_bounds__(256) resolve_small_groups_kernel(const u32 *__
             for (u32 x = 0; x < size; ++x) smaller += ext[x] < ext[nl] ? 1u : 0u;
     }
     keep8[j] = decided ? 0 : 1;
+    rowout[j] = decided ? g + smaller : g;  // what rank[s] has to say: the final row, or the group's first row
     if (decided) {
         const u32 row = g + smaller;
         sa[row] = s;
-        rank[s] = row;
         if (s == 0) *primary = row;
         if (bwt) {
             u8 c = 0;
@@ -1209,6 +1225,15 @@ __global__ void __launch_bounds__(256) resolve_small_groups_kernel(const u32 *__
             bwt[row] = c;
         }
     }
+}
+
+// rank[act[j]] = row[j]; short: [count, (suffix, row) ...]
+__global__ void __launch_bounds__(256) scatter_ranks_kernel(const u32 *__restrict__ act, const u32 *__restrict__ row, u32 m,
+                                                            const u32 *__restrict__ shorts, u32 *__restrict__ rank) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < m) rank[act[j]] = row[j];
+    if (j == 0 && shorts)
+        for (u32 i = 0; i < shorts[0]; ++i) rank[shorts[1 + 2 * i]] = shorts[2 + 2 * i];
 }
 
 // bytes (0 / 1) -> bitmap words, one thread per 64 elements
@@ -1273,13 +1298,14 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
 
     // ---- round 0, preferred: MSD bucket sort of 8-byte elements (round0_msd.cu) ----
     bool done0 = false;
+    const u32 *short_rank = nullptr;  // bucketed round 0: ranks of the short suffixes of oversize buckets
     u32 depth0 = 0;  // symbols every active group shares after round 0 (0: K)
     u64 *rk_free[2] = {nullptr, nullptr};  // large buffers that are dead after round 0 (round keys go there)
     {
         Round0Msd r0{};
         if (msd_make_plan(len, ix.sigma, b, r0.plan)) {
             Arena::Mark mk = ar.mark();
-            r0.bufA = keysA; r0.bufB = keysB; r0.rank = rank; r0.actbits = actbits;
+            r0.bufA = keysA; r0.bufB = keysB; r0.actbits = actbits;
             r0.d_primary = d_primary.ptr;
             done0 = round0_msd(ix, want_bwt, r0);
             if (done0) {
@@ -1296,6 +1322,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 ix.stats.shallow_buckets = r0.shallow_buckets;
                 ix.stats.shallow_elems = r0.shallow_buckets ? r0.shallow_elems : 0;
                 depth0 = r0.depth0;
+                short_rank = r0.short_rank;
                 // the active rows, in row order, with their group heads
                 t = ix.timer.begin("compact0", (double)len * 0.125);
                 m = count_active<true>((const u8 *)actbits, len, tile_counts, d_total, st);
@@ -1385,12 +1412,15 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
     // ---- doubling rounds over the active set ----
     u8 *bwt_rows = (want_bwt && bwt_in_sort) ? ix.bwt.ptr : nullptr;
     bool need_bwt_fix = false;
+    // the list as round 0 left it: what rank[] has to hold for its suffixes (round0_msd.cu writes no ranks)
+    const u32 *act0 = act, *row0 = grp;
+    const u32 m0 = m;
     if (m && (u64)m * 64 <= (u64)len && b <= 8 && !env_int("B200SA_NO_EXT_TIEBREAK", 0)) {
         // a small active set: groups of two to four chance collisions are decided by the next 64 bits of text
         t = ix.timer.begin("resolve_small", (double)m * 40.0);
         u8 *keep8 = ar.get<u8>((size_t)m + 64);
-        u32 *act_r = ar.get<u32>(m), *grp_r = ar.get<u32>(m);
-        resolve_small_groups_kernel<<<div_up_u(m, 256), 256, 0, st>>>(act, grp, m, ix.packed, b, K, n, sa, rank, bwt_rows,
+        u32 *act_r = ar.get<u32>(m), *grp_r = ar.get<u32>(m), *rowout = ar.get<u32>(m);
+        resolve_small_groups_kernel<<<div_up_u(m, 256), 256, 0, st>>>(act, grp, m, ix.packed, b, K, n, sa, rowout, bwt_rows,
                                                                       d_primary.ptr, keep8);
         KERNEL_CHECK();
         const u64 kw = ((u64)m + 63) / 64;
@@ -1400,9 +1430,20 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
         const u32 m2 = count_active<true>(headbits, m, tile_counts, d_total, st);
         if (m2) scatter_active<true>(headbits, act, grp, m, tile_counts, act_r, grp_r, st);
         ix.stats.resolved_small = m - m2;
+        row0 = rowout;
         act = act_r;
         grp = grp_r;
         m = m2;
+        ix.timer.end(t);
+    }
+    if (m && (done0 || row0 != grp)) {
+        // ranks of the suffixes that were active after round 0 (first row of their group, or their final row where
+        // the text decided); after the bucketed round 0 everything else is marked "not materialised" first.  A text
+        // without repeats never gets here: its few chance collisions are all decided above.
+        t = ix.timer.begin("rank_scatter", (double)m0 * 12.0 + (done0 ? (double)len * 4.0 : 0.0));
+        if (done0) CUDA_CHECK(cudaMemsetAsync(rank, 0xff, (size_t)len * 4, st));
+        scatter_ranks_kernel<<<div_up_u(m0, 256), 256, 0, st>>>(act0, row0, m0, short_rank, rank);
+        KERNEL_CHECK();
         ix.timer.end(t);
     }
     if (m) {
