@@ -373,7 +373,7 @@ __device__ __forceinline__ u64 bits_ending(const u64 *__restrict__ words, u64 en
     return nbits >= 64 ? v : (v & ((1ull << nbits) - 1ull));
 }
 
-template <bool SC, bool STATS>
+template <bool SC, bool STATS, bool PF = false>
 __global__ void __launch_bounds__(256) fm_search_dna_packed_kernel(OccView ov, CTable5 c5, TextCmp tc, KTable kt, u32 len,
                                                                    const u64 *__restrict__ pw, u32 m, u32 stride,
                                                                    u64 npat, u32 *__restrict__ outL,
@@ -422,6 +422,9 @@ __global__ void __launch_bounds__(256) fm_search_dna_packed_kernel(OccView ov, C
         const u32 s = tc.sa[L];
         if (STATS) ++n_sa;
         const u32 rem = (u32)i + 1u;
+        // nine reads in ten match to the end and then ask for ISA[s - rem]: start that fetch now, behind the
+        // text comparison (B200SA_SEARCH_ISA_PREFETCH=0 turns it off)
+        if (PF && s >= rem) asm volatile("prefetch.global.L2 [%0];" ::"l"(tc.isa + (s - rem)));
         u32 k = 0;  // bases matched so far, from pattern[i] / text[s-1] downwards
         u64 t_idx = ~0ull, t_word = 0;
         bool mismatch = false;
@@ -519,7 +522,9 @@ void fm_search_packed(const DeviceIndex &ix, const u8 *d_packed, u32 m, u32 stri
         if (sc) fm_search_dna_packed_kernel<true, true><<<blocks, 256, 0, st>>>(ov, c5, tc, kt, ix.len, pw, m, stride, npat, d_L, d_R, d_stats);
         else fm_search_dna_packed_kernel<false, true><<<blocks, 256, 0, st>>>(ov, c5, tc, kt, ix.len, pw, m, stride, npat, d_L, d_R, d_stats);
     } else if (sc) {
-        fm_search_dna_packed_kernel<true, false><<<blocks, 256, 0, st>>>(ov, c5, tc, kt, ix.len, pw, m, stride, npat, d_L, d_R, nullptr);
+        static const bool pf = !(getenv("B200SA_SEARCH_ISA_PREFETCH") && atoi(getenv("B200SA_SEARCH_ISA_PREFETCH")) == 0);
+        if (pf) fm_search_dna_packed_kernel<true, false, true><<<blocks, 256, 0, st>>>(ov, c5, tc, kt, ix.len, pw, m, stride, npat, d_L, d_R, nullptr);
+        else fm_search_dna_packed_kernel<true, false, false><<<blocks, 256, 0, st>>>(ov, c5, tc, kt, ix.len, pw, m, stride, npat, d_L, d_R, nullptr);
     } else {
         fm_search_dna_packed_kernel<false, false><<<blocks, 256, 0, st>>>(ov, c5, tc, kt, ix.len, pw, m, stride, npat, d_L, d_R, nullptr);
     }
