@@ -1173,18 +1173,23 @@ __global__ void __launch_bounds__(256) bwt_fix_kernel(const u32 *__restrict__ ac
 // Small groups decided by the text.  After round 0 of a text without long repeats the active set is a
 // sprinkle of groups of two to four suffixes that share their K symbols by chance (3 Gbp of random
 // ACGT: 8 million suffixes, 0.27 %); a doubling round for them costs gathers with recovered ranks, a
-// radix sort and a scatter.  One look at the next 64 bits of text (32 symbols of DNA) decides almost
-// all of them: a member's final row is the group's first row plus the members with a smaller
-// extension.  A group is decided only as a whole (all extensions differ, none reaches the end of the
-// text); the rest stays active.  Run only while the active set is small -- in a repeat-rich text the
-// members of a group agree for thousands of symbols and the loads would be wasted.
-// keep8[j] = 1: element j stays active.  rowout[j]: the rank to materialise for element j.
+// radix sort and a scatter.  One look at the next 64 bits of text (32 symbols of DNA) orders such a
+// group: a member's row is the group's first row plus the members with a smaller extension (plus, among
+// equal extensions, the ones listed before it).  Members whose extension is unique are final; members
+// that agree on it too (copies of a repeat) stay active as a sub-group.  That also takes the chance
+// collisions OUT of the groups of a repeat-rich text -- a group {copy, copy, chance collision} would
+// otherwise break every chain that runs through it (chain_flags_kernel) -- so the kernel runs on large
+// active sets too, where it skips the pairs (two copies of a repeat agree for thousands of symbols: the
+// loads would be wasted).  A group one of whose windows reaches the end of the text is left alone.
+// Outputs by list slot (a permutation inside the group's slots): act_out, row_out (the rank to
+// materialise: first row of the sub-group = final row of a unique member), keep8 (1: stays active).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) resolve_small_groups_kernel(const u32 *__restrict__ act, const u32 *__restrict__ grp,
                                                                    u32 m, const u64 *__restrict__ packed, int bits, int K,
-                                                                   u32 n, u32 *__restrict__ sa, u32 *__restrict__ rowout,
+                                                                   u32 n, int skip_pairs, u32 *__restrict__ sa,
+                                                                   u32 *__restrict__ act_out, u32 *__restrict__ row_out,
                                                                    u8 *__restrict__ bwt, u32 *__restrict__ primary,
-                                                                   u8 *__restrict__ keep8) {
+                                                                   u8 *__restrict__ keep8, u32 *__restrict__ nresolved) {
     const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
     const u32 g = grp[j], s = act[j];
@@ -1192,38 +1197,45 @@ __global__ void __launch_bounds__(256) resolve_small_groups_kernel(const u32 *__
     u32 nl = 0, nr = 0;
     while (nl < 4u && j >= (u64)nl + 1 && grp[j - nl - 1] == g) ++nl;
     while (nr < 4u && j + nr + 1 < m && grp[j + nr + 1] == g) ++nr;
-    bool decided = nl + nr + 1u <= 4u;
+    const u32 size = nl + nr + 1u;
+    bool look = size <= 4u && !(skip_pairs && size == 2u);
     const u32 span = 64u / (u32)bits;
-    u32 smaller = 0;
-    if (decided) {
-        u64 ext[4];
-        const u32 size = nl + nr + 1u;
-        for (u32 x = 0; x < size && decided; ++x) {
-            const u32 t = act[j - nl + x];
-            decided = (u64)t + (u64)K + span <= (u64)n;
-            if (decided) ext[x] = window_at(packed, (u64)t + (u64)K, bits);
-        }
-        for (u32 x = 0; x < size && decided; ++x)
-            for (u32 y = x + 1; y < size; ++y)
-                if (ext[x] == ext[y]) decided = false;
-        if (decided)
-            for (u32 x = 0; x < size; ++x) smaller += ext[x] < ext[nl] ? 1u : 0u;
+    u64 ext[4];
+    for (u32 x = 0; x < size && look; ++x) {
+        const u32 t = act[j - nl + x];
+        look = (u64)t + (u64)K + span <= (u64)n;
+        if (look) ext[x] = window_at(packed, (u64)t + (u64)K, bits);
     }
-    keep8[j] = decided ? 0 : 1;
-    rowout[j] = decided ? g + smaller : g;  // what rank[s] has to say: the final row, or the group's first row
-    if (decided) {
-        const u32 row = g + smaller;
-        sa[row] = s;
-        if (s == 0) *primary = row;
-        if (bwt) {
-            u8 c = 0;
-            if (s) {
-                const u64 bitpos = (u64)(s - 1) * bits;
-                const u64 w = packed[bitpos >> 6];
-                c = (u8)(((w >> (64 - bits - (unsigned)(bitpos & 63))) & ((1u << bits) - 1u)) + 1u);
-            }
-            bwt[row] = c;
+    if (!look) {  // untouched
+        act_out[j] = s;
+        row_out[j] = g;
+        keep8[j] = 1;
+        return;
+    }
+    u32 smaller = 0, eq_before = 0, eq_total = 0;
+    for (u32 x = 0; x < size; ++x) {
+        smaller += ext[x] < ext[nl] ? 1u : 0u;
+        if (ext[x] == ext[nl]) {
+            ++eq_total;
+            eq_before += x < nl ? 1u : 0u;
         }
+    }
+    const u64 slot = j - nl + smaller + eq_before;
+    const u32 row = g + smaller + eq_before;
+    act_out[slot] = s;
+    row_out[slot] = g + smaller;
+    keep8[slot] = eq_total > 1u ? 1 : 0;
+    if (eq_total == 1u) atomicAdd(nresolved, 1u);
+    sa[row] = s;
+    if (s == 0) *primary = row;
+    if (bwt) {
+        u8 c = 0;
+        if (s) {
+            const u64 bitpos = (u64)(s - 1) * bits;
+            const u64 w = packed[bitpos >> 6];
+            c = (u8)(((w >> (64 - bits - (unsigned)(bitpos & 63))) & ((1u << bits) - 1u)) + 1u);
+        }
+        bwt[row] = c;
     }
 }
 
@@ -1414,29 +1426,44 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
     bool need_bwt_fix = false;
     // the list as round 0 left it: what rank[] has to hold for its suffixes (round0_msd.cu writes no ranks)
     const u32 *act0 = act, *row0 = grp;
+    const u32 *const row_first = grp;
     const u32 m0 = m;
-    if (m && (u64)m * 64 <= (u64)len && b <= 8 && !env_int("B200SA_NO_EXT_TIEBREAK", 0)) {
-        // a small active set: groups of two to four chance collisions are decided by the next 64 bits of text
+    if (m && b <= 8 && !env_int("B200SA_NO_EXT_TIEBREAK", 0)) {
+        // groups of two to four equal keys are ordered by the next 64 bits of text (pairs only while the active set
+        // is small: in a large one they are copies of repeats)
         t = ix.timer.begin("resolve_small", (double)m * 40.0);
         u8 *keep8 = ar.get<u8>((size_t)m + 64);
-        u32 *act_r = ar.get<u32>(m), *grp_r = ar.get<u32>(m), *rowout = ar.get<u32>(m);
-        resolve_small_groups_kernel<<<div_up_u(m, 256), 256, 0, st>>>(act, grp, m, ix.packed, b, K, n, sa, rowout, bwt_rows,
-                                                                      d_primary.ptr, keep8);
+        u32 *act_p = ar.get<u32>(m), *row_p = ar.get<u32>(m);
+        u32 *d_nres = ar.get<u32>(1);
+        CUDA_CHECK(cudaMemsetAsync(d_nres, 0, 4, st));
+        const int skip_pairs = (u64)m * 64 > (u64)len ? 1 : 0;
+        resolve_small_groups_kernel<<<div_up_u(m, 256), 256, 0, st>>>(act, grp, m, ix.packed, b, K, n, skip_pairs, sa, act_p,
+                                                                      row_p, bwt_rows, d_primary.ptr, keep8, d_nres);
         KERNEL_CHECK();
-        const u64 kw = ((u64)m + 63) / 64;
-        CUDA_CHECK(cudaMemsetAsync(headbits, 0, (kw + 2) * 8, st));
-        bytes_to_bits_kernel<<<div_up_u(kw, 256), 256, 0, st>>>(keep8, m, (u64 *)headbits, kw);
-        KERNEL_CHECK();
-        const u32 m2 = count_active<true>(headbits, m, tile_counts, d_total, st);
-        if (m2) scatter_active<true>(headbits, act, grp, m, tile_counts, act_r, grp_r, st);
-        ix.stats.resolved_small = m - m2;
-        row0 = rowout;
-        act = act_r;
-        grp = grp_r;
-        m = m2;
+        u32 nres = 0;
+        read_back(&nres, d_nres, 4, st);
+        ix.stats.resolved_small = nres;
+        // (the permuted list replaces the old one even when nothing was decided: sub-groups may have formed)
+        act0 = act_p;
+        row0 = row_p;
+        if (nres) {
+            u32 *act_r = ar.get<u32>(m - nres), *grp_r = ar.get<u32>(m - nres);
+            const u64 kw = ((u64)m + 63) / 64;
+            CUDA_CHECK(cudaMemsetAsync(headbits, 0, (kw + 2) * 8, st));
+            bytes_to_bits_kernel<<<div_up_u(kw, 256), 256, 0, st>>>(keep8, m, (u64 *)headbits, kw);
+            KERNEL_CHECK();
+            const u32 m2 = count_active<true>(headbits, m, tile_counts, d_total, st);
+            if (m2) scatter_active<true>(headbits, act_p, row_p, m, tile_counts, act_r, grp_r, st);
+            act = act_r;
+            grp = grp_r;
+            m = m2;
+        } else {
+            act = act_p;
+            grp = row_p;
+        }
         ix.timer.end(t);
     }
-    if (m && (done0 || row0 != grp)) {
+    if (m && (done0 || row0 != row_first)) {
         // ranks of the suffixes that were active after round 0 (first row of their group, or their final row where
         // the text decided); after the bucketed round 0 everything else is marked "not materialised" first.  A text
         // without repeats never gets here: its few chance collisions are all decided above.
