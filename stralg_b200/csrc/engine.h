@@ -32,6 +32,7 @@ struct BuildStats {
     u32 chain_rounds;    // doubling rounds that used chain offsets (sa_build.cu: chain_flags_kernel)
     u64 chain_elems;     // suffixes whose group "continued", summed over those rounds
     u32 resolved_small;  // suffixes in groups of 2..4 equal keys that the next 64 bits of text decided after round 0
+    u64 small_path_elems; // list elements ordered inside their tile (groups of up to 64), summed over rounds
 };
 
 // Occurrence-table layouts

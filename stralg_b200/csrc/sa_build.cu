@@ -1058,6 +1058,203 @@ __global__ void __launch_bounds__(CP_NT) scatter_active_kernel(const u8 *__restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// Small groups of a doubling round, ordered where they stand.  The list is grouped, a group's members
+// occupy consecutive slots AND consecutive suffix-array rows, and most groups of a text with repeats are
+// tiny (two copies of a segment: pairs).  A radix sort of (group, rank) keys moves every element eight
+// times to settle an order that each group can find among its own few members.  A tile owns RS_STEP
+// consecutive slots and loads RS_HALO more on both sides, so every group of up to RS_GMAX members that
+// touches its slots is seen whole (a group that straddles two tiles is ordered by both, identically;
+// each writes only the slots it owns): a member's new place is the group's first slot plus the members
+// with a smaller key plus the equal ones before it.  Written per owned slot: the suffix now standing
+// there, its new group head (= new rank), the bitmaps "starts a group" and "not handled here" (larger
+// groups, groups cut by the window: they go through the radix sort as before); per suffix: its row in
+// the suffix array and its rank where it changed.
+// ---------------------------------------------------------------------------------------------
+static constexpr int RS_NT = 256, RS_IPT = 10, RS_WIN = RS_NT * RS_IPT;  // 2560 slots loaded
+static constexpr int RS_HALO = 512, RS_STEP = RS_WIN - 2 * RS_HALO;      // 1536 slots owned (24 words of 64)
+static constexpr u32 RS_GMAX = 64;
+
+struct SmallArgs {
+    const u32 *act, *grp;
+    const u64 *keys;
+    u32 m;
+    int lo_bits;
+    u32 *sa, *rank;
+    u32 *vals_out, *newgrp_out;
+    u64 *headbits64, *notdone64;
+    u32 *primary;
+    u32 *handled;  // [1] slots handled by this path
+};
+
+__global__ void __launch_bounds__(RS_NT) round_small_kernel(SmallArgs a) {
+    __shared__ u32 lo_s[RS_WIN];
+    __shared__ u32 glast_s[RS_WIN];  // by window index of a group head: last window index of the group
+    __shared__ u32 gok_s[RS_WIN];    // by window index of a group head: the group lies inside the window
+    __shared__ unsigned long long hw_s[RS_STEP / 64], dw_s[RS_STEP / 64];
+    __shared__ u32 wmax[RS_NT / 32];
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u64 own0 = (u64)blockIdx.x * RS_STEP, own1 = min((u64)a.m, own0 + RS_STEP);
+    const u64 w0 = own0 >= (u64)RS_HALO ? own0 - RS_HALO : 0ull, w1 = min((u64)a.m, own0 + RS_STEP + RS_HALO);
+    const u32 wn = (u32)(w1 - w0);
+    const u32 i0 = tid * RS_IPT;
+    const u32 lomask = a.lo_bits >= 32 ? 0xffffffffu : ((1u << a.lo_bits) - 1u);
+    u32 s[RS_IPT], g[RS_IPT], lo[RS_IPT], hidx[RS_IPT];
+    u32 gprev = 0;
+    const bool has_prev = i0 < wn && w0 + i0 > 0;
+    if (has_prev) gprev = a.grp[w0 + i0 - 1];
+#pragma unroll
+    for (int q = 0; q < RS_IPT; ++q) {
+        const u32 i = i0 + q;
+        s[q] = i < wn ? a.act[w0 + i] : 0u;
+        g[q] = i < wn ? a.grp[w0 + i] : 0u;
+        lo[q] = i < wn ? (u32)a.keys[w0 + i] & lomask : 0u;
+        if (i < wn) {
+            lo_s[i] = lo[q];
+            glast_s[i] = 0;
+            gok_s[i] = 0;
+        }
+    }
+    if (tid < RS_STEP / 64) {
+        hw_s[tid] = 0ull;
+        dw_s[tid] = 0ull;
+    }
+    // window index + 1 of the latest group head at or before each element (0: the group began before the window)
+    u32 run = 0;
+    {
+        u32 pg = gprev;
+#pragma unroll
+        for (int q = 0; q < RS_IPT; ++q) {
+            const u32 i = i0 + q;
+            const bool head = i < wn && (w0 + i == 0 || g[q] != pg);
+            if (head) run = i + 1u;
+            hidx[q] = run;
+            pg = g[q];
+        }
+    }
+    u32 ex = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, ex, o);
+        if (lane >= (u32)o) ex = max(ex, t);
+    }
+    if (lane == 31) wmax[warp] = ex;
+    u32 pre = __shfl_up_sync(0xffffffffu, ex, 1);
+    if (lane == 0) pre = 0;
+    __syncthreads();
+    for (u32 w = 0; w < warp; ++w) pre = max(pre, wmax[w]);
+#pragma unroll
+    for (int q = 0; q < RS_IPT; ++q)
+        if (hidx[q] == 0) hidx[q] = pre;
+#pragma unroll
+    for (int q = 0; q < RS_IPT; ++q) {
+        const u32 i = i0 + q;
+        if (i < wn && hidx[q]) {
+            if (hidx[q] == i + 1u) gok_s[i] = 1u;
+            atomicMax(&glast_s[hidx[q] - 1u], i);
+        }
+    }
+    __syncthreads();
+    // the last group loaded must end inside the window
+    if (wn > i0 && wn - 1u < i0 + RS_IPT) {
+        const int q = (int)(wn - 1u - i0);
+        if (w1 < a.m && a.grp[w1] == g[q] && hidx[q]) gok_s[hidx[q] - 1u] = 0u;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int q = 0; q < RS_IPT; ++q) {
+        const u32 i = i0 + q;
+        if (i >= wn || !hidx[q]) continue;
+        const u32 h = hidx[q] - 1u;
+        if (!gok_s[h]) continue;
+        const u32 size = glast_s[h] - h + 1u;
+        if (size > RS_GMAX) continue;
+        u32 smaller = 0, eq_before = 0;
+        const u32 mine = lo[q];
+        for (u32 k = h; k < h + size; ++k) {
+            const u32 lk = lo_s[k];
+            smaller += lk < mine ? 1u : 0u;
+            eq_before += (lk == mine && k < i) ? 1u : 0u;
+        }
+        const u64 slot = w0 + h + smaller + eq_before;
+        if (slot < own0 || slot >= own1) continue;
+        const u32 newrank = g[q] + smaller, row = newrank + eq_before;
+        a.vals_out[slot] = s[q];
+        a.newgrp_out[slot] = newrank;
+        a.sa[row] = s[q];
+        if (smaller) a.rank[s[q]] = newrank;  // (members that stay in front keep the group head as their rank)
+        if (s[q] == 0) *a.primary = row;
+        const u32 bit = (u32)(slot - own0);
+        atomicOr(&dw_s[bit >> 6], 1ull << (bit & 63u));
+        if (eq_before == 0) atomicOr(&hw_s[bit >> 6], 1ull << (bit & 63u));
+    }
+    __syncthreads();
+    if (tid < RS_STEP / 64) {
+        const u64 base = own0 + (u64)tid * 64;
+        if (base < a.m) {
+            const u64 valid = a.m - base >= 64 ? ~0ull : ((1ull << (a.m - base)) - 1ull);
+            const u64 done = dw_s[tid];
+            // a slot not handled here counts as a group of its own for the compaction of THIS path's survivors
+            a.headbits64[base >> 6] = (u64)hw_s[tid] | ~done;
+            a.notdone64[base >> 6] = ~done & valid;
+            const u32 c = (u32)__popcll(done);
+            if (c) atomicAdd(a.handled, c);
+        }
+    }
+}
+
+// bitmap -> compacted (key, value) pairs in list order (the elements the small-group path left alone)
+__global__ void __launch_bounds__(CP_NT) scatter_pairs_kernel(const u8 *__restrict__ bits, const u64 *__restrict__ keys,
+                                                              const u32 *__restrict__ vals, u32 m, u32 sub,
+                                                              const u32 *__restrict__ tile_offsets,
+                                                              u64 *__restrict__ kout, u32 *__restrict__ vout) {
+    __shared__ u32 wsum[CP_NT / 32];
+    u32 base = tile_offsets[blockIdx.x];
+    const u32 lane = lane_id();
+    const u32 lt = lanemask_lt();
+    for (u32 q = 0; q < sub; ++q) {
+        const u64 word = ((u64)blockIdx.x * sub + q) * CP_NT + threadIdx.x;
+        const u64 mask = raw_mask(bits, word, m);
+        const u32 c = __popcll(mask);
+        u32 incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        if (lane == 31) wsum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        u32 wb = 0, total = 0;
+        for (unsigned w = 0; w < CP_NT / 32; ++w) {
+            if (w < (threadIdx.x >> 5)) wb += wsum[w];
+            total += wsum[w];
+        }
+        const u32 o = base + wb + incl - c;
+        base += total;
+        __syncthreads();
+        if (!__any_sync(0xffffffffu, mask != 0)) continue;
+        const u64 word0 = word - lane;
+#pragma unroll 4
+        for (int w = 0; w < 32; ++w) {
+            const u64 mw = __shfl_sync(0xffffffffu, mask, w);
+            const u32 ow = __shfl_sync(0xffffffffu, o, w);
+            if (!mw) continue;
+            const u64 bw = (word0 + (u64)w) * 64;
+            const u32 lo = (u32)mw, hi = (u32)(mw >> 32);
+            if ((lo >> lane) & 1u) {
+                const u32 at = ow + (u32)__popc(lo & lt);
+                kout[at] = keys[bw + lane];
+                vout[at] = vals[bw + lane];
+            }
+            if ((hi >> lane) & 1u) {
+                const u32 at = ow + (u32)__popc(lo) + (u32)__popc(hi & lt);
+                kout[at] = keys[bw + 32 + lane];
+                vout[at] = vals[bw + 32 + lane];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host orchestration
 // ---------------------------------------------------------------------------------------------
 static int env_int(const char *name, int dflt) {
@@ -1495,25 +1692,33 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
         u64 h = depth0 ? (u64)depth0 : (u64)K;
         u32 huniform[8];
         const u32 bwt_small = std::max(1u, len / (u32)std::max(1, env_int("B200SA_BWT_ROUND_FRAC", 32)));
-        // chain offsets (see chain_flags_kernel): tried while the active set is a noticeable part of the
-        // text, dropped for good once a round finds few groups that continue
-        bool chain_on = env_int("B200SA_CHAIN", 1) != 0;
-        u8 *cont8 = nullptr, *cslot = nullptr;
-        u32 *chainkey = nullptr, *d_ncont = nullptr;
-        const size_t cont_bytes = (size_t)len + 2 * (size_t)CHAIN_CAP + 8192;
+        // One region serves the chain arrays (live from chain_flags to make_keys) and the outputs of the
+        // small-group path (live from there to the end of the round).
+        bool chain_on = env_int("B200SA_CHAIN", 1) != 0 &&
+                        (u64)m * (u64)std::max(1, env_int("B200SA_CHAIN_MIN_FRAC", 64)) >= (u64)len;
+        bool small_on = env_int("B200SA_SMALL_PATH", 1) != 0;
+        int small_pause = 0;  // rounds the small-group path sits out after a round in which it found almost nothing
+        const size_t cont_bytes = ((size_t)len + 2 * (size_t)CHAIN_CAP + 8192 + 511) & ~(size_t)511;
+        const size_t m_init = m;
+        const size_t chain_bytes = chain_on ? cont_bytes + (size_t)len * 4 + ((m_init + 511) & ~(size_t)511) : 0;
+        const size_t small_bytes = small_on ? 3 * ((m_init * 4 + 511) & ~(size_t)511) : 0;
+        u8 *region = ar.get<u8>(std::max<size_t>(std::max(chain_bytes, small_bytes), 512));
+        u8 *cont8 = region, *cslot = region + cont_bytes + (size_t)len * 4;
+        u32 *chainkey = (u32 *)(region + cont_bytes);
+        u32 *valsT = (u32 *)region, *newgrpT = (u32 *)(region + ((m_init * 4 + 511) & ~(size_t)511)),
+            *bvals = (u32 *)(region + 2 * ((m_init * 4 + 511) & ~(size_t)511));
+        u32 *d_ncont = ar.get<u32>(2), *d_handled = d_ncont + 1;
+        const size_t bm_bytes = ((m_init + 63) / 64 + 2) * 8;
+        u8 *notdone = ar.get<u8>(bm_bytes), *headB = ar.get<u8>(bm_bytes);
         while (m > 0) {
             ix.stats.rounds++;
             ix.stats.sorted_total += m;
             CUDA_CHECK(cudaMemsetAsync(d_lazy, 0, 4, st));
+            // ---- chain offsets (see chain_flags_kernel): tried while the active set is a noticeable part of the
+            // text, dropped for good once a round finds few groups that continue ----
             bool use_chain = false;
             if (chain_on && h <= (u64)CHAIN_CAP && (u64)m * (u64)std::max(1, env_int("B200SA_CHAIN_MIN_FRAC", 64)) >= (u64)len) {
                 t = ix.timer.begin("chain_flags", (double)m * 13.0 + (double)len);
-                if (!cont8) {
-                    cont8 = ar.get<u8>(cont_bytes);
-                    chainkey = ar.get<u32>(len);
-                    cslot = ar.get<u8>(m);  // (m only shrinks)
-                    d_ncont = ar.get<u32>(1);
-                }
                 CUDA_CHECK(cudaMemsetAsync(cont8, 0, cont_bytes, st));
                 CUDA_CHECK(cudaMemsetAsync(cslot, 0, m, st));
                 CUDA_CHECK(cudaMemsetAsync(d_ncont, 0, 4, st));
@@ -1541,49 +1746,114 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 act, grp, m, lr, h, lo_bits, use_chain ? cslot : nullptr, chainkey, rkA, d_lazy);
             KERNEL_CHECK();
             ix.timer.end(t);
-            int npass = (key_bits + RB - 1) / RB;
-            t = ix.timer.begin("round_hist", (double)m * 8.0);
-            S::histogram(rkA, m, 0, key_bits, npass, hist, st);
-            S::scan(hist, m, npass, uniform, st);
-            read_back(huniform, uniform, (size_t)npass * 4, st);
-            ix.timer.end(t);
-            u64 *rin = rkA, *rout = rkB;
-            u32 *ain = act, *aout = act2;
-            for (int p = 0; p < npass; ++p) {
-                if (huniform[p]) continue;
-                int bits_here = std::min(RB, key_bits - p * RB);
-                t = ix.timer.begin("radix_pass", (double)m * 24.0);
-                S::pass(rin, ain, rout, aout, m, p * RB, bits_here, hist + (size_t)p * BINS, lookback, ticket, st);
+
+            // ---- groups of up to RS_GMAX members are ordered where they stand (round_small_kernel) ----
+            u32 handled = 0;
+            if (small_on && small_pause == 0) {
+                t = ix.timer.begin("round_small", (double)m * 28.0);
+                const u64 kw = ((u64)m + 63) / 64;
+                CUDA_CHECK(cudaMemsetAsync(headbits + kw * 8, 0, 16, st));
+                CUDA_CHECK(cudaMemsetAsync(notdone + kw * 8, 0, 16, st));
+                CUDA_CHECK(cudaMemsetAsync(d_handled, 0, 4, st));
+                SmallArgs sm{};
+                sm.act = act; sm.grp = grp; sm.keys = rkA; sm.m = m; sm.lo_bits = lo_bits; sm.sa = sa; sm.rank = rank;
+                sm.vals_out = valsT; sm.newgrp_out = newgrpT; sm.headbits64 = (u64 *)headbits; sm.notdone64 = (u64 *)notdone;
+                sm.primary = d_primary.ptr; sm.handled = d_handled;
+                round_small_kernel<<<div_up_u(m, RS_STEP), RS_NT, 0, st>>>(sm);
+                KERNEL_CHECK();
+                read_back(&handled, d_handled, 4, st);
                 ix.timer.end(t);
-                ix.stats.passes_elems += m;
-                std::swap(rin, rout);
-                std::swap(ain, aout);
+                ix.stats.small_path_elems += handled;
+                if ((u64)handled * 32 < (u64)m) small_pause = 3;  // (periodic texts: a few giant groups)
+                if (handled && bwt_rows) need_bwt_fix = true;     // (this path does not write BWT rows)
+            } else if (small_pause > 0) {
+                --small_pause;
             }
-            t = ix.timer.begin("round_rank", (double)m * 20.0);
-            size_t hbm = (((size_t)m + 63) / 64 + 2) * 8;
-            CUDA_CHECK(cudaMemsetAsync(headbits, 0, hbm, st));
-            RankArgs rr{};
-            rr.keys = rin; rr.vals = ain; rr.m = m; rr.gs = lo_bits; rr.keymask = ~0ull; rr.K0 = 0; rr.n = n;
-            rr.rank = rank; rr.newgrp = newgrp; rr.scatter_all = 0; rr.sa_out = sa; rr.headbits = headbits;
-            // BWT rows of moved suffixes: one gather per element and round -- kept in the rounds while the
-            // active set is small, otherwise one pass over the rows of round 0's active set at the end
-            rr.bwt = m <= bwt_small ? bwt_rows : nullptr;
-            if (bwt_rows && !rr.bwt) need_bwt_fix = true;
-            rr.prev_shift = 0; rr.packed = ix.packed; rr.bits = b;
-            rr.primary = d_primary.ptr;
-            rank_kernel<<<div_up_u(m, RK_TILE), RK_NT, 0, st>>>(rr);
-            KERNEL_CHECK();
-            ix.timer.end(t);
-            // next active set goes to whichever value buffer does not hold the sorted list
+
+            // ---- everything else: radix sort of (group, rank) keys, new ranks from the sorted list ----
+            const u32 mb = m - handled;
+            const u64 *bk = rkA;   // keys / values of the elements that go through the sort
+            const u32 *bv = act;
+            u64 *k_other = rkB;
+            u32 *v_other = act2;
+            if (handled && mb) {
+                t = ix.timer.begin("compact_big", (double)m * 0.125 + (double)mb * 24.0);
+                const u32 cnt = count_active<true>(notdone, m, tile_counts, d_total, st);
+                if (cnt != mb) throw std::runtime_error("small-group path: slot accounting is inconsistent (internal error)");
+                const u32 sub = compaction_sub(m);
+                scatter_pairs_kernel<<<div_up_u(m, (u64)CP_TILE * sub), CP_NT, 0, st>>>(notdone, rkA, act, m, sub, tile_counts,
+                                                                                       rkB, bvals);
+                KERNEL_CHECK();
+                ix.timer.end(t);
+                bk = rkB; bv = bvals; k_other = rkA; v_other = act2;
+            }
+            u8 *hb_big = handled ? headB : headbits;
+            const u32 *sorted_vals = nullptr;
+            if (mb) {
+                int npass = (key_bits + RB - 1) / RB;
+                t = ix.timer.begin("round_hist", (double)mb * 8.0);
+                S::histogram(bk, mb, 0, key_bits, npass, hist, st);
+                S::scan(hist, mb, npass, uniform, st);
+                read_back(huniform, uniform, (size_t)npass * 4, st);
+                ix.timer.end(t);
+                u64 *rin = const_cast<u64 *>(bk), *rout = k_other;
+                u32 *ain = const_cast<u32 *>(bv), *aout = v_other;
+                for (int p = 0; p < npass; ++p) {
+                    if (huniform[p]) continue;
+                    int bits_here = std::min(RB, key_bits - p * RB);
+                    t = ix.timer.begin("radix_pass", (double)mb * 24.0);
+                    S::pass(rin, ain, rout, aout, mb, p * RB, bits_here, hist + (size_t)p * BINS, lookback, ticket, st);
+                    ix.timer.end(t);
+                    ix.stats.passes_elems += mb;
+                    std::swap(rin, rout);
+                    std::swap(ain, aout);
+                }
+                t = ix.timer.begin("round_rank", (double)mb * 20.0);
+                size_t hbm = (((size_t)mb + 63) / 64 + 2) * 8;
+                CUDA_CHECK(cudaMemsetAsync(hb_big, 0, hbm, st));
+                RankArgs rr{};
+                rr.keys = rin; rr.vals = ain; rr.m = mb; rr.gs = lo_bits; rr.keymask = ~0ull; rr.K0 = 0; rr.n = n;
+                rr.rank = rank; rr.newgrp = newgrp; rr.scatter_all = 0; rr.sa_out = sa; rr.headbits = hb_big;
+                // BWT rows of moved suffixes: one gather per element and round -- kept in the rounds while the
+                // active set is small, otherwise one pass over the rows of round 0's active set at the end
+                rr.bwt = m <= bwt_small ? bwt_rows : nullptr;
+                if (bwt_rows && !rr.bwt) need_bwt_fix = true;
+                rr.prev_shift = 0; rr.packed = ix.packed; rr.bits = b;
+                rr.primary = d_primary.ptr;
+                rank_kernel<<<div_up_u(mb, RK_TILE), RK_NT, 0, st>>>(rr);
+                KERNEL_CHECK();
+                ix.timer.end(t);
+                sorted_vals = ain;
+            }
+            // ---- next active set: the survivors of both paths, one after the other (groups stay contiguous) ----
             t = ix.timer.begin("compact", (double)m * 4.0);
-            u32 m2 = count_active<false>(headbits, m, tile_counts, d_total, st);
-            if (m2) scatter_active<false>(headbits, ain, newgrp, m, tile_counts, aout, grp2, st);
+            u32 m2 = 0;
+            if (!handled) {
+                // (the whole list went through the sort: its survivors go to the value buffer the sort left free)
+                u32 *dst = sorted_vals == act ? act2 : const_cast<u32 *>(act);
+                m2 = count_active<false>(hb_big, m, tile_counts, d_total, st);
+                if (m2) scatter_active<false>(hb_big, sorted_vals, newgrp, m, tile_counts, dst, grp2, st);
+                if (dst == act2) std::swap(act, act2);
+            } else {
+                // (`act` was read for the last time by the compaction of the sorted part)
+                u32 *dst = sorted_vals == act ? act2 : const_cast<u32 *>(act);
+                if (mb && sorted_vals == act) {
+                    // the sorted values sit in `act` itself: survivors go to act2
+                }
+                const u32 mA = count_active<false>(headbits, m, tile_counts, d_total, st);
+                if (mA) scatter_active<false>(headbits, valsT, newgrpT, m, tile_counts, dst, grp2, st);
+                u32 mB = 0;
+                if (mb) {
+                    mB = count_active<false>(hb_big, mb, tile_counts, d_total, st);
+                    if (mB) scatter_active<false>(hb_big, sorted_vals, newgrp, mb, tile_counts, dst + mA, grp2 + mA, st);
+                }
+                m2 = mA + mB;
+                if (dst == act2) std::swap(act, act2);
+            }
             ix.timer.end(t);
             u32 nlazy = 0;
             read_back(&nlazy, d_lazy, 4, st);
             ix.stats.lazy_lookups += nlazy;
-            act = aout;
-            act2 = ain;
             std::swap(grp, grp2);
             m = m2;
             h *= 2;

@@ -91,6 +91,8 @@ MODES = {
     "chain_always": {"B200SA_CHAIN_MIN_FRAC": "100000000", "B200SA_CHAIN_USE_FRAC": "100000000"},
     "chain_always_shallow": {"B200SA_CHAIN_MIN_FRAC": "100000000", "B200SA_CHAIN_USE_FRAC": "100000000", "B200SA_MSD_MORE_FRAC": "1", "B200SA_MSD_OVER_FRAC": "1"},
     "chain_off": {"B200SA_CHAIN": "0"},
+    # every group goes through the radix sort (no in-tile ordering of small groups, no text tie-break)
+    "all_radix": {"B200SA_SMALL_PATH": "0", "B200SA_NO_EXT_TIEBREAK": "1"},
 }
 
 

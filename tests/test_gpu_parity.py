@@ -68,6 +68,8 @@ ROUND0_MODES = {
     "lsd10": {"B200SA_ROUND0": "lsd", "B200SA_RADIX_BITS": "10"},
     # equal K-symbol keys are never decided by the next 64 bits of text in round 0 (all of them reach the rounds)
     "msd_noext": {"B200SA_NO_EXT_TIEBREAK": "1"},
+    "msd_all_radix": {"B200SA_SMALL_PATH": "0", "B200SA_NO_EXT_TIEBREAK": "1"},
+    "lsd8_noext": {"B200SA_ROUND0": "lsd", "B200SA_RADIX_BITS": "8", "B200SA_NO_EXT_TIEBREAK": "1"},
     # chain offsets in every doubling round, however small the active set (default: only large ones)
     "msd_chain": {"B200SA_CHAIN_MIN_FRAC": "100000000", "B200SA_CHAIN_USE_FRAC": "100000000", "B200SA_NO_EXT_TIEBREAK": "1"},
     "lsd8_chain": {"B200SA_ROUND0": "lsd", "B200SA_RADIX_BITS": "8", "B200SA_CHAIN_MIN_FRAC": "100000000", "B200SA_CHAIN_USE_FRAC": "100000000"},

@@ -58,6 +58,7 @@ if __name__ == "__main__":
                    "round0_mode": st["round0_mode"], "passes0": st["passes0"], "bucket_bits": st["bucket_bits"],
                    "shallow_buckets": st["shallow_buckets"], "shallow_elems": st["shallow_elems"],
                    "chain_rounds": st["chain_rounds"], "chain_elems": st["chain_elems"], "lazy": st["lazy_lookups"],
+                   "resolved_small": st["resolved_small"],
                    "sorted_total_x": round(st["sorted_total"] / (n + 1), 2),
                    "stages_ms": {k: [v[0], round(v[1], 2)] for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
                    "stages_total_ms": round(sum(v[1] for v in agg.values()), 1), "info": info}
