@@ -373,8 +373,9 @@ __device__ __forceinline__ u64 bits_ending(const u64 *__restrict__ words, u64 en
     return nbits >= 64 ? v : (v & ((1ull << nbits) - 1ull));
 }
 
-template <bool SC, bool STATS, bool PF = false>
-__global__ void __launch_bounds__(256) fm_search_dna_packed_kernel(OccView ov, CTable5 c5, TextCmp tc, KTable kt, u32 len,
+// MINB: resident CTAs per SM the register allocation aims at (8: 32 registers, every thread slot of the SM in use)
+template <bool SC, bool STATS, bool PF = false, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB) fm_search_dna_packed_kernel(OccView ov, CTable5 c5, TextCmp tc, KTable kt, u32 len,
                                                                    const u64 *__restrict__ pw, u32 m, u32 stride,
                                                                    u64 npat, u32 *__restrict__ outL,
                                                                    u32 *__restrict__ outR,
@@ -524,7 +525,9 @@ void fm_search_packed(const DeviceIndex &ix, const u8 *d_packed, u32 m, u32 stri
     } else if (sc) {
         // (measured, 3 Gbp / 10^8 reads: 15.7 ms with the prefetch against 13.6 ms without -- off unless asked for)
         static const bool pf = getenv("B200SA_SEARCH_ISA_PREFETCH") && atoi(getenv("B200SA_SEARCH_ISA_PREFETCH")) != 0;
+        static const int occ8 = getenv("B200SA_SEARCH_OCC8") ? atoi(getenv("B200SA_SEARCH_OCC8")) : 0;
         if (pf) fm_search_dna_packed_kernel<true, false, true><<<blocks, 256, 0, st>>>(ov, c5, tc, kt, ix.len, pw, m, stride, npat, d_L, d_R, nullptr);
+        else if (occ8) fm_search_dna_packed_kernel<true, false, false, 8><<<blocks, 256, 0, st>>>(ov, c5, tc, kt, ix.len, pw, m, stride, npat, d_L, d_R, nullptr);
         else fm_search_dna_packed_kernel<true, false, false><<<blocks, 256, 0, st>>>(ov, c5, tc, kt, ix.len, pw, m, stride, npat, d_L, d_R, nullptr);
     } else {
         fm_search_dna_packed_kernel<false, false><<<blocks, 256, 0, st>>>(ov, c5, tc, kt, ix.len, pw, m, stride, npat, d_L, d_R, nullptr);

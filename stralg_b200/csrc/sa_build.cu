@@ -432,6 +432,29 @@ __global__ void __launch_bounds__(256) make_keys_round_kernel(const u32 *__restr
     if (lane == 0 && nlazy) atomicAdd(lazy_count, nlazy);
 }
 
+// the same with complete ranks (dense mode): no recovery, no warp-cooperative scans -- a plain gather
+__global__ void __launch_bounds__(256) make_keys_dense_kernel(const u32 *__restrict__ act, const u32 *__restrict__ grp, u32 m,
+                                                              const u32 *__restrict__ rank, u64 h, u32 len, int lo_bits,
+                                                              const u8 *__restrict__ cslot,
+                                                              const u32 *__restrict__ chainkey, u64 *__restrict__ keys) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
+        const u32 s = act[j];
+        u64 lo = 0;
+        bool chained = false;
+        if (cslot && cslot[j]) {
+            const u32 ck = chainkey[s];
+            if (ck != RANK_NONE) {
+                lo = ck;
+                chained = true;
+            }
+        }
+        const u64 t = (u64)s + h;
+        if (!chained && t < len) lo = rank[t];
+        keys[j] = ((u64)grp[j] << lo_bits) | lo;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Chain offsets.  Plain doubling orders a group by the ranks h symbols ahead, h doubling per round:
 // two copies of a 6 000-symbol segment stay tied for eight rounds, all of their suffixes sorted again
@@ -1072,7 +1095,7 @@ __global__ void __launch_bounds__(CP_NT) scatter_active_kernel(const u8 *__restr
 // ---------------------------------------------------------------------------------------------
 static constexpr int RS_NT = 256, RS_IPT = 10, RS_WIN = RS_NT * RS_IPT;  // 2560 slots loaded
 static constexpr int RS_HALO = 512, RS_STEP = RS_WIN - 2 * RS_HALO;      // 1536 slots owned (24 words of 64)
-static constexpr u32 RS_GMAX = 64;
+static constexpr u32 RS_GMAX = 32;
 
 struct SmallArgs {
     const u32 *act, *grp;
@@ -1384,9 +1407,10 @@ __global__ void __launch_bounds__(256) bwt_fix_kernel(const u32 *__restrict__ ac
 __global__ void __launch_bounds__(256) resolve_small_groups_kernel(const u32 *__restrict__ act, const u32 *__restrict__ grp,
                                                                    u32 m, const u64 *__restrict__ packed, int bits, int K,
                                                                    u32 n, int skip_pairs, u32 *__restrict__ sa,
-                                                                   u32 *__restrict__ act_out, u32 *__restrict__ row_out,
-                                                                   u8 *__restrict__ bwt, u32 *__restrict__ primary,
-                                                                   u8 *__restrict__ keep8, u32 *__restrict__ nresolved) {
+                                                                   u32 *__restrict__ rank, u32 *__restrict__ act_out,
+                                                                   u32 *__restrict__ row_out, u8 *__restrict__ bwt,
+                                                                   u32 *__restrict__ primary, u8 *__restrict__ keep8,
+                                                                   u32 *__restrict__ nresolved) {
     const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
     const u32 g = grp[j], s = act[j];
@@ -1423,6 +1447,7 @@ __global__ void __launch_bounds__(256) resolve_small_groups_kernel(const u32 *__
     row_out[slot] = g + smaller;
     keep8[slot] = eq_total > 1u ? 1 : 0;
     if (eq_total == 1u) atomicAdd(nresolved, 1u);
+    if (rank) rank[s] = g + smaller;  // (ranks already materialised: LSD round 0)
     sa[row] = s;
     if (s == 0) *primary = row;
     if (bwt) {
@@ -1434,6 +1459,23 @@ __global__ void __launch_bounds__(256) resolve_small_groups_kernel(const u32 *__
         }
         bwt[row] = c;
     }
+}
+
+// how many list elements stand in groups the kernel above would look at (2..4 members; pairs optional)
+__global__ void __launch_bounds__(256) count_small_groups_kernel(const u32 *__restrict__ grp, u32 m, int skip_pairs,
+                                                                 u32 *__restrict__ count) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool look = false;
+    if (j < m) {
+        const u32 g = grp[j];
+        u32 nl = 0, nr = 0;
+        while (nl < 4u && j >= (u64)nl + 1 && grp[j - nl - 1] == g) ++nl;
+        while (nr < 4u && j + nr + 1 < m && grp[j + nr + 1] == g) ++nr;
+        const u32 size = nl + nr + 1u;
+        look = size <= 4u && !(skip_pairs && size == 2u);
+    }
+    const u32 c = __popc(__ballot_sync(0xffffffffu, look));
+    if ((threadIdx.x & 31u) == 0 && c) atomicAdd(count, c);
 }
 
 // rank[act[j]] = row[j]; short: [count, (suffix, row) ...]
@@ -1623,49 +1665,56 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
     bool need_bwt_fix = false;
     // the list as round 0 left it: what rank[] has to hold for its suffixes (round0_msd.cu writes no ranks)
     const u32 *act0 = act, *row0 = grp;
-    const u32 *const row_first = grp;
     const u32 m0 = m;
     if (m && b <= 8 && !env_int("B200SA_NO_EXT_TIEBREAK", 0)) {
         // groups of two to four equal keys are ordered by the next 64 bits of text (pairs only while the active set
         // is small: in a large one they are copies of repeats)
         t = ix.timer.begin("resolve_small", (double)m * 40.0);
-        u8 *keep8 = ar.get<u8>((size_t)m + 64);
-        u32 *act_p = ar.get<u32>(m), *row_p = ar.get<u32>(m);
-        u32 *d_nres = ar.get<u32>(1);
-        CUDA_CHECK(cudaMemsetAsync(d_nres, 0, 4, st));
+        u32 *d_nres = ar.get<u32>(2);
+        CUDA_CHECK(cudaMemsetAsync(d_nres, 0, 8, st));
         const int skip_pairs = (u64)m * 64 > (u64)len ? 1 : 0;
-        resolve_small_groups_kernel<<<div_up_u(m, 256), 256, 0, st>>>(act, grp, m, ix.packed, b, K, n, skip_pairs, sa, act_p,
-                                                                      row_p, bwt_rows, d_primary.ptr, keep8, d_nres);
+        count_small_groups_kernel<<<div_up_u(m, 256), 256, 0, st>>>(grp, m, skip_pairs, d_nres + 1);
         KERNEL_CHECK();
-        u32 nres = 0;
-        read_back(&nres, d_nres, 4, st);
-        ix.stats.resolved_small = nres;
-        // (the permuted list replaces the old one even when nothing was decided: sub-groups may have formed)
-        act0 = act_p;
-        row0 = row_p;
-        if (nres) {
-            u32 *act_r = ar.get<u32>(m - nres), *grp_r = ar.get<u32>(m - nres);
-            const u64 kw = ((u64)m + 63) / 64;
-            CUDA_CHECK(cudaMemsetAsync(headbits, 0, (kw + 2) * 8, st));
-            bytes_to_bits_kernel<<<div_up_u(kw, 256), 256, 0, st>>>(keep8, m, (u64 *)headbits, kw);
+        u32 nsmall = 0;
+        read_back(&nsmall, d_nres + 1, 4, st);
+        if (nsmall) {
+            u8 *keep8 = ar.get<u8>((size_t)m + 64);
+            u32 *act_p = ar.get<u32>(m), *row_p = ar.get<u32>(m);
+            resolve_small_groups_kernel<<<div_up_u(m, 256), 256, 0, st>>>(act, grp, m, ix.packed, b, K, n, skip_pairs, sa,
+                                                                          done0 ? nullptr : rank, act_p, row_p, bwt_rows,
+                                                                          d_primary.ptr, keep8, d_nres);
             KERNEL_CHECK();
-            const u32 m2 = count_active<true>(headbits, m, tile_counts, d_total, st);
-            if (m2) scatter_active<true>(headbits, act_p, row_p, m, tile_counts, act_r, grp_r, st);
-            act = act_r;
-            grp = grp_r;
-            m = m2;
-        } else {
-            act = act_p;
-            grp = row_p;
+            u32 nres = 0;
+            read_back(&nres, d_nres, 4, st);
+            ix.stats.resolved_small = nres;
+            // (the permuted list replaces the old one even when nothing was decided: sub-groups may have formed)
+            act0 = act_p;
+            row0 = row_p;
+            if (nres) {
+                u32 *act_r = ar.get<u32>(m - nres), *grp_r = ar.get<u32>(m - nres);
+                const u64 kw = ((u64)m + 63) / 64;
+                CUDA_CHECK(cudaMemsetAsync(headbits, 0, (kw + 2) * 8, st));
+                bytes_to_bits_kernel<<<div_up_u(kw, 256), 256, 0, st>>>(keep8, m, (u64 *)headbits, kw);
+                KERNEL_CHECK();
+                const u32 m2 = count_active<true>(headbits, m, tile_counts, d_total, st);
+                if (m2) scatter_active<true>(headbits, act_p, row_p, m, tile_counts, act_r, grp_r, st);
+                act = act_r;
+                grp = grp_r;
+                m = m2;
+            } else {
+                act = act_p;
+                grp = row_p;
+            }
         }
         ix.timer.end(t);
     }
-    if (m && (done0 || row0 != row_first)) {
-        // ranks of the suffixes that were active after round 0 (first row of their group, or their final row where
-        // the text decided); after the bucketed round 0 everything else is marked "not materialised" first.  A text
-        // without repeats never gets here: its few chance collisions are all decided above.
-        t = ix.timer.begin("rank_scatter", (double)m0 * 12.0 + (done0 ? (double)len * 4.0 : 0.0));
-        if (done0) CUDA_CHECK(cudaMemsetAsync(rank, 0xff, (size_t)len * 4, st));
+    if (m && done0) {
+        // bucketed round 0: ranks of the suffixes that were active after it (first row of their group, or their final
+        // row where the text decided); everything else is marked "not materialised" first.  A text without repeats
+        // never gets here: its few chance collisions are all decided above.  (LSD round 0: rank_kernel wrote the ranks,
+        // the kernel above kept them up to date.)
+        t = ix.timer.begin("rank_scatter", (double)m0 * 12.0 + (double)len * 4.0);
+        CUDA_CHECK(cudaMemsetAsync(rank, 0xff, (size_t)len * 4, st));
         scatter_ranks_kernel<<<div_up_u(m0, 256), 256, 0, st>>>(act0, row0, m0, short_rank, rank);
         KERNEL_CHECK();
         ix.timer.end(t);
@@ -1697,7 +1746,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
         bool chain_on = env_int("B200SA_CHAIN", 1) != 0 &&
                         (u64)m * (u64)std::max(1, env_int("B200SA_CHAIN_MIN_FRAC", 64)) >= (u64)len;
         bool small_on = env_int("B200SA_SMALL_PATH", 1) != 0;
-        int small_pause = 0;  // rounds the small-group path sits out after a round in which it found almost nothing
+        int small_pause = 0, small_fails = 0;  // rounds the small-group path sits out after finding almost nothing
         const size_t cont_bytes = ((size_t)len + 2 * (size_t)CHAIN_CAP + 8192 + 511) & ~(size_t)511;
         const size_t m_init = m;
         const size_t chain_bytes = chain_on ? cont_bytes + (size_t)len * 4 + ((m_init + 511) & ~(size_t)511) : 0;
@@ -1742,8 +1791,12 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 }
             }
             t = ix.timer.begin("round_keys", (double)m * 16.0);
-            make_keys_round_kernel<<<std::max(1u, std::min(div_up_u(m, 256 * 4), 148u * 16u)), 256, 0, st>>>(
-                act, grp, m, lr, h, lo_bits, use_chain ? cslot : nullptr, chainkey, rkA, d_lazy);
+            if (lr.sparse)
+                make_keys_round_kernel<<<std::max(1u, std::min(div_up_u(m, 256 * 4), 148u * 16u)), 256, 0, st>>>(
+                    act, grp, m, lr, h, lo_bits, use_chain ? cslot : nullptr, chainkey, rkA, d_lazy);
+            else
+                make_keys_dense_kernel<<<std::max(1u, std::min(div_up_u(m, 256 * 4), 148u * 16u)), 256, 0, st>>>(
+                    act, grp, m, rank, h, len, lo_bits, use_chain ? cslot : nullptr, chainkey, rkA);
             KERNEL_CHECK();
             ix.timer.end(t);
 
@@ -1764,7 +1817,10 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 read_back(&handled, d_handled, 4, st);
                 ix.timer.end(t);
                 ix.stats.small_path_elems += handled;
-                if ((u64)handled * 32 < (u64)m) small_pause = 3;  // (periodic texts: a few giant groups)
+                if ((u64)handled * 32 < (u64)m) {  // (periodic texts: a few giant groups) -- back off 3, 6, 12 ... rounds
+                    small_pause = 3 << std::min(small_fails, 4);
+                    ++small_fails;
+                }
                 if (handled && bwt_rows) need_bwt_fix = true;     // (this path does not write BWT rows)
             } else if (small_pause > 0) {
                 --small_pause;
