@@ -43,16 +43,9 @@ __global__ void __launch_bounds__(512) hist_kernel(const u64 *__restrict__ keys,
 #pragma unroll 1
             for (int p = 0; p < npass; ++p) {
                 u32 mask = bits_left >= RB ? (u32)(BINS - 1) : ((1u << bits_left) - 1u);
-                const u32 d = (u32)k & mask;
-                // a warp whose keys all carry the same digit (periodic texts: whole rounds of them) adds once:
-                // 32 atomics on one shared-memory word would serialise
-                const unsigned act = __activemask();
-                const u32 d0 = __shfl_sync(act, d, __ffs((int)act) - 1);
-                if (__all_sync(act, d == d0)) {
-                    if ((threadIdx.x & 31u) == (u32)(__ffs((int)act) - 1)) atomicAdd(&sh_hist[p * BINS + d0], (u32)__popc(act));
-                } else {
-                    atomicAdd(&sh_hist[p * BINS + d], 1u);
-                }
+                // (same-address shared atomics of a warp are combined by the hardware: a warp-uniform fast path
+                // with a shuffle and a vote per digit measured 2.4x SLOWER on periodic texts)
+                atomicAdd(&sh_hist[p * BINS + ((u32)k & mask)], 1u);
                 k >>= RB;
                 bits_left -= RB;
             }

@@ -1673,10 +1673,13 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
         u32 *d_nres = ar.get<u32>(2);
         CUDA_CHECK(cudaMemsetAsync(d_nres, 0, 8, st));
         const int skip_pairs = (u64)m * 64 > (u64)len ? 1 : 0;
-        count_small_groups_kernel<<<div_up_u(m, 256), 256, 0, st>>>(grp, m, skip_pairs, d_nres + 1);
-        KERNEL_CHECK();
-        u32 nsmall = 0;
-        read_back(&nsmall, d_nres + 1, 4, st);
+        // (when most suffixes are active the groups are usually giant -- periodic texts: a cheap look first)
+        u32 nsmall = 1;
+        if ((u64)m * 2 > (u64)len) {
+            count_small_groups_kernel<<<div_up_u(m, 256), 256, 0, st>>>(grp, m, skip_pairs, d_nres + 1);
+            KERNEL_CHECK();
+            read_back(&nsmall, d_nres + 1, 4, st);
+        }
         if (nsmall) {
             u8 *keep8 = ar.get<u8>((size_t)m + 64);
             u32 *act_p = ar.get<u32>(m), *row_p = ar.get<u32>(m);
@@ -1735,7 +1738,6 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
         u64 *rkA = rk_free[0] ? rk_free[0] : ar.get<u64>(m);
         u64 *rkB = rk_free[1] ? rk_free[1] : ar.get<u64>(m);
         u32 *act2 = ar.get<u32>(m), *grp2 = ar.get<u32>(m);
-        u32 *newgrp = ar.get<u32>(m);
         const int lo_bits = std::max(1, log2len);
         const int key_bits = std::min(64, 2 * lo_bits);
         u64 h = depth0 ? (u64)depth0 : (u64)K;
@@ -1869,7 +1871,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 CUDA_CHECK(cudaMemsetAsync(hb_big, 0, hbm, st));
                 RankArgs rr{};
                 rr.keys = rin; rr.vals = ain; rr.m = mb; rr.gs = lo_bits; rr.keymask = ~0ull; rr.K0 = 0; rr.n = n;
-                rr.rank = rank; rr.newgrp = newgrp; rr.scatter_all = 0; rr.sa_out = sa; rr.headbits = hb_big;
+                rr.rank = rank; rr.newgrp = grp; rr.scatter_all = 0; rr.sa_out = sa; rr.headbits = hb_big;  // (newgrp: the old heads are dead, the keys carry them)
                 // BWT rows of moved suffixes: one gather per element and round -- kept in the rounds while the
                 // active set is small, otherwise one pass over the rows of round 0's active set at the end
                 rr.bwt = m <= bwt_small ? bwt_rows : nullptr;
@@ -1888,7 +1890,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 // (the whole list went through the sort: its survivors go to the value buffer the sort left free)
                 u32 *dst = sorted_vals == act ? act2 : const_cast<u32 *>(act);
                 m2 = count_active<false>(hb_big, m, tile_counts, d_total, st);
-                if (m2) scatter_active<false>(hb_big, sorted_vals, newgrp, m, tile_counts, dst, grp2, st);
+                if (m2) scatter_active<false>(hb_big, sorted_vals, grp, m, tile_counts, dst, grp2, st);
                 if (dst == act2) std::swap(act, act2);
             } else {
                 // (`act` was read for the last time by the compaction of the sorted part)
@@ -1901,7 +1903,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 u32 mB = 0;
                 if (mb) {
                     mB = count_active<false>(hb_big, mb, tile_counts, d_total, st);
-                    if (mB) scatter_active<false>(hb_big, sorted_vals, newgrp, mb, tile_counts, dst + mA, grp2 + mA, st);
+                    if (mB) scatter_active<false>(hb_big, sorted_vals, grp, mb, tile_counts, dst + mA, grp2 + mA, st);
                 }
                 m2 = mA + mB;
                 if (dst == act2) std::swap(act, act2);
