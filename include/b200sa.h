@@ -82,6 +82,11 @@ struct b200sa_stats {
     uint64_t chain_elems;     /* suffixes in groups that "continued", summed over those rounds */
     uint64_t lazy_lookups;    /* ranks of retired suffixes recovered on demand */
     uint64_t resolved_small;  /* suffixes in groups of 2..4 equal initial keys decided by the next 64 bits of text */
+    uint64_t small_path_elems; /* list elements of doubling rounds ordered inside their tile (groups of <= 32) */
+    uint64_t pivot_elems;      /* list elements of doubling rounds that stayed with their group's pivot key and
+                                  skipped the radix sort (periodic texts: nearly all), summed over rounds */
+    uint32_t pivot_rounds;     /* doubling rounds that split their groups around a pivot key */
+    uint32_t reserved0;
 };
 
 /* ---- construction ------------------------------------------------------------------------

@@ -556,6 +556,10 @@ int b200sa_stats(const b200sa_index *idx, struct b200sa_stats *out) {
     out->chain_elems = ix.stats.chain_elems;
     out->lazy_lookups = ix.stats.lazy_lookups;
     out->resolved_small = ix.stats.resolved_small;
+    out->small_path_elems = ix.stats.small_path_elems;
+    out->pivot_elems = ix.stats.pivot_elems;
+    out->pivot_rounds = ix.stats.pivot_rounds;
+    out->reserved0 = 0;
     return 0;
 }
 

@@ -171,6 +171,17 @@ struct Arena {
     }
     template <typename T>
     T *get(size_t count) { return (T *)alloc(count * sizeof(T)); }
+    // would alloc(bytes) succeed -- in a chunk that exists, or in a new one with `margin` bytes of device memory
+    // to spare?  (optional buffers of a build are dropped instead of running the device out of memory)
+    bool can_fit(size_t bytes, size_t margin) const {
+        bytes = (bytes + 511) & ~(size_t)511;
+        for (int i = 0; i < nchunks; ++i)
+            if (chunks[i].top + bytes <= chunks[i].cap) return true;
+        if (nchunks == MAX_CHUNKS) return false;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+        return free_b >= bytes + ((size_t)256 << 20) + margin;
+    }
     struct Mark {
         size_t tops[MAX_CHUNKS];
         int n;

@@ -32,7 +32,9 @@ struct BuildStats {
     u32 chain_rounds;    // doubling rounds that used chain offsets (sa_build.cu: chain_flags_kernel)
     u64 chain_elems;     // suffixes whose group "continued", summed over those rounds
     u32 resolved_small;  // suffixes in groups of 2..4 equal keys that the next 64 bits of text decided after round 0
-    u64 small_path_elems; // list elements ordered inside their tile (groups of up to 64), summed over rounds
+    u64 small_path_elems; // list elements ordered inside their tile (groups of up to 32), summed over rounds
+    u32 pivot_rounds;     // doubling rounds that split their groups around a pivot key (sa_build.cu: pivot path)
+    u64 pivot_elems;      // list elements that stayed with the pivot key and skipped the sort, summed over rounds
 };
 
 // Occurrence-table layouts

@@ -756,6 +756,7 @@ struct RankArgs {
     const u64 *packed;
     int bits;
     u32 *primary;
+    int always_write;  // later rounds: store every rank (the old identifier of a group need not be its head row)
 };
 
 __global__ void __launch_bounds__(RK_NT) rank_kernel(RankArgs a) {
@@ -919,7 +920,7 @@ __global__ void __launch_bounds__(RK_NT) rank_kernel(RankArgs a) {
         } else {
             u32 pos = (u32)(hi + (j - jb));
             // every member holds the group head as its rank: the members that stay in front keep it
-            if (newrank != (u32)hi) a.rank[s[q]] = newrank;
+            if (a.always_write || newrank != (u32)hi) a.rank[s[q]] = newrank;
             a.newgrp[j] = newrank;
             a.sa_out[pos] = s[q];
             if (s[q] == 0) {
@@ -1107,6 +1108,7 @@ struct SmallArgs {
     u64 *headbits64, *notdone64;
     u32 *primary;
     u32 *handled;  // [1] slots handled by this path
+    int always_write;  // store every rank (see RankArgs)
 };
 
 __global__ void __launch_bounds__(RS_NT) round_small_kernel(SmallArgs a) {
@@ -1204,7 +1206,7 @@ __global__ void __launch_bounds__(RS_NT) round_small_kernel(SmallArgs a) {
         a.vals_out[slot] = s[q];
         a.newgrp_out[slot] = newrank;
         a.sa[row] = s[q];
-        if (smaller) a.rank[s[q]] = newrank;  // (members that stay in front keep the group head as their rank)
+        if (smaller || a.always_write) a.rank[s[q]] = newrank;  // (members that stay in front keep the group head as their rank)
         if (s[q] == 0) *a.primary = row;
         const u32 bit = (u32)(slot - own0);
         atomicOr(&dw_s[bit >> 6], 1ull << (bit & 63u));
@@ -1275,6 +1277,331 @@ __global__ void __launch_bounds__(CP_NT) scatter_pairs_kernel(const u8 *__restri
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pivot path of a doubling round: large groups that mostly stay together.  On periodic texts (a^n, a
+// tiled block, a Fibonacci string) the active list is a few giant groups, and in a round nearly all
+// members of a group carry the SAME second key -- the rank of the one group their successors share --
+// while a minority (the suffixes whose successor has already been decided) leaves.  Sorting all of them
+// by a 64-bit key, eight passes, settles nothing for the majority.  Here every group is split three
+// ways around the second key P of its first member:
+//     L = {key < P}   E = {key == P}   R = {key > P}
+// E keeps its order and slides behind L in one stable compaction (rows head + |L| ..), it stays one
+// group; only L and R go through the radix sort, L with the group's head as first key and R with
+// head + |L| + |E| -- the row where R starts -- so that rank_kernel places both where they belong.
+//
+// Ranks are group identifiers: rank[] of a member is ANY row inside its group's row range, the same
+// for all members (the head row wherever another kernel writes it); that is all a second key has to
+// be.  An E group whose old identifier still lies in its new, smaller range keeps it -- no rank store
+// for the majority; otherwise it takes the end of its range that lies away from the cut, so a group
+// that keeps losing members on one side (periodic texts: the shorter suffixes, in front) is renamed
+// once.  Counters live in a table indexed by (list index of the group's head) / 2 (groups have at
+// least two members).
+// ---------------------------------------------------------------------------------------------
+static constexpr int PV_NT = 256, PV_IPT = 8, PV_TILE = PV_NT * PV_IPT;
+
+// exclusive prefix of `v` over an NT-thread block (wsum: NT / 32 words of shared memory; one barrier inside)
+template <int NT>
+__device__ __forceinline__ u32 block_exclusive_u32(u32 v, u32 *wsum) {
+    constexpr int NW = NT / 32;
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    u32 incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (u32)o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    u32 wb = 0;
+    for (u32 w = 0; w < warp && w < (u32)NW; ++w) wb += wsum[w];
+    return wb + incl - v;
+}
+
+// first index f <= start with a[f .. start] all equal to x, for a GROUPED list (a[i] == x is false ...
+// false true ... true on [0, start]).  Warp-cooperative like gallop_first_equal.
+__device__ u32 gallop_first_equal_u32(const u32 *__restrict__ a, u32 start, u32 x) {
+    const u32 lane = threadIdx.x & 31u;
+    const u64 off = 1ull << lane;
+    bool eq = false;
+    if (off <= (u64)start) eq = a[(u64)start - off] == x;
+    const u32 eqm = __ballot_sync(0xffffffffu, eq);
+    const int t = __ffs((int)~eqm) - 1;
+    u64 good = t > 0 ? (u64)start - (1ull << (t - 1)) : (u64)start;
+    int64_t bad = (t >= 0 && (1ull << t) <= (u64)start) ? (int64_t)((u64)start - (1ull << t)) : -1;
+    if (t < 0) {
+        good = (u64)start - (1ull << 31);
+        bad = -1;
+    }
+    while ((int64_t)good - bad > 1) {
+        const u64 span = (u64)((int64_t)good - bad);
+        const u64 idx = (u64)(bad + 1) + (span - 1) * (u64)lane / 32u;
+        const bool e2 = idx < good && a[idx] == x;
+        const u32 m2 = __ballot_sync(0xffffffffu, e2);
+        if (m2) {
+            const int f = __ffs((int)m2) - 1;
+            const u64 gi = (u64)(bad + 1) + (span - 1) * (u64)f / 32u;
+            if (f > 0) bad = (int64_t)((u64)(bad + 1) + (span - 1) * (u64)(f - 1) / 32u);
+            good = gi;
+        } else {
+            bad = (int64_t)((u64)(bad + 1) + (span - 1) * 31u / 32u);
+        }
+    }
+    return (u32)good;
+}
+
+struct PivotArgs {
+    const u32 *act, *grp;
+    u64 *keys;                    // round keys by list index (R members get their first key rewritten)
+    u32 m;
+    int lo_bits;
+    unsigned long long *cnt64;    // [m / 2 + 1] by (list index of the group's head) >> 1: |E| << 32 | |L|
+    u8 *ebits8;                   // bit per list element: its second key equals the pivot
+    u8 *note8;                    // bit per list element: it goes through the sort (L or R)
+    u8 *surv8;                    // bit per list element: E member of a group that keeps at least two
+    u32 *tile_e;                  // [tiles + 1] E members per tile (exclusive offsets after the scan)
+    u32 *sa, *rank, *newgrp, *primary;
+};
+
+// eight consecutive words of a list (vector loads where the tile is full)
+__device__ __forceinline__ void pv_load8(const u32 *__restrict__ p, u64 j0, u32 m, u32 (&v)[PV_IPT]) {
+    if (j0 + PV_IPT <= m && ((((uintptr_t)(p + j0)) & 15) == 0)) {
+        const uint4 x = *(const uint4 *)(p + j0), y = *(const uint4 *)(p + j0 + 4);
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < PV_IPT; ++q) v[q] = j0 + q < m ? p[j0 + q] : 0u;
+    }
+}
+// the low words of eight consecutive round keys
+__device__ __forceinline__ void pv_load8_lo(const u64 *__restrict__ k, u64 j0, u32 m, u32 lomask, u32 (&v)[PV_IPT]) {
+    if (j0 + PV_IPT <= m && ((((uintptr_t)(k + j0)) & 15) == 0)) {
+#pragma unroll
+        for (int q = 0; q < PV_IPT / 2; ++q) {
+            const uint4 x = *(const uint4 *)(k + j0 + 2 * q);
+            v[2 * q] = x.x & lomask;
+            v[2 * q + 1] = x.z & lomask;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < PV_IPT; ++q) v[q] = j0 + q < m ? (u32)k[j0 + q] & lomask : 0u;
+    }
+}
+
+// hidx[q] = tile-local index + 1 of the head of element q's group (0: the group began before the tile, its
+// head stands at list index *carry_jh).  Ends with a block barrier.
+__device__ __forceinline__ void pv_heads(const u32 *__restrict__ grp, u32 m, u64 tile_base, const u32 (&g)[PV_IPT],
+                                         u32 (&hidx)[PV_IPT], u32 *wmax, u32 *carry_jh) {
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u64 j0 = tile_base + (u64)tid * PV_IPT;
+    u32 pg = (j0 > 0 && j0 < m) ? grp[j0 - 1] : 0u;
+    u32 run = 0;
+#pragma unroll
+    for (int q = 0; q < PV_IPT; ++q) {
+        const u64 j = j0 + q;
+        const bool head = j < m && (j == 0 || g[q] != pg);
+        if (head) run = (u32)(j - tile_base) + 1u;
+        hidx[q] = run;
+        pg = g[q];
+    }
+    u32 ex = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, ex, o);
+        if (lane >= (u32)o) ex = max(ex, t);
+    }
+    if (lane == 31) wmax[warp] = ex;
+    u32 pre = __shfl_up_sync(0xffffffffu, ex, 1);
+    if (lane == 0) pre = 0;
+    if (warp == 0) {
+        u32 cj = (u32)tile_base;
+        const bool first_is_head = __shfl_sync(0xffffffffu, (int)(hidx[0] != 0u), 0) != 0;
+        if (tile_base > 0 && tile_base < m && !first_is_head) {
+            const u32 g0 = __shfl_sync(0xffffffffu, g[0], 0);
+            cj = gallop_first_equal_u32(grp, (u32)tile_base, g0);
+        }
+        if (lane == 0) *carry_jh = cj;
+    }
+    __syncthreads();
+    for (u32 w = 0; w < warp; ++w) pre = max(pre, wmax[w]);
+#pragma unroll
+    for (int q = 0; q < PV_IPT; ++q)
+        if (hidx[q] == 0) hidx[q] = pre;
+}
+
+__global__ void __launch_bounds__(PV_NT) pivot_classify_kernel(PivotArgs a) {
+    __shared__ u32 hpiv[PV_TILE];  // by tile-local index of a group head: the pivot key
+    __shared__ u32 wmax[PV_NT / 32], wsum[PV_NT / 32];
+    __shared__ u32 carry_jh_s, carry_piv_s, blkL, blkE;
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u64 tile_base = (u64)blockIdx.x * PV_TILE;
+    const u64 j0 = tile_base + (u64)tid * PV_IPT;
+    const u32 lomask = a.lo_bits >= 32 ? 0xffffffffu : ((1u << a.lo_bits) - 1u);
+    u32 g[PV_IPT], lo[PV_IPT], hidx[PV_IPT];
+    pv_load8(a.grp, j0, a.m, g);
+    pv_load8_lo(a.keys, j0, a.m, lomask, lo);
+    if (tid == 0) {
+        blkL = 0;
+        blkE = 0;
+    }
+    pv_heads(a.grp, a.m, tile_base, g, hidx, wmax, &carry_jh_s);
+#pragma unroll
+    for (int q = 0; q < PV_IPT; ++q) {
+        const u64 j = j0 + q;
+        if (j < a.m && hidx[q] == (u32)(j - tile_base) + 1u) hpiv[hidx[q] - 1u] = lo[q];
+    }
+    if (tid == 0) carry_piv_s = (u32)a.keys[carry_jh_s] & lomask;
+    __syncthreads();
+    const u32 cj = carry_jh_s, cp = carry_piv_s;
+    u32 ebyte = 0, nbyte = 0;
+    u32 cur = 0xffffffffu, nL = 0, nE = 0;
+    bool one_run = true;
+#pragma unroll
+    for (int q = 0; q < PV_IPT; ++q) {
+        const u64 j = j0 + q;
+        if (j >= a.m) break;
+        const u32 jh = hidx[q] ? (u32)tile_base + hidx[q] - 1u : cj;
+        const u32 P = hidx[q] ? hpiv[hidx[q] - 1u] : cp;
+        if (jh != cur) {
+            if (cur != 0xffffffffu) {
+                one_run = false;
+                if (nL | nE) atomicAdd(&a.cnt64[cur >> 1], ((unsigned long long)nE << 32) | (unsigned long long)nL);
+            }
+            cur = jh;
+            nL = 0;
+            nE = 0;
+        }
+        const bool isE = lo[q] == P;
+        nL += lo[q] < P ? 1u : 0u;
+        nE += isE ? 1u : 0u;
+        ebyte |= (isE ? 1u : 0u) << q;
+        nbyte |= (isE ? 0u : 1u) << q;
+    }
+    // the run a thread ends with: whole warps inside the tile's first group add up before they touch a counter
+    const u32 cur0 = __shfl_sync(0xffffffffu, cur, 0);
+    const bool simple = one_run && cur == cur0 && cur != 0xffffffffu;
+    if (__all_sync(0xffffffffu, simple)) {
+        const u32 tl = __reduce_add_sync(0xffffffffu, nL), te = __reduce_add_sync(0xffffffffu, nE);
+        if (lane == 0) {
+            if (cur0 == cj) {
+                if (tl) atomicAdd(&blkL, tl);
+                if (te) atomicAdd(&blkE, te);
+            } else if (tl | te) {
+                atomicAdd(&a.cnt64[cur0 >> 1], ((unsigned long long)te << 32) | (unsigned long long)tl);
+            }
+        }
+    } else if (cur != 0xffffffffu && (nL | nE)) {
+        if (cur == cj) {
+            if (nL) atomicAdd(&blkL, nL);
+            if (nE) atomicAdd(&blkE, nE);
+        } else {
+            atomicAdd(&a.cnt64[cur >> 1], ((unsigned long long)nE << 32) | (unsigned long long)nL);
+        }
+    }
+    if (j0 < a.m) {
+        a.ebits8[j0 >> 3] = (u8)ebyte;
+        a.note8[j0 >> 3] = (u8)nbyte;
+    }
+    u32 c = (u32)__popc(ebyte);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) wsum[warp] = c;
+    __syncthreads();
+    if (tid == 0) {
+        if (blkL | blkE) atomicAdd(&a.cnt64[cj >> 1], ((unsigned long long)blkE << 32) | (unsigned long long)blkL);
+        u32 t = 0;
+        for (int w = 0; w < PV_NT / 32; ++w) t += wsum[w];
+        a.tile_e[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(PV_NT) pivot_apply_kernel(PivotArgs a) {
+    // by tile-local index of a group head (index PV_TILE: the group that began before the tile)
+    __shared__ u32 s_nL[PV_TILE + 1], s_nE[PV_TILE + 1], s_eb[PV_TILE + 1], s_id[PV_TILE + 1], s_piv[PV_TILE + 1];
+    __shared__ u32 wmax[PV_NT / 32], wsum[PV_NT / 32];
+    __shared__ u32 carry_jh_s;
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u64 tile_base = (u64)blockIdx.x * PV_TILE;
+    const u64 j0 = tile_base + (u64)tid * PV_IPT;
+    const u32 lomask = a.lo_bits >= 32 ? 0xffffffffu : ((1u << a.lo_bits) - 1u);
+    u32 g[PV_IPT], lo[PV_IPT], s[PV_IPT], hidx[PV_IPT];
+    pv_load8(a.grp, j0, a.m, g);
+    pv_load8(a.act, j0, a.m, s);
+    pv_load8_lo(a.keys, j0, a.m, lomask, lo);
+    const u32 ebyte = j0 < a.m ? (u32)a.ebits8[j0 >> 3] : 0u;
+    pv_heads(a.grp, a.m, tile_base, g, hidx, wmax, &carry_jh_s);
+    // E members before this thread's elements, over the whole list
+    const u32 excl = a.tile_e[blockIdx.x] + block_exclusive_u32<PV_NT>((u32)__popc(ebyte), wsum);
+    // identifier of an E group: the old one while it lies inside the new range, else the far end of the range
+    auto new_id = [](u32 old, u32 nh, u32 nt) { return (old >= nh && old <= nt) ? RANK_NONE : (old < nh ? nt : nh); };
+#pragma unroll
+    for (int q = 0; q < PV_IPT; ++q) {
+        const u64 j = j0 + q;
+        if (j < a.m && hidx[q] == (u32)(j - tile_base) + 1u) {
+            const unsigned long long c = a.cnt64[j >> 1];
+            const u32 nL = (u32)c, nE = (u32)(c >> 32), ix = hidx[q] - 1u;
+            s_nL[ix] = nL;
+            s_nE[ix] = nE;
+            s_eb[ix] = excl + (u32)__popc(ebyte & ((1u << q) - 1u));
+            s_piv[ix] = lo[q];
+            s_id[ix] = nE > 1u ? new_id(a.rank[s[q]], g[q] + nL, g[q] + nL + nE - 1u) : RANK_NONE;
+        }
+    }
+    const u32 cj = carry_jh_s;
+    if (warp == 0 && cj < (u32)tile_base) {  // (uniform over the block) the group that reaches into the tile
+        const unsigned long long c = a.cnt64[cj >> 1];
+        const u32 nL = (u32)c, nE = (u32)(c >> 32);
+        // E members before list index cj: the offset of its tile plus the set bits of that tile below it
+        const u32 ct = cj / (u32)PV_TILE, cb = cj % (u32)PV_TILE;
+        const u64 w = ((const u64 *)a.ebits8)[(u64)ct * (PV_TILE / 64) + lane];
+        u32 pc = 0;
+        if (lane * 64u + 64u <= cb) pc = (u32)__popcll(w);
+        else if (lane * 64u < cb) pc = (u32)__popcll(w & ((1ull << (cb - lane * 64u)) - 1ull));
+        pc = __reduce_add_sync(0xffffffffu, pc);
+        if (lane == 0) {
+            const u32 g0 = a.grp[tile_base];
+            s_nL[PV_TILE] = nL;
+            s_nE[PV_TILE] = nE;
+            s_eb[PV_TILE] = a.tile_e[ct] + pc;
+            s_piv[PV_TILE] = (u32)a.keys[cj] & lomask;
+            s_id[PV_TILE] = nE > 1u ? new_id(a.rank[a.act[tile_base]], g0 + nL, g0 + nL + nE - 1u) : RANK_NONE;
+        }
+    }
+    __syncthreads();
+    u32 sbyte = 0;
+#pragma unroll
+    for (int q = 0; q < PV_IPT; ++q) {
+        const u64 j = j0 + q;
+        if (j >= a.m) break;
+        const u32 ix = hidx[q] ? hidx[q] - 1u : (u32)PV_TILE;
+        const u32 nL = s_nL[ix], nE = s_nE[ix];
+        if ((ebyte >> q) & 1u) {
+            const u32 eidx = excl + (u32)__popc(ebyte & ((1u << q) - 1u));
+            const u32 nh = g[q] + nL, row = nh + (eidx - s_eb[ix]);
+            a.sa[row] = s[q];
+            a.newgrp[j] = nh;
+            if (s[q] == 0) *a.primary = row;
+            if (nE == 1u) {
+                a.rank[s[q]] = row;  // alone: final
+            } else {
+                sbyte |= 1u << q;
+                const u32 id = s_id[ix];
+                if (id != RANK_NONE) a.rank[s[q]] = id;
+            }
+        } else if (lo[q] > s_piv[ix]) {
+            a.keys[j] = ((u64)(g[q] + nL + nE) << a.lo_bits) | (u64)lo[q];
+        }
+    }
+    if (j0 < a.m) a.surv8[j0 >> 3] = (u8)sbyte;
+}
+
+// groups in a grouped list (positions whose group differs from the one before)
+__global__ void __launch_bounds__(256) count_heads_kernel(const u32 *__restrict__ grp, u32 m, u32 *__restrict__ count) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    u32 c = 0;
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) c += (j == 0 || grp[j] != grp[j - 1]) ? 1u : 0u;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31u) == 0 && c) atomicAdd(count, c);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1681,8 +2008,10 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
             read_back(&nsmall, d_nres + 1, 4, st);
         }
         if (nsmall) {
+            // the permuted list goes into a buffer that is dead until the rounds write their keys (both m <= len words)
             u8 *keep8 = ar.get<u8>((size_t)m + 64);
-            u32 *act_p = ar.get<u32>(m), *row_p = ar.get<u32>(m);
+            u32 *act_p = (u32 *)rk_free[0], *row_p = act_p + m;
+            u32 *act_old = act, *grp_old = grp;
             resolve_small_groups_kernel<<<div_up_u(m, 256), 256, 0, st>>>(act, grp, m, ix.packed, b, K, n, skip_pairs, sa,
                                                                           done0 ? nullptr : rank, act_p, row_p, bwt_rows,
                                                                           d_primary.ptr, keep8, d_nres);
@@ -1693,20 +2022,19 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
             // (the permuted list replaces the old one even when nothing was decided: sub-groups may have formed)
             act0 = act_p;
             row0 = row_p;
+            // the list the rounds start from goes back into the buffers of the old one (dead now); act0 / row0 stay
+            // where they are until the ranks have been scattered
             if (nres) {
-                u32 *act_r = ar.get<u32>(m - nres), *grp_r = ar.get<u32>(m - nres);
                 const u64 kw = ((u64)m + 63) / 64;
                 CUDA_CHECK(cudaMemsetAsync(headbits, 0, (kw + 2) * 8, st));
                 bytes_to_bits_kernel<<<div_up_u(kw, 256), 256, 0, st>>>(keep8, m, (u64 *)headbits, kw);
                 KERNEL_CHECK();
                 const u32 m2 = count_active<true>(headbits, m, tile_counts, d_total, st);
-                if (m2) scatter_active<true>(headbits, act_p, row_p, m, tile_counts, act_r, grp_r, st);
-                act = act_r;
-                grp = grp_r;
+                if (m2) scatter_active<true>(headbits, act_p, row_p, m, tile_counts, act_old, grp_old, st);
                 m = m2;
             } else {
-                act = act_p;
-                grp = row_p;
+                CUDA_CHECK(cudaMemcpyAsync(act_old, act_p, (size_t)m * 4, cudaMemcpyDeviceToDevice, st));
+                CUDA_CHECK(cudaMemcpyAsync(grp_old, row_p, (size_t)m * 4, cudaMemcpyDeviceToDevice, st));
             }
         }
         ix.timer.end(t);
@@ -1748,19 +2076,53 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
         bool chain_on = env_int("B200SA_CHAIN", 1) != 0 &&
                         (u64)m * (u64)std::max(1, env_int("B200SA_CHAIN_MIN_FRAC", 64)) >= (u64)len;
         bool small_on = env_int("B200SA_SMALL_PATH", 1) != 0;
+        bool pivot_on = env_int("B200SA_PIVOT", 1) != 0;
         int small_pause = 0, small_fails = 0;  // rounds the small-group path sits out after finding almost nothing
+        int pivot_pause = 0, pivot_fails = 0;  // the same for the pivot path
+        bool ids_are_heads = true;             // rank[] of an active suffix is the first row of its group (until the pivot path runs)
         const size_t cont_bytes = ((size_t)len + 2 * (size_t)CHAIN_CAP + 8192 + 511) & ~(size_t)511;
         const size_t m_init = m;
-        const size_t chain_bytes = chain_on ? cont_bytes + (size_t)len * 4 + ((m_init + 511) & ~(size_t)511) : 0;
-        const size_t small_bytes = small_on ? 3 * ((m_init * 4 + 511) & ~(size_t)511) : 0;
-        u8 *region = ar.get<u8>(std::max<size_t>(std::max(chain_bytes, small_bytes), 512));
+        const size_t third = (m_init * 4 + 64 + 511) & ~(size_t)511;
+        size_t chain_bytes = chain_on ? cont_bytes + (size_t)len * 4 + ((m_init + 511) & ~(size_t)511) : 0;
+        size_t split_bytes = (small_on || pivot_on) ? 3 * third : 0;
+        // the optional paths are dropped, the larger first, rather than running the device out of memory
+        const size_t mem_margin = (size_t)2 << 30;
+        if (split_bytes > chain_bytes && !ar.can_fit(split_bytes, mem_margin)) {
+            split_bytes = 0;
+            small_on = pivot_on = false;
+        }
+        if (chain_bytes && !ar.can_fit(std::max(chain_bytes, split_bytes), mem_margin)) {
+            chain_bytes = 0;
+            chain_on = false;
+            if (split_bytes && !ar.can_fit(split_bytes, mem_margin)) {
+                split_bytes = 0;
+                small_on = pivot_on = false;
+            }
+        }
+        u8 *region = ar.get<u8>(std::max<size_t>(std::max(chain_bytes, split_bytes), 512));
         u8 *cont8 = region, *cslot = region + cont_bytes + (size_t)len * 4;
         u32 *chainkey = (u32 *)(region + cont_bytes);
-        u32 *valsT = (u32 *)region, *newgrpT = (u32 *)(region + ((m_init * 4 + 511) & ~(size_t)511)),
-            *bvals = (u32 *)(region + 2 * ((m_init * 4 + 511) & ~(size_t)511));
-        u32 *d_ncont = ar.get<u32>(2), *d_handled = d_ncont + 1;
+        // three list-sized buffers of the split paths; `r0` changes places with the list when the pivot path has
+        // assembled the next one there (every list buffer holds m_init words) -- from then on the region holds a
+        // list and the chain arrays, which share it, are not used any more
+        u32 *r0 = (u32 *)region, *newgrpT = (u32 *)(region + third), *bvals = (u32 *)(region + 2 * third);
+        u32 *d_ncont = ar.get<u32>(4), *d_handled = d_ncont + 1, *d_nheads = d_ncont + 2;
         const size_t bm_bytes = ((m_init + 63) / 64 + 2) * 8;
         u8 *notdone = ar.get<u8>(bm_bytes), *headB = ar.get<u8>(bm_bytes);
+        u8 *ebits8 = pivot_on ? ar.get<u8>(bm_bytes) : nullptr;
+        u32 *pv_tile_e = pivot_on ? ar.get<u32>((size_t)div_up_u(m_init, PV_TILE) + 2) : nullptr;
+        // large groups or small ones?  (decides which of the two split paths a round tries first)
+        const u32 pivot_min = (u32)std::max(2, env_int("B200SA_PIVOT_MIN", 1 << 16));
+        const bool pivot_force = env_int("B200SA_PIVOT_FORCE", 0) != 0;  // (tests: every round, whatever it finds)
+        bool prefer_pivot = pivot_force;
+        if (pivot_on && !pivot_force && m >= pivot_min) {
+            CUDA_CHECK(cudaMemsetAsync(d_nheads, 0, 4, st));
+            count_heads_kernel<<<std::max(1u, std::min(div_up_u(m, 256 * 8), 148u * 8u)), 256, 0, st>>>(grp, m, d_nheads);
+            KERNEL_CHECK();
+            u32 nheads = 0;
+            read_back(&nheads, d_nheads, 4, st);
+            prefer_pivot = (u64)nheads * 64 <= (u64)m;
+        }
         while (m > 0) {
             ix.stats.rounds++;
             ix.stats.sorted_total += m;
@@ -1802,9 +2164,53 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
             KERNEL_CHECK();
             ix.timer.end(t);
 
+            // ---- large groups that mostly stay together: split around a pivot key, only the minority is sorted ----
+            bool pivoted = false;
+            u32 n_e = 0;
+            if (pivot_on && prefer_pivot && pivot_pause == 0 && m >= pivot_min) {
+                t = ix.timer.begin("pivot_classify", (double)m * 16.0);
+                const u32 ntl = div_up_u(m, PV_TILE);
+                PivotArgs pv{};
+                pv.act = act; pv.grp = grp; pv.keys = rkA; pv.m = m; pv.lo_bits = lo_bits;
+                pv.cnt64 = (unsigned long long *)r0; pv.ebits8 = ebits8; pv.note8 = notdone; pv.surv8 = headbits;
+                pv.tile_e = pv_tile_e; pv.sa = sa; pv.rank = rank; pv.newgrp = newgrpT; pv.primary = d_primary.ptr;
+                const u64 kw = ((u64)m + 63) / 64;
+                CUDA_CHECK(cudaMemsetAsync(r0, 0, (size_t)(m / 2) * 8, st));
+                CUDA_CHECK(cudaMemsetAsync(ebits8 + kw * 8, 0, 16, st));
+                CUDA_CHECK(cudaMemsetAsync(notdone + kw * 8, 0, 16, st));
+                CUDA_CHECK(cudaMemsetAsync(headbits + kw * 8, 0, 16, st));
+                pivot_classify_kernel<<<ntl, PV_NT, 0, st>>>(pv);
+                KERNEL_CHECK();
+                scan_tiles_kernel<<<1, 1024, 0, st>>>(pv_tile_e, ntl, d_total);
+                KERNEL_CHECK();
+                unsigned long long tot_e = 0;
+                read_back(&tot_e, d_total, 8, st);
+                ix.timer.end(t);
+                n_e = (u32)tot_e;
+                if ((u64)n_e * 3 >= (u64)m || pivot_force) {
+                    t = ix.timer.begin("pivot_apply", (double)m * 28.0);
+                    pivot_apply_kernel<<<ntl, PV_NT, 0, st>>>(pv);
+                    KERNEL_CHECK();
+                    ix.timer.end(t);
+                    pivoted = true;
+                    ids_are_heads = false;
+                    chain_on = false;
+                    pivot_fails = 0;
+                    ix.stats.sorted_total -= n_e;
+                    ix.stats.pivot_rounds++;
+                    ix.stats.pivot_elems += n_e;
+                    if (bwt_rows) need_bwt_fix = true;  // (this path does not write BWT rows)
+                } else {  // the groups scatter: nothing was changed, the round goes on as usual; back off 2, 4, 8 ... rounds
+                    pivot_pause = 2 << std::min(pivot_fails, 4);
+                    ++pivot_fails;
+                }
+            } else if (pivot_pause > 0) {
+                --pivot_pause;
+            }
+
             // ---- groups of up to RS_GMAX members are ordered where they stand (round_small_kernel) ----
             u32 handled = 0;
-            if (small_on && small_pause == 0) {
+            if (!pivoted && small_on && small_pause == 0) {
                 t = ix.timer.begin("round_small", (double)m * 28.0);
                 const u64 kw = ((u64)m + 63) / 64;
                 CUDA_CHECK(cudaMemsetAsync(headbits + kw * 8, 0, 16, st));
@@ -1812,8 +2218,8 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 CUDA_CHECK(cudaMemsetAsync(d_handled, 0, 4, st));
                 SmallArgs sm{};
                 sm.act = act; sm.grp = grp; sm.keys = rkA; sm.m = m; sm.lo_bits = lo_bits; sm.sa = sa; sm.rank = rank;
-                sm.vals_out = valsT; sm.newgrp_out = newgrpT; sm.headbits64 = (u64 *)headbits; sm.notdone64 = (u64 *)notdone;
-                sm.primary = d_primary.ptr; sm.handled = d_handled;
+                sm.vals_out = r0; sm.newgrp_out = newgrpT; sm.headbits64 = (u64 *)headbits; sm.notdone64 = (u64 *)notdone;
+                sm.primary = d_primary.ptr; sm.handled = d_handled; sm.always_write = ids_are_heads ? 0 : 1;
                 round_small_kernel<<<div_up_u(m, RS_STEP), RS_NT, 0, st>>>(sm);
                 KERNEL_CHECK();
                 read_back(&handled, d_handled, 4, st);
@@ -1822,22 +2228,24 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 if ((u64)handled * 32 < (u64)m) {  // (periodic texts: a few giant groups) -- back off 3, 6, 12 ... rounds
                     small_pause = 3 << std::min(small_fails, 4);
                     ++small_fails;
+                    prefer_pivot = true;  // (large groups: the pivot path is the one to try)
                 }
                 if (handled && bwt_rows) need_bwt_fix = true;     // (this path does not write BWT rows)
             } else if (small_pause > 0) {
                 --small_pause;
             }
+            const bool split = pivoted || handled != 0;  // part of the list has been placed without the sort
 
             // ---- everything else: radix sort of (group, rank) keys, new ranks from the sorted list ----
-            const u32 mb = m - handled;
+            const u32 mb = pivoted ? m - n_e : m - handled;
             const u64 *bk = rkA;   // keys / values of the elements that go through the sort
             const u32 *bv = act;
             u64 *k_other = rkB;
             u32 *v_other = act2;
-            if (handled && mb) {
+            if (split && mb) {
                 t = ix.timer.begin("compact_big", (double)m * 0.125 + (double)mb * 24.0);
                 const u32 cnt = count_active<true>(notdone, m, tile_counts, d_total, st);
-                if (cnt != mb) throw std::runtime_error("small-group path: slot accounting is inconsistent (internal error)");
+                if (cnt != mb) throw std::runtime_error("split paths: slot accounting is inconsistent (internal error)");
                 const u32 sub = compaction_sub(m);
                 scatter_pairs_kernel<<<div_up_u(m, (u64)CP_TILE * sub), CP_NT, 0, st>>>(notdone, rkA, act, m, sub, tile_counts,
                                                                                        rkB, bvals);
@@ -1845,7 +2253,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 ix.timer.end(t);
                 bk = rkB; bv = bvals; k_other = rkA; v_other = act2;
             }
-            u8 *hb_big = handled ? headB : headbits;
+            u8 *hb_big = split ? headB : headbits;
             const u32 *sorted_vals = nullptr;
             if (mb) {
                 int npass = (key_bits + RB - 1) / RB;
@@ -1878,6 +2286,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 if (bwt_rows && !rr.bwt) need_bwt_fix = true;
                 rr.prev_shift = 0; rr.packed = ix.packed; rr.bits = b;
                 rr.primary = d_primary.ptr;
+                rr.always_write = ids_are_heads ? 0 : 1;
                 rank_kernel<<<div_up_u(mb, RK_TILE), RK_NT, 0, st>>>(rr);
                 KERNEL_CHECK();
                 ix.timer.end(t);
@@ -1886,7 +2295,20 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
             // ---- next active set: the survivors of both paths, one after the other (groups stay contiguous) ----
             t = ix.timer.begin("compact", (double)m * 4.0);
             u32 m2 = 0;
-            if (!handled) {
+            if (pivoted) {
+                // E groups first (they kept their list order; singletons among them have retired), then the survivors of
+                // the sort; the list is assembled in r0 -- the counters there are dead -- which then changes places
+                // with the old list
+                const u32 mA = count_active<true>(headbits, m, tile_counts, d_total, st);
+                if (mA) scatter_active<true>(headbits, act, newgrpT, m, tile_counts, r0, grp2, st);
+                u32 mB = 0;
+                if (mb) {
+                    mB = count_active<false>(hb_big, mb, tile_counts, d_total, st);
+                    if (mB) scatter_active<false>(hb_big, sorted_vals, grp, mb, tile_counts, r0 + mA, grp2 + mA, st);
+                }
+                m2 = mA + mB;
+                std::swap(act, r0);
+            } else if (!handled) {
                 // (the whole list went through the sort: its survivors go to the value buffer the sort left free)
                 u32 *dst = sorted_vals == act ? act2 : const_cast<u32 *>(act);
                 m2 = count_active<false>(hb_big, m, tile_counts, d_total, st);
@@ -1899,7 +2321,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                     // the sorted values sit in `act` itself: survivors go to act2
                 }
                 const u32 mA = count_active<false>(headbits, m, tile_counts, d_total, st);
-                if (mA) scatter_active<false>(headbits, valsT, newgrpT, m, tile_counts, dst, grp2, st);
+                if (mA) scatter_active<false>(headbits, r0, newgrpT, m, tile_counts, dst, grp2, st);
                 u32 mB = 0;
                 if (mb) {
                     mB = count_active<false>(hb_big, mb, tile_counts, d_total, st);

@@ -93,6 +93,9 @@ MODES = {
     "chain_off": {"B200SA_CHAIN": "0"},
     # every group goes through the radix sort (no in-tile ordering of small groups, no text tie-break)
     "all_radix": {"B200SA_SMALL_PATH": "0", "B200SA_NO_EXT_TIEBREAK": "1"},
+    # groups split around a pivot key in every round / by the path's own heuristics on lists of any size
+    "pivot_force": {"B200SA_PIVOT_MIN": "2", "B200SA_PIVOT_FORCE": "1"},
+    "pivot_auto": {"B200SA_PIVOT_MIN": "2", "B200SA_SMALL_PATH": "0"},
 }
 
 
@@ -218,6 +221,17 @@ def test_repeat_rich_256M(engine):
     torch.cuda.synchronize()
     st, _ = _build_and_check(engine, text, n, 5, f"repeat-rich {info}")
     assert st["round0_mode"] == 1, st
+
+
+@pytest.mark.parametrize("kind", ["acgt4", "period1000", "fib"])
+def test_periodic_pivot_path_64M(engine, kind):
+    """Config 5 (C5c-e) at 2^26: the doubling rounds of periodic texts must run on the pivot path (the majority of
+    every group keeps its place, only the minority is sorted) and yield the suffix array the checker accepts."""
+    from stralg_b200 import texts as T
+    n = int(float(os.environ.get("B200SA_PERIODIC_N", 1 << 26)))
+    text, sigma = T.stress_text(engine.load(), kind, n)
+    st, _ = _build_and_check(engine, text, n, sigma, kind)
+    assert st["pivot_rounds"] >= 10 and st["pivot_elems"] > 4 * n, st
 
 
 def test_unary_2pow30(engine):

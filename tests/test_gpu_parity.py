@@ -73,6 +73,12 @@ ROUND0_MODES = {
     # chain offsets in every doubling round, however small the active set (default: only large ones)
     "msd_chain": {"B200SA_CHAIN_MIN_FRAC": "100000000", "B200SA_CHAIN_USE_FRAC": "100000000", "B200SA_NO_EXT_TIEBREAK": "1"},
     "lsd8_chain": {"B200SA_ROUND0": "lsd", "B200SA_RADIX_BITS": "8", "B200SA_CHAIN_MIN_FRAC": "100000000", "B200SA_CHAIN_USE_FRAC": "100000000"},
+    # pivot path (sa_build.cu pivot_classify_kernel / pivot_apply_kernel) in every doubling round whatever it finds,
+    # and with its own heuristics on lists of any size
+    "msd_pivot": {"B200SA_PIVOT_MIN": "2", "B200SA_PIVOT_FORCE": "1", "B200SA_NO_EXT_TIEBREAK": "1"},
+    "lsd8_pivot": {"B200SA_ROUND0": "lsd", "B200SA_RADIX_BITS": "8", "B200SA_PIVOT_MIN": "2", "B200SA_PIVOT_FORCE": "1"},
+    "lsd10_pivot_auto": {"B200SA_ROUND0": "lsd", "B200SA_RADIX_BITS": "10", "B200SA_PIVOT_MIN": "2"},
+    "msd_pivot_auto_nochain": {"B200SA_PIVOT_MIN": "2", "B200SA_CHAIN": "0", "B200SA_NO_EXT_TIEBREAK": "1"},
 }
 
 

@@ -58,7 +58,8 @@ if __name__ == "__main__":
                    "round0_mode": st["round0_mode"], "passes0": st["passes0"], "bucket_bits": st["bucket_bits"],
                    "shallow_buckets": st["shallow_buckets"], "shallow_elems": st["shallow_elems"],
                    "chain_rounds": st["chain_rounds"], "chain_elems": st["chain_elems"], "lazy": st["lazy_lookups"],
-                   "resolved_small": st["resolved_small"],
+                   "resolved_small": st["resolved_small"], "small_path_elems": st["small_path_elems"],
+                   "pivot_rounds": st["pivot_rounds"], "pivot_elems_x": round(st["pivot_elems"] / (n + 1), 2),
                    "sorted_total_x": round(st["sorted_total"] / (n + 1), 2),
                    "stages_ms": {k: [v[0], round(v[1], 2)] for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
                    "stages_total_ms": round(sum(v[1] for v in agg.values()), 1), "info": info}
