@@ -367,7 +367,9 @@ __global__ void __launch_bounds__(256) make_keys_round_kernel(const u32 *__restr
                                                               u32 m, LazyRank lr, u64 h, int lo_bits,
                                                               const u8 *__restrict__ cslot,
                                                               const u32 *__restrict__ chainkey,
-                                                              u64 *__restrict__ keys, u32 *__restrict__ lazy_count) {
+                                                              u64 *__restrict__ keys, u32 *__restrict__ lazy_count,
+                                                              u32 *__restrict__ pv_piv,
+                                                              unsigned long long *__restrict__ pv_cnt) {
     const u64 stride = (u64)gridDim.x * blockDim.x;  // a multiple of 32: warps stay together
     const u32 lane = threadIdx.x & 31u, gbase = lane & ~7u, gmask = 0xffu << gbase;
     u32 nlazy = 0;
@@ -425,7 +427,15 @@ __global__ void __launch_bounds__(256) make_keys_round_kernel(const u32 *__restr
                 __syncwarp();
             }
         }
-        if (j < m) keys[j] = ((u64)grp[j] << lo_bits) | lo;
+        if (j < m) {
+            const u32 gj = grp[j];
+            keys[j] = ((u64)gj << lo_bits) | lo;
+            // pivot path: the first member of a group publishes its second key and clears the group's counters
+            if (pv_piv && (j == 0 || grp[j - 1] != gj)) {
+                pv_piv[gj >> 1] = (u32)lo;
+                pv_cnt[gj >> 1] = 0ull;
+            }
+        }
     }
     // ranks that had to be recovered: the host moves to complete ranks when they become many
     nlazy = __reduce_add_sync(0xffffffffu, nlazy);
@@ -436,7 +446,9 @@ __global__ void __launch_bounds__(256) make_keys_round_kernel(const u32 *__restr
 __global__ void __launch_bounds__(256) make_keys_dense_kernel(const u32 *__restrict__ act, const u32 *__restrict__ grp, u32 m,
                                                               const u32 *__restrict__ rank, u64 h, u32 len, int lo_bits,
                                                               const u8 *__restrict__ cslot,
-                                                              const u32 *__restrict__ chainkey, u64 *__restrict__ keys) {
+                                                              const u32 *__restrict__ chainkey, u64 *__restrict__ keys,
+                                                              u32 *__restrict__ pv_piv,
+                                                              unsigned long long *__restrict__ pv_cnt) {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
         const u32 s = act[j];
@@ -451,7 +463,12 @@ __global__ void __launch_bounds__(256) make_keys_dense_kernel(const u32 *__restr
         }
         const u64 t = (u64)s + h;
         if (!chained && t < len) lo = rank[t];
-        keys[j] = ((u64)grp[j] << lo_bits) | lo;
+        const u32 gj = grp[j];
+        keys[j] = ((u64)gj << lo_bits) | lo;
+        if (pv_piv && (j == 0 || grp[j - 1] != gj)) {
+            pv_piv[gj >> 1] = (u32)lo;
+            pv_cnt[gj >> 1] = 0ull;
+        }
     }
 }
 
@@ -1296,10 +1313,17 @@ __global__ void __launch_bounds__(CP_NT) scatter_pairs_kernel(const u8 *__restri
 // be.  An E group whose old identifier still lies in its new, smaller range keeps it -- no rank store
 // for the majority; otherwise it takes the end of its range that lies away from the cut, so a group
 // that keeps losing members on one side (periodic texts: the shorter suffixes, in front) is renamed
-// once.  Counters live in a table indexed by (list index of the group's head) / 2 (groups have at
-// least two members).
+// once.
+//
+// Per-group data lives in two tables indexed by (head row of the group) / 2 -- groups own at least
+// two rows, so the index is unique, and every member knows it without looking for the head of its
+// group in the list: the pivot key (written by the head's thread when the round keys are made) and
+// the counters |E| << 32 | |L| (zeroed there, accumulated by the classification).  Two passes over
+// the list: classify (classes, counters, E bitmap, per-tile E counts), apply (rows, identifiers, the
+// E part of the NEXT list written in place at the E members' prefix count -- no separate compaction).
 // ---------------------------------------------------------------------------------------------
 static constexpr int PV_NT = 256, PV_IPT = 8, PV_TILE = PV_NT * PV_IPT;
+static constexpr u32 PV_HEADFLAG = 0x80000000u;
 
 // exclusive prefix of `v` over an NT-thread block (wsum: NT / 32 words of shared memory; one barrier inside)
 template <int NT>
@@ -1319,49 +1343,22 @@ __device__ __forceinline__ u32 block_exclusive_u32(u32 v, u32 *wsum) {
     return wb + incl - v;
 }
 
-// first index f <= start with a[f .. start] all equal to x, for a GROUPED list (a[i] == x is false ...
-// false true ... true on [0, start]).  Warp-cooperative like gallop_first_equal.
-__device__ u32 gallop_first_equal_u32(const u32 *__restrict__ a, u32 start, u32 x) {
-    const u32 lane = threadIdx.x & 31u;
-    const u64 off = 1ull << lane;
-    bool eq = false;
-    if (off <= (u64)start) eq = a[(u64)start - off] == x;
-    const u32 eqm = __ballot_sync(0xffffffffu, eq);
-    const int t = __ffs((int)~eqm) - 1;
-    u64 good = t > 0 ? (u64)start - (1ull << (t - 1)) : (u64)start;
-    int64_t bad = (t >= 0 && (1ull << t) <= (u64)start) ? (int64_t)((u64)start - (1ull << t)) : -1;
-    if (t < 0) {
-        good = (u64)start - (1ull << 31);
-        bad = -1;
-    }
-    while ((int64_t)good - bad > 1) {
-        const u64 span = (u64)((int64_t)good - bad);
-        const u64 idx = (u64)(bad + 1) + (span - 1) * (u64)lane / 32u;
-        const bool e2 = idx < good && a[idx] == x;
-        const u32 m2 = __ballot_sync(0xffffffffu, e2);
-        if (m2) {
-            const int f = __ffs((int)m2) - 1;
-            const u64 gi = (u64)(bad + 1) + (span - 1) * (u64)f / 32u;
-            if (f > 0) bad = (int64_t)((u64)(bad + 1) + (span - 1) * (u64)(f - 1) / 32u);
-            good = gi;
-        } else {
-            bad = (int64_t)((u64)(bad + 1) + (span - 1) * 31u / 32u);
-        }
-    }
-    return (u32)good;
-}
-
 struct PivotArgs {
     const u32 *act, *grp;
     u64 *keys;                    // round keys by list index (R members get their first key rewritten)
     u32 m;
     int lo_bits;
-    unsigned long long *cnt64;    // [m / 2 + 1] by (list index of the group's head) >> 1: |E| << 32 | |L|
+    const u32 *piv;               // by head row >> 1: the pivot key
+    unsigned long long *cnt64;    // by head row >> 1: |E| << 32 | |L|
     u8 *ebits8;                   // bit per list element: its second key equals the pivot
     u8 *note8;                    // bit per list element: it goes through the sort (L or R)
-    u8 *surv8;                    // bit per list element: E member of a group that keeps at least two
     u32 *tile_e;                  // [tiles + 1] E members per tile (exclusive offsets after the scan)
-    u32 *sa, *rank, *newgrp, *primary;
+    u32 *tile_c;                  // [tiles + 1] E members at or after the tile's last group head (| PV_HEADFLAG), or of
+                                  // the whole tile when no group begins in it; after the scan: E members of the group
+                                  // that reaches into the tile, counted over the tiles before it
+    u32 *sa, *rank, *primary;
+    u32 *out_act, *out_grp;       // the E part of the next list
+    u32 *singles;                 // [1] E groups of one member (final; they are taken out of the next list afterwards)
 };
 
 // eight consecutive words of a list (vector loads where the tile is full)
@@ -1389,110 +1386,70 @@ __device__ __forceinline__ void pv_load8_lo(const u64 *__restrict__ k, u64 j0, u
     }
 }
 
-// hidx[q] = tile-local index + 1 of the head of element q's group (0: the group began before the tile, its
-// head stands at list index *carry_jh).  Ends with a block barrier.
-__device__ __forceinline__ void pv_heads(const u32 *__restrict__ grp, u32 m, u64 tile_base, const u32 (&g)[PV_IPT],
-                                         u32 (&hidx)[PV_IPT], u32 *wmax, u32 *carry_jh) {
-    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const u64 j0 = tile_base + (u64)tid * PV_IPT;
-    u32 pg = (j0 > 0 && j0 < m) ? grp[j0 - 1] : 0u;
-    u32 run = 0;
-#pragma unroll
-    for (int q = 0; q < PV_IPT; ++q) {
-        const u64 j = j0 + q;
-        const bool head = j < m && (j == 0 || g[q] != pg);
-        if (head) run = (u32)(j - tile_base) + 1u;
-        hidx[q] = run;
-        pg = g[q];
-    }
-    u32 ex = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const u32 t = __shfl_up_sync(0xffffffffu, ex, o);
-        if (lane >= (u32)o) ex = max(ex, t);
-    }
-    if (lane == 31) wmax[warp] = ex;
-    u32 pre = __shfl_up_sync(0xffffffffu, ex, 1);
-    if (lane == 0) pre = 0;
-    if (warp == 0) {
-        u32 cj = (u32)tile_base;
-        const bool first_is_head = __shfl_sync(0xffffffffu, (int)(hidx[0] != 0u), 0) != 0;
-        if (tile_base > 0 && tile_base < m && !first_is_head) {
-            const u32 g0 = __shfl_sync(0xffffffffu, g[0], 0);
-            cj = gallop_first_equal_u32(grp, (u32)tile_base, g0);
-        }
-        if (lane == 0) *carry_jh = cj;
-    }
-    __syncthreads();
-    for (u32 w = 0; w < warp; ++w) pre = max(pre, wmax[w]);
-#pragma unroll
-    for (int q = 0; q < PV_IPT; ++q)
-        if (hidx[q] == 0) hidx[q] = pre;
-}
-
 __global__ void __launch_bounds__(PV_NT) pivot_classify_kernel(PivotArgs a) {
-    __shared__ u32 hpiv[PV_TILE];  // by tile-local index of a group head: the pivot key
-    __shared__ u32 wmax[PV_NT / 32], wsum[PV_NT / 32];
-    __shared__ u32 carry_jh_s, carry_piv_s, blkL, blkE;
+    __shared__ u32 wsum[PV_NT / 32], wmax[PV_NT / 32], wsum2[PV_NT / 32];
+    __shared__ u32 blkL, blkE, lmax_s;
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const u64 tile_base = (u64)blockIdx.x * PV_TILE;
     const u64 j0 = tile_base + (u64)tid * PV_IPT;
     const u32 lomask = a.lo_bits >= 32 ? 0xffffffffu : ((1u << a.lo_bits) - 1u);
-    u32 g[PV_IPT], lo[PV_IPT], hidx[PV_IPT];
+    u32 g[PV_IPT], lo[PV_IPT];
     pv_load8(a.grp, j0, a.m, g);
     pv_load8_lo(a.keys, j0, a.m, lomask, lo);
+    const u32 g0 = a.grp[tile_base];  // the group the tile begins in: its counts are summed over the block first
+    u32 gprev = (j0 > 0 && j0 < a.m) ? a.grp[j0 - 1] : 0u;
     if (tid == 0) {
         blkL = 0;
         blkE = 0;
     }
-    pv_heads(a.grp, a.m, tile_base, g, hidx, wmax, &carry_jh_s);
-#pragma unroll
-    for (int q = 0; q < PV_IPT; ++q) {
-        const u64 j = j0 + q;
-        if (j < a.m && hidx[q] == (u32)(j - tile_base) + 1u) hpiv[hidx[q] - 1u] = lo[q];
-    }
-    if (tid == 0) carry_piv_s = (u32)a.keys[carry_jh_s] & lomask;
     __syncthreads();
-    const u32 cj = carry_jh_s, cp = carry_piv_s;
     u32 ebyte = 0, nbyte = 0;
-    u32 cur = 0xffffffffu, nL = 0, nE = 0;
-    bool one_run = true;
+    u32 cur = 0, nL = 0, nE = 0, P = 0;
+    bool have = false, one_run = true;
+    u32 lh = 0, ea = 0;  // tile-local index + 1 of this thread's last group head; its E members at or after it
 #pragma unroll
     for (int q = 0; q < PV_IPT; ++q) {
         const u64 j = j0 + q;
         if (j >= a.m) break;
-        const u32 jh = hidx[q] ? (u32)tile_base + hidx[q] - 1u : cj;
-        const u32 P = hidx[q] ? hpiv[hidx[q] - 1u] : cp;
-        if (jh != cur) {
-            if (cur != 0xffffffffu) {
+        const bool head = j == 0 || g[q] != gprev;
+        gprev = g[q];
+        if (head) {
+            lh = (u32)(j - tile_base) + 1u;
+            ea = 0;
+        }
+        if (!have || g[q] != cur) {
+            if (have) {
                 one_run = false;
                 if (nL | nE) atomicAdd(&a.cnt64[cur >> 1], ((unsigned long long)nE << 32) | (unsigned long long)nL);
             }
-            cur = jh;
+            have = true;
+            cur = g[q];
             nL = 0;
             nE = 0;
+            P = a.piv[cur >> 1];
         }
         const bool isE = lo[q] == P;
         nL += lo[q] < P ? 1u : 0u;
         nE += isE ? 1u : 0u;
+        ea += isE ? 1u : 0u;
         ebyte |= (isE ? 1u : 0u) << q;
         nbyte |= (isE ? 0u : 1u) << q;
     }
-    // the run a thread ends with: whole warps inside the tile's first group add up before they touch a counter
+    // the run a thread ends with: whole warps inside one group add up before they touch a counter
     const u32 cur0 = __shfl_sync(0xffffffffu, cur, 0);
-    const bool simple = one_run && cur == cur0 && cur != 0xffffffffu;
+    const bool simple = have && one_run && cur == cur0;
     if (__all_sync(0xffffffffu, simple)) {
         const u32 tl = __reduce_add_sync(0xffffffffu, nL), te = __reduce_add_sync(0xffffffffu, nE);
         if (lane == 0) {
-            if (cur0 == cj) {
+            if (cur0 == g0) {
                 if (tl) atomicAdd(&blkL, tl);
                 if (te) atomicAdd(&blkE, te);
             } else if (tl | te) {
                 atomicAdd(&a.cnt64[cur0 >> 1], ((unsigned long long)te << 32) | (unsigned long long)tl);
             }
         }
-    } else if (cur != 0xffffffffu && (nL | nE)) {
-        if (cur == cj) {
+    } else if (have && (nL | nE)) {
+        if (cur == g0) {
             if (nL) atomicAdd(&blkL, nL);
             if (nE) atomicAdd(&blkE, nE);
         } else {
@@ -1503,23 +1460,109 @@ __global__ void __launch_bounds__(PV_NT) pivot_classify_kernel(PivotArgs a) {
         a.ebits8[j0 >> 3] = (u8)ebyte;
         a.note8[j0 >> 3] = (u8)nbyte;
     }
-    u32 c = (u32)__popc(ebyte);
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (lane == 0) wsum[warp] = c;
+    // per-tile summaries: E members, and E members at or after the last group head
+    const u32 myE = (u32)__popc(ebyte);
+    const u32 c = __reduce_add_sync(0xffffffffu, myE);
+    const u32 mx = __reduce_max_sync(0xffffffffu, lh);
+    if (lane == 0) {
+        wsum[warp] = c;
+        wmax[warp] = mx;
+    }
     __syncthreads();
     if (tid == 0) {
-        if (blkL | blkE) atomicAdd(&a.cnt64[cj >> 1], ((unsigned long long)blkE << 32) | (unsigned long long)blkL);
-        u32 t = 0;
-        for (int w = 0; w < PV_NT / 32; ++w) t += wsum[w];
+        u32 t = 0, l = 0;
+        for (int w = 0; w < PV_NT / 32; ++w) {
+            t += wsum[w];
+            l = max(l, wmax[w]);
+        }
         a.tile_e[blockIdx.x] = t;
+        lmax_s = l;
+        if (blkL | blkE) atomicAdd(&a.cnt64[g0 >> 1], ((unsigned long long)blkE << 32) | (unsigned long long)blkL);
     }
+    __syncthreads();
+    const u32 lmax = lmax_s;
+    u32 after = myE;  // (no head in the tile: everything counts)
+    if (lmax) {
+        const u32 owner = (lmax - 1u) / (u32)PV_IPT;
+        after = tid > owner ? myE : (tid == owner ? ea : 0u);
+    }
+    after = __reduce_add_sync(0xffffffffu, after);
+    if (lane == 0) wsum2[warp] = after;
+    __syncthreads();
+    if (tid == 0) {
+        u32 t = 0;
+        for (int w = 0; w < PV_NT / 32; ++w) t += wsum2[w];
+        a.tile_c[blockIdx.x] = t | (lmax ? PV_HEADFLAG : 0u);
+    }
+}
+
+// single block: tile_e -> exclusive offsets (total to *total); tile_c -> E members of the group that reaches into
+// each tile, counted over the tiles before it (a segmented scan: a tile in which a group begins starts a new sum)
+__global__ void __launch_bounds__(1024) pivot_scan_kernel(u32 *__restrict__ tile_e, u32 *__restrict__ tile_c, u32 ntiles,
+                                                          unsigned long long *__restrict__ total) {
+    __shared__ u64 wsum[32], wseg[32];
+    __shared__ u64 carry, ccarry;
+    constexpr u64 F = 1ull << 63;  // "a group begins in this stretch of tiles"
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        carry = 0;
+        ccarry = 0;
+    }
+    __syncthreads();
+    for (u32 base = 0; base < ntiles; base += 1024) {
+        const u32 i = base + threadIdx.x;
+        const u64 v = i < ntiles ? tile_e[i] : 0;
+        const u32 c0 = i < ntiles ? tile_c[i] : 0u;
+        // flag | value; combine(earlier, later) = later.flag ? later : (earlier.flag, earlier.value + later.value)
+        u64 x = (u64)(c0 & ~PV_HEADFLAG) | ((c0 & PV_HEADFLAG) ? F : 0ull);
+        u64 incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u64 t = __shfl_up_sync(0xffffffffu, incl, o);
+            const u64 y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= (u32)o) {
+                incl += t;
+                if (!(x & F)) x = (y & F) | ((y & ~F) + x);
+            }
+        }
+        if (lane == 31) {
+            wsum[warp] = incl;
+            wseg[warp] = x;
+        }
+        __syncthreads();
+        u64 wb = 0;
+        u64 pre = ccarry;  // segment sum that reaches this warp: the carry, then the warps before it
+        for (u32 w = 0; w < warp; ++w) {
+            wb += wsum[w];
+            const u64 y = wseg[w];
+            pre = (y & F) ? (y & ~F) : pre + y;
+        }
+        const u64 excl = carry + wb + incl - v;
+        // value reaching into element i: the inclusive segment value of its predecessor (inside the warp that value
+        // already sums the warp's earlier lanes, unless a head cut it)
+        const u64 xp = __shfl_up_sync(0xffffffffu, x, 1);
+        const u64 into = lane == 0 ? pre : ((xp & F) ? (xp & ~F) : pre + xp);
+        if (i < ntiles) {
+            tile_e[i] = (u32)excl;
+            tile_c[i] = (u32)into;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) {
+            carry = excl + v;
+            ccarry = (x & F) ? (x & ~F) : pre + x;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
 }
 
 __global__ void __launch_bounds__(PV_NT) pivot_apply_kernel(PivotArgs a) {
     // by tile-local index of a group head (index PV_TILE: the group that began before the tile)
-    __shared__ u32 s_nL[PV_TILE + 1], s_nE[PV_TILE + 1], s_eb[PV_TILE + 1], s_id[PV_TILE + 1], s_piv[PV_TILE + 1];
+    __shared__ u16 s_eh[PV_TILE + 2];   // E members of the tile before the head
+    __shared__ u32 s_id[PV_TILE + 1];   // new identifier of the E group, RANK_NONE: unchanged
+    // the tile's E members in list order
+    __shared__ u32 sh_s[PV_TILE], sh_nh[PV_TILE], sh_row[PV_TILE], sh_rk[PV_TILE];
     __shared__ u32 wmax[PV_NT / 32], wsum[PV_NT / 32];
-    __shared__ u32 carry_jh_s;
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const u64 tile_base = (u64)blockIdx.x * PV_TILE;
     const u64 j0 = tile_base + (u64)tid * PV_IPT;
@@ -1529,70 +1572,117 @@ __global__ void __launch_bounds__(PV_NT) pivot_apply_kernel(PivotArgs a) {
     pv_load8(a.act, j0, a.m, s);
     pv_load8_lo(a.keys, j0, a.m, lomask, lo);
     const u32 ebyte = j0 < a.m ? (u32)a.ebits8[j0 >> 3] : 0u;
-    pv_heads(a.grp, a.m, tile_base, g, hidx, wmax, &carry_jh_s);
-    // E members before this thread's elements, over the whole list
-    const u32 excl = a.tile_e[blockIdx.x] + block_exclusive_u32<PV_NT>((u32)__popc(ebyte), wsum);
+    // tile-local index + 1 of the head of every element's group (0: it began before the tile)
+    {
+        u32 pg = (j0 > 0 && j0 < a.m) ? a.grp[j0 - 1] : 0u;
+        u32 run = 0;
+#pragma unroll
+        for (int q = 0; q < PV_IPT; ++q) {
+            const u64 j = j0 + q;
+            const bool head = j < a.m && (j == 0 || g[q] != pg);
+            if (head) run = (u32)(j - tile_base) + 1u;
+            hidx[q] = run;
+            pg = g[q];
+        }
+        u32 ex = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, ex, o);
+            if (lane >= (u32)o) ex = max(ex, t);
+        }
+        if (lane == 31) wmax[warp] = ex;
+        u32 pre = __shfl_up_sync(0xffffffffu, ex, 1);
+        if (lane == 0) pre = 0;
+        __syncthreads();
+        for (u32 w = 0; w < warp; ++w) pre = max(pre, wmax[w]);
+#pragma unroll
+        for (int q = 0; q < PV_IPT; ++q)
+            if (hidx[q] == 0) hidx[q] = pre;
+    }
+    // E members of the tile before this thread's elements
+    const u32 excl = block_exclusive_u32<PV_NT>((u32)__popc(ebyte), wsum);
+    const u32 tile_off = a.tile_e[blockIdx.x], ecarry = a.tile_c[blockIdx.x];
     // identifier of an E group: the old one while it lies inside the new range, else the far end of the range
     auto new_id = [](u32 old, u32 nh, u32 nt) { return (old >= nh && old <= nt) ? RANK_NONE : (old < nh ? nt : nh); };
 #pragma unroll
     for (int q = 0; q < PV_IPT; ++q) {
         const u64 j = j0 + q;
         if (j < a.m && hidx[q] == (u32)(j - tile_base) + 1u) {
-            const unsigned long long c = a.cnt64[j >> 1];
+            const unsigned long long c = a.cnt64[g[q] >> 1];
             const u32 nL = (u32)c, nE = (u32)(c >> 32), ix = hidx[q] - 1u;
-            s_nL[ix] = nL;
-            s_nE[ix] = nE;
-            s_eb[ix] = excl + (u32)__popc(ebyte & ((1u << q) - 1u));
-            s_piv[ix] = lo[q];
+            s_eh[ix] = (u16)(excl + (u32)__popc(ebyte & ((1u << q) - 1u)));
             s_id[ix] = nE > 1u ? new_id(a.rank[s[q]], g[q] + nL, g[q] + nL + nE - 1u) : RANK_NONE;
         }
     }
-    const u32 cj = carry_jh_s;
-    if (warp == 0 && cj < (u32)tile_base) {  // (uniform over the block) the group that reaches into the tile
-        const unsigned long long c = a.cnt64[cj >> 1];
+    if (tid == 0 && hidx[0] == 0) {  // the group that reaches into the tile
+        const unsigned long long c = a.cnt64[g[0] >> 1];
         const u32 nL = (u32)c, nE = (u32)(c >> 32);
-        // E members before list index cj: the offset of its tile plus the set bits of that tile below it
-        const u32 ct = cj / (u32)PV_TILE, cb = cj % (u32)PV_TILE;
-        const u64 w = ((const u64 *)a.ebits8)[(u64)ct * (PV_TILE / 64) + lane];
-        u32 pc = 0;
-        if (lane * 64u + 64u <= cb) pc = (u32)__popcll(w);
-        else if (lane * 64u < cb) pc = (u32)__popcll(w & ((1ull << (cb - lane * 64u)) - 1ull));
-        pc = __reduce_add_sync(0xffffffffu, pc);
-        if (lane == 0) {
-            const u32 g0 = a.grp[tile_base];
-            s_nL[PV_TILE] = nL;
-            s_nE[PV_TILE] = nE;
-            s_eb[PV_TILE] = a.tile_e[ct] + pc;
-            s_piv[PV_TILE] = (u32)a.keys[cj] & lomask;
-            s_id[PV_TILE] = nE > 1u ? new_id(a.rank[a.act[tile_base]], g0 + nL, g0 + nL + nE - 1u) : RANK_NONE;
+        s_id[PV_TILE] = nE > 1u ? new_id(a.rank[s[0]], g[0] + nL, g[0] + nL + nE - 1u) : RANK_NONE;
+    }
+    __syncthreads();
+    {
+        u32 cur = 0, nL = 0, nE = 0, P = 0;
+        bool have = false;
+#pragma unroll
+        for (int q = 0; q < PV_IPT; ++q) {
+            const u64 j = j0 + q;
+            if (j >= a.m) break;
+            if (!have || g[q] != cur) {
+                have = true;
+                cur = g[q];
+                const unsigned long long c = a.cnt64[cur >> 1];
+                nL = (u32)c;
+                nE = (u32)(c >> 32);
+                P = a.piv[cur >> 1];
+            }
+            if ((ebyte >> q) & 1u) {
+                const u32 el = excl + (u32)__popc(ebyte & ((1u << q) - 1u));
+                const u32 within = hidx[q] ? el - (u32)s_eh[hidx[q] - 1u] : el + ecarry;
+                const u32 nh = cur + nL, row = nh + within;
+                sh_s[el] = s[q];
+                sh_nh[el] = nh;
+                sh_row[el] = row;
+                u32 rk = RANK_NONE;
+                if (nE == 1u) {
+                    rk = row;  // alone: final
+                    atomicAdd(a.singles, 1u);
+                } else {
+                    rk = s_id[hidx[q] ? hidx[q] - 1u : (u32)PV_TILE];
+                }
+                sh_rk[el] = rk;
+            } else if (lo[q] > P) {
+                a.keys[j] = ((u64)(cur + nL + nE) << a.lo_bits) | (u64)lo[q];
+            }
         }
     }
     __syncthreads();
-    u32 sbyte = 0;
-#pragma unroll
-    for (int q = 0; q < PV_IPT; ++q) {
-        const u64 j = j0 + q;
-        if (j >= a.m) break;
-        const u32 ix = hidx[q] ? hidx[q] - 1u : (u32)PV_TILE;
-        const u32 nL = s_nL[ix], nE = s_nE[ix];
-        if ((ebyte >> q) & 1u) {
-            const u32 eidx = excl + (u32)__popc(ebyte & ((1u << q) - 1u));
-            const u32 nh = g[q] + nL, row = nh + (eidx - s_eb[ix]);
-            a.sa[row] = s[q];
-            a.newgrp[j] = nh;
-            if (s[q] == 0) *a.primary = row;
-            if (nE == 1u) {
-                a.rank[s[q]] = row;  // alone: final
-            } else {
-                sbyte |= 1u << q;
-                const u32 id = s_id[ix];
-                if (id != RANK_NONE) a.rank[s[q]] = id;
-            }
-        } else if (lo[q] > s_piv[ix]) {
-            a.keys[j] = ((u64)(g[q] + nL + nE) << a.lo_bits) | (u64)lo[q];
-        }
+    // consecutive threads write consecutive entries of the next list and (inside a group) consecutive rows
+    u32 ne = 0;  // E members of the tile (the warp totals of the prefix sum above)
+    for (int w = 0; w < PV_NT / 32; ++w) ne += wsum[w];
+    for (u32 k = tid; k < ne; k += PV_NT) {
+        const u32 sv = sh_s[k], row = sh_row[k], rk = sh_rk[k];
+        a.out_act[tile_off + k] = sv;
+        a.out_grp[tile_off + k] = sh_nh[k];
+        a.sa[row] = sv;
+        if (rk != RANK_NONE) a.rank[sv] = rk;
+        if (sv == 0) *a.primary = row;
     }
-    if (j0 < a.m) a.surv8[j0 >> 3] = (u8)sbyte;
+}
+
+// E part of the list the pivot path has written: bit j is set unless entry j is a group of its own
+__global__ void __launch_bounds__(256) pivot_keep_kernel(const u32 *__restrict__ grp, u32 ne, u64 *__restrict__ bits64,
+                                                         u64 nwords) {
+    const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwords) return;
+    u64 v = 0;
+    const u64 base = w * 64;
+    for (u32 i = 0; i < 64 && base + i < ne; ++i) {
+        const u64 j = base + i;
+        const u32 g = grp[j];
+        const bool single = (j == 0 || grp[j - 1] != g) && (j + 1 >= ne || grp[j + 1] != g);
+        v |= (u64)(single ? 0u : 1u) << i;
+    }
+    bits64[w] = v;
 }
 
 // groups in a grouped list (positions whose group differs from the one before)
@@ -2109,8 +2199,14 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
         u32 *d_ncont = ar.get<u32>(4), *d_handled = d_ncont + 1, *d_nheads = d_ncont + 2;
         const size_t bm_bytes = ((m_init + 63) / 64 + 2) * 8;
         u8 *notdone = ar.get<u8>(bm_bytes), *headB = ar.get<u8>(bm_bytes);
+        // pivot path: per-group tables by (head row) / 2, E bitmap, per-tile counts
+        const size_t pv_entries = (size_t)len / 2 + 2;
+        if (pivot_on && !ar.can_fit(pv_entries * 12 + bm_bytes, mem_margin)) pivot_on = false;
         u8 *ebits8 = pivot_on ? ar.get<u8>(bm_bytes) : nullptr;
         u32 *pv_tile_e = pivot_on ? ar.get<u32>((size_t)div_up_u(m_init, PV_TILE) + 2) : nullptr;
+        u32 *pv_tile_c = pivot_on ? ar.get<u32>((size_t)div_up_u(m_init, PV_TILE) + 2) : nullptr;
+        unsigned long long *pv_cnt = pivot_on ? ar.get<unsigned long long>(pv_entries) : nullptr;
+        u32 *pv_piv = pivot_on ? ar.get<u32>(pv_entries) : nullptr;
         // large groups or small ones?  (decides which of the two split paths a round tries first)
         const u32 pivot_min = (u32)std::max(2, env_int("B200SA_PIVOT_MIN", 1 << 16));
         const bool pivot_force = env_int("B200SA_PIVOT_FORCE", 0) != 0;  // (tests: every round, whatever it finds)
@@ -2155,33 +2251,36 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 }
             }
             t = ix.timer.begin("round_keys", (double)m * 16.0);
+            const bool try_pivot = pivot_on && prefer_pivot && pivot_pause == 0 && m >= pivot_min;
             if (lr.sparse)
                 make_keys_round_kernel<<<std::max(1u, std::min(div_up_u(m, 256 * 4), 148u * 16u)), 256, 0, st>>>(
-                    act, grp, m, lr, h, lo_bits, use_chain ? cslot : nullptr, chainkey, rkA, d_lazy);
+                    act, grp, m, lr, h, lo_bits, use_chain ? cslot : nullptr, chainkey, rkA, d_lazy,
+                    try_pivot ? pv_piv : nullptr, pv_cnt);
             else
                 make_keys_dense_kernel<<<std::max(1u, std::min(div_up_u(m, 256 * 4), 148u * 16u)), 256, 0, st>>>(
-                    act, grp, m, rank, h, len, lo_bits, use_chain ? cslot : nullptr, chainkey, rkA);
+                    act, grp, m, rank, h, len, lo_bits, use_chain ? cslot : nullptr, chainkey, rkA,
+                    try_pivot ? pv_piv : nullptr, pv_cnt);
             KERNEL_CHECK();
             ix.timer.end(t);
 
             // ---- large groups that mostly stay together: split around a pivot key, only the minority is sorted ----
             bool pivoted = false;
-            u32 n_e = 0;
-            if (pivot_on && prefer_pivot && pivot_pause == 0 && m >= pivot_min) {
-                t = ix.timer.begin("pivot_classify", (double)m * 16.0);
+            u32 n_e = 0, n_single = 0;
+            if (try_pivot) {
+                t = ix.timer.begin("pivot_classify", (double)m * 12.0);
                 const u32 ntl = div_up_u(m, PV_TILE);
                 PivotArgs pv{};
                 pv.act = act; pv.grp = grp; pv.keys = rkA; pv.m = m; pv.lo_bits = lo_bits;
-                pv.cnt64 = (unsigned long long *)r0; pv.ebits8 = ebits8; pv.note8 = notdone; pv.surv8 = headbits;
-                pv.tile_e = pv_tile_e; pv.sa = sa; pv.rank = rank; pv.newgrp = newgrpT; pv.primary = d_primary.ptr;
+                pv.piv = pv_piv; pv.cnt64 = pv_cnt; pv.ebits8 = ebits8; pv.note8 = notdone;
+                pv.tile_e = pv_tile_e; pv.tile_c = pv_tile_c; pv.sa = sa; pv.rank = rank; pv.primary = d_primary.ptr;
+                pv.out_act = r0; pv.out_grp = grp2; pv.singles = d_nheads;
                 const u64 kw = ((u64)m + 63) / 64;
-                CUDA_CHECK(cudaMemsetAsync(r0, 0, (size_t)(m / 2) * 8, st));
                 CUDA_CHECK(cudaMemsetAsync(ebits8 + kw * 8, 0, 16, st));
                 CUDA_CHECK(cudaMemsetAsync(notdone + kw * 8, 0, 16, st));
-                CUDA_CHECK(cudaMemsetAsync(headbits + kw * 8, 0, 16, st));
+                CUDA_CHECK(cudaMemsetAsync(d_nheads, 0, 4, st));
                 pivot_classify_kernel<<<ntl, PV_NT, 0, st>>>(pv);
                 KERNEL_CHECK();
-                scan_tiles_kernel<<<1, 1024, 0, st>>>(pv_tile_e, ntl, d_total);
+                pivot_scan_kernel<<<1, 1024, 0, st>>>(pv_tile_e, pv_tile_c, ntl, d_total);
                 KERNEL_CHECK();
                 unsigned long long tot_e = 0;
                 read_back(&tot_e, d_total, 8, st);
@@ -2191,6 +2290,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                     t = ix.timer.begin("pivot_apply", (double)m * 28.0);
                     pivot_apply_kernel<<<ntl, PV_NT, 0, st>>>(pv);
                     KERNEL_CHECK();
+                    read_back(&n_single, d_nheads, 4, st);
                     ix.timer.end(t);
                     pivoted = true;
                     ids_are_heads = false;
@@ -2296,11 +2396,24 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
             t = ix.timer.begin("compact", (double)m * 4.0);
             u32 m2 = 0;
             if (pivoted) {
-                // E groups first (they kept their list order; singletons among them have retired), then the survivors of
-                // the sort; the list is assembled in r0 -- the counters there are dead -- which then changes places
-                // with the old list
-                const u32 mA = count_active<true>(headbits, m, tile_counts, d_total, st);
-                if (mA) scatter_active<true>(headbits, act, newgrpT, m, tile_counts, r0, grp2, st);
+                // E groups first (the pivot path has written them to r0 / grp2 in list order), then the survivors of
+                // the sort; r0 then changes places with the old list
+                u32 mA = n_e;
+                if (n_single) {
+                    // E groups of one member are final: out of the list (rare; through two buffers that are free now)
+                    const u64 kw = ((u64)n_e + 63) / 64;
+                    CUDA_CHECK(cudaMemsetAsync(headbits + kw * 8, 0, 16, st));
+                    pivot_keep_kernel<<<div_up_u(kw, 256), 256, 0, st>>>(grp2, n_e, (u64 *)headbits, kw);
+                    KERNEL_CHECK();
+                    mA = count_active<true>(headbits, n_e, tile_counts, d_total, st);
+                    if (mA != n_e - n_single) throw std::runtime_error("pivot path: single-member groups miscounted (internal error)");
+                    u32 *tmpA = const_cast<u32 *>(act);
+                    if (mA) {
+                        scatter_active<true>(headbits, r0, grp2, n_e, tile_counts, tmpA, newgrpT, st);
+                        CUDA_CHECK(cudaMemcpyAsync(r0, tmpA, (size_t)mA * 4, cudaMemcpyDeviceToDevice, st));
+                        CUDA_CHECK(cudaMemcpyAsync(grp2, newgrpT, (size_t)mA * 4, cudaMemcpyDeviceToDevice, st));
+                    }
+                }
                 u32 mB = 0;
                 if (mb) {
                     mB = count_active<false>(hb_big, mb, tile_counts, d_total, st);
