@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <functional>
 #include <vector>
 
 namespace b200sa {
@@ -792,7 +793,8 @@ __global__ void __launch_bounds__(RK_NT) rank_kernel(RankArgs a) {
     u32 s[RK_IPT];
     u64 kprev = 0, knext = 0;
     u32 sprev = 0, snext = 0;
-    if (j0 + RK_IPT <= m) {
+    // (lists made by the pivot path start at any element of a buffer: vector loads only where they are aligned)
+    if (j0 + RK_IPT <= m && ((((uintptr_t)(keys + j0)) | ((uintptr_t)(vals + j0))) & 15) == 0) {
         const uint4 *kp = (const uint4 *)(keys + j0);
 #pragma unroll
         for (int q = 0; q < RK_IPT / 2; ++q) {
@@ -1323,7 +1325,6 @@ __global__ void __launch_bounds__(CP_NT) scatter_pairs_kernel(const u8 *__restri
 // E part of the NEXT list written in place at the E members' prefix count -- no separate compaction).
 // ---------------------------------------------------------------------------------------------
 static constexpr int PV_NT = 256, PV_IPT = 8, PV_TILE = PV_NT * PV_IPT;
-static constexpr u32 PV_HEADFLAG = 0x80000000u;
 
 // exclusive prefix of `v` over an NT-thread block (wsum: NT / 32 words of shared memory; one barrier inside)
 template <int NT>
@@ -1344,21 +1345,21 @@ __device__ __forceinline__ u32 block_exclusive_u32(u32 v, u32 *wsum) {
 }
 
 struct PivotArgs {
-    const u32 *act, *grp;
-    u64 *keys;                    // round keys by list index (R members get their first key rewritten)
+    const u32 *act;               // values (suffixes) of the list
+    u64 *keys;                    // its round keys: [first row of the group : lo_bits | second key : lo_bits]; R members
+                                  // get their first key rewritten
     u32 m;
     int lo_bits;
-    const u32 *piv;               // by head row >> 1: the pivot key
+    u32 *piv;                     // by head row >> 1: the pivot key
     unsigned long long *cnt64;    // by head row >> 1: |E| << 32 | |L|
-    u8 *ebits8;                   // bit per list element: its second key equals the pivot
-    u8 *note8;                    // bit per list element: it goes through the sort (L or R)
+    u8 *ebits8, *lbits8, *rbits8; // bit per list element: its class
     u32 *tile_e;                  // [tiles + 1] E members per tile (exclusive offsets after the scan)
-    u32 *tile_c;                  // [tiles + 1] E members at or after the tile's last group head (| PV_HEADFLAG), or of
-                                  // the whole tile when no group begins in it; after the scan: E members of the group
-                                  // that reaches into the tile, counted over the tiles before it
+    unsigned long long *totals;   // [0] E members (written by the scan), [1] L members (accumulated here)
     u32 *sa, *rank, *primary;
-    u32 *out_act, *out_grp;       // the E part of the next list
+    u32 *out_act, *out_grp;       // where the E part goes in the next list
     u32 *singles;                 // [1] E groups of one member (final; they are taken out of the next list afterwards)
+    u32 *dropbits;                // bit per entry of the next list: such a member stands there
+    u32 out_base;                 // entry of the next list where this list's E part begins
 };
 
 // eight consecutive words of a list (vector loads where the tile is full)
@@ -1371,52 +1372,67 @@ __device__ __forceinline__ void pv_load8(const u32 *__restrict__ p, u64 j0, u32 
         for (int q = 0; q < PV_IPT; ++q) v[q] = j0 + q < m ? p[j0 + q] : 0u;
     }
 }
-// the low words of eight consecutive round keys
-__device__ __forceinline__ void pv_load8_lo(const u64 *__restrict__ k, u64 j0, u32 m, u32 lomask, u32 (&v)[PV_IPT]) {
+// eight consecutive round keys, split into group (first row) and second key
+__device__ __forceinline__ void pv_load8_keys(const u64 *__restrict__ k, u64 j0, u32 m, int lo_bits, u32 lomask,
+                                              u32 (&g)[PV_IPT], u32 (&lo)[PV_IPT]) {
     if (j0 + PV_IPT <= m && ((((uintptr_t)(k + j0)) & 15) == 0)) {
 #pragma unroll
         for (int q = 0; q < PV_IPT / 2; ++q) {
             const uint4 x = *(const uint4 *)(k + j0 + 2 * q);
-            v[2 * q] = x.x & lomask;
-            v[2 * q + 1] = x.z & lomask;
+            const u64 k0 = ((u64)x.y << 32) | x.x, k1 = ((u64)x.w << 32) | x.z;
+            g[2 * q] = (u32)(k0 >> lo_bits);
+            lo[2 * q] = x.x & lomask;
+            g[2 * q + 1] = (u32)(k1 >> lo_bits);
+            lo[2 * q + 1] = x.z & lomask;
         }
     } else {
 #pragma unroll
-        for (int q = 0; q < PV_IPT; ++q) v[q] = j0 + q < m ? (u32)k[j0 + q] & lomask : 0u;
+        for (int q = 0; q < PV_IPT; ++q) {
+            const u64 kk = j0 + q < m ? k[j0 + q] : 0ull;
+            g[q] = (u32)(kk >> lo_bits);
+            lo[q] = (u32)kk & lomask;
+        }
+    }
+}
+
+// lists made by the pivot path itself: the first member of every group publishes its second key and clears the
+// group's counters (for the round's list the kernels that make the keys do it)
+__global__ void __launch_bounds__(256) pivot_heads_kernel(const u64 *__restrict__ keys, u32 m, int lo_bits,
+                                                          u32 *__restrict__ piv, unsigned long long *__restrict__ cnt64) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const u64 k = keys[j];
+    const u32 g = (u32)(k >> lo_bits);
+    if (j == 0 || (u32)(keys[j - 1] >> lo_bits) != g) {
+        const u32 lomask = lo_bits >= 32 ? 0xffffffffu : ((1u << lo_bits) - 1u);
+        piv[g >> 1] = (u32)k & lomask;
+        cnt64[g >> 1] = 0ull;
     }
 }
 
 __global__ void __launch_bounds__(PV_NT) pivot_classify_kernel(PivotArgs a) {
-    __shared__ u32 wsum[PV_NT / 32], wmax[PV_NT / 32], wsum2[PV_NT / 32];
-    __shared__ u32 blkL, blkE, lmax_s;
+    __shared__ u32 wsum[PV_NT / 32];
+    __shared__ u32 blkL, blkE, allL;
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const u64 tile_base = (u64)blockIdx.x * PV_TILE;
     const u64 j0 = tile_base + (u64)tid * PV_IPT;
     const u32 lomask = a.lo_bits >= 32 ? 0xffffffffu : ((1u << a.lo_bits) - 1u);
     u32 g[PV_IPT], lo[PV_IPT];
-    pv_load8(a.grp, j0, a.m, g);
-    pv_load8_lo(a.keys, j0, a.m, lomask, lo);
-    const u32 g0 = a.grp[tile_base];  // the group the tile begins in: its counts are summed over the block first
-    u32 gprev = (j0 > 0 && j0 < a.m) ? a.grp[j0 - 1] : 0u;
+    pv_load8_keys(a.keys, j0, a.m, a.lo_bits, lomask, g, lo);
+    const u32 g0 = (u32)(a.keys[tile_base] >> a.lo_bits);  // the group the tile begins in: its counts are summed over the block first
     if (tid == 0) {
         blkL = 0;
         blkE = 0;
+        allL = 0;
     }
     __syncthreads();
-    u32 ebyte = 0, nbyte = 0;
-    u32 cur = 0, nL = 0, nE = 0, P = 0;
+    u32 ebyte = 0, lbyte = 0, rbyte = 0;
+    u32 cur = 0, nL = 0, nE = 0, P = 0, myL = 0;
     bool have = false, one_run = true;
-    u32 lh = 0, ea = 0;  // tile-local index + 1 of this thread's last group head; its E members at or after it
 #pragma unroll
     for (int q = 0; q < PV_IPT; ++q) {
         const u64 j = j0 + q;
         if (j >= a.m) break;
-        const bool head = j == 0 || g[q] != gprev;
-        gprev = g[q];
-        if (head) {
-            lh = (u32)(j - tile_base) + 1u;
-            ea = 0;
-        }
         if (!have || g[q] != cur) {
             if (have) {
                 one_run = false;
@@ -1428,12 +1444,13 @@ __global__ void __launch_bounds__(PV_NT) pivot_classify_kernel(PivotArgs a) {
             nE = 0;
             P = a.piv[cur >> 1];
         }
-        const bool isE = lo[q] == P;
-        nL += lo[q] < P ? 1u : 0u;
+        const bool isE = lo[q] == P, isL = lo[q] < P;
+        nL += isL ? 1u : 0u;
+        myL += isL ? 1u : 0u;
         nE += isE ? 1u : 0u;
-        ea += isE ? 1u : 0u;
         ebyte |= (isE ? 1u : 0u) << q;
-        nbyte |= (isE ? 0u : 1u) << q;
+        lbyte |= (isL ? 1u : 0u) << q;
+        rbyte |= ((isE || isL) ? 0u : 1u) << q;
     }
     // the run a thread ends with: whole warps inside one group add up before they touch a counter
     const u32 cur0 = __shfl_sync(0xffffffffu, cur, 0);
@@ -1458,123 +1475,47 @@ __global__ void __launch_bounds__(PV_NT) pivot_classify_kernel(PivotArgs a) {
     }
     if (j0 < a.m) {
         a.ebits8[j0 >> 3] = (u8)ebyte;
-        a.note8[j0 >> 3] = (u8)nbyte;
+        a.lbits8[j0 >> 3] = (u8)lbyte;
+        a.rbits8[j0 >> 3] = (u8)rbyte;
     }
-    // per-tile summaries: E members, and E members at or after the last group head
-    const u32 myE = (u32)__popc(ebyte);
-    const u32 c = __reduce_add_sync(0xffffffffu, myE);
-    const u32 mx = __reduce_max_sync(0xffffffffu, lh);
+    // E members of the tile; L members of the whole list
+    const u32 c = __reduce_add_sync(0xffffffffu, (u32)__popc(ebyte));
+    const u32 cl = __reduce_add_sync(0xffffffffu, myL);
     if (lane == 0) {
         wsum[warp] = c;
-        wmax[warp] = mx;
+        if (cl) atomicAdd(&allL, cl);
     }
-    __syncthreads();
-    if (tid == 0) {
-        u32 t = 0, l = 0;
-        for (int w = 0; w < PV_NT / 32; ++w) {
-            t += wsum[w];
-            l = max(l, wmax[w]);
-        }
-        a.tile_e[blockIdx.x] = t;
-        lmax_s = l;
-        if (blkL | blkE) atomicAdd(&a.cnt64[g0 >> 1], ((unsigned long long)blkE << 32) | (unsigned long long)blkL);
-    }
-    __syncthreads();
-    const u32 lmax = lmax_s;
-    u32 after = myE;  // (no head in the tile: everything counts)
-    if (lmax) {
-        const u32 owner = (lmax - 1u) / (u32)PV_IPT;
-        after = tid > owner ? myE : (tid == owner ? ea : 0u);
-    }
-    after = __reduce_add_sync(0xffffffffu, after);
-    if (lane == 0) wsum2[warp] = after;
     __syncthreads();
     if (tid == 0) {
         u32 t = 0;
-        for (int w = 0; w < PV_NT / 32; ++w) t += wsum2[w];
-        a.tile_c[blockIdx.x] = t | (lmax ? PV_HEADFLAG : 0u);
+        for (int w = 0; w < PV_NT / 32; ++w) t += wsum[w];
+        a.tile_e[blockIdx.x] = t;
+        if (blkL | blkE) atomicAdd(&a.cnt64[g0 >> 1], ((unsigned long long)blkE << 32) | (unsigned long long)blkL);
+        if (allL) atomicAdd(&a.totals[1], (unsigned long long)allL);
     }
-}
-
-// single block: tile_e -> exclusive offsets (total to *total); tile_c -> E members of the group that reaches into
-// each tile, counted over the tiles before it (a segmented scan: a tile in which a group begins starts a new sum)
-__global__ void __launch_bounds__(1024) pivot_scan_kernel(u32 *__restrict__ tile_e, u32 *__restrict__ tile_c, u32 ntiles,
-                                                          unsigned long long *__restrict__ total) {
-    __shared__ u64 wsum[32], wseg[32];
-    __shared__ u64 carry, ccarry;
-    constexpr u64 F = 1ull << 63;  // "a group begins in this stretch of tiles"
-    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        carry = 0;
-        ccarry = 0;
-    }
-    __syncthreads();
-    for (u32 base = 0; base < ntiles; base += 1024) {
-        const u32 i = base + threadIdx.x;
-        const u64 v = i < ntiles ? tile_e[i] : 0;
-        const u32 c0 = i < ntiles ? tile_c[i] : 0u;
-        // flag | value; combine(earlier, later) = later.flag ? later : (earlier.flag, earlier.value + later.value)
-        u64 x = (u64)(c0 & ~PV_HEADFLAG) | ((c0 & PV_HEADFLAG) ? F : 0ull);
-        u64 incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const u64 t = __shfl_up_sync(0xffffffffu, incl, o);
-            const u64 y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= (u32)o) {
-                incl += t;
-                if (!(x & F)) x = (y & F) | ((y & ~F) + x);
-            }
-        }
-        if (lane == 31) {
-            wsum[warp] = incl;
-            wseg[warp] = x;
-        }
-        __syncthreads();
-        u64 wb = 0;
-        u64 pre = ccarry;  // segment sum that reaches this warp: the carry, then the warps before it
-        for (u32 w = 0; w < warp; ++w) {
-            wb += wsum[w];
-            const u64 y = wseg[w];
-            pre = (y & F) ? (y & ~F) : pre + y;
-        }
-        const u64 excl = carry + wb + incl - v;
-        // value reaching into element i: the inclusive segment value of its predecessor (inside the warp that value
-        // already sums the warp's earlier lanes, unless a head cut it)
-        const u64 xp = __shfl_up_sync(0xffffffffu, x, 1);
-        const u64 into = lane == 0 ? pre : ((xp & F) ? (xp & ~F) : pre + xp);
-        if (i < ntiles) {
-            tile_e[i] = (u32)excl;
-            tile_c[i] = (u32)into;
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) {
-            carry = excl + v;
-            ccarry = (x & F) ? (x & ~F) : pre + x;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *total = carry;
 }
 
 __global__ void __launch_bounds__(PV_NT) pivot_apply_kernel(PivotArgs a) {
     // by tile-local index of a group head (index PV_TILE: the group that began before the tile)
-    __shared__ u16 s_eh[PV_TILE + 2];   // E members of the tile before the head
     __shared__ u32 s_id[PV_TILE + 1];   // new identifier of the E group, RANK_NONE: unchanged
     // the tile's E members in list order
-    __shared__ u32 sh_s[PV_TILE], sh_nh[PV_TILE], sh_row[PV_TILE], sh_rk[PV_TILE];
+    __shared__ u32 sh_s[PV_TILE], sh_nh[PV_TILE], sh_rk[PV_TILE];
+    __shared__ u32 sh_drop[PV_TILE / 32];  // E members of the tile that are alone in their group
     __shared__ u32 wmax[PV_NT / 32], wsum[PV_NT / 32];
+    __shared__ u32 any_single;
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const u64 tile_base = (u64)blockIdx.x * PV_TILE;
     const u64 j0 = tile_base + (u64)tid * PV_IPT;
     const u32 lomask = a.lo_bits >= 32 ? 0xffffffffu : ((1u << a.lo_bits) - 1u);
     u32 g[PV_IPT], lo[PV_IPT], s[PV_IPT], hidx[PV_IPT];
-    pv_load8(a.grp, j0, a.m, g);
+    pv_load8_keys(a.keys, j0, a.m, a.lo_bits, lomask, g, lo);
     pv_load8(a.act, j0, a.m, s);
-    pv_load8_lo(a.keys, j0, a.m, lomask, lo);
+    if (tid < PV_TILE / 32) sh_drop[tid] = 0;
+    if (tid == 0) any_single = 0;
     const u32 ebyte = j0 < a.m ? (u32)a.ebits8[j0 >> 3] : 0u;
     // tile-local index + 1 of the head of every element's group (0: it began before the tile)
     {
-        u32 pg = (j0 > 0 && j0 < a.m) ? a.grp[j0 - 1] : 0u;
+        u32 pg = (j0 > 0 && j0 < a.m) ? (u32)(a.keys[j0 - 1] >> a.lo_bits) : 0u;
         u32 run = 0;
 #pragma unroll
         for (int q = 0; q < PV_IPT; ++q) {
@@ -1601,16 +1542,16 @@ __global__ void __launch_bounds__(PV_NT) pivot_apply_kernel(PivotArgs a) {
     }
     // E members of the tile before this thread's elements
     const u32 excl = block_exclusive_u32<PV_NT>((u32)__popc(ebyte), wsum);
-    const u32 tile_off = a.tile_e[blockIdx.x], ecarry = a.tile_c[blockIdx.x];
-    // identifier of an E group: the old one while it lies inside the new range, else the far end of the range
-    auto new_id = [](u32 old, u32 nh, u32 nt) { return (old >= nh && old <= nt) ? RANK_NONE : (old < nh ? nt : nh); };
+    const u32 tile_off = a.tile_e[blockIdx.x];
+    // identifier of an E group: the old one while it lies inside the new range, else the middle of the range (a
+    // group that loses members at one end, or at both, keeps it for many rounds)
+    auto new_id = [](u32 old, u32 nh, u32 nt) { return (old >= nh && old <= nt) ? RANK_NONE : nh + (nt - nh) / 2u; };
 #pragma unroll
     for (int q = 0; q < PV_IPT; ++q) {
         const u64 j = j0 + q;
         if (j < a.m && hidx[q] == (u32)(j - tile_base) + 1u) {
             const unsigned long long c = a.cnt64[g[q] >> 1];
             const u32 nL = (u32)c, nE = (u32)(c >> 32), ix = hidx[q] - 1u;
-            s_eh[ix] = (u16)(excl + (u32)__popc(ebyte & ((1u << q) - 1u)));
             s_id[ix] = nE > 1u ? new_id(a.rank[s[q]], g[q] + nL, g[q] + nL + nE - 1u) : RANK_NONE;
         }
     }
@@ -1637,15 +1578,18 @@ __global__ void __launch_bounds__(PV_NT) pivot_apply_kernel(PivotArgs a) {
             }
             if ((ebyte >> q) & 1u) {
                 const u32 el = excl + (u32)__popc(ebyte & ((1u << q) - 1u));
-                const u32 within = hidx[q] ? el - (u32)s_eh[hidx[q] - 1u] : el + ecarry;
-                const u32 nh = cur + nL, row = nh + within;
+                const u32 nh = cur + nL;
                 sh_s[el] = s[q];
                 sh_nh[el] = nh;
-                sh_row[el] = row;
-                u32 rk = RANK_NONE;
+                u32 rk;
                 if (nE == 1u) {
-                    rk = row;  // alone: final
+                    // alone: final.  (The rows of members that stay in the list are written when they leave it.)
+                    rk = nh;
+                    a.sa[nh] = s[q];
+                    if (s[q] == 0) *a.primary = nh;
                     atomicAdd(a.singles, 1u);
+                    atomicOr(&sh_drop[el >> 5], 1u << (el & 31u));
+                    any_single = 1;
                 } else {
                     rk = s_id[hidx[q] ? hidx[q] - 1u : (u32)PV_TILE];
                 }
@@ -1656,33 +1600,31 @@ __global__ void __launch_bounds__(PV_NT) pivot_apply_kernel(PivotArgs a) {
         }
     }
     __syncthreads();
-    // consecutive threads write consecutive entries of the next list and (inside a group) consecutive rows
+    // consecutive threads write consecutive entries of the next list
     u32 ne = 0;  // E members of the tile (the warp totals of the prefix sum above)
     for (int w = 0; w < PV_NT / 32; ++w) ne += wsum[w];
     for (u32 k = tid; k < ne; k += PV_NT) {
-        const u32 sv = sh_s[k], row = sh_row[k], rk = sh_rk[k];
+        const u32 sv = sh_s[k], rk = sh_rk[k];
         a.out_act[tile_off + k] = sv;
         a.out_grp[tile_off + k] = sh_nh[k];
-        a.sa[row] = sv;
         if (rk != RANK_NONE) a.rank[sv] = rk;
-        if (sv == 0) *a.primary = row;
+    }
+    if (any_single) {
+        for (u32 k = tid; k < ne; k += PV_NT)
+            if ((sh_drop[k >> 5] >> (k & 31u)) & 1u) {
+                const u32 p = a.out_base + tile_off + k;
+                atomicOr(&a.dropbits[p >> 5], 1u << (p & 31u));
+            }
     }
 }
 
-// E part of the list the pivot path has written: bit j is set unless entry j is a group of its own
-__global__ void __launch_bounds__(256) pivot_keep_kernel(const u32 *__restrict__ grp, u32 ne, u64 *__restrict__ bits64,
-                                                         u64 nwords) {
+// drop bitmap -> keep bitmap over the first n entries (one thread per 64 entries)
+__global__ void __launch_bounds__(256) pivot_keep_kernel(u64 *__restrict__ bits64, u32 n, u64 nwords) {
     const u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwords) return;
-    u64 v = 0;
     const u64 base = w * 64;
-    for (u32 i = 0; i < 64 && base + i < ne; ++i) {
-        const u64 j = base + i;
-        const u32 g = grp[j];
-        const bool single = (j == 0 || grp[j - 1] != g) && (j + 1 >= ne || grp[j + 1] != g);
-        v |= (u64)(single ? 0u : 1u) << i;
-    }
-    bits64[w] = v;
+    const u64 valid = (u64)n - base >= 64 ? ~0ull : ((1ull << ((u64)n - base)) - 1ull);
+    bits64[w] = ~bits64[w] & valid;
 }
 
 // groups in a grouped list (positions whose group differs from the one before)
@@ -2201,15 +2143,17 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
         u8 *notdone = ar.get<u8>(bm_bytes), *headB = ar.get<u8>(bm_bytes);
         // pivot path: per-group tables by (head row) / 2, E bitmap, per-tile counts
         const size_t pv_entries = (size_t)len / 2 + 2;
-        if (pivot_on && !ar.can_fit(pv_entries * 12 + bm_bytes, mem_margin)) pivot_on = false;
+        if (pivot_on && !ar.can_fit(pv_entries * 12 + 2 * bm_bytes, mem_margin)) pivot_on = false;
         u8 *ebits8 = pivot_on ? ar.get<u8>(bm_bytes) : nullptr;
         u32 *pv_tile_e = pivot_on ? ar.get<u32>((size_t)div_up_u(m_init, PV_TILE) + 2) : nullptr;
-        u32 *pv_tile_c = pivot_on ? ar.get<u32>((size_t)div_up_u(m_init, PV_TILE) + 2) : nullptr;
+        u8 *rbits8 = pivot_on ? ar.get<u8>(bm_bytes) : nullptr;
+        unsigned long long *d_pvtot = ar.get<unsigned long long>(2);
         unsigned long long *pv_cnt = pivot_on ? ar.get<unsigned long long>(pv_entries) : nullptr;
         u32 *pv_piv = pivot_on ? ar.get<u32>(pv_entries) : nullptr;
         // large groups or small ones?  (decides which of the two split paths a round tries first)
         const u32 pivot_min = (u32)std::max(2, env_int("B200SA_PIVOT_MIN", 1 << 16));
         const bool pivot_force = env_int("B200SA_PIVOT_FORCE", 0) != 0;  // (tests: every round, whatever it finds)
+        const u32 pivot_sub_min = std::max(2u, pivot_min / 16u);  // lists of the pivot path that are split again
         bool prefer_pivot = pivot_force;
         if (pivot_on && !pivot_force && m >= pivot_min) {
             CUDA_CHECK(cudaMemsetAsync(d_nheads, 0, 4, st));
@@ -2263,43 +2207,163 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
             KERNEL_CHECK();
             ix.timer.end(t);
 
-            // ---- large groups that mostly stay together: split around a pivot key, only the minority is sorted ----
+            // ---- large groups that mostly stay together: split around a pivot key (pivot_classify_kernel).  The
+            // E part of every group goes straight into the next list; its L members and its R members, each
+            // compacted into a list of their own, are split again the same way (a group whose members carry two
+            // or three distinct second keys -- a Fibonacci string -- never reaches the radix sort); lists that are
+            // small, or whose groups scatter, are sorted ----
             bool pivoted = false;
-            u32 n_e = 0, n_single = 0;
+            u32 m2 = 0;
             if (try_pivot) {
-                t = ix.timer.begin("pivot_classify", (double)m * 12.0);
-                const u32 ntl = div_up_u(m, PV_TILE);
-                PivotArgs pv{};
-                pv.act = act; pv.grp = grp; pv.keys = rkA; pv.m = m; pv.lo_bits = lo_bits;
-                pv.piv = pv_piv; pv.cnt64 = pv_cnt; pv.ebits8 = ebits8; pv.note8 = notdone;
-                pv.tile_e = pv_tile_e; pv.tile_c = pv_tile_c; pv.sa = sa; pv.rank = rank; pv.primary = d_primary.ptr;
-                pv.out_act = r0; pv.out_grp = grp2; pv.singles = d_nheads;
-                const u64 kw = ((u64)m + 63) / 64;
-                CUDA_CHECK(cudaMemsetAsync(ebits8 + kw * 8, 0, 16, st));
-                CUDA_CHECK(cudaMemsetAsync(notdone + kw * 8, 0, 16, st));
-                CUDA_CHECK(cudaMemsetAsync(d_nheads, 0, 4, st));
-                pivot_classify_kernel<<<ntl, PV_NT, 0, st>>>(pv);
-                KERNEL_CHECK();
-                pivot_scan_kernel<<<1, 1024, 0, st>>>(pv_tile_e, pv_tile_c, ntl, d_total);
-                KERNEL_CHECK();
-                unsigned long long tot_e = 0;
-                read_back(&tot_e, d_total, 8, st);
-                ix.timer.end(t);
-                n_e = (u32)tot_e;
-                if ((u64)n_e * 3 >= (u64)m || pivot_force) {
-                    t = ix.timer.begin("pivot_apply", (double)m * 28.0);
-                    pivot_apply_kernel<<<ntl, PV_NT, 0, st>>>(pv);
+                const int key_bits_here = key_bits;
+                PivotArgs base{};
+                base.lo_bits = lo_bits; base.piv = pv_piv; base.cnt64 = pv_cnt; base.ebits8 = ebits8; base.lbits8 = notdone;
+                base.rbits8 = rbits8; base.tile_e = pv_tile_e; base.totals = d_pvtot; base.sa = sa; base.rank = rank;
+                base.primary = d_primary.ptr; base.singles = d_nheads;
+                u32 out_n = 0;           // entries of the next list (r0 / grp2) written so far
+                u64 pv_e = 0, pv_sorted = 0;
+                auto classify = [&](u64 *kx, const u32 *vx, u32 n, bool publish, u32 &ne, u32 &nl) {
+                    PivotArgs pv = base;
+                    pv.keys = kx; pv.act = vx; pv.m = n;
+                    const u32 ntl = div_up_u(n, PV_TILE);
+                    const u64 kw = ((u64)n + 63) / 64;
+                    CUDA_CHECK(cudaMemsetAsync(ebits8 + kw * 8, 0, 16, st));
+                    CUDA_CHECK(cudaMemsetAsync(notdone + kw * 8, 0, 16, st));
+                    CUDA_CHECK(cudaMemsetAsync(rbits8 + kw * 8, 0, 16, st));
+                    CUDA_CHECK(cudaMemsetAsync(d_pvtot, 0, 16, st));
+                    if (publish) {
+                        pivot_heads_kernel<<<div_up_u(n, 256), 256, 0, st>>>(kx, n, lo_bits, pv_piv, pv_cnt);
+                        KERNEL_CHECK();
+                    }
+                    pivot_classify_kernel<<<ntl, PV_NT, 0, st>>>(pv);
                     KERNEL_CHECK();
-                    read_back(&n_single, d_nheads, 4, st);
-                    ix.timer.end(t);
+                    scan_tiles_kernel<<<1, 1024, 0, st>>>(pv_tile_e, ntl, d_pvtot);
+                    KERNEL_CHECK();
+                    unsigned long long tot[2] = {0, 0};
+                    read_back(tot, d_pvtot, 16, st);
+                    ne = (u32)tot[0];
+                    nl = (u32)tot[1];
+                };
+                // radix sort of one list, new ranks, survivors appended to the next list
+                auto sort_list = [&](u64 *kx, u32 *vx, u32 n, u64 *ky, u32 *vy, u32 *ng) {
+                    int npass = (key_bits_here + RB - 1) / RB;
+                    int tt = ix.timer.begin("round_hist", (double)n * 8.0);
+                    S::histogram(kx, n, 0, key_bits_here, npass, hist, st);
+                    S::scan(hist, n, npass, uniform, st);
+                    read_back(huniform, uniform, (size_t)npass * 4, st);
+                    ix.timer.end(tt);
+                    u64 *rin = kx, *rout = ky;
+                    u32 *ain = vx, *aout = vy;
+                    for (int p = 0; p < npass; ++p) {
+                        if (huniform[p]) continue;
+                        int bits_here = std::min(RB, key_bits_here - p * RB);
+                        tt = ix.timer.begin("radix_pass", (double)n * 24.0);
+                        S::pass(rin, ain, rout, aout, n, p * RB, bits_here, hist + (size_t)p * BINS, lookback, ticket, st);
+                        ix.timer.end(tt);
+                        ix.stats.passes_elems += n;
+                        std::swap(rin, rout);
+                        std::swap(ain, aout);
+                    }
+                    tt = ix.timer.begin("round_rank", (double)n * 20.0);
+                    CUDA_CHECK(cudaMemsetAsync(headB, 0, (((size_t)n + 63) / 64 + 2) * 8, st));
+                    RankArgs rr{};
+                    rr.keys = rin; rr.vals = ain; rr.m = n; rr.gs = lo_bits; rr.keymask = ~0ull; rr.K0 = 0; rr.n = ix.n;
+                    rr.rank = rank; rr.newgrp = ng; rr.scatter_all = 0; rr.sa_out = sa; rr.headbits = headB;
+                    rr.bwt = nullptr; rr.prev_shift = 0; rr.packed = ix.packed; rr.bits = b;
+                    rr.primary = d_primary.ptr;
+                    rr.always_write = 1;
+                    rank_kernel<<<div_up_u(n, RK_TILE), RK_NT, 0, st>>>(rr);
+                    KERNEL_CHECK();
+                    ix.timer.end(tt);
+                    tt = ix.timer.begin("compact", (double)n * 4.0);
+                    const u32 mB = count_active<false>(headB, n, tile_counts, d_total, st);
+                    if (mB) scatter_active<false>(headB, ain, ng, n, tile_counts, r0 + out_n, grp2 + out_n, st);
+                    out_n += mB;
+                    pv_sorted += n;
+                    ix.timer.end(tt);
+                };
+                // one list: keys / values in (kx, vx); (ky, vy) = the other buffer pair over the same index range;
+                // ng = as many free words (new ranks by sorted index)
+                std::function<void(int, u64 *, u32 *, u32, u64 *, u32 *, u32 *, u32, u32)> process;
+                process = [&](int level, u64 *kx, u32 *vx, u32 n, u64 *ky, u32 *vy, u32 *ng, u32 ne, u32 nl) {
+                    // (level 0 arrives classified)
+                    bool go = level == 0;
+                    if (level > 0 && level < 8 && n >= pivot_sub_min) {
+                        int tt = ix.timer.begin("pivot_classify", (double)n * 16.0);
+                        classify(kx, vx, n, true, ne, nl);
+                        ix.timer.end(tt);
+                        go = (u64)ne * 3 >= (u64)n || pivot_force;
+                    }
+                    if (!go) {
+                        sort_list(kx, vx, n, ky, vy, ng);
+                        return;
+                    }
+                    int tt = ix.timer.begin("pivot_apply", (double)n * 24.0);
+                    PivotArgs pv = base;
+                    pv.keys = kx; pv.act = vx; pv.m = n;
+                    pv.out_act = r0 + out_n; pv.out_grp = grp2 + out_n; pv.out_base = out_n; pv.dropbits = (u32 *)headbits;
+                    pivot_apply_kernel<<<div_up_u(n, PV_TILE), PV_NT, 0, st>>>(pv);
+                    KERNEL_CHECK();
+                    ix.timer.end(tt);
+                    out_n += ne;
+                    pv_e += ne;
+                    const u32 nr = n - ne - nl;
+                    if (nl | nr) {
+                        tt = ix.timer.begin("compact_big", (double)n * 0.25 + (double)(nl + nr) * 24.0);
+                        const u32 sub = compaction_sub(n);
+                        if (nl) {
+                            const u32 cnt = count_active<true>(notdone, n, tile_counts, d_total, st);
+                            if (cnt != nl) throw std::runtime_error("pivot path: L members miscounted (internal error)");
+                            scatter_pairs_kernel<<<div_up_u(n, (u64)CP_TILE * sub), CP_NT, 0, st>>>(notdone, kx, vx, n, sub, tile_counts, ky, vy);
+                            KERNEL_CHECK();
+                        }
+                        if (nr) {
+                            const u32 cnt = count_active<true>(rbits8, n, tile_counts, d_total, st);
+                            if (cnt != nr) throw std::runtime_error("pivot path: R members miscounted (internal error)");
+                            scatter_pairs_kernel<<<div_up_u(n, (u64)CP_TILE * sub), CP_NT, 0, st>>>(rbits8, kx, vx, n, sub, tile_counts, ky + nl, vy + nl);
+                            KERNEL_CHECK();
+                        }
+                        ix.timer.end(tt);
+                        if (nl) process(level + 1, ky, vy, nl, kx, vx, ng, 0, 0);
+                        if (nr) process(level + 1, ky + nl, vy + nl, nr, kx + nl, vx + nl, ng + nl, 0, 0);
+                    }
+                };
+                t = ix.timer.begin("pivot_classify", (double)m * 16.0);
+                u32 n_e = 0, n_l = 0;
+                classify(rkA, act, m, false, n_e, n_l);
+                ix.timer.end(t);
+                if ((u64)n_e * 3 >= (u64)m || pivot_force) {
                     pivoted = true;
                     ids_are_heads = false;
                     chain_on = false;
                     pivot_fails = 0;
-                    ix.stats.sorted_total -= n_e;
+                    CUDA_CHECK(cudaMemsetAsync(d_nheads, 0, 4, st));
+                    CUDA_CHECK(cudaMemsetAsync(headbits, 0, (((size_t)m + 63) / 64 + 2) * 8, st));  // (no entry of the next list is dropped)
+                    // (the old list is dead once its L and R members have been copied out: its value buffer is the
+                    // scratch of the deeper levels; the old group heads are dead already, the keys carry them)
+                    process(0, rkA, const_cast<u32 *>(act), m, rkB, bvals, grp, n_e, n_l);
+                    ix.stats.sorted_total -= (u64)m - pv_sorted;
                     ix.stats.pivot_rounds++;
-                    ix.stats.pivot_elems += n_e;
+                    ix.stats.pivot_elems += pv_e;
                     if (bwt_rows) need_bwt_fix = true;  // (this path does not write BWT rows)
+                    // E groups of one member are final: out of the list (rare; through two buffers that are free now)
+                    u32 n_single = 0;
+                    read_back(&n_single, d_nheads, 4, st);
+                    m2 = out_n;
+                    if (n_single) {
+                        // the survivors are copied to the old list's buffers (free now), which stay the list
+                        t = ix.timer.begin("compact", (double)out_n * 16.0);
+                        const u64 kw = ((u64)out_n + 63) / 64;
+                        pivot_keep_kernel<<<div_up_u(kw, 256), 256, 0, st>>>((u64 *)headbits, out_n, kw);
+                        KERNEL_CHECK();
+                        m2 = count_active<true>(headbits, out_n, tile_counts, d_total, st);
+                        if (m2 != out_n - n_single) throw std::runtime_error("pivot path: single-member groups miscounted (internal error)");
+                        if (m2) scatter_active<true>(headbits, r0, grp2, out_n, tile_counts, const_cast<u32 *>(act), newgrpT, st);
+                        std::swap(grp2, newgrpT);
+                        ix.timer.end(t);
+                    } else {
+                        std::swap(act, r0);
+                    }
                 } else {  // the groups scatter: nothing was changed, the round goes on as usual; back off 2, 4, 8 ... rounds
                     pivot_pause = 2 << std::min(pivot_fails, 4);
                     ++pivot_fails;
@@ -2308,9 +2372,10 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 --pivot_pause;
             }
 
+            if (!pivoted) {
             // ---- groups of up to RS_GMAX members are ordered where they stand (round_small_kernel) ----
             u32 handled = 0;
-            if (!pivoted && small_on && small_pause == 0) {
+            if (small_on && small_pause == 0) {
                 t = ix.timer.begin("round_small", (double)m * 28.0);
                 const u64 kw = ((u64)m + 63) / 64;
                 CUDA_CHECK(cudaMemsetAsync(headbits + kw * 8, 0, 16, st));
@@ -2334,10 +2399,10 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
             } else if (small_pause > 0) {
                 --small_pause;
             }
-            const bool split = pivoted || handled != 0;  // part of the list has been placed without the sort
+            const bool split = handled != 0;  // part of the list has been placed without the sort
 
             // ---- everything else: radix sort of (group, rank) keys, new ranks from the sorted list ----
-            const u32 mb = pivoted ? m - n_e : m - handled;
+            const u32 mb = m - handled;
             const u64 *bk = rkA;   // keys / values of the elements that go through the sort
             const u32 *bv = act;
             u64 *k_other = rkB;
@@ -2394,34 +2459,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
             }
             // ---- next active set: the survivors of both paths, one after the other (groups stay contiguous) ----
             t = ix.timer.begin("compact", (double)m * 4.0);
-            u32 m2 = 0;
-            if (pivoted) {
-                // E groups first (the pivot path has written them to r0 / grp2 in list order), then the survivors of
-                // the sort; r0 then changes places with the old list
-                u32 mA = n_e;
-                if (n_single) {
-                    // E groups of one member are final: out of the list (rare; through two buffers that are free now)
-                    const u64 kw = ((u64)n_e + 63) / 64;
-                    CUDA_CHECK(cudaMemsetAsync(headbits + kw * 8, 0, 16, st));
-                    pivot_keep_kernel<<<div_up_u(kw, 256), 256, 0, st>>>(grp2, n_e, (u64 *)headbits, kw);
-                    KERNEL_CHECK();
-                    mA = count_active<true>(headbits, n_e, tile_counts, d_total, st);
-                    if (mA != n_e - n_single) throw std::runtime_error("pivot path: single-member groups miscounted (internal error)");
-                    u32 *tmpA = const_cast<u32 *>(act);
-                    if (mA) {
-                        scatter_active<true>(headbits, r0, grp2, n_e, tile_counts, tmpA, newgrpT, st);
-                        CUDA_CHECK(cudaMemcpyAsync(r0, tmpA, (size_t)mA * 4, cudaMemcpyDeviceToDevice, st));
-                        CUDA_CHECK(cudaMemcpyAsync(grp2, newgrpT, (size_t)mA * 4, cudaMemcpyDeviceToDevice, st));
-                    }
-                }
-                u32 mB = 0;
-                if (mb) {
-                    mB = count_active<false>(hb_big, mb, tile_counts, d_total, st);
-                    if (mB) scatter_active<false>(hb_big, sorted_vals, grp, mb, tile_counts, r0 + mA, grp2 + mA, st);
-                }
-                m2 = mA + mB;
-                std::swap(act, r0);
-            } else if (!handled) {
+            if (!handled) {
                 // (the whole list went through the sort: its survivors go to the value buffer the sort left free)
                 u32 *dst = sorted_vals == act ? act2 : const_cast<u32 *>(act);
                 m2 = count_active<false>(hb_big, m, tile_counts, d_total, st);
@@ -2444,6 +2482,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 if (dst == act2) std::swap(act, act2);
             }
             ix.timer.end(t);
+            }  // !pivoted
             u32 nlazy = 0;
             read_back(&nlazy, d_lazy, 4, st);
             ix.stats.lazy_lookups += nlazy;
