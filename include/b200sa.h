@@ -86,7 +86,8 @@ struct b200sa_stats {
     uint64_t pivot_elems;      /* list elements of doubling rounds that stayed with their group's pivot key and
                                   skipped the radix sort (periodic texts: nearly all), summed over rounds */
     uint32_t pivot_rounds;     /* doubling rounds that split their groups around a pivot key */
-    uint32_t reserved0;
+    uint32_t pair_placed;      /* suffixes in groups of two equal initial keys (a position of a repeat and the same
+                                  position of its copy) decided by one text comparison per repeat */
 };
 
 /* ---- construction ------------------------------------------------------------------------

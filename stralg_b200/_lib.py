@@ -42,7 +42,7 @@ class Stats(C.Structure):
         ("shallow_buckets", C.c_uint32), ("chain_rounds", C.c_uint32), ("shallow_elems", C.c_uint64),
         ("chain_elems", C.c_uint64), ("lazy_lookups", C.c_uint64), ("resolved_small", C.c_uint64),
         ("small_path_elems", C.c_uint64), ("pivot_elems", C.c_uint64), ("pivot_rounds", C.c_uint32),
-        ("reserved0", C.c_uint32),
+        ("pair_placed", C.c_uint32),
     ]
 
 

@@ -559,7 +559,7 @@ int b200sa_stats(const b200sa_index *idx, struct b200sa_stats *out) {
     out->small_path_elems = ix.stats.small_path_elems;
     out->pivot_elems = ix.stats.pivot_elems;
     out->pivot_rounds = ix.stats.pivot_rounds;
-    out->reserved0 = 0;
+    out->pair_placed = ix.stats.pair_placed;
     return 0;
 }
 

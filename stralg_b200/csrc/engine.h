@@ -35,6 +35,7 @@ struct BuildStats {
     u64 small_path_elems; // list elements ordered inside their tile (groups of up to 32), summed over rounds
     u32 pivot_rounds;     // doubling rounds that split their groups around a pivot key (sa_build.cu: pivot path)
     u64 pivot_elems;      // list elements that stayed with the pivot key and skipped the sort, summed over rounds
+    u32 pair_placed;      // suffixes in groups of two that one text comparison per repeat decided after round 0
 };
 
 // Occurrence-table layouts

@@ -311,12 +311,9 @@ __device__ __forceinline__ u32 lazy_rank_of(const LazyRank &lr, u32 t) {
             else hi = mid;
         }
     }
-    const bool t_short = (u64)t + (u64)lr.K > (u64)lr.n;
-    if (t_short) {
-        while (lr.sa0[lo] != t) ++lo;
-    } else {
-        while ((u64)lr.sa0[lo] + (u64)lr.K > (u64)lr.n) ++lo;
-    }
+    // t stands in the run of rows that share its key (short suffixes first; a pair that the text decided holds
+    // two long ones): the row that holds it
+    while (lo + 1 < lr.len && lr.sa0[lo] != t) ++lo;
     return lo;
 }
 
@@ -1627,6 +1624,232 @@ __global__ void __launch_bounds__(256) pivot_keep_kernel(u64 *__restrict__ bits6
     bits64[w] = ~bits64[w] & valid;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pairs decided by the text.  After round 0 of a text with long exact repeats nearly every group of
+// equal keys is a PAIR {s, s + D}: a position of a copied segment and the same position of its copy.
+// All pairs of one segment have the same answer: consecutive pairs (s, s + D), (s + 1, s + 1 + D), ...
+// overlap in K - 1 symbols, so the two suffixes of every pair of the run agree up to the end of the
+// run's last pair, position e, and are told apart by what follows text[e + K) on the two sides -- ONE
+// comparison of a few symbols for thousands of pairs, instead of doubling rounds that find the end
+// of the segment by its ranks.  Three passes:
+//   pair_partner  (list order)  partner[s] for the two members of every group of exactly two
+//   pair_runs     (text order)  the run a pair belongs to ends at the first position whose successor
+//                               is not the successor's partner's predecessor; the comparison there
+//                               gives 1 (this side is smaller) / 2 (the partner is) / 0 (undecided
+//                               within the symbols looked at, or the run is longer than the cap)
+//   pair_place    (list order)  decided pairs take their two rows in the right order (the BWT rows
+//                               swap with them) and leave the list; their ranks are never materialised
+// Everything else -- larger groups, undecided pairs -- goes through the doubling rounds as before.
+// ---------------------------------------------------------------------------------------------
+static constexpr int PR_NT = 256, PR_BPT = 8, PR_TILE = PR_NT * PR_BPT;
+static constexpr u32 PR_CAP = 1u << 16;   // longest run followed beyond a tile (longer runs stay undecided)
+static constexpr int PR_CMP_WORDS = 256;  // 64-bit windows compared at the end of a run before giving up (a multiple of 32)
+
+__global__ void __launch_bounds__(256) pair_partner_kernel(const u32 *__restrict__ act, const u32 *__restrict__ grp, u32 m,
+                                                           u32 *__restrict__ partner, u32 *__restrict__ npairs) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool pair = false;
+    if (j + 1 < m) {
+        const u32 g = grp[j];
+        pair = (j == 0 || grp[j - 1] != g) && grp[j + 1] == g && (j + 2 >= m || grp[j + 2] != g);
+        if (pair) {
+            const u32 s1 = act[j], s2 = act[j + 1];
+            partner[s1] = s2;
+            partner[s2] = s1;
+        }
+    }
+    const u32 c = (u32)__popc(__ballot_sync(0xffffffffu, pair));
+    if ((threadIdx.x & 31u) == 0 && c) atomicAdd(npairs, c);
+}
+
+// suffixes u and v (u != v): 1 = u is the smaller one, 2 = v is, 0 = undecided within PR_CMP_WORDS windows.
+// Warp-cooperative (all lanes call it with the same arguments, the result is uniform): lane l looks at window
+// 32 * step + l, the first lane that sees a difference -- or the end of a suffix -- decides.
+__device__ __forceinline__ u32 pair_compare_warp(const u64 *__restrict__ packed, int bits, u32 n, u64 u, u64 v) {
+    const u32 lane = threadIdx.x & 31u;
+    const u32 spw = 64u / (u32)bits;
+#pragma unroll 1
+    for (int it = 0; it < PR_CMP_WORDS / 32; ++it) {
+        const u64 off = (u64)(it * 32 + (int)lane) * spw;
+        const u64 uu = u + off, vv = v + off;
+        const u64 ru = uu < n ? n - uu : 0ull, rv = vv < n ? n - vv : 0ull;  // symbols left before the sentinel
+        const u64 c = min((u64)spw, min(ru, rv));
+        u32 res = 0;
+        if (c) {
+            const u64 x = window_at(packed, uu, bits), y = window_at(packed, vv, bits);
+            const u64 mask = c * bits >= 64 ? ~0ull : ~(~0ull >> (c * bits));
+            if ((x ^ y) & mask) res = x > y ? 2u : 1u;  // (big-endian windows: the first differing symbol decides)
+        }
+        // one suffix ends inside this window (or before it): the sentinel is the smallest symbol
+        if (!res && c < spw) res = ru < rv ? 1u : 2u;
+        const u32 bal = __ballot_sync(0xffffffffu, res != 0u);
+        if (bal) return __shfl_sync(0xffffffffu, res, __ffs((int)bal) - 1);
+    }
+    return 0u;
+}
+
+// partner[] is padded with RANK_NONE far beyond len; ord[] is zeroed by the caller
+__global__ void __launch_bounds__(PR_NT) pair_runs_kernel(const u32 *__restrict__ partner, u32 n, const u64 *__restrict__ packed,
+                                                          int bits, int K, u8 *__restrict__ ord) {
+    __shared__ u8 RES[PR_TILE];        // result of the comparison at the run ends inside the tile
+    __shared__ u16 qpos[PR_TILE];      // the run ends inside the tile
+    __shared__ u32 qn;
+    __shared__ u32 wmin[PR_NT / 32];
+    __shared__ u32 beyond[2];          // first position at or after the end of the tile that ends a run; the result there
+    __shared__ u8 lastlink[PR_NT];
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u64 T0 = (u64)blockIdx.x * PR_TILE;
+    const u64 p0 = T0 + (u64)tid * PR_BPT;
+    u32 v[PR_BPT + 1];
+    {
+        const uint4 a = *(const uint4 *)(partner + p0), b = *(const uint4 *)(partner + p0 + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        v[8] = partner[p0 + 8];
+    }
+    u32 abits = 0, lbits = 0;  // bit i: position p0 + i is a pair member / its pair is followed by the next position's pair
+#pragma unroll
+    for (int i = 0; i < PR_BPT; ++i) {
+        const bool a = v[i] != RANK_NONE;
+        abits |= (a ? 1u : 0u) << i;
+        lbits |= ((a && v[i + 1] == v[i] + 1u) ? 1u : 0u) << i;
+    }
+    lastlink[tid] = (u8)((lbits >> (PR_BPT - 1)) & 1u);
+    if (tid == 0) qn = 0;
+    if (!__syncthreads_or((int)abits)) return;  // no pair member in this tile
+    const u32 NONEPOS = 0xffffffffu;
+    const u32 zeros = ~lbits & ((1u << PR_BPT) - 1u);
+    const u32 firstz = zeros ? tid * PR_BPT + (u32)(__ffs((int)zeros) - 1) : NONEPOS;
+    u32 sm = firstz;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_down_sync(0xffffffffu, sm, o);
+        if (lane + (u32)o < 32u) sm = min(sm, t);
+    }
+    if (lane == 0) wmin[warp] = sm;
+    u32 after = __shfl_down_sync(0xffffffffu, sm, 1);  // min over the later threads of this warp
+    if (lane == 31) after = NONEPOS;
+    // run ends inside the chunk (pair members whose pair is not followed by the next position's pair) are queued
+    {
+        u32 ends = abits & zeros;
+        while (ends) {
+            const int i = __ffs((int)ends) - 1;
+            ends &= ends - 1;
+            qpos[atomicAdd(&qn, 1u)] = (u16)(tid * PR_BPT + (u32)i);
+        }
+    }
+    __syncthreads();
+    for (u32 ww = warp + 1; ww < PR_NT / 32; ++ww) after = min(after, wmin[ww]);
+    // the run that leaves the tile: warp 0 looks for its end (at most PR_CAP positions ahead, 256 per step)
+    if (warp == 0) {
+        u32 found = NONEPOS;
+        if (lastlink[PR_NT - 1]) {
+            for (u32 it = 0; it < PR_CAP / 256u && found == NONEPOS; ++it) {
+                const u64 at = T0 + PR_TILE + (u64)it * 256u + (u64)lane * 8u;
+                const uint4 a = *(const uint4 *)(partner + at), b = *(const uint4 *)(partner + at + 4);
+                const u32 x[9] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, partner[at + 8]};
+                u32 nz = 0;  // bit i: position at + i ends a run
+#pragma unroll
+                for (int i = 0; i < 8; ++i) nz |= ((x[i] != RANK_NONE && x[i + 1] == x[i] + 1u) ? 0u : 1u) << i;
+                const u32 bal = __ballot_sync(0xffffffffu, nz != 0u);
+                if (bal) {
+                    const int l0 = __ffs((int)bal) - 1;
+                    const u32 z0 = __shfl_sync(0xffffffffu, nz, l0);
+                    found = (u32)PR_TILE + it * 256u + (u32)l0 * 8u + (u32)(__ffs((int)z0) - 1);
+                }
+            }
+        }
+        u32 r = 0;
+        if (found != NONEPOS) {  // (uniform over the warp)
+            const u64 e = T0 + found;
+            const u32 pe = partner[e];
+            if (pe != RANK_NONE) r = pair_compare_warp(packed, bits, n, e + (u64)K, (u64)pe + (u64)K);
+        }
+        if (lane == 0) {
+            beyond[0] = found;
+            beyond[1] = r;
+        }
+    }
+    // the comparisons at the queued run ends, one warp each
+    {
+        const u32 nq = qn;
+        for (u32 k = warp; k < nq; k += PR_NT / 32) {
+            const u32 rel = qpos[k];
+            const u64 e = T0 + rel;
+            const u32 pe = partner[e];
+            const u32 r = pair_compare_warp(packed, bits, n, e + (u64)K, (u64)pe + (u64)K);
+            if (lane == 0) RES[rel] = (u8)r;
+        }
+    }
+    __syncthreads();
+    if (!abits) return;
+    u32 nextz = after != NONEPOS ? after : beyond[0];  // first run end after this chunk (relative to T0)
+    u64 out = 0;
+#pragma unroll
+    for (int i = PR_BPT - 1; i >= 0; --i) {
+        const u32 rel = tid * PR_BPT + (u32)i;
+        if (!((lbits >> i) & 1u)) nextz = rel;
+        if ((abits >> i) & 1u) {
+            u32 r = 0;
+            if (nextz != NONEPOS && nextz - rel <= PR_CAP) r = nextz < (u32)PR_TILE ? (u32)RES[nextz] : beyond[1];
+            out |= (u64)r << (8 * i);
+        }
+    }
+    *(u64 *)(ord + p0) = out;
+}
+
+// keep8[j] = 1: the element stays in the list
+__global__ void __launch_bounds__(256) pair_place_kernel(const u32 *__restrict__ act, const u32 *__restrict__ grp, u32 m,
+                                                         const u8 *__restrict__ ord, u32 *__restrict__ sa, u8 *__restrict__ bwt,
+                                                         u32 *__restrict__ actbits, u32 *__restrict__ primary,
+                                                         u8 *__restrict__ keep8, u32 *__restrict__ nplaced) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool placed = false;
+    if (j < m) {
+        const u32 g = grp[j];
+        const bool head = j == 0 || grp[j - 1] != g;
+        // a group of exactly two: this element and the one after it (head), or the one before it
+        bool pair;
+        u64 jh;
+        if (head) {
+            pair = j + 1 < m && grp[j + 1] == g && (j + 2 >= m || grp[j + 2] != g);
+            jh = j;
+        } else {
+            pair = (j + 1 >= m || grp[j + 1] != g) && (j == 1 || grp[j - 2] != g);
+            jh = j - 1;
+        }
+        u32 o = 0, s1 = 0;
+        if (pair) {
+            s1 = act[jh];
+            o = ord[s1];
+        }
+        placed = pair && o != 0u;
+        keep8[j] = placed ? 0 : 1;
+        if (placed && head) {
+            const u32 s2 = act[j + 1];
+            if (o == 2u) {  // the second one is the smaller suffix: the two rows change places
+                sa[g] = s2;
+                sa[g + 1] = s1;
+                if (bwt) {
+                    const u8 b0 = bwt[g], b1 = bwt[g + 1];
+                    bwt[g] = b1;
+                    bwt[g + 1] = b0;
+                }
+            }
+            if (s1 == 0) *primary = o == 2u ? g + 1 : g;
+            if (s2 == 0) *primary = o == 2u ? g : g + 1;
+            // the two rows are final: no longer "active after round 0"
+            if ((g & 31u) != 31u) {
+                atomicAnd(&actbits[g >> 5], ~(3u << (g & 31u)));
+            } else {
+                atomicAnd(&actbits[g >> 5], ~(1u << 31));
+                atomicAnd(&actbits[(g >> 5) + 1], ~1u);
+            }
+        }
+    }
+    const u32 c = (u32)__popc(__ballot_sync(0xffffffffu, placed));
+    if ((threadIdx.x & 31u) == 0 && c) atomicAdd(nplaced, c);
+}
+
 // groups in a grouped list (positions whose group differs from the one before)
 __global__ void __launch_bounds__(256) count_heads_kernel(const u32 *__restrict__ grp, u32 m, u32 *__restrict__ count) {
     const u64 stride = (u64)gridDim.x * blockDim.x;
@@ -1846,6 +2069,13 @@ __global__ void __launch_bounds__(256) scatter_ranks_kernel(const u32 *__restric
         for (u32 i = 0; i < shorts[0]; ++i) rank[shorts[1 + 2 * i]] = shorts[2 + 2 * i];
 }
 
+// rank[act[j]] = row[j] for the elements that leave the list (keep8[j] == 0)
+__global__ void __launch_bounds__(256) scatter_ranks_left_kernel(const u32 *__restrict__ act, const u32 *__restrict__ row,
+                                                                 const u8 *__restrict__ keep8, u32 m, u32 *__restrict__ rank) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < m && !keep8[j]) rank[act[j]] = row[j];
+}
+
 // bytes (0 / 1) -> bitmap words, one thread per 64 elements
 __global__ void __launch_bounds__(256) bytes_to_bits_kernel(const u8 *__restrict__ b8, u32 m, u64 *__restrict__ bits64,
                                                             u64 nwords) {
@@ -2024,7 +2254,8 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
     bool need_bwt_fix = false;
     // the list as round 0 left it: what rank[] has to hold for its suffixes (round0_msd.cu writes no ranks)
     const u32 *act0 = act, *row0 = grp;
-    const u32 m0 = m;
+    u32 m0 = m;
+    bool rank_marked = false;  // rank[] has been set to "not materialised" (and holds the ranks of decided suffixes)
     if (m && b <= 8 && !env_int("B200SA_NO_EXT_TIEBREAK", 0)) {
         // groups of two to four equal keys are ordered by the next 64 bits of text (pairs only while the active set
         // is small: in a large one they are copies of repeats)
@@ -2056,6 +2287,14 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
             row0 = row_p;
             // the list the rounds start from goes back into the buffers of the old one (dead now); act0 / row0 stay
             // where they are until the ranks have been scattered
+            if (nres && done0) {
+                // the suffixes decided here are final but their rows still count as "active after round 0": their ranks
+                // are materialised now (the pair path below may replace the list the other ranks are scattered from)
+                CUDA_CHECK(cudaMemsetAsync(rank, 0xff, (size_t)len * 4, st));
+                scatter_ranks_left_kernel<<<div_up_u(m, 256), 256, 0, st>>>(act_p, row_p, keep8, m, rank);
+                KERNEL_CHECK();
+                rank_marked = true;
+            }
             if (nres) {
                 const u64 kw = ((u64)m + 63) / 64;
                 CUDA_CHECK(cudaMemsetAsync(headbits, 0, (kw + 2) * 8, st));
@@ -2071,13 +2310,68 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
         }
         ix.timer.end(t);
     }
+    const int pairs_mode = env_int("B200SA_PAIRS", 1);  // 0: off, 2: on lists of any size (tests)
+    if (m && done0 && rk_free[1] && b <= 8 && pairs_mode && ((u64)m * 64 >= (u64)len || pairs_mode == 2)) {
+        // pairs of a text with long exact repeats: decided by one comparison per copied segment (pair_runs_kernel)
+        t = ix.timer.begin("pair_partner", (double)m * 16.0 + (double)len * 4.0);
+        const size_t pt_entries = (size_t)len + PR_CAP + 2 * PR_TILE + 16;
+        const size_t pt_padded = (pt_entries + 127) & ~(size_t)127;
+        const size_t ord_bytes = (((size_t)len + PR_TILE) / PR_TILE + 1) * PR_TILE;
+        // (in the round-key buffer that is free now when the text is long enough for the padding to fit, else carved)
+        u32 *partner = pt_padded * 4 + ord_bytes <= ((size_t)len + 2) * 8 ? (u32 *)rk_free[1]
+                                                                        : (u32 *)ar.get<u8>(pt_padded * 4 + ord_bytes);
+        u8 *ord = (u8 *)(partner + pt_padded);
+        u32 *d_pr = ar.get<u32>(2);
+        CUDA_CHECK(cudaMemsetAsync(partner, 0xff, pt_entries * 4, st));
+        CUDA_CHECK(cudaMemsetAsync(d_pr, 0, 8, st));
+        pair_partner_kernel<<<div_up_u(m, 256), 256, 0, st>>>(act, grp, m, partner, d_pr);
+        KERNEL_CHECK();
+        u32 npairs = 0;
+        read_back(&npairs, d_pr, 4, st);
+        ix.timer.end(t);
+        if (npairs && ((u64)npairs * 8 >= (u64)m || pairs_mode == 2)) {  // (two members each: at least a quarter of the list)
+            t = ix.timer.begin("pair_runs", (double)len * 5.0);
+            CUDA_CHECK(cudaMemsetAsync(ord, 0, ord_bytes, st));
+            pair_runs_kernel<<<div_up_u(len, PR_TILE), PR_NT, 0, st>>>(partner, n, ix.packed, b, K, ord);
+            KERNEL_CHECK();
+            ix.timer.end(t);
+            t = ix.timer.begin("pair_place", (double)m * 14.0);
+            u8 *keep8 = ar.get<u8>((size_t)m + 64);
+            pair_place_kernel<<<div_up_u(m, 256), 256, 0, st>>>(act, grp, m, ord, sa, bwt_rows, actbits, d_primary.ptr, keep8, d_pr + 1);
+            KERNEL_CHECK();
+            u32 nplaced = 0;
+            read_back(&nplaced, d_pr + 1, 4, st);
+            ix.stats.pair_placed = nplaced;
+            if (nplaced) {
+                // the rest of the list, through the buffer that held the list round 0 left (its ranks are not needed:
+                // only suffixes that stay active get one)
+                u32 *tmpA = (u32 *)rk_free[0], *tmpB = tmpA + m;
+                const u64 kw = ((u64)m + 63) / 64;
+                CUDA_CHECK(cudaMemsetAsync(headbits, 0, (kw + 2) * 8, st));
+                bytes_to_bits_kernel<<<div_up_u(kw, 256), 256, 0, st>>>(keep8, m, (u64 *)headbits, kw);
+                KERNEL_CHECK();
+                const u32 m2 = count_active<true>(headbits, m, tile_counts, d_total, st);
+                if (m2 != m - nplaced) throw std::runtime_error("pair path: list accounting is inconsistent (internal error)");
+                if (m2) {
+                    scatter_active<true>(headbits, act, grp, m, tile_counts, tmpA, tmpB, st);
+                    CUDA_CHECK(cudaMemcpyAsync(const_cast<u32 *>(act), tmpA, (size_t)m2 * 4, cudaMemcpyDeviceToDevice, st));
+                    CUDA_CHECK(cudaMemcpyAsync(grp, tmpB, (size_t)m2 * 4, cudaMemcpyDeviceToDevice, st));
+                }
+                m = m2;
+                act0 = act;
+                row0 = grp;
+                m0 = m;
+            }
+            ix.timer.end(t);
+        }
+    }
     if (m && done0) {
         // bucketed round 0: ranks of the suffixes that were active after it (first row of their group, or their final
         // row where the text decided); everything else is marked "not materialised" first.  A text without repeats
         // never gets here: its few chance collisions are all decided above.  (LSD round 0: rank_kernel wrote the ranks,
         // the kernel above kept them up to date.)
         t = ix.timer.begin("rank_scatter", (double)m0 * 12.0 + (double)len * 4.0);
-        CUDA_CHECK(cudaMemsetAsync(rank, 0xff, (size_t)len * 4, st));
+        if (!rank_marked) CUDA_CHECK(cudaMemsetAsync(rank, 0xff, (size_t)len * 4, st));
         scatter_ranks_kernel<<<div_up_u(m0, 256), 256, 0, st>>>(act0, row0, m0, short_rank, rank);
         KERNEL_CHECK();
         ix.timer.end(t);

@@ -64,6 +64,28 @@ def nonuniform_texts():
     out.append(("binary_runs_600k", runs, 3))
     out.append(("sym16_skewed_500k", _skewed(rng, 500000, [0.85] + [0.01] * 15), 17))
     out.append(("byte_skewed_400k", _skewed(rng, 400000, [0.9] + [0.1 / 254] * 254), 256))
+    # exact copies of segments, two of each (pairs of equal keys; pair_runs_kernel): plain, overlapping an earlier copy,
+    # tandem (distance shorter than the segment), one ending at the end of the text, one longer than a tile
+    t = base.copy()
+    for k in range(60):
+        ln = int(rng.integers(300, 6000))
+        src = int(rng.integers(0, len(t) - ln))
+        dst = int(rng.integers(0, len(t) - ln))
+        t[dst:dst + ln] = t[src:src + ln].copy()
+    t[500000:503000] = t[500100:503100].copy()
+    t[-4000:] = t[200000:204000].copy()
+    t[40000:70000] = t[800000:830000].copy()
+    out.append(("pair_copies_1M", t, 5))
+    # the same on a binary alphabet (64 symbols per compared window) and with a long run inside the copies
+    t2 = rng.integers(1, 3, 700000).astype(np.uint8)
+    for k in range(30):
+        ln = int(rng.integers(500, 9000))
+        src = int(rng.integers(0, len(t2) - ln))
+        dst = int(rng.integers(0, len(t2) - ln))
+        t2[dst:dst + ln] = t2[src:src + ln].copy()
+    t2[100000:100700] = 1
+    t2[400000:400700] = 1
+    out.append(("pair_copies_binary_700k", t2, 3))
     return out
 
 
@@ -78,7 +100,8 @@ def _texts():
 
 
 NAMES = ["polyA_mid_end_1M", "polyA_tandemCA_1M", "block_copies_1M", "skewed_70A_1M", "skewed_97A_300k",
-         "hg38_sample_500k", "hg38_tiled_mut_1200k", "binary_runs_600k", "sym16_skewed_500k", "byte_skewed_400k"]
+         "hg38_sample_500k", "hg38_tiled_mut_1200k", "binary_runs_600k", "sym16_skewed_500k", "byte_skewed_400k",
+         "pair_copies_1M", "pair_copies_binary_700k"]
 
 # default plan; never add a level (everything oversize becomes a shallow group, however much it is);
 # always add a level when one bucket is oversize; tiny buckets (many segments per tile) with shallow groups
@@ -96,6 +119,11 @@ MODES = {
     # groups split around a pivot key in every round / by the path's own heuristics on lists of any size
     "pivot_force": {"B200SA_PIVOT_MIN": "2", "B200SA_PIVOT_FORCE": "1"},
     "pivot_auto": {"B200SA_PIVOT_MIN": "2", "B200SA_SMALL_PATH": "0"},
+    # groups of two decided by one text comparison per repeat, on lists of any size; with and without the tie-break
+    # by the next 64 bits of text in front of it; never
+    "pairs_force": {"B200SA_PAIRS": "2"},
+    "pairs_force_noext": {"B200SA_PAIRS": "2", "B200SA_NO_EXT_TIEBREAK": "1"},
+    "pairs_off": {"B200SA_PAIRS": "0"},
 }
 
 

@@ -59,6 +59,7 @@ if __name__ == "__main__":
                    "shallow_buckets": st["shallow_buckets"], "shallow_elems": st["shallow_elems"],
                    "chain_rounds": st["chain_rounds"], "chain_elems": st["chain_elems"], "lazy": st["lazy_lookups"],
                    "resolved_small": st["resolved_small"], "small_path_elems": st["small_path_elems"],
+                   "pair_placed": st["pair_placed"],
                    "pivot_rounds": st["pivot_rounds"], "pivot_elems_x": round(st["pivot_elems"] / (n + 1), 2),
                    "sorted_total_x": round(st["sorted_total"] / (n + 1), 2),
                    "stages_ms": {k: [v[0], round(v[1], 2)] for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
