@@ -1394,16 +1394,22 @@ __device__ __forceinline__ void pv_load8_keys(const u64 *__restrict__ k, u64 j0,
 
 // lists made by the pivot path itself: the first member of every group publishes its second key and clears the
 // group's counters (for the round's list the kernels that make the keys do it)
-__global__ void __launch_bounds__(256) pivot_heads_kernel(const u64 *__restrict__ keys, u32 m, int lo_bits,
-                                                          u32 *__restrict__ piv, unsigned long long *__restrict__ cnt64) {
-    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
-    const u64 k = keys[j];
-    const u32 g = (u32)(k >> lo_bits);
-    if (j == 0 || (u32)(keys[j - 1] >> lo_bits) != g) {
-        const u32 lomask = lo_bits >= 32 ? 0xffffffffu : ((1u << lo_bits) - 1u);
-        piv[g >> 1] = (u32)k & lomask;
-        cnt64[g >> 1] = 0ull;
+__global__ void __launch_bounds__(PV_NT) pivot_heads_kernel(const u64 *__restrict__ keys, u32 m, int lo_bits,
+                                                            u32 *__restrict__ piv, unsigned long long *__restrict__ cnt64) {
+    const u64 j0 = ((u64)blockIdx.x * PV_NT + threadIdx.x) * PV_IPT;
+    if (j0 >= m) return;
+    const u32 lomask = lo_bits >= 32 ? 0xffffffffu : ((1u << lo_bits) - 1u);
+    u32 g[PV_IPT], lo[PV_IPT];
+    pv_load8_keys(keys, j0, m, lo_bits, lomask, g, lo);
+    u32 pg = j0 > 0 ? (u32)(keys[j0 - 1] >> lo_bits) : 0u;
+#pragma unroll
+    for (int q = 0; q < PV_IPT; ++q) {
+        const u64 j = j0 + q;
+        if (j < m && (j == 0 || g[q] != pg)) {
+            piv[g[q] >> 1] = lo[q];
+            cnt64[g[q] >> 1] = 0ull;
+        }
+        pg = g[q];
     }
 }
 
@@ -1492,11 +1498,13 @@ __global__ void __launch_bounds__(PV_NT) pivot_classify_kernel(PivotArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(PV_NT) pivot_apply_kernel(PivotArgs a) {
+// (the staging arrays are indexed e + e / 32: a thread's eight consecutive E members would otherwise hit four banks)
+#define PV_PAD(e) ((e) + ((e) >> 5))
+__global__ void __launch_bounds__(PV_NT, 4) pivot_apply_kernel(PivotArgs a) {
     // by tile-local index of a group head (index PV_TILE: the group that began before the tile)
     __shared__ u32 s_id[PV_TILE + 1];   // new identifier of the E group, RANK_NONE: unchanged
     // the tile's E members in list order
-    __shared__ u32 sh_s[PV_TILE], sh_nh[PV_TILE], sh_rk[PV_TILE];
+    __shared__ u32 sh_s[PV_TILE + PV_TILE / 32], sh_nh[PV_TILE + PV_TILE / 32], sh_rk[PV_TILE + PV_TILE / 32];
     __shared__ u32 sh_drop[PV_TILE / 32];  // E members of the tile that are alone in their group
     __shared__ u32 wmax[PV_NT / 32], wsum[PV_NT / 32];
     __shared__ u32 any_single;
@@ -1576,8 +1584,8 @@ __global__ void __launch_bounds__(PV_NT) pivot_apply_kernel(PivotArgs a) {
             if ((ebyte >> q) & 1u) {
                 const u32 el = excl + (u32)__popc(ebyte & ((1u << q) - 1u));
                 const u32 nh = cur + nL;
-                sh_s[el] = s[q];
-                sh_nh[el] = nh;
+                sh_s[PV_PAD(el)] = s[q];
+                sh_nh[PV_PAD(el)] = nh;
                 u32 rk;
                 if (nE == 1u) {
                     // alone: final.  (The rows of members that stay in the list are written when they leave it.)
@@ -1590,7 +1598,7 @@ __global__ void __launch_bounds__(PV_NT) pivot_apply_kernel(PivotArgs a) {
                 } else {
                     rk = s_id[hidx[q] ? hidx[q] - 1u : (u32)PV_TILE];
                 }
-                sh_rk[el] = rk;
+                sh_rk[PV_PAD(el)] = rk;
             } else if (lo[q] > P) {
                 a.keys[j] = ((u64)(cur + nL + nE) << a.lo_bits) | (u64)lo[q];
             }
@@ -1601,9 +1609,9 @@ __global__ void __launch_bounds__(PV_NT) pivot_apply_kernel(PivotArgs a) {
     u32 ne = 0;  // E members of the tile (the warp totals of the prefix sum above)
     for (int w = 0; w < PV_NT / 32; ++w) ne += wsum[w];
     for (u32 k = tid; k < ne; k += PV_NT) {
-        const u32 sv = sh_s[k], rk = sh_rk[k];
+        const u32 sv = sh_s[PV_PAD(k)], rk = sh_rk[PV_PAD(k)];
         a.out_act[tile_off + k] = sv;
-        a.out_grp[tile_off + k] = sh_nh[k];
+        a.out_grp[tile_off + k] = sh_nh[PV_PAD(k)];
         if (rk != RANK_NONE) a.rank[sv] = rk;
     }
     if (any_single) {
@@ -1653,9 +1661,9 @@ __global__ void __launch_bounds__(256) pair_partner_kernel(const u32 *__restrict
         const u32 g = grp[j];
         pair = (j == 0 || grp[j - 1] != g) && grp[j + 1] == g && (j + 2 >= m || grp[j + 2] != g);
         if (pair) {
+            // (only the member that stands first in the text: the runs of pair_runs_kernel are made of those)
             const u32 s1 = act[j], s2 = act[j + 1];
-            partner[s1] = s2;
-            partner[s2] = s1;
+            partner[min(s1, s2)] = max(s1, s2);
         }
     }
     const u32 c = (u32)__popc(__ballot_sync(0xffffffffu, pair));
@@ -1803,7 +1811,10 @@ __global__ void __launch_bounds__(256) pair_place_kernel(const u32 *__restrict__
                                                          u32 *__restrict__ actbits, u32 *__restrict__ primary,
                                                          u8 *__restrict__ keep8, u32 *__restrict__ nplaced) {
     const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 lane = threadIdx.x & 31u;
     bool placed = false;
+    u32 cw = 0xffffffffu, cm = 0;  // word of the active-row bitmap this lane clears bits in; the bits
+    bool spill = false;            // ... and bit 0 of the next word (the pair's rows straddle two words)
     if (j < m) {
         const u32 g = grp[j];
         const bool head = j == 0 || grp[j - 1] != g;
@@ -1817,16 +1828,18 @@ __global__ void __launch_bounds__(256) pair_place_kernel(const u32 *__restrict__
             pair = (j + 1 >= m || grp[j + 1] != g) && (j == 1 || grp[j - 2] != g);
             jh = j - 1;
         }
-        u32 o = 0, s1 = 0;
+        u32 o = 0, s1 = 0, s2 = 0;
         if (pair) {
             s1 = act[jh];
-            o = ord[s1];
+            s2 = act[jh + 1];
+            // the result stands at the member that comes first in the text: 1 = that one is the smaller suffix
+            o = ord[min(s1, s2)];
+            if (o && s2 < s1) o = 3u - o;  // -> 1: the first list element (s1) is the smaller suffix, 2: the second
         }
         placed = pair && o != 0u;
         keep8[j] = placed ? 0 : 1;
         if (placed && head) {
-            const u32 s2 = act[j + 1];
-            if (o == 2u) {  // the second one is the smaller suffix: the two rows change places
+            if (o == 2u) {  // the two rows change places
                 sa[g] = s2;
                 sa[g + 1] = s1;
                 if (bwt) {
@@ -1838,16 +1851,24 @@ __global__ void __launch_bounds__(256) pair_place_kernel(const u32 *__restrict__
             if (s1 == 0) *primary = o == 2u ? g + 1 : g;
             if (s2 == 0) *primary = o == 2u ? g : g + 1;
             // the two rows are final: no longer "active after round 0"
+            cw = g >> 5;
             if ((g & 31u) != 31u) {
-                atomicAnd(&actbits[g >> 5], ~(3u << (g & 31u)));
+                cm = 3u << (g & 31u);
             } else {
-                atomicAnd(&actbits[g >> 5], ~(1u << 31));
-                atomicAnd(&actbits[(g >> 5) + 1], ~1u);
+                cm = 1u << 31;
+                spill = true;
             }
         }
     }
+    // rows grow along the list: the lanes of a warp that clear bits of one word do it with one atomic
+    {
+        const u32 peers = __match_any_sync(0xffffffffu, cw);
+        const u32 all = __reduce_or_sync(peers, cm);
+        if (cw != 0xffffffffu && lane == (u32)(__ffs((int)peers) - 1)) atomicAnd(&actbits[cw], ~all);
+        if (spill) atomicAnd(&actbits[cw + 1], ~1u);
+    }
     const u32 c = (u32)__popc(__ballot_sync(0xffffffffu, placed));
-    if ((threadIdx.x & 31u) == 0 && c) atomicAdd(nplaced, c);
+    if (lane == 0 && c) atomicAdd(nplaced, c);
 }
 
 // groups in a grouped list (positions whose group differs from the one before)
@@ -2287,9 +2308,10 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
             row0 = row_p;
             // the list the rounds start from goes back into the buffers of the old one (dead now); act0 / row0 stay
             // where they are until the ranks have been scattered
-            if (nres && done0) {
-                // the suffixes decided here are final but their rows still count as "active after round 0": their ranks
-                // are materialised now (the pair path below may replace the list the other ranks are scattered from)
+            if (nres && done0 && nres < m) {
+                // the suffixes decided here are final but their rows still count as "active after round 0": when rounds
+                // follow, their ranks are materialised now (the pair path below may replace the list the other ranks
+                // are scattered from)
                 CUDA_CHECK(cudaMemsetAsync(rank, 0xff, (size_t)len * 4, st));
                 scatter_ranks_left_kernel<<<div_up_u(m, 256), 256, 0, st>>>(act_p, row_p, keep8, m, rank);
                 KERNEL_CHECK();
@@ -2342,6 +2364,8 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
             u32 nplaced = 0;
             read_back(&nplaced, d_pr + 1, 4, st);
             ix.stats.pair_placed = nplaced;
+            ix.timer.end(t);
+            t = ix.timer.begin("pair_compact", (double)m * 10.0);
             if (nplaced) {
                 // the rest of the list, through the buffer that held the list round 0 left (its ranks are not needed:
                 // only suffixes that stay active get one)
@@ -2526,7 +2550,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                     CUDA_CHECK(cudaMemsetAsync(rbits8 + kw * 8, 0, 16, st));
                     CUDA_CHECK(cudaMemsetAsync(d_pvtot, 0, 16, st));
                     if (publish) {
-                        pivot_heads_kernel<<<div_up_u(n, 256), 256, 0, st>>>(kx, n, lo_bits, pv_piv, pv_cnt);
+                        pivot_heads_kernel<<<div_up_u(n, PV_TILE), PV_NT, 0, st>>>(kx, n, lo_bits, pv_piv, pv_cnt);
                         KERNEL_CHECK();
                     }
                     pivot_classify_kernel<<<ntl, PV_NT, 0, st>>>(pv);

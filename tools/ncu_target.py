@@ -1,6 +1,7 @@
-"""Short workloads to run UNDER ncu (one GPU):  python tools/ncu_target.py build|search|repeat [n] [reads]
+"""Short workloads to run UNDER ncu (one GPU):  python tools/ncu_target.py build|search|repeat|stress:<kind> [n] [reads]
 build : two builds of n random ACGT symbols (SA + BWT + C + O)          -> round-0 kernels
 repeat: one build of the repeat-rich text               -> doubling / chain kernels
+stress:<kind>: one build (SA only) of a config-5 text (unary, acgt4, period1000, fib)      -> pivot path kernels
 search: index of n symbols (k-mer table + text comparison), `reads` 100-bp reads, byte and packed kernels
 Numbers printed by a run under ncu are never bench values."""
 import ctypes as C
@@ -17,8 +18,14 @@ lib = stralg_b200.load()
 what = sys.argv[1] if len(sys.argv) > 1 else "build"
 n = int(float(sys.argv[2])) if len(sys.argv) > 2 else 3_000_000_000
 reads_n = int(float(sys.argv[3])) if len(sys.argv) > 3 else 100_000_000
-text = T.random_codes(lib, n, 4, T.SEED)
-if what == "build":
+text = None if what.startswith("stress:") else T.random_codes(lib, n, 4, T.SEED)
+if what.startswith("stress:"):
+    text, sigma = T.stress_text(lib, what.split(":")[1], n)
+    torch.cuda.synchronize()
+    idx = stralg_b200.SuffixArrayIndex.build(text[:n], sigma, occ=False)
+    print(idx.stats())
+    idx.close()
+elif what == "build":
     for _ in range(2):
         stralg_b200.SuffixArrayIndex.build(text[:n], 5, occ=True).close()
 elif what == "repeat":
