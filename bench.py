@@ -860,6 +860,7 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
     chk = stralg_b200._lib.check
     # search index: C + sampled O, plus SA / ISA / packed text for the unique-interval shortcut
     idx = build(textcmp=True, ktable=True)
+    kk = idx.stats()["ktable_k"]
     lib.b200sa_release_workspace(local_rank)
     # contiguous shards of the read set, one per rank; (L, R) reach rank 0 inside the step
     from stralg_b200.shard import ShardedSearch
@@ -1039,7 +1040,7 @@ def search_bench(args, lib, stralg_b200, torch, dev, local_rank, stream, text, n
                    "miss_fraction": MISS_PER_1024 / 1024.0, "gather": ("search kernels store (L,R) into rank 0's HBM through NVLink peer memory (symmetric memory) + one "
                               "device-side barrier" if ss.transport == "p2p" else
                               f"NCCL gather of (L,R) to rank 0, {ss.chunks} piece(s) per shard") if world > 1
-                   else "none (1 GPU)", "l2": "index (1.5 GB O + 8.6 GB k-mer table) and reads larger than L2"},
+                   else "none (1 GPU)", "ktable_k": kk, "l2": f"index (1.5 GB O + {8 * 4 ** kk / 1e9:.1f} GB k-mer table, k = {kk}) and reads larger than L2"},
         "clocks": sampler.summary(tw0, tw1), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "kernel_only_patterns_per_s_per_gpu": shard / (kernel_ms / 1e3),
         "byte_api": {"kernel_only_patterns_per_s_per_gpu": shard / (byte_ms / 1e3), "kernel_ms": byte_ms,

@@ -88,6 +88,8 @@ struct b200sa_stats {
     uint32_t pivot_rounds;     /* doubling rounds that split their groups around a pivot key */
     uint32_t pair_placed;      /* suffixes in groups of two equal initial keys (a position of a repeat and the same
                                   position of its copy) decided by one text comparison per repeat */
+    uint32_t ktable_k;         /* symbols per entry of the k-mer seed table (B200SA_BUILD_KTABLE), 0 = none */
+    uint32_t reserved1;
 };
 
 /* ---- construction ------------------------------------------------------------------------

@@ -560,6 +560,8 @@ int b200sa_stats(const b200sa_index *idx, struct b200sa_stats *out) {
     out->pivot_elems = ix.stats.pivot_elems;
     out->pivot_rounds = ix.stats.pivot_rounds;
     out->pair_placed = ix.stats.pair_placed;
+    out->ktable_k = ix.ktable.ptr ? (uint32_t)ix.ktable_k : 0u;
+    out->reserved1 = 0;
     return 0;
 }
 
@@ -1296,7 +1298,7 @@ b200sa_index *b200sa_load(const char *path, int device, void *stream, enum b200s
             if (fh.occ_layout == 2) good = good && fh.sigma > 5 && fh.occ_block_bytes == hdr_words * 4 + 64;
             if (fh.occ_layout != 0) good = good && fh.occ_blocks == blocks;
             if (fh.occ_layout == 0) good = good && fh.occ_blocks == 0;
-            good = good && fh.ktable_k <= 15 && (fh.ktable_k == 0 || fh.occ_layout == 1);
+            good = good && fh.ktable_k <= 16 && (fh.ktable_k == 0 || fh.occ_layout == 1);
             if (!good) throw std::invalid_argument("index file header is inconsistent (O-table layout / k-mer table)");
         }
         DeviceIndex &ix = h->ix;

@@ -128,10 +128,11 @@ struct KTable {
     int k;
 };
 
-__global__ void __launch_bounds__(256) ktable_build_kernel(OccView ov, CTable5 c5, u32 len, int k, u32 entries,
+__global__ void __launch_bounds__(256) ktable_build_kernel(OccView ov, CTable5 c5, u32 len, int k, u64 entries,
                                                            uint2 *__restrict__ tab) {
-    u32 x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= entries) return;
+    const u64 x64 = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x64 >= entries) return;
+    const u32 x = (u32)x64;  // (k <= 16: a k-mer is at most 32 bits)
     u32 L = 0, R = len;
     for (int j = 0; j < k && L < R; ++j) {
         const u32 a = ((x >> (2 * (k - 1 - j))) & 3u) + 1u;
@@ -575,20 +576,29 @@ void fm_search(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fix
     KERNEL_CHECK();
 }
 
-// The largest k <= 15 whose table (8 bytes per k-mer) stays under three bytes per text symbol:
-// k = 15 (8.6 GB) at 3 Gbp, 13 at 256 Mi, 9 at 1 Mi.  Once the search kernel had become DRAM-bound
-// every extra symbol of k paid (3 Gbp, 10^8 reads of 100 bp: k = 12: 23.6 ms, 13: 20.5, 14: 17.7,
-// 15: 15.7) -- each one removes about 1.65 random O-block fetches per read.
+// The largest k whose table (8 bytes per k-mer) stays under a budget of bytes per text symbol: three for a lean
+// index (k = 15, 8.6 GB, at 3 Gbp; 13 at 256 Mi; 9 at 1 Mi), twelve -- and k up to 16 -- for an index that keeps the
+// suffix array, its inverse and the packed text for the unique-interval shortcut anyway (8.25 bytes per symbol):
+// k = 16, 34 GB, at 3 Gbp.  Once the search kernel had become DRAM-bound every extra symbol of k paid (3 Gbp, 10^8
+// reads of 100 bp, byte kernel: k = 12: 23.6 ms, 13: 20.5, 14: 17.7, 15: 15.7; packed kernel: 15: 13.5, 16: 11.5) --
+// each one removes random O-block fetches from every read.
 void build_ktable(DeviceIndex &ix) {
     if (ix.occ_layout != OCC_DNA32) return;
-    int k = 15;
-    while (k > 0 && (8ull << (2 * k)) > 3ull * (u64)ix.len) --k;
+    const bool rich = ix.text_packed.ptr && ix.isa.ptr && ix.sa.ptr;
+    int k = rich ? 16 : 15;
+    while (k > 0 && (8ull << (2 * k)) > (rich ? 12ull : 3ull) * (u64)ix.len) --k;
     if (const char *e = getenv("B200SA_KTABLE_K")) {
-        k = std::max(4, std::min(15, atoi(e)));
-        while (k > 0 && (1ull << (2 * k)) > (u64)ix.len) --k;
+        // (an explicit request may go one symbol further: k = 16 is a 34 GB table, 11 bytes per symbol at 3 Gbp)
+        k = std::max(4, std::min(16, atoi(e)));
+        while (k > 0 && (1ull << (2 * k)) > 2 * (u64)ix.len) --k;
     }
     if (k < 4) return;
-    const u32 entries = 1u << (2 * k);
+    u64 entries = 1ull << (2 * k);
+    // (a table that does not fit next to what the device already holds: one symbol less)
+    for (;; --k, entries >>= 2) {
+        size_t free_b = 0, total_b = 0;
+        if (k <= 12 || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b > entries * 8 + ((size_t)4 << 30)) break;
+    }
     ix.ktable.alloc(entries, ix.stream);
     ix.ktable_k = k;
     OccView ov = occ_view(ix);
