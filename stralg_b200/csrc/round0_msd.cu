@@ -736,8 +736,9 @@ __device__ __forceinline__ void l3_emit(const L3Args &a, u32 g, u64 e, bool acti
 static constexpr int L3_CNTN = L3_CAP + 16;        // counters per tile (the blocked scan reads a little past bin M)
 static constexpr int L3_PAD = L3_CROWD;             // guard elements on both sides of X (the ordering window never exceeds it)
 static constexpr int L3_ABW = L3_MASKW + 2;         // words of the tile's slice of the active bitmap (any alignment)
+static constexpr int L3_WLW = L3_MASKW;             // words of per-32-position window bounds
 static constexpr size_t L3_SMEM = (size_t)(L3_CAP + 2 * L3_PAD) * 8 + (size_t)L3_CNTN * 4 + (size_t)L3_CNTN * 2 +
-                                  (size_t)(L3_MASKW + 1) * 4 * 2 + 64 * 4 + 8 * 4 + (size_t)L3_ABW * 4;
+                                  (size_t)(L3_MASKW + 1) * 4 * 2 + 64 * 4 + 8 * 4 + (size_t)L3_ABW * 4 + (size_t)L3_WLW * 4;
 
 // sum of the four bytes of x
 __device__ __forceinline__ u32 bytesum(u32 x) { return __dp4a(x, 0x01010101u, 0u); }
@@ -758,6 +759,8 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
     u32 *misc = segpre + (L3_MASKW + 1);              // [64]
     u32 *nxt = misc + 64;                             // [8] next tile: index, b0, b1, E0, M
     u32 *abits = nxt + 8;                             // [L3_ABW] active bits of the tile's rows, global word alignment
+    u32 *wloc = abits + L3_ABW;                       // [L3_WLW] per 32 positions of the grouped tile: the largest (sub-bin
+                                                      // occupancy - 1) of an element standing there = the window pass 3 needs
     uint2 *segtab = (uint2 *)Xhi;                     // aliases the element arrays until the elements are scattered
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const u32 remmask = a.R >= 32 ? ~0u : ((1u << a.R) - 1u);
@@ -793,10 +796,12 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
     if (tid < (u32)L3_PAD) Xhi[-(int)tid - 1] = 0u;
     if (tid == 0) misc[32] = 0;  // largest slot seen in the tile
     for (u32 i = tid; i < (u32)L3_ABW; i += L3_NT) abits[i] = 0;
+    for (u32 i = tid; i < (u32)L3_WLW; i += L3_NT) wloc[i] = 0;
     u32 prevE0 = 0, prevM = 0;   // rows of the previous tile whose active bits still sit in `abits`
 
     while (true) {
         __syncthreads();  // `nxt` is published, the counters are zero, the previous tile has left X
+        if (tid < (u32)L3_WLW) wloc[tid] = 0;  // (written by pass 2, behind the barriers of pass 1)
         if (prevM) {
             // the previous tile's slice of the active bitmap: interior words are owned by the tile, the
             // first and the last one may be shared with its neighbours
@@ -921,11 +926,15 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
                 if ((u32)j * L3_NT >= M) break;
                 if (i < M) {
                     const u32 word = meta[j] & 8191u, sub8 = (meta[j] >> 13) & 31u, slot = meta[j] >> 18;
-                    const u32 below = bytesum(cnt[word] & ((1u << sub8) - 1u));
+                    const u32 cw = cnt[word];
+                    const u32 below = bytesum(cw & ((1u << sub8) - 1u));
                     const u64 e = src[i];
                     const u32 at = (u32)pre[word] + below + slot;
                     Xhi[at] = (u32)(e >> 32);
                     Xlo[at] = (u32)e;
+                    // an element is at most (occupancy of its sub-bin - 1) positions away from its place
+                    const u32 need = ((cw >> sub8) & 255u) - 1u;
+                    if (need) atomicMax(&wloc[at >> 5], need);
                 }
             }
             // right guards: the largest key, never "smaller than" an element
@@ -948,7 +957,7 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
         // ordered by key, so the sorted position of the element at p is p minus the larger keys
         // among the W positions to its left plus the smaller keys among the W to its right
         // (elements outside its sub-bin contribute nothing).  No per-element loop bounds: W is
-        // uniform over the tile.  The high word of an element is [rest of key | preceding
+        // uniform over a warp (Wl <= W).  The high word of an element is [rest of key | preceding
         // symbol]; its bits above `pb` order the elements of all buckets under one level-1
         // parent, so bucket boundaries need a check only in tiles that span two parents
         // (always with a single level).  Equal keys (a short suffix next to its padded twin, or
@@ -956,6 +965,9 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
         const u32 pbmask = (1u << a.pb) - 1u;
         for (u32 p = tid; p < M; p += L3_NT) {
             const u32 hp = Xhi[p];
+            // the window the 32 positions of this warp need (uniform over the warp): the tile-wide bound W is set by
+            // one or two crowded sub-bins, and by every pair of equal keys on a text with repeats
+            const u32 Wl = wloc[p >> 5];
             u32 r = p;
             bool eq = false;
             if (!segcheck) {
@@ -963,7 +975,7 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
                 // a < (b & ~mask) likewise; the guards on both sides of X make bounds checks unnecessary
                 const u32 hp_hi = hp | pbmask, hp_lo = hp & ~pbmask;
                 u32 near = 0xffffffffu;  // smallest difference to a neighbour's word: <= pbmask means an equal key
-                for (u32 d = 1; d <= W; ++d) {
+                for (u32 d = 1; d <= Wl; ++d) {
                     const u32 hl = Xhi[(int)(p - d)], hr = Xhi[p + d];
                     r -= hl > hp_hi ? 1u : 0u;
                     r += hr < hp_lo ? 1u : 0u;
@@ -973,7 +985,7 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
             } else {
                 const u32 kp = hp >> a.pb;
                 bool lv = true, rv = true;
-                for (u32 d = 1; d <= W; ++d) {
+                for (u32 d = 1; d <= Wl; ++d) {
                     lv = lv && p >= d;
                     rv = rv && p + d < M;
                     const u32 xl = p - d + 1u, xr = p + d;  // a bucket starts here: the neighbour is beyond it
@@ -1002,7 +1014,7 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
                 const bool e_short = is_short_suffix(se, a.K, a.n);
                 u32 longs_before = 0;
                 bool lv = true, rv = true;
-                for (u32 d = 1; d <= W; ++d) {
+                for (u32 d = 1; d <= Wl; ++d) {
                     lv = lv && p >= d;
                     rv = rv && p + d < M;
                     if (segcheck) {
