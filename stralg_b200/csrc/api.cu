@@ -8,6 +8,7 @@
 #include <new>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <vector>
 
@@ -447,6 +448,9 @@ b200sa_index *b200sa_build(const uint8_t *codes, uint64_t n, uint32_t sigma, uin
     return h;
 }
 
+namespace {
+void mail_server_release(const b200sa_index *idx);  // (the resident one-pattern search holds pointers into the index)
+}
 int b200sa_extend(b200sa_index *idx, const uint8_t *codes, uint32_t flags) {
     if (!idx || (!codes && idx->ix.n)) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
     DeviceIndex &ix = idx->ix;
@@ -459,6 +463,7 @@ int b200sa_extend(b200sa_index *idx, const uint8_t *codes, uint32_t flags) {
     const bool need_ktable = (flags & B200SA_BUILD_KTABLE) && !ix.ktable.ptr && ix.sigma <= 5 &&
                              (need_occ || ix.occ_layout == OCC_DNA32);
     if (!need_isa && !need_lcp && !need_bwt && !need_textcmp && !need_ktable) return 0;
+    mail_server_release(idx);  // (the resident one-pattern search was launched with the tables as they were)
     API_GUARD_BEGIN
     DeviceGuard guard(ix.device);
     use_device(ix.device);
@@ -523,8 +528,127 @@ int b200sa_extend(b200sa_index *idx, const uint8_t *codes, uint32_t flags) {
     API_GUARD_END(nullptr)
 }
 
+// ---- resident one-pattern search (fm_search.cu: fm_mailbox_server_kernel) --------------------------------
+namespace {
+struct MailServer {  // one per device: a slot of mapped pinned memory, a stream of its own, the index it serves
+    std::mutex mu;
+    u8 *host = nullptr, *dev = nullptr;
+    cudaStream_t st = nullptr;
+    const b200sa_index *bound = nullptr;
+    u32 tag = 0;
+    bool broken = false;  // a request timed out once: the launch path is used from then on
+};
+MailServer g_mail[64];
+const size_t kSlotBytes = 512;
+const u32 kMailMaxPat = 31 * 6;
+inline volatile unsigned long long *slot_words(MailServer &ms) { return (volatile unsigned long long *)ms.host; }
+
+// asks the resident kernel to leave and waits for it (the caller holds ms.mu)
+void mail_server_stop(MailServer &ms) {
+    if (!ms.host) return;
+    volatile unsigned long long *w = slot_words(ms);
+    if (w[40]) {
+        w[41] = 1;
+        const auto t0 = std::chrono::steady_clock::now();
+        while (w[40] && std::chrono::steady_clock::now() - t0 < std::chrono::seconds(2)) {
+        }
+        if (w[40]) cudaStreamSynchronize(ms.st);  // (never seen: the kernel polls the flag every 16 reads of the slot)
+        w[41] = 0;
+    }
+    ms.bound = nullptr;
+}
+
+void mail_server_release(const b200sa_index *idx) {
+    const int d = idx->ix.device;
+    if (d < 0 || d >= 64) return;
+    MailServer &ms = g_mail[d];
+    std::lock_guard<std::mutex> lock(ms.mu);
+    if (ms.bound == idx) mail_server_stop(ms);
+}
+
+// one pattern through the resident kernel; false: not served (the caller takes the launch path)
+bool mail_server_search(const b200sa_index *idx, const uint8_t *pat, uint32_t m, uint32_t *L, uint32_t *R) {
+    static const int enabled = getenv("B200SA_MAIL_SERVER") ? atoi(getenv("B200SA_MAIL_SERVER")) : 1;
+    const DeviceIndex &ix = idx->ix;
+    if (!enabled || m > kMailMaxPat || ix.occ_layout != OCC_DNA32 || ix.device < 0 || ix.device >= 64) return false;
+    MailServer &ms = g_mail[ix.device];
+    std::lock_guard<std::mutex> lock(ms.mu);
+    if (ms.broken) return false;
+    if (!ms.host) {
+        if (cudaHostAlloc((void **)&ms.host, kSlotBytes, cudaHostAllocMapped) != cudaSuccess) {
+            cudaGetLastError();
+            ms.host = nullptr;
+            ms.broken = true;
+            return false;
+        }
+        memset(ms.host, 0, kSlotBytes);
+        CUDA_CHECK(cudaHostGetDevicePointer((void **)&ms.dev, ms.host, 0));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&ms.st, cudaStreamNonBlocking));
+    }
+    volatile unsigned long long *w = slot_words(ms);
+    static const u32 idle_limit = (u32)std::max(16, getenv("B200SA_MAIL_IDLE") ? atoi(getenv("B200SA_MAIL_IDLE")) : 2000);
+    auto launch = [&]() {
+        // (what the index holds must have been written before the kernel reads it: builds run in the index's stream)
+        CUDA_CHECK(cudaStreamSynchronize(ix.stream));
+        w[40] = 1;
+        w[41] = 0;
+        fm_mailbox_server_launch(ix, ms.dev, ms.tag, idle_limit, ms.st);
+        ms.bound = idx;
+    };
+    if (ms.bound != idx || !w[40]) {
+        if (w[40]) mail_server_stop(ms);
+        launch();
+    }
+    const u32 tag = (ms.tag + 1u) & 0xffffu;
+    const unsigned long long t48 = (unsigned long long)tag << 48;
+    const u32 nw = 1u + (m + 5u) / 6u;
+    for (u32 k = 1; k < nw; ++k) {
+        unsigned long long v = 0;
+        for (u32 b = 0; b < 6 && (k - 1) * 6 + b < m; ++b) v |= (unsigned long long)pat[(k - 1) * 6 + b] << (8 * b);
+        w[k] = v | t48;
+    }
+    std::atomic_thread_fence(std::memory_order_release);
+    w[0] = t48 | ((unsigned long long)m << 32);
+    const auto t0 = std::chrono::steady_clock::now();
+    u32 spins = 0;
+    for (;;) {
+        const unsigned long long r0 = w[32], r1 = w[33];
+        if ((r0 >> 48) == tag && (r1 >> 48) == tag) {
+            *L = (uint32_t)r0;
+            *R = (uint32_t)r1;
+            ms.tag = tag;
+            static const bool dbg = getenv("B200SA_MAIL_DEBUG") != nullptr;
+            if (dbg) {
+                static double sum_search = 0, sum_total = 0;
+                static unsigned cnt = 0;
+                sum_search += (double)w[34];
+                sum_total += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count();
+                if (++cnt % 4096 == 0) {
+                    fprintf(stderr, "[b200sa mail] %u requests: %.1f us round trip, %.1f us inside the search\n", cnt,
+                            sum_total / cnt / 1e3, sum_search / cnt / 1e3);
+                }
+            }
+            return true;
+        }
+        if ((++spins & 1023u) == 0) {
+            if (!w[40]) {  // the kernel left (idle) before it saw the request: the request is still in the slot
+                const unsigned long long q0 = w[32], q1 = w[33];
+                if ((q0 >> 48) == tag && (q1 >> 48) == tag) continue;
+                launch();
+            }
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) {
+                ms.broken = true;
+                w[41] = 1;
+                return false;
+            }
+        }
+    }
+}
+}  // namespace
+
 void b200sa_free(b200sa_index *idx) {
     if (!idx) return;
+    mail_server_release(idx);
     int prev = -1;
     if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
     cudaSetDevice(idx->ix.device);
@@ -761,6 +885,10 @@ int b200sa_search_batch(const b200sa_index *idx, const uint8_t *patterns, const 
     DeviceGuard guard(ix.device);
     cudaStream_t st = ix.stream;
     const uint64_t total = offsets ? offsets[npat] : (uint64_t)fixed_len * npat;
+    if (npat == 1) {  // one pattern: the resident kernel, when there is one to be had
+        const uint64_t b0 = offsets ? offsets[0] : 0;
+        if (total - b0 <= kMailMaxPat && mail_server_search(idx, patterns + b0, (uint32_t)(total - b0), L, R)) return 0;
+    }
     if (npat <= 64 && total + 16 <= kMailPat && ix.device >= 0 && ix.device < 64) {
         SearchMailbox &mb = t_search_mailbox;
         if (!mb.host[ix.device]) {
@@ -1167,6 +1295,7 @@ int b200sa_locate_batch_sorted(const b200sa_index *idx, const uint32_t *L, const
 
 int b200sa_sample_sa(b200sa_index *idx, uint32_t rate, int drop_sa) {
     if (!idx || rate < 1) return fail(B200SA_ERR_BAD_ARGUMENT, "null index or sampling rate 0", nullptr);
+    mail_server_release(idx);
     DeviceIndex &ix = idx->ix;
     if (!ix.sa.ptr) return fail(B200SA_ERR_NOT_BUILT, "suffix array was dropped (B200SA_DROP_SA)", nullptr);
     if (ix.occ_layout == OCC_NONE) return fail(B200SA_ERR_NOT_BUILT, "the sampled suffix array needs the O table (B200SA_BUILD_OCC)", nullptr);

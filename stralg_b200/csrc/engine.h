@@ -87,6 +87,8 @@ void occ_dense(const DeviceIndex &ix, u32 *d_out);  // (len+1)*sigma entries, re
 void build_ktable(DeviceIndex &ix);  // fills ix.ktable (DNA layout only)
 void fm_search(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fixed_len, u64 npat, u32 *d_L,
                u32 *d_R, cudaStream_t st, unsigned long long *d_stats = nullptr);
+// resident one-pattern search (the drop-in's iterator): a one-warp kernel that polls `d_slot` (mapped pinned memory)
+void fm_mailbox_server_launch(const DeviceIndex &ix, void *d_slot, u32 tag, u32 idle_limit, cudaStream_t st);
 // packed reads: 2 bits per base, four to a byte, first base in the high bits; read q at q * stride bytes
 void fm_search_packed(const DeviceIndex &ix, const u8 *d_packed, u32 m, u32 stride, u64 npat, u32 *d_L, u32 *d_R,
                       cudaStream_t st, unsigned long long *d_stats = nullptr);

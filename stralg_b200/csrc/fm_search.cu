@@ -148,17 +148,11 @@ __global__ void __launch_bounds__(256) ktable_build_kernel(OccView ov, CTable5 c
     tab[x] = make_uint2(L, R);
 }
 
+// one pattern: pat[begin .. begin + m), readable in aligned 8-byte words; (L, R) = the interval of bwt.c:171-198
 template <int LM, bool SC, bool STATS>
-__global__ void __launch_bounds__(256) fm_search_dna_kernel(OccView ov, CTable5 c5, TextCmp tc, KTable kt, u32 len,
-                                                            const u8 *__restrict__ pat,
-                                                            const u64 *__restrict__ off, u32 fixed_len, u64 npat,
-                                                            u32 *__restrict__ outL, u32 *__restrict__ outR,
-                                                            unsigned long long *__restrict__ stats) {
-    u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= npat) return;
-    u32 n_blk = 0, n_pw = 0, n_tw = 0, n_sa = 0;
-    u64 begin = off ? off[q] : q * (u64)fixed_len;
-    u64 m = off ? off[q + 1] - begin : (u64)fixed_len;
+__device__ __forceinline__ void fm_search_dna_one(const OccView &ov, const CTable5 &c5, const TextCmp &tc, const KTable &kt,
+                                                  u32 len, const u8 *__restrict__ pat, u64 begin, u64 m, u32 &Lout, u32 &Rout,
+                                                  u32 &n_blk, u32 &n_pw, u32 &n_tw, u32 &n_sa) {
     u32 L = 0, R = len;
     if (m > (u64)len) {
         L = 1;
@@ -327,6 +321,23 @@ __global__ void __launch_bounds__(256) fm_search_dna_kernel(OccView ov, CTable5 
             R = c5.c[a] + rank_in_block(kb2, a, Lk + 1, ov.primary);
         }
     }
+    Lout = L;
+    Rout = R;
+}
+
+template <int LM, bool SC, bool STATS>
+__global__ void __launch_bounds__(256) fm_search_dna_kernel(OccView ov, CTable5 c5, TextCmp tc, KTable kt, u32 len,
+                                                            const u8 *__restrict__ pat,
+                                                            const u64 *__restrict__ off, u32 fixed_len, u64 npat,
+                                                            u32 *__restrict__ outL, u32 *__restrict__ outR,
+                                                            unsigned long long *__restrict__ stats) {
+    u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npat) return;
+    u32 n_blk = 0, n_pw = 0, n_tw = 0, n_sa = 0;
+    u64 begin = off ? off[q] : q * (u64)fixed_len;
+    u64 m = off ? off[q + 1] - begin : (u64)fixed_len;
+    u32 L, R;
+    fm_search_dna_one<LM, SC, STATS>(ov, c5, tc, kt, len, pat, begin, m, L, R, n_blk, n_pw, n_tw, n_sa);
     outL[q] = L;
     outR[q] = R;
     if (STATS) {
@@ -335,6 +346,89 @@ __global__ void __launch_bounds__(256) fm_search_dna_kernel(OccView ov, CTable5 
         atomicAdd(&stats[2], (unsigned long long)n_tw);
         atomicAdd(&stats[3], (unsigned long long)n_sa);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One pattern at a time (the drop-in's init_bwt_exact_match_iter): a one-warp kernel that stays resident
+// while requests keep coming.  The host writes a request into a slot of mapped pinned memory -- 32 words
+// of 8 bytes, each [tag : 16 | 6 bytes of payload], word 0 = [tag | length | -], so that one coalesced
+// read of the slot tells the warp whether a complete request with the expected tag stands there -- the
+// warp unpacks the pattern into shared memory, lane 0 runs the search of the batch kernel, and (L, R) go
+// back as two tagged words the host spins on.  No launch, no stream synchronisation per pattern; the
+// kernel leaves after `idle_limit` polls without a request (or when told to), so a device-wide
+// synchronisation elsewhere in the process waits a few milliseconds at most.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 ld_sys_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys_u64(u64 *p, u64 v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <bool SC>
+__global__ void __launch_bounds__(32) fm_mailbox_server_kernel(OccView ov, CTable5 c5, TextCmp tc, KTable kt, u32 len, u64 *slot,
+                                                               u32 tag, u32 idle_limit) {
+    __shared__ __align__(16) u8 spat[32 * 6 + 32];
+    const u32 lane = threadIdx.x;
+    u64 *req = slot, *resp = slot + 32, *ctl = slot + 40;  // ctl[0]: alive (set by the host, cleared here), ctl[1]: quit
+    u32 idle = 0;
+    for (;;) {
+        const u32 expect = (tag + 1u) & 0xffffu;
+        // the whole slot in one coalesced, uncached read (ld.cv: "fetch again"; a system-scope load per lane would be
+        // 32 separate trips to host memory)
+        u64 w;
+        asm volatile("ld.global.cv.u64 %0, [%1];" : "=l"(w) : "l"(req + lane) : "memory");
+        const u64 w0 = __shfl_sync(0xffffffffu, w, 0);
+        if ((u32)(w0 >> 48) != expect) {
+            ++idle;
+            bool quit = idle > idle_limit;
+            if ((idle & 15u) == 0u) quit = quit || __shfl_sync(0xffffffffu, lane == 0 ? ld_sys_u64(ctl + 1) : 0ull, 0) != 0ull;
+            if (quit) break;
+            continue;
+        }
+        const u32 m = (u32)(w0 >> 32) & 0xffffu;
+        const u32 nw = 1u + (m + 5u) / 6u;
+        // (a word that still carries an older tag: the request is being written, look again)
+        if (!__all_sync(0xffffffffu, lane >= nw || (u32)(w >> 48) == expect)) continue;
+        if (lane >= 1u && lane < nw) {
+#pragma unroll
+            for (int b = 0; b < 6; ++b) spat[(lane - 1u) * 6u + (u32)b] = (u8)(w >> (8 * b));
+        }
+        __syncwarp();
+        if (lane < 16u) spat[m + lane] = 0;  // the search reads whole aligned words
+        __syncwarp();
+        if (lane == 0) {
+            u32 L, R, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            u64 t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            fm_search_dna_one<3, SC, false>(ov, c5, tc, kt, len, spat, 0, (u64)m, L, R, c0, c1, c2, c3);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            st_sys_u64(resp + 2, t1 - t0);  // (nanoseconds inside the search: B200SA_MAIL_DEBUG)
+            st_sys_u64(resp, (u64)L | ((u64)expect << 48));
+            st_sys_u64(resp + 1, (u64)R | ((u64)expect << 48));
+            __threadfence_system();
+        }
+        tag = expect;
+        idle = 0;
+    }
+    if (lane == 0) {
+        __threadfence_system();
+        st_sys_u64(ctl, 0ull);
+    }
+}
+
+void fm_mailbox_server_launch(const DeviceIndex &ix, void *d_slot, u32 tag, u32 idle_limit, cudaStream_t st) {
+    OccView ov = occ_view(ix);
+    CTable5 c5;
+    for (int i = 0; i < 8; ++i) c5.c[i] = ix.c_host[i];
+    TextCmp tc{ix.sa.ptr, ix.isa.ptr, ix.text_packed.ptr};
+    KTable kt{ix.ktable.ptr, ix.ktable_k};
+    const bool sc = tc.sa && tc.isa && tc.packed && ix.pk.bits == 2;
+    if (sc) fm_mailbox_server_kernel<true><<<1, 32, 0, st>>>(ov, c5, tc, kt, ix.len, (u64 *)d_slot, tag, idle_limit);
+    else fm_mailbox_server_kernel<false><<<1, 32, 0, st>>>(ov, c5, tc, kt, ix.len, (u64 *)d_slot, tag, idle_limit);
+    KERNEL_CHECK();
 }
 
 // ---------------------------------------------------------------------------------------------
