@@ -51,7 +51,9 @@ enum b200sa_error {
                                         identical to the plain recurrence (needs OCC, keeps SA)        */
 #define B200SA_BUILD_KTABLE 0x20u    /* DNA index (sigma <= 5): table of the (L, R) interval the recurrence of
                                         bwt.c:185-195 reaches on every k-mer (the largest k <= 15 whose table
-                                        stays under 3 bytes per text symbol: 15 at 3 Gbp); exact search starts from the entry of the pattern's last k
+                                        stays under 3 bytes per text symbol: 15 at 3 Gbp; with TEXTCMP, which
+                                        keeps 8 bytes per symbol anyway, k <= 16 under 12 bytes: 16, 34 GB, at
+                                        3 Gbp; B200SA_KTABLE_K overrides); exact search starts from the entry of the pattern's last k
                                         symbols instead of running those k steps; results are identical
                                         (needs OCC)                                                      */
 #define B200SA_TEXT_ON_DEVICE 0x100u /* `codes` is a device pointer (borrowed during the call)  */
@@ -146,7 +148,12 @@ int b200sa_occ(const b200sa_index *idx, const uint8_t *a, const uint32_t *i, uin
 /* ---- batched exact search (init_bwt_exact_match_iter, bwt.c:164-199) -----------------------
  * Patterns are remapped codes, concatenated; pattern p is patterns[offsets[p] .. offsets[p+1]).
  * With offsets == NULL every pattern has fixed_len symbols.  Results: half-open SA intervals
- * [L[p], R[p]); L >= R means no match.  Host-buffer and device-buffer variants. */
+ * [L[p], R[p]); L >= R means no match.  Host-buffer and device-buffer variants.
+ * A call with ONE pattern of up to 186 symbols on a DNA index (the drop-in's one-iterator-per-pattern use) is served
+ * by a one-warp kernel that stays resident on the index's device while such calls keep coming and polls a request
+ * slot in mapped pinned memory: no launch and no synchronisation per call.  It leaves by itself after a few
+ * milliseconds without a request (B200SA_MAIL_IDLE polls, default 2000) and when its index is freed or extended;
+ * B200SA_MAIL_SERVER=0 turns it off. */
 int b200sa_search_batch(const b200sa_index *idx, const uint8_t *patterns, const uint64_t *offsets,
                         uint32_t fixed_len, uint64_t npat, uint32_t *L, uint32_t *R);
 int b200sa_search_device(const b200sa_index *idx, const uint8_t *d_patterns,
