@@ -724,8 +724,12 @@ __device__ __forceinline__ void l3_emit(const L3Args &a, u32 g, u64 e, bool acti
                                         u32 gbase = 0) {
     const u32 s = (u32)e;
     a.sa[g] = s;
-    if (a.bwt) a.bwt[g] = s ? (u8)(((u32)(e >> 32) & ((1u << a.pb) - 1u)) + 1u) : (u8)0;
-    if (s == 0) *a.primary = g;
+    u32 bw = ((u32)(e >> 32) & ((1u << a.pb) - 1u)) + 1u;
+    if (s == 0) {  // (one element of the whole text: the row of the sentinel)
+        bw = 0;
+        *a.primary = g;
+    }
+    if (a.bwt) a.bwt[g] = (u8)bw;
     if (active) {
         a.grow[g] = group_head;  // (rank[s] is written from the compacted list of active rows, sa_build.cu)
         if (sbits) atomicOr(&sbits[(g - gbase) >> 5], 1u << ((g - gbase) & 31u));
@@ -975,12 +979,20 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
                 // a < (b & ~mask) likewise; the guards on both sides of X make bounds checks unnecessary
                 const u32 hp_hi = hp | pbmask, hp_lo = hp & ~pbmask;
                 u32 near = 0xffffffffu;  // smallest difference to a neighbour's word: <= pbmask means an equal key
-                for (u32 d = 1; d <= Wl; ++d) {
-                    const u32 hl = Xhi[(int)(p - d)], hr = Xhi[p + d];
-                    r -= hl > hp_hi ? 1u : 0u;
-                    r += hr < hp_lo ? 1u : 0u;
-                    near = min(near, min(hl ^ hp, hr ^ hp));
-                }
+#define L3_STEP(D)                                                        \
+    {                                                                     \
+        const u32 hl = Xhi[(int)p - (D)], hr = Xhi[p + (D)];              \
+        r -= hl > hp_hi ? 1u : 0u;                                        \
+        r += hr < hp_lo ? 1u : 0u;                                        \
+        near = min(near, min(hl ^ hp, hr ^ hp));                          \
+    }
+                // (Wl is uniform over the warp and small: straight-line steps with constant offsets, no loop control)
+                if (Wl >= 1u) L3_STEP(1)
+                if (Wl >= 2u) L3_STEP(2)
+                if (Wl >= 3u) L3_STEP(3)
+                if (Wl >= 4u) L3_STEP(4)
+                for (u32 d = 5; d <= Wl; ++d) L3_STEP((int)d)
+#undef L3_STEP
                 eq = near <= pbmask;
             } else {
                 const u32 kp = hp >> a.pb;
