@@ -98,6 +98,21 @@ class SuffixArrayIndex:
             raise B200saError(err.value, lib.b200sa_last_error().decode())
         return cls(h, device)
 
+    def extend(self, codes, *, isa=False, lcp=False, bwt=False, occ=False, textcmp=False, ktable=False) -> None:
+        """Adds tables that were not requested at build time (b200sa_extend: the reference's lazy compute_inverse /
+        compute_lcp, suffix_array.c:55-85, and init_bwt_table over an existing suffix array, bwt.c:22-89).  `codes` is
+        the text the index was built from (host array or CUDA tensor)."""
+        flags = (BUILD_ISA if isa else 0) | (BUILD_LCP if lcp else 0) | (BUILD_BWT if bwt else 0) | \
+                (BUILD_OCC if occ else 0) | (BUILD_TEXTCMP if textcmp else 0) | (BUILD_KTABLE if ktable else 0)
+        if _is_torch_tensor(codes):
+            assert codes.is_cuda and codes.dtype.itemsize == 1 and codes.is_contiguous()
+            ptr = C.c_void_p(codes.data_ptr())
+            flags |= TEXT_ON_DEVICE
+        else:
+            keep = np.ascontiguousarray(codes, dtype=np.uint8)
+            ptr = _np_ptr(keep)
+        check(_lib.load().b200sa_extend(self._h, ptr, flags))
+
     # ---- native index file (include/b200sa.h: b200sa_save / b200sa_load) ------------------------
     def save(self, path: str) -> None:
         check(_lib.load().b200sa_save(self._h, str(path).encode()))

@@ -408,3 +408,58 @@ def test_one_pattern_mailbox_path(engine, oracle):
         L9, R9 = idx.search(np.concatenate(pats), off[5:14])
         assert np.array_equal(L9, Lb[5:13]) and np.array_equal(R9, Rb[5:13])
         idx.close()
+
+
+def test_one_pattern_at_a_time_resident_kernel(engine, oracle):
+    """The drop-in's one-iterator-per-pattern use (bwt.c:164-199): single-pattern calls are served by a resident
+    one-warp kernel that polls a mailbox in pinned memory (fm_search.cu fm_mailbox_server_kernel).  Same (L, R) as the
+    batch kernel -- hits, misses, near-misses, a bad symbol, the empty pattern, lengths up to the mailbox limit and
+    beyond it (launch path) -- across the life cycle of the kernel: a second index taking the mailbox over, an index
+    being extended and freed while the kernel serves it, a pause longer than its idle limit."""
+    import time
+    rng = np.random.default_rng(123)
+    n = 300000
+    codes_a = oracle.random_codes(n, 4, seed=11)
+    codes_b = oracle.random_codes(n // 2, 4, seed=12)
+    ia = engine.SuffixArrayIndex.build(codes_a[:-1], 5, textcmp=True, ktable=True)
+    ib = engine.SuffixArrayIndex.build(codes_b[:-1], 5)  # plain recurrence: no seed table, no text comparison
+
+    def patterns(codes, count):
+        out = []
+        for _ in range(count):
+            m = int(rng.choice([1, 2, 7, 20, 33, 100, 150, 186, 187, 250]))
+            s = int(rng.integers(0, len(codes) - 1 - m))
+            p = codes[s:s + m].copy()
+            kind = rng.integers(0, 4)
+            if kind == 1:
+                p[rng.integers(0, m)] = rng.integers(1, 5)      # near-miss
+            elif kind == 2:
+                p = rng.integers(1, 5, m).astype(np.uint8)        # random
+            elif kind == 3 and m > 2:
+                p[rng.integers(0, m)] = 7                          # a symbol the text does not have
+            out.append(p.astype(np.uint8))
+        out.append(np.zeros(0, np.uint8))
+        return out
+
+    def check(idx, codes, count):
+        pats = patterns(codes, count)
+        off = np.concatenate([[0], np.cumsum([len(p) for p in pats])]).astype(np.uint64)
+        cat = np.concatenate(pats + [np.zeros(16, np.uint8)])
+        Lb, Rb = idx.search(cat, off)  # batch kernel
+        for q, p in enumerate(pats):
+            L1, R1 = idx.search(np.concatenate([p, np.zeros(8, np.uint8)]), np.array([0, len(p)], dtype=np.uint64))
+            assert (int(L1[0]), int(R1[0])) == (int(Lb[q]), int(Rb[q])), (q, len(p), L1, R1, Lb[q], Rb[q])
+
+    check(ia, codes_a, 300)
+    check(ib, codes_b, 200)          # the mailbox changes hands
+    check(ia, codes_a, 50)
+    time.sleep(0.05)                  # longer than the idle limit: the kernel has left and is launched again
+    check(ia, codes_a, 50)
+    ib2 = engine.SuffixArrayIndex.build(codes_b[:-1], 5)
+    check(ib2, codes_b, 20)
+    ib2.extend(codes_b[:-1], textcmp=True, ktable=True)  # tables change under the resident kernel: it is stopped first
+    check(ib2, codes_b, 100)
+    ib2.close()                       # freed while it holds the mailbox
+    check(ia, codes_a, 50)
+    ia.close()
+    ib.close()
