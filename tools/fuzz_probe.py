@@ -36,7 +36,23 @@ while time.time() < t_end:
         n = len(sym)
     codes = np.concatenate([sym.astype(np.uint8), np.zeros(1, np.uint8)])
     sigma = nsym + 1
-    tag = f"case {cases} seed {seed} kind {kind} n {n} sigma {sigma}"
+    # the paths of the doubling rounds that real sizes choose by themselves, forced at random on these small texts:
+    # the pivot path (sa_build.cu pivot_classify_kernel), the pair path (pair_runs_kernel), the LSD round 0
+    knobs = {}
+    if rng.integers(0, 2):
+        knobs["B200SA_PIVOT_MIN"] = "2"
+        if rng.integers(0, 2):
+            knobs["B200SA_PIVOT_FORCE"] = "1"
+    if rng.integers(0, 2):
+        knobs["B200SA_PAIRS"] = "2"
+    if rng.integers(0, 4) == 0:
+        knobs["B200SA_ROUND0"] = "lsd"
+    if rng.integers(0, 3) == 0:
+        knobs["B200SA_SMALL_PATH"] = "0"
+    for k in ("B200SA_PIVOT_MIN", "B200SA_PIVOT_FORCE", "B200SA_PAIRS", "B200SA_ROUND0", "B200SA_SMALL_PATH"):
+        os.environ.pop(k, None)
+    os.environ.update(knobs)
+    tag = f"case {cases} seed {seed} kind {kind} n {n} sigma {sigma} knobs {knobs}"
     idx = stralg_b200.SuffixArrayIndex.build(codes[:-1], sigma, isa=True, lcp=True, bwt=True, occ=True,
                                              textcmp=bool(rng.integers(0, 2)), ktable=bool(rng.integers(0, 2)))
     sa_e = o.sa(codes)
@@ -73,6 +89,11 @@ while time.time() < t_end:
         ck = o.o_checkpoints(bwt_e, sigma, 64)
         Le, Re = o.search_ck(c_e, bwt_e, ck, 64, pat, off)
     assert np.array_equal(L, Le) and np.array_equal(R, Re), tag + " (L,R)"
+    # one pattern per call (the resident kernel of a DNA index, the launch path otherwise)
+    for q in range(0, npat, 37):
+        a, b = int(off[q]), int(off[q + 1])
+        L1, R1 = idx.search(np.concatenate([pat[a:b], np.zeros(8, np.uint8)]), np.array([0, b - a], dtype=np.uint64))
+        assert (int(L1[0]), int(R1[0])) == (int(Le[q]), int(Re[q])), tag + f" one pattern q={q}"
     poff_e, pos_e = o.locate(sa_e, Le, Re)
     poff, pos = idx.locate(L, R)
     assert np.array_equal(poff, poff_e) and np.array_equal(pos, pos_e), tag + " locate"
