@@ -1653,20 +1653,54 @@ static constexpr int PR_NT = 256, PR_BPT = 8, PR_TILE = PR_NT * PR_BPT;
 static constexpr u32 PR_CAP = 1u << 16;   // longest run followed beyond a tile (longer runs stay undecided)
 static constexpr int PR_CMP_WORDS = 256;  // 64-bit windows compared at the end of a run before giving up (a multiple of 32)
 
+// PQ consecutive list elements per thread: the group heads around them come from three vector loads, and the random
+// accesses of a thread's pairs (two at most) are in flight together.
+static constexpr int PQ = 4;
+// G[k] = grp[j0 - 4 + k] for k in [0, 12) (0xffffffff outside the list; a group head row never has that value... no row
+// does: len <= 2^32 - 1), A[k] = act[j0 + k] for k in [0, 5)
+__device__ __forceinline__ void pair_window(const u32 *__restrict__ act, const u32 *__restrict__ grp, u32 m, u64 j0,
+                                            u32 (&G)[12], u32 (&A)[5]) {
+    if (j0 >= 4 && j0 + 8 <= m) {
+        const uint4 x = *(const uint4 *)(grp + j0 - 4), y = *(const uint4 *)(grp + j0), z = *(const uint4 *)(grp + j0 + 4);
+        G[0] = x.x; G[1] = x.y; G[2] = x.z; G[3] = x.w; G[4] = y.x; G[5] = y.y; G[6] = y.z; G[7] = y.w;
+        G[8] = z.x; G[9] = z.y; G[10] = z.z; G[11] = z.w;
+        const uint4 v = *(const uint4 *)(act + j0);
+        A[0] = v.x; A[1] = v.y; A[2] = v.z; A[3] = v.w;
+        A[4] = act[j0 + 4];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const int64_t j = (int64_t)j0 - 4 + k;
+            G[k] = (j >= 0 && j < (int64_t)m) ? grp[j] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) A[k] = j0 + k < m ? act[j0 + k] : 0u;
+    }
+}
+// element q of the thread (list index j0 + q < m) is the first member of a group of exactly two
+__device__ __forceinline__ bool pair_head_at(const u32 (&G)[12], int q) {
+    const u32 g = G[4 + q];
+    return G[3 + q] != g && G[5 + q] == g && G[6 + q] != g;
+}
+
 __global__ void __launch_bounds__(256) pair_partner_kernel(const u32 *__restrict__ act, const u32 *__restrict__ grp, u32 m,
                                                            u32 *__restrict__ partner, u32 *__restrict__ npairs) {
-    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    bool pair = false;
-    if (j + 1 < m) {
-        const u32 g = grp[j];
-        pair = (j == 0 || grp[j - 1] != g) && grp[j + 1] == g && (j + 2 >= m || grp[j + 2] != g);
-        if (pair) {
-            // (only the member that stands first in the text: the runs of pair_runs_kernel are made of those)
-            const u32 s1 = act[j], s2 = act[j + 1];
-            partner[min(s1, s2)] = max(s1, s2);
+    const u64 j0 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * PQ;
+    u32 c = 0;
+    if (j0 < m) {
+        u32 G[12], A[5];
+        pair_window(act, grp, m, j0, G, A);
+#pragma unroll
+        for (int q = 0; q < PQ; ++q) {
+            if (j0 + q + 1 < m && pair_head_at(G, q)) {
+                // (only the member that stands first in the text: the runs of pair_runs_kernel are made of those)
+                const u32 s1 = A[q], s2 = A[q + 1];
+                partner[min(s1, s2)] = max(s1, s2);
+                ++c;
+            }
         }
     }
-    const u32 c = (u32)__popc(__ballot_sync(0xffffffffu, pair));
+    c = __reduce_add_sync(0xffffffffu, c);
     if ((threadIdx.x & 31u) == 0 && c) atomicAdd(npairs, c);
 }
 
@@ -1805,70 +1839,93 @@ __global__ void __launch_bounds__(PR_NT) pair_runs_kernel(const u32 *__restrict_
     *(u64 *)(ord + p0) = out;
 }
 
-// keep8[j] = 1: the element stays in the list
+// keep8[j] = 1: the element stays in the list.  The thread that holds the FIRST member of a pair writes the bytes of
+// both members (the second one may belong to the next thread's elements: that thread leaves it alone).
 __global__ void __launch_bounds__(256) pair_place_kernel(const u32 *__restrict__ act, const u32 *__restrict__ grp, u32 m,
                                                          const u8 *__restrict__ ord, u32 *__restrict__ sa, u8 *__restrict__ bwt,
                                                          u32 *__restrict__ actbits, u32 *__restrict__ primary,
-                                                         u8 *__restrict__ keep8, u32 *__restrict__ nplaced) {
-    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+                                                         const u8 *__restrict__ keep_in, u8 *__restrict__ keep8,
+                                                         u32 *__restrict__ nplaced) {
+    // (keep_in: "stays" bytes of a list that has not been compacted yet -- elements it drops stay dropped)
+    const u64 j0 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * PQ;
     const u32 lane = threadIdx.x & 31u;
-    bool placed = false;
-    u32 cw = 0xffffffffu, cm = 0;  // word of the active-row bitmap this lane clears bits in; the bits
-    bool spill = false;            // ... and bit 0 of the next word (the pair's rows straddle two words)
-    if (j < m) {
-        const u32 g = grp[j];
-        const bool head = j == 0 || grp[j - 1] != g;
-        // a group of exactly two: this element and the one after it (head), or the one before it
-        bool pair;
-        u64 jh;
-        if (head) {
-            pair = j + 1 < m && grp[j + 1] == g && (j + 2 >= m || grp[j + 2] != g);
-            jh = j;
-        } else {
-            pair = (j + 1 >= m || grp[j + 1] != g) && (j == 1 || grp[j - 2] != g);
-            jh = j - 1;
+    u32 placed = 0;
+    u32 cw0 = 0xffffffffu, cw1 = 0xffffffffu, cm0 = 0, cm1 = 0;  // words of the active-row bitmap to clear bits in (two pairs at most)
+    if (j0 < m) {
+        u32 G[12], A[5];
+        pair_window(act, grp, m, j0, G, A);
+        // the results of the thread's pairs, fetched together
+        u32 o[PQ];
+        bool hd[PQ];
+#pragma unroll
+        for (int q = 0; q < PQ; ++q) {
+            hd[q] = j0 + q + 1 < m && pair_head_at(G, q);
+            o[q] = 0;
+            if (hd[q]) o[q] = ord[min(A[q], A[q + 1])];
         }
-        u32 o = 0, s1 = 0, s2 = 0;
-        if (pair) {
-            s1 = act[jh];
-            s2 = act[jh + 1];
-            // the result stands at the member that comes first in the text: 1 = that one is the smaller suffix
-            o = ord[min(s1, s2)];
-            if (o && s2 < s1) o = 3u - o;  // -> 1: the first list element (s1) is the smaller suffix, 2: the second
-        }
-        placed = pair && o != 0u;
-        keep8[j] = placed ? 0 : 1;
-        if (placed && head) {
-            if (o == 2u) {  // the two rows change places
-                sa[g] = s2;
-                sa[g + 1] = s1;
-                if (bwt) {
-                    const u8 b0 = bwt[g], b1 = bwt[g + 1];
-                    bwt[g] = b1;
-                    bwt[g + 1] = b0;
+        int np = 0;
+#pragma unroll
+        for (int q = 0; q < PQ; ++q) {
+            const u64 j = j0 + q;
+            if (j >= m) break;
+            const u32 g = G[4 + q];
+            if (hd[q]) {
+                const u32 s1 = A[q], s2 = A[q + 1];
+                // the result stands at the member that comes first in the text (1 = that one is the smaller suffix):
+                // -> 1: the first list element (s1) is the smaller suffix, 2: the second
+                u32 oo = o[q];
+                if (oo && s2 < s1) oo = 3u - oo;
+                const u8 k = oo ? 0 : 1;
+                keep8[j] = k;
+                keep8[j + 1] = k;
+                if (oo) {
+                    placed += 2;
+                    if (oo == 2u) {  // the two rows change places
+                        sa[g] = s2;
+                        sa[g + 1] = s1;
+                        if (bwt) {
+                            const u8 b0 = bwt[g], b1 = bwt[g + 1];
+                            bwt[g] = b1;
+                            bwt[g + 1] = b0;
+                        }
+                    }
+                    if (s1 == 0) *primary = oo == 2u ? g + 1 : g;
+                    if (s2 == 0) *primary = oo == 2u ? g : g + 1;
+                    // the two rows are final: no longer "active after round 0"
+                    u32 mask = 3u << (g & 31u);
+                    if ((g & 31u) == 31u) {
+                        mask = 1u << 31;
+                        atomicAnd(&actbits[(g >> 5) + 1], ~1u);
+                    }
+                    if (np == 0) {
+                        cw0 = g >> 5;
+                        cm0 = mask;
+                    } else {
+                        cw1 = g >> 5;
+                        cm1 = mask;
+                    }
+                    ++np;
                 }
-            }
-            if (s1 == 0) *primary = o == 2u ? g + 1 : g;
-            if (s2 == 0) *primary = o == 2u ? g : g + 1;
-            // the two rows are final: no longer "active after round 0"
-            cw = g >> 5;
-            if ((g & 31u) != 31u) {
-                cm = 3u << (g & 31u);
             } else {
-                cm = 1u << 31;
-                spill = true;
+                // the second member of a pair is written by the thread that holds the first one
+                const bool second = G[3 + q] == g && G[5 + q] != g && G[2 + q] != g;
+                if (!second) keep8[j] = keep_in ? keep_in[j] : (u8)1;
             }
         }
     }
     // rows grow along the list: the lanes of a warp that clear bits of one word do it with one atomic
     {
-        const u32 peers = __match_any_sync(0xffffffffu, cw);
-        const u32 all = __reduce_or_sync(peers, cm);
-        if (cw != 0xffffffffu && lane == (u32)(__ffs((int)peers) - 1)) atomicAnd(&actbits[cw], ~all);
-        if (spill) atomicAnd(&actbits[cw + 1], ~1u);
+        const u32 peers = __match_any_sync(0xffffffffu, cw0);
+        const u32 all = __reduce_or_sync(peers, cm0);
+        if (cw0 != 0xffffffffu && lane == (u32)(__ffs((int)peers) - 1)) atomicAnd(&actbits[cw0], ~all);
     }
-    const u32 c = (u32)__popc(__ballot_sync(0xffffffffu, placed));
-    if (lane == 0 && c) atomicAdd(nplaced, c);
+    if (__any_sync(0xffffffffu, cw1 != 0xffffffffu)) {
+        const u32 peers = __match_any_sync(0xffffffffu, cw1);
+        const u32 all = __reduce_or_sync(peers, cm1);
+        if (cw1 != 0xffffffffu && lane == (u32)(__ffs((int)peers) - 1)) atomicAnd(&actbits[cw1], ~all);
+    }
+    placed = __reduce_add_sync(0xffffffffu, placed);
+    if (lane == 0 && placed) atomicAdd(nplaced, placed);
 }
 
 // groups in a grouped list (positions whose group differs from the one before)
@@ -2017,10 +2074,20 @@ __global__ void __launch_bounds__(256) resolve_small_groups_kernel(const u32 *__
     const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
     const u32 g = grp[j], s = act[j];
-    // members: list elements j - nl .. j + nr (the list is grouped; a group has at least two members)
+    // members: list elements j - nl .. j + nr (the list is grouped; a group has at least two members).  The four
+    // group heads on either side are fetched at once (independent loads), then counted
+    u32 gl[4], gr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        gl[k] = j >= (u64)k + 1 ? grp[j - k - 1] : ~g;
+        gr[k] = j + k + 1 < m ? grp[j + k + 1] : ~g;
+    }
     u32 nl = 0, nr = 0;
-    while (nl < 4u && j >= (u64)nl + 1 && grp[j - nl - 1] == g) ++nl;
-    while (nr < 4u && j + nr + 1 < m && grp[j + nr + 1] == g) ++nr;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        nl += (nl == (u32)k && gl[k] == g) ? 1u : 0u;
+        nr += (nr == (u32)k && gr[k] == g) ? 1u : 0u;
+    }
     const u32 size = nl + nr + 1u;
     bool look = size <= 4u && !(skip_pairs && size == 2u);
     const u32 span = 64u / (u32)bits;
@@ -2277,6 +2344,12 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
     const u32 *act0 = act, *row0 = grp;
     u32 m0 = m;
     bool rank_marked = false;  // rank[] has been set to "not materialised" (and holds the ranks of decided suffixes)
+    const int pairs_mode = env_int("B200SA_PAIRS", 1);  // 0: off, 2: on lists of any size (tests)
+    // the tie-break below leaves its list permuted, with a "stays" byte per element, when the pair path follows it:
+    // one compaction serves both
+    bool deferred = false;
+    u32 *dl_act = nullptr, *dl_row = nullptr, dl_nres = 0;
+    u8 *dl_keep = nullptr;
     if (m && b <= 8 && !env_int("B200SA_NO_EXT_TIEBREAK", 0)) {
         // groups of two to four equal keys are ordered by the next 64 bits of text (pairs only while the active set
         // is small: in a large one they are copies of repeats)
@@ -2294,7 +2367,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
         if (nsmall) {
             // the permuted list goes into a buffer that is dead until the rounds write their keys (both m <= len words)
             u8 *keep8 = ar.get<u8>((size_t)m + 64);
-            u32 *act_p = (u32 *)rk_free[0], *row_p = act_p + m;
+            u32 *act_p = (u32 *)rk_free[0], *row_p = act_p + (((size_t)m + 3) & ~(size_t)3);  // (vector stores: 16-byte aligned)
             u32 *act_old = act, *grp_old = grp;
             resolve_small_groups_kernel<<<div_up_u(m, 256), 256, 0, st>>>(act, grp, m, ix.packed, b, K, n, skip_pairs, sa,
                                                                           done0 ? nullptr : rank, act_p, row_p, bwt_rows,
@@ -2317,7 +2390,11 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 KERNEL_CHECK();
                 rank_marked = true;
             }
-            if (nres) {
+            const bool pairs_next = done0 && rk_free[1] && pairs_mode && ((u64)m * 64 >= (u64)len || pairs_mode == 2);
+            if (nres && nres < m && pairs_next) {
+                deferred = true;
+                dl_act = act_p; dl_row = row_p; dl_keep = keep8; dl_nres = nres;
+            } else if (nres) {
                 const u64 kw = ((u64)m + 63) / 64;
                 CUDA_CHECK(cudaMemsetAsync(headbits, 0, (kw + 2) * 8, st));
                 bytes_to_bits_kernel<<<div_up_u(kw, 256), 256, 0, st>>>(keep8, m, (u64 *)headbits, kw);
@@ -2332,7 +2409,9 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
         }
         ix.timer.end(t);
     }
-    const int pairs_mode = env_int("B200SA_PAIRS", 1);  // 0: off, 2: on lists of any size (tests)
+    // (the list the pair path reads: the permuted one when the tie-break left its compaction to this path)
+    const u32 *pl_act = deferred ? dl_act : act, *pl_grp = deferred ? dl_row : grp;
+    bool pairs_done = false;
     if (m && done0 && rk_free[1] && b <= 8 && pairs_mode && ((u64)m * 64 >= (u64)len || pairs_mode == 2)) {
         // pairs of a text with long exact repeats: decided by one comparison per copied segment (pair_runs_kernel)
         t = ix.timer.begin("pair_partner", (double)m * 16.0 + (double)len * 4.0);
@@ -2346,7 +2425,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
         u32 *d_pr = ar.get<u32>(2);
         CUDA_CHECK(cudaMemsetAsync(partner, 0xff, pt_entries * 4, st));
         CUDA_CHECK(cudaMemsetAsync(d_pr, 0, 8, st));
-        pair_partner_kernel<<<div_up_u(m, 256), 256, 0, st>>>(act, grp, m, partner, d_pr);
+        pair_partner_kernel<<<div_up_u(m, 256 * PQ), 256, 0, st>>>(pl_act, pl_grp, m, partner, d_pr);
         KERNEL_CHECK();
         u32 npairs = 0;
         read_back(&npairs, d_pr, 4, st);
@@ -2359,7 +2438,8 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
             ix.timer.end(t);
             t = ix.timer.begin("pair_place", (double)m * 14.0);
             u8 *keep8 = ar.get<u8>((size_t)m + 64);
-            pair_place_kernel<<<div_up_u(m, 256), 256, 0, st>>>(act, grp, m, ord, sa, bwt_rows, actbits, d_primary.ptr, keep8, d_pr + 1);
+            pair_place_kernel<<<div_up_u(m, 256 * PQ), 256, 0, st>>>(pl_act, pl_grp, m, ord, sa, bwt_rows, actbits, d_primary.ptr,
+                                                                    deferred ? dl_keep : nullptr, keep8, d_pr + 1);
             KERNEL_CHECK();
             u32 nplaced = 0;
             read_back(&nplaced, d_pr + 1, 4, st);
@@ -2367,16 +2447,20 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
             ix.timer.end(t);
             t = ix.timer.begin("pair_compact", (double)m * 10.0);
             if (nplaced) {
-                // the rest of the list, through the buffer that held the list round 0 left (its ranks are not needed:
-                // only suffixes that stay active get one)
-                u32 *tmpA = (u32 *)rk_free[0], *tmpB = tmpA + m;
+                // the rest of the list (its ranks are the only ones that are needed: only suffixes that stay active get
+                // one).  From the tie-break's permuted list it goes straight into the list's own buffers; else through
+                // the buffer that held the list round 0 left
                 const u64 kw = ((u64)m + 63) / 64;
                 CUDA_CHECK(cudaMemsetAsync(headbits, 0, (kw + 2) * 8, st));
                 bytes_to_bits_kernel<<<div_up_u(kw, 256), 256, 0, st>>>(keep8, m, (u64 *)headbits, kw);
                 KERNEL_CHECK();
                 const u32 m2 = count_active<true>(headbits, m, tile_counts, d_total, st);
-                if (m2 != m - nplaced) throw std::runtime_error("pair path: list accounting is inconsistent (internal error)");
-                if (m2) {
+                if (m2 != m - nplaced - (deferred ? dl_nres : 0u))
+                    throw std::runtime_error("pair path: list accounting is inconsistent (internal error)");
+                if (m2 && deferred) {
+                    scatter_active<true>(headbits, pl_act, pl_grp, m, tile_counts, const_cast<u32 *>(act), grp, st);
+                } else if (m2) {
+                    u32 *tmpA = (u32 *)rk_free[0], *tmpB = tmpA + m;
                     scatter_active<true>(headbits, act, grp, m, tile_counts, tmpA, tmpB, st);
                     CUDA_CHECK(cudaMemcpyAsync(const_cast<u32 *>(act), tmpA, (size_t)m2 * 4, cudaMemcpyDeviceToDevice, st));
                     CUDA_CHECK(cudaMemcpyAsync(grp, tmpB, (size_t)m2 * 4, cudaMemcpyDeviceToDevice, st));
@@ -2385,9 +2469,22 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 act0 = act;
                 row0 = grp;
                 m0 = m;
+                pairs_done = true;
             }
             ix.timer.end(t);
         }
+    }
+    if (deferred && !pairs_done) {
+        // the pair path placed nothing: the tie-break's own compaction after all
+        t = ix.timer.begin("resolve_small", (double)m * 16.0);
+        const u64 kw = ((u64)m + 63) / 64;
+        CUDA_CHECK(cudaMemsetAsync(headbits, 0, (kw + 2) * 8, st));
+        bytes_to_bits_kernel<<<div_up_u(kw, 256), 256, 0, st>>>(dl_keep, m, (u64 *)headbits, kw);
+        KERNEL_CHECK();
+        const u32 m2 = count_active<true>(headbits, m, tile_counts, d_total, st);
+        if (m2) scatter_active<true>(headbits, dl_act, dl_row, m, tile_counts, const_cast<u32 *>(act), grp, st);
+        m = m2;
+        ix.timer.end(t);
     }
     if (m && done0) {
         // bucketed round 0: ranks of the suffixes that were active after it (first row of their group, or their final
