@@ -766,6 +766,8 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
     u32 *wloc = abits + L3_ABW;                       // [L3_WLW] per 32 positions of the grouped tile: the largest (sub-bin
                                                       // occupancy - 1) of an element standing there = the window pass 3 needs
     uint2 *segtab = (uint2 *)Xhi;                     // aliases the element arrays until the elements are scattered
+    u16 *queue = pre;                                 // positions with an equal key within reach (pass 3 -> top of the next iteration;
+                                                      // `pre` is free between pass 2 and the next tile's scan)
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const u32 remmask = a.R >= 32 ? ~0u : ((1u << a.R) - 1u);
     const u32 remsh = a.R > 0 ? 32u - (u32)a.R : 0u;  // R == 0: every key of a bucket is equal, rem == 0
@@ -798,13 +800,76 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
     for (u32 i = tid; i < (u32)L3_CNTN; i += L3_NT) cnt[i] = 0;
     // left guards: the smallest key, never "larger than" an element (pass 3)
     if (tid < (u32)L3_PAD) Xhi[-(int)tid - 1] = 0u;
-    if (tid == 0) misc[32] = 0;  // largest slot seen in the tile
+    if (tid == 0) {
+        misc[32] = 0;  // largest slot seen in the tile
+        misc[35] = 0;  // positions queued for the tie-break pass
+        misc[36] = 0;  // ... of a tile that spans two level-1 parents (bucket boundaries are checked)
+        misc[37] = 0;  // this tile defers its tie-breaks
+        misc[38] = 0;  // tie-breaks done in place in this tile
+    }
     for (u32 i = tid; i < (u32)L3_ABW; i += L3_NT) abits[i] = 0;
     for (u32 i = tid; i < (u32)L3_WLW; i += L3_NT) wloc[i] = 0;
     u32 prevE0 = 0, prevM = 0;   // rows of the previous tile whose active bits still sit in `abits`
 
     while (true) {
         __syncthreads();  // `nxt` is published, the counters are zero, the previous tile has left X
+        const u32 qn = misc[35];
+        if (qn) {  // (uniform) positions of the previous tile whose tie-break was deferred
+            const u32 qE0 = prevE0, qM = prevM;
+            const bool qseg = misc[36] != 0u;
+            const u32 pbm = (1u << a.pb) - 1u;
+            for (u32 k = tid; k < qn; k += L3_NT) {
+                const u32 p = queue[k];
+                const u32 hp = Xhi[p], kp = hp >> a.pb;
+                const u32 Wl = wloc[p >> 5];
+                const u32 se = Xlo[p];
+                const bool e_short = is_short_suffix(se, a.K, a.n);
+                // position among the other keys (as in pass 3), then the final order among equal keys: short suffixes
+                // first, shortest (largest start) first; then the long ones in position order, which form an active group
+                u32 r = p, longs_before = 0;
+                bool active = false, lv = true, rv = true;
+                for (u32 d = 1; d <= Wl; ++d) {
+                    lv = lv && p >= d;
+                    rv = rv && p + d < qM;
+                    if (qseg) {
+                        const u32 xl = p - d + 1u, xr = p + d;  // a bucket starts here: the neighbour is beyond it
+                        if (lv && ((segmask[xl >> 5] >> (xl & 31u)) & 1u)) lv = false;
+                        if (rv && ((segmask[xr >> 5] >> (xr & 31u)) & 1u)) rv = false;
+                    }
+                    if (lv) {
+                        const u32 ko = Xhi[p - d] >> a.pb;
+                        r -= ko > kp ? 1u : 0u;
+                        if (ko == kp) {
+                            const u32 so = Xlo[p - d];
+                            const bool o_short = is_short_suffix(so, a.K, a.n);
+                            // the left neighbour belongs AFTER this element
+                            if (o_short ? (e_short && so < se) : e_short) --r;
+                            if (!o_short && !e_short) { active = true; ++longs_before; }
+                        }
+                    }
+                    if (rv) {
+                        const u32 ko = Xhi[p + d] >> a.pb;
+                        r += ko < kp ? 1u : 0u;
+                        if (ko == kp) {
+                            const u32 so = Xlo[p + d];
+                            const bool o_short = is_short_suffix(so, a.K, a.n);
+                            // the right neighbour belongs BEFORE this element
+                            if (o_short ? (!e_short || so > se) : false) ++r;
+                            if (!o_short && !e_short) active = true;
+                        }
+                    }
+                }
+                l3_emit(a, qE0 + r, ((u64)hp << 32) | (u64)se, active, qE0 + r - longs_before, abits, qE0 & ~31u);
+            }
+            (void)pbm;
+            __syncthreads();  // the active bits of these rows are in `abits`; `wloc`, the queue, the segment bitmap have been read
+        }
+        if (tid == 0) {
+            // equal keys in the tile just finished: more than a sixteenth of it -> the next tile defers its tie-breaks
+            misc[37] = (qn + misc[38]) * 16u > prevM ? 1u : 0u;
+            misc[38] = 0;
+            if (qn) misc[35] = 0;
+        }
         if (tid < (u32)L3_WLW) wloc[tid] = 0;  // (written by pass 2, behind the barriers of pass 1)
         if (prevM) {
             // the previous tile's slice of the active bitmap: interior words are owned by the tile, the
@@ -826,6 +891,7 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
         const u64 *src = a.in + E0;
         // bucket boundaries need a look only in tiles that span two level-1 parents (pass 3)
         const bool segcheck = (b0 >> a.par_shift) != ((b1 - 1u) >> a.par_shift);
+        if (tid == 0) misc[36] = segcheck ? 1u : 0u;  // (read by the deferred tie-break pass at the top of the next iteration)
         // Common case: a handful of buckets under one parent -- every thread keeps their
         // (start, size) in registers and nothing about segments goes through shared memory.
         const bool few = (b1 - b0 <= 4u) && !segcheck;
@@ -967,6 +1033,7 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
         // (always with a single level).  Equal keys (a short suffix next to its padded twin, or
         // long suffixes that stay active) are rare and take the tie-break path. ----
         const u32 pbmask = (1u << a.pb) - 1u;
+        const bool defer = misc[37] != 0u;  // (set behind the barrier of pass 1)
         for (u32 p = tid; p < M; p += L3_NT) {
             const u32 hp = Xhi[p];
             // the window the 32 positions of this warp need (uniform over the warp): the tile-wide bound W is set by
@@ -1020,6 +1087,14 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
             bool active = false;
             u32 head = r;
             if (eq) {
+                if (defer) {
+                    // the CTA's tiles are full of equal keys (a text with repeats): the tie-break runs in a pass of its
+                    // own at the top of the next iteration, where every lane has such an element -- here it would make
+                    // every warp walk both paths
+                    queue[atomicAdd(&misc[35], 1u)] = (u16)p;
+                    continue;
+                }
+                atomicAdd(&misc[38], 1u);
                 // final order among equal keys: short suffixes first, shortest (largest start)
                 // first; then the long ones in position order, which form an active group
                 const u32 se = (u32)e;
