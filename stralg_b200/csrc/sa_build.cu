@@ -1656,10 +1656,10 @@ static constexpr int PR_CMP_WORDS = 256;  // 64-bit windows compared at the end 
 // PQ consecutive list elements per thread: the group heads around them come from three vector loads, and the random
 // accesses of a thread's pairs (two at most) are in flight together.
 static constexpr int PQ = 4;
-// G[k] = grp[j0 - 4 + k] for k in [0, 12) (0xffffffff outside the list; a group head row never has that value... no row
-// does: len <= 2^32 - 1), A[k] = act[j0 + k] for k in [0, 5)
+// G[k] = grp[j0 - 4 + k] for k in [0, 12) (0xffffffff outside the list; no row has that value: len <= 2^32 - 1),
+// A[k] = act[j0 + k] for k in [0, 6)
 __device__ __forceinline__ void pair_window(const u32 *__restrict__ act, const u32 *__restrict__ grp, u32 m, u64 j0,
-                                            u32 (&G)[12], u32 (&A)[5]) {
+                                            u32 (&G)[12], u32 (&A)[6]) {
     if (j0 >= 4 && j0 + 8 <= m) {
         const uint4 x = *(const uint4 *)(grp + j0 - 4), y = *(const uint4 *)(grp + j0), z = *(const uint4 *)(grp + j0 + 4);
         G[0] = x.x; G[1] = x.y; G[2] = x.z; G[3] = x.w; G[4] = y.x; G[5] = y.y; G[6] = y.z; G[7] = y.w;
@@ -1667,6 +1667,7 @@ __device__ __forceinline__ void pair_window(const u32 *__restrict__ act, const u
         const uint4 v = *(const uint4 *)(act + j0);
         A[0] = v.x; A[1] = v.y; A[2] = v.z; A[3] = v.w;
         A[4] = act[j0 + 4];
+        A[5] = act[j0 + 5];
     } else {
 #pragma unroll
         for (int k = 0; k < 12; ++k) {
@@ -1674,28 +1675,40 @@ __device__ __forceinline__ void pair_window(const u32 *__restrict__ act, const u
             G[k] = (j >= 0 && j < (int64_t)m) ? grp[j] : 0xffffffffu;
         }
 #pragma unroll
-        for (int k = 0; k < 5; ++k) A[k] = j0 + k < m ? act[j0 + k] : 0u;
+        for (int k = 0; k < 6; ++k) A[k] = j0 + k < m ? act[j0 + k] : 0u;
     }
 }
-// element q of the thread (list index j0 + q < m) is the first member of a group of exactly two
-__device__ __forceinline__ bool pair_head_at(const u32 (&G)[12], int q) {
+// element q of the thread (list index j0 + q) is the first member of a group of exactly two / exactly three: 2 / 3, else 0
+__device__ __forceinline__ u32 pair_head_at(const u32 (&G)[12], int q) {
     const u32 g = G[4 + q];
-    return G[3 + q] != g && G[5 + q] == g && G[6 + q] != g;
+    if (G[3 + q] == g || G[5 + q] != g) return 0u;
+    if (G[6 + q] != g) return 2u;
+    return G[7 + q] != g ? 3u : 0u;
 }
 
+// partner[s] for the members of groups of two and three.  Two: the member that stands first in the text points to the
+// other one (the runs of pair_runs_kernel are made of the first members).  Three: in text order, t0 -> t1 -> t2 -> t0:
+// the three comparisons order the group.
 __global__ void __launch_bounds__(256) pair_partner_kernel(const u32 *__restrict__ act, const u32 *__restrict__ grp, u32 m,
                                                            u32 *__restrict__ partner, u32 *__restrict__ npairs) {
     const u64 j0 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * PQ;
     u32 c = 0;
     if (j0 < m) {
-        u32 G[12], A[5];
+        u32 G[12], A[6];
         pair_window(act, grp, m, j0, G, A);
 #pragma unroll
         for (int q = 0; q < PQ; ++q) {
-            if (j0 + q + 1 < m && pair_head_at(G, q)) {
-                // (only the member that stands first in the text: the runs of pair_runs_kernel are made of those)
+            const u32 kind = j0 + q < m ? pair_head_at(G, q) : 0u;
+            if (kind == 2u) {
                 const u32 s1 = A[q], s2 = A[q + 1];
                 partner[min(s1, s2)] = max(s1, s2);
+                ++c;
+            } else if (kind == 3u) {
+                const u32 x = A[q], y = A[q + 1], z = A[q + 2];
+                const u32 t0 = min(x, min(y, z)), t2 = max(x, max(y, z)), t1 = x ^ y ^ z ^ t0 ^ t2;
+                partner[t0] = t1;
+                partner[t1] = t2;
+                partner[t2] = t0;
                 ++c;
             }
         }
@@ -1839,8 +1852,8 @@ __global__ void __launch_bounds__(PR_NT) pair_runs_kernel(const u32 *__restrict_
     *(u64 *)(ord + p0) = out;
 }
 
-// keep8[j] = 1: the element stays in the list.  The thread that holds the FIRST member of a pair writes the bytes of
-// both members (the second one may belong to the next thread's elements: that thread leaves it alone).
+// keep8[j] = 1: the element stays in the list.  The thread that holds the FIRST member of a pair / triple writes the
+// bytes of all its members (the others may belong to the next thread's elements: that thread leaves them alone).
 __global__ void __launch_bounds__(256) pair_place_kernel(const u32 *__restrict__ act, const u32 *__restrict__ grp, u32 m,
                                                          const u8 *__restrict__ ord, u32 *__restrict__ sa, u8 *__restrict__ bwt,
                                                          u32 *__restrict__ actbits, u32 *__restrict__ primary,
@@ -1850,18 +1863,23 @@ __global__ void __launch_bounds__(256) pair_place_kernel(const u32 *__restrict__
     const u64 j0 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * PQ;
     const u32 lane = threadIdx.x & 31u;
     u32 placed = 0;
-    u32 cw0 = 0xffffffffu, cw1 = 0xffffffffu, cm0 = 0, cm1 = 0;  // words of the active-row bitmap to clear bits in (two pairs at most)
+    u32 cw0 = 0xffffffffu, cw1 = 0xffffffffu, cm0 = 0, cm1 = 0;  // words of the active-row bitmap to clear bits in (two groups at most)
     if (j0 < m) {
-        u32 G[12], A[5];
+        u32 G[12], A[6];
         pair_window(act, grp, m, j0, G, A);
-        // the results of the thread's pairs, fetched together
-        u32 o[PQ];
-        bool hd[PQ];
+        // the results of the thread's pairs and triples, fetched together
+        u32 kind[PQ], o0[PQ], o1[PQ], o2[PQ];
 #pragma unroll
         for (int q = 0; q < PQ; ++q) {
-            hd[q] = j0 + q + 1 < m && pair_head_at(G, q);
-            o[q] = 0;
-            if (hd[q]) o[q] = ord[min(A[q], A[q + 1])];
+            kind[q] = j0 + q < m ? pair_head_at(G, q) : 0u;
+            o0[q] = o1[q] = o2[q] = 0;
+            if (kind[q] == 2u) {
+                o0[q] = ord[min(A[q], A[q + 1])];
+            } else if (kind[q] == 3u) {
+                o0[q] = ord[A[q]];
+                o1[q] = ord[A[q + 1]];
+                o2[q] = ord[A[q + 2]];
+            }
         }
         int np = 0;
 #pragma unroll
@@ -1869,17 +1887,18 @@ __global__ void __launch_bounds__(256) pair_place_kernel(const u32 *__restrict__
             const u64 j = j0 + q;
             if (j >= m) break;
             const u32 g = G[4 + q];
-            if (hd[q]) {
+            u32 rows = 0;  // rows that become final (0: none)
+            if (kind[q] == 2u) {
                 const u32 s1 = A[q], s2 = A[q + 1];
                 // the result stands at the member that comes first in the text (1 = that one is the smaller suffix):
                 // -> 1: the first list element (s1) is the smaller suffix, 2: the second
-                u32 oo = o[q];
+                u32 oo = o0[q];
                 if (oo && s2 < s1) oo = 3u - oo;
                 const u8 k = oo ? 0 : 1;
                 keep8[j] = k;
                 keep8[j + 1] = k;
                 if (oo) {
-                    placed += 2;
+                    rows = 2;
                     if (oo == 2u) {  // the two rows change places
                         sa[g] = s2;
                         sa[g + 1] = s1;
@@ -1891,25 +1910,73 @@ __global__ void __launch_bounds__(256) pair_place_kernel(const u32 *__restrict__
                     }
                     if (s1 == 0) *primary = oo == 2u ? g + 1 : g;
                     if (s2 == 0) *primary = oo == 2u ? g : g + 1;
-                    // the two rows are final: no longer "active after round 0"
-                    u32 mask = 3u << (g & 31u);
-                    if ((g & 31u) == 31u) {
-                        mask = 1u << 31;
-                        atomicAnd(&actbits[(g >> 5) + 1], ~1u);
+                }
+            } else if (kind[q] == 3u) {
+                // o_k = result at member k (list order): 1 = it is smaller than the member it points to (the next one in
+                // TEXT order, cyclically), 2 = larger.  less(x, y) for every pair follows; the ranks must be 0, 1, 2.
+                const u32 x[3] = {A[q], A[q + 1], A[q + 2]};
+                const u32 ox[3] = {o0[q], o1[q], o2[q]};
+                u32 rk[3] = {0, 0, 0};
+                bool ok = ox[0] && ox[1] && ox[2];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    // the member that x[i] points to: the smallest larger start, or the smallest of all (wrap)
+                    int tgt = -1;
+#pragma unroll
+                    for (int k2 = 0; k2 < 3; ++k2)
+                        if (k2 != i && x[k2] > x[i] && (tgt < 0 || x[k2] < x[tgt])) tgt = k2;
+                    if (tgt < 0) {
+#pragma unroll
+                        for (int k2 = 0; k2 < 3; ++k2)
+                            if (k2 != i && (tgt < 0 || x[k2] < x[tgt])) tgt = k2;
                     }
-                    if (np == 0) {
-                        cw0 = g >> 5;
-                        cm0 = mask;
-                    } else {
-                        cw1 = g >> 5;
-                        cm1 = mask;
+                    // ox[i] == 1: x[i] < x[tgt] in suffix order -> tgt gets one more smaller suffix; else x[i] does
+                    if (ox[i] == 1u) ++rk[tgt];
+                    else ++rk[i];
+                }
+                ok = ok && rk[0] != rk[1] && rk[0] != rk[2] && rk[1] != rk[2];  // (each in 0..2: a permutation)
+                const u8 k = ok ? 0 : 1;
+                keep8[j] = k;
+                keep8[j + 1] = k;
+                keep8[j + 2] = k;
+                if (ok) {
+                    rows = 3;
+                    u8 b[3] = {0, 0, 0};
+                    if (bwt) {
+                        b[0] = bwt[g];
+                        b[1] = bwt[g + 1];
+                        b[2] = bwt[g + 2];
                     }
-                    ++np;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        sa[g + rk[i]] = x[i];
+                        if (bwt) bwt[g + rk[i]] = b[i];
+                        if (x[i] == 0) *primary = g + rk[i];
+                    }
                 }
             } else {
-                // the second member of a pair is written by the thread that holds the first one
-                const bool second = G[3 + q] == g && G[5 + q] != g && G[2 + q] != g;
-                if (!second) keep8[j] = keep_in ? keep_in[j] : (u8)1;
+                // the other members of a pair / triple are written by the thread that holds the first one
+                const bool same_b = G[3 + q] == g, same_a = G[5 + q] == g;
+                const bool second_of_2 = same_b && !same_a && G[2 + q] != g;
+                const bool second_of_3 = same_b && same_a && G[2 + q] != g && G[6 + q] != g;
+                const bool third_of_3 = same_b && !same_a && G[2 + q] == g && G[1 + q] != g;
+                if (!(second_of_2 || second_of_3 || third_of_3)) keep8[j] = keep_in ? keep_in[j] : (u8)1;
+            }
+            if (rows) {
+                placed += rows;
+                // the rows are final: no longer "active after round 0"
+                const u32 full = (rows == 2u ? 3u : 7u);
+                const u32 sh = g & 31u;
+                const u32 mask = full << sh;
+                if (sh + rows > 32u) atomicAnd(&actbits[(g >> 5) + 1], ~(full >> (32u - sh)));
+                if (np == 0) {
+                    cw0 = g >> 5;
+                    cm0 = mask;
+                } else {
+                    cw1 = g >> 5;
+                    cm1 = mask;
+                }
+                ++np;
             }
         }
     }
