@@ -2417,7 +2417,10 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
     bool deferred = false;
     u32 *dl_act = nullptr, *dl_row = nullptr, dl_nres = 0;
     u8 *dl_keep = nullptr;
-    if (m && b <= 8 && !env_int("B200SA_NO_EXT_TIEBREAK", 0)) {
+    // (a large active set that the pair path takes next: that path orders groups of two and three -- a chance collision
+    // next to a pair included -- by the text itself; the pass below would only add a trip over the list)
+    const bool pairs_first = done0 && rk_free[1] && pairs_mode == 1 && (u64)m * 64 >= (u64)len;
+    if (m && b <= 8 && !pairs_first && !env_int("B200SA_NO_EXT_TIEBREAK", 0)) {
         // groups of two to four equal keys are ordered by the next 64 bits of text (pairs only while the active set
         // is small: in a large one they are copies of repeats)
         t = ix.timer.begin("resolve_small", (double)m * 40.0);
