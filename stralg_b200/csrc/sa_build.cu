@@ -2100,9 +2100,10 @@ __global__ void __launch_bounds__(256) heads_to_actbits_kernel(const u8 *__restr
 // BWT rows (stralg/bwt.c:13-20) of the rows that were active after round 0, from the final suffix
 // array: the doubling rounds over large active sets do not maintain them (one gather per moved row and
 // round); their rows are exactly the rows whose bit is set here.
-__global__ void __launch_bounds__(256) bwt_fix_kernel(const u32 *__restrict__ actbits, const u32 *__restrict__ sa, u32 len,
-                                                      const u64 *__restrict__ packed, int bits, u8 *__restrict__ bwt,
-                                                      u32 *__restrict__ primary) {
+// dense bitmaps (periodic texts: every row): one thread per row
+__global__ void __launch_bounds__(256) bwt_fix_rows_kernel(const u32 *__restrict__ actbits, const u32 *__restrict__ sa, u32 len,
+                                                           const u64 *__restrict__ packed, int bits, u8 *__restrict__ bwt,
+                                                           u32 *__restrict__ primary) {
     const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= len || !((actbits[r >> 5] >> (r & 31u)) & 1u)) return;
     const u32 s = sa[r];
@@ -2113,6 +2114,30 @@ __global__ void __launch_bounds__(256) bwt_fix_kernel(const u32 *__restrict__ ac
         const u64 bitpos = (u64)(s - 1) * bits;
         const u64 w = packed[bitpos >> 6];
         bwt[r] = (u8)(((w >> (64 - bits - (unsigned)(bitpos & 63))) & ((1u << bits) - 1u)) + 1u);
+    }
+}
+
+// sparse bitmaps (one thread per 32 rows: few rows are left once the pair path has taken its rows out)
+__global__ void __launch_bounds__(256) bwt_fix_kernel(const u32 *__restrict__ actbits, const u32 *__restrict__ sa, u32 len,
+                                                      const u64 *__restrict__ packed, int bits, u8 *__restrict__ bwt,
+                                                      u32 *__restrict__ primary) {
+    const u64 wi = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi * 32 >= len) return;
+    u32 w = actbits[wi];
+    while (w) {
+        const u32 bit = (u32)__ffs((int)w) - 1u;
+        w &= w - 1u;
+        const u64 r = wi * 32 + bit;
+        if (r >= len) break;
+        const u32 s = sa[r];
+        if (s == 0) {
+            bwt[r] = 0;
+            *primary = (u32)r;
+        } else {
+            const u64 bitpos = (u64)(s - 1) * bits;
+            const u64 pw = packed[bitpos >> 6];
+            bwt[r] = (u8)(((pw >> (64 - bits - (unsigned)(bitpos & 63))) & ((1u << bits) - 1u)) + 1u);
+        }
     }
 }
 
@@ -2410,6 +2435,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
     // the list as round 0 left it: what rank[] has to hold for its suffixes (round0_msd.cu writes no ranks)
     const u32 *act0 = act, *row0 = grp;
     u32 m0 = m;
+    const u32 m_round0 = m;  // rows round 0 left active (their bits are set in `actbits`)
     bool rank_marked = false;  // rank[] has been set to "not materialised" (and holds the ranks of decided suffixes)
     const int pairs_mode = env_int("B200SA_PAIRS", 1);  // 0: off, 2: on lists of any size (tests)
     // the tie-break below leaves its list permuted, with a "stays" byte per element, when the pair path follows it:
@@ -2540,6 +2566,15 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 row0 = grp;
                 m0 = m;
                 pairs_done = true;
+                if (env_int("B200SA_DEBUG_RESIDUAL", 0) && m) {  // (development aid: what the pair path left)
+                    u32 h[2] = {0, 0};
+                    CUDA_CHECK(cudaMemsetAsync(d_pr, 0, 8, st));
+                    count_small_groups_kernel<<<div_up_u(m, 256), 256, 0, st>>>(grp, m, 0, d_pr);
+                    count_small_groups_kernel<<<div_up_u(m, 256), 256, 0, st>>>(grp, m, 1, d_pr + 1);
+                    read_back(h, d_pr, 8, st);
+                    fprintf(stderr, "[b200sa] after the pair path: %u of %u placed, %u left: %u in groups of 2..4 (%u in 3..4)\n",
+                            nplaced, m + nplaced, m, h[0], h[1]);
+                }
             }
             ix.timer.end(t);
         }
@@ -2984,7 +3019,12 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
     }
     if (need_bwt_fix) {
         t = ix.timer.begin("bwt_fix", (double)len * 0.125);
-        bwt_fix_kernel<<<div_up_u(len, 256), 256, 0, st>>>(actbits, sa, len, ix.packed, b, ix.bwt.ptr, d_primary.ptr);
+        // rows still marked: those round 0 left active minus the ones the pair path made final
+        const u64 marked = (u64)m_round0 - (u64)ix.stats.pair_placed;
+        if (marked * 8 > (u64)len)
+            bwt_fix_rows_kernel<<<div_up_u(len, 256), 256, 0, st>>>(actbits, sa, len, ix.packed, b, ix.bwt.ptr, d_primary.ptr);
+        else
+            bwt_fix_kernel<<<div_up_u(div_up_u(len, 32), 256), 256, 0, st>>>(actbits, sa, len, ix.packed, b, ix.bwt.ptr, d_primary.ptr);
         KERNEL_CHECK();
         ix.timer.end(t);
     }
