@@ -496,13 +496,14 @@ static constexpr u32 CHAIN_CAP = 1u << 16;     // longest offset taken from a ch
 // cslot[] and cont8[] are zeroed by the caller; only "continues" is written.
 __global__ void __launch_bounds__(CF_NT) chain_flags_kernel(const u32 *__restrict__ act, const u32 *__restrict__ grp, u32 m,
                                                             const u32 *__restrict__ rank, u8 *__restrict__ cslot,
-                                                            u8 *__restrict__ cont8, u32 *__restrict__ ncont) {
+                                                            u8 *__restrict__ cont8, u32 *__restrict__ ncont, u32 tile_mul) {
     __shared__ u32 hq[CF_TILE];    // rank[s + 1] of the group head at this tile-local index
     __shared__ u32 flag[CF_TILE];  // group (by head index): still "continues"
     __shared__ u32 wmax[CF_NT / 32];
     __shared__ u32 bcount;
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const u64 tile_base = (u64)blockIdx.x * CF_STEP;
+    // (tile_mul > 1: a sample of the tiles, evenly spaced)
+    const u64 tile_base = (u64)blockIdx.x * tile_mul * CF_STEP;
     const u64 tile_end = min((u64)m, tile_base + CF_TILE);  // one past the last element loaded
     const u64 j0 = tile_base + (u64)tid * CF_IPT;
     if (tid == 0) bcount = 0;
@@ -2459,6 +2460,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
             count_small_groups_kernel<<<div_up_u(m, 256), 256, 0, st>>>(grp, m, skip_pairs, d_nres + 1);
             KERNEL_CHECK();
             read_back(&nsmall, d_nres + 1, 4, st);
+            if ((u64)nsmall * 64 < (u64)m) nsmall = 0;  // (a trip over the whole list for a sprinkle of small groups: the rounds take them)
         }
         if (nsmall) {
             // the permuted list goes into a buffer that is dead until the rounds write their keys (both m <= len words)
@@ -2695,10 +2697,25 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 CUDA_CHECK(cudaMemsetAsync(cont8, 0, cont_bytes, st));
                 CUDA_CHECK(cudaMemsetAsync(cslot, 0, m, st));
                 CUDA_CHECK(cudaMemsetAsync(d_ncont, 0, 4, st));
-                chain_flags_kernel<<<div_up_u(m, CF_STEP), CF_NT, 0, st>>>(act, grp, m, rank, cslot, cont8, d_ncont);
-                KERNEL_CHECK();
+                const u32 cf_tiles = div_up_u(m, CF_STEP);
                 u32 ncont = 0;
-                read_back(&ncont, d_ncont, 4, st);
+                bool worth = true;
+                if (cf_tiles > 16384) {
+                    // a sample of 2 048 tiles first: a list whose groups do not continue (diverged copies, periodic
+                    // texts) is not worth the full pass (what the sample marks is what the full pass would mark)
+                    const u32 mul = cf_tiles / 2048;
+                    chain_flags_kernel<<<2048, CF_NT, 0, st>>>(act, grp, m, rank, cslot, cont8, d_ncont, mul);
+                    KERNEL_CHECK();
+                    read_back(&ncont, d_ncont, 4, st);
+                    worth = (u64)ncont * (u64)std::max(1, env_int("B200SA_CHAIN_USE_FRAC", 2)) * 2 >= (u64)2048 * CF_STEP;
+                    CUDA_CHECK(cudaMemsetAsync(d_ncont, 0, 4, st));
+                    ncont = 0;
+                }
+                if (worth) {
+                    chain_flags_kernel<<<cf_tiles, CF_NT, 0, st>>>(act, grp, m, rank, cslot, cont8, d_ncont, 1);
+                    KERNEL_CHECK();
+                    read_back(&ncont, d_ncont, 4, st);
+                }
                 ix.timer.end(t);
                 // worth it when most groups continue (copies of long segments); texts whose groups are large and
                 // shallow (many diverged copies) gain nothing from it
