@@ -60,3 +60,22 @@ def test_remap_table_matches_oracle(oracle):
         assert np.array_equal(t.remap(raw), codes[:-1])
         assert t.rev_remap(t.remap(raw)) == raw
     assert RemapTable(b"acgt").remap(b"acgx") is None  # remap.c:80-84
+
+
+def test_stats_struct_layout_matches_the_header(tmp_path):
+    """struct b200sa_stats as the C compiler lays it out (include/b200sa.h) against the ctypes mirror
+    (stralg_b200/_lib.py): same size, same field offsets -- the struct grows with the library."""
+    import subprocess
+    from stralg_b200._lib import Stats
+    fields = [name for name, _ in Stats._fields_]
+    src = tmp_path / "layout.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "b200sa.h")}"',
+             'int main(void) {', '  printf("%zu\\n", sizeof(struct b200sa_stats));']
+    lines += [f'  printf("%zu\\n", offsetof(struct b200sa_stats, {f}));' for f in fields]
+    lines += ['  return 0;', '}']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert out[0] == C.sizeof(Stats)
+    assert out[1:] == [getattr(Stats, f).offset for f in fields]
