@@ -387,6 +387,7 @@ def nonuniform_builds(args, lib, stralg_b200, torch, local_rank, stream, n):
                    "doubling_rounds": st["rounds"], "round0_mode": st["round0_mode"], "partition_levels": st["passes0"],
                    "k0": st["k0"], "shallow_buckets": st["shallow_buckets"], "chain_rounds": st["chain_rounds"],
                    "pivot_rounds": st["pivot_rounds"], "pivot_elems_over_len": st["pivot_elems"] / (nn + 1),
+                   "pair_placed": st["pair_placed"], "resolved_by_text": st["resolved_small"],
                    "sorted_total_over_len": st["sorted_total"] / (nn + 1), "sa_verified": ok, "checker": why,
                    "tables": "SA + BWT + C + sampled O" if occ else "SA",
                    "top_stages_ms": {k: round(v, 2) for k, v in top}}
