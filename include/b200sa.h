@@ -91,7 +91,8 @@ struct b200sa_stats {
     uint32_t pair_placed;      /* suffixes in groups of two equal initial keys (a position of a repeat and the same
                                   position of its copy) decided by one text comparison per repeat */
     uint32_t ktable_k;         /* symbols per entry of the k-mer seed table (B200SA_BUILD_KTABLE), 0 = none */
-    uint32_t reserved1;
+    uint32_t dense_keys;       /* initial keys formed as base-(letters) numbers (alphabets that do not fill their symbol
+                                  width, e.g. DNA + N or amino acids): the number of letters, 0 = raw keys */
 };
 
 /* ---- construction ------------------------------------------------------------------------

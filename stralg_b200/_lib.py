@@ -43,7 +43,7 @@ class Stats(C.Structure):
         ("chain_elems", C.c_uint64), ("lazy_lookups", C.c_uint64), ("resolved_small", C.c_uint64),
         ("small_path_elems", C.c_uint64), ("pivot_elems", C.c_uint64), ("pivot_rounds", C.c_uint32),
         ("pair_placed", C.c_uint32),
-        ("ktable_k", C.c_uint32), ("reserved1", C.c_uint32),
+        ("ktable_k", C.c_uint32), ("dense_keys", C.c_uint32),
     ]
 
 

@@ -685,7 +685,7 @@ int b200sa_stats(const b200sa_index *idx, struct b200sa_stats *out) {
     out->pivot_rounds = ix.stats.pivot_rounds;
     out->pair_placed = ix.stats.pair_placed;
     out->ktable_k = ix.ktable.ptr ? (uint32_t)ix.ktable_k : 0u;
-    out->reserved1 = 0;
+    out->dense_keys = ix.stats.dense_keys;
     return 0;
 }
 

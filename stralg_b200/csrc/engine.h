@@ -36,6 +36,7 @@ struct BuildStats {
     u32 pivot_rounds;     // doubling rounds that split their groups around a pivot key (sa_build.cu: pivot path)
     u64 pivot_elems;      // list elements that stayed with the pivot key and skipped the sort, summed over rounds
     u32 pair_placed;      // suffixes in groups of two that one text comparison per repeat decided after round 0
+    u32 dense_keys;       // bucketed round 0 formed dense keys (round0_msd.cuh DenseKey): the number of letters
 };
 
 // Occurrence-table layouts

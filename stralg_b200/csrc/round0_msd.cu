@@ -59,10 +59,84 @@ static int env_int2(const char *name, int dflt) {
 // ---------------------------------------------------------------------------------------------
 // Planning
 // ---------------------------------------------------------------------------------------------
+static int bit_length_u64(u64 v) {
+    int l = 0;
+    while (v) { ++l; v >>= 1; }
+    return l;
+}
+static u64 pow_u64(u64 x, int k) {
+    u64 r = 1;
+    for (int i = 0; i < k; ++i) r *= x;
+    return r;
+}
+
+// Dense keys (see DenseKey): digits are not tied to symbol boundaries, a partly used top digit is
+// accounted for when the bucket bits are chosen.
+static bool msd_make_plan_dense(u32 len, u32 nsym, int b, MsdPlan &pl) {
+    const int dmax = std::max(4, std::min(10, env_int2("B200SA_MSD_DMAX", 10)));
+    const int target = std::max(1, env_int2("B200SA_MSD_AVG", 3000));
+    int log2len = 0;
+    while ((1ull << log2len) < (u64)len) ++log2len;
+    const double eff = std::log2((double)nsym);
+    const int margin = env_int2("B200SA_KEY_MARGIN", 8);
+    const int k_wanted = std::max(1, (int)std::ceil((log2len + margin) / eff));
+    int best_K = 0;
+    for (int pb = b; pb >= 0; pb -= b) {
+        int K = std::min(k_wanted, 64 / b - (pb ? 1 : 0));  // one 64-bit window holds prev + K symbols
+        const int kf = env_int2("B200SA_MSD_K", 0);
+        if (kf > 0) K = std::min(K, kf);
+        for (; K >= 1; --K) {
+            const u64 span = pow_u64(nsym, K);            // keys are 0 .. span - 1
+            const int KB = bit_length_u64(span - 1);
+            if (KB > 42) continue;
+            // bucket bits: until an average USED bucket holds <= target suffixes
+            int BB = 1;
+            auto used = [&](int bb) { return bb >= KB ? span : ((span - 1) >> (KB - bb)) + 1; };
+            while ((u64)len / used(BB) > (u64)target && BB + 1 <= 3 * dmax && BB + 1 <= KB) ++BB;
+            const int forced = env_int2("B200SA_MSD_BB", 0);
+            if (forced > 0) BB = std::max(1, std::min(std::min(3 * dmax, KB), forced));
+            const int nl = (BB + dmax - 1) / dmax;
+            int D[3] = {0, 0, 0};
+            for (int i = 0; i < nl; ++i) D[i] = BB / nl + (i < BB % nl ? 1 : 0);
+            if (KB - D[0] > 32 - pb) continue;            // 32 + pb + (KB - D1) <= 64
+            if (KB - BB > 32) continue;
+            if (K <= best_K) break;                       // (the variant that carries the preceding symbol reached as deep)
+            best_K = K;
+            pl.nlevels = nl;
+            for (int i = 0; i < 3; ++i) pl.D[i] = D[i];
+            pl.BB = BB;
+            pl.dmax = dmax;
+            pl.K = K;
+            pl.KB = KB;
+            pl.pb = pb;
+            pl.R = KB - BB;
+            pl.dense.nsym = nsym;
+            int Klo = 0;
+            while (Klo < K && pow_u64(nsym, Klo + 1) <= 0xffffffffull) ++Klo;
+            pl.dense.Klo = (u32)Klo;
+            pl.dense.Khi = (u32)(K - Klo);
+            pl.dense.powlo = (u32)pow_u64(nsym, Klo);
+            break;
+        }
+        // (carrying the preceding symbol saves the BWT gather: worth a key that is a few bits short of the wish)
+        if (best_K >= k_wanted || best_K * eff >= log2len + margin / 2) break;
+    }
+    return best_K > 0;
+}
+
 bool msd_make_plan(u32 len, u32 sigma, int bits, MsdPlan &pl) {
     const char *mode = getenv("B200SA_ROUND0");
     if (mode && !strcmp(mode, "lsd")) return false;
     const int b = bits;
+    pl.dense = DenseKey{0, 0, 0, 0};
+    {
+        // alphabets that use less than 9/10 of the codes of their symbol width: dense keys
+        const u32 nsym = sigma > 1 ? sigma - 1 : 1;
+        const int dk = env_int2("B200SA_DENSE_KEYS", -1);
+        const bool sparse_alphabet = b >= 2 && nsym >= 2 && (u64)nsym * 10 <= (9ull << b);
+        if (dk != 0 && b >= 2 && nsym >= 2 && (sparse_alphabet || dk > 0) && msd_make_plan_dense(len, nsym, b, pl)) return true;
+        pl.dense = DenseKey{0, 0, 0, 0};
+    }
     // Bucket bits: whole symbols (a digit never splits a symbol: with alphabets that do not fill
     // their b bits the leading bits of a symbol carry no information), until an average bucket
     // holds <= `target` suffixes.  At most 10 bits per level.
@@ -120,9 +194,10 @@ bool msd_make_plan(u32 len, u32 sigma, int bits, MsdPlan &pl) {
 // Level-1 histogram straight from the packed text: hist[x] = #{t in [0, n] : first D key bits of
 // suffix t == x}
 // ---------------------------------------------------------------------------------------------
-template <int BITS>
+template <int BITS, bool DENSE = false>
 __global__ void __launch_bounds__(256) msd_hist_text_kernel(const u64 *__restrict__ packed, u32 n, u64 nwords_data,
-                                                            int D, u32 *__restrict__ hist) {
+                                                            int D, u32 *__restrict__ hist, DenseKey dk = DenseKey{0, 0, 0, 0},
+                                                            int dshift = 0) {
     constexpr int CPW = 64 / BITS;
     __shared__ u32 sh[MSD_MAXBINS];
     const int bins = 1 << D;
@@ -137,7 +212,8 @@ __global__ void __launch_bounds__(256) msd_hist_text_kernel(const u64 *__restric
             if (t0 + q <= n) {
                 const int o = q * BITS;
                 u64 win = o ? ((hi << o) | (lo >> (64 - o))) : hi;
-                atomicAdd(&sh[(u32)(win >> (64 - D))], 1u);
+                if (DENSE) atomicAdd(&sh[(u32)(dense_key_of<BITS>(win, dk) >> dshift)], 1u);
+                else atomicAdd(&sh[(u32)(win >> (64 - D))], 1u);
             }
         }
     }
@@ -488,6 +564,7 @@ struct Text1Args {
     u64 restmask;     // rest = key & restmask
     int rest_shift;   // 32 + pb
     u32 *cursor;      // [1 << D] next free slot of every level-1 bucket
+    DenseKey dense;   // nsym != 0: the key is the base-nsym number of the K symbols (KB bits), digit = key >> dshift
 };
 
 // 128-bit window (H:L) of the staged text starting at bit `off`
@@ -500,7 +577,7 @@ __device__ __forceinline__ void stage_window(const u64 *st, u32 off, u64 &H, u64
 
 // BITS = symbol width, HAS_PREV = the preceding symbol is carried in the element (pb == BITS):
 // compile-time so that every per-symbol shift is an immediate.
-template <int BITS, bool HAS_PREV, int NT = T1_NT, int IPT = T1_IPT, int CTAS = 2>
+template <int BITS, bool HAS_PREV, int NT = T1_NT, int IPT = T1_IPT, int CTAS = 2, bool DENSE = false>
 __global__ void __launch_bounds__(NT, CTAS) msd_partition_text_kernel(Text1Args a) {
     constexpr int TILE = NT * IPT;
     constexpr int STAGE_MAX = TILE * 8 / 64 + 4;
@@ -553,7 +630,7 @@ __global__ void __launch_bounds__(NT, CTAS) msd_partition_text_kernel(Text1Args 
             const u32 khi = (u32)((win << lead) >> 32);  // leading 32 bits of the key
             ds[j] = 0;
             if (i0 + j < count) {
-                const u32 d = khi >> dsh;
+                const u32 d = DENSE ? (u32)(dense_key_of<BITS>(win << lead, a.dense) >> a.dshift) : khi >> dsh;
                 const u32 slot = atomicAdd(&hist[d], 1u);
                 ds[j] = d | (slot << 10);
             }
@@ -601,7 +678,7 @@ __global__ void __launch_bounds__(NT, CTAS) msd_partition_text_kernel(Text1Args 
             if (i0 + j < count) {
                 const int sh = q * b;
                 const u64 win = sh ? (H << sh) | (L >> (64 - sh)) : H;
-                const u32 rest = (u32)((win << lead) >> kshift) & restmask;
+                const u32 rest = (DENSE ? (u32)dense_key_of<BITS>(win << lead, a.dense) : (u32)((win << lead) >> kshift)) & restmask;
                 const u32 hiw = HAS_PREV ? (rest << b) | (u32)(win >> (64 - b)) : rest;
                 const u32 d = ds[j] & 1023u;
                 const u32 pos = hist[d] + (ds[j] >> 10);
@@ -1228,11 +1305,30 @@ struct OverArgs {
 };
 
 __global__ void msd_short_buckets_kernel(const u64 *__restrict__ packed, u32 n, int bits, int BB, u32 d0,
-                                         u32 *__restrict__ shortb) {
+                                         u32 *__restrict__ shortb, DenseKey dk, int R) {
     const u32 j = threadIdx.x;
     u32 v = 0xffffffffu;
-    if (j < d0 && j <= n) v = (u32)(window_at(packed, (u64)(n - j), bits) >> (64 - BB));
+    if (j < d0 && j <= n) {
+        const u64 w = window_at(packed, (u64)(n - j), bits);
+        v = dk.nsym ? (u32)(dense_key_of_bits(w, bits, dk) >> R) : (u32)(w >> (64 - BB));
+    }
     shortb[j] = v;
+}
+// Dense keys: the members of bucket x hold the keys [x << R, (x + 1) << R) (below `span` = nsym^K); they share the
+// leading base-nsym digits the two ends of that range share.  depth = the minimum over the oversize buckets.
+__global__ void __launch_bounds__(256) msd_dense_depth_kernel(const u32 *__restrict__ bstart, u64 nb, u32 maxb, int R,
+                                                              u32 nsym, u32 K, u64 span, u32 *__restrict__ depth) {
+    const u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb || bstart[b + 1] - bstart[b] <= maxb) return;
+    u64 lo = b << R, hi = ((b + 1) << R) - 1;
+    if (hi >= span) hi = span - 1;
+    u32 j = 0;  // trailing digits dropped until the two ends agree
+    while (lo != hi && j < K) {
+        lo /= nsym;
+        hi /= nsym;
+        ++j;
+    }
+    atomicMin(depth, K - j);
 }
 
 // out[0] = buckets with more than maxb suffixes, out[1] = suffixes in them
@@ -1392,11 +1488,15 @@ void fill_singleton_ranks(const DeviceIndex &ix, const u32 *actbits, u32 *rank) 
 // Host orchestration
 // ---------------------------------------------------------------------------------------------
 template <int BITS>
-static void launch_hist_text(const DeviceIndex &ix, u64 nwords_data, int D, u32 *hist, cudaStream_t st) {
+static void launch_hist_text(const DeviceIndex &ix, u64 nwords_data, int D, u32 *hist, cudaStream_t st,
+                             const MsdPlan &pl) {
     unsigned blocks = div_up_u(nwords_data, 256 * 4);
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks == 0) blocks = 1;
-    msd_hist_text_kernel<BITS><<<blocks, 256, 0, st>>>(ix.packed, ix.n, nwords_data, D, hist);
+    if (pl.dense.nsym)
+        msd_hist_text_kernel<BITS, true><<<blocks, 256, 0, st>>>(ix.packed, ix.n, nwords_data, D, hist, pl.dense, pl.KB - D);
+    else
+        msd_hist_text_kernel<BITS><<<blocks, 256, 0, st>>>(ix.packed, ix.n, nwords_data, D, hist);
     KERNEL_CHECK();
 }
 
@@ -1430,6 +1530,12 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<2, true, T1_NT, T1_IPT, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<4, true, T1_NT, T1_IPT, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<8, true, T1_NT, T1_IPT, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<2, false, T1_NT, T1_IPT, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<4, false, T1_NT, T1_IPT, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_partition_text_kernel<8, false, T1_NT, T1_IPT, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_partition_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_partition_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_local_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L3_SMEM));
@@ -1466,9 +1572,14 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     //     unless that is more than 1/8 of the text (periodic texts: every bucket), where the caller's
     //     LSD path, whose keys are K symbols deep instead of BB / bits, is the better start.
     enum { GO, MORE, FALLBACK };
+    u32 dense_d0 = 0;
     auto decide = [&](const u32 *final_start, u64 nbuckets) -> int {
         u32 maxbucket = 0;
         read_back(&maxbucket, d_misc, 4, st);
+        if (env_int2("B200SA_DEBUG_PLAN", 0))
+            fprintf(stderr, "[b200sa] round-0 plan: levels %d D %d/%d/%d BB %d K %d KB %d pb %d R %d dense %u (%u+%u, powlo %u) max bucket %u\n",
+                    pl.nlevels, pl.D[0], pl.D[1], pl.D[2], pl.BB, pl.K, pl.KB, pl.pb, pl.R, pl.dense.nsym, pl.dense.Khi,
+                    pl.dense.Klo, pl.dense.powlo, maxbucket);
         if (maxbucket <= (u32)L3_MAXB) return GO;
         if (env_int2("B200SA_MSD_NO_OVERSIZE", 0)) return FALLBACK;
         CUDA_CHECK(cudaMemsetAsync(d_over, 0, 16, st));
@@ -1478,8 +1589,9 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         read_back(h, d_over, 16, st);
         const int more_frac = std::max(1, env_int2("B200SA_MSD_MORE_FRAC", 64));
         const int bbmax = env_int2("B200SA_MSD_BBMAX", 26);
-        int room = std::min(std::min(pl.dmax, pl.R), bbmax - pl.BB) / b * b;
-        if (h[1] > (unsigned long long)len / (unsigned)more_frac && pl.nlevels < 3 && room >= b) {
+        const int bq = pl.dense.nsym ? 1 : b;  // (dense keys: digits are not tied to symbol boundaries)
+        int room = std::min(std::min(pl.dmax, pl.R), bbmax - pl.BB) / bq * bq;
+        if (h[1] > (unsigned long long)len / (unsigned)more_frac && pl.nlevels < 3 && room >= bq) {
             pl.D[pl.nlevels++] = room;
             pl.BB += room;
             pl.R -= room;
@@ -1489,6 +1601,17 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         }
         const int frac = std::max(1, env_int2("B200SA_MSD_OVER_FRAC", 8));
         if (h[1] > (unsigned long long)len / (unsigned)frac) return FALLBACK;
+        if (pl.dense.nsym) {
+            // what the members of an oversize bucket of dense keys are known to share
+            CUDA_CHECK(cudaMemsetAsync(d_misc + 2, 0xff, 4, st));
+            msd_dense_depth_kernel<<<div_up_u(nbuckets, 256), 256, 0, st>>>(final_start, nbuckets, (u32)L3_MAXB, pl.R, pl.dense.nsym,
+                                                                           (u32)pl.K, pow_u64(pl.dense.nsym, pl.K), d_misc + 2);
+            KERNEL_CHECK();
+            read_back(&dense_d0, d_misc + 2, 4, st);
+            if (env_int2("B200SA_DEBUG_PLAN", 0)) fprintf(stderr, "[b200sa] dense keys: oversize buckets share %u symbols\n", dense_d0);
+            // (a bucket that straddles a change of a leading symbol shares little: rare)
+            if (dense_d0 < (u32)std::max(2, pl.K / 4) || dense_d0 > 32) return FALLBACK;
+        }
         r.shallow_elems = h[1];  // (an upper bound: such a bucket is still sorted when its whole tile fits)
         return GO;
     };
@@ -1507,10 +1630,10 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     const u64 nwords_data = ((u64)len + ix.pk.cpw - 1) / ix.pk.cpw;
     int t = ix.timer.begin("msd_hist1", (double)len * b / 8.0);
     switch (b) {
-        case 1: launch_hist_text<1>(ix, nwords_data, pl.D[0], cursor[0], st); break;
-        case 2: launch_hist_text<2>(ix, nwords_data, pl.D[0], cursor[0], st); break;
-        case 4: launch_hist_text<4>(ix, nwords_data, pl.D[0], cursor[0], st); break;
-        default: launch_hist_text<8>(ix, nwords_data, pl.D[0], cursor[0], st); break;
+        case 1: launch_hist_text<1>(ix, nwords_data, pl.D[0], cursor[0], st, pl); break;
+        case 2: launch_hist_text<2>(ix, nwords_data, pl.D[0], cursor[0], st, pl); break;
+        case 4: launch_hist_text<4>(ix, nwords_data, pl.D[0], cursor[0], st, pl); break;
+        default: launch_hist_text<8>(ix, nwords_data, pl.D[0], cursor[0], st, pl); break;
     }
     {
         unsigned bd = std::min(1024u, std::max(32u, (unsigned)nb[0]));
@@ -1534,8 +1657,16 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         ta.cursor = cursor[0];
         t = ix.timer.begin("msd_part1", (double)len * (8.0 + b / 8.0));
         const unsigned g1 = div_up_u(len, T1_TILE);
-        const int which = (b == 1 ? 0 : b == 2 ? 1 : b == 4 ? 2 : 3) * 2 + (pl.pb ? 1 : 0);
+        ta.dense = pl.dense;
+        const int which = pl.dense.nsym ? 100 + (b == 2 ? 0 : b == 4 ? 1 : 2) * 2 + (pl.pb ? 1 : 0)
+                                        : (b == 1 ? 0 : b == 2 ? 1 : b == 4 ? 2 : 3) * 2 + (pl.pb ? 1 : 0);
         switch (which) {
+            case 100: msd_partition_text_kernel<2, false, T1_NT, T1_IPT, 2, true><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
+            case 101: msd_partition_text_kernel<2, true, T1_NT, T1_IPT, 2, true><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
+            case 102: msd_partition_text_kernel<4, false, T1_NT, T1_IPT, 2, true><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
+            case 103: msd_partition_text_kernel<4, true, T1_NT, T1_IPT, 2, true><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
+            case 104: msd_partition_text_kernel<8, false, T1_NT, T1_IPT, 2, true><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
+            case 105: msd_partition_text_kernel<8, true, T1_NT, T1_IPT, 2, true><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
             case 0: msd_partition_text_kernel<1, false><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
             case 1: msd_partition_text_kernel<1, true><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
             case 2: msd_partition_text_kernel<2, false><<<g1, T1_NT, T1_SMEM, st>>>(ta); break;
@@ -1640,10 +1771,10 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         oa.count = d_misc + 6;
         u32 *shortb = ar.get<u32>(32);
         oa.shortb = shortb;
-        oa.d0 = (u32)(pl.BB / b);
+        oa.d0 = pl.dense.nsym ? dense_d0 : (u32)(pl.BB / b);
         oa.fix = ar.get<u32>(4 * 32);
         oa.nfix = d_misc + 7;
-        msd_short_buckets_kernel<<<1, 32, 0, st>>>(ix.packed, n, b, pl.BB, oa.d0, shortb);
+        msd_short_buckets_kernel<<<1, 32, 0, st>>>(ix.packed, n, b, pl.BB, oa.d0, shortb, pl.dense, pl.R);
         KERNEL_CHECK();
         msd_bigtile_kernel<<<hmisc[5], L3_NT, RB_SMEM, st>>>(la, oa);
         KERNEL_CHECK();

@@ -15,12 +15,40 @@ __device__ __forceinline__ u64 window_at(const u64 *__restrict__ packed, u64 sym
     return (hi << o) | (lo >> (64 - o));
 }
 
+// Dense round-0 keys (alphabets that do not fill their symbol width, e.g. DNA + N in 4 bits or the
+// 20 amino acids in 8): the key of a suffix is the NUMBER its first K symbols spell in base nsym
+// instead of the K * bits raw bits, so that keys spread evenly over their KB bits whatever the
+// alphabet -- the bucket tables and the interpolation of the in-SM sort rely on that.  The number is
+// formed as hi * powlo + lo from two 32-bit halves of Khi and Klo symbols.
+struct DenseKey {
+    u32 nsym;          // 0: raw keys
+    u32 Khi, Klo;      // Khi + Klo = K
+    u32 powlo;         // nsym ^ Klo
+};
+template <int BITS>
+__device__ __forceinline__ u64 dense_key_of(u64 win, const DenseKey &dk) {  // win: window starting at the suffix
+    u32 hi = 0, lo = 0;
+    for (u32 i = 0; i < dk.Khi; ++i) {
+        hi = hi * dk.nsym + (u32)(win >> (64 - BITS));
+        win <<= BITS;
+    }
+    for (u32 i = 0; i < dk.Klo; ++i) {
+        lo = lo * dk.nsym + (u32)(win >> (64 - BITS));
+        win <<= BITS;
+    }
+    return (u64)hi * dk.powlo + lo;
+}
+__device__ __forceinline__ u64 dense_key_of_bits(u64 win, int bits, const DenseKey &dk) {
+    return bits == 2 ? dense_key_of<2>(win, dk) : bits == 4 ? dense_key_of<4>(win, dk) : dense_key_of<8>(win, dk);
+}
+
 struct MsdPlan {
     int nlevels;       // 1..3 partition levels
-    int D[3];          // digit bits per level (multiples of the symbol width)
+    int D[3];          // digit bits per level (multiples of the symbol width; any width with dense keys)
     int BB;            // total bucket bits = D[0] + D[1] + D[2]
     int K;             // symbols in the round-0 key
-    int KB;            // K * bits
+    int KB;            // key bits: K * bits, or the bits of nsym^K - 1 with dense keys
+    DenseKey dense;    // nsym == 0: raw keys
     int pb;            // bits of the preceding symbol carried in an element (0: BWT is gathered afterwards)
     int R;             // key bits left for the in-SM sort = KB - BB
     int dmax;          // largest digit a partition level takes (a multiple of the symbol width)

@@ -266,15 +266,23 @@ struct LazyRank {
     u64 keymask;
     u32 n, len;
     int K, bits;
+    int kb;                // bits of a round-0 key: K * bits, or fewer with dense keys
+    DenseKey dense;        // bucketed round 0 with dense keys (round0_msd.cuh): nsym != 0
 };
+
+// the round-0 key of suffix t, as the bucketed round 0 formed it
+__device__ __forceinline__ u64 round0_key_at(const LazyRank &lr, u32 t) {
+    const u64 w = window_at(lr.packed, t, lr.bits);
+    return lr.dense.nsym ? dense_key_of_bits(w, lr.bits, lr.dense) : w >> (64 - lr.kb);
+}
 
 __device__ __forceinline__ u32 lazy_rank_of(const LazyRank &lr, u32 t) {
     {
         const u32 r = lr.rank[t];
         if (!lr.sparse || r != RANK_NONE) return r;
     }
-    const int kb = lr.K * lr.bits;
-    const u64 key = window_at(lr.packed, t, lr.bits) >> (64 - kb);
+    const int kb = lr.kb;
+    const u64 key = round0_key_at(lr, t);
     u32 lo, hi;  // first index with key(index) >= key
     if (lr.keys0) {
         lo = 0;
@@ -296,17 +304,17 @@ __device__ __forceinline__ u32 lazy_rank_of(const LazyRank &lr, u32 t) {
             const u64 rem = key & ((1ull << rbits) - 1ull);
             const u32 g = lo + (u32)((rem * (u64)(hi - lo)) >> rbits);
             const u32 p1 = g > lo + 32u ? g - 32u : lo;
-            if ((window_at(lr.packed, lr.sa0[p1], lr.bits) >> (64 - kb)) < key) lo = p1 + 1;
+            if (round0_key_at(lr, lr.sa0[p1]) < key) lo = p1 + 1;
             else hi = p1;
             const u32 p2 = g + 32u;
             if (p2 >= lo && p2 < hi) {
-                if ((window_at(lr.packed, lr.sa0[p2], lr.bits) >> (64 - kb)) < key) lo = p2 + 1;
+                if (round0_key_at(lr, lr.sa0[p2]) < key) lo = p2 + 1;
                 else hi = p2;
             }
         }
         while (lo < hi) {
             u32 mid = lo + (hi - lo) / 2;
-            u64 km = window_at(lr.packed, lr.sa0[mid], lr.bits) >> (64 - kb);
+            u64 km = round0_key_at(lr, lr.sa0[mid]);
             if (km < key) lo = mid + 1;
             else hi = mid;
         }
@@ -396,8 +404,8 @@ __global__ void __launch_bounds__(256) make_keys_round_kernel(const u32 *__restr
                     lo = lazy_rank_of(lr, t32);
                     ++nlazy;
                 } else {
-                    const int kb = lr.K * lr.bits, rbits = kb - lr.BB;
-                    const u64 key = window_at(lr.packed, t32, lr.bits) >> (64 - kb);
+                    const int kb = lr.kb, rbits = kb - lr.BB;
+                    const u64 key = round0_key_at(lr, t32);
                     const u64 bid = rbits > 0 ? key >> rbits : key;
                     blo = lr.bstart[bid];
                     bhi = lr.bstart[bid + 1];
@@ -2333,6 +2341,8 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
                 K = r0.plan.K;
                 bwt_in_sort = r0.bwt_written;
                 lr.keys0 = nullptr; lr.bstart = r0.bucket_start; lr.BB = r0.plan.BB; lr.K = K;
+                lr.kb = r0.plan.KB; lr.dense = r0.plan.dense;
+                ix.stats.dense_keys = r0.plan.dense.nsym;
                 lr.keymask = (K * b >= 64) ? ~0ull : ((1ull << (K * b)) - 1ull);
                 ix.stats.k0 = K;
                 ix.stats.radix_bits = r0.plan.D[0];
@@ -2426,7 +2436,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
             KERNEL_CHECK();
         }
         ix.timer.end(t);
-        lr.keys0 = keys0; lr.keymask = keymask0; lr.K = K;
+        lr.keys0 = keys0; lr.keymask = keymask0; lr.K = K; lr.kb = K * b;
         rk_free[0] = kout;  // (keys0 stays: lazy ranks are looked up in it)
     }
 

@@ -86,6 +86,28 @@ def nonuniform_texts():
     t2[100000:100700] = 1
     t2[400000:400700] = 1
     out.append(("pair_copies_binary_700k", t2, 3))
+    # alphabets that do not fill their symbol width (dense initial keys, round0_msd.cuh DenseKey): DNA with N
+    # (A C G N T, N in long runs and sprinkled, one run at the very end), amino acids with copied segments,
+    # three letters with a period and a run of the smallest letter at the end
+    t = rng.choice(np.array([1, 2, 3, 5], dtype=np.uint8), 1 << 20)
+    for k in range(5):  # (about 5 % of the text, as in a real assembly: more than 1/8 would take the LSD path)
+        a = int(rng.integers(0, len(t) - 60000))
+        t[a:a + int(rng.integers(500, 20000))] = 4
+    t[rng.integers(0, len(t), 300)] = 4
+    t[-3000:] = 4
+    out.append(("dna_n_runs_1M", t, 6))
+    t = rng.integers(1, 21, 800000).astype(np.uint8)
+    for k in range(40):
+        ln = int(rng.integers(200, 20000))
+        src = int(rng.integers(0, len(t) - ln))
+        dst = int(rng.integers(0, len(t) - ln))
+        t[dst:dst + ln] = t[src:src + ln].copy()
+    t[300000:330000] = 7
+    out.append(("amino_copies_800k", t, 21))
+    t = rng.integers(1, 4, 600000).astype(np.uint8)
+    t[100000:160000] = np.tile(rng.integers(1, 4, 37).astype(np.uint8), 60000 // 37 + 1)[:60000]
+    t[-2000:] = 1
+    out.append(("ternary_period_600k", t, 4))
     return out
 
 
@@ -101,7 +123,9 @@ def _texts():
 
 NAMES = ["polyA_mid_end_1M", "polyA_tandemCA_1M", "block_copies_1M", "skewed_70A_1M", "skewed_97A_300k",
          "hg38_sample_500k", "hg38_tiled_mut_1200k", "binary_runs_600k", "sym16_skewed_500k", "byte_skewed_400k",
-         "pair_copies_1M", "pair_copies_binary_700k"]
+         "pair_copies_1M", "pair_copies_binary_700k", "dna_n_runs_1M", "amino_copies_800k", "ternary_period_600k"]
+
+SPARSE_ALPHABETS = ("dna_n_runs_1M", "amino_copies_800k", "ternary_period_600k", "sym16_skewed_500k")
 
 # default plan; never add a level (everything oversize becomes a shallow group, however much it is);
 # always add a level when one bucket is oversize; tiny buckets (many segments per tile) with shallow groups
@@ -124,6 +148,10 @@ MODES = {
     "pairs_force": {"B200SA_PAIRS": "2"},
     "pairs_force_noext": {"B200SA_PAIRS": "2", "B200SA_NO_EXT_TIEBREAK": "1"},
     "pairs_off": {"B200SA_PAIRS": "0"},
+    # initial keys as base-(letters) numbers on every alphabet / never; with shallow groups only
+    "dense_keys_on": {"B200SA_DENSE_KEYS": "1"},
+    "dense_keys_off": {"B200SA_DENSE_KEYS": "0"},
+    "dense_keys_shallow": {"B200SA_DENSE_KEYS": "1", "B200SA_MSD_MORE_FRAC": "1", "B200SA_MSD_OVER_FRAC": "1"},
 }
 
 
@@ -136,8 +164,9 @@ def test_nonuniform_tables_match_oracle(engine, oracle, ref, name, mode, monkeyp
     codes = np.concatenate([np.asarray(sym, dtype=np.uint8), np.zeros(1, np.uint8)])
     idx = engine.SuffixArrayIndex.build(codes[:-1], sigma, isa=True, lcp=True, bwt=True, occ=True)
     st = idx.stats()
-    if "B200SA_MSD_OVER_FRAC" in MODES[mode]:
-        # OVER_FRAC = 1: nothing may fall back to the LSD path
+    if "B200SA_MSD_OVER_FRAC" in MODES[mode] and mode != "dense_keys_shallow" and name not in SPARSE_ALPHABETS:
+        # OVER_FRAC = 1: nothing may fall back to the LSD path (with dense keys an oversize bucket that shares too few
+        # symbols still does)
         assert st["round0_mode"] == 1, (name, mode, st)
     sa_exp = ref.sa(codes, sigma, "sa_is") if ref is not None else oracle.sa(codes)
     sa = idx.sa()
@@ -170,6 +199,23 @@ def test_shallow_groups_are_taken(engine):
     idx = engine.SuffixArrayIndex.build(np.asarray(sym, dtype=np.uint8), sigma)
     st2 = idx.stats()
     assert st2["round0_mode"] == 1 and st2["passes0"] >= 2, st2
+    idx.close()
+
+
+def test_dense_keys_are_taken(engine):
+    """Sparse alphabets must really get dense initial keys and stay on the bucketed round 0 -- the DNA + N text
+    with its N runs as shallow groups -- and a full alphabet must not."""
+    for name, want_shallow in (("dna_n_runs_1M", True), ("amino_copies_800k", False), ("ternary_period_600k", False)):
+        _, sym, sigma = _texts()[name]
+        idx = engine.SuffixArrayIndex.build(np.asarray(sym, dtype=np.uint8), sigma)
+        st = idx.stats()
+        assert st["round0_mode"] == 1 and st["dense_keys"] == sigma - 1, (name, st)
+        if want_shallow:
+            assert st["shallow_buckets"] >= 1, (name, st)
+        idx.close()
+    _, sym, sigma = _texts()["pair_copies_1M"]
+    idx = engine.SuffixArrayIndex.build(np.asarray(sym, dtype=np.uint8), sigma)
+    assert idx.stats()["dense_keys"] == 0
     idx.close()
 
 
