@@ -18,6 +18,7 @@
 // smallest symbol; among equal padded keys they precede every long suffix, shortest first, which
 // is strcmp order on NUL-terminated strings (stralg/suffix_array.c:26-30).
 #include "round0_msd.cuh"
+#include <vector>
 
 #include <algorithm>
 #include <cmath>
@@ -72,17 +73,29 @@ static u64 pow_u64(u64 x, int k) {
 
 // Dense keys (see DenseKey): digits are not tied to symbol boundaries, a partly used top digit is
 // accounted for when the bucket bits are chosen.
-static bool msd_make_plan_dense(u32 len, u32 nsym, int b, MsdPlan &pl) {
+static bool msd_make_plan_dense(u32 len, u32 nsym, int b, MsdPlan &pl, const u64 *sym_counts) {
     const int dmax = std::max(4, std::min(10, env_int2("B200SA_MSD_DMAX", 10)));
     const int target = std::max(1, env_int2("B200SA_MSD_AVG", 3000));
     int log2len = 0;
     while ((1ull << log2len) < (u64)len) ++log2len;
-    const double eff = std::log2((double)nsym);
+    // bits a symbol really carries: the order-0 entropy of the text when the letter counts are known (a rare
+    // letter -- N in DNA -- takes a digit value but adds next to nothing), else that of equally likely letters
+    double eff = std::log2((double)nsym);
+    if (sym_counts) {
+        double tot = 0.0, H = 0.0;
+        for (u32 a = 1; a <= nsym; ++a) tot += (double)sym_counts[a];
+        for (u32 a = 1; a <= nsym && tot > 0.0; ++a)
+            if (sym_counts[a]) {
+                const double p = (double)sym_counts[a] / tot;
+                H -= p * std::log2(p);
+            }
+        if (tot > 0.0) eff = std::min(eff, std::max(0.25, H));
+    }
     const int margin = env_int2("B200SA_KEY_MARGIN", 8);
     const int k_wanted = std::max(1, (int)std::ceil((log2len + margin) / eff));
     int best_K = 0;
     for (int pb = b; pb >= 0; pb -= b) {
-        int K = std::min(k_wanted, 64 / b - (pb ? 1 : 0));  // one 64-bit window holds prev + K symbols
+        int K = std::min(k_wanted, 128 / b - (pb ? 1 : 0));  // a 128-bit window holds prev + K symbols
         const int kf = env_int2("B200SA_MSD_K", 0);
         if (kf > 0) K = std::min(K, kf);
         for (; K >= 1; --K) {
@@ -97,7 +110,9 @@ static bool msd_make_plan_dense(u32 len, u32 nsym, int b, MsdPlan &pl) {
             if (forced > 0) BB = std::max(1, std::min(std::min(3 * dmax, KB), forced));
             const int nl = (BB + dmax - 1) / dmax;
             int D[3] = {0, 0, 0};
-            for (int i = 0; i < nl; ++i) D[i] = BB / nl + (i < BB % nl ? 1 : 0);
+            // (a wide first digit leaves the element's 32 - pb bits to a deeper key)
+            D[0] = std::min(dmax, BB);
+            for (int i = 1; i < nl; ++i) D[i] = (BB - D[0]) / (nl - 1) + (i - 1 < (BB - D[0]) % (nl - 1) ? 1 : 0);
             if (KB - D[0] > 32 - pb) continue;            // 32 + pb + (KB - D1) <= 64
             if (KB - BB > 32) continue;
             if (K <= best_K) break;                       // (the variant that carries the preceding symbol reached as deep)
@@ -124,7 +139,7 @@ static bool msd_make_plan_dense(u32 len, u32 nsym, int b, MsdPlan &pl) {
     return best_K > 0;
 }
 
-bool msd_make_plan(u32 len, u32 sigma, int bits, MsdPlan &pl) {
+bool msd_make_plan(u32 len, u32 sigma, int bits, MsdPlan &pl, const u64 *sym_counts) {
     const char *mode = getenv("B200SA_ROUND0");
     if (mode && !strcmp(mode, "lsd")) return false;
     const int b = bits;
@@ -134,7 +149,7 @@ bool msd_make_plan(u32 len, u32 sigma, int bits, MsdPlan &pl) {
         const u32 nsym = sigma > 1 ? sigma - 1 : 1;
         const int dk = env_int2("B200SA_DENSE_KEYS", -1);
         const bool sparse_alphabet = b >= 2 && nsym >= 2 && (u64)nsym * 10 <= (9ull << b);
-        if (dk != 0 && b >= 2 && nsym >= 2 && (sparse_alphabet || dk > 0) && msd_make_plan_dense(len, nsym, b, pl)) return true;
+        if (dk != 0 && b >= 2 && nsym >= 2 && (sparse_alphabet || dk > 0) && msd_make_plan_dense(len, nsym, b, pl, sym_counts)) return true;
         pl.dense = DenseKey{0, 0, 0, 0};
     }
     // Bucket bits: whole symbols (a digit never splits a symbol: with alphabets that do not fill
@@ -206,14 +221,20 @@ __global__ void __launch_bounds__(256) msd_hist_text_kernel(const u64 *__restric
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < nwords_data; w += stride) {
         u64 hi = packed[w], lo = packed[w + 1];
+        const u64 lo2 = DENSE ? packed[w + 2] : 0ull;
         u64 t0 = w * CPW;
 #pragma unroll
         for (int q = 0; q < CPW; ++q) {
             if (t0 + q <= n) {
                 const int o = q * BITS;
                 u64 win = o ? ((hi << o) | (lo >> (64 - o))) : hi;
-                if (DENSE) atomicAdd(&sh[(u32)(dense_key_of<BITS>(win, dk) >> dshift)], 1u);
-                else atomicAdd(&sh[(u32)(win >> (64 - D))], 1u);
+                if (DENSE) {
+                    const u64 win2 = o ? ((lo << o) | (lo2 >> (64 - o))) : lo;
+                    atomicAdd(&sh[(u32)(dense_key_of<BITS>(win, win2, dk) >> dshift)], 1u);
+                }
+                else {
+                    atomicAdd(&sh[(u32)(win >> (64 - D))], 1u);
+                }
             }
         }
     }
@@ -551,7 +572,7 @@ __global__ void __launch_bounds__(NT, 2) msd_partition_kernel(PartArgs a) {
 static constexpr int T1_NT = 512;
 static constexpr int T1_IPT = 16;
 static constexpr int T1_TILE = T1_NT * T1_IPT;     // 8192 suffix starts
-static constexpr int T1_STAGE_MAX = T1_TILE * 8 / 64 + 4;
+static constexpr int T1_STAGE_MAX = T1_TILE * 8 / 64 + 5;
 static constexpr size_t T1_SMEM = (size_t)T1_TILE * 8 + (size_t)MSD_MAXBINS * 4 * 2 + (size_t)T1_STAGE_MAX * 8 + 32 * 4;
 
 struct Text1Args {
@@ -575,12 +596,32 @@ __device__ __forceinline__ void stage_window(const u64 *st, u32 off, u64 &H, u64
     L = o ? (w1 << o) | (w2 >> (64 - o)) : w1;
 }
 
+// 192-bit window (H:L:M) for the dense keys, whose K symbols may take more than one word
+__device__ __forceinline__ void stage_window3(const u64 *st, u32 off, u64 &H, u64 &L, u64 &M) {
+    const u32 w = off >> 6, o = off & 63u;
+    const u64 w0 = st[w], w1 = st[w + 1], w2 = st[w + 2], w3 = st[w + 3];
+    H = o ? (w0 << o) | (w1 >> (64 - o)) : w0;
+    L = o ? (w1 << o) | (w2 >> (64 - o)) : w1;
+    M = o ? (w2 << o) | (w3 >> (64 - o)) : w2;
+}
+// the 128 bits that start at the key's first symbol, from the window of position q of a group of eight
+template <int BITS, u32 LEAD>
+__device__ __forceinline__ u64 dense_key_q(u64 H, u64 L, u64 M, int sh, const DenseKey &dk) {
+    u64 a = sh ? (H << sh) | (L >> (64 - sh)) : H;
+    u64 b = sh ? (L << sh) | (M >> (64 - sh)) : L;
+    if (LEAD) {
+        a = (a << LEAD) | (b >> (64 - LEAD));
+        b <<= LEAD;
+    }
+    return dense_key_of<BITS>(a, b, dk);
+}
+
 // BITS = symbol width, HAS_PREV = the preceding symbol is carried in the element (pb == BITS):
 // compile-time so that every per-symbol shift is an immediate.
 template <int BITS, bool HAS_PREV, int NT = T1_NT, int IPT = T1_IPT, int CTAS = 2, bool DENSE = false>
 __global__ void __launch_bounds__(NT, CTAS) msd_partition_text_kernel(Text1Args a) {
     constexpr int TILE = NT * IPT;
-    constexpr int STAGE_MAX = TILE * 8 / 64 + 4;
+    constexpr int STAGE_MAX = TILE * 8 / 64 + 5;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *buf = (u64 *)smem_raw;                   // [TILE] elements grouped by digit
     u64 *stage = buf + TILE;                   // [STAGE_MAX] packed text of the tile (one word of lead-in)
@@ -598,7 +639,7 @@ __global__ void __launch_bounds__(NT, CTAS) msd_partition_text_kernel(Text1Args 
 
     // ---- stage the tile's text: word k of `stage` is packed[begin*b/64 - 1 + k] ----
     {
-        constexpr u32 nstage = (u32)(TILE / 64) * b + 4;
+        constexpr u32 nstage = (u32)(TILE / 64) * b + 5;
         const u64 w0 = begin * (u64)b / 64;
         for (u32 k = tid; k < nstage; k += NT) {
             const u64 w = w0 + k;  // index + 1
@@ -620,8 +661,9 @@ __global__ void __launch_bounds__(NT, CTAS) msd_partition_text_kernel(Text1Args 
     u32 ds[IPT];
 #pragma unroll
     for (int g = 0; g < IPT / 8; ++g) {
-        u64 H, L;
-        stage_window(stage, off0 + (u32)(8 * g * b), H, L);
+        u64 H, L, M = 0;
+        if (DENSE) stage_window3(stage, off0 + (u32)(8 * g * b), H, L, M);
+        else stage_window(stage, off0 + (u32)(8 * g * b), H, L);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int j = 8 * g + q;
@@ -630,7 +672,7 @@ __global__ void __launch_bounds__(NT, CTAS) msd_partition_text_kernel(Text1Args 
             const u32 khi = (u32)((win << lead) >> 32);  // leading 32 bits of the key
             ds[j] = 0;
             if (i0 + j < count) {
-                const u32 d = DENSE ? (u32)(dense_key_of<BITS>(win << lead, a.dense) >> a.dshift) : khi >> dsh;
+                const u32 d = DENSE ? (u32)(dense_key_q<BITS, lead>(H, L, M, sh, a.dense) >> a.dshift) : khi >> dsh;
                 const u32 slot = atomicAdd(&hist[d], 1u);
                 ds[j] = d | (slot << 10);
             }
@@ -670,15 +712,16 @@ __global__ void __launch_bounds__(NT, CTAS) msd_partition_text_kernel(Text1Args 
     // element is two 32-bit words: [rest of key | preceding symbol] and the suffix start ----
 #pragma unroll
     for (int g = 0; g < IPT / 8; ++g) {
-        u64 H, L;
-        stage_window(stage, off0 + (u32)(8 * g * b), H, L);
+        u64 H, L, M = 0;
+        if (DENSE) stage_window3(stage, off0 + (u32)(8 * g * b), H, L, M);
+        else stage_window(stage, off0 + (u32)(8 * g * b), H, L);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int j = 8 * g + q;
             if (i0 + j < count) {
                 const int sh = q * b;
                 const u64 win = sh ? (H << sh) | (L >> (64 - sh)) : H;
-                const u32 rest = (DENSE ? (u32)dense_key_of<BITS>(win << lead, a.dense) : (u32)((win << lead) >> kshift)) & restmask;
+                const u32 rest = (DENSE ? (u32)dense_key_q<BITS, lead>(H, L, M, sh, a.dense) : (u32)((win << lead) >> kshift)) & restmask;
                 const u32 hiw = HAS_PREV ? (rest << b) | (u32)(win >> (64 - b)) : rest;
                 const u32 d = ds[j] & 1023u;
                 const u32 pos = hist[d] + (ds[j] >> 10);
@@ -1309,8 +1352,8 @@ __global__ void msd_short_buckets_kernel(const u64 *__restrict__ packed, u32 n, 
     const u32 j = threadIdx.x;
     u32 v = 0xffffffffu;
     if (j < d0 && j <= n) {
-        const u64 w = window_at(packed, (u64)(n - j), bits);
-        v = dk.nsym ? (u32)(dense_key_of_bits(w, bits, dk) >> R) : (u32)(w >> (64 - BB));
+        v = dk.nsym ? (u32)(dense_key_at(packed, (u64)(n - j), bits, dk) >> R)
+                    : (u32)(window_at(packed, (u64)(n - j), bits) >> (64 - BB));
     }
     shortb[j] = v;
 }
@@ -1502,7 +1545,7 @@ static void launch_hist_text(const DeviceIndex &ix, u64 nwords_data, int D, u32 
 
 template <int NT, int IPT>
 static constexpr size_t t1_smem() {
-    return (size_t)NT * IPT * 8 + (size_t)MSD_MAXBINS * 4 * 2 + (size_t)(NT * IPT * 8 / 64 + 4) * 8 + 32 * 4;
+    return (size_t)NT * IPT * 8 + (size_t)MSD_MAXBINS * 4 * 2 + (size_t)(NT * IPT * 8 / 64 + 5) * 8 + 32 * 4;
 }
 template <int NT, int IPT, int CTAS>
 static void launch_t1_variant(const Text1Args &ta, u32 len, cudaStream_t st) {
@@ -1587,6 +1630,7 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         KERNEL_CHECK();
         unsigned long long h[2];
         read_back(h, d_over, 16, st);
+        if (env_int2("B200SA_DEBUG_PLAN", 0)) fprintf(stderr, "[b200sa] oversize buckets: %llu with %llu suffixes\n", h[0], h[1]);
         const int more_frac = std::max(1, env_int2("B200SA_MSD_MORE_FRAC", 64));
         const int bbmax = env_int2("B200SA_MSD_BBMAX", 26);
         const int bq = pl.dense.nsym ? 1 : b;  // (dense keys: digits are not tied to symbol boundaries)
@@ -1634,6 +1678,36 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         case 2: launch_hist_text<2>(ix, nwords_data, pl.D[0], cursor[0], st, pl); break;
         case 4: launch_hist_text<4>(ix, nwords_data, pl.D[0], cursor[0], st, pl); break;
         default: launch_hist_text<8>(ix, nwords_data, pl.D[0], cursor[0], st, pl); break;
+    }
+    if (pl.dense.nsym && !env_int2("B200SA_MSD_BB", 0)) {
+        // Dense keys spread evenly when the letters are equally likely.  The level-1 histogram tells how far the text
+        // is from that (a rare letter -- N in DNA --, skewed amino-acid frequencies): with H1 bits of entropy in its
+        // D1 leading key bits, a key bit carries h = (H1 - log2 fill) / D1 bits (fill: the used part of the top
+        // digit's range), and BB bucket bits give about fill * 2^(h * BB) buckets of equal weight.  More bucket bits
+        // are planned when that is fewer than the suffixes need.
+        std::vector<u32> h1((size_t)nb[0]);
+        read_back(h1.data(), cursor[0], (size_t)nb[0] * 4, st);
+        double H1 = 0.0;
+        for (u32 c : h1)
+            if (c) {
+                const double p = (double)c / (double)len;
+                H1 -= p * std::log2(p);
+            }
+        const double lfill = std::log2((double)pow_u64(pl.dense.nsym, pl.K)) - (double)pl.KB;  // <= 0
+        const double h = std::min(1.0, std::max(0.05, (H1 - lfill) / (double)pl.D[0]));
+        const double want = std::log2(std::max(2.0, (double)len / 2000.0));
+        int BBn = (int)std::ceil((want - lfill) / h);
+        BBn = std::min(BBn, std::min(pl.D[0] + 2 * pl.dmax, pl.KB));
+        if (BBn > pl.BB) {
+            const int rem = BBn - pl.D[0], nl2 = (rem + pl.dmax - 1) / pl.dmax;
+            for (int i = 0; i < nl2; ++i) pl.D[1 + i] = rem / nl2 + (i < rem % nl2 ? 1 : 0);
+            for (int i = 1 + nl2; i < 3; ++i) pl.D[i] = 0;
+            pl.nlevels = 1 + nl2;
+            pl.BB = BBn;
+            pl.R = pl.KB - BBn;
+        }
+        if (env_int2("B200SA_DEBUG_PLAN", 0))
+            fprintf(stderr, "[b200sa] dense keys: level-1 entropy %.2f of %d bits, %.3f per key bit -> %d bucket bits\n", H1, pl.D[0], h, pl.BB);
     }
     {
         unsigned bd = std::min(1024u, std::max(32u, (unsigned)nb[0]));

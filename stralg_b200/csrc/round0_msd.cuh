@@ -19,27 +19,31 @@ __device__ __forceinline__ u64 window_at(const u64 *__restrict__ packed, u64 sym
 // 20 amino acids in 8): the key of a suffix is the NUMBER its first K symbols spell in base nsym
 // instead of the K * bits raw bits, so that keys spread evenly over their KB bits whatever the
 // alphabet -- the bucket tables and the interpolation of the in-SM sort rely on that.  The number is
-// formed as hi * powlo + lo from two 32-bit halves of Khi and Klo symbols.
+// formed as hi * powlo + lo from two 32-bit halves of Khi and Klo symbols; K symbols may take up to 128 bits of text.
 struct DenseKey {
     u32 nsym;          // 0: raw keys
     u32 Khi, Klo;      // Khi + Klo = K
     u32 powlo;         // nsym ^ Klo
 };
 template <int BITS>
-__device__ __forceinline__ u64 dense_key_of(u64 win, const DenseKey &dk) {  // win: window starting at the suffix
+__device__ __forceinline__ u64 dense_key_of(u64 w0, u64 w1, const DenseKey &dk) {  // w0:w1 = 128-bit window starting at the suffix
     u32 hi = 0, lo = 0;
     for (u32 i = 0; i < dk.Khi; ++i) {
-        hi = hi * dk.nsym + (u32)(win >> (64 - BITS));
-        win <<= BITS;
+        hi = hi * dk.nsym + (u32)(w0 >> (64 - BITS));
+        w0 = (w0 << BITS) | (w1 >> (64 - BITS));
+        w1 <<= BITS;
     }
     for (u32 i = 0; i < dk.Klo; ++i) {
-        lo = lo * dk.nsym + (u32)(win >> (64 - BITS));
-        win <<= BITS;
+        lo = lo * dk.nsym + (u32)(w0 >> (64 - BITS));
+        w0 = (w0 << BITS) | (w1 >> (64 - BITS));
+        w1 <<= BITS;
     }
     return (u64)hi * dk.powlo + lo;
 }
-__device__ __forceinline__ u64 dense_key_of_bits(u64 win, int bits, const DenseKey &dk) {
-    return bits == 2 ? dense_key_of<2>(win, dk) : bits == 4 ? dense_key_of<4>(win, dk) : dense_key_of<8>(win, dk);
+// the dense key of the suffix that starts at symbol t (the packed text is padded with zero words)
+__device__ __forceinline__ u64 dense_key_at(const u64 *__restrict__ packed, u64 t, int bits, const DenseKey &dk) {
+    const u64 w0 = window_at(packed, t, bits), w1 = window_at(packed, t + (u64)(64 / bits), bits);
+    return bits == 2 ? dense_key_of<2>(w0, w1, dk) : bits == 4 ? dense_key_of<4>(w0, w1, dk) : dense_key_of<8>(w0, w1, dk);
 }
 
 struct MsdPlan {
@@ -74,7 +78,8 @@ struct Round0Msd {
 };
 
 // Plans the levels for this text; false when the bucketed sort does not apply (e.g. disabled).
-bool msd_make_plan(u32 len, u32 sigma, int bits, MsdPlan &plan);
+// sym_counts (optional): occurrences of every code, as pack_text counted them.
+bool msd_make_plan(u32 len, u32 sigma, int bits, MsdPlan &plan, const u64 *sym_counts = nullptr);
 
 // Sorts all suffixes by their first K symbols.  Buckets that exceed what one SM sorts in shared
 // memory are emitted unsorted as shallow groups (depth0 < K); returns false (nothing usable written)

@@ -272,8 +272,8 @@ struct LazyRank {
 
 // the round-0 key of suffix t, as the bucketed round 0 formed it
 __device__ __forceinline__ u64 round0_key_at(const LazyRank &lr, u32 t) {
-    const u64 w = window_at(lr.packed, t, lr.bits);
-    return lr.dense.nsym ? dense_key_of_bits(w, lr.bits, lr.dense) : w >> (64 - lr.kb);
+    if (lr.dense.nsym) return dense_key_at(lr.packed, t, lr.bits, lr.dense);
+    return window_at(lr.packed, t, lr.bits) >> (64 - lr.kb);
 }
 
 __device__ __forceinline__ u32 lazy_rank_of(const LazyRank &lr, u32 t) {
@@ -2332,7 +2332,7 @@ static void build_sa_impl(DeviceIndex &ix, bool want_bwt) {
     u64 *rk_free[2] = {nullptr, nullptr};  // large buffers that are dead after round 0 (round keys go there)
     {
         Round0Msd r0{};
-        if (msd_make_plan(len, ix.sigma, b, r0.plan)) {
+        if (msd_make_plan(len, ix.sigma, b, r0.plan, ix.sym_counts_host)) {
             Arena::Mark mk = ar.mark();
             r0.bufA = keysA; r0.bufB = keysB; r0.actbits = actbits;
             r0.d_primary = d_primary.ptr;

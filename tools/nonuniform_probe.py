@@ -29,6 +29,21 @@ def make(kind, n):
         return T.hg38_like(n, mut_inv=64), 5, {"mut_inv": 64}
     if kind == "hg38tile256":
         return T.hg38_like(n, mut_inv=256), 5, {"mut_inv": 256}
+    if kind == "dnan":  # A C G N T: 5 % N in long runs (assembly gaps) plus a sprinkle of single N
+        t = T.random_codes(lib, n, 4, T.SEED)
+        t[:n][t[:n] == 4] = 5
+        g = torch.Generator().manual_seed(3)
+        runs = max(1, n // 10_000_000)
+        for _ in range(runs):
+            ln = int(torch.randint(1000, 1_000_000, (1,), generator=g))
+            a = int(torch.randint(0, max(1, n - ln), (1,), generator=g))
+            t[a:a + ln] = 4
+        idx = torch.randint(0, n, (max(1, n // 100000),), generator=g).to(t.device)
+        t[idx] = 4
+        return t, 6, {"N_fraction": round(float((t[:n] == 4).float().mean()), 4)}
+    if kind.startswith("uniform"):  # uniformNN: NN equiprobable letters
+        k = int(kind[7:])
+        return T.random_codes(lib, n, k, T.SEED), k + 1, {}
     t, sigma = T.stress_text(lib, kind, n)
     return t, sigma, {}
 
@@ -59,7 +74,7 @@ if __name__ == "__main__":
                    "shallow_buckets": st["shallow_buckets"], "shallow_elems": st["shallow_elems"],
                    "chain_rounds": st["chain_rounds"], "chain_elems": st["chain_elems"], "lazy": st["lazy_lookups"],
                    "resolved_small": st["resolved_small"], "small_path_elems": st["small_path_elems"],
-                   "pair_placed": st["pair_placed"],
+                   "pair_placed": st["pair_placed"], "dense_keys": st["dense_keys"],
                    "pivot_rounds": st["pivot_rounds"], "pivot_elems_x": round(st["pivot_elems"] / (n + 1), 2),
                    "sorted_total_x": round(st["sorted_total"] / (n + 1), 2),
                    "stages_ms": {k: [v[0], round(v[1], 2)] for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
