@@ -131,6 +131,7 @@ static bool msd_make_plan_dense(u32 len, u32 nsym, int b, MsdPlan &pl, const u64
             pl.dense.Klo = (u32)Klo;
             pl.dense.Khi = (u32)(K - Klo);
             pl.dense.powlo = (u32)pow_u64(nsym, Klo);
+            pl.dense.ptop = pow_u64(nsym, K - 1);
             break;
         }
         // (carrying the preceding symbol saves the BWT gather: worth a key that is a few bits short of the wish)
@@ -143,14 +144,14 @@ bool msd_make_plan(u32 len, u32 sigma, int bits, MsdPlan &pl, const u64 *sym_cou
     const char *mode = getenv("B200SA_ROUND0");
     if (mode && !strcmp(mode, "lsd")) return false;
     const int b = bits;
-    pl.dense = DenseKey{0, 0, 0, 0};
+    pl.dense = DenseKey{0, 0, 0, 0, 0};
     {
         // alphabets that use less than 9/10 of the codes of their symbol width: dense keys
         const u32 nsym = sigma > 1 ? sigma - 1 : 1;
         const int dk = env_int2("B200SA_DENSE_KEYS", -1);
         const bool sparse_alphabet = b >= 2 && nsym >= 2 && (u64)nsym * 10 <= (9ull << b);
         if (dk != 0 && b >= 2 && nsym >= 2 && (sparse_alphabet || dk > 0) && msd_make_plan_dense(len, nsym, b, pl, sym_counts)) return true;
-        pl.dense = DenseKey{0, 0, 0, 0};
+        pl.dense = DenseKey{0, 0, 0, 0, 0};
     }
     // Bucket bits: whole symbols (a digit never splits a symbol: with alphabets that do not fill
     // their b bits the leading bits of a symbol carry no information), until an average bucket
@@ -211,7 +212,7 @@ bool msd_make_plan(u32 len, u32 sigma, int bits, MsdPlan &pl, const u64 *sym_cou
 // ---------------------------------------------------------------------------------------------
 template <int BITS, bool DENSE = false>
 __global__ void __launch_bounds__(256) msd_hist_text_kernel(const u64 *__restrict__ packed, u32 n, u64 nwords_data,
-                                                            int D, u32 *__restrict__ hist, DenseKey dk = DenseKey{0, 0, 0, 0},
+                                                            int D, u32 *__restrict__ hist, DenseKey dk = DenseKey{0, 0, 0, 0, 0},
                                                             int dshift = 0) {
     constexpr int CPW = 64 / BITS;
     __shared__ u32 sh[MSD_MAXBINS];
@@ -223,18 +224,24 @@ __global__ void __launch_bounds__(256) msd_hist_text_kernel(const u64 *__restric
         u64 hi = packed[w], lo = packed[w + 1];
         const u64 lo2 = DENSE ? packed[w + 2] : 0ull;
         u64 t0 = w * CPW;
+        if (DENSE) {
+            // the keys of the word's CPW consecutive suffixes: the first one in full, the others by sliding
+            const u32 K = dk.Khi + dk.Klo;
+            u64 key = dense_key_of<BITS>(hi, lo, dk);
+#pragma unroll
+            for (int q = 0; q < CPW; ++q) {
+                if (q) key = dense_key_slide(key, sym_at192<BITS>(hi, lo, lo2, (u32)(q - 1) * BITS),
+                                             sym_at192<BITS>(hi, lo, lo2, ((u32)(q - 1) + K) * BITS), dk);
+                if (t0 + q <= n) atomicAdd(&sh[(u32)(key >> dshift)], 1u);
+            }
+            continue;
+        }
 #pragma unroll
         for (int q = 0; q < CPW; ++q) {
             if (t0 + q <= n) {
                 const int o = q * BITS;
                 u64 win = o ? ((hi << o) | (lo >> (64 - o))) : hi;
-                if (DENSE) {
-                    const u64 win2 = o ? ((lo << o) | (lo2 >> (64 - o))) : lo;
-                    atomicAdd(&sh[(u32)(dense_key_of<BITS>(win, win2, dk) >> dshift)], 1u);
-                }
-                else {
-                    atomicAdd(&sh[(u32)(win >> (64 - D))], 1u);
-                }
+                atomicAdd(&sh[(u32)(win >> (64 - D))], 1u);
             }
         }
     }
@@ -658,6 +665,8 @@ __global__ void __launch_bounds__(NT, CTAS) msd_partition_text_kernel(Text1Args 
     const u32 restmask = (u32)a.restmask;               // KB - D <= 32 bits
 
     // ---- digits and slots inside the tile's digit groups (arbitrary order: MSD) ----
+    u64 dkey = 0;
+    const u32 dK = a.dense.Khi + a.dense.Klo;
     u32 ds[IPT];
 #pragma unroll
     for (int g = 0; g < IPT / 8; ++g) {
@@ -670,9 +679,14 @@ __global__ void __launch_bounds__(NT, CTAS) msd_partition_text_kernel(Text1Args 
             const int sh = q * b;
             const u64 win = sh ? (H << sh) | (L >> (64 - sh)) : H;
             const u32 khi = (u32)((win << lead) >> 32);  // leading 32 bits of the key
+            if (DENSE) {  // the first key of the group of eight in full, the others by sliding
+                if (q == 0) dkey = dense_key_q<BITS, lead>(H, L, M, 0, a.dense);
+                else dkey = dense_key_slide(dkey, sym_at192<BITS>(H, L, M, lead + (u32)(q - 1) * BITS),
+                                            sym_at192<BITS>(H, L, M, lead + ((u32)(q - 1) + dK) * BITS), a.dense);
+            }
             ds[j] = 0;
             if (i0 + j < count) {
-                const u32 d = DENSE ? (u32)(dense_key_q<BITS, lead>(H, L, M, sh, a.dense) >> a.dshift) : khi >> dsh;
+                const u32 d = DENSE ? (u32)(dkey >> a.dshift) : khi >> dsh;
                 const u32 slot = atomicAdd(&hist[d], 1u);
                 ds[j] = d | (slot << 10);
             }
@@ -718,10 +732,15 @@ __global__ void __launch_bounds__(NT, CTAS) msd_partition_text_kernel(Text1Args 
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int j = 8 * g + q;
+            if (DENSE) {
+                if (q == 0) dkey = dense_key_q<BITS, lead>(H, L, M, 0, a.dense);
+                else dkey = dense_key_slide(dkey, sym_at192<BITS>(H, L, M, lead + (u32)(q - 1) * BITS),
+                                            sym_at192<BITS>(H, L, M, lead + ((u32)(q - 1) + dK) * BITS), a.dense);
+            }
             if (i0 + j < count) {
                 const int sh = q * b;
                 const u64 win = sh ? (H << sh) | (L >> (64 - sh)) : H;
-                const u32 rest = (DENSE ? (u32)dense_key_q<BITS, lead>(H, L, M, sh, a.dense) : (u32)((win << lead) >> kshift)) & restmask;
+                const u32 rest = (DENSE ? (u32)dkey : (u32)((win << lead) >> kshift)) & restmask;
                 const u32 hiw = HAS_PREV ? (rest << b) | (u32)(win >> (64 - b)) : rest;
                 const u32 d = ds[j] & 1023u;
                 const u32 pos = hist[d] + (ds[j] >> 10);

@@ -24,7 +24,19 @@ struct DenseKey {
     u32 nsym;          // 0: raw keys
     u32 Khi, Klo;      // Khi + Klo = K
     u32 powlo;         // nsym ^ Klo
+    u64 ptop;          // nsym ^ (K - 1): weight of the leading symbol (keys of consecutive suffixes slide)
 };
+// the symbol whose first bit is bit x of the 192-bit window H:L:M (symbols never straddle words)
+template <int BITS>
+__device__ __forceinline__ u32 sym_at192(u64 H, u64 L, u64 M, u32 x) {
+    const u32 sel = x >> 6;
+    const u64 w = sel == 0 ? H : sel == 1 ? L : M;
+    return (u32)(w >> (64 - BITS - (x & 63u))) & ((1u << BITS) - 1u);
+}
+// key of the next suffix from the key of this one: drop the leading symbol, take in the one after the last
+__device__ __forceinline__ u64 dense_key_slide(u64 key, u32 d_out, u32 d_in, const DenseKey &dk) {
+    return (key - (u64)d_out * dk.ptop) * dk.nsym + d_in;
+}
 template <int BITS>
 __device__ __forceinline__ u64 dense_key_of(u64 w0, u64 w1, const DenseKey &dk) {  // w0:w1 = 128-bit window starting at the suffix
     u32 hi = 0, lo = 0;
