@@ -11,7 +11,8 @@ N = 1  -> workload "build": SA + BWT + C + sampled O of a 3 Gbp synthetic DNA te
           inside the timed region), `cpu_baseline` (the unmodified reference on the box's host
           cores, bounded sample), and the same build on NON-UNIFORM texts, each verified with the
           suffix-array checker: `build_repeat_rich` (SURVEY 8(d) C3 repeat-rich), `build_hg38_like`
-          (the reference's genome sample tiled with mutations), `config5_stress` (BASELINE
+          (the reference's genome sample tiled with mutations), `build_dna_with_n` (ACGT with 5 % N in runs, the
+          alphabet A C G N T), `config5_stress` (BASELINE
           configs[4]: five texts at 2^30), plus `compat` (numbers through libstralg_b200.so, the
           reference's own function names).
 N > 1  -> workload "search" (BASELINE.json configs[3]): the index is replicated (every rank builds
@@ -387,7 +388,7 @@ def nonuniform_builds(args, lib, stralg_b200, torch, local_rank, stream, n):
                    "doubling_rounds": st["rounds"], "round0_mode": st["round0_mode"], "partition_levels": st["passes0"],
                    "k0": st["k0"], "shallow_buckets": st["shallow_buckets"], "chain_rounds": st["chain_rounds"],
                    "pivot_rounds": st["pivot_rounds"], "pivot_elems_over_len": st["pivot_elems"] / (nn + 1),
-                   "pair_placed": st["pair_placed"], "resolved_by_text": st["resolved_small"],
+                   "pair_placed": st["pair_placed"], "resolved_by_text": st["resolved_small"], "dense_keys": st["dense_keys"],
                    "sorted_total_over_len": st["sorted_total"] / (nn + 1), "sa_verified": ok, "checker": why,
                    "tables": "SA + BWT + C + sampled O" if occ else "SA",
                    "top_stages_ms": {k: round(v, 2) for k, v in top}}
@@ -408,8 +409,14 @@ def nonuniform_builds(args, lib, stralg_b200, torch, local_rank, stream, n):
         return T.hg38_like(n, local_rank, mut_inv=64), 5, {
             "text": "hg38-10000.fa sample (499 950 bp) tiled to n with 1/64 point mutations per copy"}
 
+    def make_dna_n():
+        t, frac = T.dna_with_n(lib, n, local_rank)
+        return t, 6, {"text": "random ACGT with 5 % N in runs of 10^3-10^6 plus single N (alphabet A C G N T: dense initial keys)",
+                      "N_fraction": round(frac, 4)}
+
     out["build_repeat_rich"] = one("repeat", make_repeat, n)
     out["build_hg38_like"] = one("hg38", make_hg38, n, reps=2)
+    out["build_dna_with_n"] = one("dna_n", make_dna_n, n, reps=2)
     n5 = min(1 << 30, n)
     stress = {}
     names = {"byte": "C5a random bytes 1..255", "unary": "C5b a^n", "acgt4": "C5c (ACGT)^(n/4)",

@@ -109,6 +109,23 @@ def hg38_like(n, device=0, mut_inv=64, seed=7, base=None):
     return text
 
 
+def dna_with_n(lib, n, device=0, seed=3):
+    """Random ACGT with N the way an assembly has it: codes A C G N T = 1 2 3 4 5 (sigma 6), about 5 % N in
+    n / 10^7 runs of 10^3 .. 10^6 symbols (gaps, centromeres) plus one single N per 10^5 symbols.  Returns the text
+    (n + 1 codes, sentinel last) and the fraction of N."""
+    import torch
+    t = random_codes(lib, n, 4, SEED, device)
+    t[:n][t[:n] == 4] = 5
+    g = torch.Generator().manual_seed(seed)
+    for _ in range(max(1, n // 10_000_000)):
+        ln = min(int(torch.randint(1000, 1_000_000, (1,), generator=g)), max(1, n // 20))
+        a = int(torch.randint(0, max(1, n - ln), (1,), generator=g))
+        t[a:a + ln] = 4
+    idx = torch.randint(0, n, (max(1, n // 100000),), generator=g).to(t.device)
+    t[idx] = 4
+    return t, float((t[:n] == 4).float().mean())
+
+
 STRESS_KINDS = ("byte", "unary", "acgt4", "period1000", "fib")
 
 

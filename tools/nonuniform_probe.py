@@ -1,7 +1,8 @@
 """Build-time probe on non-uniform texts (run under gpurun):
     python tools/nonuniform_probe.py N kind[,kind...] [check]
 kinds: random, repeat (SURVEY 8(d) C3 repeat-rich), hg38tile (genome sample tiled with 1.6 % mutations),
-       hg38tile256 (0.4 % mutations), byte, unary, acgt4, period1000, fib
+       hg38tile256 (0.4 % mutations), dnan (ACGT + 5 % N in runs), uniformNN (NN equally likely letters),
+       byte, unary, acgt4, period1000, fib
 Prints one JSON line per text: build ms, rounds, stage times; `check` verifies the suffix array with the
 checker of stralg_b200/texts.py."""
 import json
@@ -30,17 +31,8 @@ def make(kind, n):
     if kind == "hg38tile256":
         return T.hg38_like(n, mut_inv=256), 5, {"mut_inv": 256}
     if kind == "dnan":  # A C G N T: 5 % N in long runs (assembly gaps) plus a sprinkle of single N
-        t = T.random_codes(lib, n, 4, T.SEED)
-        t[:n][t[:n] == 4] = 5
-        g = torch.Generator().manual_seed(3)
-        runs = max(1, n // 10_000_000)
-        for _ in range(runs):
-            ln = int(torch.randint(1000, 1_000_000, (1,), generator=g))
-            a = int(torch.randint(0, max(1, n - ln), (1,), generator=g))
-            t[a:a + ln] = 4
-        idx = torch.randint(0, n, (max(1, n // 100000),), generator=g).to(t.device)
-        t[idx] = 4
-        return t, 6, {"N_fraction": round(float((t[:n] == 4).float().mean()), 4)}
+        t, frac = T.dna_with_n(lib, n)
+        return t, 6, {"N_fraction": round(frac, 4)}
     if kind.startswith("uniform"):  # uniformNN: NN equiprobable letters
         k = int(kind[7:])
         return T.random_codes(lib, n, k, T.SEED), k + 1, {}
