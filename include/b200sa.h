@@ -287,6 +287,11 @@ uint64_t b200sa_workspace_bytes(int device);
 int b200sa_release_workspace(int device);
 /* kernels launched by this library in this process so far (bench accounting) */
 uint64_t b200sa_launch_count(void);
+/* Diagnostic, host only (no GPU needed): the plan of the bucketed initial sort for a text of `len` = n + 1 symbols
+ * over `sigma` codes; sym_counts (256 entries, occurrences per code) may be NULL.  out[16] = {applies, levels,
+ * D1, D2, D3, bucket bits, key symbols K, key bits, bits of the preceding symbol carried, remainder bits,
+ * dense letters (0 = raw keys), Khi, Klo, nsym^Klo, symbol width, 0}.  Returns 0. */
+int b200sa_plan_round0(uint32_t len, uint32_t sigma, const uint64_t *sym_counts, uint64_t out[16]);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,7 @@ SIGNATURES = {
     "b200sa_launch_count": (C.c_uint64, []),
     "b200sa_workspace_bytes": (C.c_uint64, [C.c_int]),
     "b200sa_release_workspace": (C.c_int, [C.c_int]),
+    "b200sa_plan_round0": (C.c_int, [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "b200sa_copy_o_dense": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200sa_occ": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "b200sa_search_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64,

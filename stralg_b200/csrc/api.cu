@@ -1,6 +1,7 @@
 // api.cu -- the C ABI declared in include/b200sa.h.
 #include "../../include/b200sa.h"
 #include "engine.h"
+#include "round0_msd.cuh"
 
 #include <map>
 #include <memory>
@@ -762,6 +763,16 @@ int b200sa_copy_async(const b200sa_index *idx, int what, void *host, void *strea
     API_GUARD_END(nullptr)
 }
 uint64_t b200sa_launch_count(void) { return b200sa::g_kernel_launches; }
+int b200sa_plan_round0(uint32_t len, uint32_t sigma, const uint64_t *sym_counts, uint64_t out[16]) {
+    b200sa::MsdPlan pl{};
+    const b200sa::Packing pk = b200sa::packing_for_sigma(sigma);
+    const bool ok = b200sa::msd_make_plan(len, sigma, pk.bits, pl, sym_counts);
+    const uint64_t v[16] = {ok ? 1ull : 0ull, (uint64_t)pl.nlevels, (uint64_t)pl.D[0], (uint64_t)pl.D[1], (uint64_t)pl.D[2],
+                            (uint64_t)pl.BB, (uint64_t)pl.K, (uint64_t)pl.KB, (uint64_t)pl.pb, (uint64_t)pl.R,
+                            pl.dense.nsym, pl.dense.Khi, pl.dense.Klo, pl.dense.powlo, (uint64_t)pk.bits, 0ull};
+    for (int i = 0; i < 16; ++i) out[i] = ok || i == 14 ? v[i] : 0ull;
+    return 0;
+}
 uint64_t b200sa_workspace_bytes(int device) { return g_arena[device & 63].reserved(); }
 int b200sa_release_workspace(int device) {
     API_GUARD_BEGIN
