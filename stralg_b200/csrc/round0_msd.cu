@@ -1272,14 +1272,21 @@ __global__ void __launch_bounds__(L3_NT, L3_CTAS) msd_local_sort_kernel(L3Args a
 
 // Robust variant for the tiles the fast kernel declined: bitonic sort of (composite key, element)
 // pairs.  composite = [segment : 13 | remaining key : 32 | long : 1 | n - s for short suffixes : 8]
-static constexpr size_t RB_SMEM = (size_t)RB_N * 8 * 2 + (size_t)(L3_MASKW + 1) * 4 * 2 + 64;
+template <int RBN>
+static constexpr size_t rb_smem() {
+    return (size_t)RBN * 8 * 2 + (size_t)(L3_MASKW + 1) * 4 * 2 + (size_t)(RBN / 32 + 1) * 4 + 64;
+}
+static constexpr size_t RB_SMEM = rb_smem<RB_N>();
+static constexpr int RB_N_SMALL = 4096;            // most declined tiles fit half the network: three CTAs per SM
 
-// orders the buckets [b0, b1) (M = their elements, <= L3_CAP) and emits them; all threads of the CTA
+// orders the buckets [b0, b1) (M = their elements, <= min(L3_CAP, RBN)) and emits them; all threads of the CTA
+template <int RBN>
 __device__ void robust_sort_range(const L3Args &a, u32 b0, u32 b1, unsigned char *smem_raw) {
-    u64 *SK = (u64 *)smem_raw;            // [RB_N]
-    u64 *XV = SK + RB_N;                  // [RB_N]
-    u32 *segmask = (u32 *)(XV + RB_N);
+    u64 *SK = (u64 *)smem_raw;            // [RBN]
+    u64 *XV = SK + RBN;                   // [RBN]
+    u32 *segmask = (u32 *)(XV + RBN);
     u32 *segpre = segmask + (L3_MASKW + 1);
+    u32 *headbits = segpre + (L3_MASKW + 1);  // [RBN / 32 + 1] bit i: position i starts a run of equal composites
     uint2 *segtab = (uint2 *)XV;          // only while the composites are formed
     const u32 tid = threadIdx.x;
     const u32 E0 = a.bstart[b0], E1 = a.bstart[b1];
@@ -1324,26 +1331,42 @@ __device__ void robust_sort_range(const L3Args &a, u32 b0, u32 b1, unsigned char
             __syncthreads();
         }
     }
+    // run heads as a bitmap (a group of equal long keys may hold thousands of members: no walk back element by element)
     for (u32 i = tid; i < ((M + 31u) & ~31u); i += L3_NT) {
-        if (i < M) {
-            const u64 sk = SK[i];
-            const bool is_long = ((sk >> 8) & 1ull) != 0;
-            bool active = false;
-            u32 h = i;
-            if (is_long) {
-                active = (i > 0 && SK[i - 1] == sk) || (i + 1 < M && SK[i + 1] == sk);
-                while (h > 0 && SK[h - 1] == sk) --h;
-            }
-            l3_emit(a, E0 + i, XV[i], active, E0 + h);
+        const bool hd = i < M && (i == 0 || SK[i - 1] != SK[i]);
+        const u32 bal = __ballot_sync(0xffffffffu, hd);
+        if ((tid & 31u) == 0) headbits[i >> 5] = bal;
+    }
+    __syncthreads();
+    for (u32 i = tid; i < M; i += L3_NT) {
+        const u64 sk = SK[i];
+        const bool is_long = ((sk >> 8) & 1ull) != 0;
+        bool active = false;
+        u32 h = i;
+        if (is_long) {
+            const bool head_here = (headbits[i >> 5] >> (i & 31u)) & 1u;
+            const bool next_same = i + 1 < M && !((headbits[(i + 1) >> 5] >> ((i + 1) & 31u)) & 1u);
+            active = !head_here || next_same;
+            u32 w = i >> 5;
+            u32 m = headbits[w] & (0xffffffffu >> (31u - (i & 31u)));
+            while (!m) m = headbits[--w];  // (bit 0 of word 0 is always set)
+            h = w * 32u + 31u - (u32)__clz(m);
         }
+        l3_emit(a, E0 + i, XV[i], active, E0 + h);
     }
 }
 
-__global__ void __launch_bounds__(L3_NT, 1) msd_local_sort_robust_kernel(L3Args a) {
+// Two launches over the list of declined tiles: tiles of up to RB_N_SMALL elements with the half-size network (three
+// CTAs per SM), the others with the full one; a CTA whose tile belongs to the other launch leaves at once.
+template <int RBN, int CTAS>
+__global__ void __launch_bounds__(L3_NT, CTAS) msd_local_sort_robust_kernel(L3Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (blockIdx.x >= *a.nflagged) return;
     const u32 t = a.flagged[blockIdx.x];
-    robust_sort_range(a, a.tile_first[t], a.tile_first[t + 1], smem_raw);
+    const u32 b0 = a.tile_first[t], b1 = a.tile_first[t + 1];
+    const u32 M = a.bstart[b1] - a.bstart[b0];
+    if ((M <= (u32)RB_N_SMALL) != (RBN == RB_N_SMALL)) return;
+    robust_sort_range<RBN>(a, b0, b1, smem_raw);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1441,7 +1464,7 @@ __global__ void __launch_bounds__(L3_NT, 1) msd_bigtile_kernel(L3Args a, OverArg
             M += c2;
             ++be;
         }
-        robust_sort_range(a, bb, be, smem_raw);
+        robust_sort_range<RB_N>(a, bb, be, smem_raw);
         __syncthreads();
         bb = be;
     }
@@ -1601,7 +1624,8 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         CUDA_CHECK(cudaFuncSetAttribute(msd_partition_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_partition_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
         CUDA_CHECK(cudaFuncSetAttribute(msd_local_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L3_SMEM));
-        CUDA_CHECK(cudaFuncSetAttribute(msd_local_sort_robust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_local_sort_robust_kernel<RB_N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(msd_local_sort_robust_kernel<RB_N_SMALL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rb_smem<RB_N_SMALL>()));
         CUDA_CHECK(cudaFuncSetAttribute(msd_bigtile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
     }
 
@@ -1850,7 +1874,9 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
     u32 hmisc[8];
     read_back(hmisc, d_misc, sizeof hmisc, st);
     if (hmisc[4]) {
-        msd_local_sort_robust_kernel<<<hmisc[4], L3_NT, RB_SMEM, st>>>(la);
+        msd_local_sort_robust_kernel<RB_N_SMALL, 3><<<hmisc[4], L3_NT, rb_smem<RB_N_SMALL>(), st>>>(la);
+        KERNEL_CHECK();
+        msd_local_sort_robust_kernel<RB_N, 1><<<hmisc[4], L3_NT, RB_SMEM, st>>>(la);
         KERNEL_CHECK();
         read_back(hmisc, d_misc, sizeof hmisc, st);
     }
