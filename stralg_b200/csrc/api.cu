@@ -456,7 +456,7 @@ int b200sa_extend(b200sa_index *idx, const uint8_t *codes, uint32_t flags) {
     if (!idx || (!codes && idx->ix.n)) return fail(B200SA_ERR_BAD_ARGUMENT, "null argument", nullptr);
     DeviceIndex &ix = idx->ix;
     if (!ix.sa.ptr) return fail(B200SA_ERR_NOT_BUILT, "suffix array was dropped (B200SA_DROP_SA)", nullptr);
-    const bool need_textcmp = (flags & B200SA_BUILD_TEXTCMP) && !ix.text_packed.ptr && ix.pk.bits == 2;
+    const bool need_textcmp = (flags & B200SA_BUILD_TEXTCMP) && !ix.text_packed.ptr;
     const bool need_isa = ((flags & B200SA_BUILD_ISA) || need_textcmp) && !ix.isa.ptr;
     const bool need_lcp = (flags & B200SA_BUILD_LCP) && !ix.lcp.ptr;
     const bool need_occ = (flags & B200SA_BUILD_OCC) && ix.occ_layout == OCC_NONE;

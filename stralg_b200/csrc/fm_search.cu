@@ -20,11 +20,22 @@ struct CTable5 {
     u32 c[8];
 };
 
-template <int LAYOUT>
+struct TextCmp {
+    const u32 *sa;
+    const u32 *isa;
+    const u64 *packed;  // 2-bit symbols, big-endian inside each word (sa_build.cu pack_kernel<2>)
+};
+
+// Any alphabet (byte-wide O blocks).  SC: once a single candidate row is left, the remaining symbols are compared
+// with the packed text at SA[L] instead of one O lookup each (the recurrence would walk ISA[s-1], ISA[s-2], ... as
+// long as the symbols agree); on a difference the failing step is replayed with the O table so that (L, R) is the
+// pair the reference's loop ends with (bwt.c:186-198).
+template <int LAYOUT, bool SC = false>
 __global__ void __launch_bounds__(256) fm_search_kernel(OccView ov, CTable5 c5, const u32 *__restrict__ c_dev,
                                                         u32 len, const u8 *__restrict__ pat,
                                                         const u64 *__restrict__ off, u32 fixed_len, u64 npat,
-                                                        u32 *__restrict__ outL, u32 *__restrict__ outR) {
+                                                        u32 *__restrict__ outL, u32 *__restrict__ outR,
+                                                        TextCmp tc = TextCmp{nullptr, nullptr, nullptr}, int bits = 0) {
     __shared__ u32 c_sh[256];
     if (LAYOUT != 1) {
         for (u32 i = threadIdx.x; i < 256; i += blockDim.x) c_sh[i] = i < ov.sigma ? c_dev[i] : 0;
@@ -40,7 +51,8 @@ __global__ void __launch_bounds__(256) fm_search_kernel(OccView ov, CTable5 c5, 
         L = 1;
         R = 0;
     }
-    for (int64_t i = (int64_t)m - 1; i >= 0 && L < R; --i) {
+    int64_t i = (int64_t)m - 1;
+    for (; i >= 0 && L < R && !(SC && R - L == 1); --i) {
         u32 a = p[i];
         if (a == 0 || a >= ov.sigma) {
             L = 1;
@@ -59,6 +71,38 @@ __global__ void __launch_bounds__(256) fm_search_kernel(OccView ov, CTable5 c5, 
         }
         L = ca + oL;
         R = ca + oR;
+    }
+    if (SC && LAYOUT == 2 && i >= 0 && R - L == 1) {
+        const u32 s = tc.sa[L];
+        const u64 rem = (u64)i + 1;
+        const u32 mask = (1u << bits) - 1u;
+        const u32 lg = bits == 8 ? 3u : bits == 4 ? 4u : bits == 2 ? 5u : 6u;  // log2 of the symbols per word
+        u64 k = 0, tw = 0, tw_idx = ~0ull;
+        u32 a = 0;
+        while (k < rem) {
+            a = p[i - (int64_t)k];
+            if (k >= (u64)s) break;  // suffix 0 is preceded by the sentinel only
+            const u64 t = (u64)s - 1 - k;
+            if ((t >> lg) != tw_idx) {
+                tw_idx = t >> lg;
+                tw = tc.packed[tw_idx];
+            }
+            const u32 sym = (u32)(tw >> (64u - (u32)bits - (u32)(t & ((1u << lg) - 1u)) * (u32)bits)) & mask;
+            if (a - 1u != sym) break;
+            ++k;
+        }
+        if (k == rem) {
+            L = tc.isa[s - (u32)rem];
+            R = L + 1;
+        } else if (a == 0 || a >= ov.sigma) {
+            L = 1;
+            R = 0;
+        } else {
+            // the step that fails: BWT[Lk] != a, so both ranks coincide and the interval is empty
+            const u32 Lk = k ? tc.isa[s - (u32)k] : L;
+            L = c_sh[a] + occ_byte(ov, a, Lk);
+            R = c_sh[a] + occ_byte(ov, a, Lk + 1);
+        }
     }
     outL[q] = L;
     outR[q] = R;
@@ -111,11 +155,6 @@ __device__ __forceinline__ u32 rank_in_block(const BlockRegs &blk, u32 a, u32 i,
 }
 
 // Pointers for the unique-interval shortcut (B200SA_BUILD_TEXTCMP); all null when it is off.
-struct TextCmp {
-    const u32 *sa;
-    const u32 *isa;
-    const u64 *packed;  // 2-bit symbols, big-endian inside each word (sa_build.cu pack_kernel<2>)
-};
 
 // STATS: count the memory operations of the batch (b200sa_search_traffic, a measurement aid):
 // stats[0] 32-byte O-block loads, [1] 8-byte pattern words, [2] 8-byte text words, [3] 4-byte SA/ISA loads.
@@ -665,8 +704,14 @@ void fm_search(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fix
     }
     else if (ix.occ_layout == OCC_DNA32)
         fm_search_kernel<1><<<blocks, 256, 0, st>>>(ov, c5, ix.c_table.ptr, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R);
-    else
-        fm_search_kernel<2><<<blocks, 256, 0, st>>>(ov, c5, ix.c_table.ptr, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R);
+    else {
+        static const bool no_sc2 = getenv("B200SA_SEARCH_NO_TEXTCMP") != nullptr;
+        TextCmp tc{ix.sa.ptr, ix.isa.ptr, ix.text_packed.ptr};
+        if (tc.sa && tc.isa && tc.packed && !no_sc2)
+            fm_search_kernel<2, true><<<blocks, 256, 0, st>>>(ov, c5, ix.c_table.ptr, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R, tc, ix.pk.bits);
+        else
+            fm_search_kernel<2><<<blocks, 256, 0, st>>>(ov, c5, ix.c_table.ptr, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R);
+    }
     KERNEL_CHECK();
 }
 

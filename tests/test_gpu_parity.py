@@ -161,7 +161,10 @@ def make_patterns(rng, codes, nsym, npat, mmin, mmax):
 @pytest.mark.parametrize("textcmp,ktable", [(False, False), (True, False), (False, True), (True, True)],
                          ids=["plain", "textcmp", "ktable", "textcmp_ktable"])
 @pytest.mark.parametrize("n,nsym,mmax", [(1 << 20, 4, 24), (200000, 4, 40), (50000, 2, 30), (80000, 20, 6),
-                                         (60000, 255, 4), (3000, 1, 50), (40000, 3, 200), (5000, 4, 300)])
+                                         (60000, 255, 4), (3000, 1, 50), (40000, 3, 200), (5000, 4, 300),
+                                         # other alphabets with patterns long enough for the single-candidate text
+                                         # comparison of the generic kernel (fm_search.cu: fm_search_kernel<2, true>)
+                                         (100000, 5, 60), (80000, 20, 40), (30000, 100, 30), (20000, 6, 120)])
 def test_batched_search_and_locate(engine, oracle, n, nsym, mmax, textcmp, ktable):
     """(L, R) per pattern and the position sets against the restatement of bwt.c:164-217;
     config 1 of BASELINE.json is the first row (1 Mi random ACGT, 10 k patterns)."""
