@@ -48,9 +48,10 @@ enum b200sa_error {
 #define B200SA_BUILD_TEXTCMP 0x10u   /* keep ISA + packed text: exact search finishes a unique interval
                                         (R - L == 1) by comparing the remaining pattern symbols with the
                                         text directly instead of one O lookup per symbol; results are
-                                        identical to the plain recurrence (needs OCC, keeps SA)        */
-#define B200SA_BUILD_KTABLE 0x20u    /* DNA index (sigma <= 5): table of the (L, R) interval the recurrence of
-                                        bwt.c:185-195 reaches on every k-mer (the largest k <= 15 whose table
+                                        identical to the plain recurrence (needs OCC, keeps SA); any alphabet */
+#define B200SA_BUILD_KTABLE 0x20u    /* table of the (L, R) interval the recurrence of bwt.c:185-195 reaches on
+                                        every k-mer; other alphabets than DNA: (sigma - 1)^k entries under the
+                                        same budget, fewer than 2^32.  DNA index (sigma <= 5): the largest k <= 15 whose table
                                         stays under 3 bytes per text symbol: 15 at 3 Gbp; with TEXTCMP, which
                                         keeps 8 bytes per symbol anyway, k <= 16 under 12 bytes: 16, 34 GB, at
                                         3 Gbp; B200SA_KTABLE_K overrides); exact search starts from the entry of the pattern's last k

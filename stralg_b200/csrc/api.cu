@@ -461,8 +461,7 @@ int b200sa_extend(b200sa_index *idx, const uint8_t *codes, uint32_t flags) {
     const bool need_lcp = (flags & B200SA_BUILD_LCP) && !ix.lcp.ptr;
     const bool need_occ = (flags & B200SA_BUILD_OCC) && ix.occ_layout == OCC_NONE;
     const bool need_bwt = ((flags & B200SA_BUILD_BWT) && !ix.bwt.ptr) || need_occ;
-    const bool need_ktable = (flags & B200SA_BUILD_KTABLE) && !ix.ktable.ptr && ix.sigma <= 5 &&
-                             (need_occ || ix.occ_layout == OCC_DNA32);
+    const bool need_ktable = (flags & B200SA_BUILD_KTABLE) && !ix.ktable.ptr && (need_occ || ix.occ_layout != OCC_NONE);
     if (!need_isa && !need_lcp && !need_bwt && !need_textcmp && !need_ktable) return 0;
     mail_server_release(idx);  // (the resident one-pattern search was launched with the tables as they were)
     API_GUARD_BEGIN
@@ -1438,7 +1437,7 @@ b200sa_index *b200sa_load(const char *path, int device, void *stream, enum b200s
             if (fh.occ_layout == 2) good = good && fh.sigma > 5 && fh.occ_block_bytes == hdr_words * 4 + 64;
             if (fh.occ_layout != 0) good = good && fh.occ_blocks == blocks;
             if (fh.occ_layout == 0) good = good && fh.occ_blocks == 0;
-            good = good && fh.ktable_k <= 16 && (fh.ktable_k == 0 || fh.occ_layout == 1);
+            good = good && fh.ktable_k <= 16 && (fh.ktable_k == 0 || fh.occ_layout == 1 || fh.occ_layout == 2);
             if (!good) throw std::invalid_argument("index file header is inconsistent (O-table layout / k-mer table)");
         }
         DeviceIndex &ix = h->ix;
@@ -1477,7 +1476,15 @@ b200sa_index *b200sa_load(const char *path, int device, void *stream, enum b200s
                 read_section(f, sh, ix.occ, (size_t)fh.occ_blocks * fh.occ_block_bytes, buf, st);
                 have_occ = true;
             } else if (tag == "TEXT") read_section(f, sh, ix.text_packed, words, buf, st);
-            else if (tag == "KTABLE") read_section(f, sh, ix.ktable, (size_t)1 << (2 * fh.ktable_k), buf, st);
+            else if (tag == "KTABLE") {
+                // 4^k entries over 2-bit symbols, (sigma - 1)^k over any other alphabet
+                size_t entries = (size_t)1 << (2 * fh.ktable_k);
+                if (fh.occ_layout == 2) {
+                    entries = 1;
+                    for (uint32_t j = 0; j < fh.ktable_k; ++j) entries *= (size_t)(fh.sigma - 1);
+                }
+                read_section(f, sh, ix.ktable, entries, buf, st);
+            }
             else if (tag == "SSAMARK") {
                 read_section(f, sh, ix.ssa_marks, ((size_t)ix.len + 63) / 64, buf, st);
                 have_marks = true;

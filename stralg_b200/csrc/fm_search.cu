@@ -26,16 +26,23 @@ struct TextCmp {
     const u64 *packed;  // 2-bit symbols, big-endian inside each word (sa_build.cu pack_kernel<2>)
 };
 
+struct KTable {
+    const uint2 *tab;
+    int k;
+    u32 nsym;  // 0: 2-bit symbols (entry index = the k symbols as a 2k-bit number); else the index is their base-nsym number
+};
+
 // Any alphabet (byte-wide O blocks).  SC: once a single candidate row is left, the remaining symbols are compared
 // with the packed text at SA[L] instead of one O lookup each (the recurrence would walk ISA[s-1], ISA[s-2], ... as
 // long as the symbols agree); on a difference the failing step is replayed with the O table so that (L, R) is the
 // pair the reference's loop ends with (bwt.c:186-198).
-template <int LAYOUT, bool SC = false>
+template <int LAYOUT, bool SC = false, bool AL = false>
 __global__ void __launch_bounds__(256) fm_search_kernel(OccView ov, CTable5 c5, const u32 *__restrict__ c_dev,
                                                         u32 len, const u8 *__restrict__ pat,
                                                         const u64 *__restrict__ off, u32 fixed_len, u64 npat,
                                                         u32 *__restrict__ outL, u32 *__restrict__ outR,
-                                                        TextCmp tc = TextCmp{nullptr, nullptr, nullptr}, int bits = 0) {
+                                                        TextCmp tc = TextCmp{nullptr, nullptr, nullptr}, int bits = 0,
+                                                        KTable kt = KTable{nullptr, 0, 0}) {
     __shared__ u32 c_sh[256];
     if (LAYOUT != 1) {
         for (u32 i = threadIdx.x; i < 256; i += blockDim.x) c_sh[i] = i < ov.sigma ? c_dev[i] : 0;
@@ -45,15 +52,46 @@ __global__ void __launch_bounds__(256) fm_search_kernel(OccView ov, CTable5 c5, 
     if (q >= npat) return;
     u64 begin = off ? off[q] : q * (u64)fixed_len;
     u64 m = off ? off[q + 1] - begin : (u64)fixed_len;
-    const u8 *p = pat + begin;
+    // AL: the pattern buffer is 8-byte aligned and readable up to the next 8-byte boundary (as for the DNA path): symbols
+    // come from an aligned word fetched once per eight of them instead of a byte load each -- the lanes of a warp read
+    // different patterns, so byte loads cost a sector apiece
+    u64 pword = 0, pword_addr = ~0ull;
+    auto P = [&](int64_t idx) -> u32 {
+        const u64 addr = begin + (u64)idx;
+        if (AL) {
+            if ((addr & ~7ull) != pword_addr) {
+                pword_addr = addr & ~7ull;
+                pword = *(const u64 *)(pat + pword_addr);
+            }
+            return (u32)(pword >> (8 * (addr & 7))) & 0xffu;
+        }
+        return pat[addr];
+    };
     u32 L = 0, R = len;
     if (m > (u64)len) {
         L = 1;
         R = 0;
     }
     int64_t i = (int64_t)m - 1;
+    if (LAYOUT == 2 && kt.tab && m >= (u64)kt.k && L < R) {
+        // the last k symbols select the interval the first k steps would reach (an entry with L >= R is the pair at
+        // the step that emptied the interval); a byte outside 1..nsym takes the stepwise path
+        u32 x = 0;
+        bool valid = true;
+        for (int j = 0; j < kt.k; ++j) {
+            const u32 a = P(i - j);
+            valid = valid && (a - 1u < kt.nsym);
+            x = x * kt.nsym + (a - 1u);
+        }
+        if (valid) {
+            const uint2 lr = kt.tab[x];
+            L = lr.x;
+            R = lr.y;
+            i -= kt.k;
+        }
+    }
     for (; i >= 0 && L < R && !(SC && R - L == 1); --i) {
-        u32 a = p[i];
+        u32 a = P(i);
         if (a == 0 || a >= ov.sigma) {
             L = 1;
             R = 0;
@@ -80,7 +118,7 @@ __global__ void __launch_bounds__(256) fm_search_kernel(OccView ov, CTable5 c5, 
         u64 k = 0, tw = 0, tw_idx = ~0ull;
         u32 a = 0;
         while (k < rem) {
-            a = p[i - (int64_t)k];
+            a = P(i - (int64_t)k);
             if (k >= (u64)s) break;  // suffix 0 is preceded by the sentinel only
             const u64 t = (u64)s - 1 - k;
             if ((t >> lg) != tw_idx) {
@@ -162,10 +200,6 @@ __device__ __forceinline__ u32 rank_in_block(const BlockRegs &blk, u32 a, u32 i,
 // whose symbols, in the order the recurrence consumes them (last pattern symbol first), are the
 // base-4 digits of x, most significant first; an entry with L >= R is the interval at the step
 // that emptied it, i.e. the final answer of every pattern ending in that k-mer.
-struct KTable {
-    const uint2 *tab;
-    int k;
-};
 
 __global__ void __launch_bounds__(256) ktable_build_kernel(OccView ov, CTable5 c5, u32 len, int k, u64 entries,
                                                            uint2 *__restrict__ tab) {
@@ -707,10 +741,16 @@ void fm_search(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fix
     else {
         static const bool no_sc2 = getenv("B200SA_SEARCH_NO_TEXTCMP") != nullptr;
         TextCmp tc{ix.sa.ptr, ix.isa.ptr, ix.text_packed.ptr};
-        if (tc.sa && tc.isa && tc.packed && !no_sc2)
-            fm_search_kernel<2, true><<<blocks, 256, 0, st>>>(ov, c5, ix.c_table.ptr, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R, tc, ix.pk.bits);
-        else
-            fm_search_kernel<2><<<blocks, 256, 0, st>>>(ov, c5, ix.c_table.ptr, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R);
+        static const bool no_kt2 = getenv("B200SA_SEARCH_NO_KTABLE") != nullptr;
+        KTable kt{no_kt2 ? nullptr : ix.ktable.ptr, ix.ktable_k, ix.sigma - 1};
+        const bool al = (((uintptr_t)d_pat) & 7) == 0 && !force_generic;
+        const bool sc2 = tc.sa && tc.isa && tc.packed && !no_sc2;
+#define LAUNCH_GEN(SC_, AL_) fm_search_kernel<2, SC_, AL_><<<blocks, 256, 0, st>>>(ov, c5, ix.c_table.ptr, ix.len, d_pat, d_off, fixed_len, npat, d_L, d_R, tc, ix.pk.bits, kt)
+        if (sc2 && al) LAUNCH_GEN(true, true);
+        else if (sc2) LAUNCH_GEN(true, false);
+        else if (al) LAUNCH_GEN(false, true);
+        else LAUNCH_GEN(false, false);
+#undef LAUNCH_GEN
     }
     KERNEL_CHECK();
 }
@@ -721,7 +761,58 @@ void fm_search(const DeviceIndex &ix, const u8 *d_pat, const u64 *d_off, u32 fix
 // k = 16, 34 GB, at 3 Gbp.  Once the search kernel had become DRAM-bound every extra symbol of k paid (3 Gbp, 10^8
 // reads of 100 bp, byte kernel: k = 12: 23.6 ms, 13: 20.5, 14: 17.7, 15: 15.7; packed kernel: 15: 13.5, 16: 11.5) --
 // each one removes random O-block fetches from every read.
+// the same over any alphabet: entry x = the k symbols as a base-nsym number, first processed symbol most significant
+__global__ void __launch_bounds__(256) ktable_build_generic_kernel(OccView ov, const u32 *__restrict__ c_dev, u32 len, int k,
+                                                                   u32 nsym, u32 ptop, u64 entries, uint2 *__restrict__ tab) {
+    const u64 x64 = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x64 >= entries) return;
+    u32 x = (u32)x64, pw = ptop;  // ptop = nsym^(k-1); entries < 2^32
+    u32 L = 0, R = len;
+    for (int j = 0; j < k && L < R; ++j) {
+        const u32 a = x / pw + 1u;
+        x %= pw;
+        pw /= nsym;
+        const u32 ca = c_dev[a];
+        L = ca + occ_byte(ov, a, L);
+        R = ca + occ_byte(ov, a, R);
+    }
+    tab[x64] = make_uint2(L, R);
+}
+
+static void build_ktable_generic(DeviceIndex &ix) {
+    const u32 nsym = ix.sigma - 1;
+    if (nsym < 2) return;
+    const bool rich = ix.text_packed.ptr && ix.isa.ptr && ix.sa.ptr;
+    const u64 budget = (rich ? 12ull : 3ull) * (u64)ix.len / 8;  // entries
+    int k = 0;
+    u64 entries = 1;
+    while (k < 16 && entries * nsym <= budget && entries * nsym <= 2 * (u64)ix.len && entries * nsym < (1ull << 32)) {
+        entries *= nsym;
+        ++k;
+    }
+    if (const char *e = getenv("B200SA_KTABLE_K")) {
+        const int want = std::max(1, std::min(16, atoi(e)));
+        while (k > want) {
+            entries /= nsym;
+            --k;
+        }
+    }
+    if (k < 2) return;
+    ix.ktable.alloc(entries, ix.stream);
+    ix.ktable_k = k;
+    OccView ov = occ_view(ix);
+    int t = ix.timer.begin("ktable", (double)entries * 8.0);
+    ktable_build_generic_kernel<<<div_up_u(entries, 256), 256, 0, ix.stream>>>(ov, ix.c_table.ptr, ix.len, k, nsym,
+                                                                             (u32)(entries / nsym), entries, ix.ktable.ptr);
+    KERNEL_CHECK();
+    ix.timer.end(t);
+}
+
 void build_ktable(DeviceIndex &ix) {
+    if (ix.occ_layout == OCC_BYTE) {
+        build_ktable_generic(ix);
+        return;
+    }
     if (ix.occ_layout != OCC_DNA32) return;
     const bool rich = ix.text_packed.ptr && ix.isa.ptr && ix.sa.ptr;
     int k = rich ? 16 : 15;

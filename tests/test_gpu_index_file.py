@@ -12,6 +12,8 @@ pytestmark = pytest.mark.gpu
     (300000, 4, dict(isa=True, lcp=True, bwt=True, textcmp=True, ktable=True)),
     (70001, 4, dict()),
     (50000, 20, dict(bwt=True, lcp=True)),
+    (90000, 5, dict(isa=True, bwt=True, textcmp=True, ktable=True)),   # A C G N T: base-5 seed table, text comparison
+    (60000, 20, dict(ktable=True)),
     (1, 4, dict(isa=True)),
 ])
 def test_save_load_round_trip(engine, oracle, tmp_path, n, nsym, kw):

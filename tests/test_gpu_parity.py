@@ -183,6 +183,8 @@ def test_batched_search_and_locate(engine, oracle, n, nsym, mmax, textcmp, ktabl
         if hi - lo >= 2 and k % 2:
             j = lo + int(rng.integers(0, hi - lo))
             pat[j] = 1 + (pat[j] % nsym)
+    if ktable and n >= 20000 and nsym <= 20:
+        assert idx.stats()["ktable_k"] >= 2, idx.stats()  # (every alphabet whose k-mers fit the budget has a seed table)
     L, R = idx.search(pat, off)
     Le, Re = oracle.search_ck(c, bwt, ck, 64, pat, off, threads=4)
     assert np.array_equal(L, Le) and np.array_equal(R, Re)

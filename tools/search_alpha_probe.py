@@ -9,7 +9,8 @@ from nonuniform_probe import make
 n = int(float(sys.argv[1])); nreads = int(float(sys.argv[2])); kind = sys.argv[3]; m = 100
 text, sigma, info = make(kind, n)
 tcmp = os.environ.get('PROBE_TEXTCMP', '1') == '1'
-idx = stralg_b200.SuffixArrayIndex.build(text[:n], sigma, occ=True, textcmp=tcmp)
+ktab = os.environ.get('PROBE_KTABLE', '1') == '1'
+idx = stralg_b200.SuffixArrayIndex.build(text[:n], sigma, occ=True, textcmp=tcmp, ktable=ktab)
 g = torch.Generator(device="cuda"); g.manual_seed(1)
 starts = torch.randint(0, n - m, (nreads,), generator=g, device="cuda")
 reads = text[(starts[:, None] + torch.arange(m, device="cuda")[None, :])].contiguous()
@@ -26,4 +27,4 @@ for _ in range(3):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
 found = int(((R.long() & 0xffffffff) > (L.long() & 0xffffffff)).sum())
-print({"kind": kind, "n": n, "sigma": sigma, "reads": nreads, "ms": round(ms, 2), "Mreads_s": round(nreads / ms / 1e3, 1), "found": found, "occ_layout": idx.stats()["occ_layout"], "textcmp": tcmp})
+print({"kind": kind, "n": n, "sigma": sigma, "reads": nreads, "ms": round(ms, 2), "Mreads_s": round(nreads / ms / 1e3, 1), "found": found, "occ_layout": idx.stats()["occ_layout"], "textcmp": tcmp, "ktable_k": idx.stats()["ktable_k"]})
