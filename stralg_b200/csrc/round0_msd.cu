@@ -1741,6 +1741,13 @@ bool round0_msd(DeviceIndex &ix, bool want_bwt, Round0Msd &r) {
         const double want = std::log2(std::max(2.0, (double)len / 2000.0));
         int BBn = (int)std::ceil((want - lfill) / h);
         BBn = std::min(BBn, std::min(pl.D[0] + 2 * pl.dmax, pl.KB));
+        {
+            // (never more than one bucket per 64 suffixes: a text of one letter has no entropy to plan with, and its
+            // tables must not outgrow it)
+            int log2len = 0;
+            while ((1ull << log2len) < (u64)len) ++log2len;
+            BBn = std::min(BBn, std::max(pl.BB, log2len - 6));
+        }
         if (BBn > pl.BB) {
             const int rem = BBn - pl.D[0], nl2 = (rem + pl.dmax - 1) / pl.dmax;
             for (int i = 0; i < nl2; ++i) pl.D[1 + i] = rem / nl2 + (i < rem % nl2 ? 1 : 0);
