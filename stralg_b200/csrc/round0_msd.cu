@@ -17,7 +17,13 @@
 // Suffixes whose K-window reaches the sentinel ("short", at most K of them) are padded with the
 // smallest symbol; among equal padded keys they precede every long suffix, shortest first, which
 // is strcmp order on NUL-terminated strings (stralg/suffix_array.c:26-30).
+//
+// The key is the K raw symbol fields of the packed text, or, for alphabets that leave most codes of
+// a symbol field unused (DNA with N, amino acids), the base-nsym number the K symbols spell (DenseKey,
+// round0_msd.cuh): any monotone, injective map of K-symbol prefixes serves, and only the level-1
+// kernels that read the text know which one is in use.
 #include "round0_msd.cuh"
+
 #include <vector>
 
 #include <algorithm>
