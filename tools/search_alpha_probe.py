@@ -14,6 +14,16 @@ idx = stralg_b200.SuffixArrayIndex.build(text[:n], sigma, occ=True, textcmp=tcmp
 g = torch.Generator(device="cuda"); g.manual_seed(1)
 starts = torch.randint(0, n - m, (nreads,), generator=g, device="cuda")
 reads = text[(starts[:, None] + torch.arange(m, device="cuda")[None, :])].contiguous()
+if kind == "dnan" and os.environ.get("PROBE_READS_WITH_N", "0") != "1":
+    # a sequencer does not read assembly gaps: reads that hold an N are drawn again (PROBE_READS_WITH_N=1 keeps them;
+    # an all-N read never narrows its interval and holds its whole warp for 100 steps)
+    for _ in range(8):
+        bad = (reads == 4).any(dim=1)
+        nb = int(bad.sum())
+        if not nb:
+            break
+        st2 = torch.randint(0, n - m, (nb,), generator=g, device="cuda")
+        reads[bad] = text[(st2[:, None] + torch.arange(m, device="cuda")[None, :])]
 miss = torch.arange(nreads, device="cuda") % 10 == 0
 reads[miss] = torch.randint(1, sigma, (int(miss.sum()), m), generator=g, device="cuda", dtype=torch.int16).to(torch.uint8)
 L = torch.empty(nreads, dtype=torch.int32, device="cuda"); R = torch.empty_like(L)
