@@ -76,11 +76,21 @@ def make(kind, n, nsym):
         for s in range(0, 32):
             par ^= (i >> s) & 1
         return torch.where(par == 0, torch.tensor(a, device=dev), torch.tensor(b, device=dev)).to(torch.uint8), "thue-morse"
+    if kind == 5:   # one rare letter, in runs and sprinkled (N in DNA): the keys of a sparse alphabet must stay even
+        t = rand_sym(n, max(1, nsym - 1))
+        rare = nsym
+        for _ in range(ri(0, 6)):
+            ln = ri(1, max(2, n // 40))
+            a0 = ri(0, max(1, n - ln))
+            t[a0:a0 + ln] = rare
+        idx = torch.randint(0, n, (max(1, n // ri(50, 100000)),), generator=g, device=dev)
+        t[idx] = rare
+        return t, "rare letter"
     # concatenation of differently structured parts
     parts, left, names = [], n, []
     while left > 0:
         ln = min(left, ri(1, max(2, n // 2)))
-        p, nm = make(ri(0, 5), ln, nsym)
+        p, nm = make(ri(0, 6), ln, nsym)
         parts.append(p[:ln])
         names.append(nm)
         left -= ln
@@ -93,8 +103,8 @@ t_end = time.time() + seconds
 cases = 0
 while time.time() < t_end:
     n = ri(1 << 20, 1 << ri(21, maxlog + 1))
-    nsym = [1, 2, 2, 3, 4, 4, 4, 4, 5, 15, 16, 20, 100, 255][ri(0, 14)]
-    text, name = make(ri(0, 6), n, nsym)
+    nsym = [1, 2, 2, 3, 4, 4, 4, 5, 5, 6, 15, 16, 20, 100, 255][ri(0, 15)]
+    text, name = make(ri(0, 7), n, nsym)
     n = text.numel()
     knobs = {}
     r = ri(0, 10)
